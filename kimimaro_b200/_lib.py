@@ -1,0 +1,75 @@
+"""
+ctypes binding of libb2t.so (include/b2t.h).  Fails loudly: no library or no sm_100 device means
+an exception, never a CPU fallback.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb2t.so")
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_f32 = ctypes.c_float
+c_vp = ctypes.c_void_p
+c_sz = ctypes.c_size_t
+
+_lib = None
+
+
+class B2TError(RuntimeError):
+  pass
+
+
+# name -> argtypes; every function returns int status unless listed in _RESTYPES
+_SIGNATURES = {
+  "b2t_version": [],
+  "b2t_last_error": [],
+  "b2t_device_check": [],
+  "b2t_edt": [c_vp, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_vp, c_vp],
+}
+_RESTYPES = {"b2t_last_error": ctypes.c_char_p}
+
+
+def declare(name, argtypes, restype=None):
+  """Used by the op modules to register further entry points of include/b2t.h."""
+  _SIGNATURES[name] = argtypes
+  if restype is not None:
+    _RESTYPES[name] = restype
+  if _lib is not None:
+    fn = getattr(_lib, name)
+    fn.argtypes = argtypes
+    fn.restype = _RESTYPES.get(name, c_int)
+
+
+def lib():
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise B2TError(
+        f"{LIB_PATH} is missing: build it with `python -m kimimaro_b200.build` "
+        "(kimimaro_b200 has no CPU fallback)")
+    _lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+      fn = getattr(_lib, name)
+      fn.argtypes = argtypes
+      fn.restype = _RESTYPES.get(name, c_int)
+  return _lib
+
+
+def check(status, what=""):
+  if status != 0:
+    msg = lib().b2t_last_error()
+    raise B2TError(f"{what} failed with status {status}: {msg.decode() if msg else ''}")
+
+
+def require_device():
+  import torch
+  if not torch.cuda.is_available():
+    raise B2TError("kimimaro_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+  check(lib().b2t_device_check(), "b2t_device_check")
+
+
+def stream_ptr():
+  import torch
+  return c_vp(torch.cuda.current_stream().cuda_stream)

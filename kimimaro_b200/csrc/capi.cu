@@ -1,0 +1,39 @@
+// Library-level entry points of libb2t.so: version, error string, device check.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void b2t_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+B2T_EXPORT int b2t_version(void) { return 100; }
+
+B2T_EXPORT const char* b2t_last_error(void) { return g_err; }
+
+B2T_EXPORT int b2t_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    b2t_set_error("no CUDA device: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return B2T_ERR_DEVICE;
+  }
+  cudaDeviceProp p;
+  e = cudaGetDeviceProperties(&p, dev);
+  if (e != cudaSuccess) {
+    b2t_set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return B2T_ERR_DEVICE;
+  }
+  if (p.major != 10) {
+    b2t_set_error("libb2t.so is built for sm_100a only; device %d is sm_%d%d (%s)", dev, p.major, p.minor, p.name);
+    return B2T_ERR_DEVICE;
+  }
+  return B2T_OK;
+}

@@ -1,0 +1,36 @@
+// Shared helpers for libb2t.so (sm_100a only).  Not a public header: the C ABI is include/b2t.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b2t.h"
+
+#define B2T_EXPORT extern "C" __attribute__((visibility("default")))
+
+void b2t_set_error(const char* fmt, ...);
+
+#define B2T_CUDA_TRY(expr)                                                                  \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      b2t_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      return B2T_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+#define B2T_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      b2t_set_error(__VA_ARGS__);              \
+      return B2T_ERR_ARG;                      \
+    }                                          \
+  } while (0)
+
+// 26-neighbourhood in the enumeration order the reference uses
+// (ext/skeletontricks/dijkstra_invalidation.hpp:60-124): -x,+x,-y,+y,-z,+z, xy, yz, xz diagonals, corners.
+__device__ __constant__ static const int8_t kDX[26] = {-1, 1, 0, 0, 0, 0, -1, -1, 1, 1, 0, 0, 0, 0, -1, -1, 1, 1, -1, 1, -1, -1, 1, 1, -1, 1};
+__device__ __constant__ static const int8_t kDY[26] = {0, 0, -1, 1, 0, 0, -1, 1, -1, 1, -1, -1, 1, 1, 0, 0, 0, 0, -1, -1, 1, -1, 1, -1, 1, 1};
+__device__ __constant__ static const int8_t kDZ[26] = {0, 0, 0, 0, -1, 1, 0, 0, 0, 0, -1, 1, -1, 1, -1, 1, -1, 1, -1, -1, -1, 1, -1, 1, 1, 1};
+
+static inline int b2t_ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
