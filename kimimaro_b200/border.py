@@ -1,0 +1,121 @@
+"""
+Host-side restatement of the reference's fix_borders target selection:
+
+  kimimaro/intake.py:544-585                    compute_border_targets (six faces)
+  ext/skeletontricks/skeletontricks.pyx:591-648 find_border_targets
+  ext/skeletontricks/skeletontricks.pyx:528-588 compute_centroids
+  ext/skeletontricks/skeletontricks.pyx:650-760 compute_tiebreaker_maxima, edgeness, cornerness, distsq
+
+The 2-D connected components and the 2-D EDT of each face run on the device (b2t_ccl26_roots with
+sz=1, b2t_edt with ndim=2); what is left is O(face) bookkeeping with the reference's float32 /
+float64 expression order, done here in numpy on the six faces (6 * 512^2 voxels for config 3).
+Python `set` / `list(set)` containers are kept so that the order in which a label's border targets
+are handed to trace() -- and therefore which one becomes the root (intake.py:484-486) -- is inherited
+from CPython exactly like the reference inherits it.
+"""
+import numpy as np
+
+f32 = np.float32
+
+
+def _distsq(p1x, p1y, p2x, p2y, wx, wy):
+  a = f32(wx * f32(p1x - p2x))
+  b = f32(wy * f32(p1y - p2y))
+  return f32(f32(a * a) + f32(b * b))
+
+
+def _cornerness(x, y, sx, sy, wx, wy):
+  h = f32(0.5)
+  # fourth corner uses sx for its y coordinate, as the reference does (pyx:747)
+  return min(_distsq(x, y, -h, -h, wx, wy), _distsq(x, y, f32(sx - h), -h, wx, wy),
+             _distsq(x, y, f32(sx - h), f32(sy - h), wx, wy), _distsq(x, y, -h, f32(sx - h), wx, wy))
+
+
+def _edgeness(x, y, sx, sy, wx, wy):
+  # evaluated in double (the literal 0.5 is a C double, pyx:725-730), rounded to float on return
+  x, y, sx, sy, wx, wy = (float(v) for v in (x, y, sx, sy, wx, wy))
+  return f32(min(wx * (x - 0.5), wx * (sx - 0.5 - x), wy * (y - 0.5), wy * (sy - 0.5 - y)))
+
+
+def tiebreak(px, py, x, y, centx, centy, sx, sy, wx, wy):
+  """compute_tiebreaker_maxima (pyx:650-715): closest to the label centroid, then to the plane
+  centre, then to a corner, then to an edge, else the previous maximum."""
+  px, py, x, y, centx, centy, sx, sy, wx, wy = (f32(v) for v in (px, py, x, y, centx, centy, sx, sy, wx, wy))
+  cx = f32(f32(wx * sx) / f32(2.0))
+  cy = f32(f32(wy * sy) / f32(2.0))
+  for fn in (lambda a, b: _distsq(a, b, centx, centy, wx, wy),
+             lambda a, b: _distsq(a, b, cx, cy, wx, wy),
+             lambda a, b: _cornerness(a, b, sx, sy, wx, wy),
+             lambda a, b: _edgeness(a, b, sx, sy, wx, wy)):
+    d1, d2 = fn(px, py), fn(x, y)
+    if d2 < d1:
+      return (x, y)
+    if d1 != d2:
+      return (px, py)
+  return (px, py)
+
+
+def centroid(cc_plane, label, wx, wy):
+  """compute_centroids (pyx:528-588) for one label: float32 running sums, x outer / y inner."""
+  wx, wy = f32(wx), f32(wy)
+  sx, sy = cc_plane.shape
+  xs, ys = np.nonzero(cc_plane == label)          # C-order traversal == x outer, y inner
+  xsum = np.add.accumulate(xs.astype(np.float32), dtype=np.float32)[-1]
+  ysum = np.add.accumulate(ys.astype(np.float32), dtype=np.float32)[-1]
+  ct = f32(xs.size)
+  cx = f32(f32(wx * f32(sx)) / f32(2))
+  cy = f32(f32(wy * f32(sy)) / f32(2))
+  px = f32(f32(wx * xsum) / ct)
+  py = f32(f32(wy * ysum) / ct)
+  if not (f32(px - cx) >= 0):
+    px = f32(px + wx)
+  if not (f32(py - cy) >= 0):
+    py = f32(py + wy)
+  return (int(f32(px / wx)), int(f32(py / wy)))
+
+
+def find_border_targets(dt, cc_plane, wx, wy):
+  """find_border_targets (pyx:591-648): {plane label: (x, y) of its DT maximum}, keys in the order the
+  raster scan (y outer, x inner) first meets each label on a voxel with non-zero DT."""
+  sx, sy = dt.shape
+  fdt = np.asarray(dt).reshape(-1, order="F")
+  fcc = np.asarray(cc_plane).reshape(-1, order="F")
+  sel = np.flatnonzero((fcc != 0) & (fdt != 0))
+  pts = {}
+  if sel.size == 0:
+    return pts
+  labs = fcc[sel].astype(np.int64)
+  vals = fdt[sel]
+  nlab = int(labs.max()) + 1
+  mx = np.zeros(nlab, dtype=vals.dtype)
+  np.maximum.at(mx, labs, vals)
+  is_max = vals == mx[labs]
+  cand_idx = sel[is_max]                       # raster order is preserved
+  cand_lab = labs[is_max]
+  uniq, first_pos = np.unique(labs, return_index=True)
+  for l in uniq[np.argsort(first_pos)].tolist():  # dict insertion order = first encounter (B.6)
+    pts[l] = None
+  order = np.argsort(cand_lab, kind="stable")
+  cl, ci = cand_lab[order], cand_idx[order]
+  bounds = np.flatnonzero(np.diff(cl)) + 1
+  starts = np.concatenate(([0], bounds))
+  ends = np.concatenate((bounds, [cl.size]))
+  for a, b in zip(starts.tolist(), ends.tolist()):
+    l = int(cl[a])
+    i0 = int(ci[a])
+    cur = (i0 % sx, i0 // sx)
+    if b - a > 1:
+      cxy = centroid(cc_plane, l, wx, wy)
+      for i in ci[a + 1:b].tolist():
+        r = tiebreak(cur[0], cur[1], i % sx, i // sx, cxy[0], cxy[1], sx, sy, wx, wy)
+        cur = (r[0], r[1])
+    pts[l] = cur
+  return pts
+
+
+def plane_mapping(plane, cc_plane):
+  """get_mapping (pyx:490-525) on a face: {plane component id: volume cc label}."""
+  fcc = np.asarray(cc_plane).reshape(-1)
+  fpl = np.asarray(plane).reshape(-1)
+  _, first = np.unique(fcc, return_index=True)
+  return {int(fcc[i]): int(fpl[i]) for i in first}

@@ -1,0 +1,578 @@
+// Phase A of the TEASAR trace: whole-volume, all-labels-at-once kernels (sm_100a).
+//
+// The reference traces one label at a time on bounding-box crops (kimimaro/intake.py:445-515).
+// On a B200 the label volume, its DBF and every per-voxel work field live in HBM as dense
+// [sx,sy,sz] arrays shared by all labels (labels are disjoint, so they never touch each other's
+// voxels) and the steps that precede the sequential path loop run for ALL labels in one launch:
+//
+//   label_stats      per-label voxel count, bounding box, max DBF, first voxel   (intake.py:195-203, trace.py:100, pyx:307-326)
+//   edf_multi        26-connected geometric distance field from one source per label, all labels
+//                    at once: frontier label-correcting sweep, warp per frontier voxel, lanes =
+//                    the 26 neighbours, atomicMin on the float bit pattern, ballot-compacted push.
+//                    Replaces dijkstra3d.euclidean_distance_field (trace.py:139-145, 302-307).
+//                    Distances are the least fixed point of d[v] = min_u fl(d[u] + w_uv), i.e.
+//                    bit-identical to a sequential Dijkstra regardless of relaxation order.
+//   field_argmax     per-label location of the largest finite distance (return_max_location)
+//   pdrf             fused zero2inf / inf2zero / compute_pdrf (trace.py:138,146,315-356) plus the
+//                    initialisation of the path-loop work fields and the target-bucket histogram
+//   bucket_scatter   counting sort of every label's voxels into DAF buckets (CachedTargetFinder,
+//                    pyx:995-1006, without a full sort: the finder only ever needs the maximum)
+//
+// All of it is HBM / L2-atomic bound integer and float32 work; no tensor cores.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr uint32_t kInfBits = 0x7f800000u;
+constexpr uint32_t kFrozen = 0xffffffffu;
+
+struct Dims {
+  int sx, sy, sz;
+  uint32_t sxy;
+};
+
+__device__ __forceinline__ void unravel(uint32_t loc, const Dims& d, int& x, int& y, int& z) {
+  z = loc / d.sxy;
+  const uint32_t r = loc - (uint32_t)z * d.sxy;
+  y = r / (uint32_t)d.sx;
+  x = r - (uint32_t)y * d.sx;
+}
+
+// ------------------------------------------------------------------------------------------------
+// label_stats: each thread walks a 16-voxel x segment and merges equal-label runs before touching
+// the per-label tables, which cuts the atomic traffic by the mean run length.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSeg = 16;
+
+__global__ void label_stats_kernel(const uint32_t* __restrict__ cc, const float* __restrict__ dbf, Dims d,
+                                   uint32_t nseg_x, uint64_t nsegs, uint32_t n_labels, uint32_t* __restrict__ count,
+                                   int* __restrict__ bbox, uint32_t* __restrict__ dbfmax_bits,
+                                   uint32_t* __restrict__ first) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsegs) return;
+  const uint32_t row = (uint32_t)(t / nseg_x);
+  const int x0 = (int)(t - (uint64_t)row * nseg_x) * kSeg;
+  const int y = row % (uint32_t)d.sy, z = row / (uint32_t)d.sy;
+  const uint32_t base = row * (uint32_t)d.sx;
+  const int x1 = min(x0 + kSeg, d.sx);
+  uint32_t cur = 0, cnt = 0;
+  int xa = 0, xb = 0;
+  float mx = 0.0f;
+  auto flush = [&]() {
+    if (cur != 0 && cur <= n_labels) {
+      atomicAdd(&count[cur], cnt);
+      int* b = bbox + 6 * (size_t)cur;
+      atomicMin(&b[0], xa); atomicMax(&b[3], xb);
+      atomicMin(&b[1], y); atomicMax(&b[4], y);
+      atomicMin(&b[2], z); atomicMax(&b[5], z);
+      if (dbf) atomicMax(&dbfmax_bits[cur], __float_as_uint(mx));
+      atomicMin(&first[cur], base + (uint32_t)xa);
+    }
+  };
+  for (int x = x0; x < x1; x++) {
+    const uint32_t l = cc[base + x];
+    if (l != cur) {
+      flush();
+      cur = l; cnt = 0; xa = x; mx = 0.0f;
+    }
+    cnt++; xb = x;
+    if (dbf && l) mx = fmaxf(mx, dbf[base + x]);
+  }
+  flush();
+}
+
+__global__ void bbox_init_kernel(int* bbox, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bbox[6 * i + 0] = bbox[6 * i + 1] = bbox[6 * i + 2] = 0x7fffffff;
+  bbox[6 * i + 3] = bbox[6 * i + 4] = bbox[6 * i + 5] = -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// edf_multi: persistent cooperative kernel, one grid barrier per relaxation round.
+// ctrl[0..2] = rotating frontier counters (round r reads ctrl[r%3], pushes to ctrl[(r+1)%3]);
+// ctrl[3] = rounds executed, ctrl[4] = total relaxations that improved a voxel.
+// ------------------------------------------------------------------------------------------------
+struct EdfParams {
+  const uint32_t* cc;
+  float* dist;
+  uint32_t* stamp;
+  uint32_t* queue;
+  uint32_t* ctrl;
+  uint64_t cap;
+  Dims d;
+  float w[26];
+};
+
+__global__ void edf_seed_kernel(EdfParams p, const uint32_t* __restrict__ src, uint32_t n_src) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { p.ctrl[1] = n_src; p.ctrl[0] = 0; p.ctrl[2] = 0; p.ctrl[3] = 0; p.ctrl[4] = 0; }
+  if (i < n_src) {
+    const uint32_t s = src[i];
+    p.dist[s] = 0.0f;
+    p.queue[p.cap + i] = s;  // round 1 reads buffer (1 & 1) = 1
+  }
+}
+
+template <bool HAS_FROZEN>
+__global__ void __launch_bounds__(256) edf_multi_kernel(EdfParams p) {
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  int dx = 0, dy = 0, dz = 0;
+  float w = 0.0f;
+  if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; w = p.w[lane]; }
+  const int64_t off = (int64_t)dx + (int64_t)dy * p.d.sx + (int64_t)dz * p.d.sxy;
+  const uint32_t ltmask = (1u << lane) - 1u;
+  uint32_t improved = 0;
+  uint32_t round = 1;
+  for (;;) {
+    const uint32_t n = __ldcg(&p.ctrl[round % 3]);
+    if (n == 0) break;
+    const uint32_t* qin = p.queue + (uint64_t)(round & 1) * p.cap;
+    uint32_t* qout = p.queue + (uint64_t)((round + 1) & 1) * p.cap;
+    uint32_t* cnt_out = &p.ctrl[(round + 1) % 3];
+    for (uint32_t it = gwarp; it < n; it += nwarps) {
+      const uint32_t u = __ldcg(&qin[it]);
+      const float du = __ldcg(&p.dist[u]);
+      const uint32_t lab = __ldg(&p.cc[u]);
+      int x, y, z;
+      unravel(u, p.d, x, y, z);
+      const int nx = x + dx, ny = y + dy, nz = z + dz;
+      bool push = false;
+      uint32_t v = 0;
+      if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < p.d.sx && ny < p.d.sy && nz < p.d.sz) {
+        v = (uint32_t)((int64_t)u + off);
+        if (__ldg(&p.cc[v]) == lab) {
+          bool frozen = false;
+          if (HAS_FROZEN) frozen = __ldcg(&p.stamp[v]) == kFrozen;
+          if (!frozen) {
+            const uint32_t nd = __float_as_uint(__fadd_rn(du, w));
+            const uint32_t old = atomicMin(reinterpret_cast<uint32_t*>(&p.dist[v]), nd);
+            if (nd < old) {
+              improved++;
+              push = atomicExch(&p.stamp[v], round) != round;
+            }
+          }
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, push);
+      if (m) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cnt_out, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (push) qout[base + __popc(m & ltmask)] = v;
+      }
+    }
+    grid.sync();
+    if (gwarp == 0 && lane == 0) { p.ctrl[round % 3] = 0; p.ctrl[3] = round; }
+    round++;
+  }
+  if (improved) atomicAdd(&p.ctrl[4], improved);
+}
+
+// soma free-space box (dijkstra3d free_space_radius): closed-form distances inside the box
+// inscribed in the sphere, interior frozen, shell voxels become the frontier.  One label, one source.
+__global__ void edf_freespace_seed_kernel(EdfParams p, uint32_t src, float radius, float wx, float wy, float wz) {
+  int cx, cy, cz;
+  unravel(src, p.d, cx, cy, cz);
+  const float half = radius / sqrtf(3.0f);
+  const int rx = (int)(half / wx), ry = (int)(half / wy), rz = (int)(half / wz);
+  const int bx = 2 * rx + 1, by = 2 * ry + 1, bz = 2 * rz + 1;
+  const uint64_t nbox = (uint64_t)bx * by * bz;
+  const uint32_t lab = p.cc[src];
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbox; i += (uint64_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(i % bx), iy = (int)((i / bx) % by), iz = (int)(i / ((uint64_t)bx * by));
+    const int x = cx - rx + ix, y = cy - ry + iy, z = cz - rz + iz;
+    if (x < 0 || y < 0 || z < 0 || x >= p.d.sx || y >= p.d.sy || z >= p.d.sz) continue;
+    const uint32_t loc = (uint32_t)x + (uint32_t)p.d.sx * ((uint32_t)y + (uint32_t)p.d.sy * (uint32_t)z);
+    if (p.cc[loc] != lab) continue;
+    const float ax = __fmul_rn(wx, (float)(x - cx)), ay = __fmul_rn(wy, (float)(y - cy)), az = __fmul_rn(wz, (float)(z - cz));
+    const float dd = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
+    p.dist[loc] = dd;
+    const bool shell = ix == 0 || iy == 0 || iz == 0 || ix == bx - 1 || iy == by - 1 || iz == bz - 1;
+    if (shell) {
+      const uint32_t pos = atomicAdd(&p.ctrl[1], 1u);
+      p.queue[p.cap + pos] = loc;
+    } else {
+      p.stamp[loc] = kFrozen;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// field_argmax: per label max of (dist, smallest index) packed as (dist_bits << 32) | ~index
+// ------------------------------------------------------------------------------------------------
+__global__ void field_argmax_kernel(const uint32_t* __restrict__ cc, const float* __restrict__ dist, Dims d,
+                                    uint32_t nseg_x, uint64_t nsegs, uint32_t n_labels,
+                                    unsigned long long* __restrict__ best) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsegs) return;
+  const uint32_t row = (uint32_t)(t / nseg_x);
+  const int x0 = (int)(t - (uint64_t)row * nseg_x) * kSeg;
+  const uint32_t base = row * (uint32_t)d.sx;
+  const int x1 = min(x0 + kSeg, d.sx);
+  uint32_t cur = 0;
+  unsigned long long key = 0;
+  auto flush = [&]() {
+    if (cur != 0 && cur <= n_labels && key != 0) {
+      if (key > best[cur]) atomicMax(&best[cur], key);
+    }
+  };
+  for (int x = x0; x < x1; x++) {
+    const uint32_t l = cc[base + x];
+    if (l != cur) { flush(); cur = l; key = 0; }
+    if (l) {
+      const uint32_t b = __float_as_uint(dist[base + x]);
+      if (b < kInfBits) {
+        const unsigned long long k = ((unsigned long long)b << 32) | (unsigned long long)(0xffffffffu - (base + (uint32_t)x));
+        if (k > key) key = k;
+      }
+    }
+  }
+  flush();
+}
+
+// ------------------------------------------------------------------------------------------------
+// pdrf (+ work-field init + bucket histogram)
+// ------------------------------------------------------------------------------------------------
+struct PdrfParams {
+  const uint32_t* cc;
+  const float* dbf;
+  const float* daf;          // distance-from-root field (inf where unreachable)
+  float* pdrf;
+  unsigned long long* claim; // set to ~0 (valid) on participating voxels
+  uint8_t* flag;             // cleared
+  const float* M;            // per label: f32(1 / dbf_max^1.01)     (trace.py:336)
+  const float* inv_maxdaf;   // per label: 1 / DAF[target], 0 when max_daf == 0 (trace.py:352-354)
+  const uint8_t* active;     // per label: 1 = take part
+  uint32_t* hist;            // [ (n_labels+1) * nbuckets ]
+  uint32_t n_labels;
+  int nbuckets;
+  float pdrf_scale;
+  float exponent;
+  int n_squarings;           // >= 0: exponent is 2^n (repeated squaring, trace.py:343-345); -1: powf
+  uint64_t V;
+};
+
+__device__ __forceinline__ int daf_bucket(float daf, float inv, int nb) {
+  // monotone in daf; the maximum lands in bucket nb-1
+  const float t = __fmul_rn(__fmul_rn(daf, inv), (float)(nb - 1));
+  int b = (int)t;
+  return b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b);
+}
+
+__global__ void pdrf_kernel(PdrfParams p) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.V; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t l = p.cc[i];
+    if (l == 0 || l > p.n_labels || !p.active[l]) continue;
+    float dbf = p.dbf[i];
+    if (dbf == 0.0f) dbf = __int_as_float(kInfBits);           // zero2inf (trace.py:138)
+    float daf = p.daf[i];
+    if (__float_as_uint(daf) >= kInfBits) daf = 0.0f;           // inf2zero (trace.py:146)
+    float P = __fsub_rn(1.0f, __fmul_rn(dbf, p.M[l]));
+    if (p.n_squarings >= 0) {
+      for (int k = 0; k < p.n_squarings; k++) P = __fmul_rn(P, P);
+    } else {
+      P = powf(P, p.exponent);
+    }
+    P = __fmul_rn(P, p.pdrf_scale);
+    const float inv = p.inv_maxdaf[l];
+    if (inv != 0.0f) P = __fadd_rn(P, __fmul_rn(daf, inv));
+    p.pdrf[i] = P;
+    p.claim[i] = ~0ull;
+    p.flag[i] = 0;
+    atomicAdd(&p.hist[(size_t)l * p.nbuckets + daf_bucket(daf, inv, p.nbuckets)], 1u);
+  }
+}
+
+struct ScatterParams {
+  const uint32_t* cc;
+  float* dist;               // holds DAF on entry; reset to +inf on exit for participating voxels
+  const float* inv_maxdaf;
+  const uint8_t* active;
+  uint32_t* cursor;          // exclusive-scanned histogram, advanced by the scatter
+  unsigned long long* keys;  // (daf_bits << 32) | linear index, bucket-partitioned per label
+  uint32_t n_labels;
+  int nbuckets;
+  uint64_t V;
+};
+
+__global__ void bucket_scatter_kernel(ScatterParams p) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.V; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t l = p.cc[i];
+    if (l == 0 || l > p.n_labels || !p.active[l]) continue;
+    float daf = p.dist[i];
+    if (__float_as_uint(daf) >= kInfBits) daf = 0.0f;
+    const uint32_t pos = atomicAdd(&p.cursor[(size_t)l * p.nbuckets + daf_bucket(daf, p.inv_maxdaf[l], p.nbuckets)], 1u);
+    p.keys[pos] = ((unsigned long long)__float_as_uint(daf) << 32) | (unsigned long long)i;
+    p.dist[i] = __int_as_float(kInfBits);
+  }
+}
+
+// single-CTA exclusive scan (n up to a few million): good enough for the (label x bucket) table
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n) {
+  __shared__ uint32_t s_part[1024];
+  const uint32_t t = threadIdx.x;
+  const uint64_t per = (n + 1023) / 1024;
+  const uint64_t a = (uint64_t)t * per, b = min(n, a + per);
+  uint32_t sum = 0;
+  for (uint64_t i = a; i < b; i++) sum += in[i];
+  s_part[t] = sum;
+  __syncthreads();
+  // Hillis-Steele inclusive scan of the 1024 partial sums
+  for (int ofs = 1; ofs < 1024; ofs <<= 1) {
+    uint32_t v = (t >= (uint32_t)ofs) ? s_part[t - ofs] : 0;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  uint32_t run = (t == 0) ? 0 : s_part[t - 1];
+  for (uint64_t i = a; i < b; i++) { const uint32_t v = in[i]; out[i] = run; run += v; }
+  if (t == 1023) out[n] = s_part[1023];
+}
+
+int coop_grid(const void* kernel, int threads, size_t smem, int* blocks_out) {
+  int dev = 0, sms = 0, per_sm = 0;
+  B2T_CUDA_TRY(cudaGetDevice(&dev));
+  B2T_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  B2T_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  if (per_sm < 1) { b2t_set_error("cooperative kernel does not fit on an SM"); return B2T_ERR_CUDA; }
+  *blocks_out = sms * per_sm;
+  return B2T_OK;
+}
+
+void fill_weights(float wx, float wy, float wz, float* w) {
+  // float32 expressions of ext/skeletontricks/dijkstra_invalidation.hpp:45-52 (_s, _c)
+  const float sxy = sqrtf(wx * wx + wy * wy), syz = sqrtf(wy * wy + wz * wz), sxz = sqrtf(wx * wx + wz * wz);
+  const float c = sqrtf(wx * wx + wy * wy + wz * wz);
+  w[0] = w[1] = wx; w[2] = w[3] = wy; w[4] = w[5] = wz;
+  for (int i = 6; i < 10; i++) w[i] = sxy;
+  for (int i = 10; i < 14; i++) w[i] = syz;
+  for (int i = 14; i < 18; i++) w[i] = sxz;
+  for (int i = 18; i < 26; i++) w[i] = c;
+}
+
+int check_dims(int64_t sx, int64_t sy, int64_t sz) {
+  B2T_REQUIRE(sx > 0 && sy > 0 && sz > 0, "empty volume");
+  B2T_REQUIRE((double)sx * (double)sy * (double)sz < 4294967295.0, "volumes of 2^32 voxels or more are not supported");
+  return B2T_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+B2T_EXPORT int b2t_label_stats(const uint32_t* d_cc, const float* d_dbf, int64_t sx, int64_t sy, int64_t sz,
+                               uint32_t n_labels, uint32_t* d_count, int32_t* d_bbox, float* d_dbfmax,
+                               uint32_t* d_first, void* stream) {
+  if (int rc = check_dims(sx, sy, sz)) return rc;
+  B2T_REQUIRE(d_cc && d_count && d_bbox && d_first, "b2t_label_stats: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
+  const size_t n1 = (size_t)n_labels + 1;
+  B2T_CUDA_TRY(cudaMemsetAsync(d_count, 0, n1 * sizeof(uint32_t), st));
+  B2T_CUDA_TRY(cudaMemsetAsync(d_first, 0xff, n1 * sizeof(uint32_t), st));
+  if (d_dbfmax) B2T_CUDA_TRY(cudaMemsetAsync(d_dbfmax, 0, n1 * sizeof(float), st));
+  bbox_init_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(d_bbox, (uint32_t)n1);
+  const uint32_t nseg_x = (uint32_t)((sx + kSeg - 1) / kSeg);
+  const uint64_t nsegs = (uint64_t)nseg_x * sy * sz;
+  const unsigned blocks = (unsigned)((nsegs + 255) / 256);
+  label_stats_kernel<<<blocks, 256, 0, st>>>(d_cc, d_dbf, d, nseg_x, nsegs, n_labels, d_count, d_bbox,
+                                             reinterpret_cast<uint32_t*>(d_dbfmax), d_first);
+  B2T_CUDA_TRY(cudaGetLastError());
+  return B2T_OK;
+}
+
+// d_dist must be pre-filled with +inf, d_stamp with 0 (both [V]); d_queue holds 2*queue_cap u32 with
+// queue_cap >= number of foreground voxels of the participating labels; d_ctrl holds >= 8 u32.
+B2T_EXPORT int b2t_edf_multi(const uint32_t* d_cc, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
+                             const uint32_t* d_sources, uint32_t n_sources, float free_space_radius,
+                             uint32_t h_free_space_source, float* d_dist, uint32_t* d_stamp, uint32_t* d_queue,
+                             uint64_t queue_cap, uint32_t* d_ctrl, void* stream) {
+  if (int rc = check_dims(sx, sy, sz)) return rc;
+  B2T_REQUIRE(d_cc && d_dist && d_stamp && d_queue && d_ctrl, "b2t_edf_multi: null pointer");
+  B2T_REQUIRE(queue_cap >= n_sources, "b2t_edf_multi: queue capacity below source count");
+  cudaStream_t st = (cudaStream_t)stream;
+  EdfParams p;
+  p.cc = d_cc; p.dist = d_dist; p.stamp = d_stamp; p.queue = d_queue; p.ctrl = d_ctrl; p.cap = queue_cap;
+  p.d = Dims{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
+  fill_weights(wx, wy, wz, p.w);
+  const bool frozen = free_space_radius > 0.0f;
+  if (frozen) {
+    B2T_REQUIRE(n_sources == 1, "free_space_radius needs exactly one source");
+    const uint32_t zero = 0;
+    edf_seed_kernel<<<1, 32, 0, st>>>(p, &zero, 0);  // clears ctrl
+    edf_freespace_seed_kernel<<<256, 256, 0, st>>>(p, h_free_space_source, free_space_radius, wx, wy, wz);
+  } else {
+    if (n_sources == 0) return B2T_OK;
+    edf_seed_kernel<<<(n_sources + 255) / 256, 256, 0, st>>>(p, d_sources, n_sources);
+  }
+  B2T_CUDA_TRY(cudaGetLastError());
+  const void* kern = frozen ? (const void*)edf_multi_kernel<true> : (const void*)edf_multi_kernel<false>;
+  int blocks = 0;
+  if (int rc = coop_grid(kern, 256, 0, &blocks)) return rc;
+  void* args[] = {&p};
+  B2T_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(256), args, 0, st));
+  return B2T_OK;
+}
+
+B2T_EXPORT int b2t_field_argmax(const uint32_t* d_cc, const float* d_dist, int64_t sx, int64_t sy, int64_t sz,
+                                uint32_t n_labels, uint64_t* d_best, void* stream) {
+  if (int rc = check_dims(sx, sy, sz)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
+  B2T_CUDA_TRY(cudaMemsetAsync(d_best, 0, ((size_t)n_labels + 1) * sizeof(uint64_t), st));
+  const uint32_t nseg_x = (uint32_t)((sx + kSeg - 1) / kSeg);
+  const uint64_t nsegs = (uint64_t)nseg_x * sy * sz;
+  field_argmax_kernel<<<(unsigned)((nsegs + 255) / 256), 256, 0, st>>>(d_cc, d_dist, d, nseg_x, nsegs, n_labels,
+                                                                      reinterpret_cast<unsigned long long*>(d_best));
+  B2T_CUDA_TRY(cudaGetLastError());
+  return B2T_OK;
+}
+
+// Fused compute_pdrf + work-field initialisation + target-bucket build.
+//   d_hist / d_cursor: (n_labels+1)*nbuckets + 1 u32 each; d_keys: u64 per foreground voxel.
+//   On return d_cursor[l*nbuckets + b] is the END of bucket b of label l inside d_keys (the scatter
+//   advances the exclusive offsets), d_hist holds the counts, and d_dist is +inf on every
+//   participating voxel, ready for the path loop.
+B2T_EXPORT int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist, float* d_pdrf,
+                                    uint64_t* d_claim, uint8_t* d_flag, int64_t sx, int64_t sy, int64_t sz,
+                                    uint32_t n_labels, const float* d_M, const float* d_inv_maxdaf,
+                                    const uint8_t* d_active, float pdrf_scale, float pdrf_exponent, int nbuckets,
+                                    uint32_t* d_hist, uint32_t* d_cursor, uint64_t* d_keys, void* stream) {
+  if (int rc = check_dims(sx, sy, sz)) return rc;
+  B2T_REQUIRE(nbuckets >= 1 && nbuckets <= 4096, "nbuckets out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t V = (uint64_t)sx * sy * sz;
+  const uint64_t ntab = ((uint64_t)n_labels + 1) * nbuckets;
+  B2T_CUDA_TRY(cudaMemsetAsync(d_hist, 0, (ntab + 1) * sizeof(uint32_t), st));
+  PdrfParams p;
+  p.cc = d_cc; p.dbf = d_dbf; p.daf = d_dist; p.pdrf = d_pdrf;
+  p.claim = reinterpret_cast<unsigned long long*>(d_claim); p.flag = d_flag;
+  p.M = d_M; p.inv_maxdaf = d_inv_maxdaf; p.active = d_active; p.hist = d_hist;
+  p.n_labels = n_labels; p.nbuckets = nbuckets; p.pdrf_scale = pdrf_scale; p.exponent = pdrf_exponent;
+  p.n_squarings = -1;
+  {
+    // is_power_of_two(pdrf_exponent) and pdrf_exponent < 2^16  (trace.py:343)
+    const float e = pdrf_exponent;
+    if (e == (float)(int)e && e > 0 && e < 65536.0f) {
+      const int ei = (int)e;
+      if ((ei & (ei - 1)) == 0) { int n = 0; while ((1 << n) < ei) n++; p.n_squarings = n; }
+    }
+  }
+  p.V = V;
+  const uint64_t want = (V + 255) / 256;
+  const unsigned blocks = (unsigned)(want < 148ull * 32 ? want : 148ull * 32);
+  pdrf_kernel<<<blocks, 256, 0, st>>>(p);
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(d_hist, d_cursor, ntab);
+  ScatterParams s;
+  s.cc = d_cc; s.dist = d_dist; s.inv_maxdaf = d_inv_maxdaf; s.active = d_active; s.cursor = d_cursor;
+  s.keys = reinterpret_cast<unsigned long long*>(d_keys); s.n_labels = n_labels; s.nbuckets = nbuckets; s.V = V;
+  bucket_scatter_kernel<<<blocks, 256, 0, st>>>(s);
+  B2T_CUDA_TRY(cudaGetLastError());
+  return B2T_OK;
+}
+
+// =================================================================================================
+// K6  fill_voids.fill (kimimaro/trace.py:109, soma labels only): flood the background
+// from the six faces through 6-connectivity, everything not reached becomes foreground.
+// Frontier sweep, one thread per frontier voxel, persistent cooperative kernel like edf_multi.
+// d_mask: uint8 [V] (0 background, non-zero foreground), edited in place.
+// d_reach: uint32 [V] scratch (zeroed here); d_queue: 2*queue_cap u32; d_ctrl: >= 8 u32; the number of
+// filled voxels is left in d_ctrl[5].
+// =================================================================================================
+namespace {
+
+struct FillParams {
+  uint8_t* mask;
+  uint32_t* reach;
+  uint32_t* queue;
+  uint32_t* ctrl;
+  uint64_t cap;
+  Dims d;
+  uint64_t V;
+};
+
+__global__ void fill_seed_kernel(FillParams p) {
+  // every background voxel on a face of the array seeds the flood
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.V) return;
+  if (p.mask[i]) return;
+  int x, y, z;
+  unravel((uint32_t)i, p.d, x, y, z);
+  if (x == 0 || y == 0 || z == 0 || x == p.d.sx - 1 || y == p.d.sy - 1 || z == p.d.sz - 1) {
+    p.reach[i] = 1;
+    const uint32_t pos = atomicAdd(&p.ctrl[1], 1u);
+    p.queue[p.cap + pos] = (uint32_t)i;
+  }
+}
+
+__global__ void __launch_bounds__(256) fill_flood_kernel(FillParams p) {
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  uint32_t round = 1;
+  for (;;) {
+    const uint32_t n = __ldcg(&p.ctrl[round % 3]);
+    if (n == 0) break;
+    const uint32_t* qin = p.queue + (uint64_t)(round & 1) * p.cap;
+    uint32_t* qout = p.queue + (uint64_t)((round + 1) & 1) * p.cap;
+    uint32_t* cnt_out = &p.ctrl[(round + 1) % 3];
+    for (uint32_t it = tid; it < n; it += nthreads) {
+      const uint32_t u = __ldcg(&qin[it]);
+      int x, y, z;
+      unravel(u, p.d, x, y, z);
+      const int64_t offs[6] = {-1, 1, -(int64_t)p.d.sx, (int64_t)p.d.sx, -(int64_t)p.d.sxy, (int64_t)p.d.sxy};
+      const bool ok[6] = {x > 0, x < p.d.sx - 1, y > 0, y < p.d.sy - 1, z > 0, z < p.d.sz - 1};
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        if (!ok[k]) continue;
+        const uint32_t v = (uint32_t)((int64_t)u + offs[k]);
+        if (p.mask[v]) continue;
+        if (atomicExch(&p.reach[v], 1u) == 0u) qout[atomicAdd(cnt_out, 1u)] = v;
+      }
+    }
+    grid.sync();
+    if (tid == 0) p.ctrl[round % 3] = 0;
+    round++;
+  }
+}
+
+__global__ void fill_apply_kernel(FillParams p) {
+  uint32_t filled = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.V; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (!p.mask[i] && !p.reach[i]) { p.mask[i] = 1; filled++; }
+  }
+  if (filled) atomicAdd(&p.ctrl[5], filled);
+}
+
+}  // namespace
+
+B2T_EXPORT int b2t_fill_voids(uint8_t* d_mask, int64_t sx, int64_t sy, int64_t sz, uint32_t* d_reach,
+                              uint32_t* d_queue, uint64_t queue_cap, uint32_t* d_ctrl, void* stream) {
+  if (int rc = check_dims(sx, sy, sz)) return rc;
+  B2T_REQUIRE(d_mask && d_reach && d_queue && d_ctrl, "b2t_fill_voids: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  FillParams p;
+  p.mask = d_mask; p.reach = d_reach; p.queue = d_queue; p.ctrl = d_ctrl; p.cap = queue_cap;
+  p.d = Dims{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
+  p.V = (uint64_t)sx * sy * sz;
+  B2T_CUDA_TRY(cudaMemsetAsync(d_reach, 0, p.V * sizeof(uint32_t), st));
+  B2T_CUDA_TRY(cudaMemsetAsync(d_ctrl, 0, 8 * sizeof(uint32_t), st));
+  fill_seed_kernel<<<(unsigned)((p.V + 255) / 256), 256, 0, st>>>(p);
+  int blocks = 0;
+  if (int rc = coop_grid((const void*)fill_flood_kernel, 256, 0, &blocks)) return rc;
+  void* args[] = {&p};
+  B2T_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)fill_flood_kernel, dim3(blocks), dim3(256), args, 0, st));
+  const uint64_t want = (p.V + 255) / 256;
+  fill_apply_kernel<<<(unsigned)(want < 148ull * 32 ? want : 148ull * 32), 256, 0, st>>>(p);
+  B2T_CUDA_TRY(cudaGetLastError());
+  return B2T_OK;
+}

@@ -1,0 +1,159 @@
+// Preamble / epilogue kernels around the trace, sm_100a.
+//
+//   ccl26        26-connected multi-label connected components (replaces cc3d.connected_components,
+//                kimimaro/utility.py:77): lock-free union-find over the dense volume, roots are the
+//                smallest linear index of each component, i.e. first appearance in a Fortran raster
+//                scan -- the same numbering order cc3d produces.
+//   relabel      cc[v] = rank[root[v]] after the host side has ranked the roots.
+//   gather_paths compact the per-label path segments of the trace pool into one contiguous buffer
+//                and fetch the radii (DBF at the vertex, trace.py:186-187) in the same pass.
+#include "common.cuh"
+
+namespace {
+
+struct Dims {
+  int sx, sy, sz;
+  uint32_t sxy;
+};
+
+constexpr uint32_t kNone = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t i) {
+  uint32_t p = __ldcg(&parent[i]);
+  while (p != i) {
+    const uint32_t gp = __ldcg(&parent[p]);
+    if (gp != p) parent[i] = gp;  // path halving (benign race: only ever points further up)
+    i = p;
+    p = gp;
+  }
+  return i;
+}
+
+__device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
+  for (;;) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a > b) { const uint32_t t = a; a = b; b = t; }
+    const uint32_t old = atomicMin(&parent[b], a);   // hook the larger root under the smaller
+    if (old == b) return;
+    b = old;
+  }
+}
+
+template <typename T>
+__global__ void ccl_init_kernel(const T* __restrict__ labels, uint32_t* __restrict__ parent, uint64_t V) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (uint64_t)gridDim.x * blockDim.x)
+    parent[i] = labels[i] != T(0) ? (uint32_t)i : kNone;
+}
+
+// the 13 neighbours that precede a voxel in raster order
+__device__ __constant__ const int8_t kHalf[13][3] = {
+  {-1, 0, 0}, {-1, -1, 0}, {0, -1, 0}, {1, -1, 0},
+  {-1, -1, -1}, {0, -1, -1}, {1, -1, -1}, {-1, 0, -1}, {0, 0, -1}, {1, 0, -1}, {-1, 1, -1}, {0, 1, -1}, {1, 1, -1}};
+
+template <typename T>
+__global__ void ccl_merge_kernel(const T* __restrict__ labels, uint32_t* __restrict__ parent, Dims d, uint64_t V) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (uint64_t)gridDim.x * blockDim.x) {
+    const T l = labels[i];
+    if (l == T(0)) continue;
+    const uint32_t loc = (uint32_t)i;
+    const int z = loc / d.sxy;
+    const uint32_t r = loc - (uint32_t)z * d.sxy;
+    const int y = r / (uint32_t)d.sx;
+    const int x = r - (uint32_t)y * d.sx;
+#pragma unroll
+    for (int k = 0; k < 13; k++) {
+      const int nx = x + kHalf[k][0], ny = y + kHalf[k][1], nz = z + kHalf[k][2];
+      if (nx < 0 || ny < 0 || nz < 0 || nx >= d.sx || ny >= d.sy) continue;
+      const uint32_t n = (uint32_t)nx + (uint32_t)d.sx * ((uint32_t)ny + (uint32_t)d.sy * (uint32_t)nz);
+      if (labels[n] == l) uf_union(parent, loc, n);
+    }
+  }
+}
+
+__global__ void ccl_flatten_kernel(uint32_t* __restrict__ parent, uint8_t* __restrict__ is_root, uint64_t V) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t p = parent[i];
+    if (p == kNone) { is_root[i] = 0; continue; }
+    const uint32_t r = uf_find(parent, (uint32_t)i);
+    parent[i] = r;
+    is_root[i] = r == (uint32_t)i;
+  }
+}
+
+__global__ void ccl_relabel_kernel(uint32_t* __restrict__ parent_to_cc, const int32_t* __restrict__ rank, uint64_t V) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t p = parent_to_cc[i];
+    parent_to_cc[i] = (p == kNone) ? 0u : (uint32_t)rank[p];
+  }
+}
+
+__global__ void gather_paths_kernel(const uint32_t* __restrict__ pool, const uint32_t* __restrict__ src_off,
+                                    const uint32_t* __restrict__ len, const uint64_t* __restrict__ dst_off,
+                                    const float* __restrict__ dbf, uint32_t* __restrict__ dst_vox,
+                                    float* __restrict__ dst_radius) {
+  const uint32_t j = blockIdx.x;
+  const uint32_t n = len[j];
+  const uint32_t* s = pool + src_off[j];
+  const uint64_t o = dst_off[j];
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t v = s[i];
+    dst_vox[o + i] = v;
+    dst_radius[o + i] = (v == kNone) ? 0.0f : dbf[v];
+  }
+}
+
+unsigned grid_for(uint64_t V) {
+  const uint64_t want = (V + 255) / 256;
+  return (unsigned)(want < 148ull * 64 ? want : 148ull * 64);
+}
+
+template <typename T>
+int ccl_launch(const T* labels, Dims d, uint64_t V, uint32_t* parent, uint8_t* is_root, cudaStream_t st) {
+  ccl_init_kernel<T><<<grid_for(V), 256, 0, st>>>(labels, parent, V);
+  ccl_merge_kernel<T><<<grid_for(V), 256, 0, st>>>(labels, parent, d, V);
+  ccl_flatten_kernel<<<grid_for(V), 256, 0, st>>>(parent, is_root, V);
+  B2T_CUDA_TRY(cudaGetLastError());
+  return B2T_OK;
+}
+
+}  // namespace
+
+// Step 1 of the CCL: d_parent[v] = smallest linear index of v's component (0xffffffff on background),
+// d_is_root[v] = 1 on exactly one voxel per component.  The caller ranks the roots (an exclusive
+// prefix sum over d_is_root, in raster order) and calls b2t_ccl_relabel.
+B2T_EXPORT int b2t_ccl26_roots(const void* d_labels, int label_bytes, int64_t sx, int64_t sy, int64_t sz,
+                               uint32_t* d_parent, uint8_t* d_is_root, void* stream) {
+  B2T_REQUIRE(d_labels && d_parent && d_is_root, "b2t_ccl26_roots: null pointer");
+  B2T_REQUIRE(sx > 0 && sy > 0 && sz > 0 && (double)sx * sy * sz < 4294967295.0, "bad volume shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
+  const uint64_t V = (uint64_t)sx * sy * sz;
+  switch (label_bytes) {
+    case 1: return ccl_launch<uint8_t>((const uint8_t*)d_labels, d, V, d_parent, d_is_root, st);
+    case 2: return ccl_launch<uint16_t>((const uint16_t*)d_labels, d, V, d_parent, d_is_root, st);
+    case 4: return ccl_launch<uint32_t>((const uint32_t*)d_labels, d, V, d_parent, d_is_root, st);
+    case 8: return ccl_launch<unsigned long long>((const unsigned long long*)d_labels, d, V, d_parent, d_is_root, st);
+    default: b2t_set_error("b2t_ccl26_roots: label_bytes must be 1, 2, 4 or 8"); return B2T_ERR_ARG;
+  }
+}
+
+// Step 2: d_parent (in place) becomes the cc label volume: cc[v] = d_rank[parent[v]], 0 on background.
+B2T_EXPORT int b2t_ccl_relabel(uint32_t* d_parent, const int32_t* d_rank, uint64_t n_voxels, void* stream) {
+  B2T_REQUIRE(d_parent && d_rank, "b2t_ccl_relabel: null pointer");
+  ccl_relabel_kernel<<<grid_for(n_voxels), 256, 0, (cudaStream_t)stream>>>(d_parent, d_rank, n_voxels);
+  B2T_CUDA_TRY(cudaGetLastError());
+  return B2T_OK;
+}
+
+// Compact n_seg path segments (pool[src_off[j] .. +len[j])) to dst[dst_off[j] ..) and fetch DBF at each vertex.
+B2T_EXPORT int b2t_gather_paths(const uint32_t* d_pool, const uint32_t* d_src_off, const uint32_t* d_len,
+                                const uint64_t* d_dst_off, uint32_t n_seg, const float* d_dbf, uint32_t* d_dst_vox,
+                                float* d_dst_radius, void* stream) {
+  if (n_seg == 0) return B2T_OK;
+  gather_paths_kernel<<<n_seg, 128, 0, (cudaStream_t)stream>>>(d_pool, d_src_off, d_len, d_dst_off, d_dbf, d_dst_vox,
+                                                              d_dst_radius);
+  B2T_CUDA_TRY(cudaGetLastError());
+  return B2T_OK;
+}

@@ -1,0 +1,582 @@
+// Phase B of the TEASAR trace: the per-label path loop of kimimaro/trace.py:196-267 as ONE
+// device-resident kernel (sm_100a).  One CTA owns one label for the whole loop -- no host round
+// trip per path -- and CTAs pull labels (largest first) from a device work counter, so ~1000
+// labels are in flight on the 148 SMs at any time.
+//
+//   per path:  target   manual_targets_before (LIFO) | CachedTargetFinder | manual_targets_after
+//                       (trace.py:225-230; pyx:1008-1045).  The finder is a block arg-max over the
+//                       current DAF bucket (keys built by field.cu), ties by largest index (rule T5).
+//              road     dijkstra3d.railroad(PDRF, target) (trace.py:240-242): threshold-batched
+//                       label-correcting sweep from the target, warp per frontier voxel / lane per
+//                       neighbour, atomicMin on float bits, stops once every voxel at least as
+//                       close as the best rail-adjacent voxel is final; parents by rule T3.
+//              cull     soma only (trace.py:246-251), float64 with the reference's uint32 wrap.
+//              erase    roll_invalidation_ball_inside_component (pyx:373-418 ->
+//                       dijkstra_invalidation.hpp:239-332) as a round-synchronous parallel claim:
+//                       packed (dist, seed) 64-bit atomicMin per candidate voxel, strict d < r.
+//              rail     PDRF[path] = 0 (trace.py:261-263)
+//
+// Per-voxel fields are the dense arrays of field.cu (cc, dbf, pdrf, dist, claim, stamp); per-label
+// queues live in a scratch pool indexed by the label's foreground-count prefix sum.
+#include "common.cuh"
+
+namespace {
+
+constexpr uint32_t kInfBits = 0x7f800000u;
+constexpr unsigned long long kValid = ~0ull;
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+struct Dims {
+  int sx, sy, sz;
+  uint32_t sxy;
+};
+
+struct Arena {
+  const uint32_t* cc;
+  const float* dbf;
+  float* pdrf;
+  float* dist;
+  unsigned long long* claim;
+  uint32_t* stamp;
+  Dims d;
+  float wx, wy, wz;
+};
+
+// One label to trace.  Mirrors the arguments kimimaro/intake.py:494-504 hands to trace().
+struct LabelDesc {
+  uint32_t segid;       // value of this label in cc
+  uint32_t root;        // linear index of the root voxel
+  uint32_t n_fg;        // foreground voxels (np.count_nonzero(labels), trace.py:211)
+  uint32_t region_off;  // prefix sum of n_fg over the batch: scratch region = 4 * region_off
+  uint32_t path_off;    // first slot of this label in the path pool
+  uint32_t path_cap;    // slots available
+  uint32_t tb_off, tb_n;  // manual_targets_before: targets[tb_off .. tb_off+tb_n), popped from the end
+  uint32_t ta_off, ta_n;  // manual_targets_after
+  uint32_t max_paths;   // 0xffffffff = None
+  uint32_t soma_mode;   // trace.py:118-127
+  float soma_radius;    // dbf_max * soma_invalidation_scale + soma_invalidation_const (float32)
+  uint32_t bucket_row;  // row of this label in the (label x bucket) tables = its cc id
+  uint32_t pad0, pad1;
+};
+
+struct Params {
+  float scale, konst;            // teasar_params scale / const
+  float soma_scale, soma_const;  // soma_invalidation_scale / _const
+  int nbuckets;
+  int n_desc;
+};
+
+struct Pools {
+  const unsigned long long* keys;  // bucket-partitioned (daf_bits << 32 | index)
+  const uint32_t* hist;            // bucket sizes
+  const uint32_t* cursor;          // bucket ends
+  uint32_t* scratch;               // 4 * sum(n_fg) u32
+  uint32_t* paths;                 // path pool: voxel indices, each path terminated by 0xffffffff
+  const uint32_t* targets;         // manual targets (linear indices)
+  uint32_t* out_len;               // per desc: slots written
+  uint32_t* out_npaths;            // per desc
+  int32_t* out_status;             // per desc: 0 ok, <0 error
+  uint32_t* out_stats;             // per desc x 4: relaxations, rounds, invalidated, target scans
+  uint32_t* work_counter;
+};
+
+__device__ __forceinline__ void unravel(uint32_t loc, const Dims& d, int& x, int& y, int& z) {
+  z = loc / d.sxy;
+  const uint32_t r = loc - (uint32_t)z * d.sxy;
+  y = r / (uint32_t)d.sx;
+  x = r - (uint32_t)y * d.sx;
+}
+
+// ---- block-wide reductions (all threads must call) ------------------------------------------------
+__device__ __forceinline__ uint32_t block_min_u32(uint32_t v, uint32_t* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  uint32_t r = s_red[0];
+#pragma unroll
+  for (int i = 1; i < kWarps; i++) r = min(r, s_red[i]);
+  return r;
+}
+
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t > v ? t : v;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  unsigned long long r = s_red[0];
+#pragma unroll
+  for (int i = 1; i < kWarps; i++) r = s_red[i] > r ? s_red[i] : r;
+  return r;
+}
+
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < kWarps; i++) r += s_red[i];
+  return r;
+}
+
+struct Shared {
+  uint32_t red32[kWarps];
+  unsigned long long red64[kWarps];
+  unsigned long long best;   // railroad: (dist_bits << 32) | voxel of the best rail-adjacent voxel
+  uint32_t n_keep, n_proc, n_next, n_touched;
+  uint32_t job;
+  int bucket;
+  uint32_t relax, rounds, invalidated, scans;
+};
+
+// ---- CachedTargetFinder.find_target ------------------------------------------------------------------
+__device__ uint32_t find_target(const Arena& A, const LabelDesc& L, const Pools& P, const Params& prm, Shared& S) {
+  for (;;) {
+    const int b = S.bucket;
+    if (b < 0) return 0xffffffffu;
+    const size_t row = (size_t)L.bucket_row * prm.nbuckets + b;
+    const uint32_t end = P.cursor[row], n = P.hist[row];
+    const unsigned long long* k = P.keys + (end - n);
+    unsigned long long best = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+      const unsigned long long key = k[i];
+      const uint32_t v = (uint32_t)key;
+      if (__ldcg(&A.claim[v]) == kValid && key + 1 > best) best = key + 1;  // +1 so that key 0 is distinguishable from "none"
+    }
+    best = block_max_u64(best, S.red64);
+    if (threadIdx.x == 0) S.scans++;
+    if (best != 0) return (uint32_t)(best - 1);
+    __syncthreads();
+    if (threadIdx.x == 0) S.bucket = b - 1;
+    __syncthreads();
+  }
+}
+
+// ---- dijkstra3d.railroad ----------------------------------------------------------------------------
+// Returns the path length written to out[0..): out[0] = rail voxel ... out[len-1] = target.
+__device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target, uint32_t* actA, uint32_t* actB,
+                             uint32_t* proc, uint32_t* touched, uint32_t* out, uint32_t out_cap, Shared& S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t seg = L.segid;
+  if (__ldcg(&A.pdrf[target]) == 0.0f) {
+    if (threadIdx.x == 0 && out_cap > 0) out[0] = target;
+    __syncthreads();
+    return out_cap > 0 ? 1 : 0;
+  }
+  int dx = 0, dy = 0, dz = 0;
+  if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; }
+  const int64_t off = (int64_t)dx + (int64_t)dy * A.d.sx + (int64_t)dz * A.d.sxy;
+  const uint32_t ltmask = (1u << lane) - 1u;
+
+  if (threadIdx.x == 0) {
+    A.dist[target] = 0.0f;
+    A.stamp[target] = 1;
+    actA[0] = target;
+    touched[0] = target;
+    S.n_touched = 1;
+    S.best = ~0ull;
+    S.n_keep = 0; S.n_proc = 0;
+  }
+  __syncthreads();
+  uint32_t n_act = 1;
+  uint32_t* act = actA;
+  uint32_t* alt = actB;
+  float delta = __ldcg(&A.pdrf[target]);
+  if (!(delta > 0.0f) || __float_as_uint(delta) >= kInfBits) delta = 1.0f;
+  uint32_t relax = 0, rounds = 0;
+
+  while (n_act > 0) {
+    // (a) smallest tentative distance among the active voxels
+    uint32_t mn = 0xffffffffu;
+    for (uint32_t i = threadIdx.x; i < n_act; i += kThreads) mn = min(mn, __float_as_uint(__ldcg(&A.dist[act[i]])));
+    mn = block_min_u32(mn, S.red32);
+    const uint32_t bound = (uint32_t)(S.best >> 32);  // +inf bits (or above) until a rail is seen
+    if (mn > bound) break;
+    uint32_t thr = __float_as_uint(__fadd_rn(__uint_as_float(mn), delta));
+    if (thr > bound) thr = bound;
+    // (b) split: <= thr -> expand now, <= bound -> keep for later, else drop
+    for (uint32_t i0 = 0; i0 < n_act; i0 += kThreads) {
+      const uint32_t i = i0 + threadIdx.x;
+      bool toproc = false, tokeep = false;
+      uint32_t u = 0;
+      if (i < n_act) {
+        u = act[i];
+        const uint32_t du = __float_as_uint(__ldcg(&A.dist[u]));
+        toproc = du <= thr;
+        tokeep = !toproc && du <= bound;
+        if (!toproc && !tokeep) A.stamp[u] = 0;
+      }
+      const uint32_t mp = __ballot_sync(0xffffffffu, toproc), mk = __ballot_sync(0xffffffffu, tokeep);
+      uint32_t bp = 0, bk = 0;
+      if (lane == 0) {
+        if (mp) bp = atomicAdd(&S.n_proc, __popc(mp));
+        if (mk) bk = atomicAdd(&S.n_keep, __popc(mk));
+      }
+      bp = __shfl_sync(0xffffffffu, bp, 0);
+      bk = __shfl_sync(0xffffffffu, bk, 0);
+      if (toproc) proc[bp + __popc(mp & ltmask)] = u;
+      if (tokeep) alt[bk + __popc(mk & ltmask)] = u;
+    }
+    __syncthreads();
+    const uint32_t n_proc = S.n_proc;
+    // (c) expand: warp per voxel, lane per neighbour.  New/improved voxels append to `alt`.
+    for (uint32_t it = warp; it < n_proc; it += kWarps) {
+      const uint32_t u = proc[it];
+      if (lane == 0) atomicExch(&A.stamp[u], 0u);   // from here on an improvement of u re-queues it
+      __syncwarp();
+      __threadfence_block();
+      const float du = __ldcg(&A.dist[u]);
+      int x, y, z;
+      unravel(u, A.d, x, y, z);
+      const int nx = x + dx, ny = y + dy, nz = z + dz;
+      bool push = false;
+      uint32_t v = 0;
+      if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
+        v = (uint32_t)((int64_t)u + off);
+        if (__ldg(&A.cc[v]) == seg) {
+          const float c = __ldcg(&A.pdrf[v]);
+          if (c == 0.0f) {
+            atomicMin(&S.best, ((unsigned long long)__float_as_uint(du) << 32) | u);   // rule T4 candidate
+          } else {
+            const uint32_t nd = __float_as_uint(__fadd_rn(du, c));
+            if (nd <= (uint32_t)(S.best >> 32)) {
+              const uint32_t old = atomicMin(reinterpret_cast<uint32_t*>(&A.dist[v]), nd);
+              if (nd < old) {
+                relax++;
+                if (old == kInfBits) touched[atomicAdd(&S.n_touched, 1u)] = v;
+                __threadfence_block();
+                push = atomicExch(&A.stamp[v], 1u) == 0u;
+              }
+            }
+          }
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, push);
+      if (m) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&S.n_keep, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (push) alt[base + __popc(m & ltmask)] = v;
+      }
+    }
+    __syncthreads();
+    n_act = S.n_keep;
+    { uint32_t* t = act; act = alt; alt = t; }
+    // batch-size feedback: keep roughly 2..8 voxels per warp in flight
+    if (n_proc < 2 * kWarps) delta = __fmul_rn(delta, 2.0f);
+    else if (n_proc > 8 * kWarps) delta = __fmul_rn(delta, 0.5f);
+    rounds++;
+    __syncthreads();
+    if (threadIdx.x == 0) { S.n_keep = 0; S.n_proc = 0; }
+    __syncthreads();
+  }
+  // anything still queued keeps stamp = 1; it is in `touched`, which resets it below
+
+  // (d) walk back: rail voxel, then parents by rule T3
+  uint32_t len = 0;
+  const unsigned long long best = S.best;
+  if (warp == 0) {
+    if (best == ~0ull) {
+      if (lane == 0 && out_cap > 0) out[0] = target;
+      len = 1;
+    } else {
+      uint32_t loc = (uint32_t)best;
+      {
+        int x, y, z;
+        unravel(loc, A.d, x, y, z);
+        const int nx = x + dx, ny = y + dy, nz = z + dz;
+        bool israil = false;
+        uint32_t v = 0;
+        if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
+          v = (uint32_t)((int64_t)loc + off);
+          israil = (__ldg(&A.cc[v]) == seg) && (__ldcg(&A.pdrf[v]) == 0.0f);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, israil);
+        const int first = __ffs(m) - 1;
+        const uint32_t rail = __shfl_sync(0xffffffffu, v, first < 0 ? 0 : first);
+        if (lane == 0 && len < out_cap) out[len] = rail;
+        len++;
+      }
+      uint32_t guard = 0;
+      while (loc != target && guard <= L.n_fg) {
+        if (lane == 0 && len < out_cap) out[len] = loc;
+        len++;
+        int x, y, z;
+        unravel(loc, A.d, x, y, z);
+        const int nx = x + dx, ny = y + dy, nz = z + dz;
+        unsigned long long key = ~0ull;
+        if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
+          const uint32_t v = (uint32_t)((int64_t)loc + off);
+          if (__ldg(&A.cc[v]) == seg) {
+            const uint32_t dv = __float_as_uint(__ldcg(&A.dist[v]));
+            if (dv < kInfBits) key = ((unsigned long long)dv << 32) | (unsigned long long)lane;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o);
+          key = t < key ? t : key;
+        }
+        if (key == ~0ull) break;  // cannot happen for a settled voxel
+        const int dir = (int)(key & 31u);
+        loc = (uint32_t)((int64_t)loc + (int64_t)kDX[dir] + (int64_t)kDY[dir] * A.d.sx + (int64_t)kDZ[dir] * A.d.sxy);
+        guard++;
+      }
+      if (lane == 0 && len < out_cap) out[len] = target;
+      len++;
+    }
+    if (lane == 0) S.red32[0] = len;
+  }
+  __syncthreads();
+  len = S.red32[0];
+  // (e) reset the scratch fields of every voxel this search touched
+  const uint32_t nt = S.n_touched;
+  for (uint32_t i = threadIdx.x; i < nt; i += kThreads) {
+    const uint32_t v = touched[i];
+    A.dist[v] = __int_as_float(kInfBits);
+    A.stamp[v] = 0;
+  }
+  relax = block_sum_u32(relax, S.red32);
+  if (threadIdx.x == 0) { S.relax += relax; S.rounds += rounds; }
+  __syncthreads();
+  return len;
+}
+
+// ---- roll_invalidation_ball_inside_component ---------------------------------------------------------
+// seeds[0..n_seeds) are path voxels in path order; radius_i = fl32(fl32(scale * DBF[seed]) + const)
+// (skeletontricks.pyx:393-395 under NumPy-2 scalar rules).  Returns the number of voxels invalidated.
+__device__ uint32_t invalidate(const Arena& A, const LabelDesc& L, const uint32_t* seeds, uint32_t n_seeds, float scale,
+                               float konst, uint32_t* fvA, uint32_t* fsA, uint32_t* fvB, uint32_t* fsB, Shared& S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t seg = L.segid;
+  int dx = 0, dy = 0, dz = 0;
+  if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; }
+  const int64_t off = (int64_t)dx + (int64_t)dy * A.d.sx + (int64_t)dz * A.d.sxy;
+  const uint32_t ltmask = (1u << lane) - 1u;
+  if (threadIdx.x == 0) { S.n_next = 0; }
+  __syncthreads();
+  // round 0: every still-valid seed claims itself
+  for (uint32_t i0 = 0; i0 < n_seeds; i0 += kThreads) {
+    const uint32_t i = i0 + threadIdx.x;
+    bool won = false;
+    uint32_t v = 0;
+    if (i < n_seeds) {
+      v = seeds[i];
+      if (__ldg(&A.cc[v]) == seg) won = atomicCAS(&A.claim[v], kValid, 0ull) == kValid;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, won);
+    uint32_t base = 0;
+    if (lane == 0 && m) base = atomicAdd(&S.n_next, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (won) { const uint32_t p = base + __popc(m & ltmask); fvA[p] = v; fsA[p] = i; }
+  }
+  __syncthreads();
+  uint32_t n_cur = S.n_next, total = n_cur;
+  uint32_t *fv = fvA, *fs = fsA, *nv = fvB, *ns = fsB;
+  while (n_cur > 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) S.n_next = 0;
+    __syncthreads();
+    for (uint32_t it = warp; it < n_cur; it += kWarps) {
+      const uint32_t u = fv[it], s = fs[it];
+      const uint32_t o = seeds[s];
+      const float r = __fadd_rn(__fmul_rn(scale, __ldg(&A.dbf[o])), konst);
+      int x, y, z, ox, oy, oz;
+      unravel(u, A.d, x, y, z);
+      unravel(o, A.d, ox, oy, oz);
+      const int nx = x + dx, ny = y + dy, nz = z + dz;
+      bool push = false;
+      uint32_t v = 0;
+      if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
+        v = (uint32_t)((int64_t)u + off);
+        if (__ldg(&A.cc[v]) == seg && __ldcg(&A.claim[v]) != 0ull) {
+          // float32 expression of dijkstra_invalidation.hpp:49-52,319-323
+          const float a = __fmul_rn(A.wx, (float)(nx - ox)), b = __fmul_rn(A.wy, (float)(ny - oy)),
+                      c = __fmul_rn(A.wz, (float)(nz - oz));
+          const float dd = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));
+          if (dd < r) {
+            const unsigned long long cand = ((unsigned long long)__float_as_uint(dd) << 32) | s;
+            const unsigned long long old = atomicMin(&A.claim[v], cand);
+            push = old == kValid;
+          }
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, push);
+      if (m) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&S.n_next, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (push) nv[base + __popc(m & ltmask)] = v;
+      }
+    }
+    __syncthreads();
+    const uint32_t n_next = S.n_next;
+    // end of round: winners become claimed (0) and carry their owner into the next frontier
+    for (uint32_t i = threadIdx.x; i < n_next; i += kThreads) {
+      const uint32_t v = nv[i];
+      const unsigned long long c = __ldcg(&A.claim[v]);
+      ns[i] = (uint32_t)c;
+      A.claim[v] = 0ull;
+    }
+    total += n_next;
+    n_cur = n_next;
+    { uint32_t* t = fv; fv = nv; nv = t; t = fs; fs = ns; ns = t; }
+    __syncthreads();
+  }
+  return total;
+}
+
+// ---- the per-label conductor (trace.py:196-267) ----------------------------------------------------
+__device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, const Params& prm, Shared& S,
+                            uint32_t job) {
+  uint32_t* scr = P.scratch + 4ull * L.region_off;
+  uint32_t* r0 = scr;
+  uint32_t* r1 = scr + L.n_fg;
+  uint32_t* r2 = scr + 2ull * L.n_fg;
+  uint32_t* r3 = scr + 3ull * L.n_fg;
+  uint32_t* out = P.paths + L.path_off;
+  if (threadIdx.x == 0) {
+    S.bucket = prm.nbuckets - 1;
+    S.relax = 0; S.rounds = 0; S.invalidated = 0; S.scans = 0;
+    A.pdrf[L.root] = 0.0f;      // parents[root] = 0: the first rail (trace.py:220)
+  }
+  __syncthreads();
+  uint32_t valid = L.n_fg;
+  int32_t status = 0;
+  if (L.soma_mode) {            // one-off soma invalidation around the root (trace.py:160-168)
+    const uint32_t n = invalidate(A, L, &L.root, 1, prm.soma_scale, prm.soma_const, r0, r1, r2, r3, S);
+    valid -= min(valid, n);
+  }
+  uint32_t tb_n = L.tb_n, ta_n = L.ta_n;
+  uint32_t max_paths = (L.max_paths == 0xffffffffu) ? valid : L.max_paths;
+  uint32_t npaths = 0, used = 0;
+  if ((unsigned long long)tb_n + ta_n >= max_paths) max_paths = 0;  // trace.py:217-218: return []
+  while ((valid > 0 || tb_n > 0 || ta_n > 0) && npaths < max_paths) {
+    uint32_t target;
+    if (tb_n > 0) target = P.targets[L.tb_off + (--tb_n)];
+    else if (valid == 0) target = P.targets[L.ta_off + (--ta_n)];
+    else {
+      target = find_target(A, L, P, prm, S);
+      if (target == 0xffffffffu) { status = -10; break; }   // bookkeeping mismatch: valid > 0 but no valid voxel
+    }
+    if (used + 2 > L.path_cap) { status = B2T_ERR_CAPACITY; break; }
+    uint32_t* pout = out + used;
+    const uint32_t cap = L.path_cap - used - 1;
+    uint32_t len = railroad(A, L, target, r0, r1, r2, r3, pout, cap, S);
+    if (len > cap) { status = B2T_ERR_CAPACITY; break; }
+    if (L.soma_mode) {
+      // keep path[:1] + points farther than soma_radius from the root; float64, uint32 wrap
+      int rx, ry, rz;
+      unravel(L.root, A.d, rx, ry, rz);
+      if (threadIdx.x == 0) {
+        uint32_t k = 0;
+        r0[k++] = pout[0];
+        for (uint32_t i = 0; i < len; i++) {
+          int x, y, z;
+          unravel(pout[i], A.d, x, y, z);
+          const double ddx = (double)A.wx * (double)(uint32_t)(x - rx), ddy = (double)A.wy * (double)(uint32_t)(y - ry),
+                       ddz = (double)A.wz * (double)(uint32_t)(z - rz);
+          const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)), __dmul_rn(ddz, ddz)));
+          if (dist > (double)L.soma_radius) {
+            if (k < L.n_fg) r0[k] = pout[i];
+            k++;
+          }
+        }
+        S.red32[1] = k;
+      }
+      __syncthreads();
+      const uint32_t k = S.red32[1];
+      if (k > cap || k > L.n_fg) { status = B2T_ERR_CAPACITY; break; }
+      for (uint32_t i = threadIdx.x; i < k; i += kThreads) pout[i] = r0[i];
+      len = k;
+      __syncthreads();
+    }
+    if (valid > 0) {
+      const uint32_t n = invalidate(A, L, pout, len, prm.scale, prm.konst, r0, r1, r2, r3, S);
+      valid -= min(valid, n);
+      if (threadIdx.x == 0) S.invalidated += n;
+    }
+    for (uint32_t i = threadIdx.x; i < len; i += kThreads) A.pdrf[pout[i]] = 0.0f;   // trace.py:261-263
+    if (threadIdx.x == 0) pout[len] = 0xffffffffu;
+    used += len + 1;
+    npaths++;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    P.out_len[job] = used;
+    P.out_npaths[job] = npaths;
+    P.out_status[job] = status;
+    P.out_stats[4 * job + 0] = S.relax;
+    P.out_stats[4 * job + 1] = S.rounds;
+    P.out_stats[4 * job + 2] = S.invalidated;
+    P.out_stats[4 * job + 3] = S.scans;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads) trace_kernel(Arena A, const LabelDesc* __restrict__ descs, Pools P, Params prm) {
+  __shared__ Shared S;
+  __shared__ LabelDesc L;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) S.job = atomicAdd(P.work_counter, 1u);
+    __syncthreads();
+    const uint32_t job = S.job;
+    if (job >= (uint32_t)prm.n_desc) return;
+    if (threadIdx.x == 0) L = descs[job];
+    __syncthreads();
+    trace_label(A, L, P, prm, S, job);
+  }
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI: the whole path loop for a batch of labels in one launch.
+// Replaces the body of kimimaro/trace.py:compute_paths (trace.py:196-267) and the native calls in
+// it: dijkstra3d.railroad, CachedTargetFinder.find_target, roll_invalidation_ball_inside_component.
+//   d_desc       n_desc records of 16 x u32/f32 (struct LabelDesc above, same field order)
+//   d_scratch    4 * sum(n_fg) u32;  d_paths: path pool;  d_targets: manual targets (linear indices)
+//   d_out_len / d_out_npaths / d_out_status: n_desc each; d_out_stats: 4 * n_desc; d_work_counter: 1 u32 (zeroed here)
+// =================================================================================================
+B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,
+                               uint32_t* d_stamp, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
+                               const void* d_desc, int n_desc, float scale, float konst, float soma_scale,
+                               float soma_const, int nbuckets, const uint64_t* d_keys, const uint32_t* d_hist,
+                               const uint32_t* d_cursor, uint32_t* d_scratch, uint32_t* d_paths,
+                               const uint32_t* d_targets, uint32_t* d_out_len, uint32_t* d_out_npaths,
+                               int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter, void* stream) {
+  static_assert(sizeof(LabelDesc) == 64, "LabelDesc must stay 16 x 4 bytes (mirrored in kimimaro_b200/engine.py)");
+  B2T_REQUIRE(sx > 0 && sy > 0 && sz > 0 && (double)sx * sy * sz < 4294967295.0, "bad volume shape");
+  if (n_desc <= 0) return B2T_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena A;
+  A.cc = d_cc; A.dbf = d_dbf; A.pdrf = d_pdrf; A.dist = d_dist;
+  A.claim = reinterpret_cast<unsigned long long*>(d_claim); A.stamp = d_stamp;
+  A.d = Dims{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
+  A.wx = wx; A.wy = wy; A.wz = wz;
+  Pools P;
+  P.keys = reinterpret_cast<const unsigned long long*>(d_keys); P.hist = d_hist; P.cursor = d_cursor;
+  P.scratch = d_scratch; P.paths = d_paths; P.targets = d_targets; P.out_len = d_out_len; P.out_npaths = d_out_npaths;
+  P.out_status = d_out_status; P.out_stats = d_out_stats; P.work_counter = d_work_counter;
+  Params prm{scale, konst, soma_scale, soma_const, nbuckets, n_desc};
+  B2T_CUDA_TRY(cudaMemsetAsync(d_work_counter, 0, sizeof(uint32_t), st));
+  int dev = 0, sms = 0, per_sm = 0;
+  B2T_CUDA_TRY(cudaGetDevice(&dev));
+  B2T_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  B2T_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel, kThreads, 0));
+  int blocks = sms * (per_sm > 0 ? per_sm : 1);
+  if (blocks > n_desc) blocks = n_desc;
+  trace_kernel<<<blocks, kThreads, 0, st>>>(A, reinterpret_cast<const LabelDesc*>(d_desc), P, prm);
+  B2T_CUDA_TRY(cudaGetLastError());
+  return B2T_OK;
+}

@@ -1,0 +1,373 @@
+"""
+Host side of the B200 TEASAR engine: the conductor that kimimaro/intake.py:58-221,434-593 and
+kimimaro/trace.py:36-194 are in the reference, re-hosted so that every per-voxel step is one
+launch over the WHOLE volume / ALL labels (field.cu) and the sequential path loop is one
+device-resident launch (trace.cu).  torch tensors are device buffers only.
+
+Data layout in HBM (per voxel of the [sx,sy,sz] Fortran-ordered volume, V voxels):
+  labels  L bytes   input ids                      cc      4 B  connected-component id (0 = background)
+  dbf     4 B  distance-to-boundary (K1)           dist    4 B  DAF, then railroad scratch (+inf at rest)
+  pdrf    4 B  penalised distance field            claim   8 B  ~0 = valid; 0 = invalidated; else pending (dist,seed)
+  stamp   4 B  frontier de-duplication flags
+plus per foreground voxel: keys 8 B (DAF-bucketed target list), 16 B of queue scratch, path pool.
+"""
+import ctypes
+import time
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from . import _lib, border
+from ._lib import B2TError, c_f32, c_i64, c_int, c_vp, check, lib, stream_ptr
+from .ops import edt, to_device_f
+from .skeleton import Skeleton
+
+c_u32 = ctypes.c_uint32
+c_u64 = ctypes.c_uint64
+
+_lib.declare("b2t_label_stats", [c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp])
+_lib.declare("b2t_edf_multi", [c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_u32, c_f32, c_u32,
+                               c_vp, c_vp, c_vp, c_u64, c_vp, c_vp])
+_lib.declare("b2t_field_argmax", [c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp])
+_lib.declare("b2t_pdrf_and_buckets", [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp,
+                                      c_vp, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp])
+_lib.declare("b2t_trace_batch", [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32,
+                                 c_vp, c_int, c_f32, c_f32, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp])
+_lib.declare("b2t_ccl26_roots", [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp])
+_lib.declare("b2t_ccl_relabel", [c_vp, c_vp, c_u64, c_vp])
+_lib.declare("b2t_gather_paths", [c_vp, c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp])
+
+NBUCKETS = 256
+NONE = 0xFFFFFFFF
+
+# trace()'s own defaults (kimimaro/trace.py:38-43), which differ from DEFAULT_TEASAR_PARAMS
+TRACE_DEFAULTS = dict(scale=10, const=10, soma_detection_threshold=1100, soma_acceptance_threshold=4000,
+                      pdrf_scale=5000, pdrf_exponent=16, soma_invalidation_scale=0.5, soma_invalidation_const=0,
+                      max_paths=None)
+
+
+def _p(t):
+  return c_vp(t.data_ptr()) if t is not None else c_vp(0)
+
+
+def _dev(a, dtype=None):
+  t = torch.from_numpy(np.ascontiguousarray(a))
+  return t.cuda(non_blocking=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# device-side steps
+# ------------------------------------------------------------------------------------------------
+def connected_components(d_labels, shape):
+  """cc3d.connected_components(labels) (utility.py:77): returns (cc int32 [V], n_cc)."""
+  sx, sy, sz = shape
+  V = sx * sy * sz
+  parent = torch.empty(V, dtype=torch.int32, device=d_labels.device)
+  is_root = torch.empty(V, dtype=torch.uint8, device=d_labels.device)
+  check(lib().b2t_ccl26_roots(_p(d_labels), c_int(d_labels.element_size()), c_i64(sx), c_i64(sy), c_i64(sz),
+                              _p(parent), _p(is_root), stream_ptr()), "b2t_ccl26_roots")
+  rank = torch.cumsum(is_root, 0, dtype=torch.int32)       # plumbing: rank of every root in raster order
+  n_cc = int(rank[-1].item()) if V > 0 else 0
+  del is_root
+  check(lib().b2t_ccl_relabel(_p(parent), _p(rank), c_u64(V), stream_ptr()), "b2t_ccl_relabel")
+  return parent, n_cc
+
+
+def label_stats(d_cc, d_dbf, shape, n):
+  sx, sy, sz = shape
+  dev = d_cc.device
+  count = torch.empty(n + 1, dtype=torch.int32, device=dev)
+  bbox = torch.empty((n + 1) * 6, dtype=torch.int32, device=dev)
+  dbfmax = torch.empty(n + 1, dtype=torch.float32, device=dev)
+  first = torch.empty(n + 1, dtype=torch.int32, device=dev)
+  check(lib().b2t_label_stats(_p(d_cc), _p(d_dbf), c_i64(sx), c_i64(sy), c_i64(sz), c_u32(n), _p(count), _p(bbox),
+                              _p(dbfmax), _p(first), stream_ptr()), "b2t_label_stats")
+  return count, bbox, dbfmax, first
+
+
+class Workspace:
+  """Per-volume work fields (allocated once per skeletonize call, reused by both field sweeps)."""
+  def __init__(self, V, n_fg, dev):
+    self.V, self.n_fg = V, n_fg
+    self.dist = torch.empty(V, dtype=torch.float32, device=dev)
+    self.stamp = torch.empty(V, dtype=torch.int32, device=dev)
+    self.queue = torch.empty(2 * max(n_fg, 1), dtype=torch.int32, device=dev)
+    self.ctrl = torch.zeros(16, dtype=torch.int32, device=dev)
+
+
+def edf_multi(d_cc, shape, anisotropy, d_sources, n_sources, ws, free_space=None):
+  """dijkstra3d.euclidean_distance_field for all participating labels at once -> ws.dist."""
+  sx, sy, sz = shape
+  ws.dist.fill_(float("inf"))
+  ws.stamp.zero_()
+  fsr, fss = (0.0, 0) if free_space is None else (float(free_space[0]), int(free_space[1]))
+  check(lib().b2t_edf_multi(_p(d_cc), c_i64(sx), c_i64(sy), c_i64(sz), c_f32(anisotropy[0]), c_f32(anisotropy[1]),
+                            c_f32(anisotropy[2]), _p(d_sources), c_u32(n_sources), c_f32(fsr), c_u32(fss),
+                            _p(ws.dist), _p(ws.stamp), _p(ws.queue), c_u64(ws.queue.numel() // 2), _p(ws.ctrl),
+                            stream_ptr()), "b2t_edf_multi")
+
+
+def field_argmax(d_cc, d_dist, shape, n):
+  """per label (max finite distance, smallest index attaining it) -> (values f32[n+1], index i64[n+1])."""
+  sx, sy, sz = shape
+  best = torch.empty(n + 1, dtype=torch.int64, device=d_cc.device)
+  check(lib().b2t_field_argmax(_p(d_cc), _p(d_dist), c_i64(sx), c_i64(sy), c_i64(sz), c_u32(n), _p(best),
+                               stream_ptr()), "b2t_field_argmax")
+  b = best.cpu().numpy().view(np.uint64)
+  vals = (b >> np.uint64(32)).astype(np.uint32).view(np.float32)
+  idx = (np.uint64(0xFFFFFFFF) - (b & np.uint64(0xFFFFFFFF))).astype(np.int64)
+  idx[b == 0] = -1
+  return vals, idx
+
+
+# ------------------------------------------------------------------------------------------------
+# fix_borders (intake.py:544-585)
+# ------------------------------------------------------------------------------------------------
+def compute_border_targets(d_cc, shape, anisotropy):
+  sx, sy, sz = shape
+  cc3 = d_cc.view(sz, sy, sx)
+  faces = (
+    (cc3[0, :, :], (sx, sy), (0, 1), lambda x, y: (x, y, 0)),
+    (cc3[sz - 1, :, :], (sx, sy), (0, 1), lambda x, y: (x, y, sz - 1)),
+    (cc3[:, 0, :], (sx, sz), (0, 2), lambda x, z: (x, 0, z)),
+    (cc3[:, sy - 1, :], (sx, sz), (0, 2), lambda x, z: (x, sy - 1, z)),
+    (cc3[:, :, 0], (sy, sz), (1, 2), lambda y, z: (0, y, z)),
+    (cc3[:, :, sx - 1], (sy, sz), (1, 2), lambda y, z: (sx - 1, y, z)),
+  )
+  target_list = defaultdict(set)
+  for face, pshape, dims, rotatefn in faces:
+    wx, wy = anisotropy[dims[0]], anisotropy[dims[1]]
+    plane = face.contiguous().view(-1)                     # flat Fortran order of the 2-D plane
+    if not bool(plane.any()):
+      continue
+    cc_plane, n = connected_components(plane, (pshape[0], pshape[1], 1))   # 8-connected in 2-D
+    dt_plane = edt(cc_plane.view(torch.int32), pshape, anisotropy=(wx, wy), black_border=True)
+    h_plane = plane.cpu().numpy().reshape(pshape, order="F")
+    h_cc = cc_plane.cpu().numpy().reshape(pshape, order="F")
+    h_dt = dt_plane.cpu().numpy().reshape(pshape, order="F")
+    plane_targets = border.find_border_targets(h_dt, h_cc, wx, wy)
+    remap = border.plane_mapping(h_plane, h_cc)
+    for label, pt in plane_targets.items():
+      target_list[remap[label]].add(rotatefn(int(pt[0]), int(pt[1])))
+  out = {}
+  for label, pts in target_list.items():
+    out[label] = np.array(list(pts), dtype=np.uint32)
+  return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the trace of all labels of one arena
+# ------------------------------------------------------------------------------------------------
+DESC_DTYPE = np.dtype([
+  ("segid", "<u4"), ("root", "<u4"), ("n_fg", "<u4"), ("region_off", "<u4"), ("path_off", "<u4"),
+  ("path_cap", "<u4"), ("tb_off", "<u4"), ("tb_n", "<u4"), ("ta_off", "<u4"), ("ta_n", "<u4"),
+  ("max_paths", "<u4"), ("soma_mode", "<u4"), ("soma_radius", "<f4"), ("bucket_row", "<u4"),
+  ("pad0", "<u4"), ("pad1", "<u4"),
+])
+assert DESC_DTYPE.itemsize == 64
+
+
+def compute_M(dbf_max):
+  """M = f32(1 / dbf_max ** 1.01) with the reference's numpy expression (trace.py:335-336)."""
+  f = lambda x: np.float32(x)
+  with np.errstate(all="ignore"):
+    return f(1 / (np.float32(dbf_max) ** 1.01))
+
+
+def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=None):
+  """
+  jobs: list of dicts {segid, n_fg, root (linear index or None), targets_before [linear...],
+        targets_after [...], dbf_max (np.float32), soma_mode, soma_radius, free_space}
+  n_rows: number of rows of the (label x bucket) tables minus one (= max cc id in this arena).
+  Returns (vox u32 [N] with 0xffffffff path terminators, radii f32 [N], seg_off int64 [n_jobs+1]).
+  """
+  sx, sy, sz = shape
+  V = sx * sy * sz
+  dev = d_cc.device
+  n_jobs = len(jobs)
+  L = lib()
+  tmark = time.perf_counter()
+
+  def lap(name):
+    nonlocal tmark
+    if timings is not None:
+      torch.cuda.synchronize()
+      now = time.perf_counter()
+      timings[name] = timings.get(name, 0.0) + (now - tmark)
+      tmark = now
+
+  n_fg_total = int(sum(j["n_fg"] for j in jobs))
+  ws = Workspace(V, n_fg_total, dev)
+
+  # ---- roots (trace.py:128-129, 291-308): one field sweep for every label that has no root yet ----
+  need = [j for j in jobs if j["root"] is None]
+  if need:
+    src = _dev(np.array([j["first"] for j in need], dtype=np.uint32).view(np.int32))
+    edf_multi(d_cc, shape, anisotropy, src, len(need), ws)
+    _, idx = field_argmax(d_cc, ws.dist, shape, n_rows)
+    for j in need:
+      j["root"] = int(idx[j["segid"]])
+  lap("find_root")
+
+  # ---- DAF from the roots, all labels at once (trace.py:139-145) ----
+  soma_jobs = [j for j in jobs if j.get("free_space")]
+  assert len(soma_jobs) <= 1 or n_jobs == len(soma_jobs), "free-space seeding is per arena"
+  src = _dev(np.array([j["root"] for j in jobs], dtype=np.uint32).view(np.int32))
+  if soma_jobs and n_jobs == 1:
+    edf_multi(d_cc, shape, anisotropy, src, 1, ws, free_space=(soma_jobs[0]["free_space"], jobs[0]["root"]))
+  else:
+    edf_multi(d_cc, shape, anisotropy, src, n_jobs, ws)
+  maxdaf, target_idx = field_argmax(d_cc, ws.dist, shape, n_rows)
+  lap("daf")
+
+  # ---- PDRF + work fields + target buckets (trace.py:147-148, 315-356; pyx:995-1006) ----
+  M = np.zeros(n_rows + 1, dtype=np.float32)
+  inv = np.zeros(n_rows + 1, dtype=np.float32)
+  active = np.zeros(n_rows + 1, dtype=np.uint8)
+  for j in jobs:
+    s = j["segid"]
+    M[s] = compute_M(j["dbf_max"])
+    md = np.float32(maxdaf[s])
+    with np.errstate(all="ignore"):
+      inv[s] = (1 / md) if md != 0 else np.float32(0)
+    active[s] = 1
+  d_M, d_inv, d_active = _dev(M), _dev(inv), _dev(active)
+  ntab = (n_rows + 1) * NBUCKETS
+  hist = torch.empty(ntab + 1, dtype=torch.int32, device=dev)
+  cursor = torch.empty(ntab + 1, dtype=torch.int32, device=dev)
+  keys = torch.empty(max(n_fg_total, 1), dtype=torch.int64, device=dev)
+  pdrf = torch.empty(V, dtype=torch.float32, device=dev)
+  claim = torch.empty(V, dtype=torch.int64, device=dev)
+  flag = torch.empty(V, dtype=torch.uint8, device=dev)
+  check(L.b2t_pdrf_and_buckets(_p(d_cc), _p(d_dbf), _p(ws.dist), _p(pdrf), _p(claim), _p(flag), c_i64(sx), c_i64(sy),
+                               c_i64(sz), c_u32(n_rows), _p(d_M), _p(d_inv), _p(d_active),
+                               c_f32(params["pdrf_scale"]), c_f32(params["pdrf_exponent"]), c_int(NBUCKETS),
+                               _p(hist), _p(cursor), _p(keys), stream_ptr()), "b2t_pdrf_and_buckets")
+  del flag
+  lap("pdrf")
+
+  # ---- the path loop for every label (trace.py:196-267) ----
+  desc = np.zeros(n_jobs, dtype=DESC_DTYPE)
+  targets = []
+  region = 0
+  path_off = 0
+  order = sorted(range(n_jobs), key=lambda i: -jobs[i]["n_fg"])      # largest labels first
+  for slot, i in enumerate(order):
+    j = jobs[i]
+    tb = list(j["targets_before"])
+    ta = list(j["targets_after"])
+    if not j["soma_mode"] and len(tb) == 0:
+      tb.append(int(target_idx[j["segid"]]))                          # trace.py:171-172
+    d = desc[slot]
+    d["segid"] = j["segid"]; d["root"] = j["root"]; d["n_fg"] = j["n_fg"]
+    d["region_off"] = region; region += j["n_fg"]
+    cap = 2 * j["n_fg"] + 2 * (len(tb) + len(ta)) + 64
+    d["path_off"] = path_off; d["path_cap"] = cap; path_off += cap
+    d["tb_off"] = len(targets); d["tb_n"] = len(tb); targets.extend(tb)
+    d["ta_off"] = len(targets); d["ta_n"] = len(ta); targets.extend(ta)
+    d["max_paths"] = NONE if params["max_paths"] is None else int(params["max_paths"])
+    d["soma_mode"] = 1 if j["soma_mode"] else 0
+    d["soma_radius"] = np.float32(j.get("soma_radius", 0.0))
+    d["bucket_row"] = j["segid"]
+  assert path_off < 2 ** 32 and 4 * region < 2 ** 34
+  d_desc = _dev(desc.view(np.uint8))
+  d_targets = _dev(np.array(targets + [0], dtype=np.uint32).view(np.int32))
+  scratch = torch.empty(4 * max(region, 1), dtype=torch.int32, device=dev)
+  paths = torch.empty(max(path_off, 1), dtype=torch.int32, device=dev)
+  out_len = torch.zeros(n_jobs, dtype=torch.int32, device=dev)
+  out_np = torch.zeros(n_jobs, dtype=torch.int32, device=dev)
+  out_status = torch.zeros(n_jobs, dtype=torch.int32, device=dev)
+  out_stats = torch.zeros(4 * n_jobs, dtype=torch.int32, device=dev)
+  counter = torch.zeros(1, dtype=torch.int32, device=dev)
+  ws.stamp.zero_()
+  check(L.b2t_trace_batch(_p(d_cc), _p(d_dbf), _p(pdrf), _p(ws.dist), _p(claim), _p(ws.stamp), c_i64(sx), c_i64(sy),
+                          c_i64(sz), c_f32(anisotropy[0]), c_f32(anisotropy[1]), c_f32(anisotropy[2]), _p(d_desc),
+                          c_int(n_jobs), c_f32(params["scale"]), c_f32(params["const"]),
+                          c_f32(params["soma_invalidation_scale"]), c_f32(params["soma_invalidation_const"]),
+                          c_int(NBUCKETS), _p(keys), _p(hist), _p(cursor), _p(scratch), _p(paths), _p(d_targets),
+                          _p(out_len), _p(out_np), _p(out_status), _p(out_stats), _p(counter), stream_ptr()),
+        "b2t_trace_batch")
+  h_len = out_len.cpu().numpy().astype(np.int64)
+  h_status = out_status.cpu().numpy()
+  lap("paths")
+  if (h_status != 0).any():
+    bad = int(np.flatnonzero(h_status != 0)[0])
+    raise B2TError(f"trace kernel reported status {int(h_status[bad])} for cc label {int(desc[bad]['segid'])}")
+
+  # ---- compact the path pool and fetch radii (trace.py:186-187) ----
+  seg_off = np.zeros(n_jobs + 1, dtype=np.int64)
+  np.cumsum(h_len, out=seg_off[1:])
+  total = int(seg_off[-1])
+  d_vox = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+  d_rad = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+  d_srcoff = _dev(desc["path_off"].astype(np.uint32).view(np.int32))
+  d_dstoff = _dev(seg_off[:-1].astype(np.uint64).view(np.int64))
+  check(L.b2t_gather_paths(_p(paths), _p(d_srcoff), _p(out_len), _p(d_dstoff), c_u32(n_jobs), _p(d_dbf), _p(d_vox),
+                           _p(d_rad), stream_ptr()), "b2t_gather_paths")
+  vox = d_vox.cpu().numpy().view(np.uint32)[:total]
+  rad = d_rad.cpu().numpy()[:total]
+  lap("gather")
+  stats = {"stats": out_stats.cpu().numpy().reshape(-1, 4), "npaths": out_np.cpu().numpy(),
+           "segids": desc["segid"].copy()}
+  return vox, rad, seg_off, desc["segid"].astype(np.int64), stats
+
+
+# ------------------------------------------------------------------------------------------------
+# skeleton assembly (trace.py:182-192, intake.py:509-517, 587-593) for all labels at once
+# ------------------------------------------------------------------------------------------------
+def assemble(vox, rad, seg_off, seg_ids, shape, anisotropy, offset=(0, 0, 0)):
+  """Returns {cc segid: (vertices f32 [N,3] physical, edges u32 [M,2], radii f32 [N])}."""
+  sx, sy, sz = shape
+  n = vox.size
+  out = {}
+  if n == 0:
+    return out
+  lab_of = np.repeat(np.arange(seg_ids.size, dtype=np.int64), np.diff(seg_off))
+  is_vtx = vox != NONE
+  v = vox.astype(np.int64)
+  z = v // (sx * sy)
+  r = v - z * (sx * sy)
+  y = r // sx
+  x = r - y * sx
+  # lexicographic (x,y,z) order per label == np.unique(vertices, axis=0) of consolidate()
+  ckey = (x * sy + y) * sz + z
+  gkey = lab_of * np.int64(sx * sy * sz) + ckey
+  vi = np.flatnonzero(is_vtx)
+  uniq, first, inverse = np.unique(gkey[vi], return_index=True, return_inverse=True)
+  uid = np.full(n, -1, dtype=np.int64)
+  uid[vi] = inverse
+  # edges between consecutive entries of the same path
+  a = np.flatnonzero(is_vtx[:-1] & is_vtx[1:])
+  e0, e1 = uid[a], uid[a + 1]
+  lo, hi = np.minimum(e0, e1), np.maximum(e0, e1)
+  keep = lo != hi
+  nu = uniq.size
+  ekey = np.unique(lo[keep] * np.int64(nu) + hi[keep])
+  ea, eb = ekey // nu, ekey % nu
+  # drop vertices without edges (remove_disconnected_vertices)
+  used = np.zeros(nu, dtype=bool)
+  used[ea] = True
+  used[eb] = True
+  newid = np.cumsum(used) - 1
+  ulab = lab_of[vi[first]]
+  ux, uy, uz = x[vi[first]], y[vi[first]], z[vi[first]]
+  urad = rad[vi[first]]
+  ulab_k, ux, uy, uz, urad = ulab[used], ux[used], uy[used], uz[used], urad[used]
+  ea, eb = newid[ea], newid[eb]
+  elab = ulab_k[ea] if ea.size else np.zeros(0, np.int64)
+  an = np.asarray(anisotropy, dtype=np.float32)
+  off = np.asarray(offset, dtype=np.float32)
+  verts = np.stack([ux, uy, uz], axis=1).astype(np.float32)
+  verts = np.multiply(verts + off, an, dtype=np.float32)           # intake.py:509-513
+  vstart = np.searchsorted(ulab_k, np.arange(seg_ids.size + 1))
+  estart = np.searchsorted(elab, np.arange(seg_ids.size + 1))
+  for k in range(seg_ids.size):
+    v0, v1 = vstart[k], vstart[k + 1]
+    if v1 == v0:
+      continue
+    e0_, e1_ = estart[k], estart[k + 1]
+    edges = np.stack([ea[e0_:e1_] - v0, eb[e0_:e1_] - v0], axis=1).astype(np.uint32)
+    out[int(seg_ids[k])] = (verts[v0:v1], edges, urad[v0:v1].astype(np.float32))
+  return out

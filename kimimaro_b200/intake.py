@@ -1,0 +1,322 @@
+"""
+kimimaro_b200.skeletonize -- drop-in for kimimaro.skeletonize (kimimaro/intake.py:58-143) with the
+per-label TEASAR hot path on a B200.  Same signature, same teasar_params dictionary, same result
+type ({segid: Skeleton}); no CPU fallback.
+
+Deviations from the reference, all explicit:
+  * parallel      one process drives one GPU and the device traces all labels concurrently, so the
+                  argument is accepted and ignored here; multi-GPU runs shard labels across
+                  processes (kimimaro_b200.distributed).
+  * fill_holes, fix_avocados, voxel_graph, fix_branching=False, CrackleArray input: not built yet
+                   -> NotImplementedError, never a silent CPU path.
+  * tie rules T1-T5 (oracle/oracle.c header) where the reference leaves ties to heap / sort internals.
+"""
+import ctypes
+import time
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+from ._lib import B2TError, check, lib, stream_ptr
+from .ops import edt
+from .skeleton import Skeleton
+
+c_vp, c_i64, c_u64, c_int = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int
+_lib.declare("b2t_fill_voids", [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_u64, c_vp, c_vp])
+
+
+class DimensionError(Exception):
+  pass
+
+
+DEFAULT_TEASAR_PARAMS = {       # kimimaro/intake.py:47-56
+  "scale": 1.5,
+  "const": 300,
+  "pdrf_scale": 100000,
+  "pdrf_exponent": 4,
+  "soma_acceptance_threshold": 3500,
+  "soma_detection_threshold": 750,
+  "soma_invalidation_const": 300,
+  "soma_invalidation_scale": 2,
+}
+
+_VIEW = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}
+_TVIEW = {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}
+
+
+def format_labels(labels, in_place):
+  """kimimaro/intake.py:315-342."""
+  labels = np.asarray(labels)
+  if not (in_place and labels.flags["F_CONTIGUOUS"]):
+    labels = np.copy(labels, order="F")
+  if labels.dtype == bool:
+    labels = labels.view(np.uint8)
+  original_shape = labels.shape
+  while labels.ndim < 3:
+    labels = labels[..., np.newaxis]
+  while labels.ndim > 3:
+    if labels.shape[-1] == 1:
+      labels = labels[..., 0]
+    else:
+      raise DimensionError(
+        "Input labels may be no more than three non-trivial dimensions. Got: {}".format(original_shape))
+  if labels.dtype.kind not in "iu":
+    raise TypeError("labels must be of integer or boolean type, got {}".format(labels.dtype))
+  return labels
+
+
+def _merge_params(teasar_params):
+  params = dict(engine.TRACE_DEFAULTS)
+  for k, v in teasar_params.items():
+    if k not in params:
+      # trace(**teasar_params) raises TypeError on unknown keywords (intake.py:503)
+      raise TypeError("trace() got an unexpected keyword argument '{}'".format(k))
+    params[k] = v
+  return params
+
+
+def _find_soma_root(d_dbf, shape, dbf_max):
+  """trace.py:269-289 on the device-resident DBF of a private arena."""
+  sx, sy, sz = shape
+  idx = torch.nonzero(d_dbf == float(dbf_max)).view(-1).cpu().numpy().astype(np.int64)
+  z = idx // (sx * sy)
+  r = idx - z * (sx * sy)
+  y = r // sx
+  x = r - y * sx
+  coords = np.stack([x, y, z], axis=1)
+  # np.where order is C order over (x,y,z): sort accordingly so that argmin's first-minimum matches
+  order = np.lexsort((coords[:, 2], coords[:, 1], coords[:, 0]))
+  coords = coords[order]
+  com = np.asarray(coords.astype(np.float64).sum(axis=0) / float(coords.shape[0]), dtype=np.float32)
+  root = np.argmin(np.sum((coords - com) ** 2, axis=1))
+  return tuple(coords[root].astype(np.uint32))
+
+
+def _private_arena(d_cc3, d_dbf3, segid, bbox, anisotropy, params, root, targets_before, targets_after,
+                   timings):
+  """A label whose DBF exceeds soma_detection_threshold (trace.py:108-127): crop, fill its voids,
+  redo the EDT on the crop if anything was filled, then trace it in its own arena."""
+  x0, y0, z0, x1, y1, z1 = bbox
+  shape = (x1 - x0 + 1, y1 - y0 + 1, z1 - z0 + 1)
+  V = shape[0] * shape[1] * shape[2]
+  dev = d_cc3.device
+  crop = d_cc3[z0:z1 + 1, y0:y1 + 1, x0:x1 + 1]
+  mask = (crop == segid).to(torch.uint8).contiguous().view(-1)
+  reach = torch.empty(V, dtype=torch.int32, device=dev)
+  queue = torch.empty(2 * V, dtype=torch.int32, device=dev)
+  ctrl = torch.zeros(16, dtype=torch.int32, device=dev)
+  check(lib().b2t_fill_voids(c_vp(mask.data_ptr()), c_i64(shape[0]), c_i64(shape[1]), c_i64(shape[2]),
+                             c_vp(reach.data_ptr()), c_vp(queue.data_ptr()), c_u64(V), c_vp(ctrl.data_ptr()),
+                             stream_ptr()), "b2t_fill_voids")
+  filled = int(ctrl[5].item())
+  del reach, queue
+  if filled > 0:
+    dbf = edt(mask, shape, anisotropy, black_border=bool(mask.all().item()))
+  else:
+    dbf = torch.where(mask.view(shape[2], shape[1], shape[0]) != 0,
+                      d_dbf3[z0:z1 + 1, y0:y1 + 1, x0:x1 + 1], torch.zeros((), device=dev)).contiguous().view(-1)
+  dbf_max = np.float32(dbf.max().item())
+  soma_mode = bool(dbf_max > params["soma_acceptance_threshold"])
+  off = np.array([x0, y0, z0], dtype=np.int64)
+
+  def local(pt):
+    p = np.asarray(pt, dtype=np.int64) - off
+    return int(p[0] + shape[0] * (p[1] + shape[1] * p[2]))
+
+  tb = [local(t) for t in targets_before]
+  ta = [local(t) for t in targets_after]
+  job = {"segid": 1, "n_fg": int(mask.sum().item()), "dbf_max": dbf_max, "soma_mode": soma_mode,
+         "targets_before": tb, "targets_after": ta, "root": None, "first": None}
+  if soma_mode:
+    if root is not None:
+      tb.insert(0, local(root))                               # trace.py:124-125
+    r = _find_soma_root(dbf, shape, dbf_max)
+    rlin = int(r[0]) + shape[0] * (int(r[1]) + shape[1] * int(r[2]))
+    job["root"] = rlin
+    # soma_radius = dbf_max * soma_invalidation_scale + soma_invalidation_const  (trace.py:127)
+    job["soma_radius"] = np.float32(dbf_max * params["soma_invalidation_scale"] + params["soma_invalidation_const"])
+    job["free_space"] = float(dbf[rlin].item())               # trace.py:134
+  elif root is not None:
+    job["root"] = local(root)
+  else:
+    job["first"] = int(torch.nonzero(mask)[0].item())         # first_label (pyx:307-326)
+  cc1 = mask.to(torch.int32)
+  vox, rad, seg_off, seg_ids, stats = engine.trace_arena(cc1, dbf, shape, anisotropy, [job], params, 1, timings)
+  res = engine.assemble(vox, rad, seg_off, seg_ids, shape, anisotropy, offset=(x0, y0, z0))
+  return res.get(1), stats
+
+
+def skeletonize(
+  all_labels, teasar_params=DEFAULT_TEASAR_PARAMS, anisotropy=(1, 1, 1),
+  object_ids=None, dust_threshold=1000,
+  progress=True, fix_branching=True, in_place=False,
+  fix_borders=True, parallel=1, parallel_chunk_size=100,
+  extra_targets_before=[], extra_targets_after=[],
+  fill_holes=False, fix_avocados=False,
+  voxel_graph=None, timings=None, label_subset=None, device_labels=None,
+):
+  """
+  Skeletonize all non-zero labels in a 2D or 3D image (kimimaro/intake.py:58-143).
+  Returns { segid: Skeleton } with vertices in physical units (space='physical').
+
+  Extra keyword arguments (not in the reference): timings (dict filled with per-phase seconds),
+  label_subset (callable(list of cc ids) -> list: used by the multi-GPU launcher to shard labels),
+  device_labels (a flat Fortran-ordered CUDA tensor already holding the volume: skips the H2D copy).
+  """
+  if fill_holes or fix_avocados or voxel_graph is not None or not fix_branching:
+    raise NotImplementedError(
+      "fill_holes / fix_avocados / voxel_graph / fix_branching=False are not built yet in kimimaro_b200 "
+      "(SURVEY.md 8f row N4); there is no CPU fallback")
+  _lib.require_device()
+  params = _merge_params(teasar_params)
+  anisotropy = np.array(anisotropy, dtype=np.float32)
+  an = tuple(float(a) for a in anisotropy)
+  t_all = time.perf_counter()
+  tm = timings if timings is not None else None
+
+  def lap(name, t0):
+    if tm is not None:
+      torch.cuda.synchronize()
+      tm[name] = tm.get(name, 0.0) + time.perf_counter() - t0
+    return time.perf_counter()
+
+  t0 = time.perf_counter()
+  if device_labels is not None:
+    shape = tuple(int(s) for s in all_labels)                 # all_labels carries the shape in this mode
+    while len(shape) < 3:
+      shape = shape + (1,)
+    d_labels = device_labels
+    size = int(np.prod(shape))
+  else:
+    all_labels = format_labels(all_labels, in_place=in_place)
+    shape = all_labels.shape
+    size = all_labels.size
+    if size <= dust_threshold:
+      return {}
+    flat = all_labels.reshape(-1, order="F")
+    d_labels = torch.from_numpy(flat.view(_VIEW[flat.dtype.itemsize])).cuda(non_blocking=True)
+  if size <= dust_threshold:
+    return {}
+  if d_labels.dtype in (torch.uint16, torch.uint32, torch.uint64):
+    d_labels = d_labels.view(_TVIEW[d_labels.element_size()])
+  sx, sy, sz = shape
+  V = size
+  t0 = lap("h2d", t0)
+
+  if object_ids is not None:                                   # apply_object_mask (intake.py:519-535)
+    ids = torch.as_tensor(np.asarray(object_ids).astype(np.int64), device=d_labels.device).to(d_labels.dtype)
+    d_labels = torch.where(torch.isin(d_labels, ids), d_labels, torch.zeros((), dtype=d_labels.dtype,
+                                                                           device=d_labels.device))
+  nz = d_labels != 0
+  if not bool(nz.any().item()):
+    return {}
+  black_border = bool(nz.all().item()) and bool((d_labels == d_labels[0]).all().item())   # minlabel == maxlabel
+  del nz
+
+  # ---- preamble: connected components, EDT, per-label statistics ----
+  d_cc, n_cc = engine.connected_components(d_labels, shape)
+  t0 = lap("ccl", t0)
+  d_dbf = edt(d_cc, shape, an, black_border)
+  t0 = lap("edt", t0)
+  count, bbox, dbfmax, first = engine.label_stats(d_cc, d_dbf, shape, n_cc)
+  h_count = count.cpu().numpy()
+  h_bbox = bbox.cpu().numpy().reshape(-1, 6)
+  h_dbfmax = dbfmax.cpu().numpy()
+  h_first = first.cpu().numpy().view(np.uint32).astype(np.int64)
+  # remapping: original label at the first voxel of every component (get_mapping, pyx:490-525)
+  gather_idx = torch.as_tensor(np.clip(h_first, 0, V - 1), device=d_labels.device)
+  h_orig = d_labels[gather_idx].cpu().numpy()
+  if h_orig.dtype.kind == "i" and all_labels is not None and device_labels is None and all_labels.dtype.kind == "u":
+    h_orig = h_orig.view(all_labels.dtype)
+  t0 = lap("stats", t0)
+
+  cc_segids = [int(s) for s in np.flatnonzero(h_count > dust_threshold) if s != 0]
+  if label_subset is not None:
+    cc_segids = list(label_subset(cc_segids, h_count))
+
+  def points_to_labels(pts):
+    mapping = defaultdict(list)
+    if len(pts) == 0:
+      return mapping
+    pa = np.asarray(pts, dtype=np.int64).reshape(-1, 3)
+    lin = pa[:, 0] + sx * (pa[:, 1] + sy * pa[:, 2])
+    labs = d_cc[torch.as_tensor(lin, device=d_cc.device)].cpu().numpy()
+    for pt, l in zip(pa.tolist(), labs.tolist()):
+      mapping[int(l)].append(tuple(pt))
+    return mapping
+  extra_before = points_to_labels(extra_targets_before)
+  extra_after = points_to_labels(extra_targets_after)
+
+  border_targets = {}
+  if fix_borders:
+    border_targets = engine.compute_border_targets(d_cc, shape, anisotropy)
+  t0 = lap("border_targets", t0)
+
+  # ---- per label arguments of trace() (intake.py:445-504) ----
+  jobs, private = [], []
+  for segid in cc_segids:
+    x0, y0, z0, x1, y1, z1 = (int(v) for v in h_bbox[segid])
+    if (x1 - x0 + 1) * (y1 - y0 + 1) * (z1 - z0 + 1) <= 1:
+      continue
+    tb, ta, root = [], [], None
+    bt = border_targets.get(segid)
+    if bt is not None and len(bt) > 0:
+      tb = [tuple(int(v) for v in p) for p in bt.tolist()]
+      root = tb.pop()                                           # intake.py:484-486
+    if segid in extra_before:
+      tb.extend(extra_before[segid])
+    if segid in extra_after:
+      ta.extend(extra_after[segid])
+    if h_dbfmax[segid] > params["soma_detection_threshold"]:
+      private.append((segid, (x0, y0, z0, x1, y1, z1), root, tb, ta))
+      continue
+    lin = lambda p: int(p[0]) + sx * (int(p[1]) + sy * int(p[2]))
+    jobs.append({"segid": segid, "n_fg": int(h_count[segid]), "dbf_max": np.float32(h_dbfmax[segid]),
+                 "soma_mode": False, "root": None if root is None else lin(root), "first": int(h_first[segid]),
+                 "targets_before": [lin(p) for p in tb], "targets_after": [lin(p) for p in ta]})
+
+  results = {}
+  stats_all = []
+  if jobs:
+    vox, rad, seg_off, seg_ids, stats = engine.trace_arena(d_cc, d_dbf, shape, an, jobs, params, n_cc, tm)
+    t0 = time.perf_counter()
+    results.update(engine.assemble(vox, rad, seg_off, seg_ids, shape, anisotropy))
+    stats_all.append(stats)
+    t0 = lap("assemble", t0)
+  if private:
+    d_cc3 = d_cc.view(sz, sy, sx)
+    d_dbf3 = d_dbf.view(sz, sy, sx)
+    for segid, bb, root, tb, ta in private:
+      t0 = time.perf_counter()
+      ptm = {} if tm is not None else None
+      res, stats = _private_arena(d_cc3, d_dbf3, segid, bb, an, params, root, tb, ta, ptm)
+      if res is not None:
+        results[segid] = res
+      stats_all.append(stats)
+      if tm is not None:
+        tm["soma"] = tm.get("soma", 0.0) + time.perf_counter() - t0
+        for k, v in ptm.items():
+          tm["soma_" + k] = tm.get("soma_" + k, 0.0) + v
+
+  # ---- Skeleton objects, merged per original id (intake.py:509-517, 587-593) ----
+  t0 = time.perf_counter()
+  transform = np.array([[an[0], 0, 0, 0], [0, an[1], 0, 0], [0, 0, an[2], 0]], dtype=np.float32)
+  by_orig = defaultdict(list)
+  for segid in sorted(results):
+    verts, edges, radii = results[segid]
+    if verts.shape[0] == 0 or edges.shape[0] == 0:
+      continue
+    orig = h_orig[segid].item()
+    by_orig[orig].append(Skeleton(verts, edges, radii, segid=orig, transform=transform, space="physical"))
+  out = {}
+  for orig, skels in by_orig.items():
+    out[orig] = skels[0] if len(skels) == 1 else Skeleton.simple_merge(skels).consolidate()
+  if tm is not None:
+    tm["finalize"] = tm.get("finalize", 0.0) + time.perf_counter() - t0
+    tm["total"] = time.perf_counter() - t_all
+    tm["n_cc"] = n_cc
+    tm["n_traced"] = len(jobs) + len(private)
+    tm["kernel_stats"] = stats_all
+  return out

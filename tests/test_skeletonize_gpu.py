@@ -1,0 +1,141 @@
+"""End-to-end parity of the CUDA path (kimimaro_b200.skeletonize, through the C ABI) with the CPU
+oracle (oracle/teasar.py) on the same inputs: vertex and edge arrays bit-exact, radii within 1e-4
+relative (BASELINE.json north_star).  Also the reference's own known-answer tests
+(automated_test.py:17-102, 116-199, 261-279) run against the CUDA path."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(res, ref, rtol=1e-4):
+  assert sorted(res.keys()) == sorted(ref.keys())
+  for k in ref:
+    a, b = res[k], ref[k]
+    assert a.vertices.shape == b["vertices"].shape, (k, a.vertices.shape, b["vertices"].shape)
+    assert np.array_equal(a.vertices, b["vertices"]), k
+    assert np.array_equal(a.edges, b["edges"]), k
+    np.testing.assert_allclose(a.radii, b["radii"], rtol=rtol)
+
+
+def _both(gpu, labels, **kw):
+  import kimimaro_b200
+  from oracle import teasar
+  res = kimimaro_b200.skeletonize(labels, progress=False, **kw)
+  ref = teasar.skeletonize(labels, **kw)
+  return res, ref
+
+
+def test_sphere_config0(gpu):
+  from tests.synth import sphere
+  res, ref = _both(gpu, sphere(64, 24))
+  assert len(res) == 1
+  _compare(res, ref)
+
+
+@pytest.mark.parametrize("seed,shape,n,an", [
+  (1, (96, 96, 64), 12, (16, 16, 40)),
+  (2, (128, 64, 48), 20, (1, 1, 1)),
+  (3, (64, 128, 96), 16, (4, 4, 40)),
+])
+def test_tubes_small(gpu, seed, shape, n, an):
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes(shape, n, seed=seed, anisotropy=an)
+  res, ref = _both(gpu, lab, anisotropy=an, dust_threshold=100)
+  assert len(ref) > 0
+  _compare(res, ref)
+
+
+def test_tubes_no_fix_borders(gpu):
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes((96, 96, 64), 10, seed=5)
+  res, ref = _both(gpu, lab, anisotropy=(16, 16, 40), dust_threshold=100, fix_borders=False)
+  _compare(res, ref)
+
+
+def test_small_params_many_paths(gpu):
+  # small invalidation radius -> many paths per label
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes((96, 96, 64), 6, seed=9)
+  tp = {"scale": 1.0, "const": 20, "pdrf_scale": 100000, "pdrf_exponent": 4}
+  res, ref = _both(gpu, lab, anisotropy=(16, 16, 40), dust_threshold=100, teasar_params=tp)
+  _compare(res, ref)
+
+
+# ---- the reference's own tests (automated_test.py) against the CUDA path ----
+def test_empty_image(gpu):
+  import kimimaro_b200 as kimimaro
+  assert len(kimimaro.skeletonize(np.zeros((64, 64, 64), dtype=bool), fix_borders=True)) == 0
+
+
+def test_very_sparse_image(gpu):
+  import kimimaro_b200 as kimimaro
+  labels = np.zeros((64, 64, 64), dtype=bool)
+  labels[5, 5, 5] = True
+  labels[6, 5, 5] = True
+  labels[20, 20, 20] = True
+  assert len(kimimaro.skeletonize(labels, dust_threshold=0)) == 1
+
+
+def test_solid_image(gpu):
+  import kimimaro_b200 as kimimaro
+  assert len(kimimaro.skeletonize(np.ones((128, 128, 128), dtype=bool), fix_borders=True)) == 1
+
+
+def test_square(gpu):
+  import kimimaro_b200 as kimimaro
+  for corners in (((-1, 0), (0, -1)), ((0, 0), (-1, -1))):
+    labels = np.ones((1000, 1000), dtype=np.uint8)
+    for c in corners:
+      labels[c] = 0
+    skels = kimimaro.skeletonize(labels, teasar_params=kimimaro.DEFAULT_TEASAR_PARAMS, fix_borders=False)
+    assert len(skels) == 1
+    skel = skels[1]
+    assert skel.vertices.shape[0] == 1000
+    assert skel.edges.shape[0] == 999
+    assert abs(skel.cable_length() - 999 * np.sqrt(2)) < 0.001
+    assert skel.space == "physical"
+
+
+def test_cube(gpu):
+  import kimimaro_b200 as kimimaro
+  labels = np.ones((128, 128, 128), dtype=np.uint8)
+  labels[0, 0, 0] = 0
+  labels[-1, -1, -1] = 0
+  skels = kimimaro.skeletonize(labels, fix_borders=False)
+  skel = skels[1]
+  assert skel.vertices.shape[0] == 128
+  assert skel.edges.shape[0] == 127
+  assert abs(skel.cable_length() - 127 * np.sqrt(3)) < 0.001
+
+
+@pytest.mark.parametrize("axis", ["x", "y", "z"])
+def test_fix_borders(gpu, axis):
+  import kimimaro_b200 as kimimaro
+  labels = np.zeros((256, 256, 256), dtype=np.uint8)
+  sl = [slice(64, 196)] * 3
+  sl["xyz".index(axis)] = slice(None)
+  labels[tuple(sl)] = 128
+  an = (40, 32, 20) if axis == "z" else (1, 1, 1)
+  skels = kimimaro.skeletonize(labels, teasar_params={"const": 250, "scale": 10, "pdrf_exponent": 4,
+                                                     "pdrf_scale": 100000}, anisotropy=an, fix_borders=True)
+  skel = skels[128].voxel_space()
+  for a in range(3):
+    if a == "xyz".index(axis):
+      assert np.all(skel.vertices[:, a] == np.arange(256))
+    else:
+      assert np.all(skel.vertices[:, a] == 129)
+
+
+def test_dimensions(gpu):
+  import kimimaro_b200 as kimimaro
+  for shp in ((10,), (10, 10), (10, 10, 10), (10, 10, 10, 1)):
+    kimimaro.skeletonize(np.zeros(shp, dtype=np.uint8))
+  with pytest.raises(kimimaro.DimensionError):
+    kimimaro.skeletonize(np.zeros((10, 10, 10, 2), dtype=np.uint8))
+
+
+def test_unknown_param_raises(gpu):
+  import kimimaro_b200 as kimimaro
+  with pytest.raises(TypeError):
+    kimimaro.skeletonize(np.ones((32, 32, 32), np.uint8), teasar_params={"bogus": 1}, dust_threshold=0)
