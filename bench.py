@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""
+bench.py -- voxels/sec of skeletonize() on the 512^3 connectomics-shaped volume (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size 512]
+
+One "step" = one full pass of the hot path (CCL, EDT, per-label TEASAR trace of every connected
+component above the dust threshold, skeleton assembly on rank 0) over the whole volume.
+  value   voxels/s with the label volume already resident in HBM when the timed region starts
+  e2e     the same metric through the public API kimimaro_b200.skeletonize(host ndarray): pinned host
+          buffer -> device copy and the device -> host read of every skeleton buffer inside the timed region
+The volume is SYNTHETIC (seeded generator, kimimaro_b200/datasets.py): the reference's
+benchmarks/connectomics.npy.ckl.gz is crackle-compressed and no decoder exists in this image.
+
+--impl reference times the CPU restatement of the reference (oracle/, all host cores via a fork pool
+over labels like kimimaro's parallel mode) on a bounded z-slab of the same volume.
+Under torchrun (N > 1) connected components are sharded over the ranks (strong scaling: the volume is
+fixed), one NCCL gather of skeleton buffers to rank 0 at the end, time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ANISOTROPY = (16.0, 16.0, 40.0)
+SEED = 0xB2002124
+SLAB = (160, 256)          # z-slab of the volume used as the bounded CPU sample (cuts the soma at ~14 % area)
+
+
+def make_volume(n):
+  from kimimaro_b200.datasets import synthetic_tubes
+  cache = f"/tmp/b2t_synth_{n}_{SEED:x}.npy"
+  if os.path.exists(cache):
+    return np.load(cache)
+  if n >= 512:
+    vol = synthetic_tubes((n, n, n), 2124 * (n // 512) ** 3, seed=SEED, anisotropy=ANISOTROPY, soma=True, glia=True)
+  else:
+    vol = synthetic_tubes((n, n, n), max(8, 2124 * n ** 3 // 512 ** 3), seed=SEED, anisotropy=ANISOTROPY)
+  tmp = cache + f".{os.getpid()}.tmp.npy"
+  np.save(tmp, vol)
+  os.replace(tmp, cache)
+  return vol
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+  def __init__(self, index=0):
+    self.rows, self.proc, self.index = [], None, index
+
+  def start(self):
+    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                    "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(",")])
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for r in self.rows:
+      try:
+        sm.append(float(r[0])); mx.append(float(r[1]))
+        for name, val in zip(names, r[3:7]):
+          if val.lower().startswith("active"):
+            reasons.add(name)
+      except Exception:
+        pass
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    with open(p) as f:
+      return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+  return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+  """CPU arm: the oracle port of the reference on a bounded slab, all host cores."""
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  import oracle
+  from oracle import teasar
+  oracle.build()
+  vol = make_volume(args.size)
+  z0, z1 = (SLAB if args.size >= 256 else (0, args.size))
+  sample = np.asfortranarray(vol[:, :, z0:z1])
+  cores = os.cpu_count() or 1
+  times = []
+  for i in range(args.warmup + args.steps):
+    t = time.perf_counter()
+    teasar.skeletonize(sample, anisotropy=ANISOTROPY, parallel=cores)
+    dt = time.perf_counter() - t
+    if i >= args.warmup:
+      times.append(dt)
+  ms = 1e3 * float(np.mean(times))
+  v = sample.size / (ms / 1e3)
+  line = {
+    "impl": "reference", "metric": "voxels/sec skeletonized", "value": v, "unit": "voxels/s", "n_gpus": args.gpus,
+    "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    "config": {"workload": f"synthetic-{args.size} connectomics-shaped volume, anisotropy 16x16x40, DEFAULT_TEASAR_PARAMS",
+               "sample": f"z-slab [{z0}:{z1}) of the volume ({sample.shape[0]}x{sample.shape[1]}x{sample.shape[2]})"},
+    "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port",
+                     "sample": f"z-slab [{z0}:{z1}) of the same volume, fork pool over labels"},
+    "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+  }
+  print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+  import torch
+  import torch.distributed as dist
+  from kimimaro_b200 import _lib, distributed as kdist
+  from kimimaro_b200.intake import skeletonize
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  _lib.require_device()
+
+  # data: rank 0 builds (or loads) the cached volume, the others load it afterwards
+  if rank == 0:
+    vol = make_volume(args.size)
+  if world > 1:
+    dist.barrier()
+  if rank != 0:
+    vol = make_volume(args.size)
+  shape = vol.shape
+  V = vol.size
+  flat = vol.reshape(-1, order="F")
+  pinned = torch.from_numpy(flat.view(np.uint32).view(np.int32)).pin_memory()
+  host_view = pinned.numpy().view(np.uint32).reshape(shape, order="F")       # Fortran view of the pinned buffer
+  d_labels = pinned.to(dev)
+  subset = kdist.make_label_subset(rank, world) if world > 1 else None
+
+  def step_resident(edt_events=None):
+    sk = skeletonize(shape, device_labels=d_labels, anisotropy=ANISOTROPY, progress=False, label_subset=subset,
+                     edt_events=edt_events)
+    if world > 1:
+      sk = kdist.gather_skeletons(sk, dev)
+    return sk
+
+  def step_e2e():
+    sk = skeletonize(host_view, anisotropy=ANISOTROPY, progress=False, in_place=True, label_subset=subset)
+    if world > 1:
+      sk = kdist.gather_skeletons(sk, dev)
+    return sk
+
+  def sync():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize()
+
+  def timed(fn, steps, **kw):
+    sync()
+    t = time.perf_counter()
+    out = None
+    for _ in range(steps):
+      out = fn(**kw)
+    sync()
+    dt = time.perf_counter() - t
+    if world > 1:
+      tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+      dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+      dt = float(tt.item())
+    return dt, out
+
+  for _ in range(args.warmup):
+    step_resident()
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  lib = _lib.lib()
+  lib.b2t_launch_count.restype = __import__("ctypes").c_ulonglong
+  lib.b2t_launch_count(1)
+  edt_events = []
+  dt, sk = timed(step_resident, args.steps, edt_events=edt_events)
+  launches = int(lib.b2t_launch_count(0)) // max(args.steps, 1)
+  clocks = sampler.stop() if rank == 0 else None
+  ms = 1e3 * dt / args.steps
+  value = V / (ms / 1e3)
+
+  # K1 duration from CUDA events recorded around b2t_edt on its launch stream inside the timed steps
+  torch.cuda.synchronize()
+  edt_ms = float(np.mean([a.elapsed_time(b) for a, b in edt_events])) if edt_events else None
+
+  # end to end through the public API with host buffers
+  for _ in range(min(args.warmup, 1)):
+    step_e2e()
+  dte, sk_e = timed(step_e2e, args.steps)
+  mse = 1e3 * dte / args.steps
+  d2h = 0
+  if rank == 0 and sk_e:
+    d2h = int(sum(s.vertices.nbytes + s.edges.nbytes + s.radii.nbytes for s in sk_e.values()))
+
+  # per-phase breakdown (one extra, untimed-for-the-metric step with synchronising laps)
+  tm = {}
+  skeletonize(shape, device_labels=d_labels, anisotropy=ANISOTROPY, progress=False, label_subset=subset, timings=tm)
+  phases = {k: round(1e3 * v, 3) for k, v in tm.items() if isinstance(v, float)}
+
+  if rank == 0:
+    peak, how = peaks()
+    label_bytes = 4
+    alg = (3 * label_bytes + 20) * V                     # (3L+20) B/voxel, three separable passes
+    roof = None
+    if edt_ms:
+      ach = alg / (edt_ms * 1e-3) / 1e9
+      roof = {"kernel": "b2t_edt (K1: edt_pass_x + 2x edt_pass_col)", "bound": "hbm", "achieved": ach, "peak": peak,
+              "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": how,
+              "algorithmic_bytes": alg, "ms": edt_ms}
+    # bounded CPU sample: the oracle port, one core, on the slab
+    cpu = None
+    if not args.no_cpu:
+      import oracle
+      from oracle import teasar
+      oracle.build()
+      z0, z1 = (SLAB if args.size >= 256 else (0, args.size))
+      sample = np.asfortranarray(vol[:, :, z0:z1])
+      t = time.perf_counter()
+      teasar.skeletonize(sample, anisotropy=ANISOTROPY)
+      cdt = time.perf_counter() - t
+      cpu = {"value": sample.size / cdt, "unit": "voxels/s", "cores": 1, "kind": "port",
+             "sample": f"z-slab [{z0}:{z1}) of the same volume ({sample.shape[0]}x{sample.shape[1]}x{sample.shape[2]}), {cdt:.1f} s"}
+    line = {
+      "metric": "voxels/sec skeletonized", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+      "dtype": "f32", "data": "synthetic",
+      "config": {"workload": f"synthetic-{args.size}: {shape[0]}x{shape[1]}x{shape[2]} uint32, {int(len(np.unique(vol)) - 1)} labels, "
+                             "one soma + one glia tree, anisotropy 16x16x40, DEFAULT_TEASAR_PARAMS, fix_borders",
+                 "l2": "inputs and work fields (>3 GB) exceed the 126 MB L2", "skeletons": len(sk) if sk else 0,
+                 "parallelism": f"labels sharded over {world} rank(s)"},
+      "e2e": {"value": V / (mse / 1e3), "unit": "voxels/s", "h2d_bytes_per_step": int(flat.nbytes),
+              "d2h_bytes_per_step": d2h, "ms_per_step": mse},
+      "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "phases_ms": phases,
+    }
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=3)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  ap.add_argument("--size", type=int, default=512)
+  ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+  args = ap.parse_args()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_b200(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -35,6 +35,7 @@ extern "C" {
 int b2t_version(void);                 /* e.g. 100 = 0.1.0 */
 const char* b2t_last_error(void);      /* thread-local message of the last failure */
 int b2t_device_check(void);            /* B2T_OK iff current device is compute capability 10.x */
+unsigned long long b2t_launch_count(int reset); /* kernels launched by this library so far */
 
 /* K1  anisotropic multi-label Euclidean distance transform ------------------------------------
  * replaces  edt.edt(labels, anisotropy, black_border)            kimimaro/intake.py:174-185
@@ -46,6 +47,92 @@ int b2t_device_check(void);            /* B2T_OK iff current device is compute c
  * into the last one.  d_out is used in place between passes; no workspace. */
 int b2t_edt(const void* d_labels, int label_bytes, int64_t sx, int64_t sy, int64_t sz,
             float wx, float wy, float wz, int black_border, int ndim, float* d_out, void* stream);
+
+
+/* N1  connected components ------------------------------------------------------------------------
+ * replaces  cc3d.connected_components(labels) (26-connected, multi-label; 2-D: 8-connected)
+ *           kimimaro/utility.py:77, kimimaro/intake.py:564
+ * Two steps so that the caller ranks the component roots (a prefix sum in raster order):
+ *   b2t_ccl26_roots: d_parent[v] = smallest linear index of v's component (0xffffffff on background),
+ *                    d_is_root[v] = 1 on that voxel.  Numbering by first appearance == cc3d's order.
+ *   b2t_ccl_relabel: d_parent[v] <- d_rank[d_parent[v]] (0 on background): the cc label volume. */
+int b2t_ccl26_roots(const void* d_labels, int label_bytes, int64_t sx, int64_t sy, int64_t sz,
+                    uint32_t* d_parent, uint8_t* d_is_root, void* stream);
+int b2t_ccl_relabel(uint32_t* d_parent, const int32_t* d_rank, uint64_t n_voxels, void* stream);
+
+/* per-label statistics in one pass -----------------------------------------------------------------
+ * replaces  fastremap.unique(cc_labels, return_counts=True)      kimimaro/intake.py:198
+ *           scipy.ndimage.find_objects (bounding boxes)          kimimaro/utility.py:85-102
+ *           np.max(DBF) per cropped label                        kimimaro/trace.py:100
+ *           skeletontricks.first_label                           ext/skeletontricks/skeletontricks.pyx:307-326
+ * tables have n_labels+1 entries (row 0 = background, unused); d_bbox rows are x0,y0,z0,x1,y1,z1 inclusive. */
+int b2t_label_stats(const uint32_t* d_cc, const float* d_dbf, int64_t sx, int64_t sy, int64_t sz,
+                    uint32_t n_labels, uint32_t* d_count, int32_t* d_bbox, float* d_dbfmax,
+                    uint32_t* d_first, void* stream);
+
+/* K2  geometric distance field, all labels at once ----------------------------------------------------
+ * replaces  dijkstra3d.euclidean_distance_field(labels, source, anisotropy, free_space_radius,
+ *           return_max_location=True)           kimimaro/trace.py:139-145 (DAF), :302-307 (find_root)
+ * One source voxel per participating label (d_sources, n_sources); relaxation only between voxels of
+ * equal d_cc value.  d_dist [V] must hold +inf and d_stamp [V] zero on entry; d_queue holds
+ * 2*queue_cap u32 (queue_cap >= foreground voxels of the participating labels); d_ctrl >= 8 u32.
+ * free_space_radius > 0 (soma labels, trace.py:134) needs n_sources == 1 and the source's linear
+ * index in h_free_space_source. */
+int b2t_edf_multi(const uint32_t* d_cc, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
+                  const uint32_t* d_sources, uint32_t n_sources, float free_space_radius,
+                  uint32_t h_free_space_source, float* d_dist, uint32_t* d_stamp, uint32_t* d_queue,
+                  uint64_t queue_cap, uint32_t* d_ctrl, void* stream);
+
+/* return_max_location of the call above: d_best[l] = (dist_bits << 32) | (0xffffffff - index) of the
+ * largest finite distance of label l, smallest index on ties; 0 if the label has none. */
+int b2t_field_argmax(const uint32_t* d_cc, const float* d_dist, int64_t sx, int64_t sy, int64_t sz,
+                     uint32_t n_labels, uint64_t* d_best, void* stream);
+
+/* K3  penalised distance field + target cache ---------------------------------------------------------
+ * replaces  skeletontricks.zero2inf / inf2zero     kimimaro/trace.py:138,146 (pyx:177-224)
+ *           compute_pdrf                          kimimaro/trace.py:315-356
+ *           CachedTargetFinder.__init__           ext/skeletontricks/skeletontricks.pyx:995-1006
+ * d_dist holds DAF on entry and +inf on exit; d_pdrf / d_claim / d_flag are initialised on every voxel of
+ * an active label; d_keys receives (daf_bits << 32 | index) partitioned into nbuckets DAF buckets per
+ * label: bucket b of label l is d_keys[d_cursor[l*nb+b] - d_hist[l*nb+b] .. d_cursor[l*nb+b]).
+ * d_M[l] = float32(1 / dbf_max**1.01), d_inv_maxdaf[l] = 1 / DAF[target] (0 if that is 0): computed by
+ * the host with the reference's numpy expressions (trace.py:336, 353). */
+int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist, float* d_pdrf,
+                         uint64_t* d_claim, uint8_t* d_flag, int64_t sx, int64_t sy, int64_t sz,
+                         uint32_t n_labels, const float* d_M, const float* d_inv_maxdaf,
+                         const uint8_t* d_active, float pdrf_scale, float pdrf_exponent, int nbuckets,
+                         uint32_t* d_hist, uint32_t* d_cursor, uint64_t* d_keys, void* stream);
+
+/* K4 + K5  the path loop ----------------------------------------------------------------------------------
+ * replaces  compute_paths                                   kimimaro/trace.py:196-267, including
+ *           CachedTargetFinder.find_target                  ext/skeletontricks/skeletontricks.pyx:1008-1045
+ *           dijkstra3d.railroad(PDRF, target)               kimimaro/trace.py:240-242
+ *           roll_invalidation_ball_inside_component         pyx:373-418 -> dijkstra_invalidation.hpp:239-332
+ *           the soma cull and soma invalidation             kimimaro/trace.py:160-168, 246-251
+ * d_desc: n_desc records of 64 bytes (16 little-endian 32-bit fields):
+ *   segid, root, n_fg, region_off, path_off, path_cap, tb_off, tb_n, ta_off, ta_n, max_paths (0xffffffff =
+ *   None), soma_mode, soma_radius (float32), bucket_row, 0, 0
+ * d_scratch: 4*sum(n_fg) u32; d_paths: pool of voxel indices, each path [rail ... target] terminated by
+ * 0xffffffff; d_out_len / d_out_npaths / d_out_status: n_desc; d_out_stats: 4*n_desc; d_work_counter: 1 u32. */
+int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,
+                    uint32_t* d_stamp, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
+                    const void* d_desc, int n_desc, float scale, float konst, float soma_scale,
+                    float soma_const, int nbuckets, const uint64_t* d_keys, const uint32_t* d_hist,
+                    const uint32_t* d_cursor, uint32_t* d_scratch, uint32_t* d_paths,
+                    const uint32_t* d_targets, uint32_t* d_out_len, uint32_t* d_out_npaths,
+                    int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter, void* stream);
+
+/* skeleton buffers: compact the path segments and fetch radii = DBF[vertex] (kimimaro/trace.py:186-187) */
+int b2t_gather_paths(const uint32_t* d_pool, const uint32_t* d_src_off, const uint32_t* d_len,
+                     const uint64_t* d_dst_off, uint32_t n_seg, const float* d_dbf, uint32_t* d_dst_vox,
+                     float* d_dst_radius, void* stream);
+
+/* K6  hole filling (soma labels only) -----------------------------------------------------------------------
+ * replaces  fill_voids.fill(labels, in_place=True, return_fill_count=True)    kimimaro/trace.py:109
+ * d_mask uint8 [V] edited in place; d_reach [V] u32 scratch; d_queue 2*queue_cap u32 (queue_cap >= V);
+ * the fill count is left in d_ctrl[5]. */
+int b2t_fill_voids(uint8_t* d_mask, int64_t sx, int64_t sy, int64_t sz, uint32_t* d_reach,
+                   uint32_t* d_queue, uint64_t queue_cap, uint32_t* d_ctrl, void* stream);
 
 #ifdef __cplusplus
 }

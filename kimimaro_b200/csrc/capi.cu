@@ -13,7 +13,17 @@ void b2t_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void b2t_count_launches(int n) { g_launches += (unsigned long long)n; }
+
 B2T_EXPORT int b2t_version(void) { return 100; }
+
+// number of kernels this library has launched since load (or since the last reset)
+B2T_EXPORT unsigned long long b2t_launch_count(int reset) {
+  const unsigned long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
 
 B2T_EXPORT const char* b2t_last_error(void) { return g_err; }
 

@@ -9,6 +9,7 @@
 #define B2T_EXPORT extern "C" __attribute__((visibility("default")))
 
 void b2t_set_error(const char* fmt, ...);
+void b2t_count_launches(int n);  // bookkeeping for b2t_launch_count()
 
 #define B2T_CUDA_TRY(expr)                                                                  \
   do {                                                                                      \

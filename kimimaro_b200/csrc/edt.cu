@@ -205,6 +205,7 @@ int edt_launch(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wx, fl
                                                                    black_border, 1);
   }
   B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(ndim == 3 ? 3 : 2);
   return B2T_OK;
 }
 

@@ -387,6 +387,7 @@ B2T_EXPORT int b2t_label_stats(const uint32_t* d_cc, const float* d_dbf, int64_t
   label_stats_kernel<<<blocks, 256, 0, st>>>(d_cc, d_dbf, d, nseg_x, nsegs, n_labels, d_count, d_bbox,
                                              reinterpret_cast<uint32_t*>(d_dbfmax), d_first);
   B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(2);
   return B2T_OK;
 }
 
@@ -420,6 +421,7 @@ B2T_EXPORT int b2t_edf_multi(const uint32_t* d_cc, int64_t sx, int64_t sy, int64
   if (int rc = coop_grid(kern, 256, 0, &blocks)) return rc;
   void* args[] = {&p};
   B2T_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(256), args, 0, st));
+  b2t_count_launches(frozen ? 3 : 2);
   return B2T_OK;
 }
 
@@ -434,6 +436,7 @@ B2T_EXPORT int b2t_field_argmax(const uint32_t* d_cc, const float* d_dist, int64
   field_argmax_kernel<<<(unsigned)((nsegs + 255) / 256), 256, 0, st>>>(d_cc, d_dist, d, nseg_x, nsegs, n_labels,
                                                                       reinterpret_cast<unsigned long long*>(d_best));
   B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(1);
   return B2T_OK;
 }
 
@@ -477,6 +480,7 @@ B2T_EXPORT int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, fl
   s.keys = reinterpret_cast<unsigned long long*>(d_keys); s.n_labels = n_labels; s.nbuckets = nbuckets; s.V = V;
   bucket_scatter_kernel<<<blocks, 256, 0, st>>>(s);
   B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(3);
   return B2T_OK;
 }
 
@@ -574,5 +578,6 @@ B2T_EXPORT int b2t_fill_voids(uint8_t* d_mask, int64_t sx, int64_t sy, int64_t s
   const uint64_t want = (p.V + 255) / 256;
   fill_apply_kernel<<<(unsigned)(want < 148ull * 32 ? want : 148ull * 32), 256, 0, st>>>(p);
   B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(3);
   return B2T_OK;
 }

@@ -115,6 +115,7 @@ int ccl_launch(const T* labels, Dims d, uint64_t V, uint32_t* parent, uint8_t* i
   ccl_merge_kernel<T><<<grid_for(V), 256, 0, st>>>(labels, parent, d, V);
   ccl_flatten_kernel<<<grid_for(V), 256, 0, st>>>(parent, is_root, V);
   B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(3);
   return B2T_OK;
 }
 
@@ -144,6 +145,7 @@ B2T_EXPORT int b2t_ccl_relabel(uint32_t* d_parent, const int32_t* d_rank, uint64
   B2T_REQUIRE(d_parent && d_rank, "b2t_ccl_relabel: null pointer");
   ccl_relabel_kernel<<<grid_for(n_voxels), 256, 0, (cudaStream_t)stream>>>(d_parent, d_rank, n_voxels);
   B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(1);
   return B2T_OK;
 }
 
@@ -155,5 +157,6 @@ B2T_EXPORT int b2t_gather_paths(const uint32_t* d_pool, const uint32_t* d_src_of
   gather_paths_kernel<<<n_seg, 128, 0, (cudaStream_t)stream>>>(d_pool, d_src_off, d_len, d_dst_off, d_dbf, d_dst_vox,
                                                               d_dst_radius);
   B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(1);
   return B2T_OK;
 }

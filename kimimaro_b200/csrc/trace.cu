@@ -578,5 +578,6 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
   if (blocks > n_desc) blocks = n_desc;
   trace_kernel<<<blocks, kThreads, 0, st>>>(A, reinterpret_cast<const LabelDesc*>(d_desc), P, prm);
   B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(1);
   return B2T_OK;
 }

@@ -155,7 +155,7 @@ def skeletonize(
   fix_borders=True, parallel=1, parallel_chunk_size=100,
   extra_targets_before=[], extra_targets_after=[],
   fill_holes=False, fix_avocados=False,
-  voxel_graph=None, timings=None, label_subset=None, device_labels=None,
+  voxel_graph=None, timings=None, label_subset=None, device_labels=None, edt_events=None,
 ):
   """
   Skeletonize all non-zero labels in a 2D or 3D image (kimimaro/intake.py:58-143).
@@ -163,7 +163,8 @@ def skeletonize(
 
   Extra keyword arguments (not in the reference): timings (dict filled with per-phase seconds),
   label_subset (callable(list of cc ids) -> list: used by the multi-GPU launcher to shard labels),
-  device_labels (a flat Fortran-ordered CUDA tensor already holding the volume: skips the H2D copy).
+  device_labels (a flat Fortran-ordered CUDA tensor already holding the volume: skips the H2D copy;
+  all_labels then carries the shape), edt_events (list receiving (start, end) CUDA events around K1).
   """
   if fill_holes or fix_avocados or voxel_graph is not None or not fix_branching:
     raise NotImplementedError(
@@ -218,7 +219,13 @@ def skeletonize(
   # ---- preamble: connected components, EDT, per-label statistics ----
   d_cc, n_cc = engine.connected_components(d_labels, shape)
   t0 = lap("ccl", t0)
+  if edt_events is not None:
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
   d_dbf = edt(d_cc, shape, an, black_border)
+  if edt_events is not None:
+    ev1.record()
+    edt_events.append((ev0, ev1))
   t0 = lap("edt", t0)
   count, bbox, dbfmax, first = engine.label_stats(d_cc, d_dbf, shape, n_cc)
   h_count = count.cpu().numpy()

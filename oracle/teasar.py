@@ -414,6 +414,13 @@ def compute_paths(root, labels, DBF, target_finder, parents, scale, const, aniso
 # ------------------------------------------------------------------------------------------
 # kimimaro/intake.py
 # ------------------------------------------------------------------------------------------
+_POOL_FN = None
+
+
+def _pool_call(segid):
+  return _POOL_FN(segid)
+
+
 def format_labels(labels):
   labels = np.copy(labels, order="F")
   if labels.dtype == bool:
@@ -468,7 +475,7 @@ def compute_border_targets(cc_labels, anisotropy):
 def skeletonize(all_labels, teasar_params=DEFAULT_TEASAR_PARAMS, anisotropy=(1, 1, 1), object_ids=None,
                 dust_threshold=1000, fix_branching=True, fix_borders=True,
                 extra_targets_before=(), extra_targets_after=(), invalidation_mode="rounds",
-                only_cc=None, timings=None):
+                only_cc=None, timings=None, parallel=1):
   """intake.py:58-221 + 434-517 (parallel==1 path).  Returns {orig id: skeleton dict}."""
   import time
   t0 = time.time()
@@ -500,17 +507,14 @@ def skeletonize(all_labels, teasar_params=DEFAULT_TEASAR_PARAMS, anisotropy=(1, 
     border_targets = compute_border_targets(cc_labels, anisotropy)
   t1 = time.time()
 
-  skeletons = defaultdict(list)
-  for segid in cc_segids:
-    if only_cc is not None and segid not in only_cc:
-      continue
+  def trace_one(segid):
     slices = all_slices[segid - 1]
     if slices is None:
-      continue
+      return None
     minpt = np.array([s.start for s in slices])
     vol = np.prod([s.stop - s.start for s in slices])
     if vol <= 1:
-      continue
+      return None
     labels = (cc_labels[slices] == segid)
     dbf = np.where(labels, all_dbf[slices], 0.0).astype(np.float32)
     manual_targets_before, manual_targets_after, root = [], [], None
@@ -529,10 +533,29 @@ def skeletonize(all_labels, teasar_params=DEFAULT_TEASAR_PARAMS, anisotropy=(1, 
                  manual_targets_before=manual_targets_before, manual_targets_after=manual_targets_after,
                  root=root, invalidation_mode=invalidation_mode, **teasar_params)
     if skel["vertices"].shape[0] == 0:
-      continue
+      return None
     skel["vertices"] = skel["vertices"] + minpt.astype(np.float32)
     skel["vertices"] = np.multiply(skel["vertices"], anisotropy, dtype=np.float32)
-    skeletons[remapping[segid]].append(skel)
+    return skel
+
+  todo = [s for s in cc_segids if only_cc is None or s in only_cc]
+  skeletons = defaultdict(list)
+  if parallel is not None and parallel > 1 and len(todo) > 1:
+    # the reference's parallel mode: a process pool over connected components (intake.py:344-432);
+    # fork keeps cc_labels / all_dbf shared copy-on-write instead of the reference's POSIX shm
+    import multiprocessing as mp
+    global _POOL_FN
+    _POOL_FN = trace_one
+    order = sorted(todo, key=lambda s: -counts[s])
+    with mp.get_context("fork").Pool(parallel) as pool:
+      for segid, skel in zip(order, pool.map(_pool_call, order, chunksize=1)):
+        if skel is not None:
+          skeletons[remapping[segid]].append(skel)
+  else:
+    for segid in todo:
+      skel = trace_one(segid)
+      if skel is not None:
+        skeletons[remapping[segid]].append(skel)
   out = {}
   for segid, skels in skeletons.items():
     out[segid] = skel_consolidate(skel_simple_merge(skels))

@@ -1,0 +1,267 @@
+"""CPU suite (-m "not gpu"): the oracle against brute-force definitions, against the reference's own
+in-tree extension compiled into oracle/_ref, against the reference's known-answer tests
+(automated_test.py) and against the committed golden fixtures; host logic of the product; and that
+libb2t.so loads and exports every symbol include/b2t.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- oracle EDT vs the closed-form definition ----
+def test_edt_bruteforce(orc):
+  rng = np.random.default_rng(1)
+  for trial in range(30):
+    shape = tuple(int(v) for v in rng.integers(1, 12, size=3))
+    lab = rng.integers(0, int(rng.integers(1, 5)) + 1, size=shape).astype(np.uint32)
+    if trial % 5 == 0:
+      lab[:] = 1
+    an = tuple(float(v) for v in rng.choice([1, 2.5, 4, 16, 40], size=3))
+    for bb in (False, True):
+      a = orc.edt(lab, an, bb)
+      b = orc.edt(lab, an, bb, brute_force=True)
+      assert np.array_equal(np.isinf(a), np.isinf(b))
+      fin = ~np.isinf(b)
+      np.testing.assert_allclose(a[fin], b[fin], rtol=1e-5)
+
+
+def test_edt_known_answers(orc):
+  # automated_test.py:104-114
+  lab = np.zeros((257, 257), np.uint8)
+  lab[1:-1, 1:-1] = 1
+  d = orc.edt(lab)
+  assert np.unravel_index(np.argmax(d), d.shape) == (128, 128) and d.max() == 128.0
+
+
+# ---- oracle Dijkstra pieces ----
+def test_edf_straight_line(orc):
+  f = np.ones((10, 1, 1), np.uint8, order="F")
+  d, mx = orc.euclidean_distance_field(f, (0, 0, 0), (2, 3, 4), return_max_location=True)
+  assert np.allclose(d[:, 0, 0], 2 * np.arange(10)) and mx == (9, 0, 0)
+
+
+def test_railroad_reaches_rail(orc):
+  f = np.full((9, 9, 1), 5.0, np.float32, order="F")
+  f[4, :, 0] = 1.0
+  f[4, 0, 0] = 0.0
+  p = orc.railroad(f, (4, 8, 0))
+  assert tuple(p[0]) == (4, 0, 0) and tuple(p[-1]) == (4, 8, 0) and len(p) == 9
+  assert np.all(p[:, 0] == 4)
+
+
+def test_fill_and_ccl(orc):
+  m = np.ones((7, 7, 7), np.uint8, order="F")
+  m[3, 3, 3] = 0
+  m[0, 0, 0] = 0
+  _, n = orc.fill_voids(m)
+  assert n == 1 and m[3, 3, 3] == 1 and m[0, 0, 0] == 0
+  lab = np.zeros((6, 6, 1), np.uint32, order="F")
+  lab[0:2, 0:2] = 7
+  lab[2, 2] = 7          # diagonal touch: 8-connected in 2-D
+  lab[4:6, 4:6] = 7
+  lab[0, 5] = 9
+  cc, n = orc.connected_components(lab)
+  assert n == 3 and cc[0, 0, 0] == cc[2, 2, 0] and cc[4, 4, 0] != cc[0, 0, 0]
+
+
+# ---- pinned against the reference's compiled in-tree extension ----
+def _tube(rng, shape=(40, 40, 24)):
+  vol = np.zeros(shape, np.uint8, order="F")
+  p = np.array([s // 2 for s in shape], float)
+  d = rng.normal(size=3)
+  path, seen = [], set()
+  r = int(rng.integers(2, 5))
+  for _ in range(int(rng.integers(20, 60))):
+    d = 0.85 * d + 0.15 * rng.normal(size=3)
+    d /= np.linalg.norm(d)
+    p = np.clip(p + d, 1, np.array(shape) - 2)
+    c = tuple(int(v) for v in np.round(p))
+    if c not in seen and (not path or max(abs(np.array(c) - np.array(path[-1]))) <= 1):
+      seen.add(c)
+      path.append(c)
+    x0, y0, z0 = c
+    vol[max(0, x0 - r):x0 + r + 1, max(0, y0 - r):y0 + r + 1, max(0, z0 - 1):z0 + 2] = 1
+  return vol, path
+
+
+def test_invalidation_vs_reference_ext(orc, ref_ext):
+  if ref_ext is None:
+    pytest.skip("oracle/_ref not built (no /root/reference here)")
+  rng = np.random.default_rng(3)
+  same = {"seq": 0, "rounds": 0}
+  vox_diff = {"seq": 0, "rounds": 0}
+  total = 0
+  N = 60
+  for trial in range(N):
+    vol, path = _tube(rng)
+    an = (16.0, 16.0, 40.0) if trial % 2 else (1.0, 1.0, 1.0)
+    dbf = orc.edt(vol, an, False)
+    scale, const = float(rng.choice([1.0, 1.5, 4.0])), float(rng.choice([0, 1, 3])) * an[0]
+    a = vol.copy(order="F")
+    na, a = ref_ext.roll_invalidation_ball_inside_component(a, dbf, scale, const, an, path)
+    total += int(na)
+    for mode in same:
+      b = vol.copy(order="F")
+      nb, b = orc.roll_invalidation_ball_inside_component(b, dbf, scale, const, an, path, mode=mode)
+      assert nb == int(vol.sum() - b.sum())
+      assert not np.any((a == 0) & (b != 0) & False)
+      diff = int((a != b).sum())
+      same[mode] += diff == 0
+      vox_diff[mode] += diff
+  # Tier B: the only differences are heap tie / claim-order effects on the fringe
+  assert same["seq"] >= 0.9 * N and same["rounds"] >= 0.85 * N, same
+  assert vox_diff["rounds"] <= 1e-3 * total, (vox_diff, total)
+
+
+def test_target_finder_vs_reference_ext(ref_ext):
+  if ref_ext is None:
+    pytest.skip("oracle/_ref not built")
+  from oracle import teasar
+  rng = np.random.default_rng(5)
+  mask = (rng.random((12, 11, 10)) > 0.4)
+  mask = np.asfortranarray(mask)
+  daf = np.asfortranarray(rng.permutation(mask.size).reshape(mask.shape).astype(np.float32))  # no ties
+  a = ref_ext.CachedTargetFinder(mask, daf)
+  b = teasar.CachedTargetFinder(mask, daf)
+  m = mask.copy(order="F")
+  for _ in range(50):
+    ta, tb = a.find_target(m), b.find_target(m)
+    assert tuple(int(v) for v in ta) == tb
+    m[ta] = False
+    kill = rng.random(m.shape) > 0.9
+    m[kill] = False
+    if not m.any():
+      break
+
+
+def test_border_targets_vs_reference_ext(orc, ref_ext):
+  if ref_ext is None:
+    pytest.skip("oracle/_ref not built")
+  from oracle import teasar
+  from kimimaro_b200 import border
+  rng = np.random.default_rng(8)
+  for trial in range(12):
+    plane = np.zeros((40, 33), np.uint32, order="F")
+    for l in range(1, 6):
+      x0, y0 = int(rng.integers(0, 30)), int(rng.integers(0, 24))
+      plane[x0:x0 + int(rng.integers(2, 12)), y0:y0 + int(rng.integers(2, 10))] = l
+    cc, _ = orc.connected_components(plane)
+    wx, wy = (16.0, 40.0) if trial % 2 else (1.0, 1.0)
+    dt = orc.edt(cc, (wx, wy), True)
+    want = ref_ext.find_border_targets(dt, cc.astype(np.uint32), wx, wy)
+    got_o = teasar.find_border_targets(dt, cc, wx, wy)
+    got_p = border.find_border_targets(dt, cc, wx, wy)
+    norm = lambda d: {int(k): (int(v[0]), int(v[1])) for k, v in d.items()}
+    assert norm(got_o) == norm(want)
+    assert norm(got_p) == norm(want)
+    assert list(norm(got_p)) == list(norm(want))          # dict order feeds list(set) order
+
+
+# ---- reference known-answer tests on the oracle (automated_test.py:48-102, 116-199) ----
+def _cable(s):
+  v, e = s["vertices"], s["edges"]
+  return float(np.linalg.norm(v[e[:, 0]] - v[e[:, 1]], axis=1).sum())
+
+
+def test_reference_square_and_cube(orc):
+  from oracle import teasar
+  for corners in (((-1, 0), (0, -1)), ((0, 0), (-1, -1))):
+    labels = np.ones((300, 300), np.uint8)
+    for c in corners:
+      labels[c] = 0
+    s = teasar.skeletonize(labels, fix_borders=False)[1]
+    assert s["vertices"].shape[0] == 300 and s["edges"].shape[0] == 299
+    assert abs(_cable(s) - 299 * np.sqrt(2)) < 1e-3
+  labels = np.ones((64, 64, 64), np.uint8)
+  labels[0, 0, 0] = 0
+  labels[-1, -1, -1] = 0
+  s = teasar.skeletonize(labels, fix_borders=False)[1]
+  assert s["vertices"].shape[0] == 64 and s["edges"].shape[0] == 63 and abs(_cable(s) - 63 * np.sqrt(3)) < 1e-3
+
+
+def test_reference_fix_borders(orc):
+  from oracle import teasar
+  labels = np.zeros((96, 96, 96), np.uint8)
+  labels[24:72, 24:72, :] = 128
+  sk = teasar.skeletonize(labels, teasar_params={"const": 250, "scale": 10, "pdrf_exponent": 4, "pdrf_scale": 100000},
+                          anisotropy=(40, 32, 20), dust_threshold=100)
+  v = sk[128]["vertices"] / np.array([40, 32, 20], np.float32)
+  assert np.all(v[:, 0] == v[0, 0]) and np.all(v[:, 1] == v[0, 1]) and np.array_equal(v[:, 2], np.arange(96))
+
+
+# ---- golden fixtures (tests/golden, generated by tests/golden/make_golden.py) ----
+def test_golden_fixtures(orc):
+  from oracle import teasar
+  from tests.synth import sphere, synthetic_tubes
+  g = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+  cases = {"sphere": (sphere(64, 24), {}),
+           "tubes": (synthetic_tubes((96, 96, 64), 12, seed=1), {"anisotropy": (16, 16, 40), "dust_threshold": 100})}
+  for name, (lab, kw) in cases.items():
+    sk = teasar.skeletonize(lab, **kw)
+    ids = g[f"{name}_ids"]
+    assert sorted(sk) == sorted(int(i) for i in ids)
+    for i in ids:
+      assert np.array_equal(sk[int(i)]["vertices"], g[f"{name}_{int(i)}_v"])
+      assert np.array_equal(sk[int(i)]["edges"], g[f"{name}_{int(i)}_e"])
+
+
+# ---- product host logic ----
+def test_skeleton_class():
+  from kimimaro_b200 import Skeleton
+  a = Skeleton.from_path(np.array([[0, 0, 0], [1, 1, 1], [2, 2, 2]]))
+  b = Skeleton.from_path(np.array([[2, 2, 2], [3, 2, 2]]))
+  m = Skeleton.simple_merge([a, b]).consolidate()
+  assert m.vertices.shape == (4, 3) and m.edges.shape == (3, 2)
+  assert abs(m.cable_length() - (2 * np.sqrt(3) + 1)) < 1e-6
+  assert len(m.components()) == 1 and list(m.terminals()) == [0, 3]
+  assert Skeleton.equivalent(m, Skeleton.from_swc(m.to_swc()).consolidate())
+  assert Skeleton().empty()
+
+
+def test_lpt_and_pack_roundtrip():
+  from kimimaro_b200 import Skeleton, distributed as kd
+  counts = {1: 100, 2: 90, 3: 10, 4: 5, 5: 5}
+  shards = kd.lpt_assign(list(counts), counts, 2)
+  assert sorted(sum(shards, [])) == [1, 2, 3, 4, 5]
+  assert abs(sum(counts[s] for s in shards[0]) - sum(counts[s] for s in shards[1])) <= 10
+  sk = {7: Skeleton.from_path(np.array([[0, 0, 0], [1, 0, 0]])), 9: Skeleton.from_path(np.array([[5, 5, 5], [5, 6, 5], [5, 7, 5]]))}
+  out = kd.unpack(*kd.pack(sk))
+  assert sorted(out) == [7, 9] and np.array_equal(out[9].vertices, sk[9].vertices) and np.array_equal(out[9].edges, sk[9].edges)
+
+
+def test_format_labels_and_errors():
+  pytest.importorskip("torch")
+  from kimimaro_b200 import intake
+  assert intake.format_labels(np.zeros((4, 5), np.uint8), False).shape == (4, 5, 1)
+  assert intake.format_labels(np.zeros((4, 5, 6, 1), bool), False).dtype == np.uint8
+  with pytest.raises(intake.DimensionError):
+    intake.format_labels(np.zeros((2, 2, 2, 2), np.uint8), False)
+  with pytest.raises(TypeError):
+    intake._merge_params({"nope": 1})
+
+
+# ---- the C ABI ----
+def test_libb2t_exports_every_declared_symbol():
+  from kimimaro_b200 import build
+  lib_path = build.build()
+  lib = ctypes.CDLL(lib_path)
+  header = open(os.path.join(ROOT, "include", "b2t.h")).read()
+  names = sorted(set(re.findall(r"\b(b2t_[a-z0-9_]+)\s*\(", header)))
+  assert len(names) >= 14
+  for n in names:
+    assert hasattr(lib, n), n
+  assert lib.b2t_version() >= 100
+
+
+def test_no_cpu_fallback():
+  torch = pytest.importorskip("torch")
+  if torch.cuda.is_available():
+    pytest.skip("this box has a GPU")
+  import kimimaro_b200
+  from kimimaro_b200._lib import B2TError
+  with pytest.raises(B2TError):
+    kimimaro_b200.skeletonize(np.ones((32, 32, 64), np.uint8))

@@ -139,3 +139,78 @@ def test_unknown_param_raises(gpu):
   import kimimaro_b200 as kimimaro
   with pytest.raises(TypeError):
     kimimaro.skeletonize(np.ones((32, 32, 32), np.uint8), teasar_params={"bogus": 1}, dust_threshold=0)
+
+
+def test_golden_fixtures_cuda(gpu):
+  """The committed golden vectors (tests/golden/golden_v1.npz) against the CUDA path."""
+  import os
+  import kimimaro_b200
+  from tests.synth import sphere, synthetic_tubes
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
+  cases = {"sphere": (sphere(64, 24), {}),
+           "tubes": (synthetic_tubes((96, 96, 64), 12, seed=1), {"anisotropy": (16, 16, 40), "dust_threshold": 100})}
+  for name, (lab, kw) in cases.items():
+    sk = kimimaro_b200.skeletonize(lab, progress=False, **kw)
+    ids = [int(i) for i in g[f"{name}_ids"]]
+    assert sorted(sk) == sorted(ids)
+    for i in ids:
+      assert np.array_equal(sk[i].vertices, g[f"{name}_{i}_v"])
+      assert np.array_equal(sk[i].edges, g[f"{name}_{i}_e"])
+      np.testing.assert_allclose(sk[i].radii, g[f"{name}_{i}_r"], rtol=1e-4)
+
+
+def _blob_volume(hole=True):
+  # a ball with dendrites; with the thresholds below it takes the soma branch of trace.py:108-127
+  lab = np.zeros((128, 128, 96), np.uint8, order="F")
+  xs, ys, zs = np.ogrid[:128, :128, :96]
+  lab[(xs - 64) ** 2 + (ys - 64) ** 2 + (zs - 48) ** 2 <= 30 ** 2] = 1
+  lab[60:68, 60:68, :] = 1
+  lab[:, 62:66, 46:50] = 1
+  lab[90:100, 20:120, 40:44] = 1
+  if hole:
+    lab[60:66, 60:66, 44:50] = 0      # an internal void that fill_voids must close
+  return lab
+
+
+@pytest.mark.parametrize("hole", [False, True])
+def test_soma_branch(gpu, hole):
+  tp = {"scale": 1.5, "const": 3, "pdrf_scale": 100000, "pdrf_exponent": 4, "soma_detection_threshold": 12,
+        "soma_acceptance_threshold": 20, "soma_invalidation_scale": 1.0, "soma_invalidation_const": 2}
+  res, ref = _both(gpu, _blob_volume(hole), teasar_params=tp, dust_threshold=100)
+  assert len(ref) == 1
+  _compare(res, ref)
+
+
+def test_soma_detected_not_accepted(gpu):
+  tp = {"scale": 1.5, "const": 3, "pdrf_scale": 100000, "pdrf_exponent": 4, "soma_detection_threshold": 12,
+        "soma_acceptance_threshold": 1000}
+  res, ref = _both(gpu, _blob_volume(True), teasar_params=tp, dust_threshold=100)
+  _compare(res, ref)
+
+
+def test_extra_targets_and_object_ids(gpu):
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes((96, 96, 64), 8, seed=21)
+  ids = [int(v) for v in np.unique(lab) if v != 0][:4]
+  pts = [tuple(int(c) for c in np.argwhere(lab == ids[0])[5])]
+  res, ref = _both(gpu, lab, anisotropy=(16, 16, 40), dust_threshold=100, object_ids=ids,
+                   extra_targets_after=pts, extra_targets_before=pts)
+  _compare(res, ref)
+
+
+def test_max_paths(gpu):
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes((96, 96, 64), 6, seed=9)
+  tp = {"scale": 1.0, "const": 20, "pdrf_scale": 100000, "pdrf_exponent": 4, "max_paths": 3}
+  res, ref = _both(gpu, lab, anisotropy=(16, 16, 40), dust_threshold=100, teasar_params=tp)
+  _compare(res, ref)
+
+
+def test_uint64_and_int32_labels(gpu):
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes((64, 64, 48), 5, seed=4)
+  big = lab.astype(np.uint64) * np.uint64(2 ** 40 + 7)
+  res, ref = _both(gpu, big, anisotropy=(16, 16, 40), dust_threshold=100)
+  _compare(res, ref)
+  res, ref = _both(gpu, lab.astype(np.int32), anisotropy=(16, 16, 40), dust_threshold=100)
+  _compare(res, ref)
