@@ -111,7 +111,7 @@ int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist
  *           the soma cull and soma invalidation             kimimaro/trace.py:160-168, 246-251
  * d_desc: n_desc records of 64 bytes (16 little-endian 32-bit fields):
  *   segid, root, n_fg, region_off, path_off, path_cap, tb_off, tb_n, ta_off, ta_n, max_paths (0xffffffff =
- *   None), soma_mode, soma_radius (float32), bucket_row, 0, 0
+ *   None), soma_mode, soma_radius (float32), bucket_row, soma_done, pre_invalid
  * d_scratch: 4*sum(n_fg) u32; d_paths: pool of voxel indices, each path [rail ... target] terminated by
  * 0xffffffff; d_out_len / d_out_npaths / d_out_status: n_desc; d_out_stats: 4*n_desc; d_work_counter: 1 u32. */
 int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,
@@ -121,6 +121,13 @@ int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, flo
                     const uint32_t* d_cursor, uint32_t* d_scratch, uint32_t* d_paths,
                     const uint32_t* d_targets, uint32_t* d_out_len, uint32_t* d_out_npaths,
                     int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter, void* stream);
+
+/* the same rolling-ball invalidation, grid-wide, for balls too large for one CTA (the one-off soma
+ * invalidation, kimimaro/trace.py:160-168).  d_fv / d_fs: 2*cap u32 each; count left in d_ctrl[6]. */
+int b2t_invalidate_ball(const uint32_t* d_cc, const float* d_dbf, uint64_t* d_claim, int64_t sx, int64_t sy,
+                        int64_t sz, float wx, float wy, float wz, const uint32_t* d_seeds, uint32_t n_seeds,
+                        float scale, float konst, uint32_t* d_fv, uint32_t* d_fs, uint64_t cap,
+                        uint32_t* d_ctrl, void* stream);
 
 /* skeleton buffers: compact the path segments and fetch radii = DBF[vertex] (kimimaro/trace.py:186-187) */
 int b2t_gather_paths(const uint32_t* d_pool, const uint32_t* d_src_off, const uint32_t* d_len,

@@ -55,23 +55,42 @@ def tiebreak(px, py, x, y, centx, centy, sx, sy, wx, wy):
   return (px, py)
 
 
-def centroid(cc_plane, label, wx, wy):
-  """compute_centroids (pyx:528-588) for one label: float32 running sums, x outer / y inner."""
-  wx, wy = f32(wx), f32(wy)
-  sx, sy = cc_plane.shape
-  xs, ys = np.nonzero(cc_plane == label)          # C-order traversal == x outer, y inner
-  xsum = np.add.accumulate(xs.astype(np.float32), dtype=np.float32)[-1]
-  ysum = np.add.accumulate(ys.astype(np.float32), dtype=np.float32)[-1]
-  ct = f32(xs.size)
-  cx = f32(f32(wx * f32(sx)) / f32(2))
-  cy = f32(f32(wy * f32(sy)) / f32(2))
-  px = f32(f32(wx * xsum) / ct)
-  py = f32(f32(wy * ysum) / ct)
-  if not (f32(px - cx) >= 0):
-    px = f32(px + wx)
-  if not (f32(py - cy) >= 0):
-    py = f32(py + wy)
-  return (int(f32(px / wx)), int(f32(py / wy)))
+class Centroids:
+  """compute_centroids (pyx:528-588), evaluated lazily per label: float32 running sums accumulated in
+  the reference's scan order (x outer, y inner).  One stable sort groups the face by label once."""
+  def __init__(self, cc_plane, wx, wy):
+    self.wx, self.wy = f32(wx), f32(wy)
+    self.sx, self.sy = cc_plane.shape
+    flat = np.ascontiguousarray(cc_plane).reshape(-1)        # C order == x outer, y inner
+    nz = np.flatnonzero(flat)
+    order = np.argsort(flat[nz], kind="stable")              # keeps scan order inside each label
+    self.idx = nz[order]
+    self.labs = flat[self.idx]
+    self.cache = {}
+
+  def __call__(self, label):
+    if label in self.cache:
+      return self.cache[label]
+    a = np.searchsorted(self.labs, label, side="left")
+    b = np.searchsorted(self.labs, label, side="right")
+    lin = self.idx[a:b]
+    xs = (lin // self.sy).astype(np.float32)
+    ys = (lin % self.sy).astype(np.float32)
+    wx, wy = self.wx, self.wy
+    xsum = np.add.accumulate(xs, dtype=np.float32)[-1]
+    ysum = np.add.accumulate(ys, dtype=np.float32)[-1]
+    ct = f32(lin.size)
+    cx = f32(f32(wx * f32(self.sx)) / f32(2))
+    cy = f32(f32(wy * f32(self.sy)) / f32(2))
+    px = f32(f32(wx * xsum) / ct)
+    py = f32(f32(wy * ysum) / ct)
+    if not (f32(px - cx) >= 0):
+      px = f32(px + wx)
+    if not (f32(py - cy) >= 0):
+      py = f32(py + wy)
+    r = (int(f32(px / wx)), int(f32(py / wy)))
+    self.cache[label] = r
+    return r
 
 
 def find_border_targets(dt, cc_plane, wx, wy):
@@ -95,6 +114,7 @@ def find_border_targets(dt, cc_plane, wx, wy):
   uniq, first_pos = np.unique(labs, return_index=True)
   for l in uniq[np.argsort(first_pos)].tolist():  # dict insertion order = first encounter (B.6)
     pts[l] = None
+  cents = None
   order = np.argsort(cand_lab, kind="stable")
   cl, ci = cand_lab[order], cand_idx[order]
   bounds = np.flatnonzero(np.diff(cl)) + 1
@@ -105,7 +125,9 @@ def find_border_targets(dt, cc_plane, wx, wy):
     i0 = int(ci[a])
     cur = (i0 % sx, i0 // sx)
     if b - a > 1:
-      cxy = centroid(cc_plane, l, wx, wy)
+      if cents is None:
+        cents = Centroids(cc_plane, wx, wy)
+      cxy = cents(l)
       for i in ci[a + 1:b].tolist():
         r = tiebreak(cur[0], cur[1], i % sx, i // sx, cxy[0], cxy[1], sx, sy, wx, wy)
         cur = (r[0], r[1])

@@ -581,3 +581,129 @@ B2T_EXPORT int b2t_fill_voids(uint8_t* d_mask, int64_t sx, int64_t sy, int64_t s
   b2t_count_launches(3);
   return B2T_OK;
 }
+
+// =================================================================================================
+// Grid-wide rolling-ball invalidation (same round-synchronous claim semantics as trace.cu's
+// in-CTA version) for seeds whose ball is too large for one CTA: the one-off soma invalidation
+// (kimimaro/trace.py:160-168 -> skeletontricks.pyx:373-418 -> dijkstra_invalidation.hpp:239-332).
+// All SMs expand the frontier; two grid barriers per round (claim, then finalise owners).
+//   d_seeds[n_seeds]: linear indices; radius_i = fl32(fl32(scale * dbf[seed_i]) + konst)
+//   d_fv / d_fs: 2 * cap u32 each (frontier voxels / owning seed), cap >= label's voxel count
+//   d_ctrl: >= 8 u32; the number of invalidated voxels is left in d_ctrl[6]
+// =================================================================================================
+namespace {
+
+struct BallParams {
+  const uint32_t* cc;
+  const float* dbf;
+  unsigned long long* claim;
+  const uint32_t* seeds;
+  uint32_t n_seeds;
+  uint32_t* fv;
+  uint32_t* fs;
+  uint32_t* ctrl;
+  uint64_t cap;
+  Dims d;
+  float wx, wy, wz, scale, konst;
+};
+
+__global__ void ball_seed_kernel(BallParams p) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_seeds) return;
+  const uint32_t v = p.seeds[i];
+  if (atomicCAS(&p.claim[v], ~0ull, 0ull) == ~0ull) {
+    const uint32_t pos = atomicAdd(&p.ctrl[1], 1u);
+    p.fv[p.cap + pos] = v;   // round 1 reads buffer 1
+    p.fs[p.cap + pos] = i;
+    atomicAdd(&p.ctrl[6], 1u);
+  }
+}
+
+__global__ void __launch_bounds__(256) ball_flood_kernel(BallParams p) {
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  int dx = 0, dy = 0, dz = 0;
+  if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; }
+  const int64_t off = (int64_t)dx + (int64_t)dy * p.d.sx + (int64_t)dz * p.d.sxy;
+  const uint32_t ltmask = (1u << lane) - 1u;
+  uint32_t round = 1;
+  for (;;) {
+    const uint32_t n = __ldcg(&p.ctrl[round % 3]);
+    if (n == 0) break;
+    const uint32_t* qv = p.fv + (uint64_t)(round & 1) * p.cap;
+    const uint32_t* qs = p.fs + (uint64_t)(round & 1) * p.cap;
+    uint32_t* nv = p.fv + (uint64_t)((round + 1) & 1) * p.cap;
+    uint32_t* ns = p.fs + (uint64_t)((round + 1) & 1) * p.cap;
+    uint32_t* cnt_out = &p.ctrl[(round + 1) % 3];
+    for (uint32_t it = gwarp; it < n; it += nwarps) {
+      const uint32_t u = __ldcg(&qv[it]), s = __ldcg(&qs[it]);
+      const uint32_t o = p.seeds[s];
+      const uint32_t seg = __ldg(&p.cc[o]);
+      const float r = __fadd_rn(__fmul_rn(p.scale, __ldg(&p.dbf[o])), p.konst);
+      int x, y, z, ox, oy, oz;
+      unravel(u, p.d, x, y, z);
+      unravel(o, p.d, ox, oy, oz);
+      const int nx = x + dx, ny = y + dy, nz = z + dz;
+      bool push = false;
+      uint32_t v = 0;
+      if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < p.d.sx && ny < p.d.sy && nz < p.d.sz) {
+        v = (uint32_t)((int64_t)u + off);
+        if (__ldg(&p.cc[v]) == seg && __ldcg(&p.claim[v]) != 0ull) {
+          const float a = __fmul_rn(p.wx, (float)(nx - ox)), b = __fmul_rn(p.wy, (float)(ny - oy)),
+                      c = __fmul_rn(p.wz, (float)(nz - oz));
+          const float dd = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));
+          if (dd < r) {
+            const unsigned long long cand = ((unsigned long long)__float_as_uint(dd) << 32) | s;
+            push = atomicMin(&p.claim[v], cand) == ~0ull;
+          }
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, push);
+      if (m) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cnt_out, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (push) nv[base + __popc(m & ltmask)] = v;
+      }
+    }
+    grid.sync();
+    const uint32_t n_next = __ldcg(cnt_out);
+    for (uint32_t i = tid; i < n_next; i += nthreads) {
+      const uint32_t v = nv[i];
+      ns[i] = (uint32_t)__ldcg(&p.claim[v]);
+      p.claim[v] = 0ull;
+    }
+    if (tid == 0) { p.ctrl[round % 3] = 0; p.ctrl[6] += n_next; }
+    grid.sync();
+    round++;
+  }
+}
+
+}  // namespace
+
+B2T_EXPORT int b2t_invalidate_ball(const uint32_t* d_cc, const float* d_dbf, uint64_t* d_claim, int64_t sx, int64_t sy,
+                                   int64_t sz, float wx, float wy, float wz, const uint32_t* d_seeds, uint32_t n_seeds,
+                                   float scale, float konst, uint32_t* d_fv, uint32_t* d_fs, uint64_t cap,
+                                   uint32_t* d_ctrl, void* stream) {
+  if (int rc = check_dims(sx, sy, sz)) return rc;
+  B2T_REQUIRE(d_cc && d_dbf && d_claim && d_seeds && d_fv && d_fs && d_ctrl, "b2t_invalidate_ball: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  B2T_CUDA_TRY(cudaMemsetAsync(d_ctrl, 0, 8 * sizeof(uint32_t), st));
+  if (n_seeds == 0) return B2T_OK;
+  BallParams p;
+  p.cc = d_cc; p.dbf = d_dbf; p.claim = reinterpret_cast<unsigned long long*>(d_claim); p.seeds = d_seeds;
+  p.n_seeds = n_seeds; p.fv = d_fv; p.fs = d_fs; p.ctrl = d_ctrl; p.cap = cap;
+  p.d = Dims{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
+  p.wx = wx; p.wy = wy; p.wz = wz; p.scale = scale; p.konst = konst;
+  ball_seed_kernel<<<(n_seeds + 255) / 256, 256, 0, st>>>(p);
+  int blocks = 0;
+  if (int rc = coop_grid((const void*)ball_flood_kernel, 256, 0, &blocks)) return rc;
+  void* args[] = {&p};
+  B2T_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)ball_flood_kernel, dim3(blocks), dim3(256), args, 0, st));
+  b2t_count_launches(2);
+  return B2T_OK;
+}

@@ -57,7 +57,8 @@ struct LabelDesc {
   uint32_t soma_mode;   // trace.py:118-127
   float soma_radius;    // dbf_max * soma_invalidation_scale + soma_invalidation_const (float32)
   uint32_t bucket_row;  // row of this label in the (label x bucket) tables = its cc id
-  uint32_t pad0, pad1;
+  uint32_t soma_done;   // 1: the one-off soma invalidation already ran grid-wide (b2t_invalidate_ball)
+  uint32_t pre_invalid; // voxels it invalidated
 };
 
 struct Params {
@@ -453,7 +454,8 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
   uint32_t valid = L.n_fg;
   int32_t status = 0;
   if (L.soma_mode) {            // one-off soma invalidation around the root (trace.py:160-168)
-    const uint32_t n = invalidate(A, L, &L.root, 1, prm.soma_scale, prm.soma_const, r0, r1, r2, r3, S);
+    const uint32_t n = L.soma_done ? L.pre_invalid
+                                   : invalidate(A, L, &L.root, 1, prm.soma_scale, prm.soma_const, r0, r1, r2, r3, S);
     valid -= min(valid, n);
   }
   uint32_t tb_n = L.tb_n, ta_n = L.ta_n;

@@ -37,6 +37,8 @@ _lib.declare("b2t_trace_batch", [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i6
                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp])
 _lib.declare("b2t_ccl26_roots", [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp])
 _lib.declare("b2t_ccl_relabel", [c_vp, c_vp, c_u64, c_vp])
+_lib.declare("b2t_invalidate_ball", [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_u32, c_f32, c_f32,
+                                     c_vp, c_vp, c_u64, c_vp, c_vp])
 _lib.declare("b2t_gather_paths", [c_vp, c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp])
 
 NBUCKETS = 256
@@ -164,7 +166,7 @@ DESC_DTYPE = np.dtype([
   ("segid", "<u4"), ("root", "<u4"), ("n_fg", "<u4"), ("region_off", "<u4"), ("path_off", "<u4"),
   ("path_cap", "<u4"), ("tb_off", "<u4"), ("tb_n", "<u4"), ("ta_off", "<u4"), ("ta_n", "<u4"),
   ("max_paths", "<u4"), ("soma_mode", "<u4"), ("soma_radius", "<f4"), ("bucket_row", "<u4"),
-  ("pad0", "<u4"), ("pad1", "<u4"),
+  ("soma_done", "<u4"), ("pre_invalid", "<u4"),
 ])
 assert DESC_DTYPE.itemsize == 64
 
@@ -272,9 +274,23 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
     d["soma_radius"] = np.float32(j.get("soma_radius", 0.0))
     d["bucket_row"] = j["segid"]
   assert path_off < 2 ** 32 and 4 * region < 2 ** 34
+  scratch = torch.empty(4 * max(region, 1), dtype=torch.int32, device=dev)
+  # soma labels: the one-off ball around the root (trace.py:160-168) is far too large for one CTA
+  for slot in range(n_jobs):
+    if desc[slot]["soma_mode"]:
+      n = int(desc[slot]["n_fg"])
+      base = 4 * int(desc[slot]["region_off"])
+      seeds = _dev(np.array([desc[slot]["root"]], dtype=np.uint32).view(np.int32))
+      check(L.b2t_invalidate_ball(_p(d_cc), _p(d_dbf), _p(claim), c_i64(sx), c_i64(sy), c_i64(sz),
+                                  c_f32(anisotropy[0]), c_f32(anisotropy[1]), c_f32(anisotropy[2]), _p(seeds), c_u32(1),
+                                  c_f32(params["soma_invalidation_scale"]), c_f32(params["soma_invalidation_const"]),
+                                  c_vp(scratch.data_ptr() + 4 * base), c_vp(scratch.data_ptr() + 4 * (base + 2 * n)),
+                                  c_u64(n), _p(ws.ctrl), stream_ptr()), "b2t_invalidate_ball")
+      desc[slot]["soma_done"] = 1
+      desc[slot]["pre_invalid"] = int(ws.ctrl[6].item())
+  lap("soma_ball")
   d_desc = _dev(desc.view(np.uint8))
   d_targets = _dev(np.array(targets + [0], dtype=np.uint32).view(np.int32))
-  scratch = torch.empty(4 * max(region, 1), dtype=torch.int32, device=dev)
   paths = torch.empty(max(path_off, 1), dtype=torch.int32, device=dev)
   out_len = torch.zeros(n_jobs, dtype=torch.int32, device=dev)
   out_np = torch.zeros(n_jobs, dtype=torch.int32, device=dev)
