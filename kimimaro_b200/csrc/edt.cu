@@ -44,20 +44,32 @@ edt_pass_x_kernel(const T* __restrict__ labels, float* __restrict__ out, int sx,
   float* orow = out + row * sx;
   const int K = (sx + 31) >> 5;
 
-  // sweep 1: label-change and non-zero bit masks, one ballot per group of 32 voxels
+  // sweep 1: label-change and non-zero bit masks, one ballot per group of 32 voxels.
+  // Loads are issued 16 groups (2 KB of uint32 labels per warp) at a time before any of them is consumed.
   T carry = 0;
-#pragma unroll 4
-  for (int k = 0; k < K; k++) {
-    const int p = (k << 5) + lane;
-    const bool valid = p < sx;
-    const T lab = valid ? lrow[p] : T(0);
-    T prev = __shfl_up_sync(0xffffffffu, lab, 1);
-    if (lane == 0) prev = carry;
-    const bool brk = valid && (p == 0 || lab != prev);
-    const uint32_t mb = __ballot_sync(0xffffffffu, brk);
-    const uint32_t mn = __ballot_sync(0xffffffffu, valid && lab != T(0));
-    carry = __shfl_sync(0xffffffffu, lab, 31);
-    if (lane == 0) { s_brk[warp][k] = mb; s_nz[warp][k] = mn; }
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    T lab16[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const int p = ((k0 + j) << 5) + lane;
+      lab16[j] = (p < sx) ? lrow[p] : T(0);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const int k = k0 + j;
+      if (k < K) {
+        const int p = (k << 5) + lane;
+        const bool valid = p < sx;
+        const T lab = lab16[j];
+        T prev = __shfl_up_sync(0xffffffffu, lab, 1);
+        if (lane == 0) prev = carry;
+        const bool brk = valid && (p == 0 || lab != prev);
+        const uint32_t mb = __ballot_sync(0xffffffffu, brk);
+        const uint32_t mn = __ballot_sync(0xffffffffu, valid && lab != T(0));
+        carry = __shfl_sync(0xffffffffu, lab, 31);
+        if (lane == 0) { s_brk[warp][k] = mb; s_nz[warp][k] = mn; }
+      }
+    }
   }
   __syncwarp();
   // sweep 2 (uniform): position of the first label change after each group
@@ -106,11 +118,40 @@ edt_pass_x_kernel(const T* __restrict__ labels, float* __restrict__ out, int sx,
 // pass y / z: columns of length n with element stride cstride; lanes run along the contiguous
 // axis.  grid.x = tiles of 32 columns, grid.y = index along the remaining axis.
 // ------------------------------------------------------------------------------------------------
+constexpr int kBlk = 8;   // rows per summary block of the column pass
+
+// One candidate row of the windowed search.  Returns true when the walk in this direction is over.
+// u = staged value of the row (sign bit = label change between this row and the previous one),
+// d = distance in rows from the voxel being solved.
+template <bool UP>
+__device__ __forceinline__ bool edt_visit(uint32_t u, float d, float w2, float& best, bool edge_counts) {
+  const float wd = __fmul_rn(__fmul_rn(w2, d), d);
+  if (wd >= best) return true;                       // no farther row can win: w^2 d^2 only grows
+  if (UP) {
+    // walking towards row 0: this row is still inside the run; a flag on it closes the run above it
+    best = fminf(best, __fadd_rn(__uint_as_float(u & 0x7fffffffu), wd));
+    if (u >> 31) {
+      if (edge_counts) { const float e = d + 1.0f; best = fminf(best, __fmul_rn(__fmul_rn(w2, e), e)); }
+      return true;
+    }
+    return false;
+  } else {
+    // walking towards the end: a flag on this row means the run ended on the previous one
+    if (u >> 31) { best = fminf(best, wd); return true; }
+    best = fminf(best, __fadd_rn(__uint_as_float(u), wd));
+    return false;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 edt_pass_col_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, int64_t cstride, int nx,
                     int64_t ostride, float w, int black_border, int do_sqrt) {
-  extern __shared__ float g[];  // [n][32], sign bit = "label differs from the previous voxel of the column"
+  // g[n][32]: staged column values, sign bit = "label differs from the previous voxel of the column"
+  // sm[nb][32]: per 8-row block: minimum |value| of the block, sign bit = "some row of the block is flagged"
+  extern __shared__ float g[];
+  const int nb = (n + kBlk - 1) / kBlk;
+  float* sm = g + (size_t)n * 32;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int x = blockIdx.x * 32 + lane;
@@ -129,51 +170,83 @@ edt_pass_col_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, 
     g[y * 32 + lane] = v;
   }
   __syncthreads();
+  for (int b = warp; b < nb; b += kWarpsPerBlock) {
+    uint32_t mn = 0x7f800000u, flag = 0;
+    const int r1 = min(n, (b + 1) * kBlk);
+    for (int r = b * kBlk; r < r1; r++) {
+      const uint32_t u = __float_as_uint(g[r * 32 + lane]);
+      mn = min(mn, u & 0x7fffffffu);   // non-negative floats order like their bit patterns
+      flag |= u & 0x80000000u;
+    }
+    sm[b * 32 + lane] = __uint_as_float(mn | flag);
+  }
+  __syncthreads();
   if (!xin) return;
 
   const float w2 = __fmul_rn(w, w);
+  const bool bb = black_border != 0;
   for (int i = warp; i < n; i += kWarpsPerBlock) {
     const uint32_t gi = __float_as_uint(g[i * 32 + lane]);
     float best = __uint_as_float(gi & 0x7fffffffu);
     if (best != 0.0f) {  // background stays 0
-      // walk towards the start of the column
+      const int bi = i / kBlk;
+      // ---------------- towards row 0 ----------------
       {
-        bool brk = (gi >> 31) != 0;
-        int top = i;
-        float d = 1.0f;
-        for (;;) {
-          const float wd = __fmul_rn(__fmul_rn(w2, d), d);
-          if (brk) {
-            if (top > 0 || black_border) best = fminf(best, wd);
-            break;
-          }
+        bool done = false;
+        if (gi >> 31) {                                  // the run starts on this very row
+          if (i > 0 || bb) best = fminf(best, w2);
+          done = true;
+        }
+        int r = i - 1;
+        for (; !done && r >= bi * kBlk; r--)              // rest of the own block, row by row
+          done = edt_visit<true>(__float_as_uint(g[r * 32 + lane]), (float)(i - r), w2, best, (r > 0) || bb);
+        for (int b = bi - 1; !done && b >= 0; b--) {     // whole blocks above
+          const float dmin = (float)(i - (b * kBlk + kBlk - 1));
+          const float wd = __fmul_rn(__fmul_rn(w2, dmin), dmin);
           if (wd >= best) break;
-          top--;
-          const uint32_t u = __float_as_uint(g[top * 32 + lane]);
-          best = fminf(best, __fadd_rn(__uint_as_float(u & 0x7fffffffu), wd));
-          brk = (u >> 31) != 0;
-          d += 1.0f;
+          const uint32_t s = __float_as_uint(sm[b * 32 + lane]);
+          if (!(s >> 31) && __fadd_rn(__uint_as_float(s), wd) >= best) continue;   // nothing in it can win
+          uint32_t u[kBlk];
+#pragma unroll
+          for (int k = 0; k < kBlk; k++) u[k] = __float_as_uint(g[(b * kBlk + kBlk - 1 - k) * 32 + lane]);
+#pragma unroll
+          for (int k = 0; k < kBlk; k++) {
+            if (!done) {
+              const int rr = b * kBlk + kBlk - 1 - k;
+              done = edt_visit<true>(u[k], (float)(i - rr), w2, best, (rr > 0) || bb);
+            }
+          }
         }
       }
-      // walk towards the end of the column
+      // ---------------- towards the end of the column ----------------
       {
-        int bot = i + 1;
-        float d = 1.0f;
-        for (;;) {
-          const float wd = __fmul_rn(__fmul_rn(w2, d), d);
-          if (bot >= n) {
-            if (black_border) best = fminf(best, wd);
-            break;
+        bool done = false;
+        int r = i + 1;
+        const int own_end = min(n, (bi + 1) * kBlk);
+        for (; !done && r < own_end; r++)
+          done = edt_visit<false>(__float_as_uint(g[r * 32 + lane]), (float)(r - i), w2, best, false);
+        for (int b = bi + 1; !done && b < nb; b++) {
+          const float dmin = (float)(b * kBlk - i);
+          const float wd = __fmul_rn(__fmul_rn(w2, dmin), dmin);
+          if (wd >= best) { done = true; break; }
+          const uint32_t s = __float_as_uint(sm[b * 32 + lane]);
+          if (!(s >> 31) && __fadd_rn(__uint_as_float(s), wd) >= best) continue;
+          const int r1 = min(n, (b + 1) * kBlk);
+          if (r1 - b * kBlk == kBlk) {
+            uint32_t u[kBlk];
+#pragma unroll
+            for (int k = 0; k < kBlk; k++) u[k] = __float_as_uint(g[(b * kBlk + k) * 32 + lane]);
+#pragma unroll
+            for (int k = 0; k < kBlk; k++)
+              if (!done) done = edt_visit<false>(u[k], (float)(b * kBlk + k - i), w2, best, false);
+          } else {
+            for (int rr = b * kBlk; !done && rr < r1; rr++)
+              done = edt_visit<false>(__float_as_uint(g[rr * 32 + lane]), (float)(rr - i), w2, best, false);
           }
-          if (wd >= best) break;
-          const uint32_t u = __float_as_uint(g[bot * 32 + lane]);
-          if (u >> 31) {
-            best = fminf(best, wd);
-            break;
-          }
-          best = fminf(best, __fadd_rn(__uint_as_float(u), wd));
-          bot++;
-          d += 1.0f;
+        }
+        if (!done && bb) {                               // ran off the end of the array inside the run
+          const float e = (float)(n - i);
+          best = fminf(best, __fmul_rn(__fmul_rn(w2, e), e));
         }
       }
       if (do_sqrt) best = sqrtf(best);
@@ -192,14 +265,14 @@ int edt_launch(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wx, fl
                                                                           black_border);
   }
   {
-    const size_t smem = (size_t)sy * 32 * sizeof(float);
+    const size_t smem = ((size_t)sy + (sy + kBlk - 1) / kBlk) * 32 * sizeof(float);
     B2T_CUDA_TRY(cudaFuncSetAttribute(edt_pass_col_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     dim3 grid((unsigned)b2t_ceil_div(sx, 32), (unsigned)sz);
     edt_pass_col_kernel<T><<<grid, kWarpsPerBlock * 32, smem, st>>>(labels, out, (int)sy, sx, (int)sx, sx * sy, wy,
                                                                    black_border, ndim == 2);
   }
   if (ndim == 3) {
-    const size_t smem = (size_t)sz * 32 * sizeof(float);
+    const size_t smem = ((size_t)sz + (sz + kBlk - 1) / kBlk) * 32 * sizeof(float);
     dim3 grid((unsigned)b2t_ceil_div(sx, 32), (unsigned)sy);
     edt_pass_col_kernel<T><<<grid, kWarpsPerBlock * 32, smem, st>>>(labels, out, (int)sz, sx * sy, (int)sx, sx, wz,
                                                                    black_border, 1);
@@ -219,7 +292,7 @@ B2T_EXPORT int b2t_edt(const void* d_labels, int label_bytes, int64_t sx, int64_
   B2T_REQUIRE(ndim == 2 || ndim == 3, "b2t_edt: ndim must be 2 or 3");
   B2T_REQUIRE(ndim == 3 || sz == 1, "b2t_edt: ndim=2 requires sz == 1");
   B2T_REQUIRE(sx <= 32 * kMaxGroups, "b2t_edt: sx > %d not supported", 32 * kMaxGroups);
-  B2T_REQUIRE(sy * 128 <= 227 * 1024 && sz * 128 <= 227 * 1024, "b2t_edt: sy, sz > 1816 not supported");
+  B2T_REQUIRE(sy * 144 <= 227 * 1024 && sz * 144 <= 227 * 1024, "b2t_edt: sy, sz > 1614 not supported");
   B2T_REQUIRE(sz <= 65535 && sy <= 65535, "b2t_edt: extent too large for grid.y");
   cudaStream_t st = (cudaStream_t)stream;
   black_border = black_border ? 1 : 0;

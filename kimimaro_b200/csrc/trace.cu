@@ -78,7 +78,7 @@ struct Pools {
   uint32_t* out_len;               // per desc: slots written
   uint32_t* out_npaths;            // per desc
   int32_t* out_status;             // per desc: 0 ok, <0 error
-  uint32_t* out_stats;             // per desc x 4: relaxations, rounds, invalidated, target scans
+  uint32_t* out_stats;             // per desc x 4: relaxations, rounds, invalidated, elapsed microseconds
   uint32_t* work_counter;
 };
 
@@ -445,7 +445,9 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
   uint32_t* r2 = scr + 2ull * L.n_fg;
   uint32_t* r3 = scr + 3ull * L.n_fg;
   uint32_t* out = P.paths + L.path_off;
+  unsigned long long t_start = 0;
   if (threadIdx.x == 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     S.bucket = prm.nbuckets - 1;
     S.relax = 0; S.rounds = 0; S.invalidated = 0; S.scans = 0;
     A.pdrf[L.root] = 0.0f;      // parents[root] = 0: the first rail (trace.py:220)
@@ -520,7 +522,9 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
     P.out_stats[4 * job + 0] = S.relax;
     P.out_stats[4 * job + 1] = S.rounds;
     P.out_stats[4 * job + 2] = S.invalidated;
-    P.out_stats[4 * job + 3] = S.scans;
+    unsigned long long t_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    P.out_stats[4 * job + 3] = (uint32_t)((t_end - t_start) / 1000ull);   // microseconds this label held its CTA
   }
   __syncthreads();
 }
