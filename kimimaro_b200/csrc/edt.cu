@@ -18,6 +18,8 @@
 //            parabola height and the "label changes here" flag.
 //            R L + R 4 + W 4 bytes per voxel; sqrt fused into the last pass.
 // Algorithmic traffic: (3L + 20) bytes per voxel; 32 B/voxel for uint32 labels.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -143,7 +145,7 @@ __device__ __forceinline__ bool edt_visit(uint32_t u, float d, float w2, float& 
   }
 }
 
-template <typename T>
+template <typename T, bool SKIP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 edt_pass_col_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, int64_t cstride, int nx,
                     int64_t ostride, float w, int black_border, int do_sqrt) {
@@ -158,29 +160,52 @@ edt_pass_col_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, 
   const bool xin = x < nx;
   const int64_t base = (int64_t)blockIdx.y * ostride + x;
 
-  for (int y = warp; y < n; y += kWarpsPerBlock) {
-    float v = 0.0f;
-    if (xin) {
-      const int64_t idx = base + (int64_t)y * cstride;
-      v = f[idx];
-      const T lab = labels[idx];
-      const bool brk = (y == 0) || (labels[idx - cstride] != lab);
-      if (brk) v = __uint_as_float(__float_as_uint(v) | 0x80000000u);
+  // stage the tile: every warp owns a contiguous band of rows and keeps 16 independent 128-byte
+  // loads in flight (8 rows of f + 8 rows of labels) before touching any of them
+  {
+    const int R = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int y0 = warp * R, y1 = min(n, y0 + R);
+    T prev = T(0);
+    if (xin && y0 > 0 && y0 < n) prev = labels[base + (int64_t)(y0 - 1) * cstride];
+    for (int yb = y0; yb < y1; yb += 8) {
+      float fv[8];
+      T lv[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int y = yb + k;
+        fv[k] = 0.0f; lv[k] = T(0);
+        if (xin && y < y1) {
+          const int64_t idx = base + (int64_t)y * cstride;
+          fv[k] = f[idx];
+          lv[k] = labels[idx];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int y = yb + k;
+        if (y < y1) {
+          float v = fv[k];
+          if (xin && (y == 0 || lv[k] != prev)) v = __uint_as_float(__float_as_uint(v) | 0x80000000u);
+          g[y * 32 + lane] = v;
+          prev = lv[k];
+        }
+      }
     }
-    g[y * 32 + lane] = v;
   }
   __syncthreads();
-  for (int b = warp; b < nb; b += kWarpsPerBlock) {
-    uint32_t mn = 0x7f800000u, flag = 0;
-    const int r1 = min(n, (b + 1) * kBlk);
-    for (int r = b * kBlk; r < r1; r++) {
-      const uint32_t u = __float_as_uint(g[r * 32 + lane]);
-      mn = min(mn, u & 0x7fffffffu);   // non-negative floats order like their bit patterns
-      flag |= u & 0x80000000u;
+  if (SKIP) {
+    for (int b = warp; b < nb; b += kWarpsPerBlock) {
+      uint32_t mn = 0x7f800000u, flag = 0;
+      const int r1 = min(n, (b + 1) * kBlk);
+      for (int r = b * kBlk; r < r1; r++) {
+        const uint32_t u = __float_as_uint(g[r * 32 + lane]);
+        mn = min(mn, u & 0x7fffffffu);   // non-negative floats order like their bit patterns
+        flag |= u & 0x80000000u;
+      }
+      sm[b * 32 + lane] = __uint_as_float(mn | flag);
     }
-    sm[b * 32 + lane] = __uint_as_float(mn | flag);
+    __syncthreads();
   }
-  __syncthreads();
   if (!xin) return;
 
   const float w2 = __fmul_rn(w, w);
@@ -204,8 +229,10 @@ edt_pass_col_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, 
           const float dmin = (float)(i - (b * kBlk + kBlk - 1));
           const float wd = __fmul_rn(__fmul_rn(w2, dmin), dmin);
           if (wd >= best) break;
-          const uint32_t s = __float_as_uint(sm[b * 32 + lane]);
-          if (!(s >> 31) && __fadd_rn(__uint_as_float(s), wd) >= best) continue;   // nothing in it can win
+          if (SKIP) {
+            const uint32_t s = __float_as_uint(sm[b * 32 + lane]);
+            if (!(s >> 31) && __fadd_rn(__uint_as_float(s), wd) >= best) continue;   // nothing in it can win
+          }
           uint32_t u[kBlk];
 #pragma unroll
           for (int k = 0; k < kBlk; k++) u[k] = __float_as_uint(g[(b * kBlk + kBlk - 1 - k) * 32 + lane]);
@@ -229,8 +256,10 @@ edt_pass_col_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, 
           const float dmin = (float)(b * kBlk - i);
           const float wd = __fmul_rn(__fmul_rn(w2, dmin), dmin);
           if (wd >= best) { done = true; break; }
-          const uint32_t s = __float_as_uint(sm[b * 32 + lane]);
-          if (!(s >> 31) && __fadd_rn(__uint_as_float(s), wd) >= best) continue;
+          if (SKIP) {
+            const uint32_t s = __float_as_uint(sm[b * 32 + lane]);
+            if (!(s >> 31) && __fadd_rn(__uint_as_float(s), wd) >= best) continue;
+          }
           const int r1 = min(n, (b + 1) * kBlk);
           if (r1 - b * kBlk == kBlk) {
             uint32_t u[kBlk];
@@ -259,6 +288,7 @@ template <typename T>
 int edt_launch(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz, int black_border,
                int ndim, float* out, cudaStream_t st) {
   const int64_t nrows = sy * sz;
+  static const bool skip = []() { const char* e = getenv("B2T_EDT_SKIP"); return e ? (e[0] != '0') : true; }();
   {
     const int64_t blocks = (nrows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     edt_pass_x_kernel<T><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(labels, out, (int)sx, nrows, wx,
@@ -266,16 +296,25 @@ int edt_launch(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wx, fl
   }
   {
     const size_t smem = ((size_t)sy + (sy + kBlk - 1) / kBlk) * 32 * sizeof(float);
-    B2T_CUDA_TRY(cudaFuncSetAttribute(edt_pass_col_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2T_CUDA_TRY(cudaFuncSetAttribute(edt_pass_col_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2T_CUDA_TRY(cudaFuncSetAttribute(edt_pass_col_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     dim3 grid((unsigned)b2t_ceil_div(sx, 32), (unsigned)sz);
-    edt_pass_col_kernel<T><<<grid, kWarpsPerBlock * 32, smem, st>>>(labels, out, (int)sy, sx, (int)sx, sx * sy, wy,
-                                                                   black_border, ndim == 2);
+    if (skip)
+      edt_pass_col_kernel<T, true><<<grid, kWarpsPerBlock * 32, smem, st>>>(labels, out, (int)sy, sx, (int)sx, sx * sy, wy,
+                                                                           black_border, ndim == 2);
+    else
+      edt_pass_col_kernel<T, false><<<grid, kWarpsPerBlock * 32, smem, st>>>(labels, out, (int)sy, sx, (int)sx, sx * sy, wy,
+                                                                            black_border, ndim == 2);
   }
   if (ndim == 3) {
     const size_t smem = ((size_t)sz + (sz + kBlk - 1) / kBlk) * 32 * sizeof(float);
     dim3 grid((unsigned)b2t_ceil_div(sx, 32), (unsigned)sy);
-    edt_pass_col_kernel<T><<<grid, kWarpsPerBlock * 32, smem, st>>>(labels, out, (int)sz, sx * sy, (int)sx, sx, wz,
-                                                                   black_border, 1);
+    if (skip)
+      edt_pass_col_kernel<T, true><<<grid, kWarpsPerBlock * 32, smem, st>>>(labels, out, (int)sz, sx * sy, (int)sx, sx, wz,
+                                                                           black_border, 1);
+    else
+      edt_pass_col_kernel<T, false><<<grid, kWarpsPerBlock * 32, smem, st>>>(labels, out, (int)sz, sx * sy, (int)sx, sx, wz,
+                                                                            black_border, 1);
   }
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(ndim == 3 ? 3 : 2);

@@ -273,13 +273,13 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
     d["soma_mode"] = 1 if j["soma_mode"] else 0
     d["soma_radius"] = np.float32(j.get("soma_radius", 0.0))
     d["bucket_row"] = j["segid"]
-  assert path_off < 2 ** 32 and 4 * region < 2 ** 34
-  scratch = torch.empty(4 * max(region, 1), dtype=torch.int32, device=dev)
+  assert path_off < 2 ** 32 and 5 * region < 2 ** 34
+  scratch = torch.empty(5 * max(region, 1), dtype=torch.int32, device=dev)
   # soma labels: the one-off ball around the root (trace.py:160-168) is far too large for one CTA
   for slot in range(n_jobs):
     if desc[slot]["soma_mode"]:
       n = int(desc[slot]["n_fg"])
-      base = 4 * int(desc[slot]["region_off"])
+      base = 5 * int(desc[slot]["region_off"])
       seeds = _dev(np.array([desc[slot]["root"]], dtype=np.uint32).view(np.int32))
       check(L.b2t_invalidate_ball(_p(d_cc), _p(d_dbf), _p(claim), c_i64(sx), c_i64(sy), c_i64(sz),
                                   c_f32(anisotropy[0]), c_f32(anisotropy[1]), c_f32(anisotropy[2]), _p(seeds), c_u32(1),
@@ -322,68 +322,83 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
   d_dstoff = _dev(seg_off[:-1].astype(np.uint64).view(np.int64))
   check(L.b2t_gather_paths(_p(paths), _p(d_srcoff), _p(out_len), _p(d_dstoff), c_u32(n_jobs), _p(d_dbf), _p(d_vox),
                            _p(d_rad), stream_ptr()), "b2t_gather_paths")
-  vox = d_vox.cpu().numpy().view(np.uint32)[:total]
-  rad = d_rad.cpu().numpy()[:total]
   lap("gather")
   stats = {"stats": out_stats.cpu().numpy().reshape(-1, 4), "npaths": out_np.cpu().numpy(),
            "segids": desc["segid"].copy()}
-  return vox, rad, seg_off, desc["segid"].astype(np.int64), stats
+  return d_vox[:total], d_rad[:total], seg_off, desc["segid"].astype(np.int64), stats
 
 
 # ------------------------------------------------------------------------------------------------
 # skeleton assembly (trace.py:182-192, intake.py:509-517, 587-593) for all labels at once
 # ------------------------------------------------------------------------------------------------
-def assemble(vox, rad, seg_off, seg_ids, shape, anisotropy, offset=(0, 0, 0)):
-  """Returns {cc segid: (vertices f32 [N,3] physical, edges u32 [M,2], radii f32 [N])}."""
+def assemble(d_vox, d_rad, seg_off, seg_ids, shape, anisotropy, offset=(0, 0, 0)):
+  """
+  Skeleton.from_path / simple_merge / consolidate (trace.py:182-184) for ALL labels at once,
+  on the device, with torch sort/unique/cumsum as plumbing (the reference's counterpart is np.unique on
+  the host): unique vertices per label in lexicographic (x,y,z) order, edges remapped / sorted / unique /
+  no self loops, vertices without edges dropped, radii of the vertex, then voxel -> physical units in
+  float32 exactly like intake.py:509-513.
+  Returns {cc segid: (vertices f32 [N,3] physical, edges u32 [M,2], radii f32 [N])} (numpy views).
+  """
   sx, sy, sz = shape
-  n = vox.size
+  V = sx * sy * sz
   out = {}
+  n = int(d_vox.numel())
   if n == 0:
     return out
-  lab_of = np.repeat(np.arange(seg_ids.size, dtype=np.int64), np.diff(seg_off))
-  is_vtx = vox != NONE
-  v = vox.astype(np.int64)
+  dev = d_vox.device
+  n_seg = int(seg_ids.size)
+  lens = torch.as_tensor(np.diff(seg_off), device=dev)
+  lab_of = torch.repeat_interleave(torch.arange(n_seg, device=dev, dtype=torch.int64), lens)
+  is_vtx = d_vox != -1                                       # 0xffffffff terminators
+  v = d_vox.to(torch.int64) & 0xFFFFFFFF
   z = v // (sx * sy)
   r = v - z * (sx * sy)
   y = r // sx
   x = r - y * sx
-  # lexicographic (x,y,z) order per label == np.unique(vertices, axis=0) of consolidate()
-  ckey = (x * sy + y) * sz + z
-  gkey = lab_of * np.int64(sx * sy * sz) + ckey
-  vi = np.flatnonzero(is_vtx)
-  uniq, first, inverse = np.unique(gkey[vi], return_index=True, return_inverse=True)
-  uid = np.full(n, -1, dtype=np.int64)
+  gkey = lab_of * V + ((x * sy + y) * sz + z)                # label-major, then lexicographic (x,y,z)
+  vi = torch.nonzero(is_vtx).view(-1)
+  uniq, inverse = torch.unique(gkey[vi], sorted=True, return_inverse=True)
+  nu = int(uniq.numel())
+  uid = torch.full((n,), -1, dtype=torch.int64, device=dev)
   uid[vi] = inverse
-  # edges between consecutive entries of the same path
-  a = np.flatnonzero(is_vtx[:-1] & is_vtx[1:])
+  a = torch.nonzero(is_vtx[:-1] & is_vtx[1:]).view(-1)       # consecutive entries of one path
   e0, e1 = uid[a], uid[a + 1]
-  lo, hi = np.minimum(e0, e1), np.maximum(e0, e1)
+  lo, hi = torch.minimum(e0, e1), torch.maximum(e0, e1)
   keep = lo != hi
-  nu = uniq.size
-  ekey = np.unique(lo[keep] * np.int64(nu) + hi[keep])
+  ekey = torch.unique(lo[keep] * nu + hi[keep], sorted=True)
   ea, eb = ekey // nu, ekey % nu
-  # drop vertices without edges (remove_disconnected_vertices)
-  used = np.zeros(nu, dtype=bool)
+  used = torch.zeros(nu, dtype=torch.bool, device=dev)
   used[ea] = True
   used[eb] = True
-  newid = np.cumsum(used) - 1
-  ulab = lab_of[vi[first]]
-  ux, uy, uz = x[vi[first]], y[vi[first]], z[vi[first]]
-  urad = rad[vi[first]]
-  ulab_k, ux, uy, uz, urad = ulab[used], ux[used], uy[used], uz[used], urad[used]
+  newid = torch.cumsum(used, 0) - 1
+  urad = torch.empty(nu, dtype=torch.float32, device=dev)
+  urad[inverse] = d_rad[vi]                                  # every occurrence of a vertex carries the same DBF
+  ulab = uniq // V
+  ck = uniq - ulab * V
+  ux = ck // (sy * sz)
+  uy = (ck // sz) % sy
+  uz = ck % sz
+  ulab_k = ulab[used]
+  verts = torch.stack([ux[used], uy[used], uz[used]], dim=1).to(torch.float32)
+  an = torch.as_tensor(np.asarray(anisotropy, dtype=np.float32), device=dev)
+  off = torch.as_tensor(np.asarray(offset, dtype=np.float32), device=dev)
+  verts = (verts + off) * an                                 # float32, intake.py:509-513
   ea, eb = newid[ea], newid[eb]
-  elab = ulab_k[ea] if ea.size else np.zeros(0, np.int64)
-  an = np.asarray(anisotropy, dtype=np.float32)
-  off = np.asarray(offset, dtype=np.float32)
-  verts = np.stack([ux, uy, uz], axis=1).astype(np.float32)
-  verts = np.multiply(verts + off, an, dtype=np.float32)           # intake.py:509-513
-  vstart = np.searchsorted(ulab_k, np.arange(seg_ids.size + 1))
-  estart = np.searchsorted(elab, np.arange(seg_ids.size + 1))
-  for k in range(seg_ids.size):
-    v0, v1 = vstart[k], vstart[k + 1]
+  elab = ulab_k[ea]
+  bounds = torch.arange(n_seg + 1, device=dev, dtype=torch.int64)
+  vstart = torch.searchsorted(ulab_k.contiguous(), bounds)
+  estart = torch.searchsorted(elab.contiguous(), bounds)
+  edges = torch.stack([ea - vstart[elab], eb - vstart[elab]], dim=1).to(torch.int32)
+  h_verts = verts.cpu().numpy()
+  h_edges = edges.cpu().numpy().view(np.uint32)
+  h_rad = urad[used].cpu().numpy()
+  h_vs = vstart.cpu().numpy()
+  h_es = estart.cpu().numpy()
+  for k in range(n_seg):
+    v0, v1 = int(h_vs[k]), int(h_vs[k + 1])
     if v1 == v0:
       continue
-    e0_, e1_ = estart[k], estart[k + 1]
-    edges = np.stack([ea[e0_:e1_] - v0, eb[e0_:e1_] - v0], axis=1).astype(np.uint32)
-    out[int(seg_ids[k])] = (verts[v0:v1], edges, urad[v0:v1].astype(np.float32))
+    e0_, e1_ = int(h_es[k]), int(h_es[k + 1])
+    out[int(seg_ids[k])] = (h_verts[v0:v1], h_edges[e0_:e1_], h_rad[v0:v1])
   return out

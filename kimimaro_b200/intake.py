@@ -311,12 +311,13 @@ def skeletonize(
   t0 = time.perf_counter()
   transform = np.array([[an[0], 0, 0, 0], [0, an[1], 0, 0], [0, 0, an[2], 0]], dtype=np.float32)
   by_orig = defaultdict(list)
+  h_orig_list = h_orig.tolist()
   for segid in sorted(results):
     verts, edges, radii = results[segid]
     if verts.shape[0] == 0 or edges.shape[0] == 0:
       continue
-    orig = h_orig[segid].item()
-    by_orig[orig].append(Skeleton(verts, edges, radii, segid=orig, transform=transform, space="physical"))
+    orig = h_orig_list[segid]
+    by_orig[orig].append(Skeleton._from_arrays(verts, edges, radii, orig, transform, "physical"))
   out = {}
   for orig, skels in by_orig.items():
     out[orig] = skels[0] if len(skels) == 1 else Skeleton.simple_merge(skels).consolidate()

@@ -41,6 +41,23 @@ class Skeleton:
       {"id": "vertex_types", "data_type": "uint8", "num_components": 1},
     ]
 
+  @classmethod
+  def _from_arrays(cls, vertices, edges, radii, segid, transform, space):
+    """Trusted fast path for the engine: arrays already have the right dtype and shape."""
+    self = object.__new__(cls)
+    self.id = segid
+    self.space = space
+    self.vertices = vertices
+    self.edges = edges
+    self.radii = radii
+    self.vertex_types = np.zeros((vertices.shape[0],), np.uint8)
+    self.transform = transform
+    self.extra_attributes = [
+      {"id": "radius", "data_type": "float32", "num_components": 1},
+      {"id": "vertex_types", "data_type": "uint8", "num_components": 1},
+    ]
+    return self
+
   # -- basic -----------------------------------------------------------------------------------
   def empty(self):
     return self.vertices.size == 0 or self.edges.size == 0
