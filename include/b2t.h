@@ -112,7 +112,7 @@ int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist
  * d_desc: n_desc records of 64 bytes (16 little-endian 32-bit fields):
  *   segid, root, n_fg, region_off, path_off, path_cap, tb_off, tb_n, ta_off, ta_n, max_paths (0xffffffff =
  *   None), soma_mode, soma_radius (float32), bucket_row, soma_done, pre_invalid
- * d_scratch: 5*sum(n_fg) u32; d_paths: pool of voxel indices, each path [rail ... target] terminated by
+ * d_scratch: 6*sum(n_fg) u32; d_paths: pool of voxel indices, each path [rail ... target] terminated by
  * 0xffffffff; d_out_len / d_out_npaths / d_out_status: n_desc; d_out_stats: 4*n_desc; d_work_counter: 1 u32. */
 int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,
                     uint32_t* d_stamp, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,

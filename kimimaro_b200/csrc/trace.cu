@@ -48,7 +48,7 @@ struct LabelDesc {
   uint32_t segid;       // value of this label in cc
   uint32_t root;        // linear index of the root voxel
   uint32_t n_fg;        // foreground voxels (np.count_nonzero(labels), trace.py:211)
-  uint32_t region_off;  // prefix sum of n_fg over the batch: scratch region starts at 5 * region_off
+  uint32_t region_off;  // prefix sum of n_fg over the batch: scratch region starts at 6 * region_off
   uint32_t path_off;    // first slot of this label in the path pool
   uint32_t path_cap;    // slots available
   uint32_t tb_off, tb_n;  // manual_targets_before: targets[tb_off .. tb_off+tb_n), popped from the end
@@ -72,7 +72,7 @@ struct Pools {
   const unsigned long long* keys;  // bucket-partitioned (daf_bits << 32 | index)
   const uint32_t* hist;            // bucket sizes
   const uint32_t* cursor;          // bucket ends
-  uint32_t* scratch;               // 5 * sum(n_fg) u32
+  uint32_t* scratch;               // 6 * sum(n_fg) u32
   uint32_t* paths;                 // path pool: voxel indices, each path terminated by 0xffffffff
   const uint32_t* targets;         // manual targets (linear indices)
   uint32_t* out_len;               // per desc: slots written
@@ -165,8 +165,8 @@ __device__ uint32_t find_target(const Arena& A, const LabelDesc& L, const Pools&
 // ---- dijkstra3d.railroad ----------------------------------------------------------------------------
 // Returns the path length written to out[0..): out[0] = rail voxel ... out[len-1] = target.
 __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target, uint32_t* actA, uint32_t* actB,
-                             uint32_t* proc, uint32_t* farB, uint32_t* touched, uint32_t* out, uint32_t out_cap,
-                             Shared& S) {
+                             uint32_t* proc, uint32_t* farA, uint32_t* farB, uint32_t* touched, uint32_t* out,
+                             uint32_t out_cap, Shared& S) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t seg = L.segid;
   if (__ldcg(&A.pdrf[target]) == 0.0f) {
@@ -179,127 +179,162 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
   const int64_t off = (int64_t)dx + (int64_t)dy * A.d.sx + (int64_t)dz * A.d.sxy;
   const uint32_t ltmask = (1u << lane) - 1u;
 
-  // Near / far pile.  `near` holds voxels whose tentative distance is <= thr and is expanded completely
-  // every round (no rescans); everything else waits in `far`, which is only scanned when `near` runs
-  // dry, to pick the next threshold.  Relaxation order never changes the result (least fixed point),
-  // it only changes how much work is redone.
-  uint32_t* near = actA;
-  uint32_t* nxt = actB;
-  uint32_t* far = proc;
+  // Three-level pile.  `mid` is a bounded band of candidates (tentative distance <= thr_mid) that is
+  // rescanned every round to pull the next narrow batch (<= thr_near) into `proc`; everything farther
+  // waits in `far`, which is scanned only when `mid` drains.  Relaxation order never changes the result
+  // (the distances are a least fixed point); narrow batches keep the re-relaxation work near Dijkstra's.
+  uint32_t* mid = actA;
+  uint32_t* mid2 = actB;
+  uint32_t* far = farA;
   uint32_t* far2 = farB;
   if (threadIdx.x == 0) {
     A.dist[target] = 0.0f;
     A.stamp[target] = 1;
-    near[0] = target;
+    mid[0] = target;
     touched[0] = target;
     S.n_touched = 1;
     S.best = ~0ull;
     S.n_keep = 0; S.n_proc = 0; S.n_next = 0;
   }
   __syncthreads();
-  uint32_t n_near = 1, n_far = 0;
-  float delta = __ldcg(&A.pdrf[target]);
+  uint32_t n_mid = 1, n_far = 0;
+  float delta = __ldcg(&A.pdrf[target]);                      // width of the near batch
   if (!(delta > 0.0f) || __float_as_uint(delta) >= kInfBits) delta = 1.0f;
-  uint32_t thr = __float_as_uint(delta);
+  float delta_mid = __fmul_rn(delta, 16.0f);                   // width of the mid band
+  uint32_t thr_mid = __float_as_uint(delta_mid);
   uint32_t relax = 0, rounds = 0;
 
   for (;;) {
-    // ---- expand the whole near band ----
-    while (n_near > 0) {
-      for (uint32_t it = warp; it < n_near; it += kWarps) {
-        const uint32_t u = near[it];
-        if (lane == 0) atomicExch(&A.stamp[u], 0u);   // from here on an improvement of u re-queues it
-        __syncwarp();
-        __threadfence_block();
-        const float du = __ldcg(&A.dist[u]);
-        int x, y, z;
-        unravel(u, A.d, x, y, z);
-        const int nx = x + dx, ny = y + dy, nz = z + dz;
-        bool push_near = false, push_far = false;
-        uint32_t v = 0;
-        if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz &&
-            __float_as_uint(du) <= (uint32_t)(S.best >> 32)) {
-          v = (uint32_t)((int64_t)u + off);
-          if (__ldg(&A.cc[v]) == seg) {
-            const float c = __ldcg(&A.pdrf[v]);
-            if (c == 0.0f) {
-              atomicMin(&S.best, ((unsigned long long)__float_as_uint(du) << 32) | u);   // rule T4 candidate
-            } else {
-              const uint32_t nd = __float_as_uint(__fadd_rn(du, c));
-              if (nd <= (uint32_t)(S.best >> 32)) {
-                const uint32_t old = atomicMin(reinterpret_cast<uint32_t*>(&A.dist[v]), nd);
-                if (nd < old) {
-                  relax++;
-                  if (old == kInfBits) touched[atomicAdd(&S.n_touched, 1u)] = v;
-                  __threadfence_block();
-                  if (atomicExch(&A.stamp[v], 1u) == 0u) { push_near = nd <= thr; push_far = !push_near; }
-                }
+    if (n_mid == 0) {
+      // ---- refill the mid band from the far pile ----
+      if (n_far == 0) break;
+      const uint32_t bound = (uint32_t)(S.best >> 32);
+      uint32_t mn = 0xffffffffu;
+      for (uint32_t i = threadIdx.x; i < n_far; i += kThreads) mn = min(mn, __float_as_uint(__ldcg(&A.dist[far[i]])));
+      mn = block_min_u32(mn, S.red32);
+      if (mn > bound) break;                                  // nothing left that could beat the rail we have
+      thr_mid = __float_as_uint(__fadd_rn(__uint_as_float(mn), delta_mid));
+      if (thr_mid > bound) thr_mid = bound;
+      for (uint32_t i0 = 0; i0 < n_far; i0 += kThreads) {
+        const uint32_t i = i0 + threadIdx.x;
+        bool tomid = false, tokeep = false;
+        uint32_t u = 0;
+        if (i < n_far) {
+          u = far[i];
+          const uint32_t du = __float_as_uint(__ldcg(&A.dist[u]));
+          tomid = du <= thr_mid;
+          tokeep = !tomid && du <= bound;
+          if (!tomid && !tokeep) A.stamp[u] = 0;              // dropped: a later improvement must re-queue it
+        }
+        const uint32_t mp = __ballot_sync(0xffffffffu, tomid), mk = __ballot_sync(0xffffffffu, tokeep);
+        uint32_t bp = 0, bk = 0;
+        if (lane == 0) {
+          if (mp) bp = atomicAdd(&S.n_keep, __popc(mp));
+          if (mk) bk = atomicAdd(&S.n_next, __popc(mk));
+        }
+        bp = __shfl_sync(0xffffffffu, bp, 0);
+        bk = __shfl_sync(0xffffffffu, bk, 0);
+        if (tomid) mid[bp + __popc(mp & ltmask)] = u;
+        if (tokeep) far2[bk + __popc(mk & ltmask)] = u;
+      }
+      __syncthreads();
+      n_mid = S.n_keep;
+      n_far = S.n_next;
+      { uint32_t* t = far; far = far2; far2 = t; }
+      if (n_mid < 64 * kWarps) delta_mid = __fmul_rn(delta_mid, 2.0f);          // aim at ~0.5-2 k candidates
+      else if (n_mid > 256 * kWarps) delta_mid = __fmul_rn(delta_mid, 0.5f);
+      __syncthreads();
+      if (threadIdx.x == 0) { S.n_keep = 0; S.n_next = 0; }
+      __syncthreads();
+      continue;
+    }
+    // ---- (a) smallest tentative distance in the mid band ----
+    uint32_t mn = 0xffffffffu;
+    for (uint32_t i = threadIdx.x; i < n_mid; i += kThreads) mn = min(mn, __float_as_uint(__ldcg(&A.dist[mid[i]])));
+    mn = block_min_u32(mn, S.red32);
+    const uint32_t bound = (uint32_t)(S.best >> 32);
+    uint32_t thr = __float_as_uint(__fadd_rn(__uint_as_float(mn), delta));
+    if (thr > bound) thr = bound;
+    // ---- (b) split the band: <= thr expand now, <= bound keep, else drop ----
+    for (uint32_t i0 = 0; i0 < n_mid; i0 += kThreads) {
+      const uint32_t i = i0 + threadIdx.x;
+      bool toproc = false, tokeep = false;
+      uint32_t u = 0;
+      if (i < n_mid) {
+        u = mid[i];
+        const uint32_t du = __float_as_uint(__ldcg(&A.dist[u]));
+        toproc = du <= thr;
+        tokeep = !toproc && du <= bound;
+        if (!toproc && !tokeep) A.stamp[u] = 0;
+      }
+      const uint32_t mp = __ballot_sync(0xffffffffu, toproc), mk = __ballot_sync(0xffffffffu, tokeep);
+      uint32_t bp = 0, bk = 0;
+      if (lane == 0) {
+        if (mp) bp = atomicAdd(&S.n_proc, __popc(mp));
+        if (mk) bk = atomicAdd(&S.n_keep, __popc(mk));
+      }
+      bp = __shfl_sync(0xffffffffu, bp, 0);
+      bk = __shfl_sync(0xffffffffu, bk, 0);
+      if (toproc) proc[bp + __popc(mp & ltmask)] = u;
+      if (tokeep) mid2[bk + __popc(mk & ltmask)] = u;
+    }
+    __syncthreads();
+    const uint32_t n_proc = S.n_proc;
+    // ---- (c) expand the batch: warp per voxel, lane per neighbour ----
+    for (uint32_t it = warp; it < n_proc; it += kWarps) {
+      const uint32_t u = proc[it];
+      if (lane == 0) atomicExch(&A.stamp[u], 0u);   // from here on an improvement of u re-queues it
+      __syncwarp();
+      __threadfence_block();
+      const float du = __ldcg(&A.dist[u]);
+      int x, y, z;
+      unravel(u, A.d, x, y, z);
+      const int nx = x + dx, ny = y + dy, nz = z + dz;
+      bool push_mid = false, push_far = false;
+      uint32_t v = 0;
+      if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
+        v = (uint32_t)((int64_t)u + off);
+        if (__ldg(&A.cc[v]) == seg) {
+          const float c = __ldcg(&A.pdrf[v]);
+          if (c == 0.0f) {
+            atomicMin(&S.best, ((unsigned long long)__float_as_uint(du) << 32) | u);   // rule T4 candidate
+          } else {
+            const uint32_t nd = __float_as_uint(__fadd_rn(du, c));
+            if (nd <= (uint32_t)(S.best >> 32)) {
+              const uint32_t old = atomicMin(reinterpret_cast<uint32_t*>(&A.dist[v]), nd);
+              if (nd < old) {
+                relax++;
+                if (old == kInfBits) touched[atomicAdd(&S.n_touched, 1u)] = v;
+                __threadfence_block();
+                if (atomicExch(&A.stamp[v], 1u) == 0u) { push_mid = nd <= thr_mid; push_far = !push_mid; }
               }
             }
           }
         }
-        const uint32_t mn_ = __ballot_sync(0xffffffffu, push_near), mf_ = __ballot_sync(0xffffffffu, push_far);
-        if (mn_ | mf_) {
-          uint32_t bn = 0, bf = 0;
-          if (lane == 0) {
-            if (mn_) bn = atomicAdd(&S.n_keep, __popc(mn_));
-            if (mf_) bf = atomicAdd(&S.n_proc, __popc(mf_));
-          }
-          bn = __shfl_sync(0xffffffffu, bn, 0);
-          bf = __shfl_sync(0xffffffffu, bf, 0);
-          if (push_near) nxt[bn + __popc(mn_ & ltmask)] = v;
-          if (push_far) far[n_far + bf + __popc(mf_ & ltmask)] = v;
+      }
+      const uint32_t mm = __ballot_sync(0xffffffffu, push_mid), mf = __ballot_sync(0xffffffffu, push_far);
+      if (mm | mf) {
+        uint32_t bm = 0, bf = 0;
+        if (lane == 0) {
+          if (mm) bm = atomicAdd(&S.n_keep, __popc(mm));
+          if (mf) bf = atomicAdd(&S.n_next, __popc(mf));
         }
+        bm = __shfl_sync(0xffffffffu, bm, 0);
+        bf = __shfl_sync(0xffffffffu, bf, 0);
+        if (push_mid) mid2[bm + __popc(mm & ltmask)] = v;
+        if (push_far) far[n_far + bf + __popc(mf & ltmask)] = v;
       }
-      __syncthreads();
-      n_near = S.n_keep;
-      n_far += S.n_proc;
-      { uint32_t* t = near; near = nxt; nxt = t; }
-      rounds++;
-      __syncthreads();
-      if (threadIdx.x == 0) { S.n_keep = 0; S.n_proc = 0; }
-      __syncthreads();
-    }
-    // ---- near ran dry: pick the next band from the far pile ----
-    if (n_far == 0) break;
-    const uint32_t bound = (uint32_t)(S.best >> 32);
-    uint32_t mn = 0xffffffffu;
-    for (uint32_t i = threadIdx.x; i < n_far; i += kThreads) mn = min(mn, __float_as_uint(__ldcg(&A.dist[far[i]])));
-    mn = block_min_u32(mn, S.red32);
-    if (mn > bound) break;                                  // nothing left that could beat the rail we have
-    thr = __float_as_uint(__fadd_rn(__uint_as_float(mn), delta));
-    if (thr > bound) thr = bound;
-    for (uint32_t i0 = 0; i0 < n_far; i0 += kThreads) {
-      const uint32_t i = i0 + threadIdx.x;
-      bool tonear = false, tokeep = false;
-      uint32_t u = 0;
-      if (i < n_far) {
-        u = far[i];
-        const uint32_t du = __float_as_uint(__ldcg(&A.dist[u]));
-        tonear = du <= thr;
-        tokeep = !tonear && du <= bound;                    // farther than the best rail: drop (stays in `touched`)
-        if (!tonear && !tokeep) A.stamp[u] = 0;             // a later improvement must be able to re-queue it
-      }
-      const uint32_t mp = __ballot_sync(0xffffffffu, tonear), mk = __ballot_sync(0xffffffffu, tokeep);
-      uint32_t bp = 0, bk = 0;
-      if (lane == 0) {
-        if (mp) bp = atomicAdd(&S.n_keep, __popc(mp));
-        if (mk) bk = atomicAdd(&S.n_next, __popc(mk));
-      }
-      bp = __shfl_sync(0xffffffffu, bp, 0);
-      bk = __shfl_sync(0xffffffffu, bk, 0);
-      if (tonear) near[bp + __popc(mp & ltmask)] = u;
-      if (tokeep) far2[bk + __popc(mk & ltmask)] = u;
     }
     __syncthreads();
-    n_near = S.n_keep;
-    n_far = S.n_next;
-    { uint32_t* t = far; far = far2; far2 = t; }
-    // band-width feedback: aim for a few hundred voxels per refill
-    if (n_near < 16 * kWarps) delta = __fmul_rn(delta, 2.0f);
-    else if (n_near > 128 * kWarps) delta = __fmul_rn(delta, 0.5f);
+    n_mid = S.n_keep;
+    n_far += S.n_next;
+    { uint32_t* t = mid; mid = mid2; mid2 = t; }
+    // batch-size feedback: keep roughly 2..8 voxels per warp in flight
+    if (n_proc < 2 * kWarps) delta = __fmul_rn(delta, 2.0f);
+    else if (n_proc > 8 * kWarps) delta = __fmul_rn(delta, 0.5f);
+    rounds++;
     __syncthreads();
-    if (threadIdx.x == 0) { S.n_keep = 0; S.n_next = 0; }
+    if (threadIdx.x == 0) { S.n_keep = 0; S.n_proc = 0; S.n_next = 0; }
     __syncthreads();
   }
   // anything still queued keeps stamp = 1; it is in `touched`, which resets it below
@@ -461,12 +496,13 @@ __device__ uint32_t invalidate(const Arena& A, const LabelDesc& L, const uint32_
 // ---- the per-label conductor (trace.py:196-267) ----------------------------------------------------
 __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, const Params& prm, Shared& S,
                             uint32_t job) {
-  uint32_t* scr = P.scratch + 5ull * L.region_off;
+  uint32_t* scr = P.scratch + 6ull * L.region_off;
   uint32_t* r0 = scr;
   uint32_t* r1 = scr + L.n_fg;
   uint32_t* r2 = scr + 2ull * L.n_fg;
   uint32_t* r3 = scr + 3ull * L.n_fg;
   uint32_t* r4 = scr + 4ull * L.n_fg;
+  uint32_t* r5 = scr + 5ull * L.n_fg;
   uint32_t* out = P.paths + L.path_off;
   unsigned long long t_start = 0;
   if (threadIdx.x == 0) {
@@ -498,7 +534,7 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
     if (used + 2 > L.path_cap) { status = B2T_ERR_CAPACITY; break; }
     uint32_t* pout = out + used;
     const uint32_t cap = L.path_cap - used - 1;
-    uint32_t len = railroad(A, L, target, r0, r1, r2, r4, r3, pout, cap, S);
+    uint32_t len = railroad(A, L, target, r0, r1, r2, r4, r5, r3, pout, cap, S);
     if (len > cap) { status = B2T_ERR_CAPACITY; break; }
     if (L.soma_mode) {
       // keep path[:1] + points farther than soma_radius from the root; float64, uint32 wrap
@@ -574,7 +610,7 @@ __global__ void __launch_bounds__(kThreads) trace_kernel(Arena A, const LabelDes
 // Replaces the body of kimimaro/trace.py:compute_paths (trace.py:196-267) and the native calls in
 // it: dijkstra3d.railroad, CachedTargetFinder.find_target, roll_invalidation_ball_inside_component.
 //   d_desc       n_desc records of 16 x u32/f32 (struct LabelDesc above, same field order)
-//   d_scratch    5 * sum(n_fg) u32;  d_paths: path pool;  d_targets: manual targets (linear indices)
+//   d_scratch    6 * sum(n_fg) u32;  d_paths: path pool;  d_targets: manual targets (linear indices)
 //   d_out_len / d_out_npaths / d_out_status: n_desc each; d_out_stats: 4 * n_desc; d_work_counter: 1 u32 (zeroed here)
 // =================================================================================================
 B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,

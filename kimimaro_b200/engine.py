@@ -273,13 +273,13 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
     d["soma_mode"] = 1 if j["soma_mode"] else 0
     d["soma_radius"] = np.float32(j.get("soma_radius", 0.0))
     d["bucket_row"] = j["segid"]
-  assert path_off < 2 ** 32 and 5 * region < 2 ** 34
-  scratch = torch.empty(5 * max(region, 1), dtype=torch.int32, device=dev)
+  assert path_off < 2 ** 32 and 6 * region < 2 ** 34
+  scratch = torch.empty(6 * max(region, 1), dtype=torch.int32, device=dev)
   # soma labels: the one-off ball around the root (trace.py:160-168) is far too large for one CTA
   for slot in range(n_jobs):
     if desc[slot]["soma_mode"]:
       n = int(desc[slot]["n_fg"])
-      base = 5 * int(desc[slot]["region_off"])
+      base = 6 * int(desc[slot]["region_off"])
       seeds = _dev(np.array([desc[slot]["root"]], dtype=np.uint32).view(np.int32))
       check(L.b2t_invalidate_ball(_p(d_cc), _p(d_dbf), _p(claim), c_i64(sx), c_i64(sy), c_i64(sz),
                                   c_f32(anisotropy[0]), c_f32(anisotropy[1]), c_f32(anisotropy[2]), _p(seeds), c_u32(1),
