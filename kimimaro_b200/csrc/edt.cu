@@ -284,6 +284,243 @@ edt_pass_col_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, 
   }
 }
 
+// ================================================================================================
+// v2 kernels (ncu on the v1 kernels above showed them ISSUE-bound, not memory-bound: 1293 warp
+// instructions per 512-voxel row in pass x, 513 per 32-voxel warp-row in pass y; DRAM traffic was
+// already equal to the algorithmic bytes).  The v2 kernels cut the instruction count:
+//   pass x  each lane keeps SEG consecutive labels of the row in registers (uint4 loads), finds the
+//           run boundaries of its own segment sequentially and gets the rest from ONE inclusive
+//           warp max-scan (last label change to the left) and ONE min-scan (next change to the right).
+//   pass y/z one THREAD per column runs the O(n) lower-envelope algorithm (Felzenszwalb & Huttenlocher)
+//           with its parabola stack in local memory (hot top in registers); lanes are 32 adjacent
+//           columns, so every row access of the warp is one coalesced 128-byte segment and there is no
+//           shared-memory tile at all.  Float operations mirror oracle/oracle.c (edt_parabolic_run)
+//           one for one -- run-relative indices, the same intersection formula, FLT_MAX in place of
+//           +inf inside the envelope arithmetic -- so the result is bit-identical to the CPU restatement.
+// ================================================================================================
+constexpr float kFltMax = 3.4028234664e38f;
+
+template <int SEG>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+edt_pass_x_v2_kernel(const uint32_t* __restrict__ labels, float* __restrict__ out, int sx, int64_t nrows, float w,
+                     int black_border) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= nrows) return;
+  const uint32_t* lrow = labels + row * sx;
+  float* orow = out + row * sx;
+  const int p0 = lane * SEG;
+  uint32_t lab[SEG];
+#pragma unroll
+  for (int q = 0; q < SEG / 4; q++) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (p0 + 4 * q < sx) v = *reinterpret_cast<const uint4*>(lrow + p0 + 4 * q);
+    lab[4 * q] = v.x; lab[4 * q + 1] = v.y; lab[4 * q + 2] = v.z; lab[4 * q + 3] = v.w;
+  }
+  uint32_t prev = __shfl_up_sync(0xffffffffu, lab[SEG - 1], 1);
+  // label changes inside the segment: bit j set <=> position p0+j starts a run
+  uint32_t brk = 0;
+#pragma unroll
+  for (int j = 0; j < SEG; j++) {
+    const int p = p0 + j;
+    const uint32_t pl = (j == 0) ? prev : lab[j - 1];
+    if (p < sx && (p == 0 || lab[j] != pl)) brk |= 1u << j;
+  }
+  // last change at or before the end of my segment / first change at or after its start, across lanes
+  int last_in = brk ? p0 + 31 - __clz(brk) : -1;
+  int first_in = brk ? p0 + __ffs(brk) - 1 : sx;
+  int lastb = last_in, firstb = first_in;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, lastb, o);
+    const int b = __shfl_down_sync(0xffffffffu, firstb, o);
+    if (lane >= o) lastb = max(lastb, a);
+    if (lane + o < 32) firstb = min(firstb, b);
+  }
+  int left_in = __shfl_up_sync(0xffffffffu, lastb, 1);      // last change strictly before my segment
+  int right_in = __shfl_down_sync(0xffffffffu, firstb, 1);  // first change strictly after my segment
+  if (lane == 0) left_in = 0;
+  if (lane == 31) right_in = sx;
+  float val[SEG];
+#pragma unroll
+  for (int j = 0; j < SEG; j++) {
+    const int p = p0 + j;
+    const uint32_t le = brk & (0xffffffffu >> (31 - j));
+    const uint32_t gt = (j == 31) ? 0u : (brk & (0xffffffffu << (j + 1)));
+    const int s = le ? (p0 + 31 - __clz(le)) : left_in;
+    const int nx = gt ? (p0 + __ffs(gt) - 1) : right_in;
+    float v = 0.0f;
+    if (lab[j] != 0) {
+      const bool lok = (s > 0) || black_border, rok = (nx < sx) || black_border;
+      if (lok || rok) {
+        const int dl = p - s + 1, dr = nx - p;
+        const int d = lok ? (rok ? min(dl, dr) : dl) : dr;
+        const float fd = __fmul_rn((float)d, w);
+        v = __fmul_rn(fd, fd);
+      } else {
+        v = __int_as_float(0x7f800000);
+      }
+    }
+    val[j] = v;
+  }
+#pragma unroll
+  for (int q = 0; q < SEG / 4; q++)
+    if (p0 + 4 * q < sx)
+      *reinterpret_cast<float4*>(orow + p0 + 4 * q) = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
+}
+
+// intersection of the parabola rooted at run-relative row i (height fi) with the one at v (height h):
+// same expression as oracle.c / the edt library: (f[i] - f[v] + (i-v) w^2 (i+v)) / (2 (i-v) w^2)
+__device__ __forceinline__ float fh_intersect(float fi, int i, float h, int v, float w2) {
+  const float f1 = __fmul_rn((float)(i - v), w2);
+  const float f2 = (float)(i + v);
+  return __fdiv_rn(__fadd_rn(__fsub_rn(fi, h), __fmul_rn(f1, f2)), __fmul_rn(2.0f, f1));
+}
+
+template <typename T, int NMAX>
+__global__ void __launch_bounds__(128)
+edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, int64_t cstride, int nx,
+                       int64_t ostride, float w, int black_border, int last_pass) {
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  if (x >= nx) return;
+  const int64_t base = (int64_t)blockIdx.y * ostride + x;
+  const float w2 = __fmul_rn(w, w);
+  // envelope entries of all runs of the column, concatenated.  Entry 0 of a run always sits on the run's
+  // first row (F&H never pops it), so ev[first] is the run start; its ez slot (the -inf boundary, never
+  // read as a number) stores (run end row << 16 | number of entries).
+  uint16_t ev[NMAX];
+  float eh[NMAX];
+  float ez[NMAX];
+
+  // ---------------- build ----------------
+  int ktot = 0;          // entries written so far
+  int k_lo = 0, k = -1;  // first / top entry of the open run
+  int a = 0;             // first row of the open run
+  T run_lab = T(0);
+  int tv = 0; float th = 0.0f, tz = 0.0f;   // top entry, cached
+  for (int i0 = 0; i0 < n; i0 += 8) {
+    float fv[8];
+    T lv[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      fv[j] = 0.0f; lv[j] = T(0);
+      if (i0 + j < n) {
+        const int64_t idx = base + (int64_t)(i0 + j) * cstride;
+        fv[j] = f[idx];
+        lv[j] = labels[idx];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int i = i0 + j;
+      if (i < n) {
+        const T lab = lv[j];
+        float fi = fv[j];
+        if (fi > kFltMax) fi = kFltMax;                      // tofinite()
+        if (lab != run_lab) {
+          if (run_lab != T(0)) ez[k_lo] = __uint_as_float(((uint32_t)i << 16) | (uint32_t)(k - k_lo + 1));
+          run_lab = lab;
+          if (lab != T(0)) {
+            a = i; k_lo = ktot; k = ktot; ktot++;
+            ev[k] = (uint16_t)i; eh[k] = fi;
+            tv = 0; th = fi; tz = -__int_as_float(0x7f800000);
+          }
+        } else if (lab != T(0)) {
+          const int ir = i - a;
+          float s = fh_intersect(fi, ir, th, tv, w2);
+          while (k > k_lo && s <= tz) {
+            k--;
+            tv = (int)ev[k] - a; th = eh[k]; tz = (k > k_lo) ? ez[k] : -__int_as_float(0x7f800000);
+            s = fh_intersect(fi, ir, th, tv, w2);
+          }
+          k++;
+          ktot = k + 1;
+          ev[k] = (uint16_t)i; eh[k] = fi; ez[k] = s;
+          tv = ir; th = fi; tz = s;
+        }
+      }
+    }
+  }
+  if (run_lab != T(0)) ez[k_lo] = __uint_as_float(((uint32_t)n << 16) | (uint32_t)(k - k_lo + 1));
+
+  // ---------------- query ----------------
+  int r_lo = 0, r_cnt = 0, r_a = n, r_b = n;      // current run: entries [r_lo, r_lo+r_cnt), rows [r_a, r_b)
+  if (ktot > 0) {
+    const uint32_t pk = __float_as_uint(ez[0]);
+    r_a = (int)ev[0]; r_b = (int)(pk >> 16); r_cnt = (int)(pk & 0xffffu);
+  }
+  int kk = 0;
+  int cv = 0; float ch = eh[0];
+  float nz = (r_cnt > 1) ? ez[1] : __int_as_float(0x7f800000);
+  for (int i = 0; i < n; i++) {
+    if (i >= r_b) {                                           // move to the next run of this column
+      r_lo += r_cnt;
+      if (r_lo < ktot) {
+        const uint32_t pk = __float_as_uint(ez[r_lo]);
+        r_a = (int)ev[r_lo]; r_b = (int)(pk >> 16); r_cnt = (int)(pk & 0xffffu);
+        kk = r_lo; cv = 0; ch = eh[kk];
+        nz = (r_cnt > 1) ? ez[kk + 1] : __int_as_float(0x7f800000);
+      } else {
+        r_a = n; r_b = n + 1; r_cnt = 0;
+      }
+    }
+    if (i >= r_a && i < r_b) {
+      const int ir = i - r_a;
+      while (nz < (float)ir) {
+        kk++;
+        cv = (int)ev[kk] - r_a; ch = eh[kk];
+        nz = (kk + 1 < r_lo + r_cnt) ? ez[kk + 1] : __int_as_float(0x7f800000);
+      }
+      const float di = (float)(ir - cv);
+      float val = __fadd_rn(__fmul_rn(__fmul_rn(w2, di), di), ch);
+      if (r_a > 0 || black_border) { const float e = (float)(ir + 1); val = fminf(val, __fmul_rn(__fmul_rn(w2, e), e)); }
+      if (r_b < n || black_border) { const float e = (float)(r_b - i); val = fminf(val, __fmul_rn(__fmul_rn(w2, e), e)); }
+      if (last_pass) val = (val >= kFltMax) ? __int_as_float(0x7f800000) : sqrtf(val);
+      f[base + (int64_t)i * cstride] = val;
+    }
+  }
+}
+
+template <typename T>
+int edt_launch_v2(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz, int black_border,
+                  int ndim, float* out, cudaStream_t st, bool* handled) {
+  *handled = false;
+  const int64_t nmax = sy > sz ? sy : sz;
+  if (nmax > 2048 || nmax >= 32768) return B2T_OK;
+  *handled = true;
+  const int64_t nrows = sy * sz;
+  bool x_done = false;
+  if (sizeof(T) == 4 && (sx % 4) == 0 && sx <= 1024 && ((uintptr_t)labels % 16) == 0 && ((uintptr_t)out % 16) == 0) {
+    const unsigned blocks = (unsigned)((nrows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const uint32_t* l32 = reinterpret_cast<const uint32_t*>(labels);
+    if (sx <= 128) edt_pass_x_v2_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, st>>>(l32, out, (int)sx, nrows, wx, black_border);
+    else if (sx <= 256) edt_pass_x_v2_kernel<8><<<blocks, kWarpsPerBlock * 32, 0, st>>>(l32, out, (int)sx, nrows, wx, black_border);
+    else if (sx <= 512) edt_pass_x_v2_kernel<16><<<blocks, kWarpsPerBlock * 32, 0, st>>>(l32, out, (int)sx, nrows, wx, black_border);
+    else edt_pass_x_v2_kernel<32><<<blocks, kWarpsPerBlock * 32, 0, st>>>(l32, out, (int)sx, nrows, wx, black_border);
+    x_done = true;
+  }
+  if (!x_done) {
+    const int64_t blocks = (nrows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    edt_pass_x_kernel<T><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(labels, out, (int)sx, nrows, wx, black_border);
+  }
+  const dim3 gy((unsigned)b2t_ceil_div(sx, 128), (unsigned)sz), gz((unsigned)b2t_ceil_div(sx, 128), (unsigned)sy);
+#define B2T_FH(NM)                                                                                                    \
+  do {                                                                                                                \
+    edt_pass_col_fh_kernel<T, NM><<<gy, 128, 0, st>>>(labels, out, (int)sy, sx, (int)sx, sx * sy, wy, black_border,  \
+                                                     ndim == 2);                                                      \
+    if (ndim == 3)                                                                                                    \
+      edt_pass_col_fh_kernel<T, NM><<<gz, 128, 0, st>>>(labels, out, (int)sz, sx * sy, (int)sx, sx, wz, black_border, 1); \
+  } while (0)
+  if (nmax <= 256) B2T_FH(256);
+  else if (nmax <= 512) B2T_FH(512);
+  else if (nmax <= 1024) B2T_FH(1024);
+  else B2T_FH(2048);
+#undef B2T_FH
+  B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(ndim == 3 ? 3 : 2);
+  return B2T_OK;
+}
+
 template <typename T>
 int edt_launch(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz, int black_border,
                int ndim, float* out, cudaStream_t st) {
@@ -335,6 +572,19 @@ B2T_EXPORT int b2t_edt(const void* d_labels, int label_bytes, int64_t sx, int64_
   B2T_REQUIRE(sz <= 65535 && sy <= 65535, "b2t_edt: extent too large for grid.y");
   cudaStream_t st = (cudaStream_t)stream;
   black_border = black_border ? 1 : 0;
+  static const bool use_v2 = []() { const char* e = getenv("B2T_EDT_ALGO"); return !(e && e[0] == 'w'); }();
+  if (use_v2) {
+    bool handled = false;
+    int rc = B2T_OK;
+    switch (label_bytes) {
+      case 1: rc = edt_launch_v2<uint8_t>((const uint8_t*)d_labels, sx, sy, sz, wx, wy, wz, black_border, ndim, d_out, st, &handled); break;
+      case 2: rc = edt_launch_v2<uint16_t>((const uint16_t*)d_labels, sx, sy, sz, wx, wy, wz, black_border, ndim, d_out, st, &handled); break;
+      case 4: rc = edt_launch_v2<uint32_t>((const uint32_t*)d_labels, sx, sy, sz, wx, wy, wz, black_border, ndim, d_out, st, &handled); break;
+      case 8: rc = edt_launch_v2<unsigned long long>((const unsigned long long*)d_labels, sx, sy, sz, wx, wy, wz, black_border, ndim, d_out, st, &handled); break;
+      default: b2t_set_error("b2t_edt: label_bytes must be 1, 2, 4 or 8 (got %d)", label_bytes); return B2T_ERR_ARG;
+    }
+    if (handled || rc != B2T_OK) return rc;
+  }
   switch (label_bytes) {
     case 1: return edt_launch<uint8_t>((const uint8_t*)d_labels, sx, sy, sz, wx, wy, wz, black_border, ndim, d_out, st);
     case 2: return edt_launch<uint16_t>((const uint16_t*)d_labels, sx, sy, sz, wx, wy, wz, black_border, ndim, d_out, st);

@@ -29,6 +29,17 @@ __device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t i) {
   return i;
 }
 
+// read-only traversal: used by the flatten pass, where a concurrent path-halving store could otherwise
+// overwrite an already flattened parent[i] = root with a non-root ancestor
+__device__ __forceinline__ uint32_t uf_find_ro(const uint32_t* parent, uint32_t i) {
+  uint32_t p = __ldcg(&parent[i]);
+  while (p != i) {
+    i = p;
+    p = __ldcg(&parent[i]);
+  }
+  return i;
+}
+
 __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
   for (;;) {
     a = uf_find(parent, a);
@@ -76,8 +87,8 @@ __global__ void ccl_flatten_kernel(uint32_t* __restrict__ parent, uint8_t* __res
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t p = parent[i];
     if (p == kNone) { is_root[i] = 0; continue; }
-    const uint32_t r = uf_find(parent, (uint32_t)i);
-    parent[i] = r;
+    const uint32_t r = uf_find_ro(parent, (uint32_t)i);
+    parent[i] = r;   // every store of this kernel writes a root, so concurrent readers stay correct
     is_root[i] = r == (uint32_t)i;
   }
 }

@@ -242,7 +242,7 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
   keys = torch.empty(max(n_fg_total, 1), dtype=torch.int64, device=dev)
   pdrf = torch.empty(V, dtype=torch.float32, device=dev)
   claim = torch.empty(V, dtype=torch.int64, device=dev)
-  flag = torch.empty(V, dtype=torch.uint8, device=dev)
+  flag = torch.empty(V, dtype=torch.uint8, device=dev)   # vestigial init target of the fused kernel
   check(L.b2t_pdrf_and_buckets(_p(d_cc), _p(d_dbf), _p(ws.dist), _p(pdrf), _p(claim), _p(flag), c_i64(sx), c_i64(sy),
                                c_i64(sz), c_u32(n_rows), _p(d_M), _p(d_inv), _p(d_active),
                                c_f32(params["pdrf_scale"]), c_f32(params["pdrf_exponent"]), c_int(NBUCKETS),

@@ -214,3 +214,18 @@ def test_uint64_and_int32_labels(gpu):
   _compare(res, ref)
   res, ref = _both(gpu, lab.astype(np.int32), anisotropy=(16, 16, 40), dust_threshold=100)
   _compare(res, ref)
+
+
+def test_ccl_exact_and_deterministic(gpu, orc):
+  """N1: the union-find CCL against the oracle's (numbering included), repeated to catch races."""
+  import torch
+  from kimimaro_b200 import engine, ops
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes((256, 256, 128), 150, seed=33)
+  ref, n_ref = orc.connected_components(lab)
+  d = ops.to_device_f(lab, gpu).view(torch.int32)
+  for _ in range(5):
+    cc, n = engine.connected_components(d, lab.shape)
+    assert n == n_ref
+    got = cc.cpu().numpy().view(np.uint32).reshape(lab.shape, order="F")
+    assert np.array_equal(got, ref)
