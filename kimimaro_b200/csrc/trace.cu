@@ -24,7 +24,7 @@ namespace {
 
 constexpr uint32_t kInfBits = 0x7f800000u;
 constexpr unsigned long long kValid = ~0ull;
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;   // 16 warps: a whole narrow batch expands in one pass
 constexpr int kWarps = kThreads / 32;
 
 struct Dims {
@@ -294,8 +294,9 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
       uint32_t v = 0;
       if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
         v = (uint32_t)((int64_t)u + off);
-        if (__ldg(&A.cc[v]) == seg) {
-          const float c = __ldcg(&A.pdrf[v]);
+        const uint32_t lv = __ldg(&A.cc[v]);        // independent loads, issued together
+        const float c = __ldcg(&A.pdrf[v]);
+        if (lv == seg) {
           if (c == 0.0f) {
             atomicMin(&S.best, ((unsigned long long)__float_as_uint(du) << 32) | u);   // rule T4 candidate
           } else {
@@ -456,7 +457,9 @@ __device__ uint32_t invalidate(const Arena& A, const LabelDesc& L, const uint32_
       uint32_t v = 0;
       if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
         v = (uint32_t)((int64_t)u + off);
-        if (__ldg(&A.cc[v]) == seg && __ldcg(&A.claim[v]) != 0ull) {
+        const uint32_t lv = __ldg(&A.cc[v]);
+        const unsigned long long cl = __ldcg(&A.claim[v]);
+        if (lv == seg && cl != 0ull) {
           // float32 expression of dijkstra_invalidation.hpp:49-52,319-323
           const float a = __fmul_rn(A.wx, (float)(nx - ox)), b = __fmul_rn(A.wy, (float)(ny - oy)),
                       c = __fmul_rn(A.wz, (float)(nz - oz));
@@ -588,7 +591,7 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads) trace_kernel(Arena A, const LabelDesc* __restrict__ descs, Pools P, Params prm) {
+__global__ void __launch_bounds__(kThreads, 3) trace_kernel(Arena A, const LabelDesc* __restrict__ descs, Pools P, Params prm) {
   __shared__ Shared S;
   __shared__ LabelDesc L;
   for (;;) {

@@ -331,14 +331,17 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
 # ------------------------------------------------------------------------------------------------
 # skeleton assembly (trace.py:182-192, intake.py:509-517, 587-593) for all labels at once
 # ------------------------------------------------------------------------------------------------
-def assemble(d_vox, d_rad, seg_off, seg_ids, shape, anisotropy, offset=(0, 0, 0)):
+def assemble(d_vox, d_rad, seg_off, seg_ids, shape, anisotropy, offset=(0, 0, 0), group_ids=None):
   """
   Skeleton.from_path / simple_merge / consolidate (trace.py:182-184) for ALL labels at once,
   on the device, with torch sort/unique/cumsum as plumbing (the reference's counterpart is np.unique on
   the host): unique vertices per label in lexicographic (x,y,z) order, edges remapped / sorted / unique /
   no self loops, vertices without edges dropped, radii of the vertex, then voxel -> physical units in
   float32 exactly like intake.py:509-513.
-  Returns {cc segid: (vertices f32 [N,3] physical, edges u32 [M,2], radii f32 [N])} (numpy views).
+  group_ids (one id per segment, default: the segment's own cc id) lets several connected components of
+  one original label be consolidated together, which is what intake.py:587-593 (merge) does afterwards:
+  components are disjoint voxel sets, so merging is the same sort over the union.
+  Returns {group id: (vertices f32 [N,3] physical, edges u32 [M,2], radii f32 [N])} (numpy views).
   """
   sx, sy, sz = shape
   V = sx * sy * sz
@@ -348,8 +351,12 @@ def assemble(d_vox, d_rad, seg_off, seg_ids, shape, anisotropy, offset=(0, 0, 0)
     return out
   dev = d_vox.device
   n_seg = int(seg_ids.size)
+  if group_ids is None:
+    group_ids = seg_ids
+  groups, group_rank = np.unique(np.asarray(group_ids), return_inverse=True)
+  n_grp = int(groups.size)
   lens = torch.as_tensor(np.diff(seg_off), device=dev)
-  lab_of = torch.repeat_interleave(torch.arange(n_seg, device=dev, dtype=torch.int64), lens)
+  lab_of = torch.repeat_interleave(torch.as_tensor(group_rank.astype(np.int64), device=dev), lens)
   is_vtx = d_vox != -1                                       # 0xffffffff terminators
   v = d_vox.to(torch.int64) & 0xFFFFFFFF
   z = v // (sx * sy)
@@ -386,7 +393,7 @@ def assemble(d_vox, d_rad, seg_off, seg_ids, shape, anisotropy, offset=(0, 0, 0)
   verts = (verts + off) * an                                 # float32, intake.py:509-513
   ea, eb = newid[ea], newid[eb]
   elab = ulab_k[ea]
-  bounds = torch.arange(n_seg + 1, device=dev, dtype=torch.int64)
+  bounds = torch.arange(n_grp + 1, device=dev, dtype=torch.int64)
   vstart = torch.searchsorted(ulab_k.contiguous(), bounds)
   estart = torch.searchsorted(elab.contiguous(), bounds)
   edges = torch.stack([ea - vstart[elab], eb - vstart[elab]], dim=1).to(torch.int32)
@@ -395,10 +402,10 @@ def assemble(d_vox, d_rad, seg_off, seg_ids, shape, anisotropy, offset=(0, 0, 0)
   h_rad = urad[used].cpu().numpy()
   h_vs = vstart.cpu().numpy()
   h_es = estart.cpu().numpy()
-  for k in range(n_seg):
-    v0, v1 = int(h_vs[k]), int(h_vs[k + 1])
+  h_vs, h_es, gl = h_vs.tolist(), h_es.tolist(), groups.tolist()
+  for k in range(n_grp):
+    v0, v1 = h_vs[k], h_vs[k + 1]
     if v1 == v0:
       continue
-    e0_, e1_ = int(h_es[k]), int(h_es[k + 1])
-    out[int(seg_ids[k])] = (h_verts[v0:v1], h_edges[e0_:e1_], h_rad[v0:v1])
+    out[gl[k]] = (h_verts[v0:v1], h_edges[h_es[k]:h_es[k + 1]], h_rad[v0:v1])
   return out

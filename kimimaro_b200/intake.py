@@ -284,12 +284,13 @@ def skeletonize(
                  "soma_mode": False, "root": None if root is None else lin(root), "first": int(h_first[segid]),
                  "targets_before": [lin(p) for p in tb], "targets_after": [lin(p) for p in ta]})
 
-  results = {}
+  results = {}            # original label -> (vertices, edges, radii), all its ordinary components merged
+  private_results = []    # (original label, arrays) of labels traced in a private arena
   stats_all = []
   if jobs:
     vox, rad, seg_off, seg_ids, stats = engine.trace_arena(d_cc, d_dbf, shape, an, jobs, params, n_cc, tm)
     t0 = time.perf_counter()
-    results.update(engine.assemble(vox, rad, seg_off, seg_ids, shape, anisotropy))
+    results.update(engine.assemble(vox, rad, seg_off, seg_ids, shape, anisotropy, group_ids=h_orig[seg_ids]))
     stats_all.append(stats)
     t0 = lap("assemble", t0)
   if private:
@@ -300,7 +301,7 @@ def skeletonize(
       ptm = {} if tm is not None else None
       res, stats = _private_arena(d_cc3, d_dbf3, segid, bb, an, params, root, tb, ta, ptm)
       if res is not None:
-        results[segid] = res
+        private_results.append((h_orig[segid].item(), res))
       stats_all.append(stats)
       if tm is not None:
         tm["soma"] = tm.get("soma", 0.0) + time.perf_counter() - t0
@@ -311,12 +312,13 @@ def skeletonize(
   t0 = time.perf_counter()
   transform = np.array([[an[0], 0, 0, 0], [0, an[1], 0, 0], [0, 0, an[2], 0]], dtype=np.float32)
   by_orig = defaultdict(list)
-  h_orig_list = h_orig.tolist()
-  for segid in sorted(results):
-    verts, edges, radii = results[segid]
+  for orig, (verts, edges, radii) in results.items():
     if verts.shape[0] == 0 or edges.shape[0] == 0:
       continue
-    orig = h_orig_list[segid]
+    by_orig[orig].append(Skeleton._from_arrays(verts, edges, radii, orig, transform, "physical"))
+  for orig, (verts, edges, radii) in private_results:
+    if verts.shape[0] == 0 or edges.shape[0] == 0:
+      continue
     by_orig[orig].append(Skeleton._from_arrays(verts, edges, radii, orig, transform, "physical"))
   out = {}
   for orig, skels in by_orig.items():
