@@ -105,18 +105,20 @@ def find_border_targets(dt, cc_plane, wx, wy):
     return pts
   labs = fcc[sel].astype(np.int64)
   vals = fdt[sel]
-  nlab = int(labs.max()) + 1
-  mx = np.zeros(nlab, dtype=vals.dtype)
-  np.maximum.at(mx, labs, vals)
-  is_max = vals == mx[labs]
-  cand_idx = sel[is_max]                       # raster order is preserved
-  cand_lab = labs[is_max]
-  uniq, first_pos = np.unique(labs, return_index=True)
-  for l in uniq[np.argsort(first_pos)].tolist():  # dict insertion order = first encounter (B.6)
+  # group by label with ONE stable sort (raster order survives inside each group)
+  order = np.argsort(labs, kind="stable")
+  sl, sv, si = labs[order], vals[order], sel[order]
+  gstart = np.concatenate(([0], np.flatnonzero(np.diff(sl)) + 1))
+  gmax = np.maximum.reduceat(sv, gstart)
+  glen = np.diff(np.concatenate((gstart, [sl.size])))
+  is_max = sv == np.repeat(gmax, glen)
+  cand_idx = si[is_max]                        # grouped by label, raster order inside a group
+  cand_lab = sl[is_max]
+  first_pos = si[gstart]                       # first raster position of every label
+  for l in sl[gstart][np.argsort(first_pos, kind="stable")].tolist():  # dict insertion order = first encounter (B.6)
     pts[l] = None
   cents = None
-  order = np.argsort(cand_lab, kind="stable")
-  cl, ci = cand_lab[order], cand_idx[order]
+  cl, ci = cand_lab, cand_idx
   bounds = np.flatnonzero(np.diff(cl)) + 1
   starts = np.concatenate(([0], bounds))
   ends = np.concatenate((bounds, [cl.size]))

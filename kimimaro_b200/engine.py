@@ -77,6 +77,19 @@ def connected_components(d_labels, shape):
   return parent, n_cc
 
 
+def _ccl_nosync(d_labels, shape):
+  """connected_components without reading the component count back (faces only need the labels)."""
+  sx, sy, sz = shape
+  V = sx * sy * sz
+  parent = torch.empty(V, dtype=torch.int32, device=d_labels.device)
+  is_root = torch.empty(V, dtype=torch.uint8, device=d_labels.device)
+  check(lib().b2t_ccl26_roots(_p(d_labels), c_int(d_labels.element_size()), c_i64(sx), c_i64(sy), c_i64(sz),
+                              _p(parent), _p(is_root), stream_ptr()), "b2t_ccl26_roots")
+  rank = torch.cumsum(is_root, 0, dtype=torch.int32)
+  check(lib().b2t_ccl_relabel(_p(parent), _p(rank), c_u64(V), stream_ptr()), "b2t_ccl_relabel")
+  return parent
+
+
 def label_stats(d_cc, d_dbf, shape, n):
   sx, sy, sz = shape
   dev = d_cc.device
@@ -138,21 +151,36 @@ def compute_border_targets(d_cc, shape, anisotropy):
     (cc3[:, :, 0], (sy, sz), (1, 2), lambda y, z: (0, y, z)),
     (cc3[:, :, sx - 1], (sy, sz), (1, 2), lambda y, z: (sx - 1, y, z)),
   )
-  target_list = defaultdict(set)
+  # device part for all six faces first (2-D CCL + 2-D EDT, asynchronous), one synchronisation, then the
+  # host bookkeeping of the faces on a small thread pool (numpy releases the GIL in its sorts)
+  staged = []
   for face, pshape, dims, rotatefn in faces:
     wx, wy = anisotropy[dims[0]], anisotropy[dims[1]]
     plane = face.contiguous().view(-1)                     # flat Fortran order of the 2-D plane
-    if not bool(plane.any()):
-      continue
-    cc_plane, n = connected_components(plane, (pshape[0], pshape[1], 1))   # 8-connected in 2-D
-    dt_plane = edt(cc_plane.view(torch.int32), pshape, anisotropy=(wx, wy), black_border=True)
-    h_plane = plane.cpu().numpy().reshape(pshape, order="F")
-    h_cc = cc_plane.cpu().numpy().reshape(pshape, order="F")
-    h_dt = dt_plane.cpu().numpy().reshape(pshape, order="F")
+    cc_plane = _ccl_nosync(plane, (pshape[0], pshape[1], 1))   # 8-connected in 2-D
+    dt_plane = edt(cc_plane, pshape, anisotropy=(wx, wy), black_border=True)
+    staged.append((plane.to("cpu", non_blocking=True), cc_plane.to("cpu", non_blocking=True),
+                   dt_plane.to("cpu", non_blocking=True), pshape, wx, wy, rotatefn))
+  torch.cuda.synchronize()
+
+  def host_part(item):
+    plane, cc_plane, dt_plane, pshape, wx, wy, rotatefn = item
+    h_plane = plane.numpy().reshape(pshape, order="F")
+    if not h_plane.any():
+      return []
+    h_cc = cc_plane.numpy().reshape(pshape, order="F")
+    h_dt = dt_plane.numpy().reshape(pshape, order="F")
     plane_targets = border.find_border_targets(h_dt, h_cc, wx, wy)
     remap = border.plane_mapping(h_plane, h_cc)
-    for label, pt in plane_targets.items():
-      target_list[remap[label]].add(rotatefn(int(pt[0]), int(pt[1])))
+    return [(remap[label], rotatefn(int(pt[0]), int(pt[1]))) for label, pt in plane_targets.items()]
+
+  from concurrent.futures import ThreadPoolExecutor
+  with ThreadPoolExecutor(max_workers=6) as pool:
+    per_face = list(pool.map(host_part, staged))
+  target_list = defaultdict(set)
+  for items in per_face:                                   # same insertion order as the sequential loop
+    for label, pt in items:
+      target_list[label].add(pt)
   out = {}
   for label, pts in target_list.items():
     out[label] = np.array(list(pts), dtype=np.uint32)
@@ -253,26 +281,30 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
   # ---- the path loop for every label (trace.py:196-267) ----
   desc = np.zeros(n_jobs, dtype=DESC_DTYPE)
   targets = []
-  region = 0
-  path_off = 0
   order = sorted(range(n_jobs), key=lambda i: -jobs[i]["n_fg"])      # largest labels first
-  for slot, i in enumerate(order):
+  cols = {k: [] for k in ("segid", "root", "n_fg", "tb_off", "tb_n", "ta_off", "ta_n", "soma_mode", "soma_radius")}
+  for i in order:
     j = jobs[i]
-    tb = list(j["targets_before"])
-    ta = list(j["targets_after"])
+    tb = j["targets_before"]
+    ta = j["targets_after"]
     if not j["soma_mode"] and len(tb) == 0:
-      tb.append(int(target_idx[j["segid"]]))                          # trace.py:171-172
-    d = desc[slot]
-    d["segid"] = j["segid"]; d["root"] = j["root"]; d["n_fg"] = j["n_fg"]
-    d["region_off"] = region; region += j["n_fg"]
-    cap = 2 * j["n_fg"] + 2 * (len(tb) + len(ta)) + 64
-    d["path_off"] = path_off; d["path_cap"] = cap; path_off += cap
-    d["tb_off"] = len(targets); d["tb_n"] = len(tb); targets.extend(tb)
-    d["ta_off"] = len(targets); d["ta_n"] = len(ta); targets.extend(ta)
-    d["max_paths"] = NONE if params["max_paths"] is None else int(params["max_paths"])
-    d["soma_mode"] = 1 if j["soma_mode"] else 0
-    d["soma_radius"] = np.float32(j.get("soma_radius", 0.0))
-    d["bucket_row"] = j["segid"]
+      tb = [int(target_idx[j["segid"]])]                              # trace.py:171-172
+    cols["segid"].append(j["segid"]); cols["root"].append(j["root"]); cols["n_fg"].append(j["n_fg"])
+    cols["tb_off"].append(len(targets)); cols["tb_n"].append(len(tb)); targets.extend(tb)
+    cols["ta_off"].append(len(targets)); cols["ta_n"].append(len(ta)); targets.extend(ta)
+    cols["soma_mode"].append(1 if j["soma_mode"] else 0)
+    cols["soma_radius"].append(j.get("soma_radius", 0.0))
+  for k, v in cols.items():
+    desc[k] = np.asarray(v)
+  nfg = desc["n_fg"].astype(np.int64)
+  caps = 2 * nfg + 2 * (desc["tb_n"].astype(np.int64) + desc["ta_n"]) + 64
+  desc["region_off"] = np.concatenate(([0], np.cumsum(nfg)[:-1]))
+  desc["path_off"] = np.concatenate(([0], np.cumsum(caps)[:-1]))
+  desc["path_cap"] = caps
+  desc["max_paths"] = NONE if params["max_paths"] is None else int(params["max_paths"])
+  desc["bucket_row"] = desc["segid"]
+  region = int(nfg.sum())
+  path_off = int(caps.sum())
   assert path_off < 2 ** 32 and 6 * region < 2 ** 34
   scratch = torch.empty(6 * max(region, 1), dtype=torch.int32, device=dev)
   # soma labels: the one-off ball around the root (trace.py:160-168) is far too large for one CTA
