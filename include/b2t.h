@@ -136,7 +136,7 @@ int b2t_gather_paths(const uint32_t* d_pool, const uint32_t* d_src_off, const ui
 
 /* K6  hole filling (soma labels only) -----------------------------------------------------------------------
  * replaces  fill_voids.fill(labels, in_place=True, return_fill_count=True)    kimimaro/trace.py:109
- * d_mask uint8 [V] edited in place; d_reach [V] u32 scratch; d_queue 2*queue_cap u32 (queue_cap >= V);
+ * d_mask uint8 [V] edited in place; d_reach [V] u32 scratch; d_queue >= V u32 scratch (queue_cap >= V);
  * the fill count is left in d_ctrl[5]. */
 int b2t_fill_voids(uint8_t* d_mask, int64_t sx, int64_t sy, int64_t sz, uint32_t* d_reach,
                    uint32_t* d_queue, uint64_t queue_cap, uint32_t* d_ctrl, void* stream);

@@ -378,19 +378,19 @@ __device__ __forceinline__ float fh_intersect(float fi, int i, float h, int v, f
 }
 
 template <typename T, int NMAX>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 12)
 edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, int64_t cstride, int nx,
                        int64_t ostride, float w, int black_border, int last_pass) {
   const int x = blockIdx.x * 128 + threadIdx.x;
   if (x >= nx) return;
   const int64_t base = (int64_t)blockIdx.y * ostride + x;
   const float w2 = __fmul_rn(w, w);
-  // envelope entries of all runs of the column, concatenated.  Entry 0 of a run always sits on the run's
-  // first row (F&H never pops it), so ev[first] is the run start; its ez slot (the -inf boundary, never
-  // read as a number) stores (run end row << 16 | number of entries).
-  uint16_t ev[NMAX];
-  float eh[NMAX];
-  float ez[NMAX];
+  const float kInf = __int_as_float(0x7f800000);
+  // envelope entries of all runs of the column, concatenated, one 16-byte record each (one LDL/STL.128):
+  //   .x = row of the parabola, .y = its height, .z = left end of its reign (run-relative), .w = run header
+  // Entry 0 of a run always sits on the run's first row (F&H never pops it), so its .x is the run start;
+  // its .z (the -inf boundary, never read as a number) is unused and .w holds (run end row << 16 | entries).
+  uint4 e[NMAX];
 
   // ---------------- build ----------------
   int ktot = 0;          // entries written so far
@@ -418,48 +418,52 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
         float fi = fv[j];
         if (fi > kFltMax) fi = kFltMax;                      // tofinite()
         if (lab != run_lab) {
-          if (run_lab != T(0)) ez[k_lo] = __uint_as_float(((uint32_t)i << 16) | (uint32_t)(k - k_lo + 1));
+          if (run_lab != T(0)) e[k_lo].w = ((uint32_t)i << 16) | (uint32_t)(k - k_lo + 1);
           run_lab = lab;
           if (lab != T(0)) {
             a = i; k_lo = ktot; k = ktot; ktot++;
-            ev[k] = (uint16_t)i; eh[k] = fi;
-            tv = 0; th = fi; tz = -__int_as_float(0x7f800000);
+            e[k] = make_uint4((uint32_t)i, __float_as_uint(fi), 0u, 0u);
+            tv = 0; th = fi; tz = -kInf;
           }
         } else if (lab != T(0)) {
           const int ir = i - a;
           float s = fh_intersect(fi, ir, th, tv, w2);
           while (k > k_lo && s <= tz) {
             k--;
-            tv = (int)ev[k] - a; th = eh[k]; tz = (k > k_lo) ? ez[k] : -__int_as_float(0x7f800000);
+            const uint4 t = e[k];
+            tv = (int)t.x - a; th = __uint_as_float(t.y); tz = (k > k_lo) ? __uint_as_float(t.z) : -kInf;
             s = fh_intersect(fi, ir, th, tv, w2);
           }
           k++;
           ktot = k + 1;
-          ev[k] = (uint16_t)i; eh[k] = fi; ez[k] = s;
+          e[k] = make_uint4((uint32_t)i, __float_as_uint(fi), __float_as_uint(s), 0u);
           tv = ir; th = fi; tz = s;
         }
       }
     }
   }
-  if (run_lab != T(0)) ez[k_lo] = __uint_as_float(((uint32_t)n << 16) | (uint32_t)(k - k_lo + 1));
+  if (run_lab != T(0)) e[k_lo].w = ((uint32_t)n << 16) | (uint32_t)(k - k_lo + 1);
 
   // ---------------- query ----------------
   int r_lo = 0, r_cnt = 0, r_a = n, r_b = n;      // current run: entries [r_lo, r_lo+r_cnt), rows [r_a, r_b)
+  int kk = 0, cv = 0;
+  float ch = 0.0f, nz = kInf;
+  uint4 nxt = make_uint4(0u, 0u, 0u, 0u);          // entry kk+1, prefetched
   if (ktot > 0) {
-    const uint32_t pk = __float_as_uint(ez[0]);
-    r_a = (int)ev[0]; r_b = (int)(pk >> 16); r_cnt = (int)(pk & 0xffffu);
+    const uint4 t = e[0];
+    r_a = (int)t.x; r_b = (int)(t.w >> 16); r_cnt = (int)(t.w & 0xffffu);
+    ch = __uint_as_float(t.y);
+    if (r_cnt > 1) { nxt = e[1]; nz = __uint_as_float(nxt.z); }
   }
-  int kk = 0;
-  int cv = 0; float ch = eh[0];
-  float nz = (r_cnt > 1) ? ez[1] : __int_as_float(0x7f800000);
   for (int i = 0; i < n; i++) {
     if (i >= r_b) {                                           // move to the next run of this column
       r_lo += r_cnt;
       if (r_lo < ktot) {
-        const uint32_t pk = __float_as_uint(ez[r_lo]);
-        r_a = (int)ev[r_lo]; r_b = (int)(pk >> 16); r_cnt = (int)(pk & 0xffffu);
-        kk = r_lo; cv = 0; ch = eh[kk];
-        nz = (r_cnt > 1) ? ez[kk + 1] : __int_as_float(0x7f800000);
+        const uint4 t = e[r_lo];
+        r_a = (int)t.x; r_b = (int)(t.w >> 16); r_cnt = (int)(t.w & 0xffffu);
+        kk = r_lo; cv = 0; ch = __uint_as_float(t.y);
+        nz = kInf;
+        if (r_cnt > 1) { nxt = e[kk + 1]; nz = __uint_as_float(nxt.z); }
       } else {
         r_a = n; r_b = n + 1; r_cnt = 0;
       }
@@ -468,14 +472,15 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
       const int ir = i - r_a;
       while (nz < (float)ir) {
         kk++;
-        cv = (int)ev[kk] - r_a; ch = eh[kk];
-        nz = (kk + 1 < r_lo + r_cnt) ? ez[kk + 1] : __int_as_float(0x7f800000);
+        cv = (int)nxt.x - r_a; ch = __uint_as_float(nxt.y);
+        nz = kInf;
+        if (kk + 1 < r_lo + r_cnt) { nxt = e[kk + 1]; nz = __uint_as_float(nxt.z); }
       }
       const float di = (float)(ir - cv);
       float val = __fadd_rn(__fmul_rn(__fmul_rn(w2, di), di), ch);
-      if (r_a > 0 || black_border) { const float e = (float)(ir + 1); val = fminf(val, __fmul_rn(__fmul_rn(w2, e), e)); }
-      if (r_b < n || black_border) { const float e = (float)(r_b - i); val = fminf(val, __fmul_rn(__fmul_rn(w2, e), e)); }
-      if (last_pass) val = (val >= kFltMax) ? __int_as_float(0x7f800000) : sqrtf(val);
+      if (r_a > 0 || black_border) { const float ee = (float)(ir + 1); val = fminf(val, __fmul_rn(__fmul_rn(w2, ee), ee)); }
+      if (r_b < n || black_border) { const float ee = (float)(r_b - i); val = fminf(val, __fmul_rn(__fmul_rn(w2, ee), ee)); }
+      if (last_pass) val = (val >= kFltMax) ? kInf : sqrtf(val);
       f[base + (int64_t)i * cstride] = val;
     }
   }

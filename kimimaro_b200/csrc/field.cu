@@ -485,104 +485,6 @@ B2T_EXPORT int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, fl
 }
 
 // =================================================================================================
-// K6  fill_voids.fill (kimimaro/trace.py:109, soma labels only): flood the background
-// from the six faces through 6-connectivity, everything not reached becomes foreground.
-// Frontier sweep, one thread per frontier voxel, persistent cooperative kernel like edf_multi.
-// d_mask: uint8 [V] (0 background, non-zero foreground), edited in place.
-// d_reach: uint32 [V] scratch (zeroed here); d_queue: 2*queue_cap u32; d_ctrl: >= 8 u32; the number of
-// filled voxels is left in d_ctrl[5].
-// =================================================================================================
-namespace {
-
-struct FillParams {
-  uint8_t* mask;
-  uint32_t* reach;
-  uint32_t* queue;
-  uint32_t* ctrl;
-  uint64_t cap;
-  Dims d;
-  uint64_t V;
-};
-
-__global__ void fill_seed_kernel(FillParams p) {
-  // every background voxel on a face of the array seeds the flood
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.V) return;
-  if (p.mask[i]) return;
-  int x, y, z;
-  unravel((uint32_t)i, p.d, x, y, z);
-  if (x == 0 || y == 0 || z == 0 || x == p.d.sx - 1 || y == p.d.sy - 1 || z == p.d.sz - 1) {
-    p.reach[i] = 1;
-    const uint32_t pos = atomicAdd(&p.ctrl[1], 1u);
-    p.queue[p.cap + pos] = (uint32_t)i;
-  }
-}
-
-__global__ void __launch_bounds__(256) fill_flood_kernel(FillParams p) {
-  cg::grid_group grid = cg::this_grid();
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t nthreads = gridDim.x * blockDim.x;
-  uint32_t round = 1;
-  for (;;) {
-    const uint32_t n = __ldcg(&p.ctrl[round % 3]);
-    if (n == 0) break;
-    const uint32_t* qin = p.queue + (uint64_t)(round & 1) * p.cap;
-    uint32_t* qout = p.queue + (uint64_t)((round + 1) & 1) * p.cap;
-    uint32_t* cnt_out = &p.ctrl[(round + 1) % 3];
-    for (uint32_t it = tid; it < n; it += nthreads) {
-      const uint32_t u = __ldcg(&qin[it]);
-      int x, y, z;
-      unravel(u, p.d, x, y, z);
-      const int64_t offs[6] = {-1, 1, -(int64_t)p.d.sx, (int64_t)p.d.sx, -(int64_t)p.d.sxy, (int64_t)p.d.sxy};
-      const bool ok[6] = {x > 0, x < p.d.sx - 1, y > 0, y < p.d.sy - 1, z > 0, z < p.d.sz - 1};
-#pragma unroll
-      for (int k = 0; k < 6; k++) {
-        if (!ok[k]) continue;
-        const uint32_t v = (uint32_t)((int64_t)u + offs[k]);
-        if (p.mask[v]) continue;
-        if (atomicExch(&p.reach[v], 1u) == 0u) qout[atomicAdd(cnt_out, 1u)] = v;
-      }
-    }
-    grid.sync();
-    if (tid == 0) p.ctrl[round % 3] = 0;
-    round++;
-  }
-}
-
-__global__ void fill_apply_kernel(FillParams p) {
-  uint32_t filled = 0;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.V; i += (uint64_t)gridDim.x * blockDim.x) {
-    if (!p.mask[i] && !p.reach[i]) { p.mask[i] = 1; filled++; }
-  }
-  if (filled) atomicAdd(&p.ctrl[5], filled);
-}
-
-}  // namespace
-
-B2T_EXPORT int b2t_fill_voids(uint8_t* d_mask, int64_t sx, int64_t sy, int64_t sz, uint32_t* d_reach,
-                              uint32_t* d_queue, uint64_t queue_cap, uint32_t* d_ctrl, void* stream) {
-  if (int rc = check_dims(sx, sy, sz)) return rc;
-  B2T_REQUIRE(d_mask && d_reach && d_queue && d_ctrl, "b2t_fill_voids: null pointer");
-  cudaStream_t st = (cudaStream_t)stream;
-  FillParams p;
-  p.mask = d_mask; p.reach = d_reach; p.queue = d_queue; p.ctrl = d_ctrl; p.cap = queue_cap;
-  p.d = Dims{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
-  p.V = (uint64_t)sx * sy * sz;
-  B2T_CUDA_TRY(cudaMemsetAsync(d_reach, 0, p.V * sizeof(uint32_t), st));
-  B2T_CUDA_TRY(cudaMemsetAsync(d_ctrl, 0, 8 * sizeof(uint32_t), st));
-  fill_seed_kernel<<<(unsigned)((p.V + 255) / 256), 256, 0, st>>>(p);
-  int blocks = 0;
-  if (int rc = coop_grid((const void*)fill_flood_kernel, 256, 0, &blocks)) return rc;
-  void* args[] = {&p};
-  B2T_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)fill_flood_kernel, dim3(blocks), dim3(256), args, 0, st));
-  const uint64_t want = (p.V + 255) / 256;
-  fill_apply_kernel<<<(unsigned)(want < 148ull * 32 ? want : 148ull * 32), 256, 0, st>>>(p);
-  B2T_CUDA_TRY(cudaGetLastError());
-  b2t_count_launches(3);
-  return B2T_OK;
-}
-
-// =================================================================================================
 // Grid-wide rolling-ball invalidation (same round-synchronous claim semantics as trace.cu's
 // in-CTA version) for seeds whose ball is too large for one CTA: the one-off soma invalidation
 // (kimimaro/trace.py:160-168 -> skeletontricks.pyx:373-418 -> dijkstra_invalidation.hpp:239-332).
