@@ -382,106 +382,123 @@ __global__ void __launch_bounds__(128, 12)
 edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, int64_t cstride, int nx,
                        int64_t ostride, float w, int black_border, int last_pass) {
   const int x = blockIdx.x * 128 + threadIdx.x;
-  if (x >= nx) return;
-  const int64_t base = (int64_t)blockIdx.y * ostride + x;
+  const bool active = x < nx;                      // no early return: the warp reduces loop bounds together
+  const int64_t base = (int64_t)blockIdx.y * ostride + (active ? x : 0);
   const float w2 = __fmul_rn(w, w);
   const float kInf = __int_as_float(0x7f800000);
-  // envelope entries of all runs of the column, concatenated, one 16-byte record each (one LDL/STL.128):
-  //   .x = row of the parabola, .y = its height, .z = left end of its reign (run-relative), .w = run header
-  // Entry 0 of a run always sits on the run's first row (F&H never pops it), so its .x is the run start;
-  // its .z (the -inf boundary, never read as a number) is unused and .w holds (run end row << 16 | entries).
-  uint4 e[NMAX];
+  constexpr int kChunk = 32;                       // rows between flushes
+  // Envelope entries of the runs that are not flushed yet, concatenated: row (ev), height (eh), left end
+  // of the parabola's reign (ez, run-relative).  Entry 0 of a run always sits on the run's first row (F&H
+  // never pops it), so ev[first] is the run start; its ez slot (the -inf boundary, never read as a
+  // number) stores (run end row << 16 | number of entries).  Completed runs are queried every kChunk rows
+  // and the stack restarts from 0 whenever no run is open, so for the thin processes of a connectomics
+  // volume only a few dozen entries are ever live (cache resident); a blob keeps its run open and simply
+  // grows the stack up to the run length.
+  uint16_t ev[NMAX];
+  float eh[NMAX];
+  float ez[NMAX];
 
-  // ---------------- build ----------------
-  int ktot = 0;          // entries written so far
+  int ktot = 0;          // entries in the stack
   int k_lo = 0, k = -1;  // first / top entry of the open run
   int a = 0;             // first row of the open run
   T run_lab = T(0);
   int tv = 0; float th = 0.0f, tz = 0.0f;   // top entry, cached
-  for (int i0 = 0; i0 < n; i0 += 8) {
-    float fv[8];
-    T lv[8];
+  // query cursor over the closed runs
+  int q_next = 0;                            // first row not written yet
+  int r_lo = 0, r_cnt = 0, r_a = 0x7fffffff, r_b = 0;
+  int kk = 0, cv = 0;
+  float ch = 0.0f, nz = kInf;
+
+  for (int c0 = 0; c0 < n; c0 += kChunk) {
+    const int c1 = min(n, c0 + kChunk);
+    // ---------------- build: rows [c0, c1) ----------------
+    for (int i0 = c0; i0 < c1; i0 += 8) {
+      float fv[8];
+      T lv[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      fv[j] = 0.0f; lv[j] = T(0);
-      if (i0 + j < n) {
-        const int64_t idx = base + (int64_t)(i0 + j) * cstride;
-        fv[j] = f[idx];
-        lv[j] = labels[idx];
+      for (int j = 0; j < 8; j++) {
+        fv[j] = 0.0f; lv[j] = T(0);
+        if (active && i0 + j < c1) {
+          const int64_t idx = base + (int64_t)(i0 + j) * cstride;
+          fv[j] = f[idx];
+          lv[j] = labels[idx];
+        }
       }
-    }
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int i = i0 + j;
-      if (i < n) {
-        const T lab = lv[j];
-        float fi = fv[j];
-        if (fi > kFltMax) fi = kFltMax;                      // tofinite()
-        if (lab != run_lab) {
-          if (run_lab != T(0)) e[k_lo].w = ((uint32_t)i << 16) | (uint32_t)(k - k_lo + 1);
-          run_lab = lab;
-          if (lab != T(0)) {
-            a = i; k_lo = ktot; k = ktot; ktot++;
-            e[k] = make_uint4((uint32_t)i, __float_as_uint(fi), 0u, 0u);
-            tv = 0; th = fi; tz = -kInf;
+      for (int j = 0; j < 8; j++) {
+        const int i = i0 + j;
+        if (i < c1) {
+          const T lab = lv[j];
+          float fi = fv[j];
+          if (fi > kFltMax) fi = kFltMax;                      // tofinite()
+          if (lab != run_lab) {
+            if (run_lab != T(0)) ez[k_lo] = __uint_as_float(((uint32_t)i << 16) | (uint32_t)(k - k_lo + 1));
+            run_lab = lab;
+            if (lab != T(0)) {
+              a = i; k_lo = ktot; k = ktot; ktot++;
+              ev[k] = (uint16_t)i; eh[k] = fi;
+              tv = 0; th = fi; tz = -kInf;
+            }
+          } else if (lab != T(0)) {
+            const int ir = i - a;
+            float s = fh_intersect(fi, ir, th, tv, w2);
+            while (k > k_lo && s <= tz) {
+              k--;
+              tv = (int)ev[k] - a; th = eh[k]; tz = (k > k_lo) ? ez[k] : -kInf;
+              s = fh_intersect(fi, ir, th, tv, w2);
+            }
+            k++;
+            ktot = k + 1;
+            ev[k] = (uint16_t)i; eh[k] = fi; ez[k] = s;
+            tv = ir; th = fi; tz = s;
           }
-        } else if (lab != T(0)) {
-          const int ir = i - a;
-          float s = fh_intersect(fi, ir, th, tv, w2);
-          while (k > k_lo && s <= tz) {
-            k--;
-            const uint4 t = e[k];
-            tv = (int)t.x - a; th = __uint_as_float(t.y); tz = (k > k_lo) ? __uint_as_float(t.z) : -kInf;
-            s = fh_intersect(fi, ir, th, tv, w2);
-          }
-          k++;
-          ktot = k + 1;
-          e[k] = make_uint4((uint32_t)i, __float_as_uint(fi), __float_as_uint(s), 0u);
-          tv = ir; th = fi; tz = s;
         }
       }
     }
-  }
-  if (run_lab != T(0)) e[k_lo].w = ((uint32_t)n << 16) | (uint32_t)(k - k_lo + 1);
-
-  // ---------------- query ----------------
-  int r_lo = 0, r_cnt = 0, r_a = n, r_b = n;      // current run: entries [r_lo, r_lo+r_cnt), rows [r_a, r_b)
-  int kk = 0, cv = 0;
-  float ch = 0.0f, nz = kInf;
-  uint4 nxt = make_uint4(0u, 0u, 0u, 0u);          // entry kk+1, prefetched
-  if (ktot > 0) {
-    const uint4 t = e[0];
-    r_a = (int)t.x; r_b = (int)(t.w >> 16); r_cnt = (int)(t.w & 0xffffu);
-    ch = __uint_as_float(t.y);
-    if (r_cnt > 1) { nxt = e[1]; nz = __uint_as_float(nxt.z); }
-  }
-  for (int i = 0; i < n; i++) {
-    if (i >= r_b) {                                           // move to the next run of this column
-      r_lo += r_cnt;
-      if (r_lo < ktot) {
-        const uint4 t = e[r_lo];
-        r_a = (int)t.x; r_b = (int)(t.w >> 16); r_cnt = (int)(t.w & 0xffffu);
-        kk = r_lo; cv = 0; ch = __uint_as_float(t.y);
-        nz = kInf;
-        if (r_cnt > 1) { nxt = e[kk + 1]; nz = __uint_as_float(nxt.z); }
-      } else {
-        r_a = n; r_b = n + 1; r_cnt = 0;
+    const bool open = run_lab != T(0) && c1 < n;
+    if (run_lab != T(0) && c1 == n) {                        // the column ends inside a run
+      ez[k_lo] = __uint_as_float(((uint32_t)n << 16) | (uint32_t)(k - k_lo + 1));
+      run_lab = T(0);
+    }
+    // ---------------- query: rows [q_next, q_end) of the closed runs ----------------
+    const int q_end = open ? a : c1;                         // rows of a still open run wait for its end
+    const int kdone = open ? k_lo : ktot;                    // entries that belong to closed runs
+    const bool todo = active && q_next < q_end;
+    const int lo = __reduce_min_sync(0xffffffffu, todo ? q_next : 0x7fffffff);
+    const int hi = __reduce_max_sync(0xffffffffu, todo ? q_end : 0);
+    for (int i = lo; i < hi; i++) {
+      if (todo && i >= q_next && i < q_end) {
+        if (i >= r_b) {                                       // move to the next closed run
+          r_lo += r_cnt;
+          if (r_lo < kdone) {
+            const uint32_t pk = __float_as_uint(ez[r_lo]);
+            r_a = (int)ev[r_lo]; r_b = (int)(pk >> 16); r_cnt = (int)(pk & 0xffffu);
+            kk = r_lo; cv = 0; ch = eh[kk];
+            nz = (r_cnt > 1) ? ez[kk + 1] : kInf;
+          } else {
+            r_a = 0x7fffffff; r_b = q_end; r_cnt = 0;        // only background left before q_end
+          }
+        }
+        if (i >= r_a && i < r_b) {
+          const int ir = i - r_a;
+          while (nz < (float)ir) {
+            kk++;
+            cv = (int)ev[kk] - r_a; ch = eh[kk];
+            nz = (kk + 1 < r_lo + r_cnt) ? ez[kk + 1] : kInf;
+          }
+          const float di = (float)(ir - cv);
+          float val = __fadd_rn(__fmul_rn(__fmul_rn(w2, di), di), ch);
+          if (r_a > 0 || black_border) { const float ee = (float)(ir + 1); val = fminf(val, __fmul_rn(__fmul_rn(w2, ee), ee)); }
+          if (r_b < n || black_border) { const float ee = (float)(r_b - i); val = fminf(val, __fmul_rn(__fmul_rn(w2, ee), ee)); }
+          if (last_pass) val = (val >= kFltMax) ? kInf : sqrtf(val);
+          f[base + (int64_t)i * cstride] = val;
+        }
       }
     }
-    if (i >= r_a && i < r_b) {
-      const int ir = i - r_a;
-      while (nz < (float)ir) {
-        kk++;
-        cv = (int)nxt.x - r_a; ch = __uint_as_float(nxt.y);
-        nz = kInf;
-        if (kk + 1 < r_lo + r_cnt) { nxt = e[kk + 1]; nz = __uint_as_float(nxt.z); }
-      }
-      const float di = (float)(ir - cv);
-      float val = __fadd_rn(__fmul_rn(__fmul_rn(w2, di), di), ch);
-      if (r_a > 0 || black_border) { const float ee = (float)(ir + 1); val = fminf(val, __fmul_rn(__fmul_rn(w2, ee), ee)); }
-      if (r_b < n || black_border) { const float ee = (float)(r_b - i); val = fminf(val, __fmul_rn(__fmul_rn(w2, ee), ee)); }
-      if (last_pass) val = (val >= kFltMax) ? kInf : sqrtf(val);
-      f[base + (int64_t)i * cstride] = val;
+    if (q_end > q_next) q_next = q_end;
+    if (!open) {                                             // everything flushed: restart the stack
+      ktot = 0; k_lo = 0; k = -1;
+      r_lo = 0; r_cnt = 0; r_a = 0x7fffffff; r_b = 0;
     }
   }
 }
