@@ -117,23 +117,50 @@ def find_border_targets(dt, cc_plane, wx, wy):
   first_pos = si[gstart]                       # first raster position of every label
   for l in sl[gstart][np.argsort(first_pos, kind="stable")].tolist():  # dict insertion order = first encounter (B.6)
     pts[l] = None
-  cents = None
+  # Labels with a single maximum are done.  For the others the reference folds compute_tiebreaker_maxima
+  # over the candidates in raster order; that comparator is a lexicographic strict order on
+  # (distance to the label centroid, to the plane centre, cornerness, edgeness) that keeps the earlier
+  # candidate on a full tie, so the fold equals "lexicographic minimum, earliest on ties" -- evaluated here
+  # for all candidates of all labels at once with the same float32 / float64 expression order.
   cl, ci = cand_lab, cand_idx
   bounds = np.flatnonzero(np.diff(cl)) + 1
   starts = np.concatenate(([0], bounds))
   ends = np.concatenate((bounds, [cl.size]))
-  for a, b in zip(starts.tolist(), ends.tolist()):
-    l = int(cl[a])
-    i0 = int(ci[a])
-    cur = (i0 % sx, i0 // sx)
-    if b - a > 1:
-      if cents is None:
-        cents = Centroids(cc_plane, wx, wy)
-      cxy = cents(l)
-      for i in ci[a + 1:b].tolist():
-        r = tiebreak(cur[0], cur[1], i % sx, i // sx, cxy[0], cxy[1], sx, sy, wx, wy)
-        cur = (r[0], r[1])
-    pts[l] = cur
+  single = (ends - starts) == 1
+  for l, i in zip(cl[starts[single]].tolist(), ci[starts[single]].tolist()):
+    pts[l] = (i % sx, i // sx)
+  if (~single).any():
+    cents = Centroids(cc_plane, wx, wy)
+    multi = np.repeat(~single, ends - starts)
+    ml, mi = cl[multi], ci[multi]
+    px = (mi % sx).astype(np.float32)
+    py = (mi // sx).astype(np.float32)
+    labs_multi = cl[starts[~single]]
+    cxy = np.array([cents(int(l)) for l in labs_multi.tolist()], dtype=np.float32).reshape(-1, 2)
+    rep = (ends - starts)[~single]
+    centx = np.repeat(cxy[:, 0], rep)
+    centy = np.repeat(cxy[:, 1], rep)
+    wxf, wyf, fsx, fsy = f32(wx), f32(wy), f32(sx), f32(sy)
+    half = f32(0.5)
+
+    def dsq(ax, ay, bx, by):                       # distsq (pyx:750-760), float32 throughout
+      u = wxf * (ax - bx)
+      v = wyf * (ay - by)
+      return u * u + v * v
+
+    c1 = dsq(px, py, centx, centy)
+    c2 = dsq(px, py, f32(f32(wxf * fsx) / f32(2.0)), f32(f32(wyf * fsy) / f32(2.0)))
+    c3 = np.minimum(np.minimum(dsq(px, py, -half, -half), dsq(px, py, f32(fsx - half), -half)),
+                    np.minimum(dsq(px, py, f32(fsx - half), f32(fsy - half)), dsq(px, py, -half, f32(fsx - half))))
+    pxd, pyd = px.astype(np.float64), py.astype(np.float64)
+    wxd, wyd = float(wxf), float(wyf)
+    c4 = np.minimum(np.minimum(wxd * (pxd - 0.5), wxd * (float(sx) - 0.5 - pxd)),
+                    np.minimum(wyd * (pyd - 0.5), wyd * (float(sy) - 0.5 - pyd))).astype(np.float32)
+    order = np.lexsort((np.arange(ml.size), c4, c3, c2, c1, ml))
+    ml_sorted = ml[order]
+    firsts = np.concatenate(([0], np.flatnonzero(np.diff(ml_sorted)) + 1))
+    for l, i in zip(ml_sorted[firsts].tolist(), mi[order][firsts].tolist()):
+      pts[l] = (i % sx, i // sx)
   return pts
 
 

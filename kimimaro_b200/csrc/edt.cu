@@ -377,8 +377,8 @@ __device__ __forceinline__ float fh_intersect(float fi, int i, float h, int v, f
   return __fdiv_rn(__fadd_rn(__fsub_rn(fi, h), __fmul_rn(f1, f2)), __fmul_rn(2.0f, f1));
 }
 
-template <typename T, int NMAX>
-__global__ void __launch_bounds__(128, 12)
+template <typename T, int NMAX, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, int64_t cstride, int nx,
                        int64_t ostride, float w, int black_border, int last_pass) {
   const int x = blockIdx.x * 128 + threadIdx.x;
@@ -526,18 +526,27 @@ int edt_launch_v2(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wx,
     edt_pass_x_kernel<T><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(labels, out, (int)sx, nrows, wx, black_border);
   }
   const dim3 gy((unsigned)b2t_ceil_div(sx, 128), (unsigned)sz), gz((unsigned)b2t_ceil_div(sx, 128), (unsigned)sy);
-#define B2T_FH(NM)                                                                                                    \
+  static const int minb = []() { const char* e = getenv("B2T_FH_MINB"); return e ? atoi(e) : 12; }();
+#define B2T_FH2(NM, MB)                                                                                               \
   do {                                                                                                                \
-    edt_pass_col_fh_kernel<T, NM><<<gy, 128, 0, st>>>(labels, out, (int)sy, sx, (int)sx, sx * sy, wy, black_border,  \
-                                                     ndim == 2);                                                      \
+    edt_pass_col_fh_kernel<T, NM, MB><<<gy, 128, 0, st>>>(labels, out, (int)sy, sx, (int)sx, sx * sy, wy,            \
+                                                         black_border, ndim == 2);                                    \
     if (ndim == 3)                                                                                                    \
-      edt_pass_col_fh_kernel<T, NM><<<gz, 128, 0, st>>>(labels, out, (int)sz, sx * sy, (int)sx, sx, wz, black_border, 1); \
+      edt_pass_col_fh_kernel<T, NM, MB><<<gz, 128, 0, st>>>(labels, out, (int)sz, sx * sy, (int)sx, sx, wz,          \
+                                                           black_border, 1);                                          \
+  } while (0)
+#define B2T_FH(NM)                          \
+  do {                                      \
+    if (minb >= 16) B2T_FH2(NM, 16);        \
+    else if (minb <= 8) B2T_FH2(NM, 8);     \
+    else B2T_FH2(NM, 12);                   \
   } while (0)
   if (nmax <= 256) B2T_FH(256);
   else if (nmax <= 512) B2T_FH(512);
   else if (nmax <= 1024) B2T_FH(1024);
   else B2T_FH(2048);
 #undef B2T_FH
+#undef B2T_FH2
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(ndim == 3 ? 3 : 2);
   return B2T_OK;
