@@ -129,6 +129,11 @@ int b2t_invalidate_ball(const uint32_t* d_cc, const float* d_dbf, uint64_t* d_cl
                         float scale, float konst, uint32_t* d_fv, uint32_t* d_fs, uint64_t cap,
                         uint32_t* d_ctrl, void* stream);
 
+/* N2 helper: strictly sequential float32 sums per segment (label centroids of a face in the reference's
+ * accumulation order, ext/skeletontricks/skeletontricks.pyx:528-588 compute_centroids). */
+int b2t_segment_seqsum(const float* d_xs, const float* d_ys, const int64_t* d_off, uint32_t n_seg,
+                       float* d_outx, float* d_outy, void* stream);
+
 /* skeleton buffers: compact the path segments and fetch radii = DBF[vertex] (kimimaro/trace.py:186-187) */
 int b2t_gather_paths(const uint32_t* d_pool, const uint32_t* d_src_off, const uint32_t* d_len,
                      const uint64_t* d_dst_off, uint32_t n_seg, const float* d_dbf, uint32_t* d_dst_vox,

@@ -164,6 +164,86 @@ def find_border_targets(dt, cc_plane, wx, wy):
   return pts
 
 
+def centroid_from_sums(xsum, ysum, count, sx, sy, wx, wy):
+  """The tail of compute_centroids (pyx:566-586) from the sequential float32 sums of a label."""
+  wx, wy = f32(wx), f32(wy)
+  ct = f32(count)
+  cx = f32(f32(wx * f32(sx)) / f32(2))
+  cy = f32(f32(wy * f32(sy)) / f32(2))
+  px = f32(f32(wx * f32(xsum)) / ct)
+  py = f32(f32(wy * f32(ysum)) / ct)
+  if not (f32(px - cx) >= 0):
+    px = f32(px + wx)
+  if not (f32(py - cy) >= 0):
+    py = f32(py + wy)
+  return (int(f32(px / wx)), int(f32(py / wy)))
+
+
+def targets_from_candidates(cand_idx, cand_lab, labels, first_pos, xsum, ysum, count, sx, sy, wx, wy):
+  """
+  find_border_targets (pyx:591-648) when the per-label reductions were done on the device:
+    cand_idx / cand_lab  flat (x + sx*y) positions of every voxel that attains its label's DT maximum, in
+                         raster order, and their labels
+    labels, first_pos    the labels present and the raster position where each is first met
+    xsum, ysum, count    per entry of `labels`: sequential float32 coordinate sums (scan order x outer,
+                         y inner) and voxel count, for compute_centroids
+  Returns {label: (x, y)} with keys in first-encounter order.
+  """
+  pts = {}
+  if len(labels) == 0:
+    return pts
+  labels = np.asarray(labels)
+  for l in labels[np.argsort(np.asarray(first_pos), kind="stable")].tolist():
+    pts[l] = None
+  slot = {int(l): k for k, l in enumerate(labels.tolist())}
+  order = np.argsort(cand_lab, kind="stable")
+  cl, ci = np.asarray(cand_lab)[order], np.asarray(cand_idx)[order]
+  bounds = np.flatnonzero(np.diff(cl)) + 1
+  starts = np.concatenate(([0], bounds))
+  ends = np.concatenate((bounds, [cl.size]))
+  single = (ends - starts) == 1
+  for l, i in zip(cl[starts[single]].tolist(), ci[starts[single]].tolist()):
+    pts[l] = (i % sx, i // sx)
+  if (~single).any():
+    multi = np.repeat(~single, ends - starts)
+    ml, mi = cl[multi], ci[multi]
+    px = (mi % sx).astype(np.float32)
+    py = (mi // sx).astype(np.float32)
+    labs_multi = cl[starts[~single]]
+    cxy = np.array([centroid_from_sums(xsum[slot[l]], ysum[slot[l]], count[slot[l]], sx, sy, wx, wy)
+                    for l in labs_multi.tolist()], dtype=np.float32).reshape(-1, 2)
+    rep = (ends - starts)[~single]
+    c1, c2, c3, c4 = _criteria(px, py, np.repeat(cxy[:, 0], rep), np.repeat(cxy[:, 1], rep), sx, sy, wx, wy)
+    o2 = np.lexsort((np.arange(ml.size), c4, c3, c2, c1, ml))
+    ml_sorted = ml[o2]
+    firsts = np.concatenate(([0], np.flatnonzero(np.diff(ml_sorted)) + 1))
+    for l, i in zip(ml_sorted[firsts].tolist(), mi[o2][firsts].tolist()):
+      pts[l] = (i % sx, i // sx)
+  return pts
+
+
+def _criteria(px, py, centx, centy, sx, sy, wx, wy):
+  """The four tie-break criteria of compute_tiebreaker_maxima (pyx:650-760) for arrays of candidates, with the
+  reference's float32 (distsq, cornerness) and float64 (edgeness) expression order."""
+  wxf, wyf, fsx, fsy = f32(wx), f32(wy), f32(sx), f32(sy)
+  half = f32(0.5)
+
+  def dsq(ax, ay, bx, by):
+    u = wxf * (ax - bx)
+    v = wyf * (ay - by)
+    return u * u + v * v
+
+  c1 = dsq(px, py, centx, centy)
+  c2 = dsq(px, py, f32(f32(wxf * fsx) / f32(2.0)), f32(f32(wyf * fsy) / f32(2.0)))
+  c3 = np.minimum(np.minimum(dsq(px, py, -half, -half), dsq(px, py, f32(fsx - half), -half)),
+                  np.minimum(dsq(px, py, f32(fsx - half), f32(fsy - half)), dsq(px, py, -half, f32(fsx - half))))
+  pxd, pyd = px.astype(np.float64), py.astype(np.float64)
+  wxd, wyd = float(wxf), float(wyf)
+  c4 = np.minimum(np.minimum(wxd * (pxd - 0.5), wxd * (float(sx) - 0.5 - pxd)),
+                  np.minimum(wyd * (pyd - 0.5), wyd * (float(sy) - 0.5 - pyd))).astype(np.float32)
+  return c1, c2, c3, c4
+
+
 def plane_mapping(plane, cc_plane):
   """get_mapping (pyx:490-525) on a face: {plane component id: volume cc label}."""
   fcc = np.asarray(cc_plane).reshape(-1)

@@ -526,7 +526,7 @@ int edt_launch_v2(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wx,
     edt_pass_x_kernel<T><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(labels, out, (int)sx, nrows, wx, black_border);
   }
   const dim3 gy((unsigned)b2t_ceil_div(sx, 128), (unsigned)sz), gz((unsigned)b2t_ceil_div(sx, 128), (unsigned)sy);
-  static const int minb = []() { const char* e = getenv("B2T_FH_MINB"); return e ? atoi(e) : 12; }();
+  static const int minb = []() { const char* e = getenv("B2T_FH_MINB"); return e ? atoi(e) : 8; }();
 #define B2T_FH2(NM, MB)                                                                                               \
   do {                                                                                                                \
     edt_pass_col_fh_kernel<T, NM, MB><<<gy, 128, 0, st>>>(labels, out, (int)sy, sx, (int)sx, sx * sy, wy,            \

@@ -258,6 +258,34 @@ B2T_EXPORT int b2t_fill_voids(uint8_t* d_mask, int64_t sx, int64_t sy, int64_t s
   return B2T_OK;
 }
 
+// Sequential float32 sums over segments: out[s] = ((0 + v[a]) + v[a+1]) + ... for a = off[s] .. off[s+1]-1.
+// One thread per segment, strictly left to right, because the reference accumulates label centroids in
+// float32 in scan order (compute_centroids, ext/skeletontricks/skeletontricks.pyx:528-588: `xsum[label] += x`)
+// and a tree reduction would round differently once a sum passes 2^24.
+__global__ void segment_seqsum_kernel(const float* __restrict__ xs, const float* __restrict__ ys,
+                                      const int64_t* __restrict__ off, uint32_t n_seg, float* __restrict__ outx,
+                                      float* __restrict__ outy) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  float ax = 0.0f, ay = 0.0f;
+  for (int64_t i = off[s]; i < off[s + 1]; i++) {
+    ax = __fadd_rn(ax, xs[i]);
+    ay = __fadd_rn(ay, ys[i]);
+  }
+  outx[s] = ax;
+  outy[s] = ay;
+}
+
+B2T_EXPORT int b2t_segment_seqsum(const float* d_xs, const float* d_ys, const int64_t* d_off, uint32_t n_seg,
+                                  float* d_outx, float* d_outy, void* stream) {
+  if (n_seg == 0) return B2T_OK;
+  B2T_REQUIRE(d_xs && d_ys && d_off && d_outx && d_outy, "b2t_segment_seqsum: null pointer");
+  segment_seqsum_kernel<<<(n_seg + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_xs, d_ys, d_off, n_seg, d_outx, d_outy);
+  B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(1);
+  return B2T_OK;
+}
+
 // Compact n_seg path segments (pool[src_off[j] .. +len[j])) to dst[dst_off[j] ..) and fetch DBF at each vertex.
 B2T_EXPORT int b2t_gather_paths(const uint32_t* d_pool, const uint32_t* d_src_off, const uint32_t* d_len,
                                 const uint64_t* d_dst_off, uint32_t n_seg, const float* d_dbf, uint32_t* d_dst_vox,

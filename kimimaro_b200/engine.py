@@ -39,6 +39,7 @@ _lib.declare("b2t_ccl26_roots", [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c
 _lib.declare("b2t_ccl_relabel", [c_vp, c_vp, c_u64, c_vp])
 _lib.declare("b2t_invalidate_ball", [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_u32, c_f32, c_f32,
                                      c_vp, c_vp, c_u64, c_vp, c_vp])
+_lib.declare("b2t_segment_seqsum", [c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp])
 _lib.declare("b2t_gather_paths", [c_vp, c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp])
 
 NBUCKETS = 256
@@ -151,36 +152,62 @@ def compute_border_targets(d_cc, shape, anisotropy):
     (cc3[:, :, 0], (sy, sz), (1, 2), lambda y, z: (0, y, z)),
     (cc3[:, :, sx - 1], (sy, sz), (1, 2), lambda y, z: (sx - 1, y, z)),
   )
-  # device part for all six faces first (2-D CCL + 2-D EDT, asynchronous), one synchronisation, then the
-  # host bookkeeping of the faces on a small thread pool (numpy releases the GIL in its sorts)
+  # Per face, on the device: 2-D connected components, 2-D EDT (both through the C ABI), then the
+  # per-label reductions of find_border_targets / compute_centroids / get_mapping as torch plumbing
+  # (scatter-reduce, sort, searchsorted) plus b2t_segment_seqsum for the reference's sequential float32
+  # centroid sums.  Only the candidates that tie for a label's DT maximum (a few thousand numbers per face)
+  # go to the host, where the reference's tie-break order is applied (border.targets_from_candidates).
+  L = lib()
   staged = []
   for face, pshape, dims, rotatefn in faces:
-    wx, wy = anisotropy[dims[0]], anisotropy[dims[1]]
-    plane = face.contiguous().view(-1)                     # flat Fortran order of the 2-D plane
-    cc_plane = _ccl_nosync(plane, (pshape[0], pshape[1], 1))   # 8-connected in 2-D
-    dt_plane = edt(cc_plane, pshape, anisotropy=(wx, wy), black_border=True)
-    staged.append((plane.to("cpu", non_blocking=True), cc_plane.to("cpu", non_blocking=True),
-                   dt_plane.to("cpu", non_blocking=True), pshape, wx, wy, rotatefn))
-  torch.cuda.synchronize()
-
-  def host_part(item):
-    plane, cc_plane, dt_plane, pshape, wx, wy, rotatefn = item
-    h_plane = plane.numpy().reshape(pshape, order="F")
-    if not h_plane.any():
-      return []
-    h_cc = cc_plane.numpy().reshape(pshape, order="F")
-    h_dt = dt_plane.numpy().reshape(pshape, order="F")
-    plane_targets = border.find_border_targets(h_dt, h_cc, wx, wy)
-    remap = border.plane_mapping(h_plane, h_cc)
-    return [(remap[label], rotatefn(int(pt[0]), int(pt[1]))) for label, pt in plane_targets.items()]
-
-  from concurrent.futures import ThreadPoolExecutor
-  with ThreadPoolExecutor(max_workers=6) as pool:
-    per_face = list(pool.map(host_part, staged))
+    wx, wy = float(anisotropy[dims[0]]), float(anisotropy[dims[1]])
+    p0, p1 = int(pshape[0]), int(pshape[1])
+    P = p0 * p1
+    dev = face.device
+    plane = face.contiguous().view(-1)                     # flat Fortran order of the 2-D plane: x + p0*y
+    cc_plane = _ccl_nosync(plane, (p0, p1, 1))             # 8-connected in 2-D (intake.py:564)
+    dt = edt(cc_plane, pshape, anisotropy=(wx, wy), black_border=True)       # intake.py:565
+    cc64 = cc_plane.to(torch.int64)
+    idx_sel = torch.nonzero((cc64 != 0) & (dt != 0)).view(-1)
+    if idx_sel.numel() == 0:
+      continue
+    lab_sel = cc64[idx_sel]
+    dt_sel = dt[idx_sel]
+    mx = torch.zeros(P + 1, dtype=torch.float32, device=dev).scatter_reduce_(0, lab_sel, dt_sel, "amax")
+    is_max = dt_sel == mx[lab_sel]
+    cand_idx, cand_lab = idx_sel[is_max], lab_sel[is_max]
+    present = torch.unique(cand_lab)
+    first_pos = torch.full((P + 1,), P, dtype=torch.int64, device=dev).scatter_reduce_(0, lab_sel, idx_sel, "amin")
+    vol_of = torch.zeros(P + 1, dtype=torch.int32, device=dev)
+    vol_of[cc64] = plane                                   # get_mapping: every voxel of a component agrees
+    # centroid sums in the reference's scan order (x outer, y inner), strictly sequential in float32
+    cc_c = cc_plane.view(p1, p0).t().contiguous().view(-1)                   # index = x*p1 + y
+    vals, order = torch.sort(cc_c, stable=True)
+    xs = (order // p1).to(torch.float32)
+    ys = (order % p1).to(torch.float32)
+    seg_lo = torch.searchsorted(vals, present.to(vals.dtype))
+    seg_hi = torch.searchsorted(vals, present.to(vals.dtype), right=True)
+    n_seg = int(present.numel())
+    # segments are not adjacent (labels absent from `present` sit in between): gather them into one run
+    lens = seg_hi - seg_lo
+    off = torch.zeros(n_seg + 1, dtype=torch.int64, device=dev)
+    off[1:] = torch.cumsum(lens, 0)
+    pos = torch.repeat_interleave(seg_lo - off[:-1], lens) + torch.arange(int(off[-1].item()), device=dev)
+    gx, gy = xs[pos].contiguous(), ys[pos].contiguous()
+    sumx = torch.empty(n_seg, dtype=torch.float32, device=dev)
+    sumy = torch.empty(n_seg, dtype=torch.float32, device=dev)
+    check(L.b2t_segment_seqsum(_p(gx), _p(gy), _p(off), c_u32(n_seg), _p(sumx), _p(sumy), stream_ptr()),
+          "b2t_segment_seqsum")
+    staged.append((cand_idx.cpu().numpy(), cand_lab.cpu().numpy(), present.cpu().numpy(),
+                   first_pos[present].cpu().numpy(), sumx.cpu().numpy(), sumy.cpu().numpy(), lens.cpu().numpy(),
+                   vol_of[present].cpu().numpy(), p0, p1, wx, wy, rotatefn))
   target_list = defaultdict(set)
-  for items in per_face:                                   # same insertion order as the sequential loop
-    for label, pt in items:
-      target_list[label].add(pt)
+  for (cand_idx, cand_lab, present, first_pos, sumx, sumy, cnt, vol_of, p0, p1, wx, wy, rotatefn) in staged:
+    plane_targets = border.targets_from_candidates(cand_idx, cand_lab, present, first_pos, sumx, sumy, cnt,
+                                                   p0, p1, wx, wy)
+    vol = {int(l): int(v) for l, v in zip(present.tolist(), vol_of.tolist())}
+    for label, pt in plane_targets.items():
+      target_list[vol[label]].add(rotatefn(int(pt[0]), int(pt[1])))
   out = {}
   for label, pts in target_list.items():
     out[label] = np.array(list(pts), dtype=np.uint32)

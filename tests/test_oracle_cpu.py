@@ -161,6 +161,40 @@ def test_border_targets_vs_reference_ext(orc, ref_ext):
     assert list(norm(got_p)) == list(norm(want))          # dict order feeds list(set) order
 
 
+def test_targets_from_candidates_vs_reference_ext(orc, ref_ext):
+  """The host half of the device-assisted border-target path, fed with numpy-computed reductions."""
+  if ref_ext is None:
+    pytest.skip("oracle/_ref not built")
+  from kimimaro_b200 import border
+  rng = np.random.default_rng(18)
+  for trial in range(10):
+    plane = np.zeros((48, 37), np.uint32, order="F")
+    for l in range(1, 8):
+      x0, y0 = int(rng.integers(0, 36)), int(rng.integers(0, 26))
+      plane[x0:x0 + int(rng.integers(2, 14)), y0:y0 + int(rng.integers(2, 12))] = l
+    cc, _ = orc.connected_components(plane)
+    wx, wy = (16.0, 40.0) if trial % 2 else (1.0, 1.0)
+    dt = orc.edt(cc, (wx, wy), True)
+    want = ref_ext.find_border_targets(dt, cc.astype(np.uint32), wx, wy)
+    sx, sy = cc.shape
+    fcc, fdt = cc.reshape(-1, order="F").astype(np.int64), dt.reshape(-1, order="F")
+    sel = np.flatnonzero((fcc != 0) & (fdt != 0))
+    labs = np.unique(fcc[sel])
+    mx = {l: fdt[sel][fcc[sel] == l].max() for l in labs}
+    keep = np.array([fdt[i] == mx[fcc[i]] for i in sel], dtype=bool)
+    first = [int(sel[fcc[sel] == l][0]) for l in labs]
+    c_order = np.ascontiguousarray(cc)
+    xs, ys, ct = [], [], []
+    for l in labs:
+      xx, yy = np.nonzero(c_order == l)
+      xs.append(np.add.accumulate(xx.astype(np.float32), dtype=np.float32)[-1])
+      ys.append(np.add.accumulate(yy.astype(np.float32), dtype=np.float32)[-1])
+      ct.append(xx.size)
+    got = border.targets_from_candidates(sel[keep], fcc[sel][keep], labs, first, xs, ys, ct, sx, sy, wx, wy)
+    norm = lambda d: {int(k): (int(v[0]), int(v[1])) for k, v in d.items()}
+    assert norm(got) == norm(want) and list(norm(got)) == list(norm(want))
+
+
 # ---- reference known-answer tests on the oracle (automated_test.py:48-102, 116-199) ----
 def _cable(s):
   v, e = s["vertices"], s["edges"]
