@@ -50,6 +50,14 @@ def make_volume(n):
   return vol
 
 
+def workload_name(vol, size):
+  shape = vol.shape
+  extra = "one soma + one glia tree, " if size >= 512 else ""
+  return (f"synthetic-{size}: {shape[0]}x{shape[1]}x{shape[2]} uint32, {int(len(np.unique(vol)) - 1)} labels, {extra}"
+          "anisotropy 16x16x40, DEFAULT_TEASAR_PARAMS, fix_borders (BASELINE.json configs[2] shape; the reference's "
+          "connectomics.npy.ckl.gz cannot be decoded in this image)")
+
+
 class ClockSampler:
   """nvidia-smi clocks / throttle reasons sampled during the timed region."""
   def __init__(self, index=0):
@@ -127,7 +135,7 @@ def run_reference(args):
     "impl": "reference", "metric": "voxels/sec skeletonized", "value": v, "unit": "voxels/s", "n_gpus": args.gpus,
     "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-    "config": {"workload": f"synthetic-{args.size} connectomics-shaped volume, anisotropy 16x16x40, DEFAULT_TEASAR_PARAMS",
+    "config": {"workload": workload_name(vol, args.size),
                "sample": f"z-slab [{z0}:{z1}) of the volume ({sample.shape[0]}x{sample.shape[1]}x{sample.shape[2]})"},
     "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port",
                      "sample": f"z-slab [{z0}:{z1}) of the same volume, fork pool over labels"},
@@ -260,8 +268,7 @@ def run_b200(args):
       "metric": "voxels/sec skeletonized", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
       "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
       "dtype": "f32", "data": "synthetic",
-      "config": {"workload": f"synthetic-{args.size}: {shape[0]}x{shape[1]}x{shape[2]} uint32, {int(len(np.unique(vol)) - 1)} labels, "
-                             "one soma + one glia tree, anisotropy 16x16x40, DEFAULT_TEASAR_PARAMS, fix_borders",
+      "config": {"workload": workload_name(vol, args.size),
                  "l2": "inputs and work fields (>3 GB) exceed the 126 MB L2", "skeletons": len(sk) if sk else 0,
                  "parallelism": f"labels sharded over {world} rank(s)"},
       "e2e": {"value": V / (mse / 1e3), "unit": "voxels/s", "h2d_bytes_per_step": int(flat.nbytes),

@@ -241,8 +241,8 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
       n_mid = S.n_keep;
       n_far = S.n_next;
       { uint32_t* t = far; far = far2; far2 = t; }
-      if (n_mid < 64 * kWarps) delta_mid = __fmul_rn(delta_mid, 2.0f);          // aim at ~0.5-2 k candidates
-      else if (n_mid > 256 * kWarps) delta_mid = __fmul_rn(delta_mid, 0.5f);
+      if (n_mid < 256) delta_mid = __fmul_rn(delta_mid, 2.0f);                  // aim at 256..1024 candidates
+      else if (n_mid > 1024) delta_mid = __fmul_rn(delta_mid, 0.5f);
       __syncthreads();
       if (threadIdx.x == 0) { S.n_keep = 0; S.n_next = 0; }
       __syncthreads();
@@ -250,7 +250,15 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
     }
     // ---- (a) smallest tentative distance in the mid band ----
     uint32_t mn = 0xffffffffu;
-    for (uint32_t i = threadIdx.x; i < n_mid; i += kThreads) mn = min(mn, __float_as_uint(__ldcg(&A.dist[mid[i]])));
+    for (uint32_t i0 = threadIdx.x; i0 < n_mid; i0 += 4 * kThreads) {
+      uint32_t id[4], dv[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const uint32_t i = i0 + q * kThreads; id[q] = (i < n_mid) ? mid[i] : 0xffffffffu; }
+#pragma unroll
+      for (int q = 0; q < 4; q++) dv[q] = (id[q] != 0xffffffffu) ? __float_as_uint(__ldcg(&A.dist[id[q]])) : 0xffffffffu;
+#pragma unroll
+      for (int q = 0; q < 4; q++) mn = min(mn, dv[q]);
+    }
     mn = block_min_u32(mn, S.red32);
     const uint32_t bound = (uint32_t)(S.best >> 32);
     uint32_t thr = __float_as_uint(__fadd_rn(__uint_as_float(mn), delta));
