@@ -236,7 +236,10 @@ def run_b200(args):
   if rank == 0 and sk_e:
     d2h = int(sum(s.vertices.nbytes + s.edges.nbytes + s.radii.nbytes for s in sk_e.values()))
 
-  # per-phase breakdown (one extra, untimed-for-the-metric step with synchronising laps)
+  # per-phase breakdowns (extra steps with synchronising laps, not part of the metric)
+  tme = {}
+  skeletonize(host_view, anisotropy=ANISOTROPY, progress=False, in_place=True, label_subset=subset, timings=tme)
+  e2e_phases = {k: round(1e3 * v, 3) for k, v in tme.items() if isinstance(v, float)}
   tm = {}
   skeletonize(shape, device_labels=d_labels, anisotropy=ANISOTROPY, progress=False, label_subset=subset, timings=tm)
   phases = {k: round(1e3 * v, 3) for k, v in tm.items() if isinstance(v, float)}
@@ -274,6 +277,7 @@ def run_b200(args):
       "e2e": {"value": V / (mse / 1e3), "unit": "voxels/s", "h2d_bytes_per_step": int(flat.nbytes),
               "d2h_bytes_per_step": d2h, "ms_per_step": mse},
       "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "phases_ms": phases,
+      "e2e_phases_ms": e2e_phases,
     }
     print(json.dumps(line), flush=True)
   if world > 1:
