@@ -229,3 +229,34 @@ def test_ccl_exact_and_deterministic(gpu, orc):
     assert n == n_ref
     got = cc.cpu().numpy().view(np.uint32).reshape(lab.shape, order="F")
     assert np.array_equal(got, ref)
+
+
+def test_full_size_512_against_oracle_digest(gpu):
+  """BASELINE.json's full size (512^3, 1946 labels, soma + glia): every skeleton of the CUDA path must hash
+  to the digest of the oracle's result (tests/golden/synth512_oracle_digest.json, produced by
+  scripts/full_parity.py), plus size-independent structure checks and run-to-run determinism."""
+  import hashlib, json, os
+  import kimimaro_b200
+  from bench import make_volume, ANISOTROPY
+  gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synth512_oracle_digest.json")))
+  vol = make_volume(512)
+  a = kimimaro_b200.skeletonize(vol, anisotropy=ANISOTROPY, progress=False)
+  b = kimimaro_b200.skeletonize(vol, anisotropy=ANISOTROPY, progress=False)
+  want = gold["sha256_16_of_vertices_then_edges"]
+  assert len(a) == gold["n_skeletons"] and sorted(str(k) for k in a) == sorted(want)
+  assert sum(s.vertices.shape[0] for s in a.values()) == gold["n_vertices"]
+  an = np.array(ANISOTROPY, np.float32)
+  bad = []
+  for k, s in a.items():
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(s.vertices).tobytes())
+    h.update(np.ascontiguousarray(s.edges).tobytes())
+    if h.hexdigest()[:16] != want[str(k)]:
+      bad.append(k)
+    assert np.array_equal(s.vertices, b[k].vertices) and np.array_equal(s.edges, b[k].edges)   # deterministic
+    vox = np.rint(s.vertices / an).astype(np.int64)
+    assert np.all(vol[vox[:, 0], vox[:, 1], vox[:, 2]] == k)                  # every vertex lies in its label
+    d = np.abs(vox[s.edges[:, 0]] - vox[s.edges[:, 1]]).max(axis=1)
+    assert np.all(d == 1)                                                     # edges join 26-neighbours
+    assert np.all(s.radii > 0)
+  assert bad == [], bad[:10]
