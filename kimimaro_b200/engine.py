@@ -233,12 +233,39 @@ def compute_M(dbf_max):
     return f(1 / (np.float32(dbf_max) ** 1.01))
 
 
+class Jobs:
+  """The per-label arguments of trace() (kimimaro/intake.py:494-504) for every label of one arena, as arrays.
+  root == -1 means "find a root" (trace.py:128-129); tb / ta map a job index to its list of manual targets
+  (linear voxel indices) and only hold the labels that have any."""
+  def __init__(self, segid, n_fg, first, root, dbf_max, tb=None, ta=None, soma_mode=None, soma_radius=None,
+               free_space=None):
+    self.segid = np.asarray(segid, dtype=np.int64)
+    n = self.segid.size
+    self.n_fg = np.asarray(n_fg, dtype=np.int64)
+    self.first = np.asarray(first, dtype=np.int64)
+    self.root = np.asarray(root, dtype=np.int64).copy()
+    self.dbf_max = np.asarray(dbf_max, dtype=np.float32)
+    self.tb = tb if tb is not None else {}
+    self.ta = ta if ta is not None else {}
+    self.soma_mode = np.zeros(n, dtype=bool) if soma_mode is None else np.asarray(soma_mode, dtype=bool)
+    self.soma_radius = np.zeros(n, dtype=np.float32) if soma_radius is None else np.asarray(soma_radius, dtype=np.float32)
+    self.free_space = np.zeros(n, dtype=np.float32) if free_space is None else np.asarray(free_space, dtype=np.float32)
+
+  def __len__(self):
+    return int(self.segid.size)
+
+
+def compute_M_array(dbf_max):
+  """compute_M for an array of labels: the same float32 power the scalar expression uses (trace.py:336)."""
+  with np.errstate(all="ignore"):
+    return (np.float32(1) / np.power(np.asarray(dbf_max, dtype=np.float32), 1.01)).astype(np.float32)
+
+
 def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=None):
   """
-  jobs: list of dicts {segid, n_fg, root (linear index or None), targets_before [linear...],
-        targets_after [...], dbf_max (np.float32), soma_mode, soma_radius, free_space}
-  n_rows: number of rows of the (label x bucket) tables minus one (= max cc id in this arena).
-  Returns (vox u32 [N] with 0xffffffff path terminators, radii f32 [N], seg_off int64 [n_jobs+1]).
+  jobs: a Jobs table.  n_rows: rows of the (label x bucket) tables minus one (= max cc id in this arena).
+  Returns (vox i32 device [N] with -1 path terminators, radii f32 device [N], seg_off int64 [n_jobs+1],
+  seg ids, stats).
   """
   sx, sy, sz = shape
   V = sx * sy * sz
@@ -255,25 +282,24 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
       timings[name] = timings.get(name, 0.0) + (now - tmark)
       tmark = now
 
-  n_fg_total = int(sum(j["n_fg"] for j in jobs))
+  n_fg_total = int(jobs.n_fg.sum())
   ws = Workspace(V, n_fg_total, dev)
 
   # ---- roots (trace.py:128-129, 291-308): one field sweep for every label that has no root yet ----
-  need = [j for j in jobs if j["root"] is None]
-  if need:
-    src = _dev(np.array([j["first"] for j in need], dtype=np.uint32).view(np.int32))
-    edf_multi(d_cc, shape, anisotropy, src, len(need), ws)
+  need = np.flatnonzero(jobs.root < 0)
+  if need.size:
+    src = _dev(jobs.first[need].astype(np.uint32).view(np.int32))
+    edf_multi(d_cc, shape, anisotropy, src, int(need.size), ws)
     _, idx = field_argmax(d_cc, ws.dist, shape, n_rows)
-    for j in need:
-      j["root"] = int(idx[j["segid"]])
+    jobs.root[need] = idx[jobs.segid[need]]
   lap("find_root")
 
   # ---- DAF from the roots, all labels at once (trace.py:139-145) ----
-  soma_jobs = [j for j in jobs if j.get("free_space")]
-  assert len(soma_jobs) <= 1 or n_jobs == len(soma_jobs), "free-space seeding is per arena"
-  src = _dev(np.array([j["root"] for j in jobs], dtype=np.uint32).view(np.int32))
-  if soma_jobs and n_jobs == 1:
-    edf_multi(d_cc, shape, anisotropy, src, 1, ws, free_space=(soma_jobs[0]["free_space"], jobs[0]["root"]))
+  has_free = jobs.free_space > 0
+  assert not has_free.any() or n_jobs == 1, "free-space seeding is per arena"
+  src = _dev(jobs.root.astype(np.uint32).view(np.int32))
+  if has_free.any():
+    edf_multi(d_cc, shape, anisotropy, src, 1, ws, free_space=(float(jobs.free_space[0]), int(jobs.root[0])))
   else:
     edf_multi(d_cc, shape, anisotropy, src, n_jobs, ws)
   maxdaf, target_idx = field_argmax(d_cc, ws.dist, shape, n_rows)
@@ -283,13 +309,11 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
   M = np.zeros(n_rows + 1, dtype=np.float32)
   inv = np.zeros(n_rows + 1, dtype=np.float32)
   active = np.zeros(n_rows + 1, dtype=np.uint8)
-  for j in jobs:
-    s = j["segid"]
-    M[s] = compute_M(j["dbf_max"])
-    md = np.float32(maxdaf[s])
-    with np.errstate(all="ignore"):
-      inv[s] = (1 / md) if md != 0 else np.float32(0)
-    active[s] = 1
+  M[jobs.segid] = compute_M_array(jobs.dbf_max)
+  md = maxdaf[jobs.segid].astype(np.float32)
+  with np.errstate(all="ignore"):
+    inv[jobs.segid] = np.where(md != 0, np.float32(1) / md, np.float32(0)).astype(np.float32)   # trace.py:352-354
+  active[jobs.segid] = 1
   d_M, d_inv, d_active = _dev(M), _dev(inv), _dev(active)
   ntab = (n_rows + 1) * NBUCKETS
   hist = torch.empty(ntab + 1, dtype=torch.int32, device=dev)
@@ -306,25 +330,43 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
   lap("pdrf")
 
   # ---- the path loop for every label (trace.py:196-267) ----
+  order = np.argsort(-jobs.n_fg, kind="stable")                       # largest labels first
   desc = np.zeros(n_jobs, dtype=DESC_DTYPE)
-  targets = []
-  order = sorted(range(n_jobs), key=lambda i: -jobs[i]["n_fg"])      # largest labels first
-  cols = {k: [] for k in ("segid", "root", "n_fg", "tb_off", "tb_n", "ta_off", "ta_n", "soma_mode", "soma_radius")}
-  for i in order:
-    j = jobs[i]
-    tb = j["targets_before"]
-    ta = j["targets_after"]
-    if not j["soma_mode"] and len(tb) == 0:
-      tb = [int(target_idx[j["segid"]])]                              # trace.py:171-172
-    cols["segid"].append(j["segid"]); cols["root"].append(j["root"]); cols["n_fg"].append(j["n_fg"])
-    cols["tb_off"].append(len(targets)); cols["tb_n"].append(len(tb)); targets.extend(tb)
-    cols["ta_off"].append(len(targets)); cols["ta_n"].append(len(ta)); targets.extend(ta)
-    cols["soma_mode"].append(1 if j["soma_mode"] else 0)
-    cols["soma_radius"].append(j.get("soma_radius", 0.0))
-  for k, v in cols.items():
-    desc[k] = np.asarray(v)
+  desc["segid"] = jobs.segid[order]
+  desc["root"] = jobs.root[order]
+  desc["n_fg"] = jobs.n_fg[order]
+  desc["soma_mode"] = jobs.soma_mode[order]
+  desc["soma_radius"] = jobs.soma_radius[order]
+  # manual targets: labels without any get the DAF arg-max appended unless in soma mode (trace.py:171-172)
+  tb_n = np.zeros(n_jobs, dtype=np.int64)
+  ta_n = np.zeros(n_jobs, dtype=np.int64)
+  for i, lst in jobs.tb.items():
+    tb_n[i] = len(lst)
+  for i, lst in jobs.ta.items():
+    ta_n[i] = len(lst)
+  auto = (tb_n == 0) & ~jobs.soma_mode
+  tb_n_eff = tb_n + auto
+  cnt = (tb_n_eff + ta_n)[order]
+  starts = np.concatenate(([0], np.cumsum(cnt)))
+  targets = np.zeros(int(starts[-1]) + 1, dtype=np.int64)
+  desc["tb_off"] = starts[:-1]
+  desc["tb_n"] = tb_n_eff[order]
+  desc["ta_off"] = starts[:-1] + tb_n_eff[order]
+  desc["ta_n"] = ta_n[order]
+  slot_of = np.empty(n_jobs, dtype=np.int64)
+  slot_of[order] = np.arange(n_jobs)
+  auto_idx = np.flatnonzero(auto)
+  targets[starts[slot_of[auto_idx]]] = target_idx[jobs.segid[auto_idx]]
+  for i, lst in jobs.tb.items():
+    if len(lst):
+      o = starts[slot_of[i]]
+      targets[o:o + len(lst)] = lst
+  for i, lst in jobs.ta.items():
+    if len(lst):
+      o = starts[slot_of[i]] + tb_n_eff[i]
+      targets[o:o + len(lst)] = lst
   nfg = desc["n_fg"].astype(np.int64)
-  caps = 2 * nfg + 2 * (desc["tb_n"].astype(np.int64) + desc["ta_n"]) + 64
+  caps = 2 * nfg + 2 * cnt + 64
   desc["region_off"] = np.concatenate(([0], np.cumsum(nfg)[:-1]))
   desc["path_off"] = np.concatenate(([0], np.cumsum(caps)[:-1]))
   desc["path_cap"] = caps
@@ -335,8 +377,8 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
   assert path_off < 2 ** 32 and 6 * region < 2 ** 34
   scratch = torch.empty(6 * max(region, 1), dtype=torch.int32, device=dev)
   # soma labels: the one-off ball around the root (trace.py:160-168) is far too large for one CTA
-  for slot in range(n_jobs):
-    if desc[slot]["soma_mode"]:
+  for slot in np.flatnonzero(desc["soma_mode"]).tolist():
+    if True:
       n = int(desc[slot]["n_fg"])
       base = 6 * int(desc[slot]["region_off"])
       seeds = _dev(np.array([desc[slot]["root"]], dtype=np.uint32).view(np.int32))
@@ -349,7 +391,7 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
       desc[slot]["pre_invalid"] = int(ws.ctrl[6].item())
   lap("soma_ball")
   d_desc = _dev(desc.view(np.uint8))
-  d_targets = _dev(np.array(targets + [0], dtype=np.uint32).view(np.int32))
+  d_targets = _dev(targets.astype(np.uint32).view(np.int32))
   paths = torch.empty(max(path_off, 1), dtype=torch.int32, device=dev)
   out_len = torch.zeros(n_jobs, dtype=torch.int32, device=dev)
   out_np = torch.zeros(n_jobs, dtype=torch.int32, device=dev)

@@ -127,23 +127,24 @@ def _private_arena(d_cc3, d_dbf3, segid, bbox, anisotropy, params, root, targets
 
   tb = [local(t) for t in targets_before]
   ta = [local(t) for t in targets_after]
-  job = {"segid": 1, "n_fg": int(mask.sum().item()), "dbf_max": dbf_max, "soma_mode": soma_mode,
-         "targets_before": tb, "targets_after": ta, "root": None, "first": None}
+  n_fg = int(mask.sum().item())
+  rlin, first, soma_radius, free_space = -1, 0, 0.0, 0.0
   if soma_mode:
     if root is not None:
       tb.insert(0, local(root))                               # trace.py:124-125
     r = _find_soma_root(dbf, shape, dbf_max)
     rlin = int(r[0]) + shape[0] * (int(r[1]) + shape[1] * int(r[2]))
-    job["root"] = rlin
     # soma_radius = dbf_max * soma_invalidation_scale + soma_invalidation_const  (trace.py:127)
-    job["soma_radius"] = np.float32(dbf_max * params["soma_invalidation_scale"] + params["soma_invalidation_const"])
-    job["free_space"] = float(dbf[rlin].item())               # trace.py:134
+    soma_radius = np.float32(dbf_max * params["soma_invalidation_scale"] + params["soma_invalidation_const"])
+    free_space = float(dbf[rlin].item())                      # trace.py:134
   elif root is not None:
-    job["root"] = local(root)
+    rlin = local(root)
   else:
-    job["first"] = int(torch.nonzero(mask)[0].item())         # first_label (pyx:307-326)
+    first = int(torch.nonzero(mask)[0].item())                # first_label (pyx:307-326)
+  jobs = engine.Jobs([1], [n_fg], [first], [rlin], [dbf_max], tb={0: tb} if tb else {}, ta={0: ta} if ta else {},
+                     soma_mode=[soma_mode], soma_radius=[soma_radius], free_space=[free_space])
   cc1 = mask.to(torch.int32)
-  vox, rad, seg_off, seg_ids, stats = engine.trace_arena(cc1, dbf, shape, anisotropy, [job], params, 1, timings)
+  vox, rad, seg_off, seg_ids, stats = engine.trace_arena(cc1, dbf, shape, anisotropy, jobs, params, 1, timings)
   res = engine.assemble(vox, rad, seg_off, seg_ids, shape, anisotropy, offset=(x0, y0, z0))
   return res.get(1), stats
 
@@ -261,12 +262,15 @@ def skeletonize(
     border_targets = engine.compute_border_targets(d_cc, shape, anisotropy)
   t0 = lap("border_targets", t0)
 
-  # ---- per label arguments of trace() (intake.py:445-504) ----
-  jobs, private = [], []
-  for segid in cc_segids:
-    x0, y0, z0, x1, y1, z1 = (int(v) for v in h_bbox[segid])
-    if (x1 - x0 + 1) * (y1 - y0 + 1) * (z1 - z0 + 1) <= 1:
-      continue
+  # ---- per label arguments of trace() (intake.py:445-504), as one table ----
+  segs = np.asarray(cc_segids, dtype=np.int64)
+  if segs.size:
+    ext = (h_bbox[segs, 3:6].astype(np.int64) - h_bbox[segs, 0:3].astype(np.int64) + 1)
+    segs = segs[np.prod(ext, axis=1) > 1]                       # roi.volume() <= 1 is skipped (intake.py:455-456)
+  is_private = h_dbfmax[segs] > params["soma_detection_threshold"]   # trace.py:108: takes the fill / re-EDT branch
+  lin = lambda p: int(p[0]) + sx * (int(p[1]) + sy * int(p[2]))
+
+  def manual_targets(segid):
     tb, ta, root = [], [], None
     bt = border_targets.get(segid)
     if bt is not None and len(bt) > 0:
@@ -276,18 +280,33 @@ def skeletonize(
       tb.extend(extra_before[segid])
     if segid in extra_after:
       ta.extend(extra_after[segid])
-    if h_dbfmax[segid] > params["soma_detection_threshold"]:
-      private.append((segid, (x0, y0, z0, x1, y1, z1), root, tb, ta))
-      continue
-    lin = lambda p: int(p[0]) + sx * (int(p[1]) + sy * int(p[2]))
-    jobs.append({"segid": segid, "n_fg": int(h_count[segid]), "dbf_max": np.float32(h_dbfmax[segid]),
-                 "soma_mode": False, "root": None if root is None else lin(root), "first": int(h_first[segid]),
-                 "targets_before": [lin(p) for p in tb], "targets_after": [lin(p) for p in ta]})
+    return tb, ta, root
+
+  private = []
+  for segid in segs[is_private].tolist():
+    tb, ta, root = manual_targets(segid)
+    private.append((segid, tuple(int(v) for v in h_bbox[segid]), root, tb, ta))
+  main = segs[~is_private]
+  roots = np.full(main.size, -1, dtype=np.int64)
+  tb_map, ta_map = {}, {}
+  has_targets = set(border_targets.keys()) | set(extra_before.keys()) | set(extra_after.keys())
+  if has_targets:
+    for i, segid in enumerate(main.tolist()):
+      if segid not in has_targets:
+        continue
+      tb, ta, root = manual_targets(segid)
+      if root is not None:
+        roots[i] = lin(root)
+      if tb:
+        tb_map[i] = [lin(p) for p in tb]
+      if ta:
+        ta_map[i] = [lin(p) for p in ta]
+  jobs = engine.Jobs(main, h_count[main], h_first[main], roots, h_dbfmax[main], tb=tb_map, ta=ta_map)
 
   results = {}            # original label -> (vertices, edges, radii), all its ordinary components merged
   private_results = []    # (original label, arrays) of labels traced in a private arena
   stats_all = []
-  if jobs:
+  if len(jobs):
     vox, rad, seg_off, seg_ids, stats = engine.trace_arena(d_cc, d_dbf, shape, an, jobs, params, n_cc, tm)
     t0 = time.perf_counter()
     results.update(engine.assemble(vox, rad, seg_off, seg_ids, shape, anisotropy, group_ids=h_orig[seg_ids]))
