@@ -256,9 +256,11 @@ class Jobs:
 
 
 def compute_M_array(dbf_max):
-  """compute_M for an array of labels: the same float32 power the scalar expression uses (trace.py:336)."""
+  """compute_M for every label.  Deliberately a loop over numpy SCALARS: the reference evaluates
+  `f(1 / (dbf_max ** 1.01))` on a np.float32 scalar (trace.py:336), and numpy's vectorised float32 power
+  (SIMD) rounds differently from the scalar path in ~17 % of the cases -- one ulp of M is enough to move a path."""
   with np.errstate(all="ignore"):
-    return (np.float32(1) / np.power(np.asarray(dbf_max, dtype=np.float32), 1.01)).astype(np.float32)
+    return np.array([np.float32(1 / (d ** 1.01)) for d in np.asarray(dbf_max, dtype=np.float32)], dtype=np.float32)
 
 
 def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=None):
