@@ -36,6 +36,9 @@ int b2t_version(void);                 /* e.g. 100 = 0.1.0 */
 const char* b2t_last_error(void);      /* thread-local message of the last failure */
 int b2t_device_check(void);            /* B2T_OK iff current device is compute capability 10.x */
 unsigned long long b2t_launch_count(int reset); /* kernels launched by this library so far */
+/* cap resident blocks per SM of the cooperative sweeps / of the path-loop kernel (0 = no cap) so that two
+ * arenas can be traced concurrently on two streams */
+int b2t_set_launch_limits(int coop_blocks_per_sm, int trace_blocks_per_sm);
 
 /* K1  anisotropic multi-label Euclidean distance transform ------------------------------------
  * replaces  edt.edt(labels, anisotropy, black_border)            kimimaro/intake.py:174-185

@@ -16,6 +16,18 @@ void b2t_set_error(const char* fmt, ...) {
 static unsigned long long g_launches = 0;
 void b2t_count_launches(int n) { g_launches += (unsigned long long)n; }
 
+static int g_coop_limit = 0, g_trace_limit = 0;
+int b2t_coop_limit() { return g_coop_limit; }
+int b2t_trace_limit() { return g_trace_limit; }
+
+// Cap the resident blocks per SM of the cooperative sweeps / of the path-loop kernel (0 = no cap), so that
+// a private-arena pipeline on a second stream can run next to the path loop of the main arena.
+B2T_EXPORT int b2t_set_launch_limits(int coop_blocks_per_sm, int trace_blocks_per_sm) {
+  g_coop_limit = coop_blocks_per_sm < 0 ? 0 : coop_blocks_per_sm;
+  g_trace_limit = trace_blocks_per_sm < 0 ? 0 : trace_blocks_per_sm;
+  return B2T_OK;
+}
+
 B2T_EXPORT int b2t_version(void) { return 100; }
 
 // number of kernels this library has launched since load (or since the last reset)

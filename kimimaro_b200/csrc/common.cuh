@@ -10,6 +10,8 @@
 
 void b2t_set_error(const char* fmt, ...);
 void b2t_count_launches(int n);  // bookkeeping for b2t_launch_count()
+int b2t_coop_limit();    // max blocks per SM for cooperative kernels (0 = whatever fits), see b2t_set_launch_limits
+int b2t_trace_limit();   // max blocks per SM for the path-loop kernel (0 = whatever fits)
 
 #define B2T_CUDA_TRY(expr)                                                                  \
   do {                                                                                      \

@@ -343,6 +343,7 @@ int coop_grid(const void* kernel, int threads, size_t smem, int* blocks_out) {
   B2T_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   B2T_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
   if (per_sm < 1) { b2t_set_error("cooperative kernel does not fit on an SM"); return B2T_ERR_CUDA; }
+  if (b2t_coop_limit() > 0 && per_sm > b2t_coop_limit()) per_sm = b2t_coop_limit();
   *blocks_out = sms * per_sm;
   return B2T_OK;
 }

@@ -650,7 +650,9 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
   B2T_CUDA_TRY(cudaGetDevice(&dev));
   B2T_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   B2T_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel, kThreads, 0));
-  int blocks = sms * (per_sm > 0 ? per_sm : 1);
+  if (per_sm < 1) per_sm = 1;
+  if (b2t_trace_limit() > 0 && per_sm > b2t_trace_limit()) per_sm = b2t_trace_limit();
+  int blocks = sms * per_sm;
   if (blocks > n_desc) blocks = n_desc;
   trace_kernel<<<blocks, kThreads, 0, st>>>(A, reinterpret_cast<const LabelDesc*>(d_desc), P, prm);
   B2T_CUDA_TRY(cudaGetLastError());

@@ -40,6 +40,7 @@ _lib.declare("b2t_ccl_relabel", [c_vp, c_vp, c_u64, c_vp])
 _lib.declare("b2t_invalidate_ball", [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_u32, c_f32, c_f32,
                                      c_vp, c_vp, c_u64, c_vp, c_vp])
 _lib.declare("b2t_segment_seqsum", [c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp])
+_lib.declare("b2t_set_launch_limits", [c_int, c_int])
 _lib.declare("b2t_gather_paths", [c_vp, c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp])
 
 NBUCKETS = 256
@@ -263,11 +264,10 @@ def compute_M_array(dbf_max):
     return np.array([np.float32(1 / (d ** 1.01)) for d in np.asarray(dbf_max, dtype=np.float32)], dtype=np.float32)
 
 
-def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=None):
+def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=None):
   """
-  jobs: a Jobs table.  n_rows: rows of the (label x bucket) tables minus one (= max cc id in this arena).
-  Returns (vox i32 device [N] with -1 path terminators, radii f32 device [N], seg_off int64 [n_jobs+1],
-  seg ids, stats).
+  Everything up to and including the (asynchronous) launch of the path-loop kernel; returns the state that
+  trace_arena_finish() needs.  jobs: a Jobs table.  n_rows: rows of the (label x bucket) tables minus one (= max cc id in this arena).
   """
   sx, sy, sz = shape
   V = sx * sy * sz
@@ -408,14 +408,32 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
                           c_int(NBUCKETS), _p(keys), _p(hist), _p(cursor), _p(scratch), _p(paths), _p(d_targets),
                           _p(out_len), _p(out_np), _p(out_status), _p(out_stats), _p(counter), stream_ptr()),
         "b2t_trace_batch")
-  h_len = out_len.cpu().numpy().astype(np.int64)
-  h_status = out_status.cpu().numpy()
+  keep = (ws, pdrf, claim, keys, hist, cursor, scratch, d_desc, d_targets, counter)   # alive until the kernel is done
+  return dict(desc=desc, paths=paths, out_len=out_len, out_np=out_np, out_status=out_status, out_stats=out_stats,
+              d_dbf=d_dbf, n_jobs=n_jobs, timings=timings, tmark=tmark, keep=keep)
+
+
+def trace_arena_finish(st):
+  """Wait for the path-loop kernel, compact the path pool, fetch radii (trace.py:186-187)."""
+  L = lib()
+  desc, n_jobs, timings = st["desc"], st["n_jobs"], st["timings"]
+  tmark = st["tmark"]
+  dev = st["paths"].device
+
+  def lap(name):
+    nonlocal tmark
+    if timings is not None:
+      torch.cuda.synchronize()
+      now = time.perf_counter()
+      timings[name] = timings.get(name, 0.0) + (now - tmark)
+      tmark = now
+
+  h_len = st["out_len"].cpu().numpy().astype(np.int64)
+  h_status = st["out_status"].cpu().numpy()
   lap("paths")
   if (h_status != 0).any():
     bad = int(np.flatnonzero(h_status != 0)[0])
     raise B2TError(f"trace kernel reported status {int(h_status[bad])} for cc label {int(desc[bad]['segid'])}")
-
-  # ---- compact the path pool and fetch radii (trace.py:186-187) ----
   seg_off = np.zeros(n_jobs + 1, dtype=np.int64)
   np.cumsum(h_len, out=seg_off[1:])
   total = int(seg_off[-1])
@@ -423,12 +441,19 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
   d_rad = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
   d_srcoff = _dev(desc["path_off"].astype(np.uint32).view(np.int32))
   d_dstoff = _dev(seg_off[:-1].astype(np.uint64).view(np.int64))
-  check(L.b2t_gather_paths(_p(paths), _p(d_srcoff), _p(out_len), _p(d_dstoff), c_u32(n_jobs), _p(d_dbf), _p(d_vox),
-                           _p(d_rad), stream_ptr()), "b2t_gather_paths")
+  check(L.b2t_gather_paths(_p(st["paths"]), _p(d_srcoff), _p(st["out_len"]), _p(d_dstoff), c_u32(n_jobs),
+                           _p(st["d_dbf"]), _p(d_vox), _p(d_rad), stream_ptr()), "b2t_gather_paths")
   lap("gather")
-  stats = {"stats": out_stats.cpu().numpy().reshape(-1, 4), "npaths": out_np.cpu().numpy(),
+  stats = {"stats": st["out_stats"].cpu().numpy().reshape(-1, 4), "npaths": st["out_np"].cpu().numpy(),
            "segids": desc["segid"].copy()}
+  st["keep"] = None
   return d_vox[:total], d_rad[:total], seg_off, desc["segid"].astype(np.int64), stats
+
+
+def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=None):
+  """Root, DAF, PDRF, path loop, path buffers for every label of one arena (kimimaro/trace.py:36-194).
+  Returns (vox i32 device [N] with -1 path terminators, radii f32 device [N], seg_off int64 [n_jobs+1], seg ids, stats)."""
+  return trace_arena_finish(trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings))
 
 
 # ------------------------------------------------------------------------------------------------

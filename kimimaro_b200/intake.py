@@ -306,26 +306,51 @@ def skeletonize(
   results = {}            # original label -> (vertices, edges, radii), all its ordinary components merged
   private_results = []    # (original label, arrays) of labels traced in a private arena
   stats_all = []
+  # The path loop of the main arena is latency-bound (one CTA per label), the private arenas (soma branch)
+  # are throughput kernels: run them side by side -- the main path kernel is launched asynchronously with
+  # a reduced footprint, the private arenas go to a second stream, then the main arena is collected.
+  overlap = len(jobs) > 0 and len(private) > 0 and tm is None
+  handle = None
   if len(jobs):
-    vox, rad, seg_off, seg_ids, stats = engine.trace_arena(d_cc, d_dbf, shape, an, jobs, params, n_cc, tm)
-    t0 = time.perf_counter()
-    results.update(engine.assemble(vox, rad, seg_off, seg_ids, shape, anisotropy, group_ids=h_orig[seg_ids]))
-    stats_all.append(stats)
-    t0 = lap("assemble", t0)
+    if overlap:
+      lib().b2t_set_launch_limits(0, 2)
+    handle = engine.trace_arena_start(d_cc, d_dbf, shape, an, jobs, params, n_cc, tm)
+    if not overlap:
+      vox, rad, seg_off, seg_ids, stats = engine.trace_arena_finish(handle)
+      handle = None
+      t0 = time.perf_counter()
+      results.update(engine.assemble(vox, rad, seg_off, seg_ids, shape, anisotropy, group_ids=h_orig[seg_ids]))
+      stats_all.append(stats)
+      t0 = lap("assemble", t0)
   if private:
     d_cc3 = d_cc.view(sz, sy, sx)
     d_dbf3 = d_dbf.view(sz, sy, sx)
-    for segid, bb, root, tb, ta in private:
-      t0 = time.perf_counter()
-      ptm = {} if tm is not None else None
-      res, stats = _private_arena(d_cc3, d_dbf3, segid, bb, an, params, root, tb, ta, ptm)
-      if res is not None:
-        private_results.append((h_orig[segid].item(), res))
-      stats_all.append(stats)
-      if tm is not None:
-        tm["soma"] = tm.get("soma", 0.0) + time.perf_counter() - t0
-        for k, v in ptm.items():
-          tm["soma_" + k] = tm.get("soma_" + k, 0.0) + v
+    main_stream = torch.cuda.current_stream()
+    side = torch.cuda.Stream() if overlap else main_stream
+    if overlap:
+      side.wait_stream(main_stream)
+      lib().b2t_set_launch_limits(2, 0)
+    try:
+      with torch.cuda.stream(side):
+        for segid, bb, root, tb, ta in private:
+          t0 = time.perf_counter()
+          ptm = {} if tm is not None else None
+          res, stats = _private_arena(d_cc3, d_dbf3, segid, bb, an, params, root, tb, ta, ptm)
+          if res is not None:
+            private_results.append((h_orig[segid].item(), res))
+          stats_all.append(stats)
+          if tm is not None:
+            tm["soma"] = tm.get("soma", 0.0) + time.perf_counter() - t0
+            for k, v in ptm.items():
+              tm["soma_" + k] = tm.get("soma_" + k, 0.0) + v
+    finally:
+      lib().b2t_set_launch_limits(0, 0)
+    if overlap:
+      main_stream.wait_stream(side)
+  if handle is not None:
+    vox, rad, seg_off, seg_ids, stats = engine.trace_arena_finish(handle)
+    results.update(engine.assemble(vox, rad, seg_off, seg_ids, shape, anisotropy, group_ids=h_orig[seg_ids]))
+    stats_all.insert(0, stats)
 
   # ---- Skeleton objects, merged per original id (intake.py:509-517, 587-593) ----
   t0 = time.perf_counter()
