@@ -12,6 +12,7 @@ Deviations from the reference, all explicit:
   * tie rules T1-T5 (oracle/oracle.c header) where the reference leaves ties to heap / sort internals.
 """
 import ctypes
+import os
 import time
 from collections import defaultdict
 
@@ -309,7 +310,9 @@ def skeletonize(
   # The path loop of the main arena is latency-bound (one CTA per label), the private arenas (soma branch)
   # are throughput kernels: run them side by side -- the main path kernel is launched asynchronously with
   # a reduced footprint, the private arenas go to a second stream, then the main arena is collected.
-  overlap = len(jobs) > 0 and len(private) > 0 and tm is None
+  # Measured on synthetic-512: with the cooperative sweeps capped at 2 blocks/SM the private arena slows down
+  # by more than the overlap saves (211 vs 163 ms per pass), so this stays off unless B2T_OVERLAP=1.
+  overlap = (os.environ.get("B2T_OVERLAP", "0") == "1") and len(jobs) > 0 and len(private) > 0 and tm is None
   handle = None
   if len(jobs):
     if overlap:
