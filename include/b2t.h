@@ -80,11 +80,13 @@ int b2t_label_stats(const uint32_t* d_cc, const float* d_dbf, int64_t sx, int64_
  * equal d_cc value.  d_dist [V] must hold +inf and d_stamp [V] zero on entry; d_queue holds
  * 2*queue_cap u32 (queue_cap >= foreground voxels of the participating labels); d_ctrl >= 8 u32.
  * free_space_radius > 0 (soma labels, trace.py:134) needs n_sources == 1 and the source's linear
- * index in h_free_space_source. */
+ * index in h_free_space_source.
+ * d_node_weights != NULL turns the sweep into dijkstra3d.parental_field(PDRF, root) (kimimaro/trace.py:155,
+ * fix_branching=False): the cost of entering voxel v is d_node_weights[v]; parents follow from the distances. */
 int b2t_edf_multi(const uint32_t* d_cc, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
                   const uint32_t* d_sources, uint32_t n_sources, float free_space_radius,
-                  uint32_t h_free_space_source, float* d_dist, uint32_t* d_stamp, uint32_t* d_queue,
-                  uint64_t queue_cap, uint32_t* d_ctrl, void* stream);
+                  uint32_t h_free_space_source, const float* d_node_weights, float* d_dist, uint32_t* d_stamp,
+                  uint32_t* d_queue, uint64_t queue_cap, uint32_t* d_ctrl, void* stream);
 
 /* return_max_location of the call above: d_best[l] = (dist_bits << 32) | (0xffffffff - index) of the
  * largest finite distance of label l, smallest index on ties; 0 if the label has none. */
@@ -112,6 +114,7 @@ int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist
  *           dijkstra3d.railroad(PDRF, target)               kimimaro/trace.py:240-242
  *           roll_invalidation_ball_inside_component         pyx:373-418 -> dijkstra_invalidation.hpp:239-332
  *           the soma cull and soma invalidation             kimimaro/trace.py:160-168, 246-251
+ *           dijkstra3d.path_from_parents (fix_branching == 0: d_dist must hold the parental field) trace.py:244
  * d_desc: n_desc records of 64 bytes (16 little-endian 32-bit fields):
  *   segid, root, n_fg, region_off, path_off, path_cap, tb_off, tb_n, ta_off, ta_n, max_paths (0xffffffff =
  *   None), soma_mode, soma_radius (float32), bucket_row, soma_done, pre_invalid
@@ -120,7 +123,7 @@ int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist
 int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,
                     uint32_t* d_stamp, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
                     const void* d_desc, int n_desc, float scale, float konst, float soma_scale,
-                    float soma_const, int nbuckets, const uint64_t* d_keys, const uint32_t* d_hist,
+                    float soma_const, int fix_branching, int nbuckets, const uint64_t* d_keys, const uint32_t* d_hist,
                     const uint32_t* d_cursor, uint32_t* d_scratch, uint32_t* d_paths,
                     const uint32_t* d_targets, uint32_t* d_out_len, uint32_t* d_out_npaths,
                     int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter, void* stream);

@@ -99,6 +99,7 @@ __global__ void bbox_init_kernel(int* bbox, uint32_t n) {
 // ------------------------------------------------------------------------------------------------
 struct EdfParams {
   const uint32_t* cc;
+  const float* node_w;   // NULL: edge lengths (euclidean_distance_field); else cost of ENTERING a voxel (parental_field)
   float* dist;
   uint32_t* stamp;
   uint32_t* queue;
@@ -118,7 +119,7 @@ __global__ void edf_seed_kernel(EdfParams p, const uint32_t* __restrict__ src, u
   }
 }
 
-template <bool HAS_FROZEN>
+template <bool HAS_FROZEN, bool NODE_W>
 __global__ void __launch_bounds__(256) edf_multi_kernel(EdfParams p) {
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256) edf_multi_kernel(EdfParams p) {
           bool frozen = false;
           if (HAS_FROZEN) frozen = __ldcg(&p.stamp[v]) == kFrozen;
           if (!frozen) {
-            const uint32_t nd = __float_as_uint(__fadd_rn(du, w));
+            const uint32_t nd = __float_as_uint(__fadd_rn(du, NODE_W ? __ldg(&p.node_w[v]) : w));
             const uint32_t old = atomicMin(reinterpret_cast<uint32_t*>(&p.dist[v]), nd);
             if (nd < old) {
               improved++;
@@ -396,19 +397,21 @@ B2T_EXPORT int b2t_label_stats(const uint32_t* d_cc, const float* d_dbf, int64_t
 // queue_cap >= number of foreground voxels of the participating labels; d_ctrl holds >= 8 u32.
 B2T_EXPORT int b2t_edf_multi(const uint32_t* d_cc, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
                              const uint32_t* d_sources, uint32_t n_sources, float free_space_radius,
-                             uint32_t h_free_space_source, float* d_dist, uint32_t* d_stamp, uint32_t* d_queue,
-                             uint64_t queue_cap, uint32_t* d_ctrl, void* stream) {
+                             uint32_t h_free_space_source, const float* d_node_weights, float* d_dist,
+                             uint32_t* d_stamp, uint32_t* d_queue, uint64_t queue_cap, uint32_t* d_ctrl, void* stream) {
   if (int rc = check_dims(sx, sy, sz)) return rc;
   B2T_REQUIRE(d_cc && d_dist && d_stamp && d_queue && d_ctrl, "b2t_edf_multi: null pointer");
   B2T_REQUIRE(queue_cap >= n_sources, "b2t_edf_multi: queue capacity below source count");
   cudaStream_t st = (cudaStream_t)stream;
   EdfParams p;
-  p.cc = d_cc; p.dist = d_dist; p.stamp = d_stamp; p.queue = d_queue; p.ctrl = d_ctrl; p.cap = queue_cap;
+  p.cc = d_cc; p.node_w = d_node_weights; p.dist = d_dist; p.stamp = d_stamp; p.queue = d_queue; p.ctrl = d_ctrl;
+  p.cap = queue_cap;
   p.d = Dims{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
   fill_weights(wx, wy, wz, p.w);
   const bool frozen = free_space_radius > 0.0f;
   if (frozen) {
     B2T_REQUIRE(n_sources == 1, "free_space_radius needs exactly one source");
+    B2T_REQUIRE(d_node_weights == nullptr, "free_space_radius and node weights are exclusive");
     const uint32_t zero = 0;
     edf_seed_kernel<<<1, 32, 0, st>>>(p, &zero, 0);  // clears ctrl
     edf_freespace_seed_kernel<<<256, 256, 0, st>>>(p, h_free_space_source, free_space_radius, wx, wy, wz);
@@ -417,7 +420,8 @@ B2T_EXPORT int b2t_edf_multi(const uint32_t* d_cc, int64_t sx, int64_t sy, int64
     edf_seed_kernel<<<(n_sources + 255) / 256, 256, 0, st>>>(p, d_sources, n_sources);
   }
   B2T_CUDA_TRY(cudaGetLastError());
-  const void* kern = frozen ? (const void*)edf_multi_kernel<true> : (const void*)edf_multi_kernel<false>;
+  const void* kern = frozen ? (const void*)edf_multi_kernel<true, false>
+                            : (d_node_weights ? (const void*)edf_multi_kernel<false, true> : (const void*)edf_multi_kernel<false, false>);
   int blocks = 0;
   if (int rc = coop_grid(kern, 256, 0, &blocks)) return rc;
   void* args[] = {&p};

@@ -66,6 +66,7 @@ struct Params {
   float soma_scale, soma_const;  // soma_invalidation_scale / _const
   int nbuckets;
   int n_desc;
+  int fix_branching;             // 0: paths come from the parental field already in A.dist (trace.py:154-158, 244)
 };
 
 struct Pools {
@@ -504,6 +505,58 @@ __device__ uint32_t invalidate(const Arena& A, const LabelDesc& L, const uint32_
   return total;
 }
 
+// ---- dijkstra3d.path_from_parents on the parental field held in A.dist (fix_branching=False) ---------
+// parents follow rule T3 (neighbour with the smallest (dist, direction)); the path is returned in
+// source -> target order like the library does: out[0] = root ... out[len-1] = target.
+__device__ uint32_t path_from_parents(const Arena& A, const LabelDesc& L, uint32_t target, uint32_t* out,
+                                      uint32_t out_cap, Shared& S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t seg = L.segid;
+  int dx = 0, dy = 0, dz = 0;
+  if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; }
+  const int64_t off = (int64_t)dx + (int64_t)dy * A.d.sx + (int64_t)dz * A.d.sxy;
+  if (warp == 0) {
+    uint32_t len = 0, loc = target, guard = 0;
+    while (guard <= L.n_fg) {
+      if (lane == 0 && len < out_cap) out[len] = loc;
+      len++;
+      if (loc == L.root) break;
+      const uint32_t dloc = __float_as_uint(__ldcg(&A.dist[loc]));
+      int x, y, z;
+      unravel(loc, A.d, x, y, z);
+      const int nx = x + dx, ny = y + dy, nz = z + dz;
+      unsigned long long key = ~0ull;
+      if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
+        const uint32_t v = (uint32_t)((int64_t)loc + off);
+        if (__ldg(&A.cc[v]) == seg) {
+          const uint32_t dv = __float_as_uint(__ldcg(&A.dist[v]));
+          if (dv < kInfBits) key = ((unsigned long long)dv << 32) | (unsigned long long)lane;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o);
+        key = t < key ? t : key;
+      }
+      if (key == ~0ull || dloc >= kInfBits) break;            // unreachable target: the walk stops here
+      const int dir = (int)(key & 31u);
+      loc = (uint32_t)((int64_t)loc + (int64_t)kDX[dir] + (int64_t)kDY[dir] * A.d.sx + (int64_t)kDZ[dir] * A.d.sxy);
+      guard++;
+    }
+    if (lane == 0) S.red32[0] = len;
+  }
+  __syncthreads();
+  const uint32_t len = S.red32[0];
+  const uint32_t n = len < out_cap ? len : out_cap;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n / 2; i += kThreads) {   // reverse: source first
+    const uint32_t a = out[i], b = out[n - 1 - i];
+    out[i] = b; out[n - 1 - i] = a;
+  }
+  __syncthreads();
+  return len;
+}
+
 // ---- the per-label conductor (trace.py:196-267) ----------------------------------------------------
 __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, const Params& prm, Shared& S,
                             uint32_t job) {
@@ -545,7 +598,8 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
     if (used + 2 > L.path_cap) { status = B2T_ERR_CAPACITY; break; }
     uint32_t* pout = out + used;
     const uint32_t cap = L.path_cap - used - 1;
-    uint32_t len = railroad(A, L, target, r0, r1, r2, r4, r5, r3, pout, cap, S);
+    uint32_t len = prm.fix_branching ? railroad(A, L, target, r0, r1, r2, r4, r5, r3, pout, cap, S)
+                                     : path_from_parents(A, L, target, pout, cap, S);
     if (len > cap) { status = B2T_ERR_CAPACITY; break; }
     if (L.soma_mode) {
       // keep path[:1] + points farther than soma_radius from the root; float64, uint32 wrap
@@ -579,7 +633,8 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
       valid -= min(valid, n);
       if (threadIdx.x == 0) S.invalidated += n;
     }
-    for (uint32_t i = threadIdx.x; i < len; i += kThreads) A.pdrf[pout[i]] = 0.0f;   // trace.py:261-263
+    if (prm.fix_branching)
+      for (uint32_t i = threadIdx.x; i < len; i += kThreads) A.pdrf[pout[i]] = 0.0f;   // trace.py:261-263
     if (threadIdx.x == 0) pout[len] = 0xffffffffu;
     used += len + 1;
     npaths++;
@@ -627,7 +682,8 @@ __global__ void __launch_bounds__(kThreads, 3) trace_kernel(Arena A, const Label
 B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,
                                uint32_t* d_stamp, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
                                const void* d_desc, int n_desc, float scale, float konst, float soma_scale,
-                               float soma_const, int nbuckets, const uint64_t* d_keys, const uint32_t* d_hist,
+                               float soma_const, int fix_branching, int nbuckets, const uint64_t* d_keys,
+                               const uint32_t* d_hist,
                                const uint32_t* d_cursor, uint32_t* d_scratch, uint32_t* d_paths,
                                const uint32_t* d_targets, uint32_t* d_out_len, uint32_t* d_out_npaths,
                                int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter, void* stream) {
@@ -644,7 +700,7 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
   P.keys = reinterpret_cast<const unsigned long long*>(d_keys); P.hist = d_hist; P.cursor = d_cursor;
   P.scratch = d_scratch; P.paths = d_paths; P.targets = d_targets; P.out_len = d_out_len; P.out_npaths = d_out_npaths;
   P.out_status = d_out_status; P.out_stats = d_out_stats; P.work_counter = d_work_counter;
-  Params prm{scale, konst, soma_scale, soma_const, nbuckets, n_desc};
+  Params prm{scale, konst, soma_scale, soma_const, nbuckets, n_desc, fix_branching ? 1 : 0};
   B2T_CUDA_TRY(cudaMemsetAsync(d_work_counter, 0, sizeof(uint32_t), st));
   int dev = 0, sms = 0, per_sm = 0;
   B2T_CUDA_TRY(cudaGetDevice(&dev));

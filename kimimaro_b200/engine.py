@@ -28,12 +28,12 @@ c_u64 = ctypes.c_uint64
 
 _lib.declare("b2t_label_stats", [c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp])
 _lib.declare("b2t_edf_multi", [c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_u32, c_f32, c_u32,
-                               c_vp, c_vp, c_vp, c_u64, c_vp, c_vp])
+                               c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, c_vp])
 _lib.declare("b2t_field_argmax", [c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp])
 _lib.declare("b2t_pdrf_and_buckets", [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp,
                                       c_vp, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp])
 _lib.declare("b2t_trace_batch", [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32,
-                                 c_vp, c_int, c_f32, c_f32, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                 c_vp, c_int, c_f32, c_f32, c_f32, c_f32, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp])
 _lib.declare("b2t_ccl26_roots", [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp])
 _lib.declare("b2t_ccl_relabel", [c_vp, c_vp, c_u64, c_vp])
@@ -114,15 +114,16 @@ class Workspace:
     self.ctrl = torch.zeros(16, dtype=torch.int32, device=dev)
 
 
-def edf_multi(d_cc, shape, anisotropy, d_sources, n_sources, ws, free_space=None):
-  """dijkstra3d.euclidean_distance_field for all participating labels at once -> ws.dist."""
+def edf_multi(d_cc, shape, anisotropy, d_sources, n_sources, ws, free_space=None, node_weights=None):
+  """dijkstra3d.euclidean_distance_field for all participating labels at once -> ws.dist.
+  node_weights (a [V] float tensor) turns it into dijkstra3d.parental_field(node_weights, source)."""
   sx, sy, sz = shape
   ws.dist.fill_(float("inf"))
   ws.stamp.zero_()
   fsr, fss = (0.0, 0) if free_space is None else (float(free_space[0]), int(free_space[1]))
   check(lib().b2t_edf_multi(_p(d_cc), c_i64(sx), c_i64(sy), c_i64(sz), c_f32(anisotropy[0]), c_f32(anisotropy[1]),
                             c_f32(anisotropy[2]), _p(d_sources), c_u32(n_sources), c_f32(fsr), c_u32(fss),
-                            _p(ws.dist), _p(ws.stamp), _p(ws.queue), c_u64(ws.queue.numel() // 2), _p(ws.ctrl),
+                            _p(node_weights), _p(ws.dist), _p(ws.stamp), _p(ws.queue), c_u64(ws.queue.numel() // 2), _p(ws.ctrl),
                             stream_ptr()), "b2t_edf_multi")
 
 
@@ -330,6 +331,12 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
                                _p(hist), _p(cursor), _p(keys), stream_ptr()), "b2t_pdrf_and_buckets")
   del flag
   lap("pdrf")
+  fix_branching = bool(params.get("fix_branching", True))
+  if not fix_branching:
+    # parents = dijkstra3d.parental_field(PDRF, root) (trace.py:154-155), every label in one sweep; the
+    # distances stay in ws.dist and the path kernel derives parents from them (rule T3)
+    edf_multi(d_cc, shape, anisotropy, src, n_jobs, ws, node_weights=pdrf)
+    lap("parental_field")
 
   # ---- the path loop for every label (trace.py:196-267) ----
   order = np.argsort(-jobs.n_fg, kind="stable")                       # largest labels first
@@ -405,7 +412,8 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
                           c_i64(sz), c_f32(anisotropy[0]), c_f32(anisotropy[1]), c_f32(anisotropy[2]), _p(d_desc),
                           c_int(n_jobs), c_f32(params["scale"]), c_f32(params["const"]),
                           c_f32(params["soma_invalidation_scale"]), c_f32(params["soma_invalidation_const"]),
-                          c_int(NBUCKETS), _p(keys), _p(hist), _p(cursor), _p(scratch), _p(paths), _p(d_targets),
+                          c_int(1 if fix_branching else 0), c_int(NBUCKETS), _p(keys), _p(hist), _p(cursor), _p(scratch),
+                          _p(paths), _p(d_targets),
                           _p(out_len), _p(out_np), _p(out_status), _p(out_stats), _p(counter), stream_ptr()),
         "b2t_trace_batch")
   keep = (ws, pdrf, claim, keys, hist, cursor, scratch, d_desc, d_targets, counter)   # alive until the kernel is done

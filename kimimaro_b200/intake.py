@@ -7,7 +7,7 @@ Deviations from the reference, all explicit:
   * parallel      one process drives one GPU and the device traces all labels concurrently, so the
                   argument is accepted and ignored here; multi-GPU runs shard labels across
                   processes (kimimaro_b200.distributed).
-  * fill_holes, fix_avocados, voxel_graph, fix_branching=False, CrackleArray input: not built yet
+  * fill_holes, fix_avocados, voxel_graph, CrackleArray input: not built yet
                    -> NotImplementedError, never a silent CPU path.
   * tie rules T1-T5 (oracle/oracle.c header) where the reference leaves ties to heap / sort internals.
 """
@@ -168,12 +168,13 @@ def skeletonize(
   device_labels (a flat Fortran-ordered CUDA tensor already holding the volume: skips the H2D copy;
   all_labels then carries the shape), edt_events (list receiving (start, end) CUDA events around K1).
   """
-  if fill_holes or fix_avocados or voxel_graph is not None or not fix_branching:
+  if fill_holes or fix_avocados or voxel_graph is not None:
     raise NotImplementedError(
-      "fill_holes / fix_avocados / voxel_graph / fix_branching=False are not built yet in kimimaro_b200 "
+      "fill_holes / fix_avocados / voxel_graph are not built yet in kimimaro_b200 "
       "(SURVEY.md 8f row N4); there is no CPU fallback")
   _lib.require_device()
   params = _merge_params(teasar_params)
+  params["fix_branching"] = bool(fix_branching)
   anisotropy = np.array(anisotropy, dtype=np.float32)
   an = tuple(float(a) for a in anisotropy)
   t_all = time.perf_counter()

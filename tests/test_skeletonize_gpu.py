@@ -260,3 +260,22 @@ def test_full_size_512_against_oracle_digest(gpu):
     assert np.all(d == 1)                                                     # edges join 26-neighbours
     assert np.all(s.radii > 0)
   assert bad == [], bad[:10]
+
+
+@pytest.mark.parametrize("seed", [2, 11])
+def test_no_fix_branching(gpu, seed):
+  """fix_branching=False (trace.py:154-158, 244): one parental field per label, paths by pointer walk."""
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes((96, 96, 64), 8, seed=seed)
+  tp = {"scale": 1.0, "const": 30, "pdrf_scale": 100000, "pdrf_exponent": 4}
+  res, ref = _both(gpu, lab, anisotropy=(16, 16, 40), dust_threshold=100, teasar_params=tp, fix_branching=False)
+  assert len(ref) > 0
+  _compare(res, ref)
+
+
+def test_no_fix_branching_2d_slice(gpu):
+  # automated_test.py:562-563 runs fix_branching=False on a 2-D slice
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes((128, 128, 64), 14, seed=3)[:, :, 30]
+  res, ref = _both(gpu, lab, anisotropy=(16, 16, 40), dust_threshold=50, fix_branching=False)
+  _compare(res, ref)
