@@ -526,6 +526,61 @@ __global__ void ball_seed_kernel(BallParams p) {
   }
 }
 
+// single seed: no ownership to arbitrate, so a voxel is claimed the moment it is first reached (same result as
+// the round-synchronous claim with one candidate seed) -- one grid barrier per round, no finalise pass
+__global__ void __launch_bounds__(256) ball_flood_single_kernel(BallParams p) {
+  cg::grid_group grid = cg::this_grid();
+  const int lane = threadIdx.x & 31;
+  const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  int dx = 0, dy = 0, dz = 0;
+  if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; }
+  const int64_t off = (int64_t)dx + (int64_t)dy * p.d.sx + (int64_t)dz * p.d.sxy;
+  const uint32_t ltmask = (1u << lane) - 1u;
+  const uint32_t o = p.seeds[0];
+  const uint32_t seg = __ldg(&p.cc[o]);
+  const float r = __fadd_rn(__fmul_rn(p.scale, __ldg(&p.dbf[o])), p.konst);
+  int ox, oy, oz;
+  unravel(o, p.d, ox, oy, oz);
+  uint32_t round = 1;
+  for (;;) {
+    const uint32_t n = __ldcg(&p.ctrl[round % 3]);
+    if (n == 0) break;
+    const uint32_t* qv = p.fv + (uint64_t)(round & 1) * p.cap;
+    uint32_t* nv = p.fv + (uint64_t)((round + 1) & 1) * p.cap;
+    uint32_t* cnt_out = &p.ctrl[(round + 1) % 3];
+    for (uint32_t it = gwarp; it < n; it += nwarps) {
+      const uint32_t u = __ldcg(&qv[it]);
+      int x, y, z;
+      unravel(u, p.d, x, y, z);
+      const int nx = x + dx, ny = y + dy, nz = z + dz;
+      bool push = false;
+      uint32_t v = 0;
+      if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < p.d.sx && ny < p.d.sy && nz < p.d.sz) {
+        v = (uint32_t)((int64_t)u + off);
+        const uint32_t lv = __ldg(&p.cc[v]);
+        const unsigned long long cl = __ldcg(&p.claim[v]);
+        if (lv == seg && cl == ~0ull) {
+          const float a = __fmul_rn(p.wx, (float)(nx - ox)), b = __fmul_rn(p.wy, (float)(ny - oy)),
+                      c = __fmul_rn(p.wz, (float)(nz - oz));
+          const float dd = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));
+          if (dd < r) push = atomicCAS(&p.claim[v], ~0ull, 0ull) == ~0ull;
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, push);
+      if (m) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cnt_out, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (push) nv[base + __popc(m & ltmask)] = v;
+      }
+    }
+    grid.sync();
+    if (gwarp == 0 && lane == 0) { p.ctrl[round % 3] = 0; p.ctrl[6] += __ldcg(cnt_out); }
+    round++;
+  }
+}
+
 __global__ void __launch_bounds__(256) ball_flood_kernel(BallParams p) {
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
@@ -608,9 +663,10 @@ B2T_EXPORT int b2t_invalidate_ball(const uint32_t* d_cc, const float* d_dbf, uin
   p.wx = wx; p.wy = wy; p.wz = wz; p.scale = scale; p.konst = konst;
   ball_seed_kernel<<<(n_seeds + 255) / 256, 256, 0, st>>>(p);
   int blocks = 0;
-  if (int rc = coop_grid((const void*)ball_flood_kernel, 256, 0, &blocks)) return rc;
+  const void* kern = (n_seeds == 1) ? (const void*)ball_flood_single_kernel : (const void*)ball_flood_kernel;
+  if (int rc = coop_grid(kern, 256, 0, &blocks)) return rc;
   void* args[] = {&p};
-  B2T_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)ball_flood_kernel, dim3(blocks), dim3(256), args, 0, st));
+  B2T_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(256), args, 0, st));
   b2t_count_launches(2);
   return B2T_OK;
 }
