@@ -40,6 +40,10 @@ def make_volume(n):
   cache = f"/tmp/b2t_synth_{n}_{SEED:x}.npy"
   if os.path.exists(cache):
     return np.load(cache)
+  if n == 1024:
+    # BASELINE.json configs[4]: 1024^3 = 2x2x2 tiling of the 512^3 volume, label ids offset per tile
+    from kimimaro_b200.datasets import tiled
+    return tiled(make_volume(512), (2, 2, 2))
   if n >= 512:
     vol = synthetic_tubes((n, n, n), 2124 * (n // 512) ** 3, seed=SEED, anisotropy=ANISOTROPY, soma=True, glia=True)
   else:
@@ -120,7 +124,7 @@ def run_reference(args):
   oracle.build()
   vol = make_volume(args.size)
   z0, z1 = (SLAB if args.size >= 256 else (0, args.size))
-  sample = np.asfortranarray(vol[:, :, z0:z1])
+  sample = np.asfortranarray(vol[:512, :512, z0:z1])
   cores = os.cpu_count() or 1
   times = []
   for i in range(args.warmup + args.steps):
@@ -261,7 +265,7 @@ def run_b200(args):
       from oracle import teasar
       oracle.build()
       z0, z1 = (SLAB if args.size >= 256 else (0, args.size))
-      sample = np.asfortranarray(vol[:, :, z0:z1])
+      sample = np.asfortranarray(vol[:512, :512, z0:z1])
       t = time.perf_counter()
       teasar.skeletonize(sample, anisotropy=ANISOTROPY)
       cdt = time.perf_counter() - t
