@@ -245,7 +245,8 @@ def _criteria(px, py, centx, centy, sx, sy, wx, wy):
 
 
 def plane_mapping(plane, cc_plane):
-  """get_mapping (pyx:490-525) on a face: {plane component id: volume cc label}."""
+  """get_mapping (pyx:490-525) on a face: {plane component id: volume cc label}.  (All-host variant, kept for
+  the CPU tests; the engine builds this table on the device.)"""
   fcc = np.asarray(cc_plane).reshape(-1)
   fpl = np.asarray(plane).reshape(-1)
   _, first = np.unique(fcc, return_index=True)

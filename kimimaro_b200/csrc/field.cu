@@ -248,7 +248,6 @@ struct PdrfParams {
   const float* daf;          // distance-from-root field (inf where unreachable)
   float* pdrf;
   unsigned long long* claim; // set to ~0 (valid) on participating voxels
-  uint8_t* flag;             // cleared
   const float* M;            // per label: f32(1 / dbf_max^1.01)     (trace.py:336)
   const float* inv_maxdaf;   // per label: 1 / DAF[target], 0 when max_daf == 0 (trace.py:352-354)
   const uint8_t* active;     // per label: 1 = take part
@@ -287,7 +286,6 @@ __global__ void pdrf_kernel(PdrfParams p) {
     if (inv != 0.0f) P = __fadd_rn(P, __fmul_rn(daf, inv));
     p.pdrf[i] = P;
     p.claim[i] = ~0ull;
-    p.flag[i] = 0;
     atomicAdd(&p.hist[(size_t)l * p.nbuckets + daf_bucket(daf, inv, p.nbuckets)], 1u);
   }
 }
@@ -451,7 +449,7 @@ B2T_EXPORT int b2t_field_argmax(const uint32_t* d_cc, const float* d_dist, int64
 //   advances the exclusive offsets), d_hist holds the counts, and d_dist is +inf on every
 //   participating voxel, ready for the path loop.
 B2T_EXPORT int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist, float* d_pdrf,
-                                    uint64_t* d_claim, uint8_t* d_flag, int64_t sx, int64_t sy, int64_t sz,
+                                    uint64_t* d_claim, int64_t sx, int64_t sy, int64_t sz,
                                     uint32_t n_labels, const float* d_M, const float* d_inv_maxdaf,
                                     const uint8_t* d_active, float pdrf_scale, float pdrf_exponent, int nbuckets,
                                     uint32_t* d_hist, uint32_t* d_cursor, uint64_t* d_keys, void* stream) {
@@ -463,7 +461,7 @@ B2T_EXPORT int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, fl
   B2T_CUDA_TRY(cudaMemsetAsync(d_hist, 0, (ntab + 1) * sizeof(uint32_t), st));
   PdrfParams p;
   p.cc = d_cc; p.dbf = d_dbf; p.daf = d_dist; p.pdrf = d_pdrf;
-  p.claim = reinterpret_cast<unsigned long long*>(d_claim); p.flag = d_flag;
+  p.claim = reinterpret_cast<unsigned long long*>(d_claim);
   p.M = d_M; p.inv_maxdaf = d_inv_maxdaf; p.active = d_active; p.hist = d_hist;
   p.n_labels = n_labels; p.nbuckets = nbuckets; p.pdrf_scale = pdrf_scale; p.exponent = pdrf_exponent;
   p.n_squarings = -1;

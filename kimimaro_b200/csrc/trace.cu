@@ -137,7 +137,7 @@ struct Shared {
   uint32_t n_keep, n_proc, n_next, n_touched;
   uint32_t job;
   int bucket;
-  uint32_t relax, rounds, invalidated, scans;
+  uint32_t relax, rounds, invalidated;
 };
 
 // ---- CachedTargetFinder.find_target ------------------------------------------------------------------
@@ -155,7 +155,6 @@ __device__ uint32_t find_target(const Arena& A, const LabelDesc& L, const Pools&
       if (__ldcg(&A.claim[v]) == kValid && key + 1 > best) best = key + 1;  // +1 so that key 0 is distinguishable from "none"
     }
     best = block_max_u64(best, S.red64);
-    if (threadIdx.x == 0) S.scans++;
     if (best != 0) return (uint32_t)(best - 1);
     __syncthreads();
     if (threadIdx.x == 0) S.bucket = b - 1;
@@ -572,7 +571,7 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
   if (threadIdx.x == 0) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     S.bucket = prm.nbuckets - 1;
-    S.relax = 0; S.rounds = 0; S.invalidated = 0; S.scans = 0;
+    S.relax = 0; S.rounds = 0; S.invalidated = 0;
     A.pdrf[L.root] = 0.0f;      // parents[root] = 0: the first rail (trace.py:220)
   }
   __syncthreads();

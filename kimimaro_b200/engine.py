@@ -20,8 +20,7 @@ import torch
 
 from . import _lib, border
 from ._lib import B2TError, c_f32, c_i64, c_int, c_vp, check, lib, stream_ptr
-from .ops import edt, to_device_f
-from .skeleton import Skeleton
+from .ops import edt
 
 c_u32 = ctypes.c_uint32
 c_u64 = ctypes.c_uint64
@@ -30,7 +29,7 @@ _lib.declare("b2t_label_stats", [c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c
 _lib.declare("b2t_edf_multi", [c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_u32, c_f32, c_u32,
                                c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, c_vp])
 _lib.declare("b2t_field_argmax", [c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp])
-_lib.declare("b2t_pdrf_and_buckets", [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp,
+_lib.declare("b2t_pdrf_and_buckets", [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp,
                                       c_vp, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp])
 _lib.declare("b2t_trace_batch", [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32,
                                  c_vp, c_int, c_f32, c_f32, c_f32, c_f32, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
@@ -56,7 +55,7 @@ def _p(t):
   return c_vp(t.data_ptr()) if t is not None else c_vp(0)
 
 
-def _dev(a, dtype=None):
+def _dev(a):
   t = torch.from_numpy(np.ascontiguousarray(a))
   return t.cuda(non_blocking=True)
 
@@ -228,13 +227,6 @@ DESC_DTYPE = np.dtype([
 assert DESC_DTYPE.itemsize == 64
 
 
-def compute_M(dbf_max):
-  """M = f32(1 / dbf_max ** 1.01) with the reference's numpy expression (trace.py:335-336)."""
-  f = lambda x: np.float32(x)
-  with np.errstate(all="ignore"):
-    return f(1 / (np.float32(dbf_max) ** 1.01))
-
-
 class Jobs:
   """The per-label arguments of trace() (kimimaro/intake.py:494-504) for every label of one arena, as arrays.
   root == -1 means "find a root" (trace.py:128-129); tb / ta map a job index to its list of manual targets
@@ -324,12 +316,10 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   keys = torch.empty(max(n_fg_total, 1), dtype=torch.int64, device=dev)
   pdrf = torch.empty(V, dtype=torch.float32, device=dev)
   claim = torch.empty(V, dtype=torch.int64, device=dev)
-  flag = torch.empty(V, dtype=torch.uint8, device=dev)   # vestigial init target of the fused kernel
-  check(L.b2t_pdrf_and_buckets(_p(d_cc), _p(d_dbf), _p(ws.dist), _p(pdrf), _p(claim), _p(flag), c_i64(sx), c_i64(sy),
+  check(L.b2t_pdrf_and_buckets(_p(d_cc), _p(d_dbf), _p(ws.dist), _p(pdrf), _p(claim), c_i64(sx), c_i64(sy),
                                c_i64(sz), c_u32(n_rows), _p(d_M), _p(d_inv), _p(d_active),
                                c_f32(params["pdrf_scale"]), c_f32(params["pdrf_exponent"]), c_int(NBUCKETS),
                                _p(hist), _p(cursor), _p(keys), stream_ptr()), "b2t_pdrf_and_buckets")
-  del flag
   lap("pdrf")
   fix_branching = bool(params.get("fix_branching", True))
   if not fix_branching:
@@ -387,7 +377,7 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   scratch = torch.empty(6 * max(region, 1), dtype=torch.int32, device=dev)
   # soma labels: the one-off ball around the root (trace.py:160-168) is far too large for one CTA
   for slot in np.flatnonzero(desc["soma_mode"]).tolist():
-    if True:
+    if desc[slot]["soma_mode"]:
       n = int(desc[slot]["n_fg"])
       base = 6 * int(desc[slot]["region_off"])
       seeds = _dev(np.array([desc[slot]["root"]], dtype=np.uint32).view(np.int32))

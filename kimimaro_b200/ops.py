@@ -9,11 +9,7 @@ loc = x + sx*(y + sy*z) (kimimaro/intake.py:320-322).
 import numpy as np
 import torch
 
-from . import _lib
 from ._lib import c_f32, c_i64, c_int, c_vp, check, lib, stream_ptr
-
-_TORCH_LABEL_DTYPES = {1: torch.uint8, 2: torch.uint16, 4: torch.uint32, 8: torch.uint64}
-
 
 def _ptr(t):
   return c_vp(t.data_ptr())
