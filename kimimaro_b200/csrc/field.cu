@@ -120,7 +120,7 @@ __global__ void edf_seed_kernel(EdfParams p, const uint32_t* __restrict__ src, u
 }
 
 template <bool HAS_FROZEN, bool NODE_W>
-__global__ void __launch_bounds__(256) edf_multi_kernel(EdfParams p) {
+__global__ void __launch_bounds__(256, 8) edf_multi_kernel(EdfParams p) {
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
   const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -526,7 +526,7 @@ __global__ void ball_seed_kernel(BallParams p) {
 
 // single seed: no ownership to arbitrate, so a voxel is claimed the moment it is first reached (same result as
 // the round-synchronous claim with one candidate seed) -- one grid barrier per round, no finalise pass
-__global__ void __launch_bounds__(256) ball_flood_single_kernel(BallParams p) {
+__global__ void __launch_bounds__(256, 8) ball_flood_single_kernel(BallParams p) {
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
   const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
