@@ -120,7 +120,7 @@ __global__ void edf_seed_kernel(EdfParams p, const uint32_t* __restrict__ src, u
 }
 
 template <bool HAS_FROZEN, bool NODE_W>
-__global__ void __launch_bounds__(256, 8) edf_multi_kernel(EdfParams p) {
+__global__ void __launch_bounds__(1024, 2) edf_multi_kernel(EdfParams p) {
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
   const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -421,9 +421,9 @@ B2T_EXPORT int b2t_edf_multi(const uint32_t* d_cc, int64_t sx, int64_t sy, int64
   const void* kern = frozen ? (const void*)edf_multi_kernel<true, false>
                             : (d_node_weights ? (const void*)edf_multi_kernel<false, true> : (const void*)edf_multi_kernel<false, false>);
   int blocks = 0;
-  if (int rc = coop_grid(kern, 256, 0, &blocks)) return rc;
+  if (int rc = coop_grid(kern, 1024, 0, &blocks)) return rc;   // few large blocks: the grid barrier costs per block
   void* args[] = {&p};
-  B2T_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(256), args, 0, st));
+  B2T_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(1024), args, 0, st));
   b2t_count_launches(frozen ? 3 : 2);
   return B2T_OK;
 }
@@ -526,7 +526,7 @@ __global__ void ball_seed_kernel(BallParams p) {
 
 // single seed: no ownership to arbitrate, so a voxel is claimed the moment it is first reached (same result as
 // the round-synchronous claim with one candidate seed) -- one grid barrier per round, no finalise pass
-__global__ void __launch_bounds__(256, 8) ball_flood_single_kernel(BallParams p) {
+__global__ void __launch_bounds__(1024, 2) ball_flood_single_kernel(BallParams p) {
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
   const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(256, 8) ball_flood_single_kernel(BallParams p)
   }
 }
 
-__global__ void __launch_bounds__(256) ball_flood_kernel(BallParams p) {
+__global__ void __launch_bounds__(1024, 2) ball_flood_kernel(BallParams p) {
   cg::grid_group grid = cg::this_grid();
   const int lane = threadIdx.x & 31;
   const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -662,9 +662,9 @@ B2T_EXPORT int b2t_invalidate_ball(const uint32_t* d_cc, const float* d_dbf, uin
   ball_seed_kernel<<<(n_seeds + 255) / 256, 256, 0, st>>>(p);
   int blocks = 0;
   const void* kern = (n_seeds == 1) ? (const void*)ball_flood_single_kernel : (const void*)ball_flood_kernel;
-  if (int rc = coop_grid(kern, 256, 0, &blocks)) return rc;
+  if (int rc = coop_grid(kern, 1024, 0, &blocks)) return rc;
   void* args[] = {&p};
-  B2T_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(256), args, 0, st));
+  B2T_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(1024), args, 0, st));
   b2t_count_launches(2);
   return B2T_OK;
 }
