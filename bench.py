@@ -198,14 +198,19 @@ def run_b200(args):
       dist.barrier()
       torch.cuda.synchronize()
 
+  step_log = {}
+
   def timed(fn, steps, **kw):
     sync()
     t = time.perf_counter()
     out = None
+    marks = []
     for _ in range(steps):
       out = fn(**kw)
+      marks.append(time.perf_counter())        # every step ends with a device->host read, so this is its end
     sync()
     dt = time.perf_counter() - t
+    step_log[fn.__name__] = [round(1e3 * (b - a), 2) for a, b in zip([t] + marks[:-1], marks)]
     if world > 1:
       tt = torch.tensor([dt], dtype=torch.float64, device=dev)
       dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -281,7 +286,7 @@ def run_b200(args):
       "e2e": {"value": V / (mse / 1e3), "unit": "voxels/s", "h2d_bytes_per_step": int(flat.nbytes),
               "d2h_bytes_per_step": d2h, "ms_per_step": mse},
       "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "phases_ms": phases,
-      "e2e_phases_ms": e2e_phases,
+      "e2e_phases_ms": e2e_phases, "per_step_ms": step_log,
     }
     print(json.dumps(line), flush=True)
   if world > 1:
