@@ -63,11 +63,21 @@ def check(status, what=""):
     raise B2TError(f"{what} failed with status {status}: {msg.decode() if msg else ''}")
 
 
+_checked_devices = set()
+
+
 def require_device():
+  """Raise unless the current device is an sm_100 GPU.  The answer is cached per device:
+  cudaGetDeviceProperties is slow and jittery (tens of ms, occasionally hundreds) and must not sit on the
+  per-call path of skeletonize()."""
   import torch
   if not torch.cuda.is_available():
     raise B2TError("kimimaro_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+  dev = torch.cuda.current_device()
+  if dev in _checked_devices:
+    return
   check(lib().b2t_device_check(), "b2t_device_check")
+  _checked_devices.add(dev)
 
 
 def stream_ptr():

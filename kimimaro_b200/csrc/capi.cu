@@ -47,14 +47,15 @@ B2T_EXPORT int b2t_device_check(void) {
     cudaGetLastError();
     return B2T_ERR_DEVICE;
   }
-  cudaDeviceProp p;
-  e = cudaGetDeviceProperties(&p, dev);
+  int major = 0, minor = 0;   // attribute queries are cheap; cudaGetDeviceProperties is not
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
   if (e != cudaSuccess) {
-    b2t_set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    b2t_set_error("cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
     return B2T_ERR_DEVICE;
   }
-  if (p.major != 10) {
-    b2t_set_error("libb2t.so is built for sm_100a only; device %d is sm_%d%d (%s)", dev, p.major, p.minor, p.name);
+  if (major != 10) {
+    b2t_set_error("libb2t.so is built for sm_100a only; device %d is sm_%d%d", dev, major, minor);
     return B2T_ERR_DEVICE;
   }
   return B2T_OK;
