@@ -12,6 +12,8 @@ Deviations from the reference, all explicit:
   * tie rules T1-T5 (oracle/oracle.c header) where the reference leaves ties to heap / sort internals.
 """
 import ctypes
+import functools
+import gc
 import os
 import time
 from collections import defaultdict
@@ -150,7 +152,7 @@ def _private_arena(d_cc3, d_dbf3, segid, bbox, anisotropy, params, root, targets
   return res.get(1), stats
 
 
-def skeletonize(
+def _skeletonize(
   all_labels, teasar_params=DEFAULT_TEASAR_PARAMS, anisotropy=(1, 1, 1),
   object_ids=None, dust_threshold=1000,
   progress=True, fix_branching=True, in_place=False,
@@ -378,3 +380,17 @@ def skeletonize(
     tm["n_traced"] = len(jobs) + len(private)
     tm["kernel_stats"] = stats_all
   return out
+
+
+@functools.wraps(_skeletonize)
+def skeletonize(*args, **kwargs):
+  # A full (generation 2) pass of CPython's cyclic collector walks every tracked object of the process
+  # (torch alone brings hundreds of thousands) and costs 30-40 ms -- a quarter of a 512^3 pass -- so it is
+  # suspended for the duration of the call and restored afterwards.  Results are unaffected.
+  was_enabled = gc.isenabled()
+  gc.disable()
+  try:
+    return _skeletonize(*args, **kwargs)
+  finally:
+    if was_enabled:
+      gc.enable()
