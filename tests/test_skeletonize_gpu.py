@@ -279,3 +279,14 @@ def test_no_fix_branching_2d_slice(gpu):
   lab = synthetic_tubes((128, 128, 64), 14, seed=3)[:, :, 30]
   res, ref = _both(gpu, lab, anisotropy=(16, 16, 40), dust_threshold=50, fix_branching=False)
   _compare(res, ref)
+
+
+def test_non_integer_anisotropy(gpu):
+  """Anisotropies that are not exactly representable (the x pass multiplies where the library adds repeatedly):
+  radii stay within 1e-4, vertices and edges still have to match."""
+  from tests.synth import synthetic_tubes
+  an = (3.58, 3.58, 4.1)
+  lab = synthetic_tubes((96, 96, 64), 10, seed=13, anisotropy=an)
+  tp = {"scale": 1.5, "const": 20, "pdrf_scale": 100000, "pdrf_exponent": 4}
+  res, ref = _both(gpu, lab, anisotropy=an, dust_threshold=100, teasar_params=tp)
+  _compare(res, ref)
