@@ -403,25 +403,38 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
   int a = 0;             // first row of the open run
   T run_lab = T(0);
   int tv = 0; float th = 0.0f, tz = 0.0f;   // top entry, cached
-  // query cursor over the closed runs
+  // query cursor over the closed runs; the NEXT envelope entry (row, height, left end) is always already in
+  // registers so that stepping to it never waits for local memory
   int q_next = 0;                            // first row not written yet
   int r_lo = 0, r_cnt = 0, r_a = 0x7fffffff, r_b = 0;
   int kk = 0, cv = 0;
-  float ch = 0.0f, nz = kInf;
+  float ch = 0.0f;
+  int nv = 0; float nh = 0.0f, nz = kInf;    // entry kk+1 (nz = +inf when there is none)
 
   for (int c0 = 0; c0 < n; c0 += kChunk) {
     const int c1 = min(n, c0 + kChunk);
-    // ---------------- build: rows [c0, c1) ----------------
+    // ---------------- build: rows [c0, c1), 8-row batches, the next batch is loaded while this one is used ----
+    float fv[8], fnx[8];
+    T lv[8], lnx[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      fnx[j] = 0.0f; lnx[j] = T(0);
+      if (active && c0 + j < c1) {
+        const int64_t idx = base + (int64_t)(c0 + j) * cstride;
+        fnx[j] = f[idx];
+        lnx[j] = labels[idx];
+      }
+    }
     for (int i0 = c0; i0 < c1; i0 += 8) {
-      float fv[8];
-      T lv[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) { fv[j] = fnx[j]; lv[j] = lnx[j]; }
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        fv[j] = 0.0f; lv[j] = T(0);
-        if (active && i0 + j < c1) {
-          const int64_t idx = base + (int64_t)(i0 + j) * cstride;
-          fv[j] = f[idx];
-          lv[j] = labels[idx];
+        fnx[j] = 0.0f; lnx[j] = T(0);
+        if (active && i0 + 8 + j < c1) {
+          const int64_t idx = base + (int64_t)(i0 + 8 + j) * cstride;
+          fnx[j] = f[idx];
+          lnx[j] = labels[idx];
         }
       }
 #pragma unroll
@@ -474,7 +487,8 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
             const uint32_t pk = __float_as_uint(ez[r_lo]);
             r_a = (int)ev[r_lo]; r_b = (int)(pk >> 16); r_cnt = (int)(pk & 0xffffu);
             kk = r_lo; cv = 0; ch = eh[kk];
-            nz = (r_cnt > 1) ? ez[kk + 1] : kInf;
+            nz = kInf;
+            if (r_cnt > 1) { nv = (int)ev[kk + 1]; nh = eh[kk + 1]; nz = ez[kk + 1]; }
           } else {
             r_a = 0x7fffffff; r_b = q_end; r_cnt = 0;        // only background left before q_end
           }
@@ -483,8 +497,9 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
           const int ir = i - r_a;
           while (nz < (float)ir) {
             kk++;
-            cv = (int)ev[kk] - r_a; ch = eh[kk];
-            nz = (kk + 1 < r_lo + r_cnt) ? ez[kk + 1] : kInf;
+            cv = nv - r_a; ch = nh;
+            nz = kInf;
+            if (kk + 1 < r_lo + r_cnt) { nv = (int)ev[kk + 1]; nh = eh[kk + 1]; nz = ez[kk + 1]; }
           }
           const float di = (float)(ir - cv);
           float val = __fadd_rn(__fmul_rn(__fmul_rn(w2, di), di), ch);
