@@ -260,8 +260,13 @@ def run_b200(args):
     roof = None
     if edt_ms:
       ach = alg / (edt_ms * 1e-3) / 1e9
-      roof = {"kernel": "b2t_edt (K1: edt_pass_x + 2x edt_pass_col)", "bound": "hbm", "achieved": ach, "peak": peak,
-              "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": how,
+      traffic = None
+      tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")      # dram bytes of one K1 call from an ncu capture
+      if os.path.exists(tpath) and args.size == 512:
+        with open(tpath) as tf:
+          traffic = float(json.load(tf)["dram_bytes_read_plus_write"])
+      roof = {"kernel": "b2t_edt (K1: edt_pass_x_v2 + 2x edt_pass_col_fh)", "bound": "hbm", "achieved": ach, "peak": peak,
+              "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": how,
               "algorithmic_bytes": alg, "ms": edt_ms}
     # bounded CPU sample: the oracle port, one core, on the slab
     cpu = None
