@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib, engine
-from ._lib import B2TError, check, lib, stream_ptr
+from ._lib import B2TError, check, lib, stream_ptr  # noqa: F401  (B2TError is part of the module's surface)
 from .ops import edt
 from .skeleton import Skeleton
 

@@ -7,12 +7,13 @@ provides a compatible class with the fields and methods the reference's callers 
 (SURVEY 8a row T): id, vertices (float32 Nx3), edges (uint32 Mx2), radii (float32), vertex_types
 (uint8), space, transform (3x4 float32), extra_attributes; empty, from_path, simple_merge,
 consolidate, merge, clone, cable_length, components, terminals, branches, voxel_space,
-physical_space, to_swc / from_swc, equivalent.  If osteoid is importable its class is used instead.
+physical_space, to_swc / from_swc, equivalent.  The class is used unconditionally (HAVE_OSTEOID only records
+whether the original is importable; converting is `osteoid.Skeleton(s.vertices, s.edges, s.radii, ...)`).
 """
 import numpy as np
 
 try:  # pragma: no cover - not available in this image
-  from osteoid import Skeleton as _OsteoidSkeleton  # noqa: F401
+  import osteoid  # noqa: F401
   HAVE_OSTEOID = True
 except Exception:  # ImportError and friends
   HAVE_OSTEOID = False
