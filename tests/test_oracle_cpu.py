@@ -299,3 +299,23 @@ def test_no_cpu_fallback():
   from kimimaro_b200._lib import B2TError
   with pytest.raises(B2TError):
     kimimaro_b200.skeletonize(np.ones((32, 32, 64), np.uint8))
+
+
+def test_c_abi_argument_errors_without_gpu():
+  """Error behaviour of the boundary: bad arguments come back as B2T_ERR_ARG with a message, and on a box
+  without an sm_100 device b2t_device_check says so -- no crash, no silent fallback."""
+  from kimimaro_b200 import build
+  lib = ctypes.CDLL(build.build())
+  lib.b2t_last_error.restype = ctypes.c_char_p
+  i64, f32, ci, vp = ctypes.c_int64, ctypes.c_float, ctypes.c_int, ctypes.c_void_p
+  lib.b2t_edt.argtypes = [vp, ci, i64, i64, i64, f32, f32, f32, ci, ci, vp, vp]
+  assert lib.b2t_edt(None, 4, 8, 8, 8, 1.0, 1.0, 1.0, 0, 3, None, None) == -1          # B2T_ERR_ARG
+  assert b"null" in lib.b2t_last_error()
+  dummy = ctypes.create_string_buffer(64)
+  assert lib.b2t_edt(dummy, 3, 2, 2, 2, 1.0, 1.0, 1.0, 0, 3, dummy, None) == -1         # label width 3
+  assert lib.b2t_edt(dummy, 4, 2, 2, 2, 1.0, 1.0, 1.0, 0, 2, dummy, None) == -1         # ndim 2 needs sz == 1
+  assert lib.b2t_edt(dummy, 4, 5000, 2, 2, 1.0, 1.0, 1.0, 0, 3, dummy, None) == -1      # row longer than supported
+  torch = pytest.importorskip("torch")
+  if not torch.cuda.is_available():
+    assert lib.b2t_device_check() == -2                                                 # B2T_ERR_DEVICE
+    assert len(lib.b2t_last_error()) > 0
