@@ -138,36 +138,58 @@ __global__ void __launch_bounds__(1024, 2) edf_multi_kernel(EdfParams p) {
     const uint32_t* qin = p.queue + (uint64_t)(round & 1) * p.cap;
     uint32_t* qout = p.queue + (uint64_t)((round + 1) & 1) * p.cap;
     uint32_t* cnt_out = &p.ctrl[(round + 1) % 3];
-    for (uint32_t it = gwarp; it < n; it += nwarps) {
-      const uint32_t u = __ldcg(&qin[it]);
-      const float du = __ldcg(&p.dist[u]);
-      const uint32_t lab = __ldg(&p.cc[u]);
-      int x, y, z;
-      unravel(u, p.d, x, y, z);
-      const int nx = x + dx, ny = y + dy, nz = z + dz;
-      bool push = false;
-      uint32_t v = 0;
-      if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < p.d.sx && ny < p.d.sy && nz < p.d.sz) {
-        v = (uint32_t)((int64_t)u + off);
-        if (__ldg(&p.cc[v]) == lab) {
+    // two frontier voxels per warp iteration: the sweep is bound by the chain of dependent global accesses
+    // per voxel (queue -> dist/label -> neighbour label -> atomicMin -> stamp), so two independent chains
+    // in flight per warp nearly halve the time of a round
+    for (uint32_t it = gwarp * 2; it < n; it += nwarps * 2) {
+      uint32_t u[2], lab[2], v[2], lv[2];
+      float du[2];
+      bool ok[2], push[2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const bool have = it + e < n;
+        u[e] = have ? __ldcg(&qin[it + e]) : 0u;
+        ok[e] = have;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        du[e] = ok[e] ? __ldcg(&p.dist[u[e]]) : 0.0f;
+        lab[e] = ok[e] ? __ldg(&p.cc[u[e]]) : 0u;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int x, y, z;
+        unravel(u[e], p.d, x, y, z);
+        const int nx = x + dx, ny = y + dy, nz = z + dz;
+        ok[e] = ok[e] && lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < p.d.sx && ny < p.d.sy && nz < p.d.sz;
+        v[e] = ok[e] ? (uint32_t)((int64_t)u[e] + off) : 0u;
+        lv[e] = ok[e] ? __ldg(&p.cc[v[e]]) : 0xffffffffu;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        push[e] = false;
+        if (ok[e] && lv[e] == lab[e]) {
           bool frozen = false;
-          if (HAS_FROZEN) frozen = __ldcg(&p.stamp[v]) == kFrozen;
+          if (HAS_FROZEN) frozen = __ldcg(&p.stamp[v[e]]) == kFrozen;
           if (!frozen) {
-            const uint32_t nd = __float_as_uint(__fadd_rn(du, NODE_W ? __ldg(&p.node_w[v]) : w));
-            const uint32_t old = atomicMin(reinterpret_cast<uint32_t*>(&p.dist[v]), nd);
+            const uint32_t nd = __float_as_uint(__fadd_rn(du[e], NODE_W ? __ldg(&p.node_w[v[e]]) : w));
+            const uint32_t old = atomicMin(reinterpret_cast<uint32_t*>(&p.dist[v[e]]), nd);
             if (nd < old) {
               improved++;
-              push = atomicExch(&p.stamp[v], round) != round;
+              push[e] = atomicExch(&p.stamp[v[e]], round) != round;
             }
           }
         }
       }
-      const uint32_t m = __ballot_sync(0xffffffffu, push);
-      if (m) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(cnt_out, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (push) qout[base + __popc(m & ltmask)] = v;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const uint32_t m = __ballot_sync(0xffffffffu, push[e]);
+        if (m) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(cnt_out, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (push[e]) qout[base + __popc(m & ltmask)] = v[e];
+        }
       }
     }
     grid.sync();
