@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb2t.so")
+# B2T_LIB: another build of the same sources (kernel experiments); never a different implementation
+LIB_PATH = os.environ.get("B2T_LIB") or os.path.join(HERE, "libb2t.so")
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int

@@ -377,6 +377,29 @@ __device__ __forceinline__ float fh_intersect(float fi, int i, float h, int v, f
   return __fdiv_rn(__fadd_rn(__fsub_rn(fi, h), __fmul_rn(f1, f2)), __fmul_rn(2.0f, f1));
 }
 
+#ifndef B2T_FH_STREAM
+#define B2T_FH_STREAM 1
+#endif
+#ifndef B2T_FH_PEND
+#define B2T_FH_PEND 1
+#endif
+// The column pass touches every f / label exactly once: with B2T_FH_STREAM the accesses are marked evict-first
+// so that L1/L2 keep the local-memory parabola stacks instead.
+template <typename U> __device__ __forceinline__ U fh_ld(const U* p) {
+#if B2T_FH_STREAM
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ void fh_st(float* p, float v) {
+#if B2T_FH_STREAM
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+
 template <typename T, int NMAX, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, int64_t cstride, int nx,
@@ -397,6 +420,12 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
   uint16_t ev[NMAX];
   float eh[NMAX];
   float ez[NMAX];
+#define LD_EV(k_) ((int)ev[k_])
+#define LD_EH(k_) (eh[k_])
+#define LD_EZ(k_) (ez[k_])
+#define ST_EV(k_, v_) ev[k_] = (uint16_t)(v_)
+#define ST_EH(k_, v_) eh[k_] = (v_)
+#define ST_EZ(k_, v_) ez[k_] = (v_)
 
   int ktot = 0;          // entries in the stack
   int k_lo = 0, k = -1;  // first / top entry of the open run
@@ -421,8 +450,8 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
       fnx[j] = 0.0f; lnx[j] = T(0);
       if (active && c0 + j < c1) {
         const int64_t idx = base + (int64_t)(c0 + j) * cstride;
-        fnx[j] = f[idx];
-        lnx[j] = labels[idx];
+        fnx[j] = fh_ld(f + idx);
+        lnx[j] = fh_ld(labels + idx);
       }
     }
     for (int i0 = c0; i0 < c1; i0 += 8) {
@@ -433,8 +462,8 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
         fnx[j] = 0.0f; lnx[j] = T(0);
         if (active && i0 + 8 + j < c1) {
           const int64_t idx = base + (int64_t)(i0 + 8 + j) * cstride;
-          fnx[j] = f[idx];
-          lnx[j] = labels[idx];
+          fnx[j] = fh_ld(f + idx);
+          lnx[j] = fh_ld(labels + idx);
         }
       }
 #pragma unroll
@@ -445,11 +474,11 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
           float fi = fv[j];
           if (fi > kFltMax) fi = kFltMax;                      // tofinite()
           if (lab != run_lab) {
-            if (run_lab != T(0)) ez[k_lo] = __uint_as_float(((uint32_t)i << 16) | (uint32_t)(k - k_lo + 1));
+            if (run_lab != T(0)) ST_EZ(k_lo, __uint_as_float(((uint32_t)i << 16) | (uint32_t)(k - k_lo + 1)));
             run_lab = lab;
             if (lab != T(0)) {
               a = i; k_lo = ktot; k = ktot; ktot++;
-              ev[k] = (uint16_t)i; eh[k] = fi;
+              ST_EV(k, i); ST_EH(k, fi);
               tv = 0; th = fi; tz = -kInf;
             }
           } else if (lab != T(0)) {
@@ -457,12 +486,12 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
             float s = fh_intersect(fi, ir, th, tv, w2);
             while (k > k_lo && s <= tz) {
               k--;
-              tv = (int)ev[k] - a; th = eh[k]; tz = (k > k_lo) ? ez[k] : -kInf;
+              tv = LD_EV(k) - a; th = LD_EH(k); tz = (k > k_lo) ? LD_EZ(k) : -kInf;
               s = fh_intersect(fi, ir, th, tv, w2);
             }
             k++;
             ktot = k + 1;
-            ev[k] = (uint16_t)i; eh[k] = fi; ez[k] = s;
+            ST_EV(k, i); ST_EH(k, fi); ST_EZ(k, s);
             tv = ir; th = fi; tz = s;
           }
         }
@@ -470,13 +499,18 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
     }
     const bool open = run_lab != T(0) && c1 < n;
     if (run_lab != T(0) && c1 == n) {                        // the column ends inside a run
-      ez[k_lo] = __uint_as_float(((uint32_t)n << 16) | (uint32_t)(k - k_lo + 1));
+      ST_EZ(k_lo, __uint_as_float(((uint32_t)n << 16) | (uint32_t)(k - k_lo + 1)));
       run_lab = T(0);
     }
     // ---------------- query: rows [q_next, q_end) of the closed runs ----------------
     const int q_end = open ? a : c1;                         // rows of a still open run wait for its end
     const int kdone = open ? k_lo : ktot;                    // entries that belong to closed runs
+#if B2T_FH_PEND
+    // a lane whose closed runs are all written has nothing to do here (most lanes of a sparse volume)
+    const bool todo = active && q_next < q_end && ((r_cnt > 0 && q_next < r_b) || r_lo + r_cnt < kdone);
+#else
     const bool todo = active && q_next < q_end;
+#endif
     const int lo = __reduce_min_sync(0xffffffffu, todo ? q_next : 0x7fffffff);
     const int hi = __reduce_max_sync(0xffffffffu, todo ? q_end : 0);
     for (int i = lo; i < hi; i++) {
@@ -484,11 +518,11 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
         if (i >= r_b) {                                       // move to the next closed run
           r_lo += r_cnt;
           if (r_lo < kdone) {
-            const uint32_t pk = __float_as_uint(ez[r_lo]);
-            r_a = (int)ev[r_lo]; r_b = (int)(pk >> 16); r_cnt = (int)(pk & 0xffffu);
-            kk = r_lo; cv = 0; ch = eh[kk];
+            const uint32_t pk = __float_as_uint(LD_EZ(r_lo));
+            r_a = LD_EV(r_lo); r_b = (int)(pk >> 16); r_cnt = (int)(pk & 0xffffu);
+            kk = r_lo; cv = 0; ch = LD_EH(kk);
             nz = kInf;
-            if (r_cnt > 1) { nv = (int)ev[kk + 1]; nh = eh[kk + 1]; nz = ez[kk + 1]; }
+            if (r_cnt > 1) { nv = LD_EV(kk + 1); nh = LD_EH(kk + 1); nz = LD_EZ(kk + 1); }
           } else {
             r_a = 0x7fffffff; r_b = q_end; r_cnt = 0;        // only background left before q_end
           }
@@ -499,14 +533,14 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
             kk++;
             cv = nv - r_a; ch = nh;
             nz = kInf;
-            if (kk + 1 < r_lo + r_cnt) { nv = (int)ev[kk + 1]; nh = eh[kk + 1]; nz = ez[kk + 1]; }
+            if (kk + 1 < r_lo + r_cnt) { nv = LD_EV(kk + 1); nh = LD_EH(kk + 1); nz = LD_EZ(kk + 1); }
           }
           const float di = (float)(ir - cv);
           float val = __fadd_rn(__fmul_rn(__fmul_rn(w2, di), di), ch);
           if (r_a > 0 || black_border) { const float ee = (float)(ir + 1); val = fminf(val, __fmul_rn(__fmul_rn(w2, ee), ee)); }
           if (r_b < n || black_border) { const float ee = (float)(r_b - i); val = fminf(val, __fmul_rn(__fmul_rn(w2, ee), ee)); }
           if (last_pass) val = (val >= kFltMax) ? kInf : sqrtf(val);
-          f[base + (int64_t)i * cstride] = val;
+          fh_st(f + base + (int64_t)i * cstride, val);
         }
       }
     }
@@ -517,6 +551,12 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
     }
   }
 }
+#undef LD_EV
+#undef LD_EH
+#undef LD_EZ
+#undef ST_EV
+#undef ST_EH
+#undef ST_EZ
 
 template <typename T>
 int edt_launch_v2(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz, int black_border,

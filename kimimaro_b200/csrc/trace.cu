@@ -25,6 +25,9 @@ namespace {
 constexpr uint32_t kInfBits = 0x7f800000u;
 constexpr unsigned long long kValid = ~0ull;
 constexpr int kThreads = 512;   // 16 warps: a whole narrow batch expands in one pass
+#ifndef B2T_TRACE_MINB
+#define B2T_TRACE_MINB 3        // resident CTAs per SM (42 registers per thread)
+#endif
 constexpr int kWarps = kThreads / 32;
 
 struct Dims {
@@ -288,50 +291,70 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
     }
     __syncthreads();
     const uint32_t n_proc = S.n_proc;
-    // ---- (c) expand the batch: warp per voxel, lane per neighbour ----
-    for (uint32_t it = warp; it < n_proc; it += kWarps) {
-      const uint32_t u = proc[it];
-      if (lane == 0) atomicExch(&A.stamp[u], 0u);   // from here on an improvement of u re-queues it
+    // ---- (c) expand the batch: lane per neighbour, TWO voxels per warp iteration so that their chains of
+    //          dependent global accesses (stamp/dist of u -> label/weight of v -> atomicMin -> stamp of v) overlap ----
+    for (uint32_t it = warp; it < n_proc; it += 2 * kWarps) {
+      uint32_t u[2], v[2], lv[2], nd[2], old[2];
+      float du[2], c[2];
+      bool ok[2], relaxed[2], push_mid[2], push_far[2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        ok[e] = it + e * kWarps < n_proc;
+        u[e] = ok[e] ? proc[it + e * kWarps] : 0u;
+        if (ok[e] && lane == 0) atomicExch(&A.stamp[u[e]], 0u);   // from here on an improvement of u re-queues it
+      }
       __syncwarp();
       __threadfence_block();
-      const float du = __ldcg(&A.dist[u]);
-      int x, y, z;
-      unravel(u, A.d, x, y, z);
-      const int nx = x + dx, ny = y + dy, nz = z + dz;
-      bool push_mid = false, push_far = false;
-      uint32_t v = 0;
-      if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
-        v = (uint32_t)((int64_t)u + off);
-        const uint32_t lv = __ldg(&A.cc[v]);        // independent loads, issued together
-        const float c = __ldcg(&A.pdrf[v]);
-        if (lv == seg) {
-          if (c == 0.0f) {
-            atomicMin(&S.best, ((unsigned long long)__float_as_uint(du) << 32) | u);   // rule T4 candidate
+#pragma unroll
+      for (int e = 0; e < 2; e++) du[e] = ok[e] ? __ldcg(&A.dist[u[e]]) : 0.0f;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int x, y, z;
+        unravel(u[e], A.d, x, y, z);
+        const int nx = x + dx, ny = y + dy, nz = z + dz;
+        ok[e] = ok[e] && lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz;
+        v[e] = ok[e] ? (uint32_t)((int64_t)u[e] + off) : 0u;
+        lv[e] = ok[e] ? __ldg(&A.cc[v[e]]) : 0xffffffffu;       // independent loads, issued together
+        c[e] = ok[e] ? __ldcg(&A.pdrf[v[e]]) : 0.0f;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        relaxed[e] = false; push_mid[e] = false; push_far[e] = false; nd[e] = 0; old[e] = 0;
+        if (ok[e] && lv[e] == seg) {
+          if (c[e] == 0.0f) {
+            atomicMin(&S.best, ((unsigned long long)__float_as_uint(du[e]) << 32) | u[e]);   // rule T4 candidate
           } else {
-            const uint32_t nd = __float_as_uint(__fadd_rn(du, c));
-            if (nd <= (uint32_t)(S.best >> 32)) {
-              const uint32_t old = atomicMin(reinterpret_cast<uint32_t*>(&A.dist[v]), nd);
-              if (nd < old) {
-                relax++;
-                if (old == kInfBits) touched[atomicAdd(&S.n_touched, 1u)] = v;
-                __threadfence_block();
-                if (atomicExch(&A.stamp[v], 1u) == 0u) { push_mid = nd <= thr_mid; push_far = !push_mid; }
-              }
+            nd[e] = __float_as_uint(__fadd_rn(du[e], c[e]));
+            if (nd[e] <= (uint32_t)(S.best >> 32)) {
+              old[e] = atomicMin(reinterpret_cast<uint32_t*>(&A.dist[v[e]]), nd[e]);
+              relaxed[e] = nd[e] < old[e];
             }
           }
         }
       }
-      const uint32_t mm = __ballot_sync(0xffffffffu, push_mid), mf = __ballot_sync(0xffffffffu, push_far);
-      if (mm | mf) {
-        uint32_t bm = 0, bf = 0;
-        if (lane == 0) {
-          if (mm) bm = atomicAdd(&S.n_keep, __popc(mm));
-          if (mf) bf = atomicAdd(&S.n_next, __popc(mf));
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        if (relaxed[e]) {
+          relax++;
+          if (old[e] == kInfBits) touched[atomicAdd(&S.n_touched, 1u)] = v[e];
+          __threadfence_block();
+          if (atomicExch(&A.stamp[v[e]], 1u) == 0u) { push_mid[e] = nd[e] <= thr_mid; push_far[e] = !push_mid[e]; }
         }
-        bm = __shfl_sync(0xffffffffu, bm, 0);
-        bf = __shfl_sync(0xffffffffu, bf, 0);
-        if (push_mid) mid2[bm + __popc(mm & ltmask)] = v;
-        if (push_far) far[n_far + bf + __popc(mf & ltmask)] = v;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const uint32_t mm = __ballot_sync(0xffffffffu, push_mid[e]), mf = __ballot_sync(0xffffffffu, push_far[e]);
+        if (mm | mf) {
+          uint32_t bm = 0, bf = 0;
+          if (lane == 0) {
+            if (mm) bm = atomicAdd(&S.n_keep, __popc(mm));
+            if (mf) bf = atomicAdd(&S.n_next, __popc(mf));
+          }
+          bm = __shfl_sync(0xffffffffu, bm, 0);
+          bf = __shfl_sync(0xffffffffu, bf, 0);
+          if (push_mid[e]) mid2[bm + __popc(mm & ltmask)] = v[e];
+          if (push_far[e]) far[n_far + bf + __popc(mf & ltmask)] = v[e];
+        }
       }
     }
     __syncthreads();
@@ -653,7 +676,7 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads, 3) trace_kernel(Arena A, const LabelDesc* __restrict__ descs, Pools P, Params prm) {
+__global__ void __launch_bounds__(kThreads, B2T_TRACE_MINB) trace_kernel(Arena A, const LabelDesc* __restrict__ descs, Pools P, Params prm) {
   __shared__ Shared S;
   __shared__ LabelDesc L;
   for (;;) {

@@ -15,6 +15,7 @@ def main():
     vol = np.load(cache)
   else:
     vol = synthetic_tubes((n, n, n), 2124 * (n // 512) ** 3 if n >= 512 else 40, seed=0xB2002124, soma=(n >= 512), glia=(n >= 512))
+    np.save(cache, vol)
   print("gen", time.time() - t, "fg frac", float((vol != 0).mean()), flush=True)
   d = ops.to_device_f(vol)
   out = torch.empty(vol.size, dtype=torch.float32, device="cuda")
@@ -32,6 +33,7 @@ def main():
   ms = float(np.median(times))
   V = vol.size
   alg = (3 * vol.dtype.itemsize + 20) * V
-  print(json.dumps({"n": n, "ms_median": ms, "ms_min": min(times), "alg_GBps": alg / ms / 1e6, "voxels": V}))
+  digest = int(torch.nan_to_num(out, posinf=0.0).view(torch.int32).to(torch.int64).sum().item())
+  print(json.dumps({"digest": digest, "n": n, "ms_median": ms, "ms_min": min(times), "alg_GBps": alg / ms / 1e6, "voxels": V}))
 
 main()
