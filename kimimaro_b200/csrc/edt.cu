@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "edt_fh3.cuh"
 
 namespace {
 
@@ -558,6 +559,100 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
 #undef ST_EH
 #undef ST_EZ
 
+// ================================================================================================
+// v3 column pass: the body is edt_fh3.cuh (shared with the CPU test harness); this is its device context.
+// Shared memory: three [C][128] float planes (apex row, height, left end): 12*C*128 bytes per CTA.
+// ================================================================================================
+template <int C, int NMAX>
+struct FhDevCtx {
+  uint32_t sbase;   // shared-state-space address of s_plane[0][0][threadIdx.x]: slot stride 512 B, plane stride C*512 B
+  float* lv; float* lh; float* lz;      // local-memory backing, indexed by entry
+  __device__ __forceinline__ float mul(float a, float b) const { return __fmul_rn(a, b); }
+  __device__ __forceinline__ float add(float a, float b) const { return __fadd_rn(a, b); }
+  __device__ __forceinline__ float sub(float a, float b) const { return __fsub_rn(a, b); }
+  __device__ __forceinline__ float div(float a, float b) const { return __fdiv_rn(a, b); }
+  __device__ __forceinline__ float sqrt(float a) const { return __fsqrt_rn(a); }
+  __device__ __forceinline__ float fmin(float a, float b) const { return fminf(a, b); }
+  template <typename U> __device__ __forceinline__ U ld_label(const U* p) const { return __ldcs(p); }
+  __device__ __forceinline__ float ld_f(const float* p) const { return __ldcs(p); }
+  __device__ __forceinline__ void st_f(float* p, float v) const { __stcs(p, v); }
+  // explicit ld/st.shared on a 32-bit address (one address register, the plane is an immediate offset); a thread
+  // only ever reads what it wrote itself, and volatile asm statements keep their order
+  template <int PLANE> __device__ __forceinline__ float lds(int s) const {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(r) : "r"(sbase + (uint32_t)s * 512u), "n"(PLANE * C * 512));
+    return r;
+  }
+  template <int PLANE> __device__ __forceinline__ void sts(int s, float v) const {
+    asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(sbase + (uint32_t)s * 512u), "n"(PLANE * C * 512), "f"(v));
+  }
+  __device__ __forceinline__ void s_st(int s, float v, float h, float z) { sts<0>(s, v); sts<1>(s, h); sts<2>(s, z); }
+  __device__ __forceinline__ void s_st_z(int s, float z) { sts<2>(s, z); }
+  __device__ __forceinline__ float s_ld_v(int s) const { return lds<0>(s); }
+  __device__ __forceinline__ float s_ld_h(int s) const { return lds<1>(s); }
+  __device__ __forceinline__ float s_ld_z(int s) const { return lds<2>(s); }
+  __device__ __forceinline__ void l_st(int k, float v, float h, float z) { lv[k] = v; lh[k] = h; lz[k] = z; }
+  __device__ __forceinline__ void l_st_z(int k, float z) { lz[k] = z; }
+  __device__ __forceinline__ float l_ld_v(int k) const { return lv[k]; }
+  __device__ __forceinline__ float l_ld_h(int k) const { return lh[k]; }
+  __device__ __forceinline__ float l_ld_z(int k) const { return lz[k]; }
+  __device__ __forceinline__ int wmin(int x) const { return __reduce_min_sync(0xffffffffu, x); }
+  __device__ __forceinline__ int wmax(int x) const { return __reduce_max_sync(0xffffffffu, x); }
+};
+
+template <typename T, int C, int NMAX, int MINB, int R, int B>
+__global__ void __launch_bounds__(128, MINB)
+edt_pass_col_fh3_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, int64_t cstride, int nx,
+                        int64_t ostride, float w, int black_border, int last_pass) {
+  __shared__ float s_plane[3][C][128];
+  float lv[NMAX];
+  float lh[NMAX];
+  float lz[NMAX];
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const bool active = x < nx;                      // no early return: the warp reduces loop bounds together
+  const int64_t base = (int64_t)blockIdx.y * ostride + (active ? x : 0);
+  FhDevCtx<C, NMAX> cx{(uint32_t)__cvta_generic_to_shared(&s_plane[0][0][threadIdx.x]), lv, lh, lz};
+  fh3::column<T, C, R, B>(cx, labels + base, f + base, n, cstride, w, black_border != 0, last_pass != 0, active);
+}
+
+// B2T_FH3 = "C,MINB,R,B" picks one of the compiled variants (kernel experiments); the default is the measured best.
+struct Fh3Cfg { int c, minb, r, b; };
+static Fh3Cfg fh3_cfg() {
+  static const Fh3Cfg cfg = []() {
+    Fh3Cfg c{16, 8, 32, 4};
+    const char* e = getenv("B2T_FH3");
+    if (e) sscanf(e, "%d,%d,%d,%d", &c.c, &c.minb, &c.r, &c.b);
+    return c;
+  }();
+  return cfg;
+}
+
+template <typename T, int NMAX>
+bool edt_launch_fh3_passes(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wy, float wz, int black_border,
+                           int ndim, float* out, cudaStream_t st) {
+  const dim3 gy((unsigned)b2t_ceil_div(sx, 128), (unsigned)sz), gz((unsigned)b2t_ceil_div(sx, 128), (unsigned)sy);
+  const Fh3Cfg c = fh3_cfg();
+#define B2T_FH3_GO(C_, MB_, R_, B_)                                                                                    \
+  if (c.c == C_ && c.minb == MB_ && c.r == R_ && c.b == B_) {                                                          \
+    edt_pass_col_fh3_kernel<T, C_, NMAX, MB_, R_, B_><<<gy, 128, 0, st>>>(labels, out, (int)sy, sx, (int)sx, sx * sy, \
+                                                                         wy, black_border, ndim == 2);                \
+    if (ndim == 3)                                                                                                     \
+      edt_pass_col_fh3_kernel<T, C_, NMAX, MB_, R_, B_><<<gz, 128, 0, st>>>(labels, out, (int)sz, sx * sy, (int)sx,   \
+                                                                           sx, wz, black_border, 1);                  \
+    return true;                                                                                                       \
+  }
+  B2T_FH3_GO(16, 8, 32, 4)
+  B2T_FH3_GO(16, 8, 16, 4)
+  B2T_FH3_GO(16, 6, 32, 4)
+  B2T_FH3_GO(16, 8, 32, 8)
+  B2T_FH3_GO(32, 4, 32, 4)
+  B2T_FH3_GO(32, 4, 32, 8)
+  B2T_FH3_GO(8, 8, 16, 4)
+  B2T_FH3_GO(8, 12, 16, 4)
+#undef B2T_FH3_GO
+  return false;
+}
+
 template <typename T>
 int edt_launch_v2(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz, int black_border,
                   int ndim, float* out, cudaStream_t st, bool* handled) {
@@ -579,6 +674,19 @@ int edt_launch_v2(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wx,
   if (!x_done) {
     const int64_t blocks = (nrows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     edt_pass_x_kernel<T><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(labels, out, (int)sx, nrows, wx, black_border);
+  }
+  // column passes: v3 (shared-memory ring, edt_fh3.cuh) unless B2T_EDT_ALGO=2 asks for the v2 kernel
+  static const bool use_v3 = []() { const char* e = getenv("B2T_EDT_ALGO"); return !(e && e[0] == '2'); }();
+  if (use_v3 && nmax <= fh3::kMaxN) {
+    bool ok;
+    if (nmax <= 256) ok = edt_launch_fh3_passes<T, 256>(labels, sx, sy, sz, wy, wz, black_border, ndim, out, st);
+    else if (nmax <= 512) ok = edt_launch_fh3_passes<T, 512>(labels, sx, sy, sz, wy, wz, black_border, ndim, out, st);
+    else if (nmax <= 1024) ok = edt_launch_fh3_passes<T, 1024>(labels, sx, sy, sz, wy, wz, black_border, ndim, out, st);
+    else ok = edt_launch_fh3_passes<T, 2048>(labels, sx, sy, sz, wy, wz, black_border, ndim, out, st);
+    B2T_REQUIRE(ok, "b2t_edt: B2T_FH3 names a variant that is not compiled in");
+    B2T_CUDA_TRY(cudaGetLastError());
+    b2t_count_launches(ndim == 3 ? 3 : 2);
+    return B2T_OK;
   }
   const dim3 gy((unsigned)b2t_ceil_div(sx, 128), (unsigned)sz), gz((unsigned)b2t_ceil_div(sx, 128), (unsigned)sy);
   static const int minb = []() { const char* e = getenv("B2T_FH_MINB"); return e ? atoi(e) : 8; }();

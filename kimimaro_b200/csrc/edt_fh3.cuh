@@ -1,0 +1,226 @@
+// K1 column pass, v3: one thread per column, Felzenszwalb-Huttenlocher lower envelope with the parabola
+// stack in SHARED memory (a ring of C entries per thread; older entries of a deep stack -- blobs only --
+// spill to local memory).
+//
+// Same arithmetic as oracle/oracle.c edt_parabolic_run (which restates the PyPI `edt` library called at
+// kimimaro/intake.py:174-185, trace.py:112-117, intake.py:565): run-relative indices, the same
+// intersection formula with IEEE division, FLT_MAX in place of +inf, no fused multiply-add -- the
+// result is bit-identical to the CPU restatement.  What changed against the v2 kernel (edt.cu) is only
+// how the work is laid out on the machine (ncu: v2 was latency-bound on its local-memory stack and spent
+// 80 % of its 144 warp instructions per 32-voxel warp-row on integer bookkeeping and divergent control
+// flow):
+//   * stack entries live in shared memory, [entry][thread] so that any mix of depths across the lanes of a
+//     warp is bank-conflict free: three float planes (apex row, height, left end) behind one slot address;
+//   * a run's first entry is tagged with a NaN in its left-end slot: `s <= NaN` is false, so the pop loop
+//     needs no depth check, and the NaN's payload carries (run end row, number of entries) for the query;
+//   * completed runs are written every R rows by all lanes together (coalesced stores); the shared-memory
+//     part of the stack is a RING over an ever-growing entry index, so a dense segmentation (a run is always
+//     open, the stack never empties) stays inside shared memory as well, and a blob keeps the top C entries
+//     -- the ones pushes and pops touch -- there and spills only the older ones to local memory;
+//   * labels are loaded two batches ahead and f one batch ahead, f only where the label is non-zero
+//     (background needs neither its value nor a store: it stays 0 from the x pass);
+//   * the body is a __host__ __device__ template over a context type, so that tests/ can run the very same
+//     code on the CPU against the oracle (tests/test_edt_fh3_host.py); the device context is below.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define FH3_HD __host__ __device__ __forceinline__
+#else
+#define FH3_HD inline
+#endif
+
+namespace fh3 {
+
+constexpr float kFltMax = 3.4028234664e38f;
+constexpr int kBig = 0x3fffffff;
+constexpr int kMaxN = 2047;  // 11-bit row / count fields in the NaN payload
+
+union FI { float f; uint32_t u; };
+FH3_HD float u2f(uint32_t u) { FI x; x.u = u; return x.f; }
+FH3_HD uint32_t f2u(float f) { FI x; x.f = f; return x.u; }
+
+// Context interface (device: FhDevCtx in edt.cu; host: tests/host/fh3_host.cpp):
+//   float mul(a,b), add(a,b), sub(a,b), div(a,b), sqrt(a)   round-to-nearest, never contracted
+//   float fmin(a,b)
+//   T     ld_label(const T*), float ld_f(const float*), void st_f(float*, float)
+//   shared-memory ring, slot in [0, C):  s_st(slot, v, h, z), s_st_z(slot, z), s_ld_v(slot), s_ld_h(slot), s_ld_z(slot)
+//   local-memory backing, entry index:   l_st(k, v, h, z), l_st_z(k, z), l_ld_v(k), l_ld_h(k), l_ld_z(k)
+//   int   wmin(int), wmax(int)      warp-wide reductions (identity on the host)
+// An entry is (v, h, z): row of the parabola's apex (absolute, kept as a float: rows < 2^24 are exact and the
+// hot loop then needs no int->float conversion), its height, and the left end of its reign (run-relative).
+
+// intersection of the parabola rooted at run-relative row i (height fi) with the one at v (height h):
+// (f[i] - f[v] + (i-v) w^2 (i+v)) / (2 (i-v) w^2), oracle.c:137-139
+template <typename Ctx>
+FH3_HD float intersect(Ctx& cx, float fi, float ir, float h, float v, float w2) {
+  const float f1 = cx.mul(cx.sub(ir, v), w2);
+  const float f2 = cx.add(ir, v);
+  return cx.div(cx.add(cx.sub(fi, h), cx.mul(f1, f2)), cx.mul(2.0f, f1));
+}
+
+// The stack is addressed by an ever-growing entry index k.  Entries [ring_lo, k] are in the shared-memory
+// ring (slot = k mod C), entries below ring_lo that are still needed are in local memory.  For the thin
+// processes of a connectomics volume and for a dense segmentation the live window [kn, k] never exceeds C
+// and local memory is never touched; a blob keeps its top C entries -- the ones pushes and pops work on --
+// in the ring.
+#define FH3_SLOT(k_) ((k_) & (C - 1))
+#define FH3_LD_V(k_) (((k_) >= ring_lo) ? cx.s_ld_v(FH3_SLOT(k_)) : cx.l_ld_v(k_))
+#define FH3_LD_H(k_) (((k_) >= ring_lo) ? cx.s_ld_h(FH3_SLOT(k_)) : cx.l_ld_h(k_))
+#define FH3_LD_Z(k_) (((k_) >= ring_lo) ? cx.s_ld_z(FH3_SLOT(k_)) : cx.l_ld_z(k_))
+
+// C ring entries (power of two), R rows between flushes, B rows per load batch (R % B == 0)
+template <typename T, int C, int R, int B, typename Ctx>
+FH3_HD void column(Ctx& cx, const T* lp, float* fp, int n, int64_t cstride, float w, bool black_border,
+                   bool last_pass, bool active) {
+  static_assert((C & (C - 1)) == 0, "ring size must be a power of two");
+  static_assert(R % B == 0, "flush period must be a multiple of the batch");
+  const float w2 = cx.mul(w, w);
+  const float kNaN = u2f(0x7fc00000u);
+  const float kInf = u2f(0x7f800000u);
+
+  // ---- build state: the open run ----
+  T run_lab = T(0);
+  float af = 0.0f;       // first row of the open run
+  int k = -1;            // top entry
+  int k_lo = 0;          // first entry of the open run
+  int ring_lo = 0;       // entries below this index are in local memory (if still needed at all)
+  float tv = 0.0f, th = 0.0f, tz = kNaN;   // top entry, cached (tv run-relative)
+  int last_b = 0;        // end row of the most recent closed run
+  // ---- query state: closed runs not written yet occupy entries [kn, kdone) ----
+  int kn = 0;
+
+  // software pipeline: labels of batch b+2 and f of batch b+1 are in flight while batch b is consumed
+  T l0[B], l1[B], l2[B];
+  float f0[B], f1[B];
+  const T* lq = lp;      // next label batch to load
+  const float* fq = fp;  // next f batch to load
+  const int64_t bstride = (int64_t)B * cstride;
+#pragma unroll
+  for (int j = 0; j < B; j++) l1[j] = (active && j < n) ? cx.ld_label(lq + j * cstride) : T(0);
+  lq += bstride;
+#pragma unroll
+  for (int j = 0; j < B; j++) l2[j] = (active && B + j < n) ? cx.ld_label(lq + j * cstride) : T(0);
+  lq += bstride;
+#pragma unroll
+  for (int j = 0; j < B; j++) f1[j] = (l1[j] != T(0)) ? cx.ld_f(fq + j * cstride) : 0.0f;
+  fq += bstride;
+
+  for (int i0 = 0; i0 < n; i0 += B) {
+#pragma unroll
+    for (int j = 0; j < B; j++) { l0[j] = l1[j]; f0[j] = f1[j]; l1[j] = l2[j]; }
+#pragma unroll
+    for (int j = 0; j < B; j++)   // l1 != 0 implies that the row exists and the thread is active
+      f1[j] = (l1[j] != T(0)) ? cx.ld_f(fq + j * cstride) : 0.0f;
+    fq += bstride;
+#pragma unroll
+    for (int j = 0; j < B; j++) l2[j] = (active && i0 + 2 * B + j < n) ? cx.ld_label(lq + j * cstride) : T(0);
+    lq += bstride;
+    // ---------------- build: rows [i0, i0 + B); rows >= n were loaded as background ----------------
+    const float i0f = (float)i0;
+#pragma unroll
+    for (int j = 0; j < B; j++) {
+      const int i = i0 + j;
+      const T lab = l0[j];
+      const bool same = lab == run_lab;
+      if (!same && run_lab != T(0)) {            // close: tag the run's first entry with (end row, entries)
+        const float tag = u2f(0x7fc00000u | ((uint32_t)i << 11) | (uint32_t)(k - k_lo + 1));
+        if (k_lo >= ring_lo) cx.s_st_z(FH3_SLOT(k_lo), tag); else cx.l_st_z(k_lo, tag);
+        last_b = i;
+      }
+      run_lab = lab;
+      if (lab != T(0)) {
+        const float fi = cx.fmin(f0[j], kFltMax);  // the envelope arithmetic stays finite (oracle.c:182-186)
+        const float vf = i0f + (float)j;
+        float s = kNaN;
+        float ir = 0.0f;
+        if (same) {
+          ir = vf - af;
+          s = intersect(cx, fi, ir, th, tv, w2);
+          while (s <= tz) {                      // false on the run's first entry (its tz is a NaN)
+            k--;
+            if (k < ring_lo) {
+              tv = cx.l_ld_v(k) - af; th = cx.l_ld_h(k); tz = cx.l_ld_z(k);
+              ring_lo = k + 1;
+            } else {
+              tv = cx.s_ld_v(FH3_SLOT(k)) - af; th = cx.s_ld_h(FH3_SLOT(k)); tz = cx.s_ld_z(FH3_SLOT(k));
+            }
+            s = intersect(cx, fi, ir, th, tv, w2);
+          }
+        } else {
+          af = vf; k_lo = k + 1;
+        }
+        k++;
+        const int e = k - C;                     // the entry whose slot is about to be reused
+        if (e >= ring_lo) {
+          if (e >= kn)                           // still needed: spill it
+            cx.l_st(e, cx.s_ld_v(FH3_SLOT(e)), cx.s_ld_h(FH3_SLOT(e)), cx.s_ld_z(FH3_SLOT(e)));
+          ring_lo = e + 1;
+        }
+        cx.s_st(FH3_SLOT(k), vf, fi, s);
+        tv = ir; th = fi; tz = s;
+      }
+    }
+    const int c1 = i0 + B;
+    if ((c1 % R) != 0 && c1 < n) continue;
+    // ---------------- flush: write the rows of all closed runs ----------------
+    if (c1 >= n && run_lab != T(0)) {            // the column ends inside a run
+      const float tag = u2f(0x7fc00000u | ((uint32_t)n << 11) | (uint32_t)(k - k_lo + 1));
+      if (k_lo >= ring_lo) cx.s_st_z(FH3_SLOT(k_lo), tag); else cx.l_st_z(k_lo, tag);
+      last_b = n;
+      run_lab = T(0);
+    }
+    const int kdone = (run_lab != T(0)) ? k_lo : k + 1;
+    const bool todo = kn < kdone;
+    const int lo = cx.wmin(todo ? (int)FH3_LD_V(kn) : kBig);
+    const int hi = cx.wmax(todo ? last_b : 0);
+    if (lo < hi) {
+      int qa = todo ? -1 : kBig, qb = qa;        // rows [qa, qb) of the run being written; qb <= i: fetch the next
+      int kq = 0, kend = 0;
+      float qaf = 0.0f, qbf = 0.0f, cv = 0.0f, ch = 0.0f, nz = kInf;
+      bool bl = false, br = false;
+      float* fw = fp + lo * cstride;
+      float iqf = (float)lo;
+      for (int i = lo; i < hi; i++, fw += cstride, iqf += 1.0f) {
+        if (i >= qb) {                           // step to the next closed run (or to "nothing left")
+          if (kn < kdone) {
+            const uint32_t pk = f2u(FH3_LD_Z(kn));
+            qaf = FH3_LD_V(kn);
+            qa = (int)qaf;
+            qb = (int)((pk >> 11) & 0x7ffu);
+            qbf = (float)qb;
+            kq = kn; kend = kn + (int)(pk & 0x7ffu); kn = kend;
+            cv = 0.0f; ch = FH3_LD_H(kq);
+            nz = (kq + 1 < kend) ? FH3_LD_Z(kq + 1) : kInf;
+            bl = (qa > 0) || black_border;
+            br = (qb < n) || black_border;
+          } else {
+            qa = kBig; qb = kBig;
+          }
+        }
+        if (i >= qa) {                           // qa <= i < qb
+          const float ir = iqf - qaf;
+          while (nz < ir) {
+            kq++;
+            cv = FH3_LD_V(kq) - qaf;
+            ch = FH3_LD_H(kq);
+            nz = (kq + 1 < kend) ? FH3_LD_Z(kq + 1) : kInf;
+          }
+          const float di = cx.sub(ir, cv);
+          float val = cx.add(cx.mul(cx.mul(w2, di), di), ch);
+          if (bl) { const float e = cx.add(ir, 1.0f); val = cx.fmin(val, cx.mul(cx.mul(w2, e), e)); }
+          if (br) { const float e = qbf - iqf; val = cx.fmin(val, cx.mul(cx.mul(w2, e), e)); }
+          if (last_pass) val = (val >= kFltMax) ? kInf : cx.sqrt(val);
+          cx.st_f(fw, val);
+        }
+      }
+    }
+    // every closed run is written: kn == kdone, and the slots below it are free for reuse
+  }
+}
+#undef FH3_SLOT
+#undef FH3_LD_V
+#undef FH3_LD_H
+#undef FH3_LD_Z
+
+}  // namespace fh3
