@@ -40,6 +40,11 @@ def make_volume(n):
   cache = f"/tmp/b2t_synth_{n}_{SEED:x}.npy"
   if os.path.exists(cache):
     return np.load(cache)
+  # git-ignored copy of the generator's output (written by __graft_entry__.build(); it travels with the
+  # gpurun snapshot and saves a minute of generation per process on the GPU box)
+  packed = os.path.join(ROOT, "oracle", "_cache", f"synth_{n}_{SEED:x}.npz")
+  if os.path.exists(packed):
+    return np.asfortranarray(np.load(packed)["v"].astype(np.uint32))
   if n == 1024:
     # BASELINE.json configs[4]: 1024^3 = 2x2x2 tiling of the 512^3 volume, label ids offset per tile
     from kimimaro_b200.datasets import tiled

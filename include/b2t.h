@@ -46,10 +46,15 @@ int b2t_set_launch_limits(int coop_blocks_per_sm, int trace_blocks_per_sm);
  *           edt.edt(cc_plane, black_border=True, anisotropy=(wx,wy))  kimimaro/intake.py:565
  * d_labels: [sx,sy,sz] unsigned ints of label_bytes in {1,2,4,8}; d_out: float32 [sx,sy,sz].
  * ndim = 2 runs the x and y passes only (sz must be 1), ndim = 3 all three passes.
- * Three launches: pass x (run scan), pass y, pass z (windowed lower envelope); sqrt fused
- * into the last one.  d_out is used in place between passes; no workspace. */
+ * Three launches: pass x (run scan), pass y, pass z (lower envelope of parabolas per run, one thread per
+ * column); sqrt fused into the last one.  d_out is used in place between passes; no workspace. */
 int b2t_edt(const void* d_labels, int label_bytes, int64_t sx, int64_t sy, int64_t sz,
             float wx, float wy, float wz, int black_border, int ndim, float* d_out, void* stream);
+/* Tuning hook, no reference counterpart: picks the column-pass kernel of b2t_edt (results are identical).
+ * algo: 0 = keep, 1 = windowed search, 2 = F-H with a local-memory stack, 3 = F-H with a shared-memory ring
+ * (default).  c > 0 selects the compiled instantiation (ring entries, min blocks per SM, rows between flushes,
+ * rows per load batch) of algo 3; an instantiation that is not compiled in makes the next b2t_edt fail. */
+int b2t_edt_config(int algo, int c, int minb, int r, int b);
 
 
 /* N1  connected components ------------------------------------------------------------------------

@@ -28,6 +28,7 @@ _SIGNATURES = {
   "b2t_last_error": [],
   "b2t_device_check": [],
   "b2t_edt": [c_vp, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_vp, c_vp],
+  "b2t_edt_config": [c_int, c_int, c_int, c_int, c_int],
 }
 _RESTYPES = {"b2t_last_error": ctypes.c_char_p}
 

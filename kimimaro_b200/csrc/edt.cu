@@ -615,11 +615,15 @@ edt_pass_col_fh3_kernel(const T* __restrict__ labels, float* __restrict__ f, int
   fh3::column<T, C, R, B>(cx, labels + base, f + base, n, cstride, w, black_border != 0, last_pass != 0, active);
 }
 
-// B2T_FH3 = "C,MINB,R,B" picks one of the compiled variants (kernel experiments); the default is the measured best.
-struct Fh3Cfg { int c, minb, r, b; };
-static Fh3Cfg fh3_cfg() {
-  static const Fh3Cfg cfg = []() {
-    Fh3Cfg c{16, 8, 32, 4};
+// Kernel selection (experiments and A/B timing; results are identical whatever is chosen).  Initialised from the
+// environment -- B2T_EDT_ALGO: 3 = shared-memory-ring F-H (default), 2 = local-memory F-H, w = windowed search;
+// B2T_FH3 = "C,MINB,R,B": one of the compiled instantiations -- and changeable at run time with b2t_edt_config().
+struct EdtCfg { int algo, c, minb, r, b; };
+static EdtCfg& edt_cfg() {
+  static EdtCfg cfg = []() {
+    EdtCfg c{3, 16, 8, 32, 4};
+    const char* a = getenv("B2T_EDT_ALGO");
+    if (a) c.algo = (a[0] == 'w') ? 1 : (a[0] == '2' ? 2 : 3);
     const char* e = getenv("B2T_FH3");
     if (e) sscanf(e, "%d,%d,%d,%d", &c.c, &c.minb, &c.r, &c.b);
     return c;
@@ -631,7 +635,7 @@ template <typename T, int NMAX>
 bool edt_launch_fh3_passes(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wy, float wz, int black_border,
                            int ndim, float* out, cudaStream_t st) {
   const dim3 gy((unsigned)b2t_ceil_div(sx, 128), (unsigned)sz), gz((unsigned)b2t_ceil_div(sx, 128), (unsigned)sy);
-  const Fh3Cfg c = fh3_cfg();
+  const EdtCfg c = edt_cfg();
 #define B2T_FH3_GO(C_, MB_, R_, B_)                                                                                    \
   if (c.c == C_ && c.minb == MB_ && c.r == R_ && c.b == B_) {                                                          \
     edt_pass_col_fh3_kernel<T, C_, NMAX, MB_, R_, B_><<<gy, 128, 0, st>>>(labels, out, (int)sy, sx, (int)sx, sx * sy, \
@@ -676,8 +680,7 @@ int edt_launch_v2(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wx,
     edt_pass_x_kernel<T><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(labels, out, (int)sx, nrows, wx, black_border);
   }
   // column passes: v3 (shared-memory ring, edt_fh3.cuh) unless B2T_EDT_ALGO=2 asks for the v2 kernel
-  static const bool use_v3 = []() { const char* e = getenv("B2T_EDT_ALGO"); return !(e && e[0] == '2'); }();
-  if (use_v3 && nmax <= fh3::kMaxN) {
+  if (edt_cfg().algo == 3 && nmax <= fh3::kMaxN) {
     bool ok;
     if (nmax <= 256) ok = edt_launch_fh3_passes<T, 256>(labels, sx, sy, sz, wy, wz, black_border, ndim, out, st);
     else if (nmax <= 512) ok = edt_launch_fh3_passes<T, 512>(labels, sx, sy, sz, wy, wz, black_border, ndim, out, st);
@@ -754,6 +757,14 @@ int edt_launch(const T* labels, int64_t sx, int64_t sy, int64_t sz, float wx, fl
 
 }  // namespace
 
+B2T_EXPORT int b2t_edt_config(int algo, int c, int minb, int r, int b) {
+  B2T_REQUIRE(algo >= 0 && algo <= 3, "b2t_edt_config: algo must be 0 (keep), 1 (windowed), 2 (local-memory F-H) or 3 (ring F-H)");
+  EdtCfg& cfg = edt_cfg();
+  if (algo) cfg.algo = algo;
+  if (c > 0) { cfg.c = c; cfg.minb = minb; cfg.r = r; cfg.b = b; }
+  return B2T_OK;
+}
+
 B2T_EXPORT int b2t_edt(const void* d_labels, int label_bytes, int64_t sx, int64_t sy, int64_t sz, float wx, float wy,
                        float wz, int black_border, int ndim, float* d_out, void* stream) {
   B2T_REQUIRE(d_labels && d_out, "b2t_edt: null pointer");
@@ -766,8 +777,7 @@ B2T_EXPORT int b2t_edt(const void* d_labels, int label_bytes, int64_t sx, int64_
   B2T_REQUIRE(sz <= 65535 && sy <= 65535, "b2t_edt: extent too large for grid.y");
   cudaStream_t st = (cudaStream_t)stream;
   black_border = black_border ? 1 : 0;
-  static const bool use_v2 = []() { const char* e = getenv("B2T_EDT_ALGO"); return !(e && e[0] == 'w'); }();
-  if (use_v2) {
+  if (edt_cfg().algo != 1) {
     bool handled = false;
     int rc = B2T_OK;
     switch (label_bytes) {

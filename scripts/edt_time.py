@@ -10,12 +10,11 @@ def main():
   reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
   _lib.require_device()
   t = time.time()
-  cache = f"/tmp/synth_{n}.npy"
-  if os.path.exists(cache):
-    vol = np.load(cache)
+  if n == 512:
+    import bench
+    vol = bench.make_volume(512)
   else:
-    vol = synthetic_tubes((n, n, n), 2124 * (n // 512) ** 3 if n >= 512 else 40, seed=0xB2002124, soma=(n >= 512), glia=(n >= 512))
-    np.save(cache, vol)
+    vol = synthetic_tubes((n, n, n), 40, seed=0xB2002124)
   print("gen", time.time() - t, "fg frac", float((vol != 0).mean()), flush=True)
   d = ops.to_device_f(vol)
   out = torch.empty(vol.size, dtype=torch.float32, device="cuda")

@@ -1,0 +1,91 @@
+"""A/B of the K1 column-pass kernels on one GPU: every compiled variant is checked for bit-identity against
+the v2 kernel's output (and the default against the CPU oracle) and timed with CUDA events, L2 flushed
+between repetitions.  Prints one JSON object per variant and writes them to gpurun_out/edt_variants.json."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+from kimimaro_b200 import ops, _lib
+
+VARIANTS = [(16, 8, 32, 4), (16, 8, 16, 4), (16, 6, 32, 4), (16, 8, 32, 8), (32, 4, 32, 4), (32, 4, 32, 8),
+            (8, 8, 16, 4), (8, 12, 16, 4)]
+
+
+def timeit(fn, flush, reps):
+  ts = []
+  for _ in range(reps):
+    flush.zero_()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+  return float(np.median(ts)), float(min(ts))
+
+
+def main():
+  reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+  check_oracle = "--oracle" in sys.argv
+  _lib.require_device()
+  lib = _lib.lib()
+  vol = bench.make_volume(512)
+  an = bench.ANISOTROPY
+  V = vol.size
+  alg = (3 * 4 + 20) * V
+  d = ops.to_device_f(vol)
+  flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+  res = []
+
+  def run(name, out):
+    ops.edt(d, vol.shape, an, False, out=out)
+    torch.cuda.synchronize()
+
+  ref = torch.empty(V, dtype=torch.float32, device="cuda")
+  _lib.check(lib.b2t_edt_config(2, 0, 0, 0, 0))
+  run("v2", ref)
+  med, mn = timeit(lambda: ops.edt(d, vol.shape, an, False, out=ref), flush, reps)
+  res.append({"variant": "v2 (local-memory F-H)", "ms_median": med, "ms_min": mn, "alg_GBps": alg / med / 1e6})
+  print(json.dumps(res[-1]), flush=True)
+  if check_oracle:
+    from oracle import edt as orc_edt
+    t = time.time()
+    o = orc_edt(vol, an, False).reshape(-1, order="F")
+    same = bool(np.array_equal(ref.cpu().numpy(), o))
+    print(json.dumps({"v2_equals_oracle": same, "oracle_s": time.time() - t}), flush=True)
+  # dense variant of the volume (every voxel labelled, like a real segmentation): background -> blocks of 24^3
+  idx = np.indices((512 // 32, 512 // 32, 512 // 32)).reshape(3, -1)
+  blk = (3000 + idx[0] + 16 * (idx[1] + 16 * idx[2])).reshape(16, 16, 16).astype(np.uint32)
+  dense = np.asfortranarray(np.where(vol != 0, vol, np.kron(blk, np.ones((32, 32, 32), np.uint32))))
+  dd = ops.to_device_f(dense)
+  ref_d = torch.empty(V, dtype=torch.float32, device="cuda")
+  ops.edt(dd, vol.shape, an, False, out=ref_d)
+  medd, mnd = timeit(lambda: ops.edt(dd, vol.shape, an, False, out=ref_d), flush, max(3, reps // 2))
+  res.append({"variant": "v2 dense", "ms_median": medd, "ms_min": mnd})
+  print(json.dumps(res[-1]), flush=True)
+
+  out = torch.empty(V, dtype=torch.float32, device="cuda")
+  for (c, mb, r, b) in VARIANTS:
+    _lib.check(lib.b2t_edt_config(3, c, mb, r, b))
+    try:
+      out.fill_(-1.0)
+      run("v3", out)
+      same = bool(torch.equal(out, ref))
+      nbad = int((out != ref).sum().item()) if not same else 0
+      med, mn = timeit(lambda: ops.edt(d, vol.shape, an, False, out=out), flush, reps)
+      out.fill_(-1.0)
+      ops.edt(dd, vol.shape, an, False, out=out)
+      torch.cuda.synchronize()
+      same_d = bool(torch.equal(out, ref_d))
+      medd, mnd = timeit(lambda: ops.edt(dd, vol.shape, an, False, out=out), flush, max(3, reps // 2))
+      rec = {"variant": f"v3 C={c} minb={mb} R={r} B={b}", "identical_to_v2": same, "mismatches": nbad,
+             "ms_median": med, "ms_min": mn, "alg_GBps": alg / med / 1e6, "dense_identical": same_d,
+             "dense_ms_median": medd}
+    except Exception as e:  # a variant that fails must not hide the others
+      rec = {"variant": f"v3 C={c} minb={mb} R={r} B={b}", "error": str(e)}
+    res.append(rec)
+    print(json.dumps(rec), flush=True)
+  os.makedirs("gpurun_out", exist_ok=True)
+  with open("gpurun_out/edt_variants.json", "w") as f:
+    json.dump(res, f, indent=1)
+
+
+main()
