@@ -55,6 +55,21 @@ int b2t_edt(const void* d_labels, int label_bytes, int64_t sx, int64_t sy, int64
  * (default).  c > 0 selects the compiled instantiation (ring entries, min blocks per SM, rows between flushes,
  * rows per load batch) of algo 3; an instantiation that is not compiled in makes the next b2t_edt fail. */
 int b2t_edt_config(int algo, int c, int minb, int r, int b);
+/* K1 with a caller-provided workspace (the form SURVEY 8b proposes): same result as b2t_edt, bit for bit.
+ * With uint32 labels and integer anisotropy the column passes run as a hybrid: a register-window min-plus
+ * stencil over every column (exact wherever the result is at most w^2 (W+1)^2, i.e. on the thin processes a
+ * connectomics volume is made of) and the envelope kernel only over the 32-row blocks of 32-column tiles
+ * the stencil flagged (the inside of blobs).  The passes ping-pong between d_out and the workspace:
+ *   workspace = [sx*sy*sz float32][per-tile 64-bit block flags of the y and z passes],
+ * b2t_edt_workspace_bytes() says how much.  Any other input, or a workspace that is null / too small, takes the
+ * b2t_edt path (d_out in place).  Launches: memset, pass x, (stencil, envelope) x 2. */
+size_t b2t_edt_workspace_bytes(int64_t sx, int64_t sy, int64_t sz);
+int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int64_t sy, int64_t sz,
+               float wx, float wy, float wz, int black_border, int ndim, float* d_out,
+               void* d_workspace, size_t workspace_bytes, void* stream);
+/* Tuning hook of the hybrid: enable = 0 sends b2t_edt_ws down the b2t_edt path; wy, wz = stencil window radius of
+ * the y / z pass, pf = rows of load prefetch, minb = min blocks per SM (wy > 0 selects a compiled instantiation). */
+int b2t_edt_config_hybrid(int enable, int wy, int wz, int pf, int minb);
 
 
 /* N1  connected components ------------------------------------------------------------------------

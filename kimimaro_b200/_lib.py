@@ -29,8 +29,11 @@ _SIGNATURES = {
   "b2t_device_check": [],
   "b2t_edt": [c_vp, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_vp, c_vp],
   "b2t_edt_config": [c_int, c_int, c_int, c_int, c_int],
+  "b2t_edt_config_hybrid": [c_int, c_int, c_int, c_int, c_int],
+  "b2t_edt_workspace_bytes": [c_i64, c_i64, c_i64],
+  "b2t_edt_ws": [c_vp, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_vp, c_vp, c_sz, c_vp],
 }
-_RESTYPES = {"b2t_last_error": ctypes.c_char_p}
+_RESTYPES = {"b2t_last_error": ctypes.c_char_p, "b2t_edt_workspace_bytes": c_sz}
 
 
 def declare(name, argtypes, restype=None):

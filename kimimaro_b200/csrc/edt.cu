@@ -600,6 +600,80 @@ struct FhDevCtx {
   __device__ __forceinline__ int wmax(int x) const { return __reduce_max_sync(0xffffffffu, x); }
 };
 
+// device context of the stencil half of the hybrid pass (no stack): arithmetic, streaming accesses, warp votes
+struct StDevCtx {
+  unsigned long long* flag;   // flag word of this warp's tile (bit b: rows [32b, 32b+32) need the envelope kernel)
+  int last_blk;
+  __device__ __forceinline__ float mul(float a, float b) const { return __fmul_rn(a, b); }
+  __device__ __forceinline__ float add(float a, float b) const { return __fadd_rn(a, b); }
+  __device__ __forceinline__ float sqrt(float a) const { return __fsqrt_rn(a); }
+  __device__ __forceinline__ float fmin(float a, float b) const { return fminf(a, b); }
+  template <typename U> __device__ __forceinline__ U ld_label(const U* p) const { return __ldcs(p); }
+  __device__ __forceinline__ float ld_f(const float* p) const { return __ldcs(p); }
+  __device__ __forceinline__ void st_f(float* p, float v) const { __stcs(p, v); }
+  __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
+  // v >= 0 (or +inf): unsigned order of the bit patterns == order of the values
+  __device__ __forceinline__ float wmaxf(float v) const {
+    return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
+  }
+  __device__ __forceinline__ void note_row(int row) {   // called by all lanes of the warp together
+    const int blk = row >> 5;
+    if (blk != last_blk) {
+      last_blk = blk;
+      if ((threadIdx.x & 31) == 0) atomicOr(flag, 1ull << blk);
+    }
+  }
+};
+
+template <typename T, int W, int PF, int MINB, bool WRITE_BG>
+__global__ void __launch_bounds__(128, MINB)
+edt_pass_col_stencil_kernel(const T* __restrict__ labels, const float* __restrict__ fin, float* __restrict__ fout, int n,
+                            int64_t cstride, int nx, int64_t ostride, float w, int black_border, int last_pass,
+                            unsigned long long* __restrict__ flags, int ntx) {
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int tile = (blockIdx.x * 128 + (threadIdx.x & ~31)) >> 5;
+  if (tile >= ntx) return;                         // the whole warp is outside the volume
+  const bool active = x < nx;
+  const int64_t base = (int64_t)blockIdx.y * ostride + (active ? x : 0);
+  StDevCtx cx{flags + (int64_t)blockIdx.y * ntx + tile, -1};
+  fh3::stencil_column<T, W, PF, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, black_border != 0,
+                                last_pass != 0, active);
+}
+
+// envelope half of the hybrid pass: only the flagged 32-row blocks of a tile, extended to complete runs
+template <typename T, int C, int NMAX, int MINB, int R, int B>
+__global__ void __launch_bounds__(128, MINB)
+edt_pass_col_fh3_range_kernel(const T* __restrict__ labels, const float* __restrict__ fin, float* __restrict__ fout, int n,
+                              int64_t cstride, int nx, int64_t ostride, float w, int black_border, int last_pass,
+                              const unsigned long long* __restrict__ flags, int ntx) {
+  __shared__ float s_plane[3][C][128];
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int tile = (blockIdx.x * 128 + (threadIdx.x & ~31)) >> 5;
+  if (tile >= ntx) return;
+  unsigned long long m = flags[(int64_t)blockIdx.y * ntx + tile];   // warp-uniform
+  if (m == 0ull) return;
+  float lv[NMAX];
+  float lh[NMAX];
+  float lz[NMAX];
+  const bool active = x < nx;
+  const int64_t base = (int64_t)blockIdx.y * ostride + (active ? x : 0);
+  FhDevCtx<C, NMAX> cx{(uint32_t)__cvta_generic_to_shared(&s_plane[0][0][threadIdx.x]), lv, lh, lz};
+  while (m) {                                      // maximal groups of consecutive flagged blocks
+    const int b0 = __ffsll((long long)m) - 1;
+    const unsigned long long rest = ~(m >> b0);    // first clear bit above b0 ends the group
+    const int len = rest ? (__ffsll((long long)rest) - 1) : 64;
+    const int b1 = b0 + len - 1;
+    m = (b1 >= 63) ? 0ull : (m & (~0ull << (b1 + 1)));
+    const int rlo = 32 * b0, rhi = min(n - 1, 32 * b1 + 31);
+    int own_lo, own_hi;
+    fh3::extend_to_runs<T>(cx, labels + base, n, cstride, active, rlo, rhi, own_lo, own_hi);
+    const int rb = cx.wmin(own_lo), re = cx.wmax(own_hi);
+    if (rb < re)
+      fh3::column_range<T, C, R, B, true>(cx, labels + base, fin + base, fout + base, n, cstride, w, black_border != 0,
+                                          last_pass != 0, active, rb, re, own_lo, own_hi);
+  }
+}
+
 template <typename T, int C, int NMAX, int MINB, int R, int B>
 __global__ void __launch_bounds__(128, MINB)
 edt_pass_col_fh3_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, int64_t cstride, int nx,
@@ -618,14 +692,16 @@ edt_pass_col_fh3_kernel(const T* __restrict__ labels, float* __restrict__ f, int
 // Kernel selection (experiments and A/B timing; results are identical whatever is chosen).  Initialised from the
 // environment -- B2T_EDT_ALGO: 3 = shared-memory-ring F-H (default), 2 = local-memory F-H, w = windowed search;
 // B2T_FH3 = "C,MINB,R,B": one of the compiled instantiations -- and changeable at run time with b2t_edt_config().
-struct EdtCfg { int algo, c, minb, r, b; };
+struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hpf, hminb; };
 static EdtCfg& edt_cfg() {
   static EdtCfg cfg = []() {
-    EdtCfg c{3, 16, 8, 32, 4};
+    EdtCfg c{3, 16, 8, 32, 4, 1, 10, 4, 4, 8};
     const char* a = getenv("B2T_EDT_ALGO");
     if (a) c.algo = (a[0] == 'w') ? 1 : (a[0] == '2' ? 2 : 3);
     const char* e = getenv("B2T_FH3");
     if (e) sscanf(e, "%d,%d,%d,%d", &c.c, &c.minb, &c.r, &c.b);
+    const char* h = getenv("B2T_EDT_HYBRID");   // "0" = off, or "WY,WZ,PF,MINB"
+    if (h) { if (h[0] == '0' && h[1] == 0) c.hybrid = 0; else sscanf(h, "%d,%d,%d,%d", &c.hwy, &c.hwz, &c.hpf, &c.hminb); }
     return c;
   }();
   return cfg;
@@ -797,3 +873,103 @@ B2T_EXPORT int b2t_edt(const void* d_labels, int label_bytes, int64_t sx, int64_
     default: b2t_set_error("b2t_edt: label_bytes must be 1, 2, 4 or 8 (got %d)", label_bytes); return B2T_ERR_ARG;
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// hybrid pass launcher (uint32 labels, integer anisotropy): stencil kernel over all columns, then the envelope
+// kernel over the blocks the stencil flagged; out of place (fin -> fout).
+// ------------------------------------------------------------------------------------------------
+static bool edt_launch_hybrid_pass(const uint32_t* labels, const float* fin, float* fout, int n, int64_t cstride, int64_t sx,
+                                   int64_t nouter, int64_t ostride, float w, int black_border, int last, int W,
+                                   bool write_bg, unsigned long long* flags, cudaStream_t st) {
+  const EdtCfg c = edt_cfg();
+  const dim3 grid((unsigned)b2t_ceil_div(sx, 128), (unsigned)nouter);
+  const int ntx = b2t_ceil_div(sx, 32);
+  bool done = false;
+#define B2T_ST_GO(W_, PF_, MB_)                                                                                         \
+  if (!done && W == W_ && c.hpf == PF_ && c.hminb == MB_) {                                                              \
+    if (write_bg)                                                                                                         \
+      edt_pass_col_stencil_kernel<uint32_t, W_, PF_, MB_, true><<<grid, 128, 0, st>>>(                                   \
+          labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, flags, ntx);                           \
+    else                                                                                                                  \
+      edt_pass_col_stencil_kernel<uint32_t, W_, PF_, MB_, false><<<grid, 128, 0, st>>>(                                  \
+          labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, flags, ntx);                           \
+    done = true;                                                                                                          \
+  }
+  B2T_ST_GO(4, 4, 8) B2T_ST_GO(6, 4, 8) B2T_ST_GO(8, 4, 8) B2T_ST_GO(10, 4, 8) B2T_ST_GO(12, 4, 8)
+  B2T_ST_GO(4, 6, 8) B2T_ST_GO(10, 6, 8) B2T_ST_GO(4, 8, 8) B2T_ST_GO(10, 8, 8)
+  B2T_ST_GO(4, 4, 12) B2T_ST_GO(10, 4, 12) B2T_ST_GO(4, 6, 12) B2T_ST_GO(10, 6, 12)
+#undef B2T_ST_GO
+  if (!done) return false;
+  done = false;
+#define B2T_FR_GO(NM_, C_, MB_, R_, B_)                                                                                   \
+  if (!done && n <= NM_ && c.c == C_ && c.minb == MB_ && c.r == R_ && c.b == B_) {                                        \
+    edt_pass_col_fh3_range_kernel<uint32_t, C_, NM_, MB_, R_, B_><<<grid, 128, 0, st>>>(labels, fin, fout, n, cstride,   \
+                                                                                       (int)sx, ostride, w, black_border, \
+                                                                                       last, flags, ntx);                 \
+    done = true;                                                                                                          \
+  }
+#define B2T_FR_ALL(C_, MB_, R_, B_) B2T_FR_GO(256, C_, MB_, R_, B_) B2T_FR_GO(512, C_, MB_, R_, B_) B2T_FR_GO(1024, C_, MB_, R_, B_) B2T_FR_GO(2048, C_, MB_, R_, B_)
+  B2T_FR_ALL(16, 8, 32, 4) B2T_FR_ALL(16, 8, 16, 4) B2T_FR_ALL(16, 6, 32, 4) B2T_FR_ALL(32, 4, 32, 4) B2T_FR_ALL(32, 4, 32, 8)
+#undef B2T_FR_ALL
+#undef B2T_FR_GO
+  return done;
+}
+
+static bool edt_is_small_int(float w) { return w >= 1.0f && w <= 2048.0f && w == rintf(w); }
+
+B2T_EXPORT size_t b2t_edt_workspace_bytes(int64_t sx, int64_t sy, int64_t sz) {
+  if (sx <= 0 || sy <= 0 || sz <= 0) return 0;
+  const size_t ntx = (size_t)b2t_ceil_div(sx, 32);
+  return (size_t)sx * sy * sz * sizeof(float) + (ntx * (size_t)sz + ntx * (size_t)sy) * sizeof(unsigned long long);
+}
+
+B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int64_t sy, int64_t sz, float wx, float wy,
+                          float wz, int black_border, int ndim, float* d_out, void* d_workspace, size_t workspace_bytes,
+                          void* stream) {
+  const EdtCfg c = edt_cfg();
+  const int64_t nmax = sy > sz ? sy : sz;
+  // The stencil is exact -- and therefore bit-identical to the envelope -- when every value a thin voxel can take is an
+  // integer below 2^24: integer anisotropy, and thresholds w^2 (W+1)^2 below 2^24.
+  const bool hybrid_ok =
+      c.hybrid && c.algo == 3 && d_labels && d_out && d_workspace && label_bytes == 4 && (ndim == 2 || ndim == 3) &&
+      (ndim == 3 || sz == 1) && sx > 0 && sy > 0 && sz > 0 && (sx % 4) == 0 && sx <= 1024 && nmax <= fh3::kMaxN &&
+      sy <= 65535 && sz <= 65535 && ((uintptr_t)d_labels % 16) == 0 && ((uintptr_t)d_out % 16) == 0 &&
+      ((uintptr_t)d_workspace % 16) == 0 && workspace_bytes >= b2t_edt_workspace_bytes(sx, sy, sz) &&
+      edt_is_small_int(wx) && edt_is_small_int(wy) && edt_is_small_int(wz) && wy * (float)(c.hwy + 1) < 4096.0f &&
+      wz * (float)(c.hwz + 1) < 4096.0f;
+  if (!hybrid_ok) return b2t_edt(d_labels, label_bytes, sx, sy, sz, wx, wy, wz, black_border, ndim, d_out, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  black_border = black_border ? 1 : 0;
+  const uint32_t* labels = (const uint32_t*)d_labels;
+  const int64_t V = sx * sy * sz;
+  const size_t ntx = (size_t)b2t_ceil_div(sx, 32);
+  float* ws_f = (float*)d_workspace;
+  unsigned long long* flags_y = (unsigned long long*)(ws_f + V);
+  unsigned long long* flags_z = flags_y + ntx * (size_t)sz;
+  B2T_CUDA_TRY(cudaMemsetAsync(flags_y, 0, (ntx * (size_t)sz + ntx * (size_t)sy) * sizeof(unsigned long long), st));
+  float* a = (ndim == 3) ? d_out : ws_f;   // x -> a, y -> b, z -> a: the result ends in d_out either way
+  float* b = (ndim == 3) ? ws_f : d_out;
+  {
+    const int64_t nrows = sy * sz;
+    const unsigned blocks = (unsigned)((nrows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    if (sx <= 128) edt_pass_x_v2_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
+    else if (sx <= 256) edt_pass_x_v2_kernel<8><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
+    else if (sx <= 512) edt_pass_x_v2_kernel<16><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
+    else edt_pass_x_v2_kernel<32><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
+  }
+  bool ok = edt_launch_hybrid_pass(labels, a, b, (int)sy, sx, sx, sz, sx * sy, wy, black_border, ndim == 2, c.hwy, true, flags_y, st);
+  if (ok && ndim == 3)
+    ok = edt_launch_hybrid_pass(labels, b, a, (int)sz, sx * sy, sx, sy, sx, wz, black_border, 1, c.hwz, false, flags_z, st);
+  B2T_REQUIRE(ok, "b2t_edt_ws: the configured stencil / envelope variant is not compiled in");
+  B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(ndim == 3 ? 5 : 3);
+  return B2T_OK;
+}
+
+B2T_EXPORT int b2t_edt_config_hybrid(int enable, int wy, int wz, int pf, int minb) {
+  EdtCfg& cfg = edt_cfg();
+  cfg.hybrid = enable ? 1 : 0;
+  if (wy > 0) { cfg.hwy = wy; cfg.hwz = wz; cfg.hpf = pf; cfg.hminb = minb; }
+  return B2T_OK;
+}
+

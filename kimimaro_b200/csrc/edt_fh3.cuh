@@ -40,13 +40,34 @@ union FI { float f; uint32_t u; };
 FH3_HD float u2f(uint32_t u) { FI x; x.u = u; return x.f; }
 FH3_HD uint32_t f2u(float f) { FI x; x.f = f; return x.u; }
 
+FH3_HD uint32_t clz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return (uint32_t)__clz((int)x);
+#else
+  return x ? (uint32_t)__builtin_clz(x) : 32u;
+#endif
+}
+FH3_HD uint32_t brev32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return __brev(x);
+#else
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+  x = ((x >> 8) & 0x00ff00ffu) | ((x & 0x00ff00ffu) << 8);
+  return (x >> 16) | (x << 16);
+#endif
+}
+
 // Context interface (device: FhDevCtx in edt.cu; host: tests/host/fh3_host.cpp):
 //   float mul(a,b), add(a,b), sub(a,b), div(a,b), sqrt(a)   round-to-nearest, never contracted
 //   float fmin(a,b)
 //   T     ld_label(const T*), float ld_f(const float*), void st_f(float*, float)
 //   shared-memory ring, slot in [0, C):  s_st(slot, v, h, z), s_st_z(slot, z), s_ld_v(slot), s_ld_h(slot), s_ld_z(slot)
 //   local-memory backing, entry index:   l_st(k, v, h, z), l_st_z(k, z), l_ld_v(k), l_ld_h(k), l_ld_z(k)
-//   int   wmin(int), wmax(int)      warp-wide reductions (identity on the host)
+//   int   wmin(int), wmax(int), float wmaxf(float >= 0), bool any(bool)   warp-wide (identity on the host)
+//   void  note_row(int row)         hybrid pass only: "this row of my tile holds a voxel the stencil could not
+//                                   finish" (sets the bit of the row's 32-row block in the tile's flag word)
 // An entry is (v, h, z): row of the parabola's apex (absolute, kept as a float: rows < 2^24 are exact and the
 // hot loop then needs no int->float conversion), its height, and the left end of its reign (run-relative).
 
@@ -69,10 +90,14 @@ FH3_HD float intersect(Ctx& cx, float fi, float ir, float h, float v, float w2) 
 #define FH3_LD_H(k_) (((k_) >= ring_lo) ? cx.s_ld_h(FH3_SLOT(k_)) : cx.l_ld_h(k_))
 #define FH3_LD_Z(k_) (((k_) >= ring_lo) ? cx.s_ld_z(FH3_SLOT(k_)) : cx.l_ld_z(k_))
 
-// C ring entries (power of two), R rows between flushes, B rows per load batch (R % B == 0)
-template <typename T, int C, int R, int B, typename Ctx>
-FH3_HD void column(Ctx& cx, const T* lp, float* fp, int n, int64_t cstride, float w, bool black_border,
-                   bool last_pass, bool active) {
+// C ring entries (power of two), R rows between flushes, B rows per load batch (R % B == 0).
+// RANGE = false: the whole column [0, n), in place (fin == fout), background rows are never touched.
+// RANGE = true (the blob half of the hybrid pass, see below): rows [rb, re) only, out of place; a lane takes
+//   part with the rows [own_lo, own_hi) (complete runs by construction); the rest of the range is treated as
+//   background.  Background is never written.
+template <typename T, int C, int R, int B, bool RANGE, typename Ctx>
+FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, int n, int64_t cstride, float w,
+                         bool black_border, bool last_pass, bool active, int rb, int re, int own_lo, int own_hi) {
   static_assert((C & (C - 1)) == 0, "ring size must be a power of two");
   static_assert(R % B == 0, "flush period must be a multiple of the batch");
   const float w2 = cx.mul(w, w);
@@ -93,30 +118,31 @@ FH3_HD void column(Ctx& cx, const T* lp, float* fp, int n, int64_t cstride, floa
   // software pipeline: labels of batch b+2 and f of batch b+1 are in flight while batch b is consumed
   T l0[B], l1[B], l2[B];
   float f0[B], f1[B];
-  const T* lq = lp;      // next label batch to load
-  const float* fq = fp;  // next f batch to load
+  const T* lq = lp + rb * cstride;        // next label batch to load
+  const float* fq = fin + rb * cstride;   // next f batch to load
   const int64_t bstride = (int64_t)B * cstride;
+#define FH3_ROW_OK(r_) (RANGE ? ((r_) >= own_lo && (r_) < own_hi) : (active && (r_) < re))
 #pragma unroll
-  for (int j = 0; j < B; j++) l1[j] = (active && j < n) ? cx.ld_label(lq + j * cstride) : T(0);
+  for (int j = 0; j < B; j++) l1[j] = FH3_ROW_OK(rb + j) ? cx.ld_label(lq + j * cstride) : T(0);
   lq += bstride;
 #pragma unroll
-  for (int j = 0; j < B; j++) l2[j] = (active && B + j < n) ? cx.ld_label(lq + j * cstride) : T(0);
+  for (int j = 0; j < B; j++) l2[j] = FH3_ROW_OK(rb + B + j) ? cx.ld_label(lq + j * cstride) : T(0);
   lq += bstride;
 #pragma unroll
   for (int j = 0; j < B; j++) f1[j] = (l1[j] != T(0)) ? cx.ld_f(fq + j * cstride) : 0.0f;
   fq += bstride;
 
-  for (int i0 = 0; i0 < n; i0 += B) {
+  for (int i0 = rb; i0 < re; i0 += B) {
 #pragma unroll
     for (int j = 0; j < B; j++) { l0[j] = l1[j]; f0[j] = f1[j]; l1[j] = l2[j]; }
 #pragma unroll
-    for (int j = 0; j < B; j++)   // l1 != 0 implies that the row exists and the thread is active
+    for (int j = 0; j < B; j++)   // l1 != 0 implies that the row exists and the thread takes part
       f1[j] = (l1[j] != T(0)) ? cx.ld_f(fq + j * cstride) : 0.0f;
     fq += bstride;
 #pragma unroll
-    for (int j = 0; j < B; j++) l2[j] = (active && i0 + 2 * B + j < n) ? cx.ld_label(lq + j * cstride) : T(0);
+    for (int j = 0; j < B; j++) l2[j] = FH3_ROW_OK(i0 + 2 * B + j) ? cx.ld_label(lq + j * cstride) : T(0);
     lq += bstride;
-    // ---------------- build: rows [i0, i0 + B); rows >= n were loaded as background ----------------
+    // ---------------- build: rows [i0, i0 + B); rows >= re were loaded as background ----------------
     const float i0f = (float)i0;
 #pragma unroll
     for (int j = 0; j < B; j++) {
@@ -162,12 +188,12 @@ FH3_HD void column(Ctx& cx, const T* lp, float* fp, int n, int64_t cstride, floa
       }
     }
     const int c1 = i0 + B;
-    if ((c1 % R) != 0 && c1 < n) continue;
+    if (((c1 - rb) % R) != 0 && c1 < re) continue;
     // ---------------- flush: write the rows of all closed runs ----------------
-    if (c1 >= n && run_lab != T(0)) {            // the column ends inside a run
-      const float tag = u2f(0x7fc00000u | ((uint32_t)n << 11) | (uint32_t)(k - k_lo + 1));
+    if (c1 >= re && run_lab != T(0)) {           // the range ends inside a run (at the array end, or at a run end)
+      const float tag = u2f(0x7fc00000u | ((uint32_t)re << 11) | (uint32_t)(k - k_lo + 1));
       if (k_lo >= ring_lo) cx.s_st_z(FH3_SLOT(k_lo), tag); else cx.l_st_z(k_lo, tag);
-      last_b = n;
+      last_b = re;
       run_lab = T(0);
     }
     const int kdone = (run_lab != T(0)) ? k_lo : k + 1;
@@ -179,7 +205,7 @@ FH3_HD void column(Ctx& cx, const T* lp, float* fp, int n, int64_t cstride, floa
       int kq = 0, kend = 0;
       float qaf = 0.0f, qbf = 0.0f, cv = 0.0f, ch = 0.0f, nz = kInf;
       bool bl = false, br = false;
-      float* fw = fp + lo * cstride;
+      float* fw = fout + lo * cstride;
       float iqf = (float)lo;
       for (int i = lo; i < hi; i++, fw += cstride, iqf += 1.0f) {
         if (i >= qb) {                           // step to the next closed run (or to "nothing left")
@@ -217,7 +243,125 @@ FH3_HD void column(Ctx& cx, const T* lp, float* fp, int n, int64_t cstride, floa
     }
     // every closed run is written: kn == kdone, and the slots below it are free for reuse
   }
+#undef FH3_ROW_OK
 }
+
+template <typename T, int C, int R, int B, typename Ctx>
+FH3_HD void column(Ctx& cx, const T* lp, float* fp, int n, int64_t cstride, float w, bool black_border,
+                   bool last_pass, bool active) {
+  column_range<T, C, R, B, false>(cx, lp, fp, fp, n, cstride, w, black_border, last_pass, active, 0, n, 0, n);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Hybrid pass (b2t_edt_ws, integer anisotropies): a register stencil everywhere, the envelope only for blobs.
+//
+// Rows farther than W from row i contribute candidates >= thr = w^2 (W+1)^2 (a parabola's value is at least
+// w^2 d^2, and so is a run-end clamp at distance d).  Hence if the minimum v over the 2W+1 rows around i is
+// at most thr, v is the exact result.  The stencil pass computes v for every voxel from a sliding register
+// window -- no stack, no division, no divergence:
+//     v[i] = min_d ( (rows i..i+d all in i's run ? f[i+d] : 0) + w^2 d^2 )
+// Masking an unreachable row to 0 turns the tap at the first foreign row into the run-end clamp w^2 d^2, and
+// the taps beyond it cannot undercut that clamp.  Run membership is one bit per row ("same label as the row
+// before") kept in a 32-bit shift register, like the foreground bits.  Rows outside the array are virtual:
+// with black_border foreign with f = 0 (tap = clamp), without it same-run with f = +inf (tap never wins).
+// The tap loop ends as soon as w^2 d^2 reaches the warp-wide maximum of v (uniform branches), so thin
+// processes cost a few taps whatever W is.  Voxels with v > thr -- the inside of blobs -- are not final: the
+// pass records which 32-row blocks of a 32-column tile hold such voxels (cx.note_row), and a second kernel
+// runs column_range<RANGE> over those blocks, extended to complete runs, and overwrites them with the exact
+// envelope values.  With integer anisotropy all values a thin voxel can take are integers below 2^24, every
+// operation is exact, and the stencil's minimum IS the envelope algorithm's value bit for bit
+// (tests/test_edt_fh3_host.py checks the composition against the oracle).
+// ---------------------------------------------------------------------------------------------------------
+
+// W window radius, PF rows of load prefetch; 2W + PF + 1 <= 32 (the shift registers).  WRITE_BG: also store the
+// zeros of the background (needed when fout is uninitialised scratch; the volume the x pass wrote has them)
+template <typename T, int W, int PF, bool WRITE_BG, typename Ctx>
+FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, int n, int64_t cstride, float w,
+                           bool black_border, bool last_pass, bool active) {
+  constexpr int S = 2 * W + 1 + PF;    // window slots: rows i-W .. i+W+PF
+  constexpr int P = W + PF;            // the centre row is P rows behind the newest loaded row
+  static_assert(S <= 32, "window exceeds the 32-bit run/foreground shift registers");
+  const float w2 = cx.mul(w, w);
+  const float kInf = u2f(0x7f800000u);
+  float cd[W + 2];
+#pragma unroll
+  for (int d = 0; d <= W + 1; d++) cd[d] = cx.mul(cx.mul(w2, (float)d), (float)d);
+  const float thr = cd[W + 1];
+  const float edge_f = black_border ? 0.0f : kInf;
+  const uint32_t edge_link = black_border ? 0u : 1u;
+  float wf[S];
+  uint32_t em = 0xffffffffu;   // bit t: rows (j-t-1, j-t) carry the same label, j = newest loaded row
+  uint32_t fm = 0u;            // bit t: row j-t is foreground
+  T lprev = T(0);
+  const T* lq = lp;            // real rows are loaded in order: running pointers instead of 64-bit multiplies
+  const float* fq = fin;
+  float* fw = fout;
+  // row j lives in slot (j + W) mod S
+#define FH3_LOAD_ROW(j_, slot_)                                                      \
+  do {                                                                               \
+    const int jj = (j_);                                                             \
+    uint32_t link, fgb = 0u;                                                         \
+    if (jj < 0) { wf[slot_] = edge_f; link = 1u; }                                   \
+    else if (jj >= n) { wf[slot_] = edge_f; link = (jj == n) ? edge_link : 1u; }     \
+    else {                                                                           \
+      const T lj = active ? cx.ld_label(lq) : T(0);                                  \
+      wf[slot_] = active ? cx.ld_f(fq) : 0.0f;                                       \
+      lq += cstride; fq += cstride;                                                  \
+      link = (jj == 0) ? edge_link : (uint32_t)(lj == lprev);                        \
+      fgb = (uint32_t)(lj != T(0));                                                  \
+      lprev = lj;                                                                    \
+    }                                                                                \
+    em = (em << 1) | link; fm = (fm << 1) | fgb;                                     \
+  } while (0)
+#pragma unroll
+  for (int t = 0; t < S - 1; t++) FH3_LOAD_ROW(t - W, t);
+  for (int base = 0; base < n; base += S) {
+#pragma unroll
+    for (int ph = 0; ph < S; ph++) {
+      const int i = base + ph;
+      if (i < n) {
+        FH3_LOAD_ROW(i + P, (ph + S - 1) % S);
+        const int c = (ph + W) % S;
+        const bool fg = ((fm >> P) & 1u) != 0u;
+        float out = 0.0f;
+        if (cx.any(fg)) {
+          float v = wf[c];
+          // rows reachable inside the run: consecutive set links below / above the centre
+          const int rr = (int)clz32(~(em << (32 - P)));          // links (i,i+1), (i+1,i+2), ...: bits P-1, P-2, ...
+          const int ll = (int)clz32(brev32(~(em >> P)));         // links (i-1,i), (i-2,i-1), ...: bits P, P+1, ...
+          float mx = cx.wmaxf(fg ? v : 0.0f);
+#pragma unroll
+          for (int d = 1; d <= W; d++) {
+            if (!(cd[d] < mx)) break;                            // uniform: no farther row can improve any lane
+            const int cp = (ph + W + d) % S, cm = (ph + W - d + S) % S;
+            const float fp_ = (d <= rr) ? wf[cp] : 0.0f;
+            const float fm_ = (d <= ll) ? wf[cm] : 0.0f;
+            v = cx.fmin(v, cx.add(cx.fmin(fp_, fm_), cd[d]));
+            mx = cx.wmaxf(fg ? v : 0.0f);
+          }
+          if (fg) out = last_pass ? cx.sqrt(v) : v;
+          if (cx.any(fg && v > thr)) cx.note_row(i);             // not final: the envelope kernel redoes this block
+        }
+        if (WRITE_BG ? active : fg) cx.st_f(fw, out);           // !WRITE_BG: fout already holds 0 on background
+        fw += cstride;
+      }
+    }
+  }
+#undef FH3_LOAD_ROW
+}
+
+// the rows a lane contributes to the envelope half: the complete runs that meet [rlo, rhi]
+template <typename T, typename Ctx>
+FH3_HD void extend_to_runs(Ctx& cx, const T* lp, int n, int64_t cstride, bool active, int rlo, int rhi, int& own_lo,
+                           int& own_hi) {
+  own_lo = rlo; own_hi = rhi + 1;
+  if (!active) { own_lo = kBig; own_hi = 0; return; }   // takes no part, and does not widen the warp's range
+  const T a = cx.ld_label(lp + rlo * cstride);
+  if (a != T(0)) while (own_lo > 0 && cx.ld_label(lp + (own_lo - 1) * cstride) == a) own_lo--;
+  const T b = cx.ld_label(lp + rhi * cstride);
+  if (b != T(0)) while (own_hi < n && cx.ld_label(lp + own_hi * cstride) == b) own_hi++;
+}
+
 #undef FH3_SLOT
 #undef FH3_LD_V
 #undef FH3_LD_H

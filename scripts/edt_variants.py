@@ -7,8 +7,7 @@ import numpy as np, torch
 import bench
 from kimimaro_b200 import ops, _lib
 
-VARIANTS = [(16, 8, 32, 4), (16, 8, 16, 4), (16, 6, 32, 4), (16, 8, 32, 8), (32, 4, 32, 4), (32, 4, 32, 8),
-            (8, 8, 16, 4), (8, 12, 16, 4)]
+VARIANTS = [(16, 8, 32, 4), (16, 6, 32, 4), (32, 4, 32, 8)]
 
 
 def timeit(fn, flush, reps):
@@ -36,13 +35,13 @@ def main():
   res = []
 
   def run(name, out):
-    ops.edt(d, vol.shape, an, False, out=out)
+    ops.edt(d, vol.shape, an, False, out=out, workspace=False)
     torch.cuda.synchronize()
 
   ref = torch.empty(V, dtype=torch.float32, device="cuda")
   _lib.check(lib.b2t_edt_config(2, 0, 0, 0, 0))
   run("v2", ref)
-  med, mn = timeit(lambda: ops.edt(d, vol.shape, an, False, out=ref), flush, reps)
+  med, mn = timeit(lambda: ops.edt(d, vol.shape, an, False, out=ref, workspace=False), flush, reps)
   res.append({"variant": "v2 (local-memory F-H)", "ms_median": med, "ms_min": mn, "alg_GBps": alg / med / 1e6})
   print(json.dumps(res[-1]), flush=True)
   if check_oracle:
@@ -57,8 +56,8 @@ def main():
   dense = np.asfortranarray(np.where(vol != 0, vol, np.kron(blk, np.ones((32, 32, 32), np.uint32))))
   dd = ops.to_device_f(dense)
   ref_d = torch.empty(V, dtype=torch.float32, device="cuda")
-  ops.edt(dd, vol.shape, an, False, out=ref_d)
-  medd, mnd = timeit(lambda: ops.edt(dd, vol.shape, an, False, out=ref_d), flush, max(3, reps // 2))
+  ops.edt(dd, vol.shape, an, False, out=ref_d, workspace=False)
+  medd, mnd = timeit(lambda: ops.edt(dd, vol.shape, an, False, out=ref_d, workspace=False), flush, max(3, reps // 2))
   res.append({"variant": "v2 dense", "ms_median": medd, "ms_min": mnd})
   print(json.dumps(res[-1]), flush=True)
 
@@ -70,12 +69,12 @@ def main():
       run("v3", out)
       same = bool(torch.equal(out, ref))
       nbad = int((out != ref).sum().item()) if not same else 0
-      med, mn = timeit(lambda: ops.edt(d, vol.shape, an, False, out=out), flush, reps)
+      med, mn = timeit(lambda: ops.edt(d, vol.shape, an, False, out=out, workspace=False), flush, reps)
       out.fill_(-1.0)
-      ops.edt(dd, vol.shape, an, False, out=out)
+      ops.edt(dd, vol.shape, an, False, out=out, workspace=False)
       torch.cuda.synchronize()
       same_d = bool(torch.equal(out, ref_d))
-      medd, mnd = timeit(lambda: ops.edt(dd, vol.shape, an, False, out=out), flush, max(3, reps // 2))
+      medd, mnd = timeit(lambda: ops.edt(dd, vol.shape, an, False, out=out, workspace=False), flush, max(3, reps // 2))
       rec = {"variant": f"v3 C={c} minb={mb} R={r} B={b}", "identical_to_v2": same, "mismatches": nbad,
              "ms_median": med, "ms_min": mn, "alg_GBps": alg / med / 1e6, "dense_identical": same_d,
              "dense_ms_median": medd}
@@ -83,6 +82,57 @@ def main():
       rec = {"variant": f"v3 C={c} minb={mb} R={r} B={b}", "error": str(e)}
     res.append(rec)
     print(json.dumps(rec), flush=True)
+  # hybrid (b2t_edt_ws): stencil windows (y, z), prefetch, min blocks per SM x envelope variant for the flagged blocks
+  if "--hybrid" in sys.argv:
+    HY = [((10, 4, 4, 8), (16, 8, 32, 4)), ((10, 4, 4, 8), (32, 4, 32, 8)), ((10, 4, 4, 8), (16, 6, 32, 4)),
+          ((8, 4, 4, 8), (16, 8, 32, 4)), ((12, 4, 4, 8), (16, 8, 32, 4)), ((10, 6, 4, 8), (16, 8, 32, 4)),
+          ((10, 4, 6, 8), (16, 8, 32, 4)), ((10, 4, 8, 8), (16, 8, 32, 4)), ((10, 4, 4, 12), (16, 8, 32, 4)),
+          ((10, 4, 6, 12), (16, 8, 32, 4))]
+    for (wy_, wz_, pf, hmb), (c, mb, r, b) in HY:
+      _lib.check(lib.b2t_edt_config(3, c, mb, r, b))
+      _lib.check(lib.b2t_edt_config_hybrid(1, wy_, wz_, pf, hmb))
+      name = f"hybrid W=({wy_},{wz_}) pf={pf} minb={hmb} + env C={c} minb={mb} R={r} B={b}"
+      try:
+        out.fill_(-1.0)
+        ops.edt(d, vol.shape, an, False, out=out, workspace=True)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(out, ref))
+        nbad = int((out != ref).sum().item()) if not same else 0
+        med, mn = timeit(lambda: ops.edt(d, vol.shape, an, False, out=out, workspace=True), flush, reps)
+        out.fill_(-1.0)
+        ops.edt(dd, vol.shape, an, False, out=out, workspace=True)
+        torch.cuda.synchronize()
+        same_d = bool(torch.equal(out, ref_d))
+        medd, mnd = timeit(lambda: ops.edt(dd, vol.shape, an, False, out=out, workspace=True), flush, max(3, reps // 2))
+        rec = {"variant": name, "identical_to_v2": same, "mismatches": nbad, "ms_median": med, "ms_min": mn,
+               "alg_GBps": alg / med / 1e6, "dense_identical": same_d, "dense_ms_median": medd}
+      except Exception as e:
+        rec = {"variant": name, "error": str(e)}
+      res.append(rec)
+      print(json.dumps(rec), flush=True)
+    # other shapes / borders / 2-D through the hybrid, against the in-place v2 kernels
+    from kimimaro_b200.datasets import synthetic_tubes
+    _lib.check(lib.b2t_edt_config_hybrid(1, 10, 4, 4, 8))
+    _lib.check(lib.b2t_edt_config(3, 16, 8, 32, 4))
+    rng = np.random.default_rng(3)
+    small = []
+    for shape, an2, bb in [((256, 192, 96), (16, 16, 40), False), ((256, 192, 96), (4, 4, 40), True),
+                           ((128, 300, 40), (1, 1, 1), False), ((64, 64, 33), (40, 32, 20), True),
+                           ((260, 257), (100, 100), True), ((512, 512), (16, 16), True)]:
+      if len(shape) == 3:
+        lab = synthetic_tubes(shape, 40, seed=int(rng.integers(1 << 30)))
+        lab[shape[0] // 4: shape[0] // 2, shape[1] // 4: shape[1] // 2, shape[2] // 4: shape[2] // 2] = 7777
+      else:
+        lab = np.zeros(shape, np.uint32, order="F"); lab[1:-1, 1:-1] = 1; lab[100:140, 50:200] = 2
+      dl = ops.to_device_f(lab)
+      _lib.check(lib.b2t_edt_config(2, 0, 0, 0, 0))
+      r2 = ops.edt(dl, lab.shape, an2, bb, workspace=False).clone()
+      _lib.check(lib.b2t_edt_config(3, 16, 8, 32, 4))
+      r3 = ops.edt(dl, lab.shape, an2, bb, workspace=True)
+      torch.cuda.synchronize()
+      small.append({"shape": list(shape), "an": list(an2), "bb": bb, "identical": bool(torch.equal(r2, r3))})
+    print(json.dumps({"hybrid_small_cases": small}), flush=True)
+    res.append({"hybrid_small_cases": small})
   os.makedirs("gpurun_out", exist_ok=True)
   with open("gpurun_out/edt_variants.json", "w") as f:
     json.dump(res, f, indent=1)

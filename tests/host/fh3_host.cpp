@@ -36,6 +36,11 @@ struct HostCtx {
   float l_ld_z(int k) { return lz[k]; }
   int wmin(int x) const { return x; }
   int wmax(int x) const { return x; }
+  float wmaxf(float x) const { return x; }
+  bool any(bool p) const { return p; }
+  // hybrid pass: 32-row blocks of the tile of 32 columns that the stencil could not finish
+  uint64_t* flag = nullptr;
+  void note_row(int row) { if (flag) *flag |= 1ull << (row >> 5); }
 };
 
 template <typename T, int C, int R, int B>
@@ -106,6 +111,80 @@ extern "C" int fh3_host_edt(const uint32_t* labels, int64_t sx, int64_t sy, int6
     case 4: run<32, 32, 8>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
     case 5: run<8, 32, 4>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
     case 6: run<16, 16, 4>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
+    default: return -2;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Hybrid pipeline (b2t_edt_ws): plain x pass, then per pass the stencil over every column (it flags the
+// 32-row blocks of each 32-column tile it could not finish) and the envelope over the flagged blocks,
+// extended to complete runs, out of place.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+template <int W, int PF, int C, int R, int B, bool WRITE_BG>
+void hybrid_pass(const uint32_t* labels, const float* fin, float* fout, int n, int64_t cstride, int64_t sx, int64_t nouter,
+                 int64_t ostride, float w, int bb, int last, int64_t ntx, long* stats) {
+  HostCtx cx;
+  cx.lv = (float*)malloc(sizeof(float) * (n + 4)); cx.lh = (float*)malloc(sizeof(float) * (n + 4)); cx.lz = (float*)malloc(sizeof(float) * (n + 4));
+  uint64_t* flags = (uint64_t*)calloc(ntx * nouter, sizeof(uint64_t));
+  for (int64_t o = 0; o < nouter; o++)
+    for (int64_t x = 0; x < sx; x++) {
+      const int64_t base = o * ostride + x;
+      cx.flag = flags + o * ntx + (x >> 5);
+      fh3::stencil_column<uint32_t, W, PF, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true);
+    }
+  cx.flag = nullptr;
+  for (int64_t o = 0; o < nouter; o++)
+    for (int64_t x = 0; x < sx; x++) {
+      const int64_t base = o * ostride + x;
+      uint64_t m = flags[o * ntx + (x >> 5)];
+      while (m) {                                   // maximal groups of consecutive flagged blocks
+        const int b0 = __builtin_ctzll(m);
+        int b1 = b0;
+        while (b1 + 1 < 64 && ((m >> (b1 + 1)) & 1)) b1++;
+        m &= (b1 == 63) ? 0ull : (~0ull << (b1 + 1));
+        const int rlo = 32 * b0, rhi = (32 * b1 + 31 < n - 1) ? 32 * b1 + 31 : n - 1;
+        int own_lo, own_hi;
+        fh3::extend_to_runs<uint32_t>(cx, labels + base, n, cstride, true, rlo, rhi, own_lo, own_hi);
+        for (int q = 0; q < 64; q++) { cx.sv[q] = NAN; cx.sh[q] = NAN; cx.sz[q] = NAN; }
+        fh3::column_range<uint32_t, C, R, B, true>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true,
+                                                   own_lo, own_hi, own_lo, own_hi);
+        if (stats) stats[3] += rhi - rlo + 1;
+      }
+    }
+  if (stats) stats[0] += cx.spills;
+  free(flags); free(cx.lv); free(cx.lh); free(cx.lz);
+}
+
+template <int WY, int WZ, int PF>
+void run_hybrid(const uint32_t* labels, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz, int bb, int ndim,
+                float* out, long* stats) {
+  const int64_t V = sx * sy * sz, ntx = (sx + 31) / 32;
+  float* ws = (float*)malloc(sizeof(float) * V);
+  for (int64_t i = 0; i < V; i++) ws[i] = NAN;           // every voxel must be written by someone
+  for (int64_t i = 0; i < V; i++) out[i] = NAN;
+  float* a = (ndim == 3) ? out : ws;     // x -> a, y -> b, z -> a
+  float* b = (ndim == 3) ? ws : out;
+  pass_x<uint32_t>(labels, a, sx, sy * sz, wx, bb);
+  hybrid_pass<WY, PF, 4, 16, 4, true>(labels, a, b, (int)sy, sx, sx, sz, sx * sy, wy, bb, ndim == 2, ntx, stats);
+  if (ndim == 3) hybrid_pass<WZ, PF, 4, 16, 4, false>(labels, b, a, (int)sz, sx * sy, sx, sy, sx, wz, bb, 1, ntx, stats);
+  free(ws);
+}
+
+}  // namespace
+
+// variant: 0 = windows (10, 4) prefetch 4, 1 = (4, 4) pf 4, 2 = (12, 8) pf 6, 3 = (2, 1) pf 1, 4 = (8, 6) pf 8
+extern "C" int fh3_host_edt_hybrid(const uint32_t* labels, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
+                                   int bb, int ndim, int variant, float* out, long* stats) {
+  if (sy > fh3::kMaxN || sz > fh3::kMaxN) return -1;
+  switch (variant) {
+    case 0: run_hybrid<10, 4, 4>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
+    case 1: run_hybrid<4, 4, 4>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
+    case 2: run_hybrid<12, 8, 6>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
+    case 3: run_hybrid<2, 1, 1>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
+    case 4: run_hybrid<8, 6, 8>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
     default: return -2;
   }
   return 0;

@@ -27,15 +27,16 @@ def fh3():
   return ctypes.CDLL(OUT)
 
 
-def _host(lib, lab, an, bb, variant):
+def _host(lib, lab, an, bb, variant, hybrid=False):
   lab = np.asarray(lab)
   ndim = lab.ndim
   L = oracle._f(lab, np.uint32)
   sx, sy, sz = L.shape
   out = np.zeros(L.shape, np.float32, order="F")
-  stats = (ctypes.c_long * 3)(0, 0, 0)
+  stats = (ctypes.c_long * 8)()
   an = tuple(float(a) for a in an) + (1.0,) * (3 - len(an))
-  rc = lib.fh3_host_edt(oracle._p(L), ctypes.c_int64(sx), ctypes.c_int64(sy), ctypes.c_int64(sz),
+  fn = lib.fh3_host_edt_hybrid if hybrid else lib.fh3_host_edt
+  rc = fn(oracle._p(L), ctypes.c_int64(sx), ctypes.c_int64(sy), ctypes.c_int64(sz),
                         ctypes.c_float(an[0]), ctypes.c_float(an[1]), ctypes.c_float(an[2]), int(bool(bb)), ndim,
                         variant, oracle._p(out), stats)
   assert rc == 0
@@ -101,3 +102,38 @@ def test_non_integer_anisotropy(fh3):
   assert np.array_equal(np.isinf(got), np.isinf(ref)) and np.array_equal(got == 0, ref == 0)
   fin = np.isfinite(ref)
   np.testing.assert_allclose(got[fin], ref[fin], rtol=1e-4, atol=0)
+
+
+# ---- hybrid pass (b2t_edt_ws): stencil everywhere + envelope on the flagged blocks, out of place ----
+# variant = stencil windows (y, z) and prefetch, see fh3_host.cpp; every voxel of the result must have been
+# written by one of the two kernels (the harness poisons both buffers with NaN)
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+def test_hybrid_bit_identical_random(fh3, variant):
+  rng = np.random.default_rng(200 + variant)
+  for trial in range(12):
+    shape = tuple(int(x) for x in rng.integers(1, 60, size=3))
+    if trial % 5 == 0:
+      shape = (int(rng.integers(1, 24)), int(rng.integers(100, 280)), int(rng.integers(1, 4)))
+    lab = _blocky(rng, shape, int(rng.integers(1, 5)), dense=(trial % 3 == 0))
+    for an in ((1, 1, 1), (16, 16, 40), (4, 4, 40), (40, 32, 20)):
+      for bb in (False, True):
+        got, _ = _host(fh3, lab, an, bb, variant, hybrid=True)
+        assert np.array_equal(got, oracle.edt(lab, an, bb)), (shape, an, bb)
+
+
+def test_hybrid_known_shapes_and_blobs(fh3):
+  plane = np.zeros((257, 257), np.uint32, order="F")
+  plane[1:-1, 1:-1] = 1
+  got, _ = _host(fh3, plane, (100, 100), True, 0, hybrid=True)
+  assert np.array_equal(got, oracle.edt(plane, (100, 100), True))
+  ones = np.ones((40, 50, 60), np.uint32, order="F")
+  for bb in (True, False):
+    got, _ = _host(fh3, ones, (1, 1, 1), bb, 0, hybrid=True)
+    assert np.array_equal(got, oracle.edt(ones, (1, 1, 1), bb))
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes((160, 128, 64), 25, seed=77)
+  lab[40:120, 20:110, 8:56] = 999
+  for variant in (0, 1):
+    got, stats = _host(fh3, lab, (16, 16, 40), False, variant, hybrid=True)
+    assert np.array_equal(got, oracle.edt(lab, (16, 16, 40), False))
+    assert stats[3] > 0                                      # the envelope kernel had flagged blocks to redo
