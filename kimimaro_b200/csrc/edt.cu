@@ -563,9 +563,9 @@ edt_pass_col_fh_kernel(const T* __restrict__ labels, float* __restrict__ f, int 
 // v3 column pass: the body is edt_fh3.cuh (shared with the CPU test harness); this is its device context.
 // Shared memory: three [C][128] float planes (apex row, height, left end): 12*C*128 bytes per CTA.
 // ================================================================================================
-template <int C, int NMAX>
+template <int C, int NMAX, int NT = 128>
 struct FhDevCtx {
-  uint32_t sbase;   // shared-state-space address of s_plane[0][0][threadIdx.x]: slot stride 512 B, plane stride C*512 B
+  uint32_t sbase;   // shared-state-space address of s_plane[0][0][threadIdx.x]: slot stride NT*4 B, plane stride C*NT*4 B
   float* lv; float* lh; float* lz;      // local-memory backing, indexed by entry
   __device__ __forceinline__ float mul(float a, float b) const { return __fmul_rn(a, b); }
   __device__ __forceinline__ float add(float a, float b) const { return __fadd_rn(a, b); }
@@ -580,11 +580,11 @@ struct FhDevCtx {
   // only ever reads what it wrote itself, and volatile asm statements keep their order
   template <int PLANE> __device__ __forceinline__ float lds(int s) const {
     float r;
-    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(r) : "r"(sbase + (uint32_t)s * 512u), "n"(PLANE * C * 512));
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(r) : "r"(sbase + (uint32_t)s * (NT * 4u)), "n"(PLANE * C * NT * 4));
     return r;
   }
   template <int PLANE> __device__ __forceinline__ void sts(int s, float v) const {
-    asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(sbase + (uint32_t)s * 512u), "n"(PLANE * C * 512), "f"(v));
+    asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(sbase + (uint32_t)s * (NT * 4u)), "n"(PLANE * C * NT * 4), "f"(v));
   }
   __device__ __forceinline__ void s_st(int s, float v, float h, float z) { sts<0>(s, v); sts<1>(s, h); sts<2>(s, z); }
   __device__ __forceinline__ void s_st_z(int s, float z) { sts<2>(s, z); }
@@ -600,16 +600,17 @@ struct FhDevCtx {
   __device__ __forceinline__ int wmax(int x) const { return __reduce_max_sync(0xffffffffu, x); }
 };
 
-// device context of the stencil half of the hybrid pass (no stack): arithmetic, streaming accesses, warp votes
+// device context of the stencil half of the hybrid pass (no stack): arithmetic, streaming accesses, warp votes,
+// and the prefetch ring: rows go global -> shared with cp.async (no register staging, so the prefetch depth is free)
+template <int RING>
 struct StDevCtx {
   unsigned long long* flag;   // flag word of this warp's tile (bit b: rows [32b, 32b+32) need the envelope kernel)
   int last_blk;
+  uint32_t rbase;             // shared-state-space address of s_ring[0][0][threadIdx.x]: slot stride 512 B, plane RING*512 B
   __device__ __forceinline__ float mul(float a, float b) const { return __fmul_rn(a, b); }
   __device__ __forceinline__ float add(float a, float b) const { return __fadd_rn(a, b); }
   __device__ __forceinline__ float sqrt(float a) const { return __fsqrt_rn(a); }
   __device__ __forceinline__ float fmin(float a, float b) const { return fminf(a, b); }
-  template <typename U> __device__ __forceinline__ U ld_label(const U* p) const { return __ldcs(p); }
-  __device__ __forceinline__ float ld_f(const float* p) const { return __ldcs(p); }
   __device__ __forceinline__ void st_f(float* p, float v) const { __stcs(p, v); }
   __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
   // v >= 0 (or +inf): unsigned order of the bit patterns == order of the values
@@ -623,33 +624,62 @@ struct StDevCtx {
       if ((threadIdx.x & 31) == 0) atomicOr(flag, 1ull << blk);
     }
   }
+  template <typename U>
+  __device__ __forceinline__ void ring_fetch(int slot, const U* lp, const float* fp, bool real, float f_virtual) const {
+    static_assert(sizeof(U) == 4, "the ring holds 32-bit labels");
+    const uint32_t a = rbase + (uint32_t)slot * 512u;
+    if (real) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(fp) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0+%1], [%2], 4;" ::"r"(a), "n"(RING * 512), "l"(lp) : "memory");
+    } else {
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(f_virtual) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  template <int N> __device__ __forceinline__ void ring_wait() const {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+  }
+  __device__ __forceinline__ float ring_f(int slot) const {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(rbase + (uint32_t)slot * 512u) : "memory");
+    return r;
+  }
+  template <typename U> __device__ __forceinline__ U ring_l(int slot) const {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(r) : "r"(rbase + (uint32_t)slot * 512u), "n"(RING * 512) : "memory");
+    return (U)r;
+  }
 };
 
-template <typename T, int W, int PF, int MINB, bool WRITE_BG>
+template <typename T, int W, int D, int MINB, bool WRITE_BG>
 __global__ void __launch_bounds__(128, MINB)
 edt_pass_col_stencil_kernel(const T* __restrict__ labels, const float* __restrict__ fin, float* __restrict__ fout, int n,
                             int64_t cstride, int nx, int64_t ostride, float w, int black_border, int last_pass,
                             unsigned long long* __restrict__ flags, int ntx) {
+  constexpr int RING = (D < 16) ? 16 : 32;
+  __shared__ float s_ring[2][RING][128];           // plane 0: f, plane 1: labels
   const int x = blockIdx.x * 128 + threadIdx.x;
   const int tile = (blockIdx.x * 128 + (threadIdx.x & ~31)) >> 5;
   if (tile >= ntx) return;                         // the whole warp is outside the volume
   const bool active = x < nx;
   const int64_t base = (int64_t)blockIdx.y * ostride + (active ? x : 0);
-  StDevCtx cx{flags + (int64_t)blockIdx.y * ntx + tile, -1};
-  fh3::stencil_column<T, W, PF, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, black_border != 0,
-                                last_pass != 0, active);
+  StDevCtx<RING> cx{flags + (int64_t)blockIdx.y * ntx + tile, -1,
+                    (uint32_t)__cvta_generic_to_shared(&s_ring[0][0][threadIdx.x])};
+  fh3::stencil_column<T, W, D, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, black_border != 0,
+                                         last_pass != 0, active);
 }
 
-// envelope half of the hybrid pass: only the flagged 32-row blocks of a tile, extended to complete runs
+// envelope half of the hybrid pass: only the flagged 32-row blocks of a tile, extended to complete runs.
+// One WARP per CTA: most tiles have nothing flagged and leave at once, and a resident CTA that is one busy warp
+// plus three finished ones would waste three quarters of its slot.
 template <typename T, int C, int NMAX, int MINB, int R, int B>
-__global__ void __launch_bounds__(128, MINB)
+__global__ void __launch_bounds__(32, MINB)
 edt_pass_col_fh3_range_kernel(const T* __restrict__ labels, const float* __restrict__ fin, float* __restrict__ fout, int n,
                               int64_t cstride, int nx, int64_t ostride, float w, int black_border, int last_pass,
                               const unsigned long long* __restrict__ flags, int ntx) {
-  __shared__ float s_plane[3][C][128];
-  const int x = blockIdx.x * 128 + threadIdx.x;
-  const int tile = (blockIdx.x * 128 + (threadIdx.x & ~31)) >> 5;
-  if (tile >= ntx) return;
+  __shared__ float s_plane[3][C][32];
+  const int tile = blockIdx.x;
+  const int x = tile * 32 + threadIdx.x;
   unsigned long long m = flags[(int64_t)blockIdx.y * ntx + tile];   // warp-uniform
   if (m == 0ull) return;
   float lv[NMAX];
@@ -657,7 +687,7 @@ edt_pass_col_fh3_range_kernel(const T* __restrict__ labels, const float* __restr
   float lz[NMAX];
   const bool active = x < nx;
   const int64_t base = (int64_t)blockIdx.y * ostride + (active ? x : 0);
-  FhDevCtx<C, NMAX> cx{(uint32_t)__cvta_generic_to_shared(&s_plane[0][0][threadIdx.x]), lv, lh, lz};
+  FhDevCtx<C, NMAX, 32> cx{(uint32_t)__cvta_generic_to_shared(&s_plane[0][0][threadIdx.x]), lv, lh, lz};
   while (m) {                                      // maximal groups of consecutive flagged blocks
     const int b0 = __ffsll((long long)m) - 1;
     const unsigned long long rest = ~(m >> b0);    // first clear bit above b0 ends the group
@@ -695,7 +725,7 @@ edt_pass_col_fh3_kernel(const T* __restrict__ labels, float* __restrict__ f, int
 struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hpf, hminb; };
 static EdtCfg& edt_cfg() {
   static EdtCfg cfg = []() {
-    EdtCfg c{3, 16, 8, 32, 4, 1, 10, 4, 4, 8};
+    EdtCfg c{3, 16, 6, 32, 4, 1, 10, 4, 12, 8};
     const char* a = getenv("B2T_EDT_ALGO");
     if (a) c.algo = (a[0] == 'w') ? 1 : (a[0] == '2' ? 2 : 3);
     const char* e = getenv("B2T_FH3");
@@ -895,17 +925,19 @@ static bool edt_launch_hybrid_pass(const uint32_t* labels, const float* fin, flo
           labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, flags, ntx);                           \
     done = true;                                                                                                          \
   }
-  B2T_ST_GO(4, 4, 8) B2T_ST_GO(6, 4, 8) B2T_ST_GO(8, 4, 8) B2T_ST_GO(10, 4, 8) B2T_ST_GO(12, 4, 8)
-  B2T_ST_GO(4, 6, 8) B2T_ST_GO(10, 6, 8) B2T_ST_GO(4, 8, 8) B2T_ST_GO(10, 8, 8)
-  B2T_ST_GO(4, 4, 12) B2T_ST_GO(10, 4, 12) B2T_ST_GO(4, 6, 12) B2T_ST_GO(10, 6, 12)
+  B2T_ST_GO(4, 12, 8) B2T_ST_GO(6, 12, 8) B2T_ST_GO(8, 12, 8) B2T_ST_GO(10, 12, 8)
+  B2T_ST_GO(4, 8, 8) B2T_ST_GO(8, 8, 8) B2T_ST_GO(10, 8, 8)
+  B2T_ST_GO(4, 15, 8) B2T_ST_GO(8, 15, 8) B2T_ST_GO(10, 15, 8)
+  B2T_ST_GO(4, 12, 12) B2T_ST_GO(8, 12, 12) B2T_ST_GO(10, 12, 12)
+  B2T_ST_GO(4, 24, 6) B2T_ST_GO(8, 24, 6) B2T_ST_GO(10, 24, 6)
 #undef B2T_ST_GO
   if (!done) return false;
   done = false;
+  const dim3 rgrid((unsigned)ntx, (unsigned)nouter);
 #define B2T_FR_GO(NM_, C_, MB_, R_, B_)                                                                                   \
   if (!done && n <= NM_ && c.c == C_ && c.minb == MB_ && c.r == R_ && c.b == B_) {                                        \
-    edt_pass_col_fh3_range_kernel<uint32_t, C_, NM_, MB_, R_, B_><<<grid, 128, 0, st>>>(labels, fin, fout, n, cstride,   \
-                                                                                       (int)sx, ostride, w, black_border, \
-                                                                                       last, flags, ntx);                 \
+    edt_pass_col_fh3_range_kernel<uint32_t, C_, NM_, 4 * MB_, R_, B_><<<rgrid, 32, 0, st>>>(                             \
+        labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, flags, ntx);                             \
     done = true;                                                                                                          \
   }
 #define B2T_FR_ALL(C_, MB_, R_, B_) B2T_FR_GO(256, C_, MB_, R_, B_) B2T_FR_GO(512, C_, MB_, R_, B_) B2T_FR_GO(1024, C_, MB_, R_, B_) B2T_FR_GO(2048, C_, MB_, R_, B_)

@@ -262,7 +262,8 @@ FH3_HD void column(Ctx& cx, const T* lp, float* fp, int n, int64_t cstride, floa
 //     v[i] = min_d ( (rows i..i+d all in i's run ? f[i+d] : 0) + w^2 d^2 )
 // Masking an unreachable row to 0 turns the tap at the first foreign row into the run-end clamp w^2 d^2, and
 // the taps beyond it cannot undercut that clamp.  Run membership is one bit per row ("same label as the row
-// before") kept in a 32-bit shift register, like the foreground bits.  Rows outside the array are virtual:
+// before") kept in a 32-bit shift register, like the foreground bits; the clamps inside the window follow from
+// those bits alone and bound the tap loop before a single tap is evaluated.  Rows outside the array are virtual:
 // with black_border foreign with f = 0 (tap = clamp), without it same-run with f = +inf (tap never wins).
 // The tap loop ends as soon as w^2 d^2 reaches the warp-wide maximum of v (uniform branches), so thin
 // processes cost a few taps whatever W is.  Voxels with v > thr -- the inside of blobs -- are not final: the
@@ -273,14 +274,19 @@ FH3_HD void column(Ctx& cx, const T* lp, float* fp, int n, int64_t cstride, floa
 // (tests/test_edt_fh3_host.py checks the composition against the oracle).
 // ---------------------------------------------------------------------------------------------------------
 
-// W window radius, PF rows of load prefetch; 2W + PF + 1 <= 32 (the shift registers).  WRITE_BG: also store the
-// zeros of the background (needed when fout is uninitialised scratch; the volume the x pass wrote has them)
-template <typename T, int W, int PF, bool WRITE_BG, typename Ctx>
+// W window radius (taps), D rows of load prefetch.  Rows travel global -> shared-memory ring (cx.ring_fetch:
+// cp.async on the device, so the prefetch depth costs no registers) -> register window of 2W+1 rows, static
+// register indices by unrolling the row loop 2W+1 times.  WRITE_BG: also store the zeros of the background
+// (needed when fout is uninitialised scratch; the volume the x pass wrote already has them).
+// Ring interface of the context: ring_fetch(slot, lp, fp, real, f_virtual) starts the copy of one row (label and f;
+// a virtual row just stores f_virtual) and closes a group; ring_wait<N>() returns when at most N groups are still
+// in flight; ring_f(slot) / ring_l<T>(slot) read a landed row.
+template <typename T, int W, int D, bool WRITE_BG, typename Ctx>
 FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, int n, int64_t cstride, float w,
                            bool black_border, bool last_pass, bool active) {
-  constexpr int S = 2 * W + 1 + PF;    // window slots: rows i-W .. i+W+PF
-  constexpr int P = W + PF;            // the centre row is P rows behind the newest loaded row
-  static_assert(S <= 32, "window exceeds the 32-bit run/foreground shift registers");
+  constexpr int S = 2 * W + 1;         // register window: rows i-W .. i+W
+  constexpr int RING = (D < 16) ? 16 : 32;   // shared-memory ring slots (rows i+W+1 .. i+W+D in flight or landed)
+  static_assert(D >= 1 && D < RING, "prefetch depth must fit the ring");
   const float w2 = cx.mul(w, w);
   const float kInf = u2f(0x7f800000u);
   float cd[W + 2];
@@ -290,46 +296,65 @@ FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, 
   const float edge_f = black_border ? 0.0f : kInf;
   const uint32_t edge_link = black_border ? 0u : 1u;
   float wf[S];
-  uint32_t em = 0xffffffffu;   // bit t: rows (j-t-1, j-t) carry the same label, j = newest loaded row
+  uint32_t em = 0xffffffffu;   // bit t: rows (j-t-1, j-t) carry the same label, j = newest row of the window
   uint32_t fm = 0u;            // bit t: row j-t is foreground
   T lprev = T(0);
-  const T* lq = lp;            // real rows are loaded in order: running pointers instead of 64-bit multiplies
+  const T* lq = lp;            // rows are fetched in order: running pointers instead of 64-bit multiplies
   const float* fq = fin;
   float* fw = fout;
-  // row j lives in slot (j + W) mod S
-#define FH3_LOAD_ROW(j_, slot_)                                                      \
+  int jf = -W;                 // next row to fetch into the ring
+  int ja = -W;                 // next row to admit into the register window
+#define FH3_FETCH()                                                                  \
   do {                                                                               \
-    const int jj = (j_);                                                             \
-    uint32_t link, fgb = 0u;                                                         \
-    if (jj < 0) { wf[slot_] = edge_f; link = 1u; }                                   \
-    else if (jj >= n) { wf[slot_] = edge_f; link = (jj == n) ? edge_link : 1u; }     \
-    else {                                                                           \
-      const T lj = active ? cx.ld_label(lq) : T(0);                                  \
-      wf[slot_] = active ? cx.ld_f(fq) : 0.0f;                                       \
-      lq += cstride; fq += cstride;                                                  \
-      link = (jj == 0) ? edge_link : (uint32_t)(lj == lprev);                        \
+    const bool real = jf >= 0 && jf < n;                                             \
+    cx.ring_fetch(jf & (RING - 1), lq, fq, real && active, (real ? 0.0f : edge_f));  \
+    if (real) { lq += cstride; fq += cstride; }                                      \
+    jf++;                                                                            \
+  } while (0)
+  // admit row ja (landed in the ring) into window slot slot_: its f, its run link and foreground bit
+#define FH3_ADMIT(slot_)                                                             \
+  do {                                                                               \
+    uint32_t link = 1u, fgb = 0u;                                                    \
+    wf[slot_] = cx.ring_f(ja & (RING - 1));                                          \
+    if (ja >= 0 && ja < n) {                                                         \
+      const T lj = active ? cx.template ring_l<T>(ja & (RING - 1)) : T(0);           \
+      link = (ja == 0) ? edge_link : (uint32_t)(lj == lprev);                        \
       fgb = (uint32_t)(lj != T(0));                                                  \
       lprev = lj;                                                                    \
+    } else if (ja == n) {                                                            \
+      link = edge_link;                                                              \
     }                                                                                \
     em = (em << 1) | link; fm = (fm << 1) | fgb;                                     \
+    ja++;                                                                            \
   } while (0)
+  // prologue: D rows in flight, then the window rows -W .. W-1 (row j -> window slot (j + W) mod S)
+  for (int t = 0; t < D; t++) FH3_FETCH();
 #pragma unroll
-  for (int t = 0; t < S - 1; t++) FH3_LOAD_ROW(t - W, t);
+  for (int t = 0; t < S - 1; t++) {
+    FH3_FETCH();
+    cx.template ring_wait<D>();
+    FH3_ADMIT(t);
+  }
   for (int base = 0; base < n; base += S) {
 #pragma unroll
     for (int ph = 0; ph < S; ph++) {
       const int i = base + ph;
       if (i < n) {
-        FH3_LOAD_ROW(i + P, (ph + S - 1) % S);
+        FH3_FETCH();                                             // row i + W + D
+        cx.template ring_wait<D>();                              // row i + W has landed
+        FH3_ADMIT((ph + S - 1) % S);                             // ... and replaces row i - W - 1
         const int c = (ph + W) % S;
-        const bool fg = ((fm >> P) & 1u) != 0u;
+        const bool fg = ((fm >> W) & 1u) != 0u;
         float out = 0.0f;
         if (cx.any(fg)) {
           float v = wf[c];
-          // rows reachable inside the run: consecutive set links below / above the centre
-          const int rr = (int)clz32(~(em << (32 - P)));          // links (i,i+1), (i+1,i+2), ...: bits P-1, P-2, ...
-          const int ll = (int)clz32(brev32(~(em >> P)));         // links (i-1,i), (i-2,i-1), ...: bits P, P+1, ...
-          float mx = cx.wmaxf(fg ? v : 0.0f);
+          // rows reachable inside the run: consecutive set links above / below the centre
+          const int rr = (int)clz32(~(em << (32 - W)));          // links (i,i+1), (i+1,i+2), ...: bits W-1, W-2, ...
+          const int ll = (int)clz32(brev32(~(em >> W)));         // links (i-1,i), (i-2,i-1), ...: bits W, W+1, ...
+          // the run-end clamps inside the window are known from the links alone: a tight bound for the tap loop
+          if (rr < W) { const float e = (float)(rr + 1); v = cx.fmin(v, cx.mul(cx.mul(w2, e), e)); }
+          if (ll < W) { const float e = (float)(ll + 1); v = cx.fmin(v, cx.mul(cx.mul(w2, e), e)); }
+          const float mx = cx.wmaxf(fg ? v : 0.0f);
 #pragma unroll
           for (int d = 1; d <= W; d++) {
             if (!(cd[d] < mx)) break;                            // uniform: no farther row can improve any lane
@@ -337,17 +362,18 @@ FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, 
             const float fp_ = (d <= rr) ? wf[cp] : 0.0f;
             const float fm_ = (d <= ll) ? wf[cm] : 0.0f;
             v = cx.fmin(v, cx.add(cx.fmin(fp_, fm_), cd[d]));
-            mx = cx.wmaxf(fg ? v : 0.0f);
           }
           if (fg) out = last_pass ? cx.sqrt(v) : v;
           if (cx.any(fg && v > thr)) cx.note_row(i);             // not final: the envelope kernel redoes this block
         }
-        if (WRITE_BG ? active : fg) cx.st_f(fw, out);           // !WRITE_BG: fout already holds 0 on background
+        if (WRITE_BG ? active : fg) cx.st_f(fw, out);            // !WRITE_BG: fout already holds 0 on background
         fw += cstride;
       }
     }
   }
-#undef FH3_LOAD_ROW
+  cx.template ring_wait<0>();
+#undef FH3_FETCH
+#undef FH3_ADMIT
 }
 
 // the rows a lane contributes to the envelope half: the complete runs that meet [rlo, rhi]

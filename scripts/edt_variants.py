@@ -7,7 +7,7 @@ import numpy as np, torch
 import bench
 from kimimaro_b200 import ops, _lib
 
-VARIANTS = [(16, 8, 32, 4), (16, 6, 32, 4), (32, 4, 32, 8)]
+VARIANTS = [(16, 6, 32, 4)]
 
 
 def timeit(fn, flush, reps):
@@ -84,10 +84,10 @@ def main():
     print(json.dumps(rec), flush=True)
   # hybrid (b2t_edt_ws): stencil windows (y, z), prefetch, min blocks per SM x envelope variant for the flagged blocks
   if "--hybrid" in sys.argv:
-    HY = [((10, 4, 4, 8), (16, 8, 32, 4)), ((10, 4, 4, 8), (32, 4, 32, 8)), ((10, 4, 4, 8), (16, 6, 32, 4)),
-          ((8, 4, 4, 8), (16, 8, 32, 4)), ((12, 4, 4, 8), (16, 8, 32, 4)), ((10, 6, 4, 8), (16, 8, 32, 4)),
-          ((10, 4, 6, 8), (16, 8, 32, 4)), ((10, 4, 8, 8), (16, 8, 32, 4)), ((10, 4, 4, 12), (16, 8, 32, 4)),
-          ((10, 4, 6, 12), (16, 8, 32, 4))]
+    HY = [((10, 4, 12, 8), (16, 6, 32, 4)), ((8, 4, 12, 8), (16, 6, 32, 4)), ((6, 4, 12, 8), (16, 6, 32, 4)),
+          ((10, 4, 12, 8), (16, 8, 32, 4)), ((10, 4, 12, 8), (32, 4, 32, 8)), ((8, 4, 8, 8), (16, 6, 32, 4)),
+          ((8, 4, 15, 8), (16, 6, 32, 4)), ((10, 4, 15, 8), (16, 6, 32, 4)), ((8, 4, 12, 12), (16, 6, 32, 4)),
+          ((8, 4, 24, 6), (16, 6, 32, 4)), ((10, 6, 12, 8), (16, 6, 32, 4)), ((8, 8, 12, 8), (16, 6, 32, 4))]
     for (wy_, wz_, pf, hmb), (c, mb, r, b) in HY:
       _lib.check(lib.b2t_edt_config(3, c, mb, r, b))
       _lib.check(lib.b2t_edt_config_hybrid(1, wy_, wz_, pf, hmb))
@@ -112,8 +112,8 @@ def main():
       print(json.dumps(rec), flush=True)
     # other shapes / borders / 2-D through the hybrid, against the in-place v2 kernels
     from kimimaro_b200.datasets import synthetic_tubes
-    _lib.check(lib.b2t_edt_config_hybrid(1, 10, 4, 4, 8))
-    _lib.check(lib.b2t_edt_config(3, 16, 8, 32, 4))
+    _lib.check(lib.b2t_edt_config_hybrid(1, 10, 4, 12, 8))
+    _lib.check(lib.b2t_edt_config(3, 16, 6, 32, 4))
     rng = np.random.default_rng(3)
     small = []
     for shape, an2, bb in [((256, 192, 96), (16, 16, 40), False), ((256, 192, 96), (4, 4, 40), True),
@@ -127,7 +127,7 @@ def main():
       dl = ops.to_device_f(lab)
       _lib.check(lib.b2t_edt_config(2, 0, 0, 0, 0))
       r2 = ops.edt(dl, lab.shape, an2, bb, workspace=False).clone()
-      _lib.check(lib.b2t_edt_config(3, 16, 8, 32, 4))
+      _lib.check(lib.b2t_edt_config(3, 16, 6, 32, 4))
       r3 = ops.edt(dl, lab.shape, an2, bb, workspace=True)
       torch.cuda.synchronize()
       small.append({"shape": list(shape), "an": list(an2), "bb": bb, "identical": bool(torch.equal(r2, r3))})

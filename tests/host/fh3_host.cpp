@@ -39,6 +39,14 @@ struct HostCtx {
   float wmaxf(float x) const { return x; }
   bool any(bool p) const { return p; }
   // hybrid pass: 32-row blocks of the tile of 32 columns that the stencil could not finish
+  // prefetch ring of the stencil (cp.async on the device): copies complete immediately here
+  float rf[32]; uint32_t rl[32];
+  template <typename T> void ring_fetch(int slot, const T* lp, const float* fp, bool real, float f_virtual) {
+    if (real) { rl[slot] = (uint32_t)*lp; rf[slot] = *fp; } else { rl[slot] = 0xdeadbeefu; rf[slot] = f_virtual; }
+  }
+  template <int N> void ring_wait() const {}
+  float ring_f(int slot) const { return rf[slot]; }
+  template <typename T> T ring_l(int slot) const { return (T)rl[slot]; }
   uint64_t* flag = nullptr;
   void note_row(int row) { if (flag) *flag |= 1ull << (row >> 5); }
 };
@@ -175,16 +183,16 @@ void run_hybrid(const uint32_t* labels, int64_t sx, int64_t sy, int64_t sz, floa
 
 }  // namespace
 
-// variant: 0 = windows (10, 4) prefetch 4, 1 = (4, 4) pf 4, 2 = (12, 8) pf 6, 3 = (2, 1) pf 1, 4 = (8, 6) pf 8
+// variant: 0 = windows (10, 4) prefetch 12, 1 = (4, 4) pf 4, 2 = (12, 8) pf 6, 3 = (2, 1) pf 1, 4 = (8, 6) pf 31
 extern "C" int fh3_host_edt_hybrid(const uint32_t* labels, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
                                    int bb, int ndim, int variant, float* out, long* stats) {
   if (sy > fh3::kMaxN || sz > fh3::kMaxN) return -1;
   switch (variant) {
-    case 0: run_hybrid<10, 4, 4>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
+    case 0: run_hybrid<10, 4, 12>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
     case 1: run_hybrid<4, 4, 4>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
     case 2: run_hybrid<12, 8, 6>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
     case 3: run_hybrid<2, 1, 1>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
-    case 4: run_hybrid<8, 6, 8>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
+    case 4: run_hybrid<8, 6, 31>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
     default: return -2;
   }
   return 0;
