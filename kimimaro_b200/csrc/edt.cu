@@ -624,29 +624,27 @@ struct StDevCtx {
       if ((threadIdx.x & 31) == 0) atomicOr(flag, 1ull << blk);
     }
   }
-  template <typename U>
-  __device__ __forceinline__ void ring_fetch(int slot, const U* lp, const float* fp, bool real, float f_virtual) const {
+  template <typename U> __device__ __forceinline__ void ring_fetch(int off, const U* lp, const float* fp) const {
     static_assert(sizeof(U) == 4, "the ring holds 32-bit labels");
-    const uint32_t a = rbase + (uint32_t)slot * 512u;
-    if (real) {
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(fp) : "memory");
-      asm volatile("cp.async.ca.shared.global [%0+%1], [%2], 4;" ::"r"(a), "n"(RING * 512), "l"(lp) : "memory");
-    } else {
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(f_virtual) : "memory");
-    }
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rbase + (uint32_t)off), "l"(fp) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0+%1], [%2], 4;" ::"r"(rbase + (uint32_t)off), "n"(RING * 512), "l"(lp) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  __device__ __forceinline__ void ring_put(int off, float f) const {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(rbase + (uint32_t)off), "f"(f) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   template <int N> __device__ __forceinline__ void ring_wait() const {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
   }
-  __device__ __forceinline__ float ring_f(int slot) const {
+  __device__ __forceinline__ float ring_f(int off) const {
     float r;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(rbase + (uint32_t)slot * 512u) : "memory");
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(rbase + (uint32_t)off) : "memory");
     return r;
   }
-  template <typename U> __device__ __forceinline__ U ring_l(int slot) const {
+  template <typename U> __device__ __forceinline__ U ring_l(int off) const {
     uint32_t r;
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(r) : "r"(rbase + (uint32_t)slot * 512u), "n"(RING * 512) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(r) : "r"(rbase + (uint32_t)off), "n"(RING * 512) : "memory");
     return (U)r;
   }
 };
@@ -662,7 +660,7 @@ edt_pass_col_stencil_kernel(const T* __restrict__ labels, const float* __restric
   const int tile = (blockIdx.x * 128 + (threadIdx.x & ~31)) >> 5;
   if (tile >= ntx) return;                         // the whole warp is outside the volume
   const bool active = x < nx;
-  const int64_t base = (int64_t)blockIdx.y * ostride + (active ? x : 0);
+  const int64_t base = (int64_t)blockIdx.y * ostride + (active ? x : nx - 1);   // a lane outside shadows the last column
   StDevCtx<RING> cx{flags + (int64_t)blockIdx.y * ntx + tile, -1,
                     (uint32_t)__cvta_generic_to_shared(&s_ring[0][0][threadIdx.x])};
   fh3::stencil_column<T, W, D, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, black_border != 0,

@@ -278,14 +278,21 @@ FH3_HD void column(Ctx& cx, const T* lp, float* fp, int n, int64_t cstride, floa
 // cp.async on the device, so the prefetch depth costs no registers) -> register window of 2W+1 rows, static
 // register indices by unrolling the row loop 2W+1 times.  WRITE_BG: also store the zeros of the background
 // (needed when fout is uninitialised scratch; the volume the x pass wrote already has them).
-// Ring interface of the context: ring_fetch(slot, lp, fp, real, f_virtual) starts the copy of one row (label and f;
-// a virtual row just stores f_virtual) and closes a group; ring_wait<N>() returns when at most N groups are still
-// in flight; ring_f(slot) / ring_l<T>(slot) read a landed row.
+// Ring interface of the context (slots are addressed by byte offset, kRingSlotBytes apart):
+//   ring_fetch(off, lp, fp) starts the copy of one real row (label and f) and closes a group;
+//   ring_put(off, f) stores a virtual row's f and closes an (empty) group;
+//   ring_wait<N>() returns when at most N groups are still in flight; ring_f(off) / ring_l<T>(off) read a landed row.
+// Foreground is recognised by f > 0: the x pass gives every foreground voxel at least wx^2 and the passes keep it
+// positive, background is exactly 0.  A lane outside the volume shadows the last column of its tile (the kernel
+// points it there) and merely does not store.
+constexpr int kRingSlotBytes = 512;
+
 template <typename T, int W, int D, bool WRITE_BG, typename Ctx>
 FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, int n, int64_t cstride, float w,
                            bool black_border, bool last_pass, bool active) {
   constexpr int S = 2 * W + 1;         // register window: rows i-W .. i+W
   constexpr int RING = (D < 16) ? 16 : 32;   // shared-memory ring slots (rows i+W+1 .. i+W+D in flight or landed)
+  constexpr int RMASK = RING * kRingSlotBytes - 1;
   static_assert(D >= 1 && D < RING, "prefetch depth must fit the ring");
   const float w2 = cx.mul(w, w);
   const float kInf = u2f(0x7f800000u);
@@ -297,35 +304,75 @@ FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, 
   const uint32_t edge_link = black_border ? 0u : 1u;
   float wf[S];
   uint32_t em = 0xffffffffu;   // bit t: rows (j-t-1, j-t) carry the same label, j = newest row of the window
-  uint32_t fm = 0u;            // bit t: row j-t is foreground
   T lprev = T(0);
   const T* lq = lp;            // rows are fetched in order: running pointers instead of 64-bit multiplies
   const float* fq = fin;
   float* fw = fout;
-  int jf = -W;                 // next row to fetch into the ring
-  int ja = -W;                 // next row to admit into the register window
+  int jf = -W, ja = -W;        // next row to fetch into the ring / to admit into the register window
+  int fo = 0, ao = 0;          // their ring offsets
+  // generic fetch / admit: rows outside the array are virtual
 #define FH3_FETCH()                                                                  \
   do {                                                                               \
-    const bool real = jf >= 0 && jf < n;                                             \
-    cx.ring_fetch(jf & (RING - 1), lq, fq, real && active, (real ? 0.0f : edge_f));  \
-    if (real) { lq += cstride; fq += cstride; }                                      \
-    jf++;                                                                            \
+    if (jf >= 0 && jf < n) { cx.ring_fetch(fo, lq, fq); lq += cstride; fq += cstride; } \
+    else cx.ring_put(fo, edge_f);                                                    \
+    fo = (fo + kRingSlotBytes) & RMASK; jf++;                                        \
   } while (0)
-  // admit row ja (landed in the ring) into window slot slot_: its f, its run link and foreground bit
 #define FH3_ADMIT(slot_)                                                             \
   do {                                                                               \
-    uint32_t link = 1u, fgb = 0u;                                                    \
-    wf[slot_] = cx.ring_f(ja & (RING - 1));                                          \
+    uint32_t link = 1u;                                                              \
+    wf[slot_] = cx.ring_f(ao);                                                       \
     if (ja >= 0 && ja < n) {                                                         \
-      const T lj = active ? cx.template ring_l<T>(ja & (RING - 1)) : T(0);           \
+      const T lj = cx.template ring_l<T>(ao);                                        \
       link = (ja == 0) ? edge_link : (uint32_t)(lj == lprev);                        \
-      fgb = (uint32_t)(lj != T(0));                                                  \
       lprev = lj;                                                                    \
     } else if (ja == n) {                                                            \
       link = edge_link;                                                              \
     }                                                                                \
-    em = (em << 1) | link; fm = (fm << 1) | fgb;                                     \
-    ja++;                                                                            \
+    em = (em << 1) | link;                                                           \
+    ao = (ao + kRingSlotBytes) & RMASK; ja++;                                        \
+  } while (0)
+  // steady state: the fetched row i+W+D and the admitted row i+W are real rows, and not the first one
+#define FH3_FETCH_STEADY()                                                           \
+  do {                                                                               \
+    cx.ring_fetch(fo, lq, fq); lq += cstride; fq += cstride;                         \
+    fo = (fo + kRingSlotBytes) & RMASK; jf++;                                        \
+  } while (0)
+#define FH3_ADMIT_STEADY(slot_)                                                      \
+  do {                                                                               \
+    wf[slot_] = cx.ring_f(ao);                                                       \
+    const T lj = cx.template ring_l<T>(ao);                                          \
+    em = (em << 1) | (uint32_t)(lj == lprev);                                        \
+    lprev = lj;                                                                      \
+    ao = (ao + kRingSlotBytes) & RMASK; ja++;                                        \
+  } while (0)
+  // one row: centre i = window slot (ph + W) % S
+#define FH3_ROW(ph_)                                                                 \
+  do {                                                                               \
+    const int c = ((ph_) + W) % S;                                                   \
+    float v = wf[c];                                                                 \
+    const bool fg = v > 0.0f;                                                        \
+    float out = 0.0f;                                                                \
+    if (cx.any(fg)) {                                                                \
+      /* rows reachable inside the run: consecutive set links above / below the centre */ \
+      const int rr = (int)clz32(~(em << (32 - W)));        /* links (i,i+1), (i+1,i+2), ...: bits W-1, W-2, ... */ \
+      const int ll = (int)clz32(brev32(~(em >> W)));       /* links (i-1,i), (i-2,i-1), ...: bits W, W+1, ...   */ \
+      /* the run-end clamps inside the window follow from the links alone: a tight bound for the tap loop */ \
+      if (rr < W) { const float e = (float)(rr + 1); v = cx.fmin(v, cx.mul(cx.mul(w2, e), e)); } \
+      if (ll < W) { const float e = (float)(ll + 1); v = cx.fmin(v, cx.mul(cx.mul(w2, e), e)); } \
+      const float mx = cx.wmaxf(fg ? v : 0.0f);                                      \
+      _Pragma("unroll")                                                              \
+      for (int d = 1; d <= W; d++) {                                                 \
+        if (!(cd[d] < mx)) break;                          /* uniform: no farther row can improve any lane */ \
+        const int cp = ((ph_) + W + d) % S, cm = ((ph_) + W - d + S) % S;            \
+        const float fp_ = (d <= rr) ? wf[cp] : 0.0f;                                 \
+        const float fm_ = (d <= ll) ? wf[cm] : 0.0f;                                 \
+        v = cx.fmin(v, cx.add(cx.fmin(fp_, fm_), cd[d]));                            \
+      }                                                                              \
+      if (fg) out = last_pass ? cx.sqrt(v) : v;                                      \
+      if (cx.any(fg && v > thr)) cx.note_row(i);           /* not final: the envelope kernel redoes this block */ \
+    }                                                                                \
+    if (active && (WRITE_BG || fg)) cx.st_f(fw, out);      /* !WRITE_BG: fout already holds 0 on background */ \
+    fw += cstride;                                                                   \
   } while (0)
   // prologue: D rows in flight, then the window rows -W .. W-1 (row j -> window slot (j + W) mod S)
   for (int t = 0; t < D; t++) FH3_FETCH();
@@ -336,44 +383,34 @@ FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, 
     FH3_ADMIT(t);
   }
   for (int base = 0; base < n; base += S) {
+    if (base + S - 1 + W + D < n) {                              // every row this block touches is an ordinary one
 #pragma unroll
-    for (int ph = 0; ph < S; ph++) {
-      const int i = base + ph;
-      if (i < n) {
-        FH3_FETCH();                                             // row i + W + D
+      for (int ph = 0; ph < S; ph++) {
+        const int i = base + ph;
+        FH3_FETCH_STEADY();                                      // row i + W + D
         cx.template ring_wait<D>();                              // row i + W has landed
-        FH3_ADMIT((ph + S - 1) % S);                             // ... and replaces row i - W - 1
-        const int c = (ph + W) % S;
-        const bool fg = ((fm >> W) & 1u) != 0u;
-        float out = 0.0f;
-        if (cx.any(fg)) {
-          float v = wf[c];
-          // rows reachable inside the run: consecutive set links above / below the centre
-          const int rr = (int)clz32(~(em << (32 - W)));          // links (i,i+1), (i+1,i+2), ...: bits W-1, W-2, ...
-          const int ll = (int)clz32(brev32(~(em >> W)));         // links (i-1,i), (i-2,i-1), ...: bits W, W+1, ...
-          // the run-end clamps inside the window are known from the links alone: a tight bound for the tap loop
-          if (rr < W) { const float e = (float)(rr + 1); v = cx.fmin(v, cx.mul(cx.mul(w2, e), e)); }
-          if (ll < W) { const float e = (float)(ll + 1); v = cx.fmin(v, cx.mul(cx.mul(w2, e), e)); }
-          const float mx = cx.wmaxf(fg ? v : 0.0f);
+        FH3_ADMIT_STEADY((ph + S - 1) % S);                      // ... and replaces row i - W - 1
+        FH3_ROW(ph);
+      }
+    } else {
 #pragma unroll
-          for (int d = 1; d <= W; d++) {
-            if (!(cd[d] < mx)) break;                            // uniform: no farther row can improve any lane
-            const int cp = (ph + W + d) % S, cm = (ph + W - d + S) % S;
-            const float fp_ = (d <= rr) ? wf[cp] : 0.0f;
-            const float fm_ = (d <= ll) ? wf[cm] : 0.0f;
-            v = cx.fmin(v, cx.add(cx.fmin(fp_, fm_), cd[d]));
-          }
-          if (fg) out = last_pass ? cx.sqrt(v) : v;
-          if (cx.any(fg && v > thr)) cx.note_row(i);             // not final: the envelope kernel redoes this block
+      for (int ph = 0; ph < S; ph++) {
+        const int i = base + ph;
+        if (i < n) {
+          FH3_FETCH();
+          cx.template ring_wait<D>();
+          FH3_ADMIT((ph + S - 1) % S);
+          FH3_ROW(ph);
         }
-        if (WRITE_BG ? active : fg) cx.st_f(fw, out);            // !WRITE_BG: fout already holds 0 on background
-        fw += cstride;
       }
     }
   }
   cx.template ring_wait<0>();
 #undef FH3_FETCH
 #undef FH3_ADMIT
+#undef FH3_FETCH_STEADY
+#undef FH3_ADMIT_STEADY
+#undef FH3_ROW
 }
 
 // the rows a lane contributes to the envelope half: the complete runs that meet [rlo, rhi]

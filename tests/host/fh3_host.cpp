@@ -41,12 +41,13 @@ struct HostCtx {
   // hybrid pass: 32-row blocks of the tile of 32 columns that the stencil could not finish
   // prefetch ring of the stencil (cp.async on the device): copies complete immediately here
   float rf[32]; uint32_t rl[32];
-  template <typename T> void ring_fetch(int slot, const T* lp, const float* fp, bool real, float f_virtual) {
-    if (real) { rl[slot] = (uint32_t)*lp; rf[slot] = *fp; } else { rl[slot] = 0xdeadbeefu; rf[slot] = f_virtual; }
+  template <typename T> void ring_fetch(int off, const T* lp, const float* fp) {
+    rl[off / fh3::kRingSlotBytes] = (uint32_t)*lp; rf[off / fh3::kRingSlotBytes] = *fp;
   }
+  void ring_put(int off, float f) { rl[off / fh3::kRingSlotBytes] = 0xdeadbeefu; rf[off / fh3::kRingSlotBytes] = f; }
   template <int N> void ring_wait() const {}
-  float ring_f(int slot) const { return rf[slot]; }
-  template <typename T> T ring_l(int slot) const { return (T)rl[slot]; }
+  float ring_f(int off) const { return rf[off / fh3::kRingSlotBytes]; }
+  template <typename T> T ring_l(int off) const { return (T)rl[off / fh3::kRingSlotBytes]; }
   uint64_t* flag = nullptr;
   void note_row(int row) { if (flag) *flag |= 1ull << (row >> 5); }
 };
