@@ -67,9 +67,10 @@ size_t b2t_edt_workspace_bytes(int64_t sx, int64_t sy, int64_t sz);
 int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int64_t sy, int64_t sz,
                float wx, float wy, float wz, int black_border, int ndim, float* d_out,
                void* d_workspace, size_t workspace_bytes, void* stream);
-/* Tuning hook of the hybrid: enable = 0 sends b2t_edt_ws down the b2t_edt path; wy, wz = stencil window radius of
- * the y / z pass, pf = rows of load prefetch, minb = min blocks per SM (wy > 0 selects a compiled instantiation). */
-int b2t_edt_config_hybrid(int enable, int wy, int wz, int pf, int minb);
+/* Tuning hook of the hybrid: enable = 0 sends b2t_edt_ws down the b2t_edt path; wy, wz = tap radius of the stencil
+ * in the y / z pass, wr = radius of its register window (farther taps read the shared-memory ring), pf = rows of
+ * load prefetch, minb = min blocks per SM (wy > 0 selects a compiled instantiation). */
+int b2t_edt_config_hybrid(int enable, int wy, int wz, int wr, int pf, int minb);
 
 
 /* N1  connected components ------------------------------------------------------------------------

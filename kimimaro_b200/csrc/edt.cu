@@ -601,12 +601,11 @@ struct FhDevCtx {
 };
 
 // device context of the stencil half of the hybrid pass (no stack): arithmetic, streaming accesses, warp votes,
-// and the prefetch ring: rows go global -> shared with cp.async (no register staging, so the prefetch depth is free)
-template <int RING>
+// and the prefetch rings: rows go global -> shared with cp.async (no register staging, so the prefetch depth is free)
 struct StDevCtx {
   unsigned long long* flag;   // flag word of this warp's tile (bit b: rows [32b, 32b+32) need the envelope kernel)
   int last_blk;
-  uint32_t rbase;             // shared-state-space address of s_ring[0][0][threadIdx.x]: slot stride 512 B, plane RING*512 B
+  uint32_t fbase, lbase;      // shared-state-space addresses of s_f[0][threadIdx.x], s_l[0][threadIdx.x]; slots 512 B apart
   __device__ __forceinline__ float mul(float a, float b) const { return __fmul_rn(a, b); }
   __device__ __forceinline__ float add(float a, float b) const { return __fadd_rn(a, b); }
   __device__ __forceinline__ float sqrt(float a) const { return __fsqrt_rn(a); }
@@ -624,47 +623,48 @@ struct StDevCtx {
       if ((threadIdx.x & 31) == 0) atomicOr(flag, 1ull << blk);
     }
   }
-  template <typename U> __device__ __forceinline__ void ring_fetch(int off, const U* lp, const float* fp) const {
+  template <typename U> __device__ __forceinline__ void ring_fetch(int foff, int loff, const U* lp, const float* fp) const {
     static_assert(sizeof(U) == 4, "the ring holds 32-bit labels");
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rbase + (uint32_t)off), "l"(fp) : "memory");
-    asm volatile("cp.async.ca.shared.global [%0+%1], [%2], 4;" ::"r"(rbase + (uint32_t)off), "n"(RING * 512), "l"(lp) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(fbase + (uint32_t)foff), "l"(fp) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(lbase + (uint32_t)loff), "l"(lp) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  __device__ __forceinline__ void ring_put(int off, float f) const {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(rbase + (uint32_t)off), "f"(f) : "memory");
+  __device__ __forceinline__ void ring_put(int foff, float f) const {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(fbase + (uint32_t)foff), "f"(f) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   template <int N> __device__ __forceinline__ void ring_wait() const {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
   }
-  __device__ __forceinline__ float ring_f(int off) const {
+  __device__ __forceinline__ float ring_f(int foff) const {
     float r;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(rbase + (uint32_t)off) : "memory");
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(fbase + (uint32_t)foff) : "memory");
     return r;
   }
-  template <typename U> __device__ __forceinline__ U ring_l(int off) const {
+  template <typename U> __device__ __forceinline__ U ring_l(int loff) const {
     uint32_t r;
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(r) : "r"(rbase + (uint32_t)off), "n"(RING * 512) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(lbase + (uint32_t)loff) : "memory");
     return (U)r;
   }
 };
 
-template <typename T, int W, int D, int MINB, bool WRITE_BG>
+template <typename T, int W, int WR, int D, int MINB, bool WRITE_BG>
 __global__ void __launch_bounds__(128, MINB)
 edt_pass_col_stencil_kernel(const T* __restrict__ labels, const float* __restrict__ fin, float* __restrict__ fout, int n,
                             int64_t cstride, int nx, int64_t ostride, float w, int black_border, int last_pass,
                             unsigned long long* __restrict__ flags, int ntx) {
-  constexpr int RING = (D < 16) ? 16 : 32;
-  __shared__ float s_ring[2][RING][128];           // plane 0: f, plane 1: labels
+  static_assert(fh3::kRingSlotBytes == 128 * 4, "one ring slot = one float per thread of the CTA");
+  __shared__ float s_f[fh3::kRingF][128];
+  __shared__ uint32_t s_l[fh3::kRingL][128];
   const int x = blockIdx.x * 128 + threadIdx.x;
   const int tile = (blockIdx.x * 128 + (threadIdx.x & ~31)) >> 5;
   if (tile >= ntx) return;                         // the whole warp is outside the volume
   const bool active = x < nx;
   const int64_t base = (int64_t)blockIdx.y * ostride + (active ? x : nx - 1);   // a lane outside shadows the last column
-  StDevCtx<RING> cx{flags + (int64_t)blockIdx.y * ntx + tile, -1,
-                    (uint32_t)__cvta_generic_to_shared(&s_ring[0][0][threadIdx.x])};
-  fh3::stencil_column<T, W, D, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, black_border != 0,
-                                         last_pass != 0, active);
+  StDevCtx cx{flags + (int64_t)blockIdx.y * ntx + tile, -1, (uint32_t)__cvta_generic_to_shared(&s_f[0][threadIdx.x]),
+              (uint32_t)__cvta_generic_to_shared(&s_l[0][threadIdx.x])};
+  fh3::stencil_column<T, W, WR, D, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, black_border != 0,
+                                             last_pass != 0, active);
 }
 
 // envelope half of the hybrid pass: only the flagged 32-row blocks of a tile, extended to complete runs.
@@ -720,16 +720,16 @@ edt_pass_col_fh3_kernel(const T* __restrict__ labels, float* __restrict__ f, int
 // Kernel selection (experiments and A/B timing; results are identical whatever is chosen).  Initialised from the
 // environment -- B2T_EDT_ALGO: 3 = shared-memory-ring F-H (default), 2 = local-memory F-H, w = windowed search;
 // B2T_FH3 = "C,MINB,R,B": one of the compiled instantiations -- and changeable at run time with b2t_edt_config().
-struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hpf, hminb; };
+struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hwr, hpf, hminb; };
 static EdtCfg& edt_cfg() {
   static EdtCfg cfg = []() {
-    EdtCfg c{3, 16, 6, 32, 4, 1, 10, 4, 12, 8};
+    EdtCfg c{3, 16, 6, 32, 4, 1, 10, 4, 4, 11, 8};
     const char* a = getenv("B2T_EDT_ALGO");
     if (a) c.algo = (a[0] == 'w') ? 1 : (a[0] == '2' ? 2 : 3);
     const char* e = getenv("B2T_FH3");
     if (e) sscanf(e, "%d,%d,%d,%d", &c.c, &c.minb, &c.r, &c.b);
-    const char* h = getenv("B2T_EDT_HYBRID");   // "0" = off, or "WY,WZ,PF,MINB"
-    if (h) { if (h[0] == '0' && h[1] == 0) c.hybrid = 0; else sscanf(h, "%d,%d,%d,%d", &c.hwy, &c.hwz, &c.hpf, &c.hminb); }
+    const char* h = getenv("B2T_EDT_HYBRID");   // "0" = off, or "WY,WZ,WR,PF,MINB"
+    if (h) { if (h[0] == '0' && h[1] == 0) c.hybrid = 0; else sscanf(h, "%d,%d,%d,%d,%d", &c.hwy, &c.hwz, &c.hwr, &c.hpf, &c.hminb); }
     return c;
   }();
   return cfg;
@@ -913,21 +913,21 @@ static bool edt_launch_hybrid_pass(const uint32_t* labels, const float* fin, flo
   const dim3 grid((unsigned)b2t_ceil_div(sx, 128), (unsigned)nouter);
   const int ntx = b2t_ceil_div(sx, 32);
   bool done = false;
-#define B2T_ST_GO(W_, PF_, MB_)                                                                                         \
-  if (!done && W == W_ && c.hpf == PF_ && c.hminb == MB_) {                                                              \
+#define B2T_ST_GO(W_, WR_, PF_, MB_)                                                                                    \
+  if (!done && W == W_ && c.hwr == WR_ && c.hpf == PF_ && c.hminb == MB_) {                                              \
     if (write_bg)                                                                                                         \
-      edt_pass_col_stencil_kernel<uint32_t, W_, PF_, MB_, true><<<grid, 128, 0, st>>>(                                   \
+      edt_pass_col_stencil_kernel<uint32_t, W_, (WR_ < W_ ? WR_ : W_), PF_, MB_, true><<<grid, 128, 0, st>>>(            \
           labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, flags, ntx);                           \
     else                                                                                                                  \
-      edt_pass_col_stencil_kernel<uint32_t, W_, PF_, MB_, false><<<grid, 128, 0, st>>>(                                  \
+      edt_pass_col_stencil_kernel<uint32_t, W_, (WR_ < W_ ? WR_ : W_), PF_, MB_, false><<<grid, 128, 0, st>>>(           \
           labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, flags, ntx);                           \
     done = true;                                                                                                          \
   }
-  B2T_ST_GO(4, 12, 8) B2T_ST_GO(6, 12, 8) B2T_ST_GO(8, 12, 8) B2T_ST_GO(10, 12, 8)
-  B2T_ST_GO(4, 8, 8) B2T_ST_GO(8, 8, 8) B2T_ST_GO(10, 8, 8)
-  B2T_ST_GO(4, 15, 8) B2T_ST_GO(8, 15, 8) B2T_ST_GO(10, 15, 8)
-  B2T_ST_GO(4, 12, 12) B2T_ST_GO(8, 12, 12) B2T_ST_GO(10, 12, 12)
-  B2T_ST_GO(4, 24, 6) B2T_ST_GO(8, 24, 6) B2T_ST_GO(10, 24, 6)
+  // tap radius (4 .. 12), register-window radius, prefetch depth, min blocks per SM
+  B2T_ST_GO(4, 4, 11, 8) B2T_ST_GO(6, 4, 11, 8) B2T_ST_GO(8, 4, 11, 8) B2T_ST_GO(10, 4, 11, 8)
+  B2T_ST_GO(4, 6, 11, 8) B2T_ST_GO(6, 6, 11, 8) B2T_ST_GO(8, 6, 11, 8) B2T_ST_GO(10, 6, 11, 8)
+  B2T_ST_GO(4, 3, 11, 8) B2T_ST_GO(6, 3, 11, 8) B2T_ST_GO(8, 3, 11, 8) B2T_ST_GO(10, 3, 11, 8)
+  B2T_ST_GO(4, 4, 7, 8) B2T_ST_GO(8, 4, 7, 8) B2T_ST_GO(10, 4, 7, 8) B2T_ST_GO(12, 4, 7, 8)
 #undef B2T_ST_GO
   if (!done) return false;
   done = false;
@@ -996,10 +996,10 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
   return B2T_OK;
 }
 
-B2T_EXPORT int b2t_edt_config_hybrid(int enable, int wy, int wz, int pf, int minb) {
+B2T_EXPORT int b2t_edt_config_hybrid(int enable, int wy, int wz, int wr, int pf, int minb) {
   EdtCfg& cfg = edt_cfg();
   cfg.hybrid = enable ? 1 : 0;
-  if (wy > 0) { cfg.hwy = wy; cfg.hwz = wz; cfg.hpf = pf; cfg.hminb = minb; }
+  if (wy > 0) { cfg.hwy = wy; cfg.hwz = wz; cfg.hwr = wr; cfg.hpf = pf; cfg.hminb = minb; }
   return B2T_OK;
 }
 

@@ -274,81 +274,92 @@ FH3_HD void column(Ctx& cx, const T* lp, float* fp, int n, int64_t cstride, floa
 // (tests/test_edt_fh3_host.py checks the composition against the oracle).
 // ---------------------------------------------------------------------------------------------------------
 
-// W window radius (taps), D rows of load prefetch.  Rows travel global -> shared-memory ring (cx.ring_fetch:
-// cp.async on the device, so the prefetch depth costs no registers) -> register window of 2W+1 rows, static
-// register indices by unrolling the row loop 2W+1 times.  WRITE_BG: also store the zeros of the background
-// (needed when fout is uninitialised scratch; the volume the x pass wrote already has them).
-// Ring interface of the context (slots are addressed by byte offset, kRingSlotBytes apart):
-//   ring_fetch(off, lp, fp) starts the copy of one real row (label and f) and closes a group;
-//   ring_put(off, f) stores a virtual row's f and closes an (empty) group;
-//   ring_wait<N>() returns when at most N groups are still in flight; ring_f(off) / ring_l<T>(off) read a landed row.
+// W tap radius, WR <= W radius of the register window, D rows of load prefetch.  Rows travel global -> shared-memory
+// ring (cx.ring_fetch: cp.async on the device, so the prefetch depth costs no registers) -> register window of 2WR+1
+// rows with static register indices (the row loop is unrolled 2WR+1 times).  Taps at distance <= WR read registers;
+// the rarely needed taps at WR < d <= W (thick processes only) read the ring, which still holds those rows, in a
+// rolled loop -- that keeps the unrolled code inside the instruction cache (a 21-phase body at W = 10 ran at a
+// quarter of the issue rate).  WRITE_BG: also store the zeros of the background (needed when fout is uninitialised
+// scratch; the volume the x pass wrote already has them).
+// Ring interface of the context (f slots kRingSlotBytes apart, 32 of them; label slots likewise, 16 of them):
+//   ring_fetch(foff, loff, lp, fp) starts the copy of one real row (label and f) and closes a group;
+//   ring_put(foff, f) stores a virtual row's f and closes an (empty) group;
+//   ring_wait<N>() returns when at most N groups are still in flight; ring_f(foff) / ring_l<T>(loff) read a landed row.
 // Foreground is recognised by f > 0: the x pass gives every foreground voxel at least wx^2 and the passes keep it
 // positive, background is exactly 0.  A lane outside the volume shadows the last column of its tile (the kernel
 // points it there) and merely does not store.
 constexpr int kRingSlotBytes = 512;
+constexpr int kRingF = 32, kRingL = 16;
 
-template <typename T, int W, int D, bool WRITE_BG, typename Ctx>
+template <typename T, int W, int WR, int D, bool WRITE_BG, typename Ctx>
 FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, int n, int64_t cstride, float w,
                            bool black_border, bool last_pass, bool active) {
-  constexpr int S = 2 * W + 1;         // register window: rows i-W .. i+W
-  constexpr int RING = (D < 16) ? 16 : 32;   // shared-memory ring slots (rows i+W+1 .. i+W+D in flight or landed)
-  constexpr int RMASK = RING * kRingSlotBytes - 1;
-  static_assert(D >= 1 && D < RING, "prefetch depth must fit the ring");
+  constexpr int S = 2 * WR + 1;        // register window: rows i-WR .. i+WR
+  constexpr int FMASK = kRingF * kRingSlotBytes - 1, LMASK = kRingL * kRingSlotBytes - 1;
+  static_assert(WR >= 1 && WR <= W, "register window inside the tap radius");
+  static_assert(D >= 1 && D < kRingL, "rows in flight must fit the label ring");
+  static_assert(2 * W + D + 1 <= kRingF, "rows i-W .. i+W+D must fit the f ring");
   const float w2 = cx.mul(w, w);
   const float kInf = u2f(0x7f800000u);
-  float cd[W + 2];
+  float cd[WR + 1];
 #pragma unroll
-  for (int d = 0; d <= W + 1; d++) cd[d] = cx.mul(cx.mul(w2, (float)d), (float)d);
-  const float thr = cd[W + 1];
+  for (int d = 0; d <= WR; d++) cd[d] = cx.mul(cx.mul(w2, (float)d), (float)d);
+  const float thr = cx.mul(cx.mul(w2, (float)(W + 1)), (float)(W + 1));
   const float edge_f = black_border ? 0.0f : kInf;
   const uint32_t edge_link = black_border ? 0u : 1u;
   float wf[S];
-  uint32_t em = 0xffffffffu;   // bit t: rows (j-t-1, j-t) carry the same label, j = newest row of the window
+  uint32_t em = 0xffffffffu;   // bit t: rows (j-t-1, j-t) carry the same label, j = i + W (newest linked row)
   T lprev = T(0);
   const T* lq = lp;            // rows are fetched in order: running pointers instead of 64-bit multiplies
   const float* fq = fin;
   float* fw = fout;
-  int jf = -W, ja = -W;        // next row to fetch into the ring / to admit into the register window
-  int fo = 0, ao = 0;          // their ring offsets
-  // generic fetch / admit: rows outside the array are virtual
+  // three fronts, all advancing one row per step: fetch (row i+W+D), link (row i+W), admit (row i+WR)
+  int jf = -W, jl = -W, ja = -W;
+  int fo = 0, lo = 0;          // ring offsets of the fetch front (f ring, label ring)
+  int ko = 0;                  // label-ring offset of the link front
+  int ao = 0;                  // f-ring offset of the admit front
+  // generic steps: rows outside the array are virtual
 #define FH3_FETCH()                                                                  \
   do {                                                                               \
-    if (jf >= 0 && jf < n) { cx.ring_fetch(fo, lq, fq); lq += cstride; fq += cstride; } \
+    if (jf >= 0 && jf < n) { cx.ring_fetch(fo, lo, lq, fq); lq += cstride; fq += cstride; } \
     else cx.ring_put(fo, edge_f);                                                    \
-    fo = (fo + kRingSlotBytes) & RMASK; jf++;                                        \
+    fo = (fo + kRingSlotBytes) & FMASK; lo = (lo + kRingSlotBytes) & LMASK; jf++;    \
   } while (0)
-#define FH3_ADMIT(slot_)                                                             \
+#define FH3_LINK()                                                                   \
   do {                                                                               \
     uint32_t link = 1u;                                                              \
-    wf[slot_] = cx.ring_f(ao);                                                       \
-    if (ja >= 0 && ja < n) {                                                         \
-      const T lj = cx.template ring_l<T>(ao);                                        \
-      link = (ja == 0) ? edge_link : (uint32_t)(lj == lprev);                        \
+    if (jl >= 0 && jl < n) {                                                         \
+      const T lj = cx.template ring_l<T>(ko);                                        \
+      link = (jl == 0) ? edge_link : (uint32_t)(lj == lprev);                        \
       lprev = lj;                                                                    \
-    } else if (ja == n) {                                                            \
+    } else if (jl == n) {                                                            \
       link = edge_link;                                                              \
     }                                                                                \
     em = (em << 1) | link;                                                           \
-    ao = (ao + kRingSlotBytes) & RMASK; ja++;                                        \
+    ko = (ko + kRingSlotBytes) & LMASK; jl++;                                        \
   } while (0)
-  // steady state: the fetched row i+W+D and the admitted row i+W are real rows, and not the first one
-#define FH3_FETCH_STEADY()                                                           \
-  do {                                                                               \
-    cx.ring_fetch(fo, lq, fq); lq += cstride; fq += cstride;                         \
-    fo = (fo + kRingSlotBytes) & RMASK; jf++;                                        \
-  } while (0)
-#define FH3_ADMIT_STEADY(slot_)                                                      \
+#define FH3_ADMIT(slot_)                                                             \
   do {                                                                               \
     wf[slot_] = cx.ring_f(ao);                                                       \
-    const T lj = cx.template ring_l<T>(ao);                                          \
+    ao = (ao + kRingSlotBytes) & FMASK; ja++;                                        \
+  } while (0)
+  // steady state: the fetched row i+W+D and the linked row i+W are real rows, and not the first one
+#define FH3_FETCH_STEADY()                                                           \
+  do {                                                                               \
+    cx.ring_fetch(fo, lo, lq, fq); lq += cstride; fq += cstride;                     \
+    fo = (fo + kRingSlotBytes) & FMASK; lo = (lo + kRingSlotBytes) & LMASK; jf++;    \
+  } while (0)
+#define FH3_LINK_STEADY()                                                            \
+  do {                                                                               \
+    const T lj = cx.template ring_l<T>(ko);                                          \
     em = (em << 1) | (uint32_t)(lj == lprev);                                        \
     lprev = lj;                                                                      \
-    ao = (ao + kRingSlotBytes) & RMASK; ja++;                                        \
+    ko = (ko + kRingSlotBytes) & LMASK; jl++;                                        \
   } while (0)
-  // one row: centre i = window slot (ph + W) % S
+  // one row: centre i = window slot (ph + WR) % S; its f-ring offset is WR + 1 slots behind the admit front
 #define FH3_ROW(ph_)                                                                 \
   do {                                                                               \
-    const int c = ((ph_) + W) % S;                                                   \
+    const int c = ((ph_) + WR) % S;                                                  \
     float v = wf[c];                                                                 \
     const bool fg = v > 0.0f;                                                        \
     float out = 0.0f;                                                                \
@@ -360,13 +371,25 @@ FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, 
       if (rr < W) { const float e = (float)(rr + 1); v = cx.fmin(v, cx.mul(cx.mul(w2, e), e)); } \
       if (ll < W) { const float e = (float)(ll + 1); v = cx.fmin(v, cx.mul(cx.mul(w2, e), e)); } \
       const float mx = cx.wmaxf(fg ? v : 0.0f);                                      \
+      bool far = W > WR;                                                             \
       _Pragma("unroll")                                                              \
-      for (int d = 1; d <= W; d++) {                                                 \
-        if (!(cd[d] < mx)) break;                          /* uniform: no farther row can improve any lane */ \
-        const int cp = ((ph_) + W + d) % S, cm = ((ph_) + W - d + S) % S;            \
+      for (int d = 1; d <= WR; d++) {                                                \
+        if (!(cd[d] < mx)) { far = false; break; }         /* uniform: no farther row can improve any lane */ \
+        const int cp = ((ph_) + WR + d) % S, cm = ((ph_) + WR - d + S) % S;          \
         const float fp_ = (d <= rr) ? wf[cp] : 0.0f;                                 \
         const float fm_ = (d <= ll) ? wf[cm] : 0.0f;                                 \
         v = cx.fmin(v, cx.add(cx.fmin(fp_, fm_), cd[d]));                            \
+      }                                                                              \
+      if (W > WR && far) {                                 /* thick processes: the taps beyond the registers */ \
+        const int co = ao - (WR + 1) * kRingSlotBytes;                               \
+        _Pragma("unroll 1")                                                          \
+        for (int d = WR + 1; d <= W; d++) {                                          \
+          const float cdd = cx.mul(cx.mul(w2, (float)d), (float)d);                  \
+          if (!(cdd < mx)) break;                                                    \
+          const float fp_ = (d <= rr) ? cx.ring_f((co + d * kRingSlotBytes) & FMASK) : 0.0f; \
+          const float fm_ = (d <= ll) ? cx.ring_f((co - d * kRingSlotBytes) & FMASK) : 0.0f; \
+          v = cx.fmin(v, cx.add(cx.fmin(fp_, fm_), cdd));                            \
+        }                                                                            \
       }                                                                              \
       if (fg) out = last_pass ? cx.sqrt(v) : v;                                      \
       if (cx.any(fg && v > thr)) cx.note_row(i);           /* not final: the envelope kernel redoes this block */ \
@@ -374,42 +397,36 @@ FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, 
     if (active && (WRITE_BG || fg)) cx.st_f(fw, out);      /* !WRITE_BG: fout already holds 0 on background */ \
     fw += cstride;                                                                   \
   } while (0)
-  // prologue: D rows in flight, then the window rows -W .. W-1 (row j -> window slot (j + W) mod S)
+  // prologue: D rows in flight; the links of rows -W .. W-1; the window rows -WR .. WR-1 (row j -> slot (j + WR) mod S)
   for (int t = 0; t < D; t++) FH3_FETCH();
-#pragma unroll
-  for (int t = 0; t < S - 1; t++) {
+  for (int t = 0; t < 2 * W; t++) {
     FH3_FETCH();
     cx.template ring_wait<D>();
-    FH3_ADMIT(t);
+    FH3_LINK();
   }
+  ao = ((W - WR) * kRingSlotBytes) & FMASK; ja = -WR;      // the rows -W .. -WR-1 stay in the ring only
+#pragma unroll
+  for (int t = 0; t < S - 1; t++) FH3_ADMIT(t);
   for (int base = 0; base < n; base += S) {
-    if (base + S - 1 + W + D < n) {                              // every row this block touches is an ordinary one
+    const bool steady = base + S - 1 + W + D < n;                // every row this block touches is an ordinary one
 #pragma unroll
-      for (int ph = 0; ph < S; ph++) {
-        const int i = base + ph;
-        FH3_FETCH_STEADY();                                      // row i + W + D
-        cx.template ring_wait<D>();                              // row i + W has landed
-        FH3_ADMIT_STEADY((ph + S - 1) % S);                      // ... and replaces row i - W - 1
+    for (int ph = 0; ph < S; ph++) {
+      const int i = base + ph;
+      if (steady || i < n) {
+        // row i + W + D is fetched, row i + W (landed) is linked, row i + WR replaces row i - WR - 1 in the registers
+        if (steady) { FH3_FETCH_STEADY(); cx.template ring_wait<D>(); FH3_LINK_STEADY(); }
+        else { FH3_FETCH(); cx.template ring_wait<D>(); FH3_LINK(); }
+        FH3_ADMIT((ph + S - 1) % S);
         FH3_ROW(ph);
-      }
-    } else {
-#pragma unroll
-      for (int ph = 0; ph < S; ph++) {
-        const int i = base + ph;
-        if (i < n) {
-          FH3_FETCH();
-          cx.template ring_wait<D>();
-          FH3_ADMIT((ph + S - 1) % S);
-          FH3_ROW(ph);
-        }
       }
     }
   }
   cx.template ring_wait<0>();
 #undef FH3_FETCH
+#undef FH3_LINK
 #undef FH3_ADMIT
 #undef FH3_FETCH_STEADY
-#undef FH3_ADMIT_STEADY
+#undef FH3_LINK_STEADY
 #undef FH3_ROW
 }
 

@@ -84,14 +84,14 @@ def main():
     print(json.dumps(rec), flush=True)
   # hybrid (b2t_edt_ws): stencil windows (y, z), prefetch, min blocks per SM x envelope variant for the flagged blocks
   if "--hybrid" in sys.argv:
-    HY = [((10, 4, 12, 8), (16, 6, 32, 4)), ((8, 4, 12, 8), (16, 6, 32, 4)), ((6, 4, 12, 8), (16, 6, 32, 4)),
-          ((10, 4, 12, 8), (16, 8, 32, 4)), ((10, 4, 12, 8), (32, 4, 32, 8)), ((8, 4, 8, 8), (16, 6, 32, 4)),
-          ((8, 4, 15, 8), (16, 6, 32, 4)), ((10, 4, 15, 8), (16, 6, 32, 4)), ((8, 4, 12, 12), (16, 6, 32, 4)),
-          ((8, 4, 24, 6), (16, 6, 32, 4)), ((10, 6, 12, 8), (16, 6, 32, 4)), ((8, 8, 12, 8), (16, 6, 32, 4))]
-    for (wy_, wz_, pf, hmb), (c, mb, r, b) in HY:
+    HY = [((10, 4, 4, 11, 8), (16, 6, 32, 4)), ((8, 4, 4, 11, 8), (16, 6, 32, 4)), ((6, 4, 4, 11, 8), (16, 6, 32, 4)),
+          ((10, 4, 6, 11, 8), (16, 6, 32, 4)), ((10, 4, 3, 11, 8), (16, 6, 32, 4)), ((10, 4, 4, 7, 8), (16, 6, 32, 4)),
+          ((12, 4, 4, 7, 8), (16, 6, 32, 4)), ((10, 6, 4, 11, 8), (16, 6, 32, 4)), ((10, 4, 4, 11, 8), (32, 4, 32, 8)),
+          ((10, 4, 4, 11, 8), (16, 8, 32, 4))]
+    for (wy_, wz_, wr_, pf, hmb), (c, mb, r, b) in HY:
       _lib.check(lib.b2t_edt_config(3, c, mb, r, b))
-      _lib.check(lib.b2t_edt_config_hybrid(1, wy_, wz_, pf, hmb))
-      name = f"hybrid W=({wy_},{wz_}) pf={pf} minb={hmb} + env C={c} minb={mb} R={r} B={b}"
+      _lib.check(lib.b2t_edt_config_hybrid(1, wy_, wz_, wr_, pf, hmb))
+      name = f"hybrid W=({wy_},{wz_}) wr={wr_} pf={pf} minb={hmb} + env C={c} minb={mb} R={r} B={b}"
       try:
         out.fill_(-1.0)
         ops.edt(d, vol.shape, an, False, out=out, workspace=True)
@@ -112,7 +112,7 @@ def main():
       print(json.dumps(rec), flush=True)
     # other shapes / borders / 2-D through the hybrid, against the in-place v2 kernels
     from kimimaro_b200.datasets import synthetic_tubes
-    _lib.check(lib.b2t_edt_config_hybrid(1, 10, 4, 12, 8))
+    _lib.check(lib.b2t_edt_config_hybrid(1, 10, 4, 4, 11, 8))
     _lib.check(lib.b2t_edt_config(3, 16, 6, 32, 4))
     rng = np.random.default_rng(3)
     small = []

@@ -39,15 +39,15 @@ struct HostCtx {
   float wmaxf(float x) const { return x; }
   bool any(bool p) const { return p; }
   // hybrid pass: 32-row blocks of the tile of 32 columns that the stencil could not finish
-  // prefetch ring of the stencil (cp.async on the device): copies complete immediately here
-  float rf[32]; uint32_t rl[32];
-  template <typename T> void ring_fetch(int off, const T* lp, const float* fp) {
-    rl[off / fh3::kRingSlotBytes] = (uint32_t)*lp; rf[off / fh3::kRingSlotBytes] = *fp;
+  // prefetch rings of the stencil (cp.async on the device): copies complete immediately here
+  float rf[fh3::kRingF]; uint32_t rl[fh3::kRingL];
+  template <typename T> void ring_fetch(int foff, int loff, const T* lp, const float* fp) {
+    rl[loff / fh3::kRingSlotBytes] = (uint32_t)*lp; rf[foff / fh3::kRingSlotBytes] = *fp;
   }
-  void ring_put(int off, float f) { rl[off / fh3::kRingSlotBytes] = 0xdeadbeefu; rf[off / fh3::kRingSlotBytes] = f; }
+  void ring_put(int foff, float f) { rf[foff / fh3::kRingSlotBytes] = f; }
   template <int N> void ring_wait() const {}
-  float ring_f(int off) const { return rf[off / fh3::kRingSlotBytes]; }
-  template <typename T> T ring_l(int off) const { return (T)rl[off / fh3::kRingSlotBytes]; }
+  float ring_f(int foff) const { return rf[foff / fh3::kRingSlotBytes]; }
+  template <typename T> T ring_l(int loff) const { return (T)rl[loff / fh3::kRingSlotBytes]; }
   uint64_t* flag = nullptr;
   void note_row(int row) { if (flag) *flag |= 1ull << (row >> 5); }
 };
@@ -132,7 +132,7 @@ extern "C" int fh3_host_edt(const uint32_t* labels, int64_t sx, int64_t sy, int6
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 
-template <int W, int PF, int C, int R, int B, bool WRITE_BG>
+template <int W, int WR, int PF, int C, int R, int B, bool WRITE_BG>
 void hybrid_pass(const uint32_t* labels, const float* fin, float* fout, int n, int64_t cstride, int64_t sx, int64_t nouter,
                  int64_t ostride, float w, int bb, int last, int64_t ntx, long* stats) {
   HostCtx cx;
@@ -142,7 +142,7 @@ void hybrid_pass(const uint32_t* labels, const float* fin, float* fout, int n, i
     for (int64_t x = 0; x < sx; x++) {
       const int64_t base = o * ostride + x;
       cx.flag = flags + o * ntx + (x >> 5);
-      fh3::stencil_column<uint32_t, W, PF, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true);
+      fh3::stencil_column<uint32_t, W, WR, PF, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true);
     }
   cx.flag = nullptr;
   for (int64_t o = 0; o < nouter; o++)
@@ -167,7 +167,7 @@ void hybrid_pass(const uint32_t* labels, const float* fin, float* fout, int n, i
   free(flags); free(cx.lv); free(cx.lh); free(cx.lz);
 }
 
-template <int WY, int WZ, int PF>
+template <int WY, int WZ, int WR, int PF>
 void run_hybrid(const uint32_t* labels, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz, int bb, int ndim,
                 float* out, long* stats) {
   const int64_t V = sx * sy * sz, ntx = (sx + 31) / 32;
@@ -177,23 +177,24 @@ void run_hybrid(const uint32_t* labels, int64_t sx, int64_t sy, int64_t sz, floa
   float* a = (ndim == 3) ? out : ws;     // x -> a, y -> b, z -> a
   float* b = (ndim == 3) ? ws : out;
   pass_x<uint32_t>(labels, a, sx, sy * sz, wx, bb);
-  hybrid_pass<WY, PF, 4, 16, 4, true>(labels, a, b, (int)sy, sx, sx, sz, sx * sy, wy, bb, ndim == 2, ntx, stats);
-  if (ndim == 3) hybrid_pass<WZ, PF, 4, 16, 4, false>(labels, b, a, (int)sz, sx * sy, sx, sy, sx, wz, bb, 1, ntx, stats);
+  hybrid_pass<WY, (WR < WY ? WR : WY), PF, 4, 16, 4, true>(labels, a, b, (int)sy, sx, sx, sz, sx * sy, wy, bb, ndim == 2, ntx, stats);
+  if (ndim == 3) hybrid_pass<WZ, (WR < WZ ? WR : WZ), PF, 4, 16, 4, false>(labels, b, a, (int)sz, sx * sy, sx, sy, sx, wz, bb, 1, ntx, stats);
   free(ws);
 }
 
 }  // namespace
 
-// variant: 0 = windows (10, 4) prefetch 12, 1 = (4, 4) pf 4, 2 = (12, 8) pf 6, 3 = (2, 1) pf 1, 4 = (8, 6) pf 31
+// variant = tap radii (y, z), register-window radius, prefetch depth:
+//   0 = (10, 4) wr 4 pf 11   1 = (4, 4) wr 4 pf 4   2 = (12, 8) wr 5 pf 6   3 = (2, 1) wr 1 pf 1   4 = (8, 6) wr 8 pf 15
 extern "C" int fh3_host_edt_hybrid(const uint32_t* labels, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
                                    int bb, int ndim, int variant, float* out, long* stats) {
   if (sy > fh3::kMaxN || sz > fh3::kMaxN) return -1;
   switch (variant) {
-    case 0: run_hybrid<10, 4, 12>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
-    case 1: run_hybrid<4, 4, 4>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
-    case 2: run_hybrid<12, 8, 6>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
-    case 3: run_hybrid<2, 1, 1>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
-    case 4: run_hybrid<8, 6, 31>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
+    case 0: run_hybrid<10, 4, 4, 11>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
+    case 1: run_hybrid<4, 4, 4, 4>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
+    case 2: run_hybrid<12, 8, 5, 6>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
+    case 3: run_hybrid<2, 1, 1, 1>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
+    case 4: run_hybrid<8, 6, 8, 15>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
     default: return -2;
   }
   return 0;
