@@ -270,7 +270,7 @@ def run_b200(args):
       if os.path.exists(tpath) and args.size == 512:
         with open(tpath) as tf:
           traffic = float(json.load(tf)["dram_bytes_read_plus_write"])
-      roof = {"kernel": "b2t_edt (K1: edt_pass_x_v2 + 2x edt_pass_col_fh)", "bound": "hbm", "achieved": ach, "peak": peak,
+      roof = {"kernel": "b2t_edt_ws (K1: edt_pass_x_v2 + 2x [edt_pass_col_stencil + edt_pass_col_fh3_range])", "bound": "hbm", "achieved": ach, "peak": peak,
               "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": how,
               "algorithmic_bytes": alg, "ms": edt_ms}
     # bounded CPU sample: the oracle port, one core, on the slab

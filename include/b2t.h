@@ -69,7 +69,8 @@ int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int64_t sy, in
                void* d_workspace, size_t workspace_bytes, void* stream);
 /* Tuning hook of the hybrid: enable = 0 sends b2t_edt_ws down the b2t_edt path; wy, wz = tap radius of the stencil
  * in the y / z pass, wr = radius of its register window (farther taps read the shared-memory ring), pf = rows of
- * load prefetch, minb = min blocks per SM (wy > 0 selects a compiled instantiation). */
+ * load prefetch, minb = min blocks per SM.  wy > 0 fixes the radii, wy = 0 leaves them to the library (they follow
+ * the anisotropy), wy < 0 keeps them; wr > 0 selects a compiled (wr, pf, minb) instantiation. */
 int b2t_edt_config_hybrid(int enable, int wy, int wz, int wr, int pf, int minb);
 
 

@@ -720,10 +720,10 @@ edt_pass_col_fh3_kernel(const T* __restrict__ labels, float* __restrict__ f, int
 // Kernel selection (experiments and A/B timing; results are identical whatever is chosen).  Initialised from the
 // environment -- B2T_EDT_ALGO: 3 = shared-memory-ring F-H (default), 2 = local-memory F-H, w = windowed search;
 // B2T_FH3 = "C,MINB,R,B": one of the compiled instantiations -- and changeable at run time with b2t_edt_config().
-struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hwr, hpf, hminb; };
+struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hwr, hpf, hminb; int ec, eminb, er, eb; };
 static EdtCfg& edt_cfg() {
   static EdtCfg cfg = []() {
-    EdtCfg c{3, 16, 6, 32, 4, 1, 10, 4, 4, 11, 8};
+    EdtCfg c{3, 16, 6, 32, 4, 1, 0, 0, 4, 11, 8, 32, 4, 32, 8};   // hwy = 0: tap radii chosen from the anisotropy
     const char* a = getenv("B2T_EDT_ALGO");
     if (a) c.algo = (a[0] == 'w') ? 1 : (a[0] == '2' ? 2 : 3);
     const char* e = getenv("B2T_FH3");
@@ -749,14 +749,9 @@ bool edt_launch_fh3_passes(const T* labels, int64_t sx, int64_t sy, int64_t sz, 
                                                                            sx, wz, black_border, 1);                  \
     return true;                                                                                                       \
   }
-  B2T_FH3_GO(16, 8, 32, 4)
-  B2T_FH3_GO(16, 8, 16, 4)
   B2T_FH3_GO(16, 6, 32, 4)
-  B2T_FH3_GO(16, 8, 32, 8)
-  B2T_FH3_GO(32, 4, 32, 4)
+  B2T_FH3_GO(16, 8, 32, 4)
   B2T_FH3_GO(32, 4, 32, 8)
-  B2T_FH3_GO(8, 8, 16, 4)
-  B2T_FH3_GO(8, 12, 16, 4)
 #undef B2T_FH3_GO
   return false;
 }
@@ -865,7 +860,7 @@ B2T_EXPORT int b2t_edt_config(int algo, int c, int minb, int r, int b) {
   B2T_REQUIRE(algo >= 0 && algo <= 3, "b2t_edt_config: algo must be 0 (keep), 1 (windowed), 2 (local-memory F-H) or 3 (ring F-H)");
   EdtCfg& cfg = edt_cfg();
   if (algo) cfg.algo = algo;
-  if (c > 0) { cfg.c = c; cfg.minb = minb; cfg.r = r; cfg.b = b; }
+  if (c > 0) { cfg.c = c; cfg.minb = minb; cfg.r = r; cfg.b = b; cfg.ec = c; cfg.eminb = minb; cfg.er = r; cfg.eb = b; }
   return B2T_OK;
 }
 
@@ -925,21 +920,19 @@ static bool edt_launch_hybrid_pass(const uint32_t* labels, const float* fin, flo
   }
   // tap radius (4 .. 12), register-window radius, prefetch depth, min blocks per SM
   B2T_ST_GO(4, 4, 11, 8) B2T_ST_GO(6, 4, 11, 8) B2T_ST_GO(8, 4, 11, 8) B2T_ST_GO(10, 4, 11, 8)
-  B2T_ST_GO(4, 6, 11, 8) B2T_ST_GO(6, 6, 11, 8) B2T_ST_GO(8, 6, 11, 8) B2T_ST_GO(10, 6, 11, 8)
-  B2T_ST_GO(4, 3, 11, 8) B2T_ST_GO(6, 3, 11, 8) B2T_ST_GO(8, 3, 11, 8) B2T_ST_GO(10, 3, 11, 8)
-  B2T_ST_GO(4, 4, 7, 8) B2T_ST_GO(8, 4, 7, 8) B2T_ST_GO(10, 4, 7, 8) B2T_ST_GO(12, 4, 7, 8)
+  B2T_ST_GO(4, 4, 7, 8) B2T_ST_GO(10, 4, 7, 8) B2T_ST_GO(12, 4, 7, 8)
 #undef B2T_ST_GO
   if (!done) return false;
   done = false;
   const dim3 rgrid((unsigned)ntx, (unsigned)nouter);
 #define B2T_FR_GO(NM_, C_, MB_, R_, B_)                                                                                   \
-  if (!done && n <= NM_ && c.c == C_ && c.minb == MB_ && c.r == R_ && c.b == B_) {                                        \
+  if (!done && n <= NM_ && c.ec == C_ && c.eminb == MB_ && c.er == R_ && c.eb == B_) {                                    \
     edt_pass_col_fh3_range_kernel<uint32_t, C_, NM_, 4 * MB_, R_, B_><<<rgrid, 32, 0, st>>>(                             \
         labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, flags, ntx);                             \
     done = true;                                                                                                          \
   }
 #define B2T_FR_ALL(C_, MB_, R_, B_) B2T_FR_GO(256, C_, MB_, R_, B_) B2T_FR_GO(512, C_, MB_, R_, B_) B2T_FR_GO(1024, C_, MB_, R_, B_) B2T_FR_GO(2048, C_, MB_, R_, B_)
-  B2T_FR_ALL(16, 8, 32, 4) B2T_FR_ALL(16, 8, 16, 4) B2T_FR_ALL(16, 6, 32, 4) B2T_FR_ALL(32, 4, 32, 4) B2T_FR_ALL(32, 4, 32, 8)
+  B2T_FR_ALL(32, 4, 32, 8) B2T_FR_ALL(16, 6, 32, 4) B2T_FR_ALL(16, 8, 32, 4)
 #undef B2T_FR_ALL
 #undef B2T_FR_GO
   return done;
@@ -958,6 +951,10 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
                           void* stream) {
   const EdtCfg c = edt_cfg();
   const int64_t nmax = sy > sz ? sy : sz;
+  // Tap radius of a pass: a process r voxels thick along x needs taps out to r * wx / w rows, so the radius scales
+  // with wx / w (10 rows at w = wx; 4 in the z pass of a 16 x 16 x 40 nm volume).  Any radius gives the same result.
+  auto auto_radius = [&](float w) { const int r = 2 * (int)lrintf(5.0f * wx / w); return r < 4 ? 4 : (r > 10 ? 10 : r); };
+  const int hwy = c.hwy > 0 ? c.hwy : auto_radius(wy), hwz = c.hwy > 0 ? c.hwz : auto_radius(wz);
   // The stencil is exact -- and therefore bit-identical to the envelope -- when every value a thin voxel can take is an
   // integer below 2^24: integer anisotropy, and thresholds w^2 (W+1)^2 below 2^24.
   const bool hybrid_ok =
@@ -965,8 +962,8 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
       (ndim == 3 || sz == 1) && sx > 0 && sy > 0 && sz > 0 && (sx % 4) == 0 && sx <= 1024 && nmax <= fh3::kMaxN &&
       sy <= 65535 && sz <= 65535 && ((uintptr_t)d_labels % 16) == 0 && ((uintptr_t)d_out % 16) == 0 &&
       ((uintptr_t)d_workspace % 16) == 0 && workspace_bytes >= b2t_edt_workspace_bytes(sx, sy, sz) &&
-      edt_is_small_int(wx) && edt_is_small_int(wy) && edt_is_small_int(wz) && wy * (float)(c.hwy + 1) < 4096.0f &&
-      wz * (float)(c.hwz + 1) < 4096.0f;
+      edt_is_small_int(wx) && edt_is_small_int(wy) && edt_is_small_int(wz) && wy * (float)(hwy + 1) < 4096.0f &&
+      wz * (float)(hwz + 1) < 4096.0f;
   if (!hybrid_ok) return b2t_edt(d_labels, label_bytes, sx, sy, sz, wx, wy, wz, black_border, ndim, d_out, stream);
   cudaStream_t st = (cudaStream_t)stream;
   black_border = black_border ? 1 : 0;
@@ -987,9 +984,9 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
     else if (sx <= 512) edt_pass_x_v2_kernel<16><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
     else edt_pass_x_v2_kernel<32><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
   }
-  bool ok = edt_launch_hybrid_pass(labels, a, b, (int)sy, sx, sx, sz, sx * sy, wy, black_border, ndim == 2, c.hwy, true, flags_y, st);
+  bool ok = edt_launch_hybrid_pass(labels, a, b, (int)sy, sx, sx, sz, sx * sy, wy, black_border, ndim == 2, hwy, true, flags_y, st);
   if (ok && ndim == 3)
-    ok = edt_launch_hybrid_pass(labels, b, a, (int)sz, sx * sy, sx, sy, sx, wz, black_border, 1, c.hwz, false, flags_z, st);
+    ok = edt_launch_hybrid_pass(labels, b, a, (int)sz, sx * sy, sx, sy, sx, wz, black_border, 1, hwz, false, flags_z, st);
   B2T_REQUIRE(ok, "b2t_edt_ws: the configured stencil / envelope variant is not compiled in");
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(ndim == 3 ? 5 : 3);
@@ -999,7 +996,9 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
 B2T_EXPORT int b2t_edt_config_hybrid(int enable, int wy, int wz, int wr, int pf, int minb) {
   EdtCfg& cfg = edt_cfg();
   cfg.hybrid = enable ? 1 : 0;
-  if (wy > 0) { cfg.hwy = wy; cfg.hwz = wz; cfg.hwr = wr; cfg.hpf = pf; cfg.hminb = minb; }
+  if (wy > 0) { cfg.hwy = wy; cfg.hwz = wz; }
+  else if (wy == 0) { cfg.hwy = 0; cfg.hwz = 0; }   // radii from the anisotropy
+  if (wr > 0) { cfg.hwr = wr; cfg.hpf = pf; cfg.hminb = minb; }
   return B2T_OK;
 }
 

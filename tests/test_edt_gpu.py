@@ -81,3 +81,65 @@ def test_bit_identical_to_oracle(gpu, orc):
     out = ops.to_host_f(ops.edt(ops.to_device_f(lab, gpu), lab.shape, an, bb), lab.shape)
     ref = orc.edt(lab, an, bb)
     assert np.array_equal(out, ref)
+
+
+# ---- b2t_edt_ws: stencil + envelope hybrid (uint32 labels, integer anisotropy) and its fallbacks ----
+def test_hybrid_bit_identical_to_oracle(gpu, orc):
+  """ops.edt hands uint32 volumes to b2t_edt_ws; with integer anisotropy the column passes run as the register
+  stencil plus the envelope kernel on the flagged blocks, and the result is the oracle's, bit for bit."""
+  from kimimaro_b200 import ops
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes((256, 192, 96), 60, seed=78).astype(np.uint32)
+  lab[60:200, 40:150, 20:80] = 4242                       # a blob: rows the stencil cannot finish
+  lab = np.asfortranarray(lab)
+  for an, bb in (((16, 16, 40), False), ((4, 4, 40), True), ((1, 1, 1), False), ((40, 32, 20), True), ((2, 3, 5), False)):
+    out = ops.to_host_f(ops.edt(ops.to_device_f(lab, gpu), lab.shape, an, bb, workspace=True), lab.shape)
+    assert np.array_equal(out, orc.edt(lab, an, bb)), (an, bb)
+  # dense labels (a run is always open), ragged sizes, columns shorter than the stencil window, a 2-D plane
+  rng = np.random.default_rng(4)
+  for shape in ((64, 70, 33), (128, 5, 3), (32, 300, 2), (4, 3, 200), (96, 1, 1)):
+    dense = rng.integers(1, 6, size=shape).astype(np.uint32)
+    dense = np.asfortranarray(np.repeat(np.repeat(dense[:, ::4, ::3], 4, axis=1), 3, axis=2)[:, :shape[1], :shape[2]])
+    for bb in (False, True):
+      out = ops.to_host_f(ops.edt(ops.to_device_f(dense, gpu), dense.shape, (16, 16, 40), bb, workspace=True), dense.shape)
+      assert np.array_equal(out, orc.edt(dense, (16, 16, 40), bb)), (shape, bb)
+  plane = np.zeros((260, 257), np.uint32, order="F")
+  plane[1:-1, 1:-1] = 1
+  plane[100:140, 50:200] = 2
+  out = ops.to_host_f(ops.edt(ops.to_device_f(plane, gpu), plane.shape, (100, 100), True, workspace=True), plane.shape)
+  assert np.array_equal(out, orc.edt(plane, (100, 100), True))
+
+
+def test_hybrid_equals_in_place_path(gpu):
+  """Same input through b2t_edt_ws and b2t_edt: identical floats (the hybrid is an execution strategy, not an
+  approximation); also with the hybrid switched off and with a workspace that is too small (both fall back)."""
+  import torch
+  from kimimaro_b200 import ops, _lib
+  from kimimaro_b200._lib import c_f32, c_i64, c_int, c_sz, c_vp
+  from tests.synth import synthetic_tubes
+  lab = np.asfortranarray(synthetic_tubes((192, 160, 80), 40, seed=79).astype(np.uint32))
+  lab[30:150, 30:130, 10:70] = 99
+  d = ops.to_device_f(lab, gpu)
+  ref = ops.edt(d, lab.shape, (16, 16, 40), False, workspace=False).clone()
+  assert torch.equal(ops.edt(d, lab.shape, (16, 16, 40), False, workspace=True), ref)
+  lib = _lib.lib()
+  try:
+    _lib.check(lib.b2t_edt_config_hybrid(0, -1, -1, 0, 0, 0))
+    assert torch.equal(ops.edt(d, lab.shape, (16, 16, 40), False, workspace=True), ref)
+  finally:
+    _lib.check(lib.b2t_edt_config_hybrid(1, -1, -1, 0, 0, 0))
+  out = torch.empty_like(ref)
+  ws = torch.empty(1024, dtype=torch.uint8, device=gpu)
+  _lib.check(lib.b2t_edt_ws(c_vp(d.data_ptr()), c_int(4), c_i64(192), c_i64(160), c_i64(80), c_f32(16), c_f32(16), c_f32(40),
+                            c_int(0), c_int(3), c_vp(out.data_ptr()), c_vp(ws.data_ptr()), c_sz(1024), ops.stream_ptr()),
+             "b2t_edt_ws")
+  assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint32])
+def test_hybrid_fallbacks_keep_tolerance(gpu, orc, dtype):
+  # non-integer anisotropy, narrow labels, sx not a multiple of 4: b2t_edt_ws takes the b2t_edt path
+  from tests.synth import synthetic_tubes
+  for shape, an in (((96, 80, 48), (3.3, 4.7, 10.1)), ((97, 64, 40), (16, 16, 40))):
+    lab = np.asfortranarray((synthetic_tubes(shape, 12, seed=6) % 200).astype(dtype))
+    _run(gpu, orc, lab, an, False)
