@@ -370,7 +370,7 @@ FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, 
       /* the run-end clamps inside the window follow from the links alone: a tight bound for the tap loop */ \
       if (rr < W) { const float e = (float)(rr + 1); v = cx.fmin(v, cx.mul(cx.mul(w2, e), e)); } \
       if (ll < W) { const float e = (float)(ll + 1); v = cx.fmin(v, cx.mul(cx.mul(w2, e), e)); } \
-      float mx = cx.wmaxf(fg ? v : 0.0f);                  /* warp-wide bound, tightened after every tap pair */ \
+      const float mx = cx.wmaxf(fg ? v : 0.0f);                                      \
       bool far = W > WR;                                                             \
       _Pragma("unroll")                                                              \
       for (int d = 1; d <= WR; d++) {                                                \
@@ -379,7 +379,6 @@ FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, 
         const float fp_ = (d <= rr) ? wf[cp] : 0.0f;                                 \
         const float fm_ = (d <= ll) ? wf[cm] : 0.0f;                                 \
         v = cx.fmin(v, cx.add(cx.fmin(fp_, fm_), cd[d]));                            \
-        mx = cx.wmaxf(fg ? v : 0.0f);                                                \
       }                                                                              \
       if (W > WR && far) {                                 /* thick processes: the taps beyond the registers */ \
         const int co = ao - (WR + 1) * kRingSlotBytes;                               \
@@ -390,13 +389,12 @@ FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, 
           const float fp_ = (d <= rr) ? cx.ring_f((co + d * kRingSlotBytes) & FMASK) : 0.0f; \
           const float fm_ = (d <= ll) ? cx.ring_f((co - d * kRingSlotBytes) & FMASK) : 0.0f; \
           v = cx.fmin(v, cx.add(cx.fmin(fp_, fm_), cdd));                            \
-          mx = cx.wmaxf(fg ? v : 0.0f);                                              \
         }                                                                            \
       }                                                                              \
       if (fg) out = last_pass ? cx.sqrt(v) : v;                                      \
-      if (cx.any(okrow && fg && v > thr)) cx.note_row(i);  /* not final: the envelope kernel redoes this block */ \
+      if (cx.any(fg && v > thr)) cx.note_row(i);           /* not final: the envelope kernel redoes this block */ \
     }                                                                                \
-    if (okrow && active && (WRITE_BG || fg)) cx.st_f(fw, out);  /* !WRITE_BG: fout already holds 0 on background */ \
+    if (active && (WRITE_BG || fg)) cx.st_f(fw, out);      /* !WRITE_BG: fout already holds 0 on background */ \
     fw += cstride;                                                                   \
   } while (0)
   // prologue: D rows in flight; the links of rows -W .. W-1; the window rows -WR .. WR-1 (row j -> slot (j + WR) mod S)
@@ -414,13 +412,13 @@ FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, 
 #pragma unroll
     for (int ph = 0; ph < S; ph++) {
       const int i = base + ph;
-      // the last block may run past the column: those rows are virtual, computed like any other and not stored
-      const bool okrow = steady || i < n;
-      // row i + W + D is fetched, row i + W (landed) is linked, row i + WR replaces row i - WR - 1 in the registers
-      if (steady) { FH3_FETCH_STEADY(); cx.template ring_wait<D>(); FH3_LINK_STEADY(); }
-      else { FH3_FETCH(); cx.template ring_wait<D>(); FH3_LINK(); }
-      FH3_ADMIT((ph + S - 1) % S);
-      FH3_ROW(ph);
+      if (steady || i < n) {
+        // row i + W + D is fetched, row i + W (landed) is linked, row i + WR replaces row i - WR - 1 in the registers
+        if (steady) { FH3_FETCH_STEADY(); cx.template ring_wait<D>(); FH3_LINK_STEADY(); }
+        else { FH3_FETCH(); cx.template ring_wait<D>(); FH3_LINK(); }
+        FH3_ADMIT((ph + S - 1) % S);
+        FH3_ROW(ph);
+      }
     }
   }
   cx.template ring_wait<0>();

@@ -84,11 +84,13 @@ def main():
     print(json.dumps(rec), flush=True)
   # hybrid (b2t_edt_ws): stencil windows (y, z), prefetch, min blocks per SM x envelope variant for the flagged blocks
   if "--hybrid" in sys.argv:
-    HY = [((10, 4, 4, 11, 8), (32, 4, 32, 8)), ((10, 4, 4, 11, 8), (16, 6, 32, 4)), ((8, 4, 4, 11, 8), (32, 4, 32, 8)),
-          ((12, 4, 4, 7, 8), (32, 4, 32, 8)), ((10, 4, 4, 7, 8), (32, 4, 32, 8)), ((10, 6, 4, 11, 8), (32, 4, 32, 8))]
+    HY = [((10, 4, 4, 11, 8), (16, 6, 32, 4)), ((8, 4, 4, 11, 8), (16, 6, 32, 4)), ((6, 4, 4, 11, 8), (16, 6, 32, 4)),
+          ((10, 4, 6, 11, 8), (16, 6, 32, 4)), ((10, 4, 3, 11, 8), (16, 6, 32, 4)), ((10, 4, 4, 7, 8), (16, 6, 32, 4)),
+          ((12, 4, 4, 7, 8), (16, 6, 32, 4)), ((10, 6, 4, 11, 8), (16, 6, 32, 4)), ((10, 4, 4, 11, 8), (32, 4, 32, 8)),
+          ((10, 4, 4, 11, 8), (16, 8, 32, 4))]
     for (wy_, wz_, wr_, pf, hmb), (c, mb, r, b) in HY:
       _lib.check(lib.b2t_edt_config(3, c, mb, r, b))
-      _lib.check(lib.b2t_edt_config_hybrid(1, wy_, wz_ if wy_ != 12 else 4, wr_, pf, hmb))
+      _lib.check(lib.b2t_edt_config_hybrid(1, wy_, wz_, wr_, pf, hmb))
       name = f"hybrid W=({wy_},{wz_}) wr={wr_} pf={pf} minb={hmb} + env C={c} minb={mb} R={r} B={b}"
       try:
         out.fill_(-1.0)
@@ -110,8 +112,8 @@ def main():
       print(json.dumps(rec), flush=True)
     # other shapes / borders / 2-D through the hybrid, against the in-place v2 kernels
     from kimimaro_b200.datasets import synthetic_tubes
-    _lib.check(lib.b2t_edt_config_hybrid(1, 0, 0, 4, 11, 8))
-    _lib.check(lib.b2t_edt_config(3, 32, 4, 32, 8))
+    _lib.check(lib.b2t_edt_config_hybrid(1, 10, 4, 4, 11, 8))
+    _lib.check(lib.b2t_edt_config(3, 16, 6, 32, 4))
     rng = np.random.default_rng(3)
     small = []
     for shape, an2, bb in [((256, 192, 96), (16, 16, 40), False), ((256, 192, 96), (4, 4, 40), True),
