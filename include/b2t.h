@@ -60,7 +60,7 @@ int b2t_edt_config(int algo, int c, int minb, int r, int b);
  * stencil over every column (exact wherever the result is at most w^2 (W+1)^2, i.e. on the thin processes a
  * connectomics volume is made of) and the envelope kernel only over the 32-row blocks of 32-column tiles
  * the stencil flagged (the inside of blobs).  The passes ping-pong between d_out and the workspace:
- *   workspace = [sx*sy*sz float32][per-tile 64-bit block flags of the y and z passes],
+ *   workspace = [sx*sy*sz float32][per-tile 64-bit block flags of the y and z passes][the same again: predictions],
  * b2t_edt_workspace_bytes() says how much.  Any other input, or a workspace that is null / too small, takes the
  * b2t_edt path (d_out in place).  Launches: memset, pass x, (stencil, envelope) x 2. */
 size_t b2t_edt_workspace_bytes(int64_t sx, int64_t sy, int64_t sz);
@@ -72,6 +72,11 @@ int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int64_t sy, in
  * load prefetch, minb = min blocks per SM.  wy > 0 fixes the radii, wy = 0 leaves them to the library (they follow
  * the anisotropy), wy < 0 keeps them; wr > 0 selects a compiled (wr, pf, minb) instantiation. */
 int b2t_edt_config_hybrid(int enable, int wy, int wz, int wr, int pf, int minb);
+/* Tuning hook: enable = 1 runs every column pass of the hybrid as ONE "roles" launch plus a residual one: the previous
+ * pass predicts the blocks the stencil cannot finish (x pass -> y, y pass -> z), envelope warps start on them at once
+ * while stencil warps do the rest and flag what the prediction missed.  Same result bit for bit; the workspace of
+ * b2t_edt_workspace_bytes() already has room for the prediction words. */
+int b2t_edt_config_roles(int enable);
 
 
 /* N1  connected components ------------------------------------------------------------------------

@@ -301,10 +301,14 @@ edt_pass_col_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, 
 // ================================================================================================
 constexpr float kFltMax = 3.4028234664e38f;
 
-template <int SEG>
+// PRED (the "roles" form of the hybrid pass): also tell the y pass which 32-row blocks of which 32-column tiles hold a
+// value above its stencil threshold -- a necessary condition for a voxel the y stencil cannot finish -- by setting
+// bit (y >> 5) of pred[z * ntx + tile].  A hint only: it decides who computes a voxel, never what the result is.
+template <int SEG, bool PRED = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 edt_pass_x_v2_kernel(const uint32_t* __restrict__ labels, float* __restrict__ out, int sx, int64_t nrows, float w,
-                     int black_border) {
+                     int black_border, unsigned long long* __restrict__ pred = nullptr, float thr = 0.0f, int sy = 1,
+                     int ntx = 0) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= nrows) return;
@@ -368,6 +372,21 @@ edt_pass_x_v2_kernel(const uint32_t* __restrict__ labels, float* __restrict__ ou
   for (int q = 0; q < SEG / 4; q++)
     if (p0 + 4 * q < sx)
       *reinterpret_cast<float4*>(orow + p0 + 4 * q) = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
+  if (PRED) {
+    bool hot = false;
+#pragma unroll
+    for (int j = 0; j < SEG; j++) hot |= val[j] > thr;      // positions past the row end hold 0
+    const uint32_t hb = __ballot_sync(0xffffffffu, hot);
+    constexpr int LPT = 32 / SEG;                            // lanes per 32-column tile
+    if ((lane % LPT) == 0 && p0 < sx) {
+      const uint32_t tm = (LPT == 32 ? 0xffffffffu : ((1u << LPT) - 1u)) << lane;
+      if (hb & tm) {
+        const int64_t z = row / sy;
+        const int y = (int)(row - z * sy);
+        atomicOr(pred + z * ntx + (p0 >> 5), 1ull << (y >> 5));
+      }
+    }
+  }
 }
 
 // intersection of the parabola rooted at run-relative row i (height fi) with the one at v (height h):
@@ -567,6 +586,13 @@ template <int C, int NMAX, int NT = 128>
 struct FhDevCtx {
   uint32_t sbase;   // shared-state-space address of s_plane[0][0][threadIdx.x]: slot stride NT*4 B, plane stride C*NT*4 B
   float* lv; float* lh; float* lz;      // local-memory backing, indexed by entry
+  unsigned long long* nflag = nullptr;  // NEXT: prediction word of (row 0, this tile) for the next pass, rows nstride apart
+  int64_t nstride = 0;
+  unsigned long long nbit = 0;
+  __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
+  __device__ __forceinline__ void note_next(int row) const {   // called by all lanes of the warp together
+    if ((threadIdx.x & 31) == 0) atomicOr(nflag + (int64_t)row * nstride, nbit);
+  }
   __device__ __forceinline__ float mul(float a, float b) const { return __fmul_rn(a, b); }
   __device__ __forceinline__ float add(float a, float b) const { return __fadd_rn(a, b); }
   __device__ __forceinline__ float sub(float a, float b) const { return __fsub_rn(a, b); }
@@ -606,6 +632,12 @@ struct StDevCtx {
   unsigned long long* flag;   // flag word of this warp's tile (bit b: rows [32b, 32b+32) need the envelope kernel)
   int last_blk;
   uint32_t fbase, lbase;      // shared-state-space addresses of s_f[0][threadIdx.x], s_l[0][threadIdx.x]; slots 512 B apart
+  unsigned long long* nflag = nullptr;  // NEXT: see FhDevCtx
+  int64_t nstride = 0;
+  unsigned long long nbit = 0;
+  __device__ __forceinline__ void note_next(int row) const {
+    if ((threadIdx.x & 31) == 0) atomicOr(nflag + (int64_t)row * nstride, nbit);
+  }
   __device__ __forceinline__ float mul(float a, float b) const { return __fmul_rn(a, b); }
   __device__ __forceinline__ float add(float a, float b) const { return __fadd_rn(a, b); }
   __device__ __forceinline__ float sqrt(float a) const { return __fsqrt_rn(a); }
@@ -702,6 +734,64 @@ edt_pass_col_fh3_range_kernel(const T* __restrict__ labels, const float* __restr
   }
 }
 
+// "Roles" form of the hybrid pass.  ncu on the two-kernel form: the envelope kernel is a latency-bound chain (one warp
+// per blob tile walks ~450 rows at ~0.1 instructions per cycle, 18 such warps per SM, 40 % issue) that only STARTS when
+// the stencil kernel has ended.  Here the PREVIOUS pass predicts the blocks the stencil cannot finish (the x pass for y,
+// the y pass for z: a value above the threshold going in is necessary for one coming out), and one launch runs both
+// roles side by side: the CTAs with blockIdx.z == 0 are dispatched first and run the envelope over the predicted blocks
+// of their four tiles (most have none and leave at once), the CTAs with blockIdx.z == 1 run the stencil, skipping the
+// predicted blocks (PRED in edt_fh3.cuh) and flagging what the prediction missed for a residual envelope launch.  The
+// chain starts at t = 0 and the stencil warps fill the issue slots it leaves.  Both roles report rows above the next
+// pass's threshold (NEXT).  Shared memory: the 48 ring slots of the stencil role are the 3 x 16 plane slots of the
+// envelope role; a thread only ever touches column threadIdx.x of either.
+template <typename T, int W, int WR, int D, int MINB, bool WRITE_BG, bool NEXT, int NMAX, int R, int B>
+__global__ void __launch_bounds__(128, MINB)
+edt_pass_col_roles_kernel(const T* __restrict__ labels, const float* __restrict__ fin, float* __restrict__ fout, int n,
+                          int64_t cstride, int nx, int64_t ostride, float w, int black_border, int last_pass,
+                          const unsigned long long* __restrict__ pred, unsigned long long* __restrict__ resid,
+                          unsigned long long* __restrict__ next, float thr_next, int ntx) {
+  static_assert(fh3::kRingSlotBytes == 128 * 4, "one ring slot = one float per thread of the CTA");
+  static_assert(fh3::kRingF + fh3::kRingL == 48, "48 slots: f ring + label ring == 3 planes of 16 entries");
+  constexpr int C = 16;
+  __shared__ float s_raw[fh3::kRingF + fh3::kRingL][128];
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int tile = (blockIdx.x * 128 + (threadIdx.x & ~31)) >> 5;
+  if (tile >= ntx) return;                         // the whole warp is outside the volume
+  const bool active = x < nx;
+  const int outer = blockIdx.y;
+  unsigned long long m = pred[(int64_t)outer * ntx + tile];   // warp-uniform
+  const unsigned long long nbit = 1ull << (outer >> 5);
+  if (blockIdx.z == 0) {
+    if (m == 0ull) return;
+    float lv[NMAX];
+    float lh[NMAX];
+    float lz[NMAX];
+    const int64_t base = (int64_t)outer * ostride + (active ? x : 0);
+    FhDevCtx<C, NMAX, 128> cx{(uint32_t)__cvta_generic_to_shared(&s_raw[0][threadIdx.x]), lv, lh, lz, next + tile, ntx, nbit};
+    while (m) {                                    // maximal groups of consecutive predicted blocks
+      const int b0 = __ffsll((long long)m) - 1;
+      const unsigned long long rest = ~(m >> b0);
+      const int len = rest ? (__ffsll((long long)rest) - 1) : 64;
+      const int b1 = b0 + len - 1;
+      m = (b1 >= 63) ? 0ull : (m & (~0ull << (b1 + 1)));
+      const int rlo = 32 * b0, rhi = min(n - 1, 32 * b1 + 31);
+      if (rlo >= n) break;                         // a prediction is a hint: ignore bits past the column end
+      int own_lo, own_hi;
+      fh3::extend_to_runs<T>(cx, labels + base, n, cstride, active, rlo, rhi, own_lo, own_hi);
+      const int rb = cx.wmin(own_lo), re = cx.wmax(own_hi);
+      if (rb < re)
+        fh3::column_range<T, C, R, B, true, NEXT>(cx, labels + base, fin + base, fout + base, n, cstride, w, black_border != 0,
+                                                  last_pass != 0, active, rb, re, own_lo, own_hi, thr_next);
+    }
+  } else {
+    const int64_t base = (int64_t)outer * ostride + (active ? x : nx - 1);   // a lane outside shadows the last column
+    StDevCtx cx{resid + (int64_t)outer * ntx + tile, -1, (uint32_t)__cvta_generic_to_shared(&s_raw[0][threadIdx.x]),
+                (uint32_t)__cvta_generic_to_shared(&s_raw[fh3::kRingF][threadIdx.x]), next + tile, ntx, nbit};
+    fh3::stencil_column<T, W, WR, D, WRITE_BG, true, NEXT>(cx, labels + base, fin + base, fout + base, n, cstride, w,
+                                                           black_border != 0, last_pass != 0, active, m, thr_next);
+  }
+}
+
 template <typename T, int C, int NMAX, int MINB, int R, int B>
 __global__ void __launch_bounds__(128, MINB)
 edt_pass_col_fh3_kernel(const T* __restrict__ labels, float* __restrict__ f, int n, int64_t cstride, int nx,
@@ -720,16 +810,18 @@ edt_pass_col_fh3_kernel(const T* __restrict__ labels, float* __restrict__ f, int
 // Kernel selection (experiments and A/B timing; results are identical whatever is chosen).  Initialised from the
 // environment -- B2T_EDT_ALGO: 3 = shared-memory-ring F-H (default), 2 = local-memory F-H, w = windowed search;
 // B2T_FH3 = "C,MINB,R,B": one of the compiled instantiations -- and changeable at run time with b2t_edt_config().
-struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hwr, hpf, hminb; int ec, eminb, er, eb; };
+struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hwr, hpf, hminb; int ec, eminb, er, eb; int roles; };
 static EdtCfg& edt_cfg() {
   static EdtCfg cfg = []() {
-    EdtCfg c{3, 16, 6, 32, 4, 1, 0, 0, 4, 11, 8, 32, 4, 32, 8};   // hwy = 0: tap radii chosen from the anisotropy
+    EdtCfg c{3, 16, 6, 32, 4, 1, 0, 0, 4, 11, 8, 32, 4, 32, 8, 0};   // hwy = 0: tap radii chosen from the anisotropy
     const char* a = getenv("B2T_EDT_ALGO");
     if (a) c.algo = (a[0] == 'w') ? 1 : (a[0] == '2' ? 2 : 3);
     const char* e = getenv("B2T_FH3");
     if (e) sscanf(e, "%d,%d,%d,%d", &c.c, &c.minb, &c.r, &c.b);
     const char* h = getenv("B2T_EDT_HYBRID");   // "0" = off, or "WY,WZ,WR,PF,MINB"
     if (h) { if (h[0] == '0' && h[1] == 0) c.hybrid = 0; else sscanf(h, "%d,%d,%d,%d,%d", &c.hwy, &c.hwz, &c.hwr, &c.hpf, &c.hminb); }
+    const char* r = getenv("B2T_EDT_ROLES");    // "1": predicted envelope + stencil in one launch per pass
+    if (r) c.roles = atoi(r);
     return c;
   }();
   return cfg;
@@ -938,12 +1030,51 @@ static bool edt_launch_hybrid_pass(const uint32_t* labels, const float* fin, flo
   return done;
 }
 
+// roles form of one column pass: the roles kernel (envelope over the predicted blocks next to the stencil over the
+// rest), then the envelope kernel over what the stencil flagged outside the prediction.
+static bool edt_launch_roles_pass(const uint32_t* labels, const float* fin, float* fout, int n, int64_t cstride, int64_t sx,
+                                  int64_t nouter, int64_t ostride, float w, int black_border, int last, int W, bool write_bg,
+                                  const unsigned long long* pred, unsigned long long* resid, unsigned long long* next,
+                                  float thr_next, cudaStream_t st) {
+  const EdtCfg c = edt_cfg();
+  const dim3 grid((unsigned)b2t_ceil_div(sx, 128), (unsigned)nouter, 2);
+  const int ntx = b2t_ceil_div(sx, 32);
+  const bool nx_ = next != nullptr;
+  bool done = false;
+#define B2T_RO_GO(W_, BG_, NX_, NM_)                                                                                      \
+  if (!done && W == W_ && write_bg == BG_ && nx_ == NX_ && n <= NM_) {                                                    \
+    edt_pass_col_roles_kernel<uint32_t, W_, 4, 11, 8, BG_, NX_, NM_, 32, 4><<<grid, 128, 0, st>>>(                        \
+        labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, pred, resid, next, thr_next, ntx);        \
+    done = true;                                                                                                          \
+  }
+#define B2T_RO_ALL(W_) B2T_RO_GO(W_, true, true, 512) B2T_RO_GO(W_, true, true, 2048) B2T_RO_GO(W_, false, false, 512) \
+  B2T_RO_GO(W_, false, false, 2048) B2T_RO_GO(W_, true, false, 512) B2T_RO_GO(W_, true, false, 2048)
+  B2T_RO_ALL(4) B2T_RO_ALL(10)
+#undef B2T_RO_ALL
+#undef B2T_RO_GO
+  if (!done) return false;
+  done = false;
+  const dim3 rgrid((unsigned)ntx, (unsigned)nouter);
+#define B2T_FR_GO(NM_, C_, MB_, R_, B_)                                                                                   \
+  if (!done && n <= NM_ && c.ec == C_ && c.eminb == MB_ && c.er == R_ && c.eb == B_) {                                    \
+    edt_pass_col_fh3_range_kernel<uint32_t, C_, NM_, 4 * MB_, R_, B_><<<rgrid, 32, 0, st>>>(                             \
+        labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, resid, ntx);                             \
+    done = true;                                                                                                          \
+  }
+#define B2T_FR_ALL(C_, MB_, R_, B_) B2T_FR_GO(256, C_, MB_, R_, B_) B2T_FR_GO(512, C_, MB_, R_, B_) B2T_FR_GO(1024, C_, MB_, R_, B_) B2T_FR_GO(2048, C_, MB_, R_, B_)
+  B2T_FR_ALL(32, 4, 32, 8) B2T_FR_ALL(16, 6, 32, 4) B2T_FR_ALL(16, 8, 32, 4)
+#undef B2T_FR_ALL
+#undef B2T_FR_GO
+  return done;
+}
+
 static bool edt_is_small_int(float w) { return w >= 1.0f && w <= 2048.0f && w == rintf(w); }
 
 B2T_EXPORT size_t b2t_edt_workspace_bytes(int64_t sx, int64_t sy, int64_t sz) {
   if (sx <= 0 || sy <= 0 || sz <= 0) return 0;
   const size_t ntx = (size_t)b2t_ceil_div(sx, 32);
-  return (size_t)sx * sy * sz * sizeof(float) + (ntx * (size_t)sz + ntx * (size_t)sy) * sizeof(unsigned long long);
+  // scratch volume + per pass one flag word per (32-column tile, outer index), twice: flagged by the stencil, predicted
+  return (size_t)sx * sy * sz * sizeof(float) + 2 * (ntx * (size_t)sz + ntx * (size_t)sy) * sizeof(unsigned long long);
 }
 
 B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int64_t sy, int64_t sz, float wx, float wy,
@@ -973,9 +1104,29 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
   float* ws_f = (float*)d_workspace;
   unsigned long long* flags_y = (unsigned long long*)(ws_f + V);
   unsigned long long* flags_z = flags_y + ntx * (size_t)sz;
-  B2T_CUDA_TRY(cudaMemsetAsync(flags_y, 0, (ntx * (size_t)sz + ntx * (size_t)sy) * sizeof(unsigned long long), st));
+  unsigned long long* pred_y = flags_z + ntx * (size_t)sy;
+  unsigned long long* pred_z = pred_y + ntx * (size_t)sz;
+  const bool roles = c.roles != 0 && (hwy == 4 || hwy == 10) && (ndim == 2 || hwz == 4 || hwz == 10) && sx <= 512;
+  B2T_CUDA_TRY(cudaMemsetAsync(flags_y, 0, (roles ? 2 : 1) * (ntx * (size_t)sz + ntx * (size_t)sy) * sizeof(unsigned long long), st));
   float* a = (ndim == 3) ? d_out : ws_f;   // x -> a, y -> b, z -> a: the result ends in d_out either way
   float* b = (ndim == 3) ? ws_f : d_out;
+  if (roles) {
+    const int64_t nrows = sy * sz;
+    const unsigned blocks = (unsigned)((nrows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const float thr_y = wy * wy * (float)((hwy + 1) * (hwy + 1)), thr_z = wz * wz * (float)((hwz + 1) * (hwz + 1));
+    if (sx <= 128) edt_pass_x_v2_kernel<4, true><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border, pred_y, thr_y, (int)sy, (int)ntx);
+    else if (sx <= 256) edt_pass_x_v2_kernel<8, true><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border, pred_y, thr_y, (int)sy, (int)ntx);
+    else edt_pass_x_v2_kernel<16, true><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border, pred_y, thr_y, (int)sy, (int)ntx);
+    bool ok = edt_launch_roles_pass(labels, a, b, (int)sy, sx, sx, sz, sx * sy, wy, black_border, ndim == 2, hwy, true, pred_y,
+                                    flags_y, ndim == 3 ? pred_z : nullptr, thr_z, st);
+    if (ok && ndim == 3)
+      ok = edt_launch_roles_pass(labels, b, a, (int)sz, sx * sy, sx, sy, sx, wz, black_border, 1, hwz, false, pred_z, flags_z,
+                                 nullptr, 0.0f, st);
+    B2T_REQUIRE(ok, "b2t_edt_ws: the configured roles / envelope variant is not compiled in");
+    B2T_CUDA_TRY(cudaGetLastError());
+    b2t_count_launches(ndim == 3 ? 5 : 3);
+    return B2T_OK;
+  }
   {
     const int64_t nrows = sy * sz;
     const unsigned blocks = (unsigned)((nrows + kWarpsPerBlock - 1) / kWarpsPerBlock);
@@ -990,6 +1141,11 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
   B2T_REQUIRE(ok, "b2t_edt_ws: the configured stencil / envelope variant is not compiled in");
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(ndim == 3 ? 5 : 3);
+  return B2T_OK;
+}
+
+B2T_EXPORT int b2t_edt_config_roles(int enable) {
+  edt_cfg().roles = enable ? 1 : 0;
   return B2T_OK;
 }
 

@@ -68,6 +68,9 @@ FH3_HD uint32_t brev32(uint32_t x) {
 //   int   wmin(int), wmax(int), float wmaxf(float >= 0), bool any(bool)   warp-wide (identity on the host)
 //   void  note_row(int row)         hybrid pass only: "this row of my tile holds a voxel the stencil could not
 //                                   finish" (sets the bit of the row's 32-row block in the tile's flag word)
+//   void  note_next(int row)        NEXT only: "this row of my tile holds a value above the NEXT pass's threshold"
+//                                   (a hint: sets the bit of this column's outer index in the next pass's prediction
+//                                   word of (row, tile)); called by all lanes of the warp together
 // An entry is (v, h, z): row of the parabola's apex (absolute, kept as a float: rows < 2^24 are exact and the
 // hot loop then needs no int->float conversion), its height, and the left end of its reign (run-relative).
 
@@ -95,9 +98,11 @@ FH3_HD float intersect(Ctx& cx, float fi, float ir, float h, float v, float w2) 
 // RANGE = true (the blob half of the hybrid pass, see below): rows [rb, re) only, out of place; a lane takes
 //   part with the rows [own_lo, own_hi) (complete runs by construction); the rest of the range is treated as
 //   background.  Background is never written.
-template <typename T, int C, int R, int B, bool RANGE, typename Ctx>
+// NEXT: rows whose (squared) result exceeds thr_next are reported with cx.note_next (prediction for the next pass).
+template <typename T, int C, int R, int B, bool RANGE, bool NEXT = false, typename Ctx>
 FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, int n, int64_t cstride, float w,
-                         bool black_border, bool last_pass, bool active, int rb, int re, int own_lo, int own_hi) {
+                         bool black_border, bool last_pass, bool active, int rb, int re, int own_lo, int own_hi,
+                         float thr_next = 0.0f) {
   static_assert((C & (C - 1)) == 0, "ring size must be a power of two");
   static_assert(R % B == 0, "flush period must be a multiple of the batch");
   const float w2 = cx.mul(w, w);
@@ -208,6 +213,7 @@ FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, in
       float* fw = fout + lo * cstride;
       float iqf = (float)lo;
       for (int i = lo; i < hi; i++, fw += cstride, iqf += 1.0f) {
+        bool hot = false;
         if (i >= qb) {                           // step to the next closed run (or to "nothing left")
           if (kn < kdone) {
             const uint32_t pk = f2u(FH3_LD_Z(kn));
@@ -236,9 +242,11 @@ FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, in
           float val = cx.add(cx.mul(cx.mul(w2, di), di), ch);
           if (bl) { const float e = cx.add(ir, 1.0f); val = cx.fmin(val, cx.mul(cx.mul(w2, e), e)); }
           if (br) { const float e = qbf - iqf; val = cx.fmin(val, cx.mul(cx.mul(w2, e), e)); }
+          if (NEXT) hot = val > thr_next;
           if (last_pass) val = (val >= kFltMax) ? kInf : cx.sqrt(val);
           cx.st_f(fw, val);
         }
+        if (NEXT) { if (cx.any(hot)) cx.note_next(i); }   // the row loop is warp-uniform
       }
     }
     // every closed run is written: kn == kdone, and the slots below it are free for reuse
@@ -291,9 +299,15 @@ FH3_HD void column(Ctx& cx, const T* lp, float* fp, int n, int64_t cstride, floa
 constexpr int kRingSlotBytes = 512;
 constexpr int kRingF = 32, kRingL = 16;
 
-template <typename T, int W, int WR, int D, bool WRITE_BG, typename Ctx>
+// PRED: `pred` (warp-uniform) names the 32-row blocks of this tile that an envelope warp is already redoing, extended
+// to complete runs, at the same time (the "roles" kernel in edt.cu): the stencil evaluates no taps there and stores no
+// foreground -- every foreground voxel of such a block belongs to a run that meets the block, so the envelope warp
+// writes it -- but still the background zeros (WRITE_BG).  Rows of such runs OUTSIDE the predicted blocks are written
+// by both warps: with the same bits when the stencil's value is final, and otherwise the block is flagged and the
+// residual envelope launch, which runs after both, has the last word.  NEXT: see column_range.
+template <typename T, int W, int WR, int D, bool WRITE_BG, bool PRED = false, bool NEXT = false, typename Ctx>
 FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, int n, int64_t cstride, float w,
-                           bool black_border, bool last_pass, bool active) {
+                           bool black_border, bool last_pass, bool active, uint64_t pred = 0, float thr_next = 0.0f) {
   constexpr int S = 2 * WR + 1;        // register window: rows i-WR .. i+WR
   constexpr int FMASK = kRingF * kRingSlotBytes - 1, LMASK = kRingL * kRingSlotBytes - 1;
   static_assert(WR >= 1 && WR <= W, "register window inside the tap radius");
@@ -363,7 +377,8 @@ FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, 
     float v = wf[c];                                                                 \
     const bool fg = v > 0.0f;                                                        \
     float out = 0.0f;                                                                \
-    if (cx.any(fg)) {                                                                \
+    const bool skip = PRED && ((pred >> (i >> 5)) & 1ull) != 0;                      \
+    if (!skip && cx.any(fg)) {                                                       \
       /* rows reachable inside the run: consecutive set links above / below the centre */ \
       const int rr = (int)clz32(~(em << (32 - W)));        /* links (i,i+1), (i+1,i+2), ...: bits W-1, W-2, ... */ \
       const int ll = (int)clz32(brev32(~(em >> W)));       /* links (i-1,i), (i-2,i-1), ...: bits W, W+1, ...   */ \
@@ -393,8 +408,10 @@ FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, 
       }                                                                              \
       if (fg) out = last_pass ? cx.sqrt(v) : v;                                      \
       if (cx.any(fg && v > thr)) cx.note_row(i);           /* not final: the envelope kernel redoes this block */ \
+      if (NEXT) { if (cx.any(fg && v > thr_next)) cx.note_next(i); }                 \
     }                                                                                \
-    if (active && (WRITE_BG || fg)) cx.st_f(fw, out);      /* !WRITE_BG: fout already holds 0 on background */ \
+    /* !WRITE_BG: fout already holds 0 on background; skip: the foreground is the envelope warp's */ \
+    if (active && (skip ? (WRITE_BG && !fg) : (WRITE_BG || fg))) cx.st_f(fw, out);   \
     fw += cstride;                                                                   \
   } while (0)
   // prologue: D rows in flight; the links of rows -W .. W-1; the window rows -WR .. WR-1 (row j -> slot (j + WR) mod S)

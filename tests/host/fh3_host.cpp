@@ -50,6 +50,9 @@ struct HostCtx {
   template <typename T> T ring_l(int loff) const { return (T)rl[loff / fh3::kRingSlotBytes]; }
   uint64_t* flag = nullptr;
   void note_row(int row) { if (flag) *flag |= 1ull << (row >> 5); }
+  // roles form: prediction words of the next pass
+  uint64_t* nflag = nullptr; int64_t nstride = 0; uint64_t nbit = 0;
+  void note_next(int row) { if (nflag) nflag[(int64_t)row * nstride] |= nbit; }
 };
 
 template <typename T, int C, int R, int B>
@@ -145,6 +148,7 @@ void hybrid_pass(const uint32_t* labels, const float* fin, float* fout, int n, i
       fh3::stencil_column<uint32_t, W, WR, PF, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true);
     }
   cx.flag = nullptr;
+  if (stats) for (int64_t i = 0; i < ntx * nouter; i++) stats[WRITE_BG ? 6 : 7] += __builtin_popcountll(flags[i]);
   for (int64_t o = 0; o < nouter; o++)
     for (int64_t x = 0; x < sx; x++) {
       const int64_t base = o * ostride + x;
@@ -195,6 +199,140 @@ extern "C" int fh3_host_edt_hybrid(const uint32_t* labels, int64_t sx, int64_t s
     case 2: run_hybrid<12, 8, 5, 6>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
     case 3: run_hybrid<2, 1, 1, 1>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
     case 4: run_hybrid<8, 6, 8, 15>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, out, stats); break;
+    default: return -2;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Roles form of the hybrid pipeline (b2t_edt_config_roles): the previous pass predicts the blocks the stencil
+// cannot finish; per pass an envelope role over the predicted blocks and a stencil role that skips them run
+// concurrently on the device (here: in either order, `order`), then the envelope over what the stencil flagged.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+// like edt_pass_x_v2_kernel<SEG, true>: bit (y >> 5) of pred[z * ntx + tile] when a value of the tile's row exceeds thr
+void predict_from_x(const float* a, int64_t sx, int64_t sy, int64_t sz, float thr, uint64_t* pred, int64_t ntx) {
+  for (int64_t z = 0; z < sz; z++)
+    for (int64_t y = 0; y < sy; y++)
+      for (int64_t x = 0; x < sx; x++)
+        if (a[x + sx * (y + sy * z)] > thr) pred[z * ntx + (x >> 5)] |= 1ull << (y >> 5);
+}
+
+template <int C, int R, int B, bool NEXT>
+void envelope_over(HostCtx& cx, const uint32_t* labels, const float* fin, float* fout, int n, int64_t cstride, int64_t sx,
+                   int64_t nouter, int64_t ostride, float w, int bb, int last, int64_t ntx, const uint64_t* flags,
+                   uint64_t* next, float thr_next, long* stats) {
+  for (int64_t o = 0; o < nouter; o++)
+    for (int64_t t = 0; t < ntx; t++) {
+      uint64_t m = flags[o * ntx + t];
+      while (m) {                                   // maximal groups of consecutive blocks, like the kernels
+        const int b0 = __builtin_ctzll(m);
+        int b1 = b0;
+        while (b1 + 1 < 64 && ((m >> (b1 + 1)) & 1)) b1++;
+        m &= (b1 == 63) ? 0ull : (~0ull << (b1 + 1));
+        const int rlo = 32 * b0, rhi = (32 * b1 + 31 < n - 1) ? 32 * b1 + 31 : n - 1;
+        if (rlo >= n) break;
+        int lo[32], hi[32], rb = fh3::kBig, re = 0;
+        for (int l = 0; l < 32; l++) {              // the warp's common row range
+          const int64_t x = t * 32 + l;
+          lo[l] = fh3::kBig; hi[l] = 0;
+          if (x >= sx) continue;
+          fh3::extend_to_runs<uint32_t>(cx, labels + o * ostride + x, n, cstride, true, rlo, rhi, lo[l], hi[l]);
+          if (lo[l] < rb) rb = lo[l];
+          if (hi[l] > re) re = hi[l];
+        }
+        for (int l = 0; l < 32; l++) {
+          const int64_t x = t * 32 + l;
+          if (x >= sx) continue;
+          const int64_t base = o * ostride + x;
+          for (int q = 0; q < 64; q++) { cx.sv[q] = NAN; cx.sh[q] = NAN; cx.sz[q] = NAN; }
+          cx.nflag = next ? next + t : nullptr; cx.nstride = ntx; cx.nbit = 1ull << (o >> 5);
+          fh3::column_range<uint32_t, C, R, B, true, NEXT>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0,
+                                                           last != 0, true, rb, re, lo[l], hi[l], thr_next);
+        }
+        if (stats) stats[3] += rhi - rlo + 1;
+      }
+    }
+}
+
+template <int W, int WR, int PF, int C, int R, int B, bool WRITE_BG, bool NEXT>
+void roles_pass(const uint32_t* labels, const float* fin, float* fout, int n, int64_t cstride, int64_t sx, int64_t nouter,
+                int64_t ostride, float w, int bb, int last, int64_t ntx, const uint64_t* pred, uint64_t* next, float thr_next,
+                int order, long* stats) {
+  HostCtx cx;
+  cx.lv = (float*)malloc(sizeof(float) * (n + 4)); cx.lh = (float*)malloc(sizeof(float) * (n + 4)); cx.lz = (float*)malloc(sizeof(float) * (n + 4));
+  uint64_t* resid = (uint64_t*)calloc(ntx * nouter, sizeof(uint64_t));
+  for (int step = 0; step < 2; step++) {
+    if ((step == 0) == (order == 0)) {
+      cx.flag = nullptr;
+      envelope_over<C, R, B, NEXT>(cx, labels, fin, fout, n, cstride, sx, nouter, ostride, w, bb, last, ntx, pred, next, thr_next, stats);
+    } else {
+      for (int64_t o = 0; o < nouter; o++)
+        for (int64_t x = 0; x < sx; x++) {
+          const int64_t base = o * ostride + x;
+          cx.flag = resid + o * ntx + (x >> 5);
+          cx.nflag = next ? next + (x >> 5) : nullptr; cx.nstride = ntx; cx.nbit = 1ull << (o >> 5);
+          fh3::stencil_column<uint32_t, W, WR, PF, WRITE_BG, true, NEXT>(cx, labels + base, fin + base, fout + base, n, cstride, w,
+                                                                         bb != 0, last != 0, true, pred[o * ntx + (x >> 5)], thr_next);
+        }
+    }
+  }
+  cx.flag = nullptr;
+  if (stats) for (int64_t i = 0; i < ntx * nouter; i++) stats[4] += __builtin_popcountll(resid[i]);
+  envelope_over<C, R, B, false>(cx, labels, fin, fout, n, cstride, sx, nouter, ostride, w, bb, last, ntx, resid, nullptr, 0.0f, stats);
+  if (stats) stats[0] += cx.spills;
+  free(resid); free(cx.lv); free(cx.lh); free(cx.lz);
+}
+
+template <int WY, int WZ, int WR, int PF>
+void run_roles(const uint32_t* labels, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz, int bb, int ndim,
+               int order, int garbage, float* out, long* stats) {
+  const int64_t V = sx * sy * sz, ntx = (sx + 31) / 32;
+  float* ws = (float*)malloc(sizeof(float) * V);
+  for (int64_t i = 0; i < V; i++) ws[i] = NAN;           // every voxel must be written by someone
+  for (int64_t i = 0; i < V; i++) out[i] = NAN;
+  float* a = (ndim == 3) ? out : ws;     // x -> a, y -> b, z -> a
+  float* b = (ndim == 3) ? ws : out;
+  uint64_t* pred_y = (uint64_t*)calloc(ntx * sz, sizeof(uint64_t));
+  uint64_t* pred_z = (uint64_t*)calloc(ntx * sy, sizeof(uint64_t));
+  pass_x<uint32_t>(labels, a, sx, sy * sz, wx, bb);
+  const float thr_y = wy * wy * (float)((WY + 1) * (WY + 1)), thr_z = wz * wz * (float)((WZ + 1) * (WZ + 1));
+  predict_from_x(a, sx, sy, sz, thr_y, pred_y, ntx);
+  // a prediction is only a hint: any other prediction must give the same result (garbage: 1 = none, 2 = all,
+  // 3 = pseudo-random words)
+  if (garbage) {
+    uint64_t h = 0x9e3779b97f4a7c15ull;
+    for (int64_t i = 0; i < ntx * sz; i++) { h = h * 6364136223846793005ull + 1442695040888963407ull; pred_y[i] = garbage == 1 ? 0ull : (garbage == 2 ? ~0ull : (h & (h >> 7) & (h << 9))); }
+  }
+  if (stats) for (int64_t i = 0; i < ntx * sz; i++) { stats[5] += __builtin_popcountll(pred_y[i]); stats[6] += __builtin_popcountll(pred_y[i]); }
+  roles_pass<WY, (WR < WY ? WR : WY), PF, 4, 16, 4, true, true>(labels, a, b, (int)sy, sx, sx, sz, sx * sy, wy, bb, ndim == 2, ntx, pred_y,
+                                                               ndim == 3 ? pred_z : nullptr, thr_z, order, stats);
+  if (ndim == 3) {
+    if (garbage) {
+      uint64_t h = 0x2545f4914f6cdd1dull;
+      for (int64_t i = 0; i < ntx * sy; i++) { h = h * 6364136223846793005ull + 1442695040888963407ull; pred_z[i] = garbage == 1 ? 0ull : (garbage == 2 ? ~0ull : (h & (h >> 5) & (h << 11))); }
+    }
+    if (stats) for (int64_t i = 0; i < ntx * sy; i++) { stats[5] += __builtin_popcountll(pred_z[i]); stats[7] += __builtin_popcountll(pred_z[i]); }
+    roles_pass<WZ, (WR < WZ ? WR : WZ), PF, 4, 16, 4, false, false>(labels, b, a, (int)sz, sx * sy, sx, sy, sx, wz, bb, 1, ntx, pred_z,
+                                                                   nullptr, 0.0f, order, stats);
+  }
+  free(pred_y); free(pred_z); free(ws);
+}
+
+}  // namespace
+
+// variant as in fh3_host_edt_hybrid; order: 0 = envelope role first, 1 = stencil role first; garbage: see run_roles.
+// stats[3] rows given to envelope warps, stats[4] blocks the stencil flagged outside the prediction, stats[5] predicted blocks
+extern "C" int fh3_host_edt_roles(const uint32_t* labels, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
+                                  int bb, int ndim, int variant, int order, int garbage, float* out, long* stats) {
+  if (sy > fh3::kMaxN || sz > fh3::kMaxN) return -1;
+  switch (variant) {
+    case 0: run_roles<10, 4, 4, 11>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, order, garbage, out, stats); break;
+    case 1: run_roles<4, 4, 4, 4>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, order, garbage, out, stats); break;
+    case 2: run_roles<12, 8, 5, 6>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, order, garbage, out, stats); break;
+    case 3: run_roles<2, 1, 1, 1>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, order, garbage, out, stats); break;
+    case 4: run_roles<8, 6, 8, 15>(labels, sx, sy, sz, wx, wy, wz, bb, ndim, order, garbage, out, stats); break;
     default: return -2;
   }
   return 0;

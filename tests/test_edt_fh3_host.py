@@ -137,3 +137,64 @@ def test_hybrid_known_shapes_and_blobs(fh3):
     got, stats = _host(fh3, lab, (16, 16, 40), False, variant, hybrid=True)
     assert np.array_equal(got, oracle.edt(lab, (16, 16, 40), False))
     assert stats[3] > 0                                      # the envelope kernel had flagged blocks to redo
+
+
+# ---- roles form (b2t_edt_config_roles): the previous pass predicts the stencil's misses; an envelope role over the
+# prediction and a stencil role that skips it write the same buffer concurrently on the device, then the envelope over
+# what the stencil flagged.  The harness runs the two roles in either order and with wrong predictions: the result must
+# not depend on any of it (a prediction decides who computes a voxel, never what the value is).
+def _roles(lib, lab, an, bb, variant, order, garbage=0):
+  lab = np.asarray(lab)
+  ndim = lab.ndim
+  L = oracle._f(lab, np.uint32)
+  sx, sy, sz = L.shape
+  out = np.zeros(L.shape, np.float32, order="F")
+  stats = (ctypes.c_long * 8)()
+  an = tuple(float(a) for a in an) + (1.0,) * (3 - len(an))
+  rc = lib.fh3_host_edt_roles(oracle._p(L), ctypes.c_int64(sx), ctypes.c_int64(sy), ctypes.c_int64(sz),
+                              ctypes.c_float(an[0]), ctypes.c_float(an[1]), ctypes.c_float(an[2]), int(bool(bb)), ndim,
+                              variant, order, garbage, oracle._p(out), stats)
+  assert rc == 0
+  return (out.reshape(lab.shape, order="F") if ndim == 2 else out), tuple(stats)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+def test_roles_bit_identical_random(fh3, variant):
+  rng = np.random.default_rng(300 + variant)
+  for trial in range(10):
+    shape = tuple(int(x) for x in rng.integers(1, 70, size=3))
+    if trial % 5 == 0:
+      shape = (int(rng.integers(1, 40)), int(rng.integers(100, 280)), int(rng.integers(1, 4)))
+    lab = _blocky(rng, shape, int(rng.integers(1, 5)), dense=(trial % 3 == 0))
+    for an in ((1, 1, 1), (16, 16, 40), (4, 4, 40), (40, 32, 20)):
+      for bb in (False, True):
+        ref = oracle.edt(lab, an, bb)
+        for order in (0, 1):
+          got, _ = _roles(fh3, lab, an, bb, variant, order, garbage=(trial + order) % 4)
+          assert np.array_equal(got, ref), (shape, an, bb, order, trial % 4)
+
+
+def test_roles_known_shapes_and_blobs(fh3):
+  plane = np.zeros((257, 257), np.uint32, order="F")
+  plane[1:-1, 1:-1] = 1
+  for order in (0, 1):
+    got, _ = _roles(fh3, plane, (100, 100), True, 0, order)
+    assert np.array_equal(got, oracle.edt(plane, (100, 100), True))
+  ones = np.ones((40, 50, 60), np.uint32, order="F")
+  for bb in (True, False):
+    got, _ = _roles(fh3, ones, (1, 1, 1), bb, 0, 1)
+    assert np.array_equal(got, oracle.edt(ones, (1, 1, 1), bb))
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes((160, 128, 64), 25, seed=77)
+  lab[40:120, 20:110, 8:56] = 999
+  ref = oracle.edt(lab, (16, 16, 40), False)
+  for variant in (0, 1):
+    for order in (0, 1):
+      got, stats = _roles(fh3, lab, (16, 16, 40), False, variant, order)
+      assert np.array_equal(got, ref)
+      # the prediction found the blob (envelope warps had rows to do) and left the stencil little to flag
+      assert stats[3] > 0 and stats[5] > 0
+      assert stats[4] <= stats[5] // 4, stats
+    for garbage in (1, 2, 3):
+      got, _ = _roles(fh3, lab, (16, 16, 40), False, variant, 0, garbage)
+      assert np.array_equal(got, ref)
