@@ -75,8 +75,9 @@ int b2t_edt_config_hybrid(int enable, int wy, int wz, int wr, int pf, int minb);
 /* Tuning hook: enable = 1 runs every column pass of the hybrid as ONE "roles" launch plus a residual one: the previous
  * pass predicts the blocks the stencil cannot finish (x pass -> y, y pass -> z), envelope warps start on them at once
  * while stencil warps do the rest and flag what the prediction missed.  Same result bit for bit; the workspace of
- * b2t_edt_workspace_bytes() already has room for the prediction words. */
-int b2t_edt_config_roles(int enable);
+ * b2t_edt_workspace_bytes() already has room for the prediction words.  stencil_v2 = 1 runs the stencil (roles or not)
+ * with the leaner steady-state loop (labels through a register ring, one shared 32-bit row offset); same result. */
+int b2t_edt_config_roles(int enable, int stencil_v2);
 
 
 /* N1  connected components ------------------------------------------------------------------------

@@ -655,6 +655,11 @@ struct StDevCtx {
       if ((threadIdx.x & 31) == 0) atomicOr(flag, 1ull << blk);
     }
   }
+  template <typename U> __device__ __forceinline__ U ld_label(const U* p) const { return __ldcs(p); }
+  __device__ __forceinline__ void ring_fetch_f(int foff, const float* fp) const {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(fbase + (uint32_t)foff), "l"(fp) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   template <typename U> __device__ __forceinline__ void ring_fetch(int foff, int loff, const U* lp, const float* fp) const {
     static_assert(sizeof(U) == 4, "the ring holds 32-bit labels");
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(fbase + (uint32_t)foff), "l"(fp) : "memory");
@@ -680,7 +685,7 @@ struct StDevCtx {
   }
 };
 
-template <typename T, int W, int WR, int D, int MINB, bool WRITE_BG>
+template <typename T, int W, int WR, int D, int MINB, bool WRITE_BG, int OPT = 0>
 __global__ void __launch_bounds__(128, MINB)
 edt_pass_col_stencil_kernel(const T* __restrict__ labels, const float* __restrict__ fin, float* __restrict__ fout, int n,
                             int64_t cstride, int nx, int64_t ostride, float w, int black_border, int last_pass,
@@ -695,8 +700,12 @@ edt_pass_col_stencil_kernel(const T* __restrict__ labels, const float* __restric
   const int64_t base = (int64_t)blockIdx.y * ostride + (active ? x : nx - 1);   // a lane outside shadows the last column
   StDevCtx cx{flags + (int64_t)blockIdx.y * ntx + tile, -1, (uint32_t)__cvta_generic_to_shared(&s_f[0][threadIdx.x]),
               (uint32_t)__cvta_generic_to_shared(&s_l[0][threadIdx.x])};
-  fh3::stencil_column<T, W, WR, D, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, black_border != 0,
-                                             last_pass != 0, active);
+  if (OPT)
+    fh3::stencil_column_v2<T, W, WR, D, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w,
+                                                  black_border != 0, last_pass != 0, active);
+  else
+    fh3::stencil_column<T, W, WR, D, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, black_border != 0,
+                                               last_pass != 0, active);
 }
 
 // envelope half of the hybrid pass: only the flagged 32-row blocks of a tile, extended to complete runs.
@@ -744,7 +753,7 @@ edt_pass_col_fh3_range_kernel(const T* __restrict__ labels, const float* __restr
 // chain starts at t = 0 and the stencil warps fill the issue slots it leaves.  Both roles report rows above the next
 // pass's threshold (NEXT).  Shared memory: the 48 ring slots of the stencil role are the 3 x 16 plane slots of the
 // envelope role; a thread only ever touches column threadIdx.x of either.
-template <typename T, int W, int WR, int D, int MINB, bool WRITE_BG, bool NEXT, int NMAX, int R, int B>
+template <typename T, int W, int WR, int D, int MINB, bool WRITE_BG, bool NEXT, int NMAX, int R, int B, int OPT>
 __global__ void __launch_bounds__(128, MINB)
 edt_pass_col_roles_kernel(const T* __restrict__ labels, const float* __restrict__ fin, float* __restrict__ fout, int n,
                           int64_t cstride, int nx, int64_t ostride, float w, int black_border, int last_pass,
@@ -787,8 +796,12 @@ edt_pass_col_roles_kernel(const T* __restrict__ labels, const float* __restrict_
     const int64_t base = (int64_t)outer * ostride + (active ? x : nx - 1);   // a lane outside shadows the last column
     StDevCtx cx{resid + (int64_t)outer * ntx + tile, -1, (uint32_t)__cvta_generic_to_shared(&s_raw[0][threadIdx.x]),
                 (uint32_t)__cvta_generic_to_shared(&s_raw[fh3::kRingF][threadIdx.x]), next + tile, ntx, nbit};
-    fh3::stencil_column<T, W, WR, D, WRITE_BG, true, NEXT>(cx, labels + base, fin + base, fout + base, n, cstride, w,
-                                                           black_border != 0, last_pass != 0, active, m, thr_next);
+    if (OPT)
+      fh3::stencil_column_v2<T, W, WR, D, WRITE_BG, true, NEXT>(cx, labels + base, fin + base, fout + base, n, cstride, w,
+                                                                black_border != 0, last_pass != 0, active, m, thr_next);
+    else
+      fh3::stencil_column<T, W, WR, D, WRITE_BG, true, NEXT>(cx, labels + base, fin + base, fout + base, n, cstride, w,
+                                                             black_border != 0, last_pass != 0, active, m, thr_next);
   }
 }
 
@@ -810,10 +823,10 @@ edt_pass_col_fh3_kernel(const T* __restrict__ labels, float* __restrict__ f, int
 // Kernel selection (experiments and A/B timing; results are identical whatever is chosen).  Initialised from the
 // environment -- B2T_EDT_ALGO: 3 = shared-memory-ring F-H (default), 2 = local-memory F-H, w = windowed search;
 // B2T_FH3 = "C,MINB,R,B": one of the compiled instantiations -- and changeable at run time with b2t_edt_config().
-struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hwr, hpf, hminb; int ec, eminb, er, eb; int roles; };
+struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hwr, hpf, hminb; int ec, eminb, er, eb; int roles, sopt; };
 static EdtCfg& edt_cfg() {
   static EdtCfg cfg = []() {
-    EdtCfg c{3, 16, 6, 32, 4, 1, 0, 0, 4, 11, 8, 32, 4, 32, 8, 0};   // hwy = 0: tap radii chosen from the anisotropy
+    EdtCfg c{3, 16, 6, 32, 4, 1, 0, 0, 4, 11, 8, 32, 4, 32, 8, 0, 0};   // hwy = 0: tap radii chosen from the anisotropy
     const char* a = getenv("B2T_EDT_ALGO");
     if (a) c.algo = (a[0] == 'w') ? 1 : (a[0] == '2' ? 2 : 3);
     const char* e = getenv("B2T_FH3");
@@ -822,6 +835,8 @@ static EdtCfg& edt_cfg() {
     if (h) { if (h[0] == '0' && h[1] == 0) c.hybrid = 0; else sscanf(h, "%d,%d,%d,%d,%d", &c.hwy, &c.hwz, &c.hwr, &c.hpf, &c.hminb); }
     const char* r = getenv("B2T_EDT_ROLES");    // "1": predicted envelope + stencil in one launch per pass
     if (r) c.roles = atoi(r);
+    const char* o = getenv("B2T_EDT_STENCIL");  // "2": stencil_column_v2 (leaner steady state)
+    if (o) c.sopt = (atoi(o) == 2) ? 1 : 0;
     return c;
   }();
   return cfg;
@@ -1010,6 +1025,21 @@ static bool edt_launch_hybrid_pass(const uint32_t* labels, const float* fin, flo
           labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, flags, ntx);                           \
     done = true;                                                                                                          \
   }
+  // stencil_column_v2 (b2t_edt_config_roles(., 1)): the two radii the anisotropies in use ask for
+  const bool v2ok = c.sopt && c.hwr == 4 && c.hpf == 11 && c.hminb == 8 && (W == 4 || W == 10) &&
+                    ((int64_t)n + 64) * cstride < (int64_t)0xffffffffll;
+#define B2T_ST2_GO(W_)                                                                                                    \
+  if (!done && v2ok && W == W_) {                                                                                         \
+    if (write_bg)                                                                                                         \
+      edt_pass_col_stencil_kernel<uint32_t, W_, 4, 11, 8, true, 1><<<grid, 128, 0, st>>>(                                 \
+          labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, flags, ntx);                           \
+    else                                                                                                                  \
+      edt_pass_col_stencil_kernel<uint32_t, W_, 4, 11, 8, false, 1><<<grid, 128, 0, st>>>(                                \
+          labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, flags, ntx);                           \
+    done = true;                                                                                                          \
+  }
+  B2T_ST2_GO(4) B2T_ST2_GO(10)
+#undef B2T_ST2_GO
   // tap radius (4 .. 12), register-window radius, prefetch depth, min blocks per SM
   B2T_ST_GO(4, 4, 11, 8) B2T_ST_GO(6, 4, 11, 8) B2T_ST_GO(8, 4, 11, 8) B2T_ST_GO(10, 4, 11, 8)
   B2T_ST_GO(4, 4, 7, 8) B2T_ST_GO(10, 4, 7, 8) B2T_ST_GO(12, 4, 7, 8)
@@ -1041,10 +1071,15 @@ static bool edt_launch_roles_pass(const uint32_t* labels, const float* fin, floa
   const int ntx = b2t_ceil_div(sx, 32);
   const bool nx_ = next != nullptr;
   bool done = false;
+  const bool v2 = c.sopt && ((int64_t)n + 64) * cstride < (int64_t)0xffffffffll;
 #define B2T_RO_GO(W_, BG_, NX_, NM_)                                                                                      \
   if (!done && W == W_ && write_bg == BG_ && nx_ == NX_ && n <= NM_) {                                                    \
-    edt_pass_col_roles_kernel<uint32_t, W_, 4, 11, 8, BG_, NX_, NM_, 32, 4><<<grid, 128, 0, st>>>(                        \
-        labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, pred, resid, next, thr_next, ntx);        \
+    if (v2)                                                                                                               \
+      edt_pass_col_roles_kernel<uint32_t, W_, 4, 11, 8, BG_, NX_, NM_, 32, 4, 1><<<grid, 128, 0, st>>>(                   \
+          labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, pred, resid, next, thr_next, ntx);      \
+    else                                                                                                                  \
+      edt_pass_col_roles_kernel<uint32_t, W_, 4, 11, 8, BG_, NX_, NM_, 32, 4, 0><<<grid, 128, 0, st>>>(                   \
+          labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, pred, resid, next, thr_next, ntx);      \
     done = true;                                                                                                          \
   }
 #define B2T_RO_ALL(W_) B2T_RO_GO(W_, true, true, 512) B2T_RO_GO(W_, true, true, 2048) B2T_RO_GO(W_, false, false, 512) \
@@ -1144,8 +1179,9 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
   return B2T_OK;
 }
 
-B2T_EXPORT int b2t_edt_config_roles(int enable) {
+B2T_EXPORT int b2t_edt_config_roles(int enable, int stencil_v2) {
   edt_cfg().roles = enable ? 1 : 0;
+  edt_cfg().sopt = stencil_v2 ? 1 : 0;
   return B2T_OK;
 }
 

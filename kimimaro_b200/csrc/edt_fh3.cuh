@@ -447,6 +447,166 @@ FH3_HD void stencil_column(Ctx& cx, const T* lp, const float* fin, float* fout, 
 #undef FH3_ROW
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// stencil_column_v2: the same pass with a leaner steady state.  The per-SASS-line counts of the shipped stencil
+// (profiles/r01_edt_hybrid_sass_stencil_z.txt) put ~50 warp instructions of FIXED cost on every row, background
+// included: a 7-instruction "is this block steady" test per row, two 64-bit pointer bumps plus register-pair copies
+// per stream (three streams), a second shared-memory ring for the labels with its own address, offset and mask
+// upkeep, and three row counters that only the column ends need.  Here
+//   * the steady loop is its own loop (the column ends run a generic copy of the same phases);
+//   * labels travel global -> REGISTERS: a ring lr[S] with static indices, phase ph consumes the label of row i+W that
+//     it loaded S rows earlier and reloads the slot, so the label ring in shared memory and its upkeep are gone;
+//   * every global address of a row is base pointer + ONE shared 32-bit element offset (one add per row, one
+//     multiply-add-wide per stream);
+//   * the row counters exist only in the generic loop.
+// Same arithmetic, same order of operations on the values: results are bit-identical to stencil_column.  The caller
+// guarantees (n + W + D + S) * cstride < 2^32.
+// Extra context call: ring_fetch_f(foff, fp) starts the copy of one real row's f and closes a group.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int W, int WR, int D, bool WRITE_BG, bool PRED = false, bool NEXT = false, typename Ctx>
+FH3_HD void stencil_column_v2(Ctx& cx, const T* lp, const float* fin, float* fout, int n, int64_t cstride, float w,
+                              bool black_border, bool last_pass, bool active, uint64_t pred = 0, float thr_next = 0.0f) {
+  constexpr int S = 2 * WR + 1;        // register window: rows i-WR .. i+WR; also the depth of the label ring
+  constexpr int FMASK = kRingF * kRingSlotBytes - 1;
+  static_assert(WR >= 1 && WR <= W, "register window inside the tap radius");
+  static_assert(D >= 1 && 2 * W + D + 1 <= kRingF, "rows i-W .. i+W+D must fit the f ring");
+  const float w2 = cx.mul(w, w);
+  const float kInf = u2f(0x7f800000u);
+  float cd[WR + 1];
+#pragma unroll
+  for (int d = 0; d <= WR; d++) cd[d] = cx.mul(cx.mul(w2, (float)d), (float)d);
+  const float thr = cx.mul(cx.mul(w2, (float)(W + 1)), (float)(W + 1));
+  const float edge_f = black_border ? 0.0f : kInf;
+  const uint32_t edge_link = black_border ? 0u : 1u;
+  const uint32_t cs = (uint32_t)cstride;
+  float wf[S];
+  T lr[S];                     // lr[ph]: label of row base + ph + W (loaded one block of S rows earlier)
+  uint32_t em = 0xffffffffu;   // bit t: rows (j-t-1, j-t) carry the same label, j = i + W (newest linked row)
+  T lprev = T(0);
+  int fo = 0;                  // f-ring offset of the fetch front (row i + W + D)
+  int ao = 0;                  // f-ring offset of the admit front (row i + WR)
+  uint32_t eo = 0;             // element offset of row i: i * cstride
+  // generic steps (prologue and column end): rows outside the array are virtual
+#define FH3_FETCH2(jf_)                                                              \
+  do {                                                                               \
+    const int jf = (jf_);                                                            \
+    if (jf >= 0 && jf < n) cx.ring_fetch_f(fo, fin + (int64_t)jf * cstride);         \
+    else cx.ring_put(fo, edge_f);                                                    \
+    fo = (fo + kRingSlotBytes) & FMASK;                                              \
+  } while (0)
+#define FH3_LINK2(jl_, lab_)                                                         \
+  do {                                                                               \
+    const int jl = (jl_);                                                            \
+    uint32_t link = 1u;                                                              \
+    if (jl >= 0 && jl < n) {                                                         \
+      const T lj = (lab_);                                                           \
+      link = (jl == 0) ? edge_link : (uint32_t)(lj == lprev);                        \
+      lprev = lj;                                                                    \
+    } else if (jl == n) {                                                            \
+      link = edge_link;                                                              \
+    }                                                                                \
+    em = (em << 1) | link;                                                           \
+  } while (0)
+#define FH3_ADMIT2(slot_)                                                            \
+  do {                                                                               \
+    wf[slot_] = cx.ring_f(ao);                                                       \
+    ao = (ao + kRingSlotBytes) & FMASK;                                              \
+  } while (0)
+  // one row: centre i = window slot (ph + WR) % S; its f-ring offset is WR + 1 slots behind the admit front
+#define FH3_ROW2(ph_)                                                                \
+  do {                                                                               \
+    const int c = ((ph_) + WR) % S;                                                  \
+    float v = wf[c];                                                                 \
+    const bool fg = v > 0.0f;                                                        \
+    float out = 0.0f;                                                                \
+    const bool skip = PRED && ((pred >> (i >> 5)) & 1ull) != 0;                      \
+    if (!skip && cx.any(fg)) {                                                       \
+      const int rr = (int)clz32(~(em << (32 - W)));                                  \
+      const int ll = (int)clz32(brev32(~(em >> W)));                                 \
+      if (rr < W) { const float e = (float)(rr + 1); v = cx.fmin(v, cx.mul(cx.mul(w2, e), e)); } \
+      if (ll < W) { const float e = (float)(ll + 1); v = cx.fmin(v, cx.mul(cx.mul(w2, e), e)); } \
+      const float mx = cx.wmaxf(fg ? v : 0.0f);                                      \
+      bool far = W > WR;                                                             \
+      _Pragma("unroll")                                                              \
+      for (int d = 1; d <= WR; d++) {                                                \
+        if (!(cd[d] < mx)) { far = false; break; }                                   \
+        const int cp = ((ph_) + WR + d) % S, cm = ((ph_) + WR - d + S) % S;          \
+        const float fp_ = (d <= rr) ? wf[cp] : 0.0f;                                 \
+        const float fm_ = (d <= ll) ? wf[cm] : 0.0f;                                 \
+        v = cx.fmin(v, cx.add(cx.fmin(fp_, fm_), cd[d]));                            \
+      }                                                                              \
+      if (W > WR && far) {                                                           \
+        const int co = ao - (WR + 1) * kRingSlotBytes;                               \
+        _Pragma("unroll 1")                                                          \
+        for (int d = WR + 1; d <= W; d++) {                                          \
+          const float cdd = cx.mul(cx.mul(w2, (float)d), (float)d);                  \
+          if (!(cdd < mx)) break;                                                    \
+          const float fp_ = (d <= rr) ? cx.ring_f((co + d * kRingSlotBytes) & FMASK) : 0.0f; \
+          const float fm_ = (d <= ll) ? cx.ring_f((co - d * kRingSlotBytes) & FMASK) : 0.0f; \
+          v = cx.fmin(v, cx.add(cx.fmin(fp_, fm_), cdd));                            \
+        }                                                                            \
+      }                                                                              \
+      if (fg) out = last_pass ? cx.sqrt(v) : v;                                      \
+      if (cx.any(fg && v > thr)) cx.note_row(i);                                     \
+      if (NEXT) { if (cx.any(fg && v > thr_next)) cx.note_next(i); }                 \
+    }                                                                                \
+    if (active && (skip ? (WRITE_BG && !fg) : (WRITE_BG || fg))) cx.st_f(fout + eo, out); \
+    eo += cs;                                                                        \
+  } while (0)
+  // prologue: D rows in flight; the links of rows -W .. W-1 (labels read directly); the label ring for rows W .. W+S-1;
+  // the window rows -WR .. WR-1 (row j -> slot (j + WR) mod S)
+  for (int t = 0; t < D; t++) FH3_FETCH2(-W + t);
+  for (int t = 0; t < 2 * W; t++) {
+    FH3_FETCH2(-W + D + t);
+    cx.template ring_wait<D>();
+    const int jp = -W + t;
+    FH3_LINK2(jp, cx.ld_label(lp + (int64_t)jp * cstride));
+  }
+#pragma unroll
+  for (int t = 0; t < S; t++) lr[t] = (W + t < n) ? cx.ld_label(lp + (int64_t)(W + t) * cstride) : T(0);
+  ao = ((W - WR) * kRingSlotBytes) & FMASK;                // the rows -W .. -WR-1 stay in the ring only
+#pragma unroll
+  for (int t = 0; t < S - 1; t++) FH3_ADMIT2(t);
+  const float* finF = fin + (int64_t)(W + D) * cstride;    // row i + W + D
+  const T* lpS = lp + (int64_t)(W + S) * cstride;          // row i + W + S
+  int base = 0;
+  // steady state: the fetched row i+W+D, the linked row i+W and the label row i+W+S are ordinary rows
+  for (; base + S - 1 + W + (D > S ? D : S) < n; base += S) {
+#pragma unroll
+    for (int ph = 0; ph < S; ph++) {
+      const int i = base + ph;
+      cx.ring_fetch_f(fo, finF + eo);
+      fo = (fo + kRingSlotBytes) & FMASK;
+      cx.template ring_wait<D>();
+      const T lj = lr[ph];
+      em = (em << 1) | (uint32_t)(lj == lprev);
+      lprev = lj;
+      lr[ph] = cx.ld_label(lpS + eo);
+      FH3_ADMIT2((ph + S - 1) % S);
+      FH3_ROW2(ph);
+    }
+  }
+  for (; base < n; base += S) {
+#pragma unroll
+    for (int ph = 0; ph < S; ph++) {
+      const int i = base + ph;
+      if (i < n) {
+        FH3_FETCH2(i + W + D);
+        cx.template ring_wait<D>();
+        FH3_LINK2(i + W, lr[ph]);
+        if (i + W + S < n) lr[ph] = cx.ld_label(lpS + eo);
+        FH3_ADMIT2((ph + S - 1) % S);
+        FH3_ROW2(ph);
+      }
+    }
+  }
+  cx.template ring_wait<0>();
+#undef FH3_FETCH2
+#undef FH3_LINK2
+#undef FH3_ADMIT2
+#undef FH3_ROW2
+}
+
 // the rows a lane contributes to the envelope half: the complete runs that meet [rlo, rhi]
 template <typename T, typename Ctx>
 FH3_HD void extend_to_runs(Ctx& cx, const T* lp, int n, int64_t cstride, bool active, int rlo, int rhi, int& own_lo,

@@ -80,12 +80,13 @@ def d2h(arr, src):
   cu(rt.cudaMemcpy(arr.ctypes.data_as(c_vp), src, arr.nbytes, 2), "d2h")
 
 
-# (name, hybrid on, roles on, envelope variant (c, minb, r, b) or None)
+# (name, hybrid on, roles on, stencil_column_v2 on, envelope variant (c, minb, r, b) or None)
 FORMS = [
-  ("hybrid (shipped default)", 1, 0, None),
-  ("roles", 1, 1, None),
-  ("roles + residual envelope C=16 minb=6 B=4", 1, 1, (16, 6, 32, 4)),
-  ("envelope only (b2t_edt path)", 0, 0, None),
+  ("hybrid (shipped default)", 1, 0, 0, None),
+  ("hybrid + stencil v2", 1, 0, 1, None),
+  ("roles", 1, 1, 0, None),
+  ("roles + stencil v2", 1, 1, 1, None),
+  ("envelope only (b2t_edt path)", 0, 0, 0, None),
 ]
 
 
@@ -166,10 +167,10 @@ def main():
 
   first = True
   small_ref = None
-  for name, hybrid, roles, env in FORMS:
+  for name, hybrid, roles, sv2, env in FORMS:
     try:
       ok(b2t.b2t_edt_config_hybrid(hybrid, 0, 0, 4, 11, 8), "config_hybrid")
-      ok(b2t.b2t_edt_config_roles(roles), "config_roles")
+      ok(b2t.b2t_edt_config_roles(roles, sv2), "config_roles")
       if env:
         ok(b2t.b2t_edt_config(3, *env), "config")
       dst = d_ref if first else d_out

@@ -8,6 +8,9 @@
 
 #include "../../kimimaro_b200/csrc/edt_fh3.cuh"
 
+static int g_stencil_v2 = 0;   // 1: the stencil passes run fh3::stencil_column_v2
+extern "C" void fh3_host_set_stencil(int v2) { g_stencil_v2 = v2; }
+
 namespace {
 
 struct HostCtx {
@@ -44,6 +47,7 @@ struct HostCtx {
   template <typename T> void ring_fetch(int foff, int loff, const T* lp, const float* fp) {
     rl[loff / fh3::kRingSlotBytes] = (uint32_t)*lp; rf[foff / fh3::kRingSlotBytes] = *fp;
   }
+  void ring_fetch_f(int foff, const float* fp) { rf[foff / fh3::kRingSlotBytes] = *fp; }
   void ring_put(int foff, float f) { rf[foff / fh3::kRingSlotBytes] = f; }
   template <int N> void ring_wait() const {}
   float ring_f(int foff) const { return rf[foff / fh3::kRingSlotBytes]; }
@@ -145,7 +149,10 @@ void hybrid_pass(const uint32_t* labels, const float* fin, float* fout, int n, i
     for (int64_t x = 0; x < sx; x++) {
       const int64_t base = o * ostride + x;
       cx.flag = flags + o * ntx + (x >> 5);
-      fh3::stencil_column<uint32_t, W, WR, PF, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true);
+      if (g_stencil_v2)
+        fh3::stencil_column_v2<uint32_t, W, WR, PF, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true);
+      else
+        fh3::stencil_column<uint32_t, W, WR, PF, WRITE_BG>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true);
     }
   cx.flag = nullptr;
   if (stats) for (int64_t i = 0; i < ntx * nouter; i++) stats[WRITE_BG ? 6 : 7] += __builtin_popcountll(flags[i]);
@@ -273,8 +280,12 @@ void roles_pass(const uint32_t* labels, const float* fin, float* fout, int n, in
           const int64_t base = o * ostride + x;
           cx.flag = resid + o * ntx + (x >> 5);
           cx.nflag = next ? next + (x >> 5) : nullptr; cx.nstride = ntx; cx.nbit = 1ull << (o >> 5);
-          fh3::stencil_column<uint32_t, W, WR, PF, WRITE_BG, true, NEXT>(cx, labels + base, fin + base, fout + base, n, cstride, w,
-                                                                         bb != 0, last != 0, true, pred[o * ntx + (x >> 5)], thr_next);
+          if (g_stencil_v2)
+            fh3::stencil_column_v2<uint32_t, W, WR, PF, WRITE_BG, true, NEXT>(cx, labels + base, fin + base, fout + base, n, cstride, w,
+                                                                              bb != 0, last != 0, true, pred[o * ntx + (x >> 5)], thr_next);
+          else
+            fh3::stencil_column<uint32_t, W, WR, PF, WRITE_BG, true, NEXT>(cx, labels + base, fin + base, fout + base, n, cstride, w,
+                                                                           bb != 0, last != 0, true, pred[o * ntx + (x >> 5)], thr_next);
         }
     }
   }

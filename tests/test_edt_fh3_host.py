@@ -107,8 +107,16 @@ def test_non_integer_anisotropy(fh3):
 # ---- hybrid pass (b2t_edt_ws): stencil everywhere + envelope on the flagged blocks, out of place ----
 # variant = stencil windows (y, z) and prefetch, see fh3_host.cpp; every voxel of the result must have been
 # written by one of the two kernels (the harness poisons both buffers with NaN)
+@pytest.fixture(params=[0, 1], ids=["stencil_v1", "stencil_v2"])
+def stencil(fh3, request):
+  """Both stencil bodies of edt_fh3.cuh: stencil_column (shipped) and stencil_column_v2 (leaner steady state)."""
+  fh3.fh3_host_set_stencil(request.param)
+  yield request.param
+  fh3.fh3_host_set_stencil(0)
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
-def test_hybrid_bit_identical_random(fh3, variant):
+def test_hybrid_bit_identical_random(fh3, variant, stencil):
   rng = np.random.default_rng(200 + variant)
   for trial in range(12):
     shape = tuple(int(x) for x in rng.integers(1, 60, size=3))
@@ -121,7 +129,7 @@ def test_hybrid_bit_identical_random(fh3, variant):
         assert np.array_equal(got, oracle.edt(lab, an, bb)), (shape, an, bb)
 
 
-def test_hybrid_known_shapes_and_blobs(fh3):
+def test_hybrid_known_shapes_and_blobs(fh3, stencil):
   plane = np.zeros((257, 257), np.uint32, order="F")
   plane[1:-1, 1:-1] = 1
   got, _ = _host(fh3, plane, (100, 100), True, 0, hybrid=True)
@@ -159,7 +167,7 @@ def _roles(lib, lab, an, bb, variant, order, garbage=0):
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
-def test_roles_bit_identical_random(fh3, variant):
+def test_roles_bit_identical_random(fh3, variant, stencil):
   rng = np.random.default_rng(300 + variant)
   for trial in range(10):
     shape = tuple(int(x) for x in rng.integers(1, 70, size=3))
@@ -174,7 +182,7 @@ def test_roles_bit_identical_random(fh3, variant):
           assert np.array_equal(got, ref), (shape, an, bb, order, trial % 4)
 
 
-def test_roles_known_shapes_and_blobs(fh3):
+def test_roles_known_shapes_and_blobs(fh3, stencil):
   plane = np.zeros((257, 257), np.uint32, order="F")
   plane[1:-1, 1:-1] = 1
   for order in (0, 1):
