@@ -76,8 +76,9 @@ int b2t_edt_config_hybrid(int enable, int wy, int wz, int wr, int pf, int minb);
  * pass predicts the blocks the stencil cannot finish (x pass -> y, y pass -> z), envelope warps start on them at once
  * while stencil warps do the rest and flag what the prediction missed.  Same result bit for bit; the workspace of
  * b2t_edt_workspace_bytes() already has room for the prediction words.  stencil_v2 = 1 runs the stencil (roles or not)
- * with the leaner steady-state loop (labels through a register ring, one shared 32-bit row offset); same result. */
-int b2t_edt_config_roles(int enable, int stencil_v2);
+ * with the leaner steady-state loop (labels through a register ring, one shared 32-bit row offset); same result.
+ * predict_scale >= 1 scales the thresholds of the prediction (1 = every block that can need the envelope). */
+int b2t_edt_config_roles(int enable, int stencil_v2, float predict_scale);
 
 
 /* N1  connected components ------------------------------------------------------------------------

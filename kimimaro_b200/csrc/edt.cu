@@ -823,10 +823,10 @@ edt_pass_col_fh3_kernel(const T* __restrict__ labels, float* __restrict__ f, int
 // Kernel selection (experiments and A/B timing; results are identical whatever is chosen).  Initialised from the
 // environment -- B2T_EDT_ALGO: 3 = shared-memory-ring F-H (default), 2 = local-memory F-H, w = windowed search;
 // B2T_FH3 = "C,MINB,R,B": one of the compiled instantiations -- and changeable at run time with b2t_edt_config().
-struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hwr, hpf, hminb; int ec, eminb, er, eb; int roles, sopt; };
+struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hwr, hpf, hminb; int ec, eminb, er, eb; int roles, sopt; float pscale; };
 static EdtCfg& edt_cfg() {
   static EdtCfg cfg = []() {
-    EdtCfg c{3, 16, 6, 32, 4, 1, 0, 0, 4, 11, 8, 32, 4, 32, 8, 0, 0};   // hwy = 0: tap radii chosen from the anisotropy
+    EdtCfg c{3, 16, 6, 32, 4, 1, 0, 0, 4, 11, 8, 32, 4, 32, 8, 0, 0, 1.0f};   // hwy = 0: tap radii chosen from the anisotropy
     const char* a = getenv("B2T_EDT_ALGO");
     if (a) c.algo = (a[0] == 'w') ? 1 : (a[0] == '2' ? 2 : 3);
     const char* e = getenv("B2T_FH3");
@@ -1148,7 +1148,8 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
   if (roles) {
     const int64_t nrows = sy * sz;
     const unsigned blocks = (unsigned)((nrows + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    const float thr_y = wy * wy * (float)((hwy + 1) * (hwy + 1)), thr_z = wz * wz * (float)((hwz + 1) * (hwz + 1));
+    // pscale > 1 predicts fewer blocks (experiments; what it misses is flagged by the stencil and done by the residual launch)
+    const float thr_y = c.pscale * wy * wy * (float)((hwy + 1) * (hwy + 1)), thr_z = c.pscale * wz * wz * (float)((hwz + 1) * (hwz + 1));
     if (sx <= 128) edt_pass_x_v2_kernel<4, true><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border, pred_y, thr_y, (int)sy, (int)ntx);
     else if (sx <= 256) edt_pass_x_v2_kernel<8, true><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border, pred_y, thr_y, (int)sy, (int)ntx);
     else edt_pass_x_v2_kernel<16, true><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border, pred_y, thr_y, (int)sy, (int)ntx);
@@ -1179,9 +1180,10 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
   return B2T_OK;
 }
 
-B2T_EXPORT int b2t_edt_config_roles(int enable, int stencil_v2) {
+B2T_EXPORT int b2t_edt_config_roles(int enable, int stencil_v2, float predict_scale) {
   edt_cfg().roles = enable ? 1 : 0;
   edt_cfg().sopt = stencil_v2 ? 1 : 0;
+  edt_cfg().pscale = predict_scale >= 1.0f ? predict_scale : 1.0f;
   return B2T_OK;
 }
 

@@ -43,6 +43,7 @@ if rt is None:   # libb2t.so pulled its own libcudart in
 b2t.b2t_last_error.restype = ctypes.c_char_p
 b2t.b2t_edt_workspace_bytes.restype = c_sz
 b2t.b2t_edt_workspace_bytes.argtypes = [c_i64, c_i64, c_i64]
+b2t.b2t_edt_config_roles.argtypes = [c_int, c_int, c_f32]
 b2t.b2t_edt_ws.argtypes = [c_vp, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_vp, c_vp, c_sz, c_vp]
 rt.cudaMalloc.argtypes = [ctypes.POINTER(c_vp), c_sz]
 rt.cudaMemcpy.argtypes = [c_vp, c_vp, c_sz, c_int]
@@ -80,13 +81,15 @@ def d2h(arr, src):
   cu(rt.cudaMemcpy(arr.ctypes.data_as(c_vp), src, arr.nbytes, 2), "d2h")
 
 
-# (name, hybrid on, roles on, stencil_column_v2 on, envelope variant (c, minb, r, b) or None)
+# (name, hybrid on, roles on, stencil_column_v2 on, prediction scale)
 FORMS = [
-  ("hybrid (shipped default)", 1, 0, 0, None),
-  ("hybrid + stencil v2", 1, 0, 1, None),
-  ("roles", 1, 1, 0, None),
-  ("roles + stencil v2", 1, 1, 1, None),
-  ("envelope only (b2t_edt path)", 0, 0, 0, None),
+  ("hybrid (shipped default)", 1, 0, 0, 1.0),
+  ("hybrid + stencil v2", 1, 0, 1, 1.0),
+  ("roles", 1, 1, 0, 1.0),
+  ("roles + stencil v2", 1, 1, 1, 1.0),
+  ("roles + stencil v2, prediction x2", 1, 1, 1, 2.0),
+  ("roles + stencil v2, prediction x4", 1, 1, 1, 4.0),
+  ("envelope only (b2t_edt path)", 0, 0, 0, 1.0),
 ]
 
 
@@ -167,12 +170,10 @@ def main():
 
   first = True
   small_ref = None
-  for name, hybrid, roles, sv2, env in FORMS:
+  for name, hybrid, roles, sv2, pscale in FORMS:
     try:
       ok(b2t.b2t_edt_config_hybrid(hybrid, 0, 0, 4, 11, 8), "config_hybrid")
-      ok(b2t.b2t_edt_config_roles(roles, sv2), "config_roles")
-      if env:
-        ok(b2t.b2t_edt_config(3, *env), "config")
+      ok(b2t.b2t_edt_config_roles(roles, sv2, c_f32(pscale)), "config_roles")
       dst = d_ref if first else d_out
       cu(rt.cudaMemset(dst, 0xff, V * 4), "poison")
       cu(rt.cudaMemset(d_ws, 0xff, V * 4), "poison")           # a voxel nobody writes stays a NaN
