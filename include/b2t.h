@@ -79,6 +79,10 @@ int b2t_edt_config_hybrid(int enable, int wy, int wz, int wr, int pf, int minb);
  * with the leaner steady-state loop (labels through a register ring, one shared 32-bit row offset); same result.
  * predict_scale >= 1 scales the thresholds of the prediction (1 = every block that can need the envelope). */
 int b2t_edt_config_roles(int enable, int stencil_v2, float predict_scale);
+/* Tuning hook of the hybrid's envelope kernel: query_prefetch = 4 keeps the next four stack entries of the write-out in
+ * registers (the stack of a blob lives in local memory; its walk was one L2 round trip per row), 1 = the original loop.
+ * Same result. */
+int b2t_edt_config_envelope(int query_prefetch);
 
 
 /* N1  connected components ------------------------------------------------------------------------

@@ -99,7 +99,13 @@ FH3_HD float intersect(Ctx& cx, float fi, float ir, float h, float v, float w2) 
 //   part with the rows [own_lo, own_hi) (complete runs by construction); the rest of the range is treated as
 //   background.  Background is never written.
 // NEXT: rows whose (squared) result exceeds thr_next are reported with cx.note_next (prediction for the next pass).
-template <typename T, int C, int R, int B, bool RANGE, bool NEXT = false, typename Ctx>
+// QP: entries the query keeps in registers AHEAD of the one it is evaluating.  The per-SASS-line stall samples of the
+// envelope kernel (profiles/r01_edt_hybrid_sass_envelope_y.txt) put 21 % of all samples on one compare: the query's
+// `while (next left end < row)` waiting for the left end it has just asked local memory for -- a blob's stack is hundreds
+// of entries deep, far beyond the ring, and every row of the write-out walks one entry further, one L2 round trip at a
+// time.  With QP > 1 the next QP entries (apex, height, left end) are already in registers and each step only issues the
+// load of the entry QP steps ahead.  QP = 1 is the original code.
+template <typename T, int C, int R, int B, bool RANGE, bool NEXT = false, int QP = 1, typename Ctx>
 FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, int n, int64_t cstride, float w,
                          bool black_border, bool last_pass, bool active, int rb, int re, int own_lo, int own_hi,
                          float thr_next = 0.0f) {
@@ -209,6 +215,9 @@ FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, in
       int qa = todo ? -1 : kBig, qb = qa;        // rows [qa, qb) of the run being written; qb <= i: fetch the next
       int kq = 0, kend = 0;
       float qaf = 0.0f, qbf = 0.0f, cv = 0.0f, ch = 0.0f, nz = kInf;
+      float pv[QP], ph[QP], pz[QP];              // QP > 1: entries kq+1 .. kq+QP (left end +inf past the run's last one)
+#pragma unroll
+      for (int j = 0; j < QP; j++) { pv[j] = 0.0f; ph[j] = 0.0f; pz[j] = kInf; }
       bool bl = false, br = false;
       float* fw = fout + lo * cstride;
       float iqf = (float)lo;
@@ -223,7 +232,19 @@ FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, in
             qbf = (float)qb;
             kq = kn; kend = kn + (int)(pk & 0x7ffu); kn = kend;
             cv = 0.0f; ch = FH3_LD_H(kq);
-            nz = (kq + 1 < kend) ? FH3_LD_Z(kq + 1) : kInf;
+            if (QP == 1) {
+              nz = (kq + 1 < kend) ? FH3_LD_Z(kq + 1) : kInf;
+            } else {
+#pragma unroll
+              for (int j = 0; j < QP; j++) {
+                const int e = kq + 1 + j;
+                const bool in = e < kend;
+                pz[j] = in ? FH3_LD_Z(e) : kInf;
+                pv[j] = in ? FH3_LD_V(e) : 0.0f;
+                ph[j] = in ? FH3_LD_H(e) : 0.0f;
+              }
+              nz = pz[0];
+            }
             bl = (qa > 0) || black_border;
             br = (qb < n) || black_border;
           } else {
@@ -234,9 +255,22 @@ FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, in
           const float ir = iqf - qaf;
           while (nz < ir) {
             kq++;
-            cv = FH3_LD_V(kq) - qaf;
-            ch = FH3_LD_H(kq);
-            nz = (kq + 1 < kend) ? FH3_LD_Z(kq + 1) : kInf;
+            if (QP == 1) {
+              cv = FH3_LD_V(kq) - qaf;
+              ch = FH3_LD_H(kq);
+              nz = (kq + 1 < kend) ? FH3_LD_Z(kq + 1) : kInf;
+            } else {
+              cv = pv[0] - qaf;
+              ch = ph[0];
+#pragma unroll
+              for (int j = 0; j + 1 < QP; j++) { pv[j] = pv[j + 1]; ph[j] = ph[j + 1]; pz[j] = pz[j + 1]; }
+              const int e = kq + QP;
+              const bool in = e < kend;
+              pz[QP - 1] = in ? FH3_LD_Z(e) : kInf;
+              pv[QP - 1] = in ? FH3_LD_V(e) : 0.0f;
+              ph[QP - 1] = in ? FH3_LD_H(e) : 0.0f;
+              nz = pz[0];
+            }
           }
           const float di = cx.sub(ir, cv);
           float val = cx.add(cx.mul(cx.mul(w2, di), di), ch);

@@ -10,6 +10,8 @@
 
 static int g_stencil_v2 = 0;   // 1: the stencil passes run fh3::stencil_column_v2
 extern "C" void fh3_host_set_stencil(int v2) { g_stencil_v2 = v2; }
+static int g_query_prefetch = 1;   // 4: the envelope's write-out keeps four entries ahead (QP of fh3::column_range)
+extern "C" void fh3_host_set_query_prefetch(int qp) { g_query_prefetch = qp; }
 
 namespace {
 
@@ -169,8 +171,12 @@ void hybrid_pass(const uint32_t* labels, const float* fin, float* fout, int n, i
         int own_lo, own_hi;
         fh3::extend_to_runs<uint32_t>(cx, labels + base, n, cstride, true, rlo, rhi, own_lo, own_hi);
         for (int q = 0; q < 64; q++) { cx.sv[q] = NAN; cx.sh[q] = NAN; cx.sz[q] = NAN; }
-        fh3::column_range<uint32_t, C, R, B, true>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true,
-                                                   own_lo, own_hi, own_lo, own_hi);
+        if (g_query_prefetch == 4)
+          fh3::column_range<uint32_t, C, R, B, true, false, 4>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true,
+                                                               own_lo, own_hi, own_lo, own_hi);
+        else
+          fh3::column_range<uint32_t, C, R, B, true>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true,
+                                                     own_lo, own_hi, own_lo, own_hi);
         if (stats) stats[3] += rhi - rlo + 1;
       }
     }
@@ -255,8 +261,12 @@ void envelope_over(HostCtx& cx, const uint32_t* labels, const float* fin, float*
           const int64_t base = o * ostride + x;
           for (int q = 0; q < 64; q++) { cx.sv[q] = NAN; cx.sh[q] = NAN; cx.sz[q] = NAN; }
           cx.nflag = next ? next + t : nullptr; cx.nstride = ntx; cx.nbit = 1ull << (o >> 5);
-          fh3::column_range<uint32_t, C, R, B, true, NEXT>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0,
-                                                           last != 0, true, rb, re, lo[l], hi[l], thr_next);
+          if (g_query_prefetch == 4)
+            fh3::column_range<uint32_t, C, R, B, true, NEXT, 4>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0,
+                                                                last != 0, true, rb, re, lo[l], hi[l], thr_next);
+          else
+            fh3::column_range<uint32_t, C, R, B, true, NEXT>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0,
+                                                             last != 0, true, rb, re, lo[l], hi[l], thr_next);
         }
         if (stats) stats[3] += rhi - rlo + 1;
       }
