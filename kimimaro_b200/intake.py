@@ -7,8 +7,9 @@ Deviations from the reference, all explicit:
   * parallel      one process drives one GPU and the device traces all labels concurrently, so the
                   argument is accepted and ignored here; multi-GPU runs shard labels across
                   processes (kimimaro_b200.distributed).
-  * fill_holes, fix_avocados, voxel_graph, CrackleArray input: not built yet
+  * fix_avocados, voxel_graph, CrackleArray input: not built yet
                    -> NotImplementedError, never a silent CPU path.
+                  fill_holes is built (fill_all_holes below: b2t_fill_voids per component).
   * tie rules T1-T5 (oracle/oracle.c header) where the reference leaves ties to heap / sort internals.
 """
 import ctypes
@@ -97,6 +98,53 @@ def _find_soma_root(d_dbf, shape, dbf_max):
   return tuple(coords[root].astype(np.uint32))
 
 
+def _fill_voids(mask, shape):
+  """fill_voids.fill(mask, in_place=True, return_fill_count=True) (trace.py:109, intake.py:779) on a flat uint8
+  device mask in Fortran order; returns the number of voxels filled."""
+  V = shape[0] * shape[1] * shape[2]
+  dev = mask.device
+  reach = torch.empty(V, dtype=torch.int32, device=dev)
+  queue = torch.empty(2 * V, dtype=torch.int32, device=dev)
+  ctrl = torch.zeros(16, dtype=torch.int32, device=dev)
+  check(lib().b2t_fill_voids(c_vp(mask.data_ptr()), c_i64(shape[0]), c_i64(shape[1]), c_i64(shape[2]),
+                             c_vp(reach.data_ptr()), c_vp(queue.data_ptr()), c_u64(V), c_vp(ctrl.data_ptr()),
+                             stream_ptr()), "b2t_fill_voids")
+  return int(ctrl[5].item())
+
+
+def fill_all_holes(d_cc, shape, n_cc, h_count, h_bbox, fill_fn=None, return_fill_count=False):
+  """fill_all_holes (kimimaro/intake.py:747-794) on the device-resident cc volume, in place: every connected
+  component, in label order, gets its voids filled (b2t_fill_voids on its bounding-box crop); components that end up
+  inside an earlier one disappear and are not visited.  h_count / h_bbox: per-label voxel counts and inclusive
+  bounding boxes (x0, y0, z0, x1, y1, z1) of the unfilled volume."""
+  fill_fn = fill_fn or _fill_voids
+  sx, sy, sz = shape
+  d_cc3 = d_cc.view(sz, sy, sx)
+  alive = np.ones(n_cc + 1, dtype=bool)
+  pixels_filled = 0
+  for label in range(1, n_cc + 1):
+    if not alive[label] or h_count[label] == 0:
+      continue
+    x0, y0, z0, x1, y1, z1 = (int(v) for v in h_bbox[label])
+    cshape = (x1 - x0 + 1, y1 - y0 + 1, z1 - z0 + 1)
+    if cshape[0] * cshape[1] * cshape[2] == int(h_count[label]):
+      continue                                                # the component is its whole box: nothing to fill
+    crop = d_cc3[z0:z1 + 1, y0:y1 + 1, x0:x1 + 1]
+    mask = (crop == label).to(torch.uint8).contiguous().view(-1)
+    n = fill_fn(mask, cshape)
+    pixels_filled += n
+    if n == 0:
+      continue
+    m3 = mask.view(cshape[2], cshape[1], cshape[0]) != 0
+    for sub in torch.unique(crop[m3]).cpu().tolist():         # the components that were swallowed
+      if sub != label and sub != 0:
+        alive[sub] = False
+    crop[m3] = label                                          # writes through to d_cc
+  if return_fill_count:
+    return d_cc, pixels_filled
+  return d_cc
+
+
 def _private_arena(d_cc3, d_dbf3, segid, bbox, anisotropy, params, root, targets_before, targets_after,
                    timings):
   """A label whose DBF exceeds soma_detection_threshold (trace.py:108-127): crop, fill its voids,
@@ -107,14 +155,7 @@ def _private_arena(d_cc3, d_dbf3, segid, bbox, anisotropy, params, root, targets
   dev = d_cc3.device
   crop = d_cc3[z0:z1 + 1, y0:y1 + 1, x0:x1 + 1]
   mask = (crop == segid).to(torch.uint8).contiguous().view(-1)
-  reach = torch.empty(V, dtype=torch.int32, device=dev)
-  queue = torch.empty(2 * V, dtype=torch.int32, device=dev)
-  ctrl = torch.zeros(16, dtype=torch.int32, device=dev)
-  check(lib().b2t_fill_voids(c_vp(mask.data_ptr()), c_i64(shape[0]), c_i64(shape[1]), c_i64(shape[2]),
-                             c_vp(reach.data_ptr()), c_vp(queue.data_ptr()), c_u64(V), c_vp(ctrl.data_ptr()),
-                             stream_ptr()), "b2t_fill_voids")
-  filled = int(ctrl[5].item())
-  del reach, queue
+  filled = _fill_voids(mask, shape)
   if filled > 0:
     dbf = edt(mask, shape, anisotropy, black_border=bool(mask.all().item()))
   else:
@@ -170,9 +211,9 @@ def _skeletonize(
   device_labels (a flat Fortran-ordered CUDA tensor already holding the volume: skips the H2D copy;
   all_labels then carries the shape), edt_events (list receiving (start, end) CUDA events around K1).
   """
-  if fill_holes or fix_avocados or voxel_graph is not None:
+  if fix_avocados or voxel_graph is not None:
     raise NotImplementedError(
-      "fill_holes / fix_avocados / voxel_graph are not built yet in kimimaro_b200 "
+      "fix_avocados / voxel_graph are not built yet in kimimaro_b200 "
       "(SURVEY.md 8f row N4); there is no CPU fallback")
   _lib.require_device()
   params = _merge_params(teasar_params)
@@ -224,6 +265,11 @@ def _skeletonize(
   # ---- preamble: connected components, EDT, per-label statistics ----
   d_cc, n_cc = engine.connected_components(d_labels, shape)
   t0 = lap("ccl", t0)
+  if fill_holes:                                               # intake.py:166-167
+    # boxes and counts of the unfilled components; the statistics kernel wants a DBF: any float volume will do
+    c0, b0, _, _ = engine.label_stats(d_cc, torch.zeros(V, dtype=torch.float32, device=d_cc.device), shape, n_cc)
+    fill_all_holes(d_cc, shape, n_cc, c0.cpu().numpy(), b0.cpu().numpy().reshape(-1, 6))
+    t0 = lap("fill_holes", t0)
   if edt_events is not None:
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

@@ -472,10 +472,39 @@ def compute_border_targets(cc_labels, anisotropy):
   return out
 
 
+def fill_all_holes(cc_labels, n_cc, return_fill_count=False):
+  """intake.py:747-794: fill the holes of every connected component, in label order; a component that is swallowed
+  by an earlier one disappears (and is not visited any more).  In place on the F-ordered cc_labels."""
+  labels = np.unique(cc_labels)
+  labels_set = set(int(l) for l in labels)
+  labels_set.discard(0)
+  all_slices = find_objects(cc_labels, n_cc)
+  pixels_filled = 0
+  for label in labels:
+    label = int(label)
+    if label not in labels_set:
+      continue
+    slices = all_slices[label - 1]
+    if slices is None:
+      continue
+    binary_image = np.asfortranarray(cc_labels[slices] == label)
+    binary_image, N = orc.fill_voids(binary_image)
+    pixels_filled += N
+    if N == 0:
+      continue
+    sub_labels = set(int(l) for l in np.unique(cc_labels[slices] * binary_image))
+    sub_labels.remove(label)
+    labels_set -= sub_labels
+    cc_labels[slices] = cc_labels[slices] * ~binary_image + np.asarray(label, cc_labels.dtype) * binary_image
+  if return_fill_count:
+    return cc_labels, pixels_filled
+  return cc_labels
+
+
 def skeletonize(all_labels, teasar_params=DEFAULT_TEASAR_PARAMS, anisotropy=(1, 1, 1), object_ids=None,
                 dust_threshold=1000, fix_branching=True, fix_borders=True,
                 extra_targets_before=(), extra_targets_after=(), invalidation_mode="rounds",
-                only_cc=None, timings=None, parallel=1):
+                only_cc=None, timings=None, parallel=1, fill_holes=False):
   """intake.py:58-221 + 434-517 (parallel==1 path).  Returns {orig id: skeleton dict}."""
   import time
   t0 = time.time()
@@ -490,6 +519,8 @@ def skeletonize(all_labels, teasar_params=DEFAULT_TEASAR_PARAMS, anisotropy=(1, 
     return {}
   cc_labels, n_cc = orc.connected_components(all_labels)
   remapping = get_mapping(all_labels, cc_labels)
+  if fill_holes:
+    cc_labels = fill_all_holes(cc_labels, n_cc)             # intake.py:166-167
   def points_to_labels(pts):
     mapping = defaultdict(list)
     for pt in pts:

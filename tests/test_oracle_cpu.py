@@ -319,3 +319,68 @@ def test_c_abi_argument_errors_without_gpu():
   if not torch.cuda.is_available():
     assert lib.b2t_device_check() == -2                                                 # B2T_ERR_DEVICE
     assert len(lib.b2t_last_error()) > 0
+
+
+# ---- fill_holes: oracle restatement and the host logic of the device path ----
+import oracle  # noqa: E402
+
+
+def _holey_volume():
+  v = np.zeros((40, 36, 30), np.uint32, order="F")
+  v[4:30, 4:30, 4:26] = 5
+  v[10:16, 10:16, 10:16] = 9      # a nucleus: another label enclosed by 5
+  v[12:14, 12:14, 12:14] = 11     # ... with a nucleolus inside (swallowed together with 9)
+  v[20:24, 20:24, 8:12] = 0       # an enclosed void
+  v[18:20, 4:30, 18:20] = 0       # a tunnel open at both ends: not a hole
+  v[32:39, 2:20, 2:20] = 7
+  v[34:37, 6:10, 6:10] = 0
+  v[33:35, 22:30, 22:28] = 3      # solid box: nothing to fill
+  return v
+
+
+def test_fill_all_holes_oracle_matches_scipy():
+  """intake.py:747-794 restated (oracle/teasar.py): afterwards no component has a 6-connected void and the
+  swallowed components are gone; scipy.ndimage.binary_fill_holes is the independent check."""
+  import scipy.ndimage as ndi
+  from oracle import teasar
+  v = _holey_volume()
+  cc, n = oracle.connected_components(v)
+  out, filled = teasar.fill_all_holes(cc.copy(order="F"), n, return_fill_count=True)
+  assert filled > 0
+  expect = cc.copy(order="F")
+  for l in range(1, n + 1):        # label order, like the reference
+    if not (expect == l).any():
+      continue
+    expect[ndi.binary_fill_holes(expect == l)] = l
+  assert np.array_equal(out, expect)
+  assert len(np.unique(out)) < len(np.unique(cc))
+
+
+def test_fill_all_holes_host_logic_matches_oracle():
+  """kimimaro_b200.intake.fill_all_holes on CPU tensors with the fill kernel replaced by the oracle's fill: crops,
+  layout, swallowed-component bookkeeping and the write-back are the product's, the fill itself is the checker's."""
+  import scipy.ndimage as ndi
+  import torch
+  from kimimaro_b200 import intake
+  from oracle import teasar
+  v = _holey_volume()
+  cc, n = oracle.connected_components(v)
+  ref = teasar.fill_all_holes(cc.copy(order="F"), n)
+  calls = []
+
+  def fill_fn(mask, cshape):
+    m = np.asfortranarray(mask.numpy().reshape(cshape, order="F").astype(bool))
+    _, k = oracle.fill_voids(m)
+    mask.copy_(torch.from_numpy(m.reshape(-1, order="F").astype(np.uint8)))
+    calls.append(cshape)
+    return k
+
+  d_cc = torch.from_numpy(cc.reshape(-1, order="F").astype(np.int32))
+  count = np.bincount(cc.ravel(), minlength=n + 1)
+  bbox = np.zeros((n + 1, 6), np.int32)
+  for l, slc in enumerate(ndi.find_objects(cc, max_label=n), start=1):
+    bbox[l] = [slc[0].start, slc[1].start, slc[2].start, slc[0].stop - 1, slc[1].stop - 1, slc[2].stop - 1]
+  out, filled = intake.fill_all_holes(d_cc, cc.shape, n, count, bbox, fill_fn=fill_fn, return_fill_count=True)
+  got = out.numpy().reshape(cc.shape, order="F")
+  assert np.array_equal(got, ref.astype(np.int32))
+  assert filled > 0 and len(calls) >= 2
