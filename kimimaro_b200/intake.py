@@ -7,9 +7,10 @@ Deviations from the reference, all explicit:
   * parallel      one process drives one GPU and the device traces all labels concurrently, so the
                   argument is accepted and ignored here; multi-GPU runs shard labels across
                   processes (kimimaro_b200.distributed).
-  * fix_avocados, voxel_graph, CrackleArray input: not built yet
+  * voxel_graph, CrackleArray input: not built yet
                    -> NotImplementedError, never a silent CPU path.
-                  fill_holes is built (fill_all_holes below: b2t_fill_voids per component).
+                  fill_holes and fix_avocados are built (fill_all_holes, engage_avocado_protection below:
+                  b2t_fill_voids per component, b2t_edt_ws after every pass that changed something).
   * tie rules T1-T5 (oracle/oracle.c header) where the reference leaves ties to heap / sort internals.
 """
 import ctypes
@@ -145,6 +146,133 @@ def fill_all_holes(d_cc, shape, n_cc, h_count, h_bbox, fill_fn=None, return_fill
   return d_cc
 
 
+def _fill_voids_2d(plane, fill_fn):
+  """fill_voids.fill on a 2-D image (paint_walls, intake.py:666-677) with the 3-D kernel: the image is the middle
+  slice of a three-slice volume whose outer slices are solid, so its background connects only within the slice and
+  only the image's own border pixels lie on a face of the volume."""
+  b, a = plane.shape
+  if a == 0 or b == 0:
+    return plane
+  vol = torch.ones((3, b, a), dtype=torch.uint8, device=plane.device)
+  vol[1] = plane.to(torch.uint8)
+  flat = vol.view(-1)
+  fill_fn(flat, (a, b, 3))
+  return flat.view(3, b, a)[1] != 0
+
+
+def find_avocado_fruit(xline, yline, zline, cx, cy, cz, background=0):
+  """kimimaro.skeletontricks.find_avocado_fruit (pyx:905-992) on the three axis lines of the label volume through
+  (cx, cy, cz) (host arrays): the first foreign label on each of the six rays votes; a ray that reaches background
+  first, or the array end, does not.  The rays towards smaller coordinates stop before index 0, like the reference.
+  Returns (pit, fruit)."""
+  label = int(xline[cx])
+  changes = []
+  for line, c in ((xline, cx), (yline, cy), (zline, cz)):
+    for rng in (range(c, len(line)), range(c, 0, -1)):
+      for i in rng:
+        v = int(line[i])
+        if v == background:
+          break
+        if v != label:
+          changes.append(v)
+          break
+  if len(changes) < 3:
+    return (label, label)
+  allowed_differences = 1 if len(changes) > 3 else 0
+  uniq, cts = np.unique(changes, return_counts=True)
+  k = int(np.argmax(cts))
+  if len(changes) - int(cts[k]) > allowed_differences:
+    return (label, label)
+  return (label, int(uniq[k]))
+
+
+def _default_stats(d_cc, d_dbf, shape, n_cc):
+  count, bbox, _, _ = engine.label_stats(d_cc, d_dbf, shape, n_cc)
+  return count.cpu().numpy(), bbox.cpu().numpy().reshape(-1, 6)
+
+
+def engage_avocado_protection_single_pass(d_cc, d_dbf, shape, n_cc, candidates, stats_fn, fill_fn):
+  """intake.py:646-704 on the device-resident volumes.  candidates: labels in the reference's iteration order."""
+  candidates = [label for label in candidates if label != 0]
+  unchanged, changed = set(), set()
+  if len(candidates) == 0:
+    return unchanged, changed
+  sx, sy, sz = shape
+  d_cc3 = d_cc.view(sz, sy, sx)
+  d_dbf3 = d_dbf.view(sz, sy, sx)
+  h_count, h_bbox = stats_fn(d_cc, d_dbf, shape, n_cc)        # boxes as they are when the pass starts (intake.py:679)
+  for label in candidates:
+    x0, y0, z0, x1, y1, z1 = (int(v) for v in h_bbox[label])
+    ex, ey, ez = x1 - x0 + 1, y1 - y0 + 1, z1 - z0 + 1
+    crop = d_cc3[z0:z1 + 1, y0:y1 + 1, x0:x1 + 1]
+    binimg = (crop == label)                                   # image of the pit, [z, y, x]
+    # paint_walls: 2-D fills of the six faces, in the reference's order (z, y, x faces)
+    binimg[0] = _fill_voids_2d(binimg[0], fill_fn)
+    binimg[-1] = _fill_voids_2d(binimg[-1], fill_fn)
+    binimg[:, 0, :] = _fill_voids_2d(binimg[:, 0, :], fill_fn)
+    binimg[:, -1, :] = _fill_voids_2d(binimg[:, -1, :], fill_fn)
+    binimg[:, :, 0] = _fill_voids_2d(binimg[:, :, 0], fill_fn)
+    binimg[:, :, -1] = _fill_voids_2d(binimg[:, :, -1], fill_fn)
+    prod = binimg.to(torch.float32) * d_dbf3[z0:z1 + 1, y0:y1 + 1, x0:x1 + 1]
+    idx = int(torch.argmax(prod.reshape(-1)).item())           # first maximum in Fortran raster order (intake.py:595-598)
+    cz, r = divmod(idx, ex * ey)
+    cy, cx = divmod(r, ex)
+    cx, cy, cz = cx + x0, cy + y0, cz + z0
+    pit, fruit = find_avocado_fruit(d_cc3[cz, cy, :].cpu().numpy(), d_cc3[cz, :, cx].cpu().numpy(),
+                                    d_cc3[:, cy, cx].cpu().numpy(), cx, cy, cz)
+    if pit == fruit and pit not in changed:
+      unchanged.add(pit)
+    else:
+      unchanged.discard(pit)
+      unchanged.discard(fruit)
+      changed.add(pit)
+      changed.add(fruit)
+      binimg |= (crop == fruit)
+    mask = binimg.to(torch.uint8).contiguous().view(-1)
+    fill_fn(mask, (ex, ey, ez))
+    crop[mask.view(ez, ey, ex) != 0] = fruit                   # writes through to d_cc
+  return unchanged, changed
+
+
+def engage_avocado_protection(d_cc, d_dbf, shape, n_cc, soma_detection_threshold, edtfn, stats_fn=None, fill_fn=None):
+  """engage_avocado_protection (kimimaro/intake.py:600-644): a nucleus segmented apart from its cell -- the pit of an
+  avocado -- takes the label of the fruit around it; up to 20 passes for nested cases, the EDT redone after every pass
+  that changed something.  d_cc is edited in place.  Instead of renumbering (intake.py:636, not visible in the result)
+  the surviving labels keep their numbers; returns (d_dbf, last) where last[L] is the pre-protection component that
+  get_mapping(orig_cc_labels, cc_labels) (pyx:490-525: the last run start of L in raster order decides) would name for
+  the surviving component L, -1 for labels that are gone."""
+  stats_fn = stats_fn or _default_stats
+  fill_fn = fill_fn or _fill_voids
+  d_orig_cc = d_cc.clone()
+  unchanged = set()
+  t = soma_detection_threshold / 2.5
+  for _ in range(20):
+    hot = d_dbf > t
+    vals = torch.unique(d_cc[hot]).cpu().tolist()              # sorted, like fastremap.unique
+    # set(fastremap.unique(cc_labels * (all_dbf > t))): the product is 0 wherever the test fails or on background
+    has_zero = bool(((d_cc == 0) | ~hot).any().item())
+    candidates = set()
+    for v in ([0] if has_zero else []) + [int(v) for v in vals if v != 0]:
+      candidates.add(v)
+    candidates -= unchanged
+    candidates.discard(0)
+    unchanged_this_cycle, changes = engage_avocado_protection_single_pass(
+      d_cc, d_dbf, shape, n_cc, candidates, stats_fn, fill_fn)
+    unchanged |= unchanged_this_cycle
+    if len(changes) == 0:
+      break
+    d_dbf = edtfn(d_cc)
+  starts = torch.nonzero(d_cc[1:] != d_cc[:-1]).view(-1) + 1
+  starts = torch.cat([torch.zeros(1, dtype=starts.dtype, device=starts.device), starts])
+  last = torch.full((n_cc + 1,), -1, dtype=torch.int64, device=d_cc.device)
+  last.scatter_reduce_(0, d_cc[starts].to(torch.int64), starts, reduce="amax")
+  h_last = last.cpu().numpy()
+  h_src = np.full(n_cc + 1, -1, dtype=np.int64)
+  ok = h_last >= 0
+  h_src[ok] = d_orig_cc[torch.as_tensor(h_last[ok], device=d_cc.device)].cpu().numpy().astype(np.int64)
+  return d_dbf, h_src
+
+
 def _private_arena(d_cc3, d_dbf3, segid, bbox, anisotropy, params, root, targets_before, targets_after,
                    timings):
   """A label whose DBF exceeds soma_detection_threshold (trace.py:108-127): crop, fill its voids,
@@ -211,10 +339,9 @@ def _skeletonize(
   device_labels (a flat Fortran-ordered CUDA tensor already holding the volume: skips the H2D copy;
   all_labels then carries the shape), edt_events (list receiving (start, end) CUDA events around K1).
   """
-  if fix_avocados or voxel_graph is not None:
+  if voxel_graph is not None:
     raise NotImplementedError(
-      "fix_avocados / voxel_graph are not built yet in kimimaro_b200 "
-      "(SURVEY.md 8f row N4); there is no CPU fallback")
+      "voxel_graph is not built yet in kimimaro_b200 (SURVEY.md 8f row N4); there is no CPU fallback")
   _lib.require_device()
   params = _merge_params(teasar_params)
   params["fix_branching"] = bool(fix_branching)
@@ -278,6 +405,15 @@ def _skeletonize(
     ev1.record()
     edt_events.append((ev0, ev1))
   t0 = lap("edt", t0)
+  avocado_src = None
+  if fix_avocados:                                             # intake.py:187-193
+    _, _, _, first0 = engine.label_stats(d_cc, d_dbf, shape, n_cc)
+    h_first0 = first0.cpu().numpy().view(np.uint32).astype(np.int64)
+    h_orig0 = d_labels[torch.as_tensor(np.clip(h_first0, 0, V - 1), device=d_labels.device)].cpu().numpy()
+    d_dbf, avocado_src = engage_avocado_protection(
+      d_cc, d_dbf, shape, n_cc, teasar_params.get("soma_detection_threshold", 0),
+      lambda cc: edt(cc, shape, an, black_border))
+    t0 = lap("fix_avocados", t0)
   count, bbox, dbfmax, first = engine.label_stats(d_cc, d_dbf, shape, n_cc)
   h_count = count.cpu().numpy()
   h_bbox = bbox.cpu().numpy().reshape(-1, 6)
@@ -286,6 +422,10 @@ def _skeletonize(
   # remapping: original label at the first voxel of every component (get_mapping, pyx:490-525)
   gather_idx = torch.as_tensor(np.clip(h_first, 0, V - 1), device=d_labels.device)
   h_orig = d_labels[gather_idx].cpu().numpy()
+  if avocado_src is not None:                                  # adjusted_remapping (intake.py:637-642)
+    ok = avocado_src >= 0
+    h_orig = h_orig.copy()
+    h_orig[ok] = h_orig0[avocado_src[ok]]
   if h_orig.dtype.kind == "i" and all_labels is not None and device_labels is None and all_labels.dtype.kind == "u":
     h_orig = h_orig.view(all_labels.dtype)
   t0 = lap("stats", t0)

@@ -131,13 +131,17 @@ def first_label(labels):
 
 
 def get_mapping(orig_labels, cc_labels):
-  """skeletontricks.pyx:490-525  { cc label: original label }"""
+  """skeletontricks.pyx:490-525  { cc label: original label }.  Literally: in Fortran raster order, every voxel whose
+  cc label differs from the previous voxel's writes remap[cc] = orig, so the LAST run start of a cc label decides.
+  (Only matters when a cc label spans several original labels: engage_avocado_protection, intake.py:637.)"""
   cc = cc_labels.ravel(order="F")
   og = orig_labels.ravel(order="F")
   if cc.size == 0:
     return {}
-  _, first = np.unique(cc, return_index=True)
-  return {int(cc[i]): int(og[i]) for i in first}
+  starts = np.concatenate(([0], np.flatnonzero(cc[1:] != cc[:-1]) + 1))
+  rev = starts[::-1]
+  _, first_in_rev = np.unique(cc[rev], return_index=True)
+  return {int(cc[i]): int(og[i]) for i in rev[first_in_rev]}
 
 
 def _f32(x):
@@ -472,6 +476,138 @@ def compute_border_targets(cc_labels, anisotropy):
   return out
 
 
+def find_avocado_fruit(labels, cx, cy, cz, background=0):
+  """skeletontricks.pyx:905-992: walk the six axis rays from (cx,cy,cz); the first foreign label met on each ray
+  (a ray that meets background first says nothing) votes for the fruit around the pit.  The rays towards smaller
+  coordinates stop BEFORE index 0, like the reference's range(c, 0, -1)."""
+  sx, sy, sz = labels.shape[:3]
+  if cx >= sx or cy >= sy or cz >= sz:
+    raise ValueError("<{},{},{}> must be be contained within shape <{},{},{}>".format(cx, cy, cz, sx, sy, sz))
+  label = labels[cx, cy, cz]
+  changes = []
+
+  def ray(line, rng):
+    for i in rng:
+      if line[i] == background:
+        return
+      if line[i] != label:
+        changes.append(line[i])
+        return
+  ray(labels[:, cy, cz], range(cx, sx))
+  ray(labels[:, cy, cz], range(cx, 0, -1))
+  ray(labels[cx, :, cz], range(cy, sy))
+  ray(labels[cx, :, cz], range(cy, 0, -1))
+  ray(labels[cx, cy, :], range(cz, sz))
+  ray(labels[cx, cy, :], range(cz, 0, -1))
+  if len(changes) < 3:                       # too little info to make a decision
+    return (label, label)
+  allowed_differences = 1 if len(changes) > 3 else 0
+  uniq, cts = np.unique(changes, return_counts=True)
+  candidate_fruit_index = np.argmax(cts)
+  differences = len(changes) - cts[candidate_fruit_index]
+  if differences > allowed_differences:      # lots of labels around the candidate pit: not an avocado
+    return (label, label)
+  return (label, uniq[candidate_fruit_index])
+
+
+def fill_voids_2d(plane):
+  """fill_voids.fill on a 2-D image (intake.py:671-676): background not 4-connected to the image border is filled."""
+  import scipy.ndimage
+  if plane.size == 0:
+    return plane
+  return scipy.ndimage.binary_fill_holes(plane)
+
+
+def renumber(cc_labels):
+  """fastremap.renumber(arr, in_place=True) (intake.py:636): 1..N in order of first appearance in memory order
+  (Fortran raster for the F-ordered cc_labels), 0 stays 0.  Returns (renumbered, {old: new})."""
+  flat = cc_labels.ravel(order="F")
+  uniq, first = np.unique(flat, return_index=True)
+  order = np.argsort(first, kind="stable")
+  mapping = {}
+  nxt = 1
+  for u in uniq[order]:
+    if u == 0:
+      mapping[0] = 0
+    else:
+      mapping[int(u)] = nxt
+      nxt += 1
+  lut = np.zeros(int(uniq.max()) + 1, dtype=cc_labels.dtype)
+  for k, v in mapping.items():
+    lut[k] = v
+  return lut[cc_labels], mapping
+
+
+def _intset(values):
+  """set(fastremap.unique(...)): ints hash like numpy integers, so a set built from the same values in the same
+  (sorted) insertion order iterates in the same order as the reference's."""
+  return set(int(v) for v in values)
+
+
+def engage_avocado_protection_single_pass(cc_labels, all_dbf, n_cc, candidates):
+  """intake.py:646-704."""
+  candidates = [label for label in candidates if label != 0]
+  unchanged, changed = set(), set()
+  if len(candidates) == 0:
+    return cc_labels, unchanged, changed
+
+  def paint_walls(binimg):
+    binimg[:, :, 0] = fill_voids_2d(binimg[:, :, 0])
+    binimg[:, :, -1] = fill_voids_2d(binimg[:, :, -1])
+    binimg[:, 0, :] = fill_voids_2d(binimg[:, 0, :])
+    binimg[:, -1, :] = fill_voids_2d(binimg[:, -1, :])
+    binimg[0, :, :] = fill_voids_2d(binimg[0, :, :])
+    binimg[-1, :, :] = fill_voids_2d(binimg[-1, :, :])
+    return binimg
+
+  slcs = find_objects(cc_labels, n_cc)
+  for label in candidates:
+    slc = slcs[label - 1]
+    offset = np.array([s.start for s in slc])
+    binimg = paint_walls(np.asfortranarray(cc_labels[slc] == label))    # image of the pit
+    prod = binimg * all_dbf[slc]
+    coord = np.array(np.unravel_index(np.argmax(prod.ravel(order="F")), prod.shape, order="F")) + offset
+    pit, fruit = find_avocado_fruit(cc_labels, int(coord[0]), int(coord[1]), int(coord[2]))
+    pit, fruit = int(pit), int(fruit)
+    if pit == fruit and pit not in changed:
+      unchanged.add(pit)
+    else:
+      unchanged.discard(pit)
+      unchanged.discard(fruit)
+      changed.add(pit)
+      changed.add(fruit)
+      binimg |= (cc_labels[slc] == fruit)
+    binimg, N = orc.fill_voids(binimg)
+    cc_labels[slc] = cc_labels[slc] * ~binimg + np.asarray(fruit, cc_labels.dtype) * binimg
+  return cc_labels, unchanged, changed
+
+
+def engage_avocado_protection(cc_labels, all_dbf, n_cc, remapping, soma_detection_threshold, edtfn):
+  """intake.py:600-644: a nucleus segmented apart from its cell (the pit of an avocado) is given the label of the
+  fruit around it; up to 20 passes for nested cases; then renumber and re-derive the cc -> original label map.
+  Returns (cc_labels, all_dbf, remapping, n_cc)."""
+  orig_cc_labels = np.copy(cc_labels, order="F")
+  unchanged = set()
+  for _ in range(20):
+    candidates = _intset(np.unique(cc_labels * (all_dbf > soma_detection_threshold / 2.5)))
+    candidates -= unchanged
+    candidates.discard(0)
+    cc_labels, unchanged_this_cycle, changes = engage_avocado_protection_single_pass(
+      cc_labels, all_dbf, n_cc, candidates)
+    unchanged |= unchanged_this_cycle
+    if len(changes) == 0:
+      break
+    all_dbf = edtfn(cc_labels)
+  cc_labels, _ = renumber(cc_labels)
+  cc_labels = np.asfortranarray(cc_labels)
+  cc_remapping = get_mapping(orig_cc_labels, cc_labels)
+  adjusted_remapping = {}
+  for new_cc, cc in cc_remapping.items():
+    if cc in remapping:
+      adjusted_remapping[new_cc] = remapping[cc]
+  return cc_labels, all_dbf, adjusted_remapping, int(cc_labels.max())
+
+
 def fill_all_holes(cc_labels, n_cc, return_fill_count=False):
   """intake.py:747-794: fill the holes of every connected component, in label order; a component that is swallowed
   by an earlier one disappears (and is not visited any more).  In place on the F-ordered cc_labels."""
@@ -504,7 +640,7 @@ def fill_all_holes(cc_labels, n_cc, return_fill_count=False):
 def skeletonize(all_labels, teasar_params=DEFAULT_TEASAR_PARAMS, anisotropy=(1, 1, 1), object_ids=None,
                 dust_threshold=1000, fix_branching=True, fix_borders=True,
                 extra_targets_before=(), extra_targets_after=(), invalidation_mode="rounds",
-                only_cc=None, timings=None, parallel=1, fill_holes=False):
+                only_cc=None, timings=None, parallel=1, fill_holes=False, fix_avocados=False):
   """intake.py:58-221 + 434-517 (parallel==1 path).  Returns {orig id: skeleton dict}."""
   import time
   t0 = time.time()
@@ -529,7 +665,11 @@ def skeletonize(all_labels, teasar_params=DEFAULT_TEASAR_PARAMS, anisotropy=(1, 
     return mapping
   extra_targets_before = points_to_labels(extra_targets_before)
   extra_targets_after = points_to_labels(extra_targets_after)
-  all_dbf = orc.edt(cc_labels, anisotropy=anisotropy, black_border=bool(minlabel == maxlabel))
+  edtfn = lambda labels: orc.edt(labels, anisotropy=anisotropy, black_border=bool(minlabel == maxlabel))
+  all_dbf = edtfn(cc_labels)
+  if fix_avocados:                                            # intake.py:187-193
+    cc_labels, all_dbf, remapping, n_cc = engage_avocado_protection(
+      cc_labels, all_dbf, n_cc, remapping, teasar_params.get("soma_detection_threshold", 0), edtfn)
   counts = np.bincount(cc_labels.ravel(order="K"), minlength=n_cc + 1)
   cc_segids = [sid for sid in range(1, n_cc + 1) if counts[sid] > dust_threshold]
   all_slices = find_objects(cc_labels, n_cc)

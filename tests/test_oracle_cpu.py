@@ -384,3 +384,123 @@ def test_fill_all_holes_host_logic_matches_oracle():
   got = out.numpy().reshape(cc.shape, order="F")
   assert np.array_equal(got, ref.astype(np.int32))
   assert filled > 0 and len(calls) >= 2
+
+
+# ---- fix_avocados: oracle restatement pinned against the reference ----
+def test_avocado_pieces_vs_reference_ext(ref_ext):
+  """find_avocado_fruit (pyx:905-992) and get_mapping (pyx:490-525, last run start decides) against the
+  reference's own compiled extension."""
+  if ref_ext is None:
+    pytest.skip("oracle/_ref not built")
+  from oracle import teasar
+  rng = np.random.default_rng(11)
+  for trial in range(40):
+    shape = tuple(int(v) for v in rng.integers(3, 14, size=3))
+    k = int(rng.integers(2, 5))
+    lab = rng.integers(0, k + 1, size=shape).astype(np.uint32)
+    rep = tuple(int(v) for v in rng.integers(1, 4, size=3))
+    lab = np.asfortranarray(np.repeat(np.repeat(np.repeat(lab, rep[0], 0), rep[1], 1), rep[2], 2))
+    for _ in range(12):
+      c = tuple(int(rng.integers(0, s)) for s in lab.shape)
+      got = teasar.find_avocado_fruit(lab, *c)
+      ref = ref_ext.find_avocado_fruit(lab, *c)
+      assert (int(got[0]), int(got[1])) == (int(ref[0]), int(ref[1])), (trial, c)
+    # a cc labelling that is COARSER than the original one (what engage_avocado_protection feeds it, intake.py:637)
+    coarse = np.asfortranarray((lab + 1) // 2).astype(np.uint32)
+    assert teasar.get_mapping(lab, coarse) == {int(a): int(b) for a, b in ref_ext.get_mapping(lab, coarse).items()}
+
+
+def test_fix_avocados_reference_known_answer():
+  """automated_test.py:478-509 (test_fix_avocados) on the oracle's engage_avocado_protection."""
+  from oracle import teasar
+  labels = np.zeros((256, 256, 256), dtype=np.uint32, order="F")
+  labels[:50, :40, :30] = 1          # fake clipped avocado
+  labels[:25, :20, :25] = 2
+  labels[50:100, 40:100, 30:80] = 3  # double avocado
+  labels[60:90, 50:90, 40:70] = 4
+  labels[60:70, 51:89, 41:69] = 5
+  labels[200:, 200:, 200:] = 6       # not a pit
+  labels[150:200, 200:, 200:] = 7    # not a fruit
+  fn = lambda lbls: oracle.edt(lbls, (1, 1, 1), False)
+  out, dbf, remapping, n = teasar.engage_avocado_protection(
+    labels, fn(labels), 7, {i: i for i in range(1, 8)}, 1, fn)
+  assert set(int(v) for v in np.unique(out)) == {0, 1, 2, 3, 4}
+  assert np.all(out[:50, :40, :30] == 1)
+  assert np.all(out[50:100, 40:100, 30:80] == 2)
+  assert np.all(out[150:200, 200:, 200:] == 3)
+  assert np.all(out[200:, 200:, 200:] == 4)
+  assert remapping == {1: 1, 2: 3, 3: 7, 4: 6} and n == 4
+
+
+def _avocado_host_vs_oracle(labels, thr):
+  """kimimaro_b200.intake.engage_avocado_protection on CPU tensors -- kernels replaced by the oracle's fill and EDT, the
+  statistics by numpy -- against the oracle's restatement: same partition, same component -> original label map."""
+  import scipy.ndimage as ndi
+  import torch
+  from kimimaro_b200 import intake
+  from oracle import teasar
+  shape = labels.shape
+  cc, n = oracle.connected_components(labels)
+  remapping = teasar.get_mapping(labels, cc)
+  fn = lambda l: oracle.edt(np.asfortranarray(l), (1, 1, 1), False)
+  ref_cc, ref_dbf, ref_map, ref_n = teasar.engage_avocado_protection(cc.copy(order="F"), fn(cc), n, remapping, thr, fn)
+  lut = np.zeros(ref_n + 1, np.int64)
+  for k, v in ref_map.items():
+    lut[k] = v
+  ref_img = lut[ref_cc]
+
+  def fill_fn(mask, cshape):
+    m = np.asfortranarray(mask.numpy().reshape(cshape, order="F").astype(bool))
+    _, k = oracle.fill_voids(m)
+    mask.copy_(torch.from_numpy(m.reshape(-1, order="F").astype(np.uint8)))
+    return k
+
+  def stats_fn(d_cc, d_dbf, shp, n_cc):
+    a = d_cc.numpy().reshape(shp, order="F")
+    count = np.bincount(a.ravel(), minlength=n_cc + 1)
+    bbox = np.zeros((n_cc + 1, 6), np.int32)
+    for l, slc in enumerate(ndi.find_objects(a, max_label=n_cc), start=1):
+      if slc is not None:
+        bbox[l] = [slc[0].start, slc[1].start, slc[2].start, slc[0].stop - 1, slc[1].stop - 1, slc[2].stop - 1]
+    return count, bbox
+
+  def edtfn(d_cc):
+    a = d_cc.numpy().reshape(shape, order="F").astype(np.uint32)
+    return torch.from_numpy(fn(a).reshape(-1, order="F").copy())
+
+  d_cc = torch.from_numpy(cc.reshape(-1, order="F").astype(np.int32))
+  d_dbf, src = intake.engage_avocado_protection(d_cc, edtfn(d_cc), shape, n, thr, edtfn, stats_fn=stats_fn, fill_fn=fill_fn)
+  got_cc = d_cc.numpy().reshape(shape, order="F")
+  pre = np.zeros(n + 1, np.int64)
+  for k, v in remapping.items():
+    pre[k] = v
+  assert (src[np.unique(got_cc)][1:] >= 0).all() if got_cc.min() == 0 else (src[np.unique(got_cc)] >= 0).all()
+  got_img = np.where(got_cc > 0, pre[np.maximum(src[got_cc], 0)], 0)
+  assert np.array_equal(got_img, ref_img)
+  assert np.array_equal(d_dbf.numpy().reshape(shape, order="F"), ref_dbf)
+  return got_cc, cc
+
+
+def test_fix_avocados_host_logic_known_answer():
+  labels = np.zeros((128, 128, 128), dtype=np.uint32, order="F")
+  labels[:25, :20, :15] = 1          # the volume of automated_test.py:478-509 at half size
+  labels[:12, :10, :12] = 2
+  labels[25:50, 20:50, 15:40] = 3
+  labels[30:45, 25:45, 20:35] = 4
+  labels[30:35, 26:44, 21:34] = 5
+  labels[100:, 100:, 100:] = 6
+  labels[75:100, 100:, 100:] = 7
+  got, cc = _avocado_host_vs_oracle(labels, 1)
+  assert len(np.unique(got)) == 5    # background + clipped avocado + double avocado + the two that are none
+
+
+def test_fix_avocados_host_logic_random():
+  rng = np.random.default_rng(5)
+  for trial in range(6):
+    shape = tuple(int(v) for v in rng.integers(20, 44, size=3))
+    lab = np.zeros(shape, np.uint32, order="F")
+    for k in range(1, 7):              # nested boxes: later ones sit inside earlier ones more often than not
+      lo = [int(rng.integers(0, s - 6)) for s in shape]
+      hi = [int(rng.integers(l + 4, min(s, l + 4 + s // 2) + 1)) for l, s in zip(lo, shape)]
+      lab[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = k
+    _avocado_host_vs_oracle(lab, float(rng.choice([0, 1, 5])))

@@ -30,3 +30,17 @@ def test_fill_holes(gpu):
   assert 9 in ref0
   _compare(res0, ref0)
   assert not np.array_equal(res0[5].vertices, res[5].vertices)
+
+
+def test_fix_avocados(gpu):
+  import kimimaro_b200
+  labels = _cell_with_nucleus()
+  params = dict(kimimaro_b200.DEFAULT_TEASAR_PARAMS)
+  params["soma_detection_threshold"] = 300        # candidates: DBF above 300 / 2.5 nm (intake.py:619)
+  kw = dict(anisotropy=(16, 16, 40), dust_threshold=100, fix_avocados=True, teasar_params=params)
+  res, ref = _both(gpu, labels, **kw)
+  assert 9 not in ref and 5 in ref and 7 in ref    # the nucleus took the label of the cell around it
+  _compare(res, ref)
+  both = dict(kw, fill_holes=True)
+  res2, ref2 = _both(gpu, labels, **both)
+  _compare(res2, ref2)
