@@ -4,7 +4,7 @@ kimimaro_b200 -- B200-native (sm_100a) TEASAR skeletonization behind kimimaro's 
   import kimimaro_b200 as kimimaro
   skels = kimimaro.skeletonize(labels, teasar_params=kimimaro.DEFAULT_TEASAR_PARAMS, anisotropy=(16, 16, 40))
 
-mirrors kimimaro/__init__.py:18-25 for the hot path: skeletonize, DimensionError, DEFAULT_TEASAR_PARAMS
+mirrors kimimaro/__init__.py:18-25 for the hot path: skeletonize, synapses_to_targets, DimensionError, DEFAULT_TEASAR_PARAMS
 and the Skeleton result type.  Everything numeric runs in hand-written CUDA kernels reached through
 the C ABI of libb2t.so (include/b2t.h); importing this package does not need a GPU, calling it does.
 """
@@ -15,7 +15,7 @@ __version__ = "0.1.0"
 
 def __getattr__(name):
   # lazy: `import kimimaro_b200` must work on a CPU-only box (build / CI), torch is imported on first use
-  if name in ("skeletonize", "DimensionError", "DEFAULT_TEASAR_PARAMS"):
+  if name in ("skeletonize", "DimensionError", "DEFAULT_TEASAR_PARAMS", "synapses_to_targets"):
     from . import intake
     return getattr(intake, name)
   raise AttributeError(name)

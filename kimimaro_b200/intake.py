@@ -99,6 +99,32 @@ def _find_soma_root(d_dbf, shape, dbf_max):
   return tuple(coords[root].astype(np.uint32))
 
 
+def synapses_to_targets(labels, synapses, progress=False):
+  """synapses_to_targets (kimimaro/intake.py:706-745): for every label and every swc_label of its synapses, the
+  label's voxel nearest to each centroid (voxel units, same origin as labels) becomes a skeletonization target.
+  labels: 3-D array; synapses: { label: [ (centroid, swc_label), ... ] }.  Returns { (x,y,z): swc_label }.
+  Host-side preparation of extra_targets_*: numpy only, like the reference (no kernel involved)."""
+  labels = np.asarray(labels)
+  while labels.ndim > 3:
+    labels = labels[..., 0]
+  targets = {}
+  for label, pairs in synapses.items():
+    point_cloud = np.vstack((labels == label).nonzero()).T     # [ [x,y,z], ... ] in C order, like the reference
+    if len(point_cloud) == 0:
+      continue
+    swc_labels = defaultdict(list)
+    for centroid, swc_label in pairs:
+      swc_labels[swc_label].append(centroid)
+    for swc_label, centroids in swc_labels.items():
+      cents = np.asarray(centroids, dtype=np.float64).reshape(len(centroids), -1)
+      pc = point_cloud.astype(np.float64)
+      # scipy.spatial.distance.cdist(point_cloud, centroids): Euclidean, float64; argmin takes the first minimum
+      distances = np.sqrt(((pc[:, None, :] - cents[None, :, :]) ** 2).sum(axis=2))
+      minima = np.unique(np.argmin(distances, axis=0))
+      targets.update({tuple(int(v) for v in point_cloud[idx]): swc_label for idx in minima})
+  return targets
+
+
 def _fill_voids(mask, shape):
   """fill_voids.fill(mask, in_place=True, return_fill_count=True) (trace.py:109, intake.py:779) on a flat uint8
   device mask in Fortran order; returns the number of voxels filled."""

@@ -504,3 +504,33 @@ def test_fix_avocados_host_logic_random():
       hi = [int(rng.integers(l + 4, min(s, l + 4 + s // 2) + 1)) for l, s in zip(lo, shape)]
       lab[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = k
     _avocado_host_vs_oracle(lab, float(rng.choice([0, 1, 5])))
+
+
+def test_synapses_to_targets_matches_scipy_formulation():
+  """intake.py:706-745 with scipy's cdist, as the reference writes it, against kimimaro_b200.synapses_to_targets."""
+  import scipy.spatial
+  from collections import defaultdict
+  import kimimaro_b200
+  rng = np.random.default_rng(9)
+  labels = rng.integers(0, 4, size=(12, 10, 8)).astype(np.uint32)
+  synapses = {
+    1: [((3.2, 4.1, 2.7), 5), ((9.9, 0.2, 7.5), 5), ((6.0, 6.0, 3.0), 6)],
+    2: [((0.0, 0.0, 0.0), 5)],
+    9: [((1.0, 1.0, 1.0), 5)],          # no such label: skipped
+  }
+  expect = {}
+  for label, pairs in synapses.items():
+    pc = np.vstack((labels == label).nonzero()).T
+    if len(pc) == 0:
+      continue
+    by = defaultdict(list)
+    for c, s in pairs:
+      by[s].append(c)
+    for s, cents in by.items():
+      d = scipy.spatial.distance.cdist(pc, cents)
+      for idx in np.unique(np.argmin(d, axis=0)):
+        expect[tuple(int(v) for v in pc[idx])] = s
+  got = kimimaro_b200.synapses_to_targets(labels, synapses)
+  assert got == expect and len(got) >= 3
+  for pt in got:
+    assert labels[pt] in (1, 2)
