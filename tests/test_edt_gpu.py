@@ -136,6 +136,33 @@ def test_hybrid_equals_in_place_path(gpu):
   assert torch.equal(out, ref)
 
 
+def test_k1_forms_identical(gpu):
+  """The execution forms of b2t_edt_ws selectable through b2t_edt_config_roles -- both stencil bodies, with and
+  without the roles launch (prediction from the previous pass, envelope and stencil warps side by side) -- give the
+  same floats as the shipped default; a prediction scaled to miss blocks only moves work to the residual launch."""
+  import torch
+  from kimimaro_b200 import ops, _lib
+  from kimimaro_b200._lib import c_f32
+  from tests.synth import synthetic_tubes
+  lib = _lib.lib()
+  lab = np.asfortranarray(synthetic_tubes((192, 160, 96), 40, seed=80).astype(np.uint32))
+  lab[30:150, 30:130, 10:80] = 99
+  plane = np.zeros((260, 257), np.uint32, order="F")
+  plane[1:-1, 1:-1] = 1
+  plane[100:140, 50:200] = 2
+  cases = [(lab, (16, 16, 40), False), (lab, (4, 4, 40), True), (lab, (1, 1, 1), False), (lab, (40, 32, 20), True),
+           (plane, (100, 100), True)]
+  devs = [ops.to_device_f(a, gpu) for a, _, _ in cases]
+  refs = [ops.edt(d, a.shape, an, bb, workspace=True).clone() for d, (a, an, bb) in zip(devs, cases)]
+  try:
+    for roles, v2, scale in ((0, 0, 1.0), (1, 0, 1.0), (1, 1, 1.0), (1, 1, 3.0)):
+      _lib.check(lib.b2t_edt_config_roles(roles, v2, c_f32(scale)))
+      for d, (a, an, bb), ref in zip(devs, cases, refs):
+        assert torch.equal(ops.edt(d, a.shape, an, bb, workspace=True), ref), (roles, v2, scale, an, bb)
+  finally:
+    _lib.check(lib.b2t_edt_config_roles(0, 1, c_f32(1.0)))   # the shipped default
+
+
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint32])
 def test_hybrid_fallbacks_keep_tolerance(gpu, orc, dtype):
   # non-integer anisotropy, narrow labels, sx not a multiple of 4: b2t_edt_ws takes the b2t_edt path
