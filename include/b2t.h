@@ -39,6 +39,11 @@ unsigned long long b2t_launch_count(int reset); /* kernels launched by this libr
 /* cap resident blocks per SM of the cooperative sweeps / of the path-loop kernel (0 = no cap) so that two
  * arenas can be traced concurrently on two streams */
 int b2t_set_launch_limits(int coop_blocks_per_sm, int trace_blocks_per_sm);
+/* Experimental, off by default: order the invalidation rounds of the path loop (b2t_trace_batch) by the reference's
+ * heap key -- distance to the seed, dijkstra_invalidation.hpp:233-237 -- in windows of `voxels` smallest-voxel-edges
+ * instead of by hop count; 0 restores the hop-synchronous rounds.  See DESIGN.md 4 (Tier B) and the oracle's
+ * invalidation mode "window:<voxels>". */
+int b2t_set_claim_window(float voxels);
 
 /* K1  anisotropic multi-label Euclidean distance transform ------------------------------------
  * replaces  edt.edt(labels, anisotropy, black_border)            kimimaro/intake.py:174-185

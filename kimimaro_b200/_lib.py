@@ -27,6 +27,7 @@ _SIGNATURES = {
   "b2t_version": [],
   "b2t_last_error": [],
   "b2t_device_check": [],
+  "b2t_set_claim_window": [c_f32],
   "b2t_edt": [c_vp, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_vp, c_vp],
   "b2t_edt_config": [c_int, c_int, c_int, c_int, c_int],
   "b2t_edt_config_hybrid": [c_int, c_int, c_int, c_int, c_int, c_int],

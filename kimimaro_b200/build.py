@@ -37,6 +37,24 @@ def _stale():
   return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+# other builds of the same sources for kernel A/B runs (B2T_LIB=kimimaro_b200/_variants/<name>.so selects one)
+VARIANTS = {
+  "claim_window": ["-DB2T_WITH_CLAIM_WINDOW=1"],   # key-ordered invalidation rounds in the path loop (trace.cu)
+}
+
+
+def build_variant(name, verbose=False):
+  out_dir = os.path.join(HERE, "_variants")
+  os.makedirs(out_dir, exist_ok=True)
+  out = os.path.join(out_dir, name + ".so")
+  nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+  cmd = [nvcc] + NVCC_FLAGS + VARIANTS[name] + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", out]
+  if verbose:
+    print(" ".join(cmd))
+  subprocess.check_call(cmd)
+  return out
+
+
 def build(force=False, verbose=False):
   if not force and not _stale():
     return LIB
@@ -49,4 +67,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-  print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+  if "--variant" in sys.argv:
+    print(build_variant(sys.argv[sys.argv.index("--variant") + 1], verbose="--verbose" in sys.argv))
+  else:
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

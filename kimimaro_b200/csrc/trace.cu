@@ -25,6 +25,12 @@ namespace {
 constexpr uint32_t kInfBits = 0x7f800000u;
 constexpr unsigned long long kValid = ~0ull;
 constexpr int kThreads = 512;   // 16 warps: a whole narrow batch expands in one pass
+// 1: compile the key-ordered invalidation rounds (invalidate_window) into the path-loop kernel.  Off in the shipped build so
+// that the kernel the round's numbers were measured with stays what it was (the extra call costs it spill traffic);
+// `python -m kimimaro_b200.build --variant claim_window` builds kimimaro_b200/_variants/claim_window.so with it.
+#ifndef B2T_WITH_CLAIM_WINDOW
+#define B2T_WITH_CLAIM_WINDOW 0
+#endif
 #ifndef B2T_TRACE_MINB
 #define B2T_TRACE_MINB 3        // resident CTAs per SM (42 registers per thread)
 #endif
@@ -70,6 +76,7 @@ struct Params {
   int nbuckets;
   int n_desc;
   int fix_branching;             // 0: paths come from the parental field already in A.dist (trace.py:154-158, 244)
+  float claim_window;            // 0: hop-synchronous invalidation rounds; > 0: key-ordered rounds of this width (invalidate_window)
 };
 
 struct Pools {
@@ -527,6 +534,127 @@ __device__ uint32_t invalidate(const Arena& A, const LabelDesc& L, const uint32_
   return total;
 }
 
+#if B2T_WITH_CLAIM_WINDOW
+// ---- the same, ordered by KEY instead of by hop count (off by default: b2t_set_claim_window) -----------
+// The reference pops its heap in order of ||w.(v - seed)|| (dijkstra_invalidation.hpp:233-237); the hop-synchronous
+// rounds above hand a voxel to whichever seed reaches it in the fewest steps.  Where balls of different radii overlap
+// that changes owners, and with them how far the claim spreads: on the CPU (oracle/oracle.c: orc_invalidate_heap is the
+// compiled reference voxel for voxel, orc_invalidate_window is this function) hop rounds give 126 of 176 skeletons
+// identical to the reference, key rounds of one voxel's width 174 of 176 at the same number of rounds.
+// Every valid voxel next to a claimed one holds its best candidate (key << 32 | seed order) in A.claim; a round claims
+// all open candidates whose key is the smallest one or below (smallest + delta), then the new owners push candidates
+// to their neighbours with atomicMin -- a min-reduction, so the order inside a round does not matter.
+// act / act2: open candidates (ping-pong), fv / fs: the voxels claimed in this round and their seeds.
+__device__ __noinline__ uint32_t invalidate_window(const Arena& A, const LabelDesc& L, const uint32_t* seeds, uint32_t n_seeds,
+                                                   float scale, float konst, float delta, uint32_t* act, uint32_t* fv,
+                                                   uint32_t* fs, uint32_t* act2, Shared& S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t seg = L.segid;
+  int dx = 0, dy = 0, dz = 0;
+  if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; }
+  const int64_t off = (int64_t)dx + (int64_t)dy * A.d.sx + (int64_t)dz * A.d.sxy;
+  const uint32_t ltmask = (1u << lane) - 1u;
+  if (threadIdx.x == 0) { S.n_next = 0; S.n_keep = 0; }
+  __syncthreads();
+  // round 0: every still-valid seed claims itself (key 0)
+  for (uint32_t i0 = 0; i0 < n_seeds; i0 += kThreads) {
+    const uint32_t i = i0 + threadIdx.x;
+    bool won = false;
+    uint32_t v = 0;
+    if (i < n_seeds) {
+      v = seeds[i];
+      if (__ldg(&A.cc[v]) == seg) won = atomicCAS(&A.claim[v], kValid, 0ull) == kValid;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, won);
+    uint32_t base = 0;
+    if (lane == 0 && m) base = atomicAdd(&S.n_next, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (won) { const uint32_t p = base + __popc(m & ltmask); fv[p] = v; fs[p] = i; }
+  }
+  __syncthreads();
+  uint32_t n_cur = S.n_next, n_act = 0, total = n_cur;
+  while (n_cur > 0) {
+    // the voxels claimed in the last round push candidates; a voxel that gets its first one joins the open list
+    for (uint32_t it = warp; it < n_cur; it += kWarps) {
+      const uint32_t u = fv[it], s = fs[it];
+      const uint32_t o = seeds[s];
+      const float r = __fadd_rn(__fmul_rn(scale, __ldg(&A.dbf[o])), konst);
+      int x, y, z, ox, oy, oz;
+      unravel(u, A.d, x, y, z);
+      unravel(o, A.d, ox, oy, oz);
+      const int nx = x + dx, ny = y + dy, nz = z + dz;
+      bool push = false;
+      uint32_t v = 0;
+      if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
+        v = (uint32_t)((int64_t)u + off);
+        const uint32_t lv = __ldg(&A.cc[v]);
+        const unsigned long long cl = __ldcg(&A.claim[v]);
+        if (lv == seg && cl != 0ull) {
+          const float a = __fmul_rn(A.wx, (float)(nx - ox)), b = __fmul_rn(A.wy, (float)(ny - oy)),
+                      c = __fmul_rn(A.wz, (float)(nz - oz));
+          const float dd = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));
+          if (dd < r) {
+            const unsigned long long cand = ((unsigned long long)__float_as_uint(dd) << 32) | s;
+            const unsigned long long old = atomicMin(&A.claim[v], cand);
+            push = old == kValid;
+          }
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, push);
+      if (m) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&S.n_keep, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (push) act[n_act + base + __popc(m & ltmask)] = v;
+      }
+    }
+    __syncthreads();
+    n_act += S.n_keep;
+    __syncthreads();
+    if (threadIdx.x == 0) { S.n_next = 0; S.n_keep = 0; S.n_proc = 0; }
+    if (n_act == 0) break;
+    // smallest open key (non-negative floats order like their bit patterns)
+    uint32_t kmin = 0xffffffffu;
+    for (uint32_t i = threadIdx.x; i < n_act; i += kThreads) kmin = min(kmin, (uint32_t)(__ldcg(&A.claim[act[i]]) >> 32));
+    kmin = block_min_u32(kmin, S.red32);           // also orders the counter reset above before the appends below
+    const float lim = __fadd_rn(__uint_as_float(kmin), delta);
+    // claim what is inside the window, keep the rest open
+    for (uint32_t i0 = 0; i0 < n_act; i0 += kThreads) {
+      const uint32_t i = i0 + threadIdx.x;
+      bool take = false, keep = false;
+      uint32_t v = 0, owner = 0;
+      if (i < n_act) {
+        v = act[i];
+        const unsigned long long c = __ldcg(&A.claim[v]);
+        const uint32_t kb = (uint32_t)(c >> 32);
+        take = kb == kmin || __uint_as_float(kb) < lim;
+        keep = !take;
+        owner = (uint32_t)c;
+        if (take) A.claim[v] = 0ull;
+      }
+      const uint32_t mt = __ballot_sync(0xffffffffu, take), mk = __ballot_sync(0xffffffffu, keep);
+      uint32_t bt = 0, bk = 0;
+      if (lane == 0 && mt) bt = atomicAdd(&S.n_next, __popc(mt));
+      if (lane == 0 && mk) bk = atomicAdd(&S.n_proc, __popc(mk));
+      bt = __shfl_sync(0xffffffffu, bt, 0);
+      bk = __shfl_sync(0xffffffffu, bk, 0);
+      if (take) { const uint32_t p = bt + __popc(mt & ltmask); fv[p] = v; fs[p] = owner; }
+      if (keep) act2[bk + __popc(mk & ltmask)] = v;
+    }
+    __syncthreads();
+    n_cur = S.n_next;
+    n_act = S.n_proc;
+    total += n_cur;
+    { uint32_t* t = act; act = act2; act2 = t; }
+    __syncthreads();
+    if (threadIdx.x == 0) { S.n_keep = 0; }
+    __syncthreads();
+  }
+  __syncthreads();
+  return total;
+}
+#endif  // B2T_WITH_CLAIM_WINDOW
+
 // ---- dijkstra3d.path_from_parents on the parental field held in A.dist (fix_branching=False) ---------
 // parents follow rule T3 (neighbour with the smallest (dist, direction)); the path is returned in
 // source -> target order like the library does: out[0] = root ... out[len-1] = target.
@@ -601,6 +729,7 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
   uint32_t valid = L.n_fg;
   int32_t status = 0;
   if (L.soma_mode) {            // one-off soma invalidation around the root (trace.py:160-168)
+    // a single seed has no competitor: both claim orders give the same set
     const uint32_t n = L.soma_done ? L.pre_invalid
                                    : invalidate(A, L, &L.root, 1, prm.soma_scale, prm.soma_const, r0, r1, r2, r3, S);
     valid -= min(valid, n);
@@ -651,7 +780,13 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
       __syncthreads();
     }
     if (valid > 0) {
+#if B2T_WITH_CLAIM_WINDOW
+      const uint32_t n = prm.claim_window > 0.0f
+                             ? invalidate_window(A, L, pout, len, prm.scale, prm.konst, prm.claim_window, r0, r1, r2, r3, S)
+                             : invalidate(A, L, pout, len, prm.scale, prm.konst, r0, r1, r2, r3, S);
+#else
       const uint32_t n = invalidate(A, L, pout, len, prm.scale, prm.konst, r0, r1, r2, r3, S);
+#endif
       valid -= min(valid, n);
       if (threadIdx.x == 0) S.invalidated += n;
     }
@@ -701,6 +836,8 @@ __global__ void __launch_bounds__(kThreads, B2T_TRACE_MINB) trace_kernel(Arena A
 //   d_scratch    6 * sum(n_fg) u32;  d_paths: path pool;  d_targets: manual targets (linear indices)
 //   d_out_len / d_out_npaths / d_out_status: n_desc each; d_out_stats: 4 * n_desc; d_work_counter: 1 u32 (zeroed here)
 // =================================================================================================
+bool b2t_claim_window_built() { return B2T_WITH_CLAIM_WINDOW != 0; }
+
 B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,
                                uint32_t* d_stamp, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
                                const void* d_desc, int n_desc, float scale, float konst, float soma_scale,
@@ -722,7 +859,9 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
   P.keys = reinterpret_cast<const unsigned long long*>(d_keys); P.hist = d_hist; P.cursor = d_cursor;
   P.scratch = d_scratch; P.paths = d_paths; P.targets = d_targets; P.out_len = d_out_len; P.out_npaths = d_out_npaths;
   P.out_status = d_out_status; P.out_stats = d_out_stats; P.work_counter = d_work_counter;
-  Params prm{scale, konst, soma_scale, soma_const, nbuckets, n_desc, fix_branching ? 1 : 0};
+  // b2t_set_claim_window: width of the key-ordered invalidation rounds in units of the smallest voxel edge (0 = hop rounds)
+  const float wmin = wx < wy ? (wx < wz ? wx : wz) : (wy < wz ? wy : wz);
+  Params prm{scale, konst, soma_scale, soma_const, nbuckets, n_desc, fix_branching ? 1 : 0, b2t_claim_window() * wmin};
   B2T_CUDA_TRY(cudaMemsetAsync(d_work_counter, 0, sizeof(uint32_t), st));
   int dev = 0, sms = 0, per_sm = 0;
   B2T_CUDA_TRY(cudaGetDevice(&dev));

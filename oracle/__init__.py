@@ -53,6 +53,8 @@ def lib():
     _lib.orc_railroad.restype = c_i64
     _lib.orc_invalidate_seq.restype = c_i64
     _lib.orc_invalidate_rounds.restype = c_i64
+    _lib.orc_invalidate_heap.restype = c_i64
+    _lib.orc_invalidate_window.restype = c_i64
     _lib.orc_fill_voids.restype = c_i64
     _lib.orc_ccl26.restype = c_i64
   return _lib
@@ -161,16 +163,29 @@ def invalidation_radii(DBF, scale, const, path):
   return (np.float32(scale) * d + np.float32(const)).astype(np.float32)
 
 
+WINDOW_ROUNDS = [0, 0]   # (rounds, calls) of the 'window:' mode, for the design study
+
+
 def roll_invalidation_ball_inside_component(labels, DBF, scale, const, anisotropy, path, mode="rounds"):
   """skeletontricks.pyx:373-418.  labels (uint8/bool, Fortran) is edited in place.
-  mode: 'rounds' = the engine's round-synchronous claim; 'seq' = ordered best-first claim."""
+  mode: 'rounds' = the engine's round-synchronous claim; 'seq' = ordered best-first claim with canonical ties;
+  'heap' = the reference's loop literally, libstdc++'s heap order for equal keys included (== the compiled reference)."""
   assert labels.flags["F_CONTIGUOUS"] and labels.ndim == 3
   m = labels.view(np.uint8)
   sx, sy, sz = m.shape
   path = np.asarray(path, dtype=np.int64).reshape(-1, 3)
   radii = invalidation_radii(DBF, scale, const, path)
   seeds = (path[:, 0] + sx * (path[:, 1] + sy * path[:, 2])).astype(np.int64)
-  fn = lib().orc_invalidate_rounds if mode == "rounds" else lib().orc_invalidate_seq
+  if isinstance(mode, str) and mode.startswith("window:"):     # 'window:<delta in units of the smallest voxel edge>'
+    delta = np.float32(float(mode.split(":")[1]) * float(min(anisotropy)))
+    nr = c_i64(0)
+    n = lib().orc_invalidate_window(_p(m), c_i64(sx), c_i64(sy), c_i64(sz), c_f32(anisotropy[0]), c_f32(anisotropy[1]),
+                                    c_f32(anisotropy[2]), _p(seeds), _p(radii), c_i64(seeds.size), c_f32(delta),
+                                    ctypes.byref(nr))
+    WINDOW_ROUNDS[0] += nr.value
+    WINDOW_ROUNDS[1] += 1
+    return int(n), labels
+  fn = {"rounds": lib().orc_invalidate_rounds, "seq": lib().orc_invalidate_seq, "heap": lib().orc_invalidate_heap}[mode]
   n = fn(_p(m), c_i64(sx), c_i64(sy), c_i64(sz), c_f32(anisotropy[0]), c_f32(anisotropy[1]),
          c_f32(anisotropy[2]), _p(seeds), _p(radii), c_i64(seeds.size))
   return int(n), labels

@@ -448,6 +448,150 @@ ORC_API int64_t orc_invalidate_seq(uint8_t* mask, int64_t sx, int64_t sy, int64_
   return invalidated;
 }
 
+/* orc_invalidate_window: a parallel claim process ordered by KEY instead of by hop count (design study for the
+ * engine's K5): every valid voxel holds its best candidate (||w.(v - seed)||, seed order); a round
+ * claims ALL candidates whose key is below (smallest open key + delta) at once, then the new owners push candidates to
+ * their valid neighbours (min-reduction, so the order inside a round does not matter).  delta = 0 claims exact ties
+ * only and is the ordered process of orc_invalidate_seq up to pushes that undercut the current key; a delta of about
+ * one voxel needs about as many rounds as the hop-synchronous orc_invalidate_rounds. */
+ORC_API int64_t orc_invalidate_window(uint8_t* mask, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
+                                      const int64_t* seeds, const float* radii, int64_t n_seeds, float delta,
+                                      int64_t* n_rounds) {
+  const int64_t sxy = sx * sy, V = sxy * sz;
+  float* ck = (float*)malloc(sizeof(float) * V);
+  int32_t* cs = (int32_t*)malloc(sizeof(int32_t) * V);
+  int64_t* act = (int64_t*)malloc(sizeof(int64_t) * (V + n_seeds));
+  int64_t* claim = (int64_t*)malloc(sizeof(int64_t) * (V + n_seeds));
+  for (int64_t i = 0; i < V; i++) cs[i] = -1;
+  int64_t nact = 0, invalidated = 0, rounds = 0;
+  for (int64_t i = 0; i < n_seeds; i++) {
+    const int64_t s = seeds[i];
+    if (!mask[s]) continue;
+    if (cs[s] < 0) { cs[s] = (int32_t)i; ck[s] = 0.0f; act[nact++] = s; }
+  }
+  while (nact > 0) {
+    float kmin = ck[act[0]];
+    for (int64_t q = 1; q < nact; q++) if (ck[act[q]] < kmin) kmin = ck[act[q]];
+    const float lim = kmin + delta;
+    int64_t nc = 0, keep = 0;
+    for (int64_t q = 0; q < nact; q++) {
+      const int64_t v = act[q];
+      if (ck[v] == kmin || ck[v] < lim) claim[nc++] = v; else act[keep++] = v;
+    }
+    nact = keep;
+    for (int64_t q = 0; q < nc; q++) { mask[claim[q]] = 0; invalidated++; }
+    for (int64_t q = 0; q < nc; q++) {
+      const int64_t loc = claim[q];
+      const int32_t sd = cs[loc];
+      const int64_t o = seeds[sd];
+      const int64_t oz = o / sxy, oy = (o - oz * sxy) / sx, ox = o - sx * (oy + sy * oz);
+      const int64_t z = loc / sxy, y = (loc - z * sxy) / sx, x = loc - sx * (y + sy * z);
+      const float r = radii[sd];
+      for (int i = 0; i < 26; i++) {
+        const int64_t nx = x + DX[i], ny = y + DY[i], nz = z + DZ[i];
+        if (nx < 0 || ny < 0 || nz < 0 || nx >= sx || ny >= sy || nz >= sz) continue;
+        const int64_t nb = nx + sx * (ny + sy * nz);
+        if (!mask[nb]) continue;
+        const float d = seed_dist(wx, wy, wz, nx, ny, nz, ox, oy, oz);
+        if (!(d < r)) continue;
+        if (cs[nb] < 0) { cs[nb] = sd; ck[nb] = d; act[nact++] = nb; }
+        else if (d < ck[nb] || (d == ck[nb] && sd < cs[nb])) { cs[nb] = sd; ck[nb] = d; }
+      }
+    }
+    rounds++;
+  }
+  if (n_rounds) *n_rounds = rounds;
+  free(ck); free(cs); free(act); free(claim);
+  return invalidated;
+}
+
+/* orc_invalidate_heap: the reference's loop LITERALLY, including what the C++ standard leaves to the library: the
+ * order of equal keys in std::priority_queue.  libstdc++'s push_heap / pop_heap (bits/stl_heap.h: __push_heap,
+ * __adjust_heap) are restated below and driven with the reference's comparator `t1.dist >= t2.dist`
+ * (dijkstra_invalidation.hpp:233-237), the neighbours are visited in the reference's order with its aliasing at the
+ * x faces (a corner entry is gated on y and z only, hpp:116-123, so at x = 0 / sx-1 it repeats the yz diagonal and that
+ * voxel is pushed twice).  With this the restatement reproduces the compiled reference voxel for voxel
+ * (tests/test_oracle_cpu.py::test_invalidation_vs_reference_ext), i.e. every difference of the other two forms is a
+ * tie-order effect and nothing else. */
+typedef struct { float dist; int64_t orig; int64_t value; float maxd; } rnode;
+static inline int rcomp(const rnode* a, const rnode* b) { return a->dist >= b->dist; }
+static void r_push_heap(rnode* first, int64_t hole, int64_t top, rnode value) {
+  int64_t parent = (hole - 1) / 2;
+  while (hole > top && rcomp(&first[parent], &value)) {
+    first[hole] = first[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  first[hole] = value;
+}
+static void r_adjust_heap(rnode* first, int64_t hole, int64_t len, rnode value) {
+  const int64_t top = hole;
+  int64_t second = hole;
+  while (second < (len - 1) / 2) {
+    second = 2 * (second + 1);
+    if (rcomp(&first[second], &first[second - 1])) second--;
+    first[hole] = first[second];
+    hole = second;
+  }
+  if ((len & 1) == 0 && second == (len - 2) / 2) {
+    second = 2 * (second + 1);
+    first[hole] = first[second - 1];
+    hole = second - 1;
+  }
+  r_push_heap(first, hole, top, value);
+}
+
+ORC_API int64_t orc_invalidate_heap(uint8_t* mask, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
+                                    const int64_t* seeds, const float* radii, int64_t n_seeds) {
+  const int64_t sxy = sx * sy;
+  int64_t cap = 4096, n = 0;
+  rnode* a = (rnode*)malloc(sizeof(rnode) * cap);
+#define HPUSH(D, O, VV, M) do { \
+    if (n == cap) { cap *= 2; a = (rnode*)realloc(a, sizeof(rnode) * cap); } \
+    rnode xx = {(D), (O), (VV), (M)}; a[n++] = xx; r_push_heap(a, n - 1, 0, xx); } while (0)
+  for (int64_t i = 0; i < n_seeds; i++) HPUSH(0.0f, seeds[i], seeds[i], radii[i]);
+  int64_t invalidated = 0;
+  while (n > 0) {
+    const rnode top = a[0];
+    if (n > 1) {                       /* std::pop_heap */
+      const rnode value = a[n - 1];
+      a[n - 1] = a[0];
+      r_adjust_heap(a, 0, n - 1, value);
+    }
+    n--;                               /* pop_back */
+    const int64_t loc = top.value;
+    if (!mask[loc]) continue;
+    mask[loc] = 0; invalidated++;
+    const int64_t o = top.orig;
+    const int64_t oz = o / sxy, oy = (o - oz * sxy) / sx, ox = o - sx * (oy + sy * oz);
+    const int64_t z = loc / sxy, y = (loc - z * sxy) / sx, x = loc - sx * (y + sy * z);
+    int64_t nh[26];
+    nh[0] = -1 * (x > 0); nh[1] = (x < sx - 1); nh[2] = -sx * (y > 0); nh[3] = sx * (y < sy - 1);
+    nh[4] = -sxy * (z > 0); nh[5] = sxy * (z < sz - 1);
+    nh[6] = (nh[0] + nh[2]) * (nh[0] && nh[2]); nh[7] = (nh[0] + nh[3]) * (nh[0] && nh[3]);
+    nh[8] = (nh[1] + nh[2]) * (nh[1] && nh[2]); nh[9] = (nh[1] + nh[3]) * (nh[1] && nh[3]);
+    nh[10] = (nh[2] + nh[4]) * (nh[2] && nh[4]); nh[11] = (nh[2] + nh[5]) * (nh[2] && nh[5]);
+    nh[12] = (nh[3] + nh[4]) * (nh[3] && nh[4]); nh[13] = (nh[3] + nh[5]) * (nh[3] && nh[5]);
+    nh[14] = (nh[0] + nh[4]) * (nh[0] && nh[4]); nh[15] = (nh[0] + nh[5]) * (nh[0] && nh[5]);
+    nh[16] = (nh[1] + nh[4]) * (nh[1] && nh[4]); nh[17] = (nh[1] + nh[5]) * (nh[1] && nh[5]);
+    nh[18] = (nh[0] + nh[2] + nh[4]) * (nh[2] && nh[4]); nh[19] = (nh[1] + nh[2] + nh[4]) * (nh[2] && nh[4]);
+    nh[20] = (nh[0] + nh[3] + nh[4]) * (nh[3] && nh[4]); nh[21] = (nh[0] + nh[2] + nh[5]) * (nh[2] && nh[5]);
+    nh[22] = (nh[1] + nh[3] + nh[4]) * (nh[3] && nh[4]); nh[23] = (nh[1] + nh[2] + nh[5]) * (nh[2] && nh[5]);
+    nh[24] = (nh[0] + nh[3] + nh[5]) * (nh[3] && nh[5]); nh[25] = (nh[1] + nh[3] + nh[5]) * (nh[3] && nh[5]);
+    for (int i = 0; i < 26; i++) {
+      if (nh[i] == 0) continue;
+      const int64_t nb = loc + nh[i];
+      if (!mask[nb]) continue;
+      const int64_t nz = nb / sxy, ny = (nb - nz * sxy) / sx, nx = nb - sx * (ny + sy * nz);
+      const float d = seed_dist(wx, wy, wz, nx, ny, nz, ox, oy, oz);
+      if (d < top.maxd) HPUSH(d, o, nb, top.maxd);
+    }
+  }
+#undef HPUSH
+  free(a);
+  return invalidated;
+}
+
 ORC_API int64_t orc_invalidate_rounds(uint8_t* mask, int64_t sx, int64_t sy, int64_t sz, float wx, float wy,
                                       float wz, const int64_t* seeds, const float* radii, int64_t n_seeds) {
   const int64_t sxy = sx * sy, V = sxy * sz;
