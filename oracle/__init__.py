@@ -177,11 +177,12 @@ def roll_invalidation_ball_inside_component(labels, DBF, scale, const, anisotrop
   radii = invalidation_radii(DBF, scale, const, path)
   seeds = (path[:, 0] + sx * (path[:, 1] + sy * path[:, 2])).astype(np.int64)
   if isinstance(mode, str) and mode.startswith("window:"):     # 'window:<delta in units of the smallest voxel edge>'
-    delta = np.float32(float(mode.split(":")[1]) * float(min(anisotropy)))
+    parts = mode.split(":")                                    # 'window:<delta>[:hi]' (hi: the later seed wins a tie)
+    delta = np.float32(float(parts[1]) * float(min(anisotropy)))
     nr = c_i64(0)
     n = lib().orc_invalidate_window(_p(m), c_i64(sx), c_i64(sy), c_i64(sz), c_f32(anisotropy[0]), c_f32(anisotropy[1]),
                                     c_f32(anisotropy[2]), _p(seeds), _p(radii), c_i64(seeds.size), c_f32(delta),
-                                    ctypes.byref(nr))
+                                    ctypes.byref(nr), ctypes.c_int(1 if len(parts) > 2 and parts[2] == "hi" else 0))
     WINDOW_ROUNDS[0] += nr.value
     WINDOW_ROUNDS[1] += 1
     return int(n), labels

@@ -456,7 +456,7 @@ ORC_API int64_t orc_invalidate_seq(uint8_t* mask, int64_t sx, int64_t sy, int64_
  * one voxel needs about as many rounds as the hop-synchronous orc_invalidate_rounds. */
 ORC_API int64_t orc_invalidate_window(uint8_t* mask, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
                                       const int64_t* seeds, const float* radii, int64_t n_seeds, float delta,
-                                      int64_t* n_rounds) {
+                                      int64_t* n_rounds, int tie_high) {
   const int64_t sxy = sx * sy, V = sxy * sz;
   float* ck = (float*)malloc(sizeof(float) * V);
   int32_t* cs = (int32_t*)malloc(sizeof(int32_t) * V);
@@ -495,7 +495,7 @@ ORC_API int64_t orc_invalidate_window(uint8_t* mask, int64_t sx, int64_t sy, int
         const float d = seed_dist(wx, wy, wz, nx, ny, nz, ox, oy, oz);
         if (!(d < r)) continue;
         if (cs[nb] < 0) { cs[nb] = sd; ck[nb] = d; act[nact++] = nb; }
-        else if (d < ck[nb] || (d == ck[nb] && sd < cs[nb])) { cs[nb] = sd; ck[nb] = d; }
+        else if (d < ck[nb] || (d == ck[nb] && (tie_high ? sd > cs[nb] : sd < cs[nb]))) { cs[nb] = sd; ck[nb] = d; }
       }
     }
     rounds++;
