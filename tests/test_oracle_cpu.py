@@ -408,6 +408,10 @@ def test_avocado_pieces_vs_reference_ext(ref_ext):
       got = teasar.find_avocado_fruit(lab, *c)
       ref = ref_ext.find_avocado_fruit(lab, *c)
       assert (int(got[0]), int(got[1])) == (int(ref[0]), int(ref[1])), (trial, c)
+      # the product's host-side vote works on the three axis lines through the voxel (copied from the device)
+      from kimimaro_b200 import intake
+      mine = intake.find_avocado_fruit(lab[:, c[1], c[2]], lab[c[0], :, c[2]], lab[c[0], c[1], :], *c)
+      assert mine == (int(ref[0]), int(ref[1])), (trial, c)
     # a cc labelling that is COARSER than the original one (what engage_avocado_protection feeds it, intake.py:637)
     coarse = np.asfortranarray((lab + 1) // 2).astype(np.uint32)
     assert teasar.get_mapping(lab, coarse) == {int(a): int(b) for a, b in ref_ext.get_mapping(lab, coarse).items()}
