@@ -359,14 +359,30 @@ def test_fill_all_holes_oracle_matches_scipy():
   assert len(np.unique(out)) < len(np.unique(cc))
 
 
-def test_fill_all_holes_host_logic_matches_oracle():
+def _nested_boxes(rng, shape, k):
+  lab = np.zeros(shape, np.uint32, order="F")
+  for i in range(1, k + 1):              # later boxes sit inside earlier ones more often than not; some get hollowed
+    lo = [int(rng.integers(0, s - 6)) for s in shape]
+    hi = [int(rng.integers(l + 4, min(s, l + 4 + s // 2) + 1)) for l, s in zip(lo, shape)]
+    lab[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = i
+    if i % 2 == 0 and all(h - l > 4 for l, h in zip(lo, hi)):
+      lab[lo[0] + 2:hi[0] - 2, lo[1] + 2:hi[1] - 2, lo[2] + 2:hi[2] - 2] = 0
+  return lab
+
+
+@pytest.mark.parametrize("volume", ["crafted", 0, 1, 2, 3])
+def test_fill_all_holes_host_logic_matches_oracle(volume):
   """kimimaro_b200.intake.fill_all_holes on CPU tensors with the fill kernel replaced by the oracle's fill: crops,
   layout, swallowed-component bookkeeping and the write-back are the product's, the fill itself is the checker's."""
   import scipy.ndimage as ndi
   import torch
   from kimimaro_b200 import intake
   from oracle import teasar
-  v = _holey_volume()
+  if volume == "crafted":
+    v = _holey_volume()
+  else:
+    rng = np.random.default_rng(40 + volume)
+    v = _nested_boxes(rng, tuple(int(x) for x in rng.integers(20, 44, size=3)), 8)
   cc, n = oracle.connected_components(v)
   ref = teasar.fill_all_holes(cc.copy(order="F"), n)
   calls = []
@@ -386,7 +402,8 @@ def test_fill_all_holes_host_logic_matches_oracle():
   out, filled = intake.fill_all_holes(d_cc, cc.shape, n, count, bbox, fill_fn=fill_fn, return_fill_count=True)
   got = out.numpy().reshape(cc.shape, order="F")
   assert np.array_equal(got, ref.astype(np.int32))
-  assert filled > 0 and len(calls) >= 2
+  if volume == "crafted":
+    assert filled > 0 and len(calls) >= 2
 
 
 # ---- fix_avocados: oracle restatement pinned against the reference ----
