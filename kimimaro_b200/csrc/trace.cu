@@ -20,6 +20,15 @@
 // queues live in a scratch pool indexed by the label's foreground-count prefix sum.
 #include "common.cuh"
 
+// B2T_HOST_EMU: tests/host/trace_emu.cpp compiles this file with g++ against a SIMT emulation (one OS thread per CUDA
+// thread of ONE block, barriers for __syncthreads and the warp intrinsics) so that the CPU suite can run the device
+// functions below against the oracle; only the PTX timer read and the host launcher are left out of that build.
+#ifdef B2T_HOST_EMU
+#define B2T_GLOBALTIMER(v_) v_ = 0
+#else
+#define B2T_GLOBALTIMER(v_) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v_))
+#endif
+
 namespace {
 
 constexpr uint32_t kInfBits = 0x7f800000u;
@@ -720,7 +729,7 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
   uint32_t* out = P.paths + L.path_off;
   unsigned long long t_start = 0;
   if (threadIdx.x == 0) {
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    B2T_GLOBALTIMER(t_start);
     S.bucket = prm.nbuckets - 1;
     S.relax = 0; S.rounds = 0; S.invalidated = 0;
     A.pdrf[L.root] = 0.0f;      // parents[root] = 0: the first rail (trace.py:220)
@@ -805,7 +814,7 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
     P.out_stats[4 * job + 1] = S.rounds;
     P.out_stats[4 * job + 2] = S.invalidated;
     unsigned long long t_end;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    B2T_GLOBALTIMER(t_end);
     P.out_stats[4 * job + 3] = (uint32_t)((t_end - t_start) / 1000ull);   // microseconds this label held its CTA
   }
   __syncthreads();
@@ -836,6 +845,7 @@ __global__ void __launch_bounds__(kThreads, B2T_TRACE_MINB) trace_kernel(Arena A
 //   d_scratch    6 * sum(n_fg) u32;  d_paths: path pool;  d_targets: manual targets (linear indices)
 //   d_out_len / d_out_npaths / d_out_status: n_desc each; d_out_stats: 4 * n_desc; d_work_counter: 1 u32 (zeroed here)
 // =================================================================================================
+#ifndef B2T_HOST_EMU
 bool b2t_claim_window_built() { return B2T_WITH_CLAIM_WINDOW != 0; }
 
 B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,
@@ -876,3 +886,4 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
   b2t_count_launches(1);
   return B2T_OK;
 }
+#endif  // B2T_HOST_EMU

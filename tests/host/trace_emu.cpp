@@ -1,0 +1,121 @@
+// Test infrastructure, never shipped: the device functions of kimimaro_b200/csrc/trace.cu compiled for the CPU
+// against the SIMT emulation of emu_include/cuda_runtime.h, so that tests/test_trace_emu_cpu.py can run the engine's
+// invalidation -- the hop-synchronous one it ships and the key-ordered one of the claim_window variant -- on the very
+// source text the GPU runs and compare it with the oracle (orc_invalidate_rounds / orc_invalidate_window).
+#define B2T_HOST_EMU 1
+#define B2T_WITH_CLAIM_WINDOW 1
+#include <cuda_runtime.h>   // emu_include/ comes first on the include path
+
+thread_local uint3 threadIdx, blockIdx;
+uint3 blockDim, gridDim;
+namespace simt {
+Block g_block;
+struct Start { void (*fn)(void*); void* arg; unsigned tid, block; };
+static void* entry(void* p) {
+  Start* s = (Start*)p;
+  threadIdx = uint3{s->tid, 0, 0};
+  blockIdx = uint3{s->block, 0, 0};
+  s->fn(s->arg);
+  return nullptr;
+}
+void run_block(int n_threads, unsigned block, unsigned grid, void (*fn)(void*), void* arg) {
+  blockDim = uint3{(unsigned)n_threads, 1, 1};
+  gridDim = uint3{grid, 1, 1};
+  g_block.n_threads = n_threads;
+  pthread_barrier_init(&g_block.bar, nullptr, n_threads);
+  for (int w = 0; w < n_threads / 32; w++) pthread_barrier_init(&g_block.warps[w].bar, nullptr, 32);
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * n_threads);
+  Start* st = (Start*)malloc(sizeof(Start) * n_threads);
+  pthread_attr_t attr;
+  pthread_attr_init(&attr);
+  pthread_attr_setstacksize(&attr, 256 * 1024);
+  for (int t = 0; t < n_threads; t++) {
+    st[t] = Start{fn, arg, (unsigned)t, block};
+    if (pthread_create(&th[t], &attr, entry, &st[t]) != 0) { fprintf(stderr, "pthread_create failed\n"); abort(); }
+  }
+  for (int t = 0; t < n_threads; t++) pthread_join(th[t], nullptr);
+  pthread_attr_destroy(&attr);
+  pthread_barrier_destroy(&g_block.bar);
+  for (int w = 0; w < n_threads / 32; w++) pthread_barrier_destroy(&g_block.warps[w].bar);
+  free(th); free(st);
+}
+}  // namespace simt
+
+// what common.cuh declares and capi.cu defines in the real library
+void b2t_set_error(const char*, ...) {}
+void b2t_count_launches(int) {}
+int b2t_coop_limit() { return 0; }
+int b2t_trace_limit() { return 0; }
+bool b2t_claim_window_built() { return true; }
+float b2t_claim_window() { return 0.0f; }
+
+#include "../../kimimaro_b200/csrc/trace.cu"
+
+namespace {
+struct InvArgs {
+  Arena A; LabelDesc L; const uint32_t* seeds; uint32_t n_seeds; float scale, konst, delta;
+  uint32_t *r0, *r1, *r2, *r3; int mode; uint32_t result;
+};
+Shared g_S;
+void inv_thread(void* p) {
+  InvArgs* a = (InvArgs*)p;
+  const uint32_t n = a->mode ? invalidate_window(a->A, a->L, a->seeds, a->n_seeds, a->scale, a->konst, a->delta, a->r0, a->r1,
+                                                 a->r2, a->r3, g_S)
+                             : invalidate(a->A, a->L, a->seeds, a->n_seeds, a->scale, a->konst, a->r0, a->r1, a->r2, a->r3, g_S);
+  if (threadIdx.x == 0) a->result = n;
+}
+}  // namespace
+
+// One block of the engine's 512 threads runs roll_invalidation_ball_inside_component on a label of the dense arena.
+// claim: one 64-bit word per voxel, ~0 = valid (the engine's kValid), 0 = invalid; edited in place.
+// mode 0: invalidate (hop rounds); 1: invalidate_window with `delta` (already in physical units).
+extern "C" long emu_invalidate(const uint32_t* cc, const float* dbf, unsigned long long* claim, int sx, int sy, int sz,
+                               float wx, float wy, float wz, uint32_t segid, uint32_t n_fg, const uint32_t* seeds,
+                               uint32_t n_seeds, float scale, float konst, float delta, int mode) {
+  InvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A.cc = cc; a.A.dbf = dbf; a.A.claim = claim;
+  a.A.d = Dims{sx, sy, sz, (uint32_t)(sx * sy)};
+  a.A.wx = wx; a.A.wy = wy; a.A.wz = wz;
+  a.L.segid = segid; a.L.n_fg = n_fg;
+  a.seeds = seeds; a.n_seeds = n_seeds; a.scale = scale; a.konst = konst; a.delta = delta; a.mode = mode;
+  uint32_t* scratch = (uint32_t*)malloc(sizeof(uint32_t) * 4 * (size_t)(n_fg + 1));
+  a.r0 = scratch; a.r1 = scratch + n_fg; a.r2 = scratch + 2 * (size_t)n_fg; a.r3 = scratch + 3 * (size_t)n_fg;
+  simt::run_block(kThreads, 0, 1, inv_thread, &a);
+  free(scratch);
+  return (long)a.result;
+}
+
+// The whole path loop (trace_kernel: find_target -> railroad -> invalidate -> rail, trace.py:196-267) for a batch of
+// labels on ONE emulated block, which pulls the labels one after another from the work counter like a CTA on the GPU.
+// Arguments as b2t_trace_batch (host arrays instead of device arrays); claim_window in physical units, 0 = hop rounds.
+namespace {
+struct KArgs { Arena A; const LabelDesc* descs; Pools P; Params prm; };
+void kernel_thread(void* p) {
+  KArgs* k = (KArgs*)p;
+  trace_kernel(k->A, k->descs, k->P, k->prm);
+}
+}  // namespace
+
+extern "C" int emu_trace_batch(const uint32_t* cc, const float* dbf, float* pdrf, float* dist, unsigned long long* claim,
+                               uint32_t* stamp, int sx, int sy, int sz, float wx, float wy, float wz, const void* desc,
+                               int n_desc, float scale, float konst, float soma_scale, float soma_const, int fix_branching,
+                               int nbuckets, const unsigned long long* keys, const uint32_t* hist, const uint32_t* cursor,
+                               uint32_t* scratch, uint32_t* paths, const uint32_t* targets, uint32_t* out_len,
+                               uint32_t* out_npaths, int32_t* out_status, uint32_t* out_stats, uint32_t* work_counter,
+                               float claim_window) {
+  static_assert(sizeof(LabelDesc) == 64, "LabelDesc layout");
+  KArgs k;
+  memset(&k, 0, sizeof(k));
+  k.A.cc = cc; k.A.dbf = dbf; k.A.pdrf = pdrf; k.A.dist = dist; k.A.claim = claim; k.A.stamp = stamp;
+  k.A.d = Dims{sx, sy, sz, (uint32_t)(sx * sy)};
+  k.A.wx = wx; k.A.wy = wy; k.A.wz = wz;
+  k.descs = (const LabelDesc*)desc;
+  k.P.keys = keys; k.P.hist = hist; k.P.cursor = cursor; k.P.scratch = scratch; k.P.paths = paths; k.P.targets = targets;
+  k.P.out_len = out_len; k.P.out_npaths = out_npaths; k.P.out_status = out_status; k.P.out_stats = out_stats;
+  k.P.work_counter = work_counter;
+  k.prm = Params{scale, konst, soma_scale, soma_const, nbuckets, n_desc, fix_branching ? 1 : 0, claim_window};
+  *work_counter = 0;
+  simt::run_block(kThreads, 0, 1, kernel_thread, &k);
+  return 0;
+}
