@@ -9,6 +9,15 @@
 //                and fetch the radii (DBF at the vertex, trace.py:186-187) in the same pass.
 #include "common.cuh"
 
+// Kernel launches go through one macro so that the CPU suite can compile this file with g++ against the SIMT emulation of
+// tests/host/emu_include/cuda_runtime.h (B2T_HOST_EMU: the kernels here have no block-level synchronisation, so a
+// launch is a loop over blocks and threads) and run the very kernels against the oracle.
+#ifdef B2T_HOST_EMU
+#define B2T_LAUNCH(kernel_, grid_, block_, stream_) simt::seq_launch((grid_), (block_), [](auto... a_) { kernel_(a_...); })
+#else
+#define B2T_LAUNCH(kernel_, grid_, block_, stream_) kernel_<<<(grid_), (block_), 0, (stream_)>>>
+#endif
+
 namespace {
 
 struct Dims {
@@ -142,9 +151,9 @@ unsigned grid_for(uint64_t V) {
 
 template <typename T>
 int ccl_launch(const T* labels, Dims d, uint64_t V, uint32_t* parent, uint8_t* is_root, cudaStream_t st) {
-  ccl_init_kernel<T><<<grid_for(V), 256, 0, st>>>(labels, parent, V);
-  ccl_merge_kernel<T><<<grid_for(V), 256, 0, st>>>(labels, parent, d, V);
-  ccl_flatten_kernel<<<grid_for(V), 256, 0, st>>>(parent, is_root, V);
+  B2T_LAUNCH(ccl_init_kernel<T>, grid_for(V), 256, st)(labels, parent, V);
+  B2T_LAUNCH(ccl_merge_kernel<T>, grid_for(V), 256, st)(labels, parent, d, V);
+  B2T_LAUNCH(ccl_flatten_kernel, grid_for(V), 256, st)(parent, is_root, V);
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(3);
   return B2T_OK;
@@ -174,7 +183,7 @@ B2T_EXPORT int b2t_ccl26_roots(const void* d_labels, int label_bytes, int64_t sx
 // Step 2: d_parent (in place) becomes the cc label volume: cc[v] = d_rank[parent[v]], 0 on background.
 B2T_EXPORT int b2t_ccl_relabel(uint32_t* d_parent, const int32_t* d_rank, uint64_t n_voxels, void* stream) {
   B2T_REQUIRE(d_parent && d_rank, "b2t_ccl_relabel: null pointer");
-  ccl_relabel_kernel<<<grid_for(n_voxels), 256, 0, (cudaStream_t)stream>>>(d_parent, d_rank, n_voxels);
+  B2T_LAUNCH(ccl_relabel_kernel, grid_for(n_voxels), 256, (cudaStream_t)stream)(d_parent, d_rank, n_voxels);
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(1);
   return B2T_OK;
@@ -249,10 +258,10 @@ B2T_EXPORT int b2t_fill_voids(uint8_t* d_mask, int64_t sx, int64_t sy, int64_t s
   cudaStream_t st = (cudaStream_t)stream;
   Dims d{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
   B2T_CUDA_TRY(cudaMemsetAsync(d_ctrl, 0, 8 * sizeof(uint32_t), st));
-  fill_init_kernel<<<grid_for(V), 256, 0, st>>>(d_mask, d_queue, d_reach, V);
-  fill_merge_kernel<<<grid_for(V), 256, 0, st>>>(d_mask, d_queue, d, V);
-  fill_flatten_kernel<<<grid_for(V), 256, 0, st>>>(d_queue, d_reach, d, V);
-  fill_apply_kernel<<<grid_for(V), 256, 0, st>>>(d_mask, d_queue, d_reach, d_ctrl, V);
+  B2T_LAUNCH(fill_init_kernel, grid_for(V), 256, st)(d_mask, d_queue, d_reach, V);
+  B2T_LAUNCH(fill_merge_kernel, grid_for(V), 256, st)(d_mask, d_queue, d, V);
+  B2T_LAUNCH(fill_flatten_kernel, grid_for(V), 256, st)(d_queue, d_reach, d, V);
+  B2T_LAUNCH(fill_apply_kernel, grid_for(V), 256, st)(d_mask, d_queue, d_reach, d_ctrl, V);
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(4);
   return B2T_OK;
@@ -280,7 +289,7 @@ B2T_EXPORT int b2t_segment_seqsum(const float* d_xs, const float* d_ys, const in
                                   float* d_outx, float* d_outy, void* stream) {
   if (n_seg == 0) return B2T_OK;
   B2T_REQUIRE(d_xs && d_ys && d_off && d_outx && d_outy, "b2t_segment_seqsum: null pointer");
-  segment_seqsum_kernel<<<(n_seg + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_xs, d_ys, d_off, n_seg, d_outx, d_outy);
+  B2T_LAUNCH(segment_seqsum_kernel, (n_seg + 127) / 128, 128, (cudaStream_t)stream)(d_xs, d_ys, d_off, n_seg, d_outx, d_outy);
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(1);
   return B2T_OK;
@@ -291,7 +300,7 @@ B2T_EXPORT int b2t_gather_paths(const uint32_t* d_pool, const uint32_t* d_src_of
                                 const uint64_t* d_dst_off, uint32_t n_seg, const float* d_dbf, uint32_t* d_dst_vox,
                                 float* d_dst_radius, void* stream) {
   if (n_seg == 0) return B2T_OK;
-  gather_paths_kernel<<<n_seg, 128, 0, (cudaStream_t)stream>>>(d_pool, d_src_off, d_len, d_dst_off, d_dbf, d_dst_vox,
+  B2T_LAUNCH(gather_paths_kernel, n_seg, 128, (cudaStream_t)stream)(d_pool, d_src_off, d_len, d_dst_off, d_dbf, d_dst_vox,
                                                               d_dst_radius);
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(1);

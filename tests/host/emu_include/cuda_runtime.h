@@ -153,4 +153,25 @@ static inline long long max(long long a, long long b) { return a > b ? a : b; }
 namespace simt {
 // run fn(thread index) on n_threads OS threads as ONE block (threadIdx.x = 0 .. n_threads-1, blockIdx.x = block)
 void run_block(int n_threads, unsigned block, unsigned grid, void (*fn)(void*), void* arg);
+
+// kernels WITHOUT block-level synchronisation: a launch is a loop over blocks and threads on the calling thread (one
+// valid interleaving of a grid whose threads only meet in atomics)
+template <typename F> struct SeqLaunch {
+  unsigned g, b;
+  F f;
+  template <typename... A> void operator()(A... a) const {
+    gridDim = uint3{g, 1, 1};
+    blockDim = uint3{b, 1, 1};
+    for (unsigned bx = 0; bx < g; bx++)
+      for (unsigned tx = 0; tx < b; tx++) {
+        blockIdx = uint3{bx, 0, 0};
+        threadIdx = uint3{tx, 0, 0};
+        f(a...);
+      }
+  }
+};
+template <typename F> SeqLaunch<F> seq_launch(unsigned long long g, unsigned b, F f) { return SeqLaunch<F>{(unsigned)g, b, f}; }
 }  // namespace simt
+
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }

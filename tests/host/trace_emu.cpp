@@ -4,50 +4,7 @@
 // source text the GPU runs and compare it with the oracle (orc_invalidate_rounds / orc_invalidate_window).
 #define B2T_HOST_EMU 1
 #define B2T_WITH_CLAIM_WINDOW 1
-#include <cuda_runtime.h>   // emu_include/ comes first on the include path
-
-thread_local uint3 threadIdx, blockIdx;
-uint3 blockDim, gridDim;
-namespace simt {
-Block g_block;
-struct Start { void (*fn)(void*); void* arg; unsigned tid, block; };
-static void* entry(void* p) {
-  Start* s = (Start*)p;
-  threadIdx = uint3{s->tid, 0, 0};
-  blockIdx = uint3{s->block, 0, 0};
-  s->fn(s->arg);
-  return nullptr;
-}
-void run_block(int n_threads, unsigned block, unsigned grid, void (*fn)(void*), void* arg) {
-  blockDim = uint3{(unsigned)n_threads, 1, 1};
-  gridDim = uint3{grid, 1, 1};
-  g_block.n_threads = n_threads;
-  pthread_barrier_init(&g_block.bar, nullptr, n_threads);
-  for (int w = 0; w < n_threads / 32; w++) pthread_barrier_init(&g_block.warps[w].bar, nullptr, 32);
-  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * n_threads);
-  Start* st = (Start*)malloc(sizeof(Start) * n_threads);
-  pthread_attr_t attr;
-  pthread_attr_init(&attr);
-  pthread_attr_setstacksize(&attr, 256 * 1024);
-  for (int t = 0; t < n_threads; t++) {
-    st[t] = Start{fn, arg, (unsigned)t, block};
-    if (pthread_create(&th[t], &attr, entry, &st[t]) != 0) { fprintf(stderr, "pthread_create failed\n"); abort(); }
-  }
-  for (int t = 0; t < n_threads; t++) pthread_join(th[t], nullptr);
-  pthread_attr_destroy(&attr);
-  pthread_barrier_destroy(&g_block.bar);
-  for (int w = 0; w < n_threads / 32; w++) pthread_barrier_destroy(&g_block.warps[w].bar);
-  free(th); free(st);
-}
-}  // namespace simt
-
-// what common.cuh declares and capi.cu defines in the real library
-void b2t_set_error(const char*, ...) {}
-void b2t_count_launches(int) {}
-int b2t_coop_limit() { return 0; }
-int b2t_trace_limit() { return 0; }
-bool b2t_claim_window_built() { return true; }
-float b2t_claim_window() { return 0.0f; }
+#include "emu_include/simt_impl.h"   // emu_include/ comes first on the include path: <cuda_runtime.h> is the emulation
 
 #include "../../kimimaro_b200/csrc/trace.cu"
 

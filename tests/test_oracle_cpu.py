@@ -456,7 +456,7 @@ def test_fix_avocados_reference_known_answer():
   assert remapping == {1: 1, 2: 3, 3: 7, 4: 6} and n == 4
 
 
-def _avocado_host_vs_oracle(labels, thr):
+def _avocado_host_vs_oracle(labels, thr, fill_fn=None):
   """kimimaro_b200.intake.engage_avocado_protection on CPU tensors -- kernels replaced by the oracle's fill and EDT, the
   statistics by numpy -- against the oracle's restatement: same partition, same component -> original label map."""
   import scipy.ndimage as ndi
@@ -473,11 +473,12 @@ def _avocado_host_vs_oracle(labels, thr):
     lut[k] = v
   ref_img = lut[ref_cc]
 
-  def fill_fn(mask, cshape):
+  def oracle_fill(mask, cshape):
     m = np.asfortranarray(mask.numpy().reshape(cshape, order="F").astype(bool))
     _, k = oracle.fill_voids(m)
     mask.copy_(torch.from_numpy(m.reshape(-1, order="F").astype(np.uint8)))
     return k
+  fill_fn = fill_fn or oracle_fill
 
   def stats_fn(d_cc, d_dbf, shp, n_cc):
     a = d_cc.numpy().reshape(shp, order="F")
