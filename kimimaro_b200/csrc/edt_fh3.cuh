@@ -74,6 +74,10 @@ FH3_HD uint32_t brev32(uint32_t x) {
 // An entry is (v, h, z): row of the parabola's apex (absolute, kept as a float: rows < 2^24 are exact and the
 // hot loop then needs no int->float conversion), its height, and the left end of its reign (run-relative).
 
+// query lookahead of column_range (QP > 1); empty for the original loop so that it compiles to the original code
+template <int QP> struct Lookahead { float v[QP], h[QP], z[QP]; };
+template <> struct Lookahead<1> {};
+
 // intersection of the parabola rooted at run-relative row i (height fi) with the one at v (height h):
 // (f[i] - f[v] + (i-v) w^2 (i+v)) / (2 (i-v) w^2), oracle.c:137-139
 template <typename Ctx>
@@ -215,9 +219,11 @@ FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, in
       int qa = todo ? -1 : kBig, qb = qa;        // rows [qa, qb) of the run being written; qb <= i: fetch the next
       int kq = 0, kend = 0;
       float qaf = 0.0f, qbf = 0.0f, cv = 0.0f, ch = 0.0f, nz = kInf;
-      float pv[QP], ph[QP], pz[QP];              // QP > 1: entries kq+1 .. kq+QP (left end +inf past the run's last one)
+      Lookahead<QP> la;                          // QP > 1: entries kq+1 .. kq+QP (left end +inf past the run's last one)
+      if constexpr (QP > 1) {
 #pragma unroll
-      for (int j = 0; j < QP; j++) { pv[j] = 0.0f; ph[j] = 0.0f; pz[j] = kInf; }
+        for (int j = 0; j < QP; j++) { la.v[j] = 0.0f; la.h[j] = 0.0f; la.z[j] = kInf; }
+      }
       bool bl = false, br = false;
       float* fw = fout + lo * cstride;
       float iqf = (float)lo;
@@ -232,18 +238,18 @@ FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, in
             qbf = (float)qb;
             kq = kn; kend = kn + (int)(pk & 0x7ffu); kn = kend;
             cv = 0.0f; ch = FH3_LD_H(kq);
-            if (QP == 1) {
+            if constexpr (QP == 1) {
               nz = (kq + 1 < kend) ? FH3_LD_Z(kq + 1) : kInf;
             } else {
 #pragma unroll
               for (int j = 0; j < QP; j++) {
                 const int e = kq + 1 + j;
                 const bool in = e < kend;
-                pz[j] = in ? FH3_LD_Z(e) : kInf;
-                pv[j] = in ? FH3_LD_V(e) : 0.0f;
-                ph[j] = in ? FH3_LD_H(e) : 0.0f;
+                la.z[j] = in ? FH3_LD_Z(e) : kInf;
+                la.v[j] = in ? FH3_LD_V(e) : 0.0f;
+                la.h[j] = in ? FH3_LD_H(e) : 0.0f;
               }
-              nz = pz[0];
+              nz = la.z[0];
             }
             bl = (qa > 0) || black_border;
             br = (qb < n) || black_border;
@@ -255,21 +261,21 @@ FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, in
           const float ir = iqf - qaf;
           while (nz < ir) {
             kq++;
-            if (QP == 1) {
+            if constexpr (QP == 1) {
               cv = FH3_LD_V(kq) - qaf;
               ch = FH3_LD_H(kq);
               nz = (kq + 1 < kend) ? FH3_LD_Z(kq + 1) : kInf;
             } else {
-              cv = pv[0] - qaf;
-              ch = ph[0];
+              cv = la.v[0] - qaf;
+              ch = la.h[0];
 #pragma unroll
-              for (int j = 0; j + 1 < QP; j++) { pv[j] = pv[j + 1]; ph[j] = ph[j + 1]; pz[j] = pz[j + 1]; }
+              for (int j = 0; j + 1 < QP; j++) { la.v[j] = la.v[j + 1]; la.h[j] = la.h[j + 1]; la.z[j] = la.z[j + 1]; }
               const int e = kq + QP;
               const bool in = e < kend;
-              pz[QP - 1] = in ? FH3_LD_Z(e) : kInf;
-              pv[QP - 1] = in ? FH3_LD_V(e) : 0.0f;
-              ph[QP - 1] = in ? FH3_LD_H(e) : 0.0f;
-              nz = pz[0];
+              la.z[QP - 1] = in ? FH3_LD_Z(e) : kInf;
+              la.v[QP - 1] = in ? FH3_LD_V(e) : 0.0f;
+              la.h[QP - 1] = in ? FH3_LD_H(e) : 0.0f;
+              nz = la.z[0];
             }
           }
           const float di = cx.sub(ir, cv);
