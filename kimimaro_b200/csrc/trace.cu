@@ -85,7 +85,9 @@ struct Params {
   int nbuckets;
   int n_desc;
   int fix_branching;             // 0: paths come from the parental field already in A.dist (trace.py:154-158, 244)
+#if B2T_WITH_CLAIM_WINDOW
   float claim_window;            // 0: hop-synchronous invalidation rounds; > 0: key-ordered rounds of this width (invalidate_window)
+#endif
 };
 
 struct Pools {
@@ -871,7 +873,12 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
   P.out_status = d_out_status; P.out_stats = d_out_stats; P.work_counter = d_work_counter;
   // b2t_set_claim_window: width of the key-ordered invalidation rounds in units of the smallest voxel edge (0 = hop rounds)
   const float wmin = wx < wy ? (wx < wz ? wx : wz) : (wy < wz ? wy : wz);
+#if B2T_WITH_CLAIM_WINDOW
   Params prm{scale, konst, soma_scale, soma_const, nbuckets, n_desc, fix_branching ? 1 : 0, b2t_claim_window() * wmin};
+#else
+  (void)wmin;
+  Params prm{scale, konst, soma_scale, soma_const, nbuckets, n_desc, fix_branching ? 1 : 0};
+#endif
   B2T_CUDA_TRY(cudaMemsetAsync(d_work_counter, 0, sizeof(uint32_t), st));
   int dev = 0, sms = 0, per_sm = 0;
   B2T_CUDA_TRY(cudaGetDevice(&dev));
