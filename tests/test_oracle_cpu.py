@@ -559,3 +559,17 @@ def test_synapses_to_targets_matches_scipy_formulation():
   assert got == expect and len(got) >= 3
   for pt in got:
     assert labels[pt] in (1, 2)
+
+
+def test_fill_all_holes_reference_known_answer():
+  """automated_test.py:458-476 on the oracle's fill_all_holes."""
+  from oracle import teasar
+  rng = np.random.default_rng(1)
+  labels = np.zeros((64, 32, 32), dtype=np.uint32, order="F")
+  labels[0:32] = 1
+  labels[32:64] = 8
+  labels[1:31, 1:31, 1:31] = rng.integers(1, 8, size=(30, 30, 30))
+  labels[33:63, 1:31, 1:31] = rng.integers(8, 11, size=(30, 30, 30))
+  assert set(int(v) for v in np.unique(labels)) == set(range(1, 11))
+  out = teasar.fill_all_holes(labels, 10)
+  assert set(int(v) for v in np.unique(out)) == {1, 8}

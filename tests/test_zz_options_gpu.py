@@ -44,3 +44,77 @@ def test_fix_avocados(gpu):
   both = dict(kw, fill_holes=True)
   res2, ref2 = _both(gpu, labels, **both)
   _compare(res2, ref2)
+
+
+# ---- the reference's own known-answer tests that the options above unlock, and a few it has besides ----
+def test_square_with_fill_holes(gpu):
+  """automated_test.py:49-87 with fill_holes=True (the reference parametrises test_square over it)."""
+  import kimimaro_b200 as kimimaro
+  for corners in (((-1, 0), (0, -1)), ((0, 0), (-1, -1))):
+    labels = np.ones((1000, 1000), dtype=np.uint8)
+    for c in corners:
+      labels[c] = 0
+    skels = kimimaro.skeletonize(labels, teasar_params=kimimaro.DEFAULT_TEASAR_PARAMS, fix_borders=False, fill_holes=True,
+                                 progress=False)
+    assert len(skels) == 1
+    skel = skels[1]
+    assert skel.vertices.shape[0] == 1000 and skel.edges.shape[0] == 999
+    assert abs(skel.cable_length() - 999 * np.sqrt(2)) < 0.001
+
+
+def test_fill_all_holes_reference_known_answer(gpu):
+  """automated_test.py:458-476: two solid halves full of foreign-label noise; afterwards only the halves remain."""
+  import torch
+  from kimimaro_b200 import engine, intake, ops
+  rng = np.random.default_rng(1)
+  labels = np.zeros((64, 32, 32), dtype=np.uint32, order="F")
+  labels[0:32] = 1
+  labels[32:64] = 8
+  labels[1:31, 1:31, 1:31] = rng.integers(1, 8, size=(30, 30, 30))
+  labels[33:63, 1:31, 1:31] = rng.integers(8, 11, size=(30, 30, 30))
+  assert set(np.unique(labels)) == set(range(1, 11))
+  d = ops.to_device_f(labels, gpu).view(torch.int32)
+  V = labels.size
+  count, bbox, _, _ = engine.label_stats(d, torch.zeros(V, dtype=torch.float32, device=d.device), labels.shape, 10)
+  intake.fill_all_holes(d, labels.shape, 10, count.cpu().numpy(), bbox.cpu().numpy().reshape(-1, 6))
+  assert set(torch.unique(d).cpu().tolist()) == {1, 8}
+
+
+def test_binary_image(gpu):
+  """automated_test.py:39-46."""
+  import kimimaro_b200 as kimimaro
+  labels = np.ones((256, 256, 3), dtype=bool)
+  labels[-1, 0] = 0
+  labels[0, -1] = 0
+  assert len(kimimaro.skeletonize(labels, fix_borders=False, progress=False)) == 1
+
+
+def test_extra_targets_grow_the_skeleton(gpu):
+  """automated_test.py:201-232."""
+  import kimimaro_b200 as kimimaro
+  labels = np.zeros((256, 256, 1), dtype=np.uint8)
+  labels[64:196, 64:196, :] = 128
+  tp = {"const": 250, "scale": 10, "pdrf_exponent": 4, "pdrf_scale": 100000}
+
+  def run(**kw):
+    return kimimaro.skeletonize(labels, teasar_params=tp, anisotropy=(1, 1, 1), dust_threshold=1000, progress=False,
+                                fix_branching=True, fix_borders=True, **kw)[128]
+  skel1 = run()
+  skel2 = run(extra_targets_after=[(65, 65, 0)])
+  skel3 = run(extra_targets_before=[(65, 65, 0)])
+  assert skel1.vertices.size < skel2.vertices.size
+  assert skel3.vertices.size < skel2.vertices.size
+
+
+def test_parallel_argument_is_accepted(gpu):
+  """automated_test.py:234-259: four quadrants, parallel=2 (here: ignored, one GPU traces all labels)."""
+  import kimimaro_b200 as kimimaro
+  labels = np.zeros((256, 256, 128), dtype=np.uint8)
+  labels[0:128, 0:128, :] = 1
+  labels[0:128, 128:256, :] = 2
+  labels[128:256, 0:128, :] = 3
+  labels[128:256, 128:256, :] = 4
+  tp = {"const": 250, "scale": 10, "pdrf_exponent": 4, "pdrf_scale": 100000}
+  skels = kimimaro.skeletonize(labels, teasar_params=tp, anisotropy=(1, 1, 1), dust_threshold=1000, progress=False,
+                               parallel=2)
+  assert len(skels) == 4
