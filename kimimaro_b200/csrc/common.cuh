@@ -32,6 +32,18 @@ float b2t_claim_window();  // width of key-ordered invalidation rounds in smalle
     }                                          \
   } while (0)
 
+// Kernel launches of preamble.cu and field.cu go through macros so that the CPU suite can compile those files with g++
+// against the SIMT emulation of tests/host/emu_include/cuda_runtime.h (B2T_HOST_EMU) and run the very kernels on host
+// arrays against the oracle.  There B2T_LAUNCH (kernels without block-level synchronisation) is a loop over blocks and
+// threads, B2T_LAUNCH_SYNC (kernels that use __syncthreads or warp intrinsics) runs every block on OS threads.
+#ifdef B2T_HOST_EMU
+#define B2T_LAUNCH(kernel_, grid_, block_, stream_) simt::seq_launch((grid_), (block_), [](auto... a_) { kernel_(a_...); })
+#define B2T_LAUNCH_SYNC(kernel_, grid_, block_, stream_) simt::block_launch((grid_), (block_), [](auto... a_) { kernel_(a_...); })
+#else
+#define B2T_LAUNCH(kernel_, grid_, block_, stream_) kernel_<<<(grid_), (block_), 0, (stream_)>>>
+#define B2T_LAUNCH_SYNC(kernel_, grid_, block_, stream_) kernel_<<<(grid_), (block_), 0, (stream_)>>>
+#endif
+
 // 26-neighbourhood in the enumeration order the reference uses
 // (ext/skeletontricks/dijkstra_invalidation.hpp:60-124): -x,+x,-y,+y,-z,+z, xy, yz, xz diagonals, corners.
 __device__ __constant__ static const int8_t kDX[26] = {-1, 1, 0, 0, 0, 0, -1, -1, 1, 1, 0, 0, 0, 0, -1, -1, 1, 1, -1, 1, -1, -1, 1, 1, -1, 1};

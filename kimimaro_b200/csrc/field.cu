@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const uint32_t* __
   if (t == 1023) out[n] = s_part[1023];
 }
 
+#ifndef B2T_HOST_EMU
 int coop_grid(const void* kernel, int threads, size_t smem, int* blocks_out) {
   int dev = 0, sms = 0, per_sm = 0;
   B2T_CUDA_TRY(cudaGetDevice(&dev));
@@ -368,6 +369,7 @@ int coop_grid(const void* kernel, int threads, size_t smem, int* blocks_out) {
   *blocks_out = sms * per_sm;
   return B2T_OK;
 }
+#endif
 
 void fill_weights(float wx, float wy, float wz, float* w) {
   // float32 expressions of ext/skeletontricks/dijkstra_invalidation.hpp:45-52 (_s, _c)
@@ -402,11 +404,11 @@ B2T_EXPORT int b2t_label_stats(const uint32_t* d_cc, const float* d_dbf, int64_t
   B2T_CUDA_TRY(cudaMemsetAsync(d_count, 0, n1 * sizeof(uint32_t), st));
   B2T_CUDA_TRY(cudaMemsetAsync(d_first, 0xff, n1 * sizeof(uint32_t), st));
   if (d_dbfmax) B2T_CUDA_TRY(cudaMemsetAsync(d_dbfmax, 0, n1 * sizeof(float), st));
-  bbox_init_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(d_bbox, (uint32_t)n1);
+  B2T_LAUNCH(bbox_init_kernel, (unsigned)((n1 + 255) / 256), 256, st)(d_bbox, (uint32_t)n1);
   const uint32_t nseg_x = (uint32_t)((sx + kSeg - 1) / kSeg);
   const uint64_t nsegs = (uint64_t)nseg_x * sy * sz;
   const unsigned blocks = (unsigned)((nsegs + 255) / 256);
-  label_stats_kernel<<<blocks, 256, 0, st>>>(d_cc, d_dbf, d, nseg_x, nsegs, n_labels, d_count, d_bbox,
+  B2T_LAUNCH(label_stats_kernel, blocks, 256, st)(d_cc, d_dbf, d, nseg_x, nsegs, n_labels, d_count, d_bbox,
                                              reinterpret_cast<uint32_t*>(d_dbfmax), d_first);
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(2);
@@ -433,19 +435,25 @@ B2T_EXPORT int b2t_edf_multi(const uint32_t* d_cc, int64_t sx, int64_t sy, int64
     B2T_REQUIRE(n_sources == 1, "free_space_radius needs exactly one source");
     B2T_REQUIRE(d_node_weights == nullptr, "free_space_radius and node weights are exclusive");
     const uint32_t zero = 0;
-    edf_seed_kernel<<<1, 32, 0, st>>>(p, &zero, 0);  // clears ctrl
-    edf_freespace_seed_kernel<<<256, 256, 0, st>>>(p, h_free_space_source, free_space_radius, wx, wy, wz);
+    B2T_LAUNCH(edf_seed_kernel, 1, 32, st)(p, &zero, 0);  // clears ctrl
+    B2T_LAUNCH(edf_freespace_seed_kernel, 256, 256, st)(p, h_free_space_source, free_space_radius, wx, wy, wz);
   } else {
     if (n_sources == 0) return B2T_OK;
-    edf_seed_kernel<<<(n_sources + 255) / 256, 256, 0, st>>>(p, d_sources, n_sources);
+    B2T_LAUNCH(edf_seed_kernel, (n_sources + 255) / 256, 256, st)(p, d_sources, n_sources);
   }
   B2T_CUDA_TRY(cudaGetLastError());
+#ifdef B2T_HOST_EMU   // one block of 1024 emulated threads: the grid barrier is the block barrier
+  if (frozen) simt::block_launch(1, 1024, [](auto a_) { edf_multi_kernel<true, false>(a_); })(p);
+  else if (d_node_weights) simt::block_launch(1, 1024, [](auto a_) { edf_multi_kernel<false, true>(a_); })(p);
+  else simt::block_launch(1, 1024, [](auto a_) { edf_multi_kernel<false, false>(a_); })(p);
+#else
   const void* kern = frozen ? (const void*)edf_multi_kernel<true, false>
                             : (d_node_weights ? (const void*)edf_multi_kernel<false, true> : (const void*)edf_multi_kernel<false, false>);
   int blocks = 0;
   if (int rc = coop_grid(kern, 1024, 0, &blocks)) return rc;   // few large blocks: the grid barrier costs per block
   void* args[] = {&p};
   B2T_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(1024), args, 0, st));
+#endif
   b2t_count_launches(frozen ? 3 : 2);
   return B2T_OK;
 }
@@ -458,7 +466,7 @@ B2T_EXPORT int b2t_field_argmax(const uint32_t* d_cc, const float* d_dist, int64
   B2T_CUDA_TRY(cudaMemsetAsync(d_best, 0, ((size_t)n_labels + 1) * sizeof(uint64_t), st));
   const uint32_t nseg_x = (uint32_t)((sx + kSeg - 1) / kSeg);
   const uint64_t nsegs = (uint64_t)nseg_x * sy * sz;
-  field_argmax_kernel<<<(unsigned)((nsegs + 255) / 256), 256, 0, st>>>(d_cc, d_dist, d, nseg_x, nsegs, n_labels,
+  B2T_LAUNCH(field_argmax_kernel, (unsigned)((nsegs + 255) / 256), 256, st)(d_cc, d_dist, d, nseg_x, nsegs, n_labels,
                                                                       reinterpret_cast<unsigned long long*>(d_best));
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(1);
@@ -498,12 +506,12 @@ B2T_EXPORT int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, fl
   p.V = V;
   const uint64_t want = (V + 255) / 256;
   const unsigned blocks = (unsigned)(want < 148ull * 32 ? want : 148ull * 32);
-  pdrf_kernel<<<blocks, 256, 0, st>>>(p);
-  exclusive_scan_kernel<<<1, 1024, 0, st>>>(d_hist, d_cursor, ntab);
+  B2T_LAUNCH(pdrf_kernel, blocks, 256, st)(p);
+  B2T_LAUNCH_SYNC(exclusive_scan_kernel, 1, 1024, st)(d_hist, d_cursor, ntab);
   ScatterParams s;
   s.cc = d_cc; s.dist = d_dist; s.inv_maxdaf = d_inv_maxdaf; s.active = d_active; s.cursor = d_cursor;
   s.keys = reinterpret_cast<unsigned long long*>(d_keys); s.n_labels = n_labels; s.nbuckets = nbuckets; s.V = V;
-  bucket_scatter_kernel<<<blocks, 256, 0, st>>>(s);
+  B2T_LAUNCH(bucket_scatter_kernel, blocks, 256, st)(s);
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(3);
   return B2T_OK;
@@ -681,12 +689,17 @@ B2T_EXPORT int b2t_invalidate_ball(const uint32_t* d_cc, const float* d_dbf, uin
   p.n_seeds = n_seeds; p.fv = d_fv; p.fs = d_fs; p.ctrl = d_ctrl; p.cap = cap;
   p.d = Dims{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
   p.wx = wx; p.wy = wy; p.wz = wz; p.scale = scale; p.konst = konst;
-  ball_seed_kernel<<<(n_seeds + 255) / 256, 256, 0, st>>>(p);
+  B2T_LAUNCH(ball_seed_kernel, (n_seeds + 255) / 256, 256, st)(p);
+#ifdef B2T_HOST_EMU
+  if (n_seeds == 1) simt::block_launch(1, 1024, [](auto a_) { ball_flood_single_kernel(a_); })(p);
+  else simt::block_launch(1, 1024, [](auto a_) { ball_flood_kernel(a_); })(p);
+#else
   int blocks = 0;
   const void* kern = (n_seeds == 1) ? (const void*)ball_flood_single_kernel : (const void*)ball_flood_kernel;
   if (int rc = coop_grid(kern, 1024, 0, &blocks)) return rc;
   void* args[] = {&p};
   B2T_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(1024), args, 0, st));
+#endif
   b2t_count_launches(2);
   return B2T_OK;
 }

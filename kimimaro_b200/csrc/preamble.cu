@@ -9,15 +9,6 @@
 //                and fetch the radii (DBF at the vertex, trace.py:186-187) in the same pass.
 #include "common.cuh"
 
-// Kernel launches go through one macro so that the CPU suite can compile this file with g++ against the SIMT emulation of
-// tests/host/emu_include/cuda_runtime.h (B2T_HOST_EMU: the kernels here have no block-level synchronisation, so a
-// launch is a loop over blocks and threads) and run the very kernels against the oracle.
-#ifdef B2T_HOST_EMU
-#define B2T_LAUNCH(kernel_, grid_, block_, stream_) simt::seq_launch((grid_), (block_), [](auto... a_) { kernel_(a_...); })
-#else
-#define B2T_LAUNCH(kernel_, grid_, block_, stream_) kernel_<<<(grid_), (block_), 0, (stream_)>>>
-#endif
-
 namespace {
 
 struct Dims {

@@ -147,6 +147,10 @@ static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline unsigned long long min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
 static inline unsigned long long max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+static inline unsigned long min(unsigned long a, unsigned long b) { return a < b ? a : b; }
+static inline unsigned long max(unsigned long a, unsigned long b) { return a > b ? a : b; }
+static inline float min(float a, float b) { return fminf(a, b); }
+static inline float max(float a, float b) { return fmaxf(a, b); }
 static inline long long min(long long a, long long b) { return a < b ? a : b; }
 static inline long long max(long long a, long long b) { return a > b ? a : b; }
 
@@ -171,6 +175,18 @@ template <typename F> struct SeqLaunch {
   }
 };
 template <typename F> SeqLaunch<F> seq_launch(unsigned long long g, unsigned b, F f) { return SeqLaunch<F>{(unsigned)g, b, f}; }
+
+// kernels WITH block-level synchronisation: every block, one after the other, on b OS threads
+template <typename F> struct BlockLaunch {
+  unsigned g, b;
+  F f;
+  template <typename... A> void operator()(A... a) const {
+    auto call = [&]() { f(a...); };
+    using C = decltype(call);
+    for (unsigned bx = 0; bx < g; bx++) run_block((int)b, bx, g, [](void* p) { (*(C*)p)(); }, &call);
+  }
+};
+template <typename F> BlockLaunch<F> block_launch(unsigned long long g, unsigned b, F f) { return BlockLaunch<F>{(unsigned)g, b, f}; }
 }  // namespace simt
 
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
