@@ -45,4 +45,5 @@ void b2t_count_launches(int) {}
 int b2t_coop_limit() { return 0; }
 int b2t_trace_limit() { return 0; }
 bool b2t_claim_window_built() { return true; }
-float b2t_claim_window() { return 0.0f; }
+float g_emu_claim_window = 0.0f;
+float b2t_claim_window() { return g_emu_claim_window; }

@@ -3,6 +3,10 @@
 // SIMT emulation; the exported entry points take HOST pointers here.  The cooperative kernels run as one block of 1024
 // emulated threads.  tests/test_field_emu_cpu.py runs them against the oracle.
 #define B2T_HOST_EMU 1
+#ifdef B2T_EMU_COMBINED
+#include <cuda_runtime.h>
+#else
 #include "emu_include/simt_impl.h"
+#endif
 
 #include "../../kimimaro_b200/csrc/field.cu"

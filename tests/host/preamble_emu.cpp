@@ -4,6 +4,10 @@
 // points (b2t_ccl26_roots, b2t_fill_voids, ...) take HOST pointers here.  tests/test_preamble_emu_cpu.py runs them
 // against the oracle.
 #define B2T_HOST_EMU 1
+#ifdef B2T_EMU_COMBINED
+#include <cuda_runtime.h>
+#else
 #include "emu_include/simt_impl.h"
+#endif
 
 #include "../../kimimaro_b200/csrc/preamble.cu"

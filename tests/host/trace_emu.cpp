@@ -4,7 +4,11 @@
 // source text the GPU runs and compare it with the oracle (orc_invalidate_rounds / orc_invalidate_window).
 #define B2T_HOST_EMU 1
 #define B2T_WITH_CLAIM_WINDOW 1
-#include "emu_include/simt_impl.h"   // emu_include/ comes first on the include path: <cuda_runtime.h> is the emulation
+#ifdef B2T_EMU_COMBINED
+#include <cuda_runtime.h>
+#else
+#include "emu_include/simt_impl.h"
+#endif   // emu_include/ comes first on the include path: <cuda_runtime.h> is the emulation
 
 #include "../../kimimaro_b200/csrc/trace.cu"
 
@@ -76,3 +80,20 @@ extern "C" int emu_trace_batch(const uint32_t* cc, const float* dbf, float* pdrf
   simt::run_block(kThreads, 0, 1, kernel_thread, &k);
   return 0;
 }
+
+#ifdef B2T_EMU_COMBINED
+// b2t_trace_batch of include/b2t.h on host arrays (the real launcher is not compiled under B2T_HOST_EMU)
+extern "C" __attribute__((visibility("default"))) int b2t_trace_batch(
+    const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim, uint32_t* d_stamp, int64_t sx,
+    int64_t sy, int64_t sz, float wx, float wy, float wz, const void* d_desc, int n_desc, float scale, float konst,
+    float soma_scale, float soma_const, int fix_branching, int nbuckets, const uint64_t* d_keys, const uint32_t* d_hist,
+    const uint32_t* d_cursor, uint32_t* d_scratch, uint32_t* d_paths, const uint32_t* d_targets, uint32_t* d_out_len,
+    uint32_t* d_out_npaths, int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter, void*) {
+  if (n_desc <= 0) return 0;
+  const float wmin = wx < wy ? (wx < wz ? wx : wz) : (wy < wz ? wy : wz);
+  return emu_trace_batch(d_cc, d_dbf, d_pdrf, d_dist, (unsigned long long*)d_claim, d_stamp, (int)sx, (int)sy, (int)sz, wx, wy,
+                         wz, d_desc, n_desc, scale, konst, soma_scale, soma_const, fix_branching, nbuckets,
+                         (const unsigned long long*)d_keys, d_hist, d_cursor, d_scratch, d_paths, d_targets, d_out_len,
+                         d_out_npaths, d_out_status, d_out_stats, d_work_counter, b2t_claim_window() * wmin);
+}
+#endif
