@@ -29,6 +29,12 @@ DEFAULT_TEASAR_PARAMS = {          # intake.py:47-56
   "soma_invalidation_scale": 2,
 }
 
+# The claim order of roll_invalidation_ball_inside_component that the oracle runs when none is asked for: the ENGINE's
+# ("rounds": hop-synchronous; "window:1": ordered by the reference's heap key in windows of one voxel, the order the
+# claim_window build of the library runs).  "heap" is the reference's own order (== its compiled extension) and "seq" the
+# ordered process with canonical ties; see DESIGN.md 4.  tests/golden holds one set of vectors per engine order.
+DEFAULT_INVALIDATION_MODE = "rounds"
+
 
 class DimensionError(Exception):
   pass
@@ -315,9 +321,10 @@ def trace(labels, DBF, scale=10, const=10, anisotropy=(1, 1, 1),
           soma_detection_threshold=1100, soma_acceptance_threshold=4000,
           pdrf_scale=5000, pdrf_exponent=16, soma_invalidation_scale=0.5, soma_invalidation_const=0,
           fix_branching=True, manual_targets_before=None, manual_targets_after=None, root=None,
-          max_paths=None, voxel_graph=None, invalidation_mode="rounds", return_paths=False):
+          max_paths=None, voxel_graph=None, invalidation_mode=None, return_paths=False):
   """trace.py:36-194."""
   assert voxel_graph is None, "voxel_graph is out of scope (SURVEY 8f N4)"
+  invalidation_mode = invalidation_mode or DEFAULT_INVALIDATION_MODE
   manual_targets_before = [] if manual_targets_before is None else manual_targets_before
   manual_targets_after = [] if manual_targets_after is None else manual_targets_after
   dbf_max = np.max(DBF)
@@ -639,10 +646,11 @@ def fill_all_holes(cc_labels, n_cc, return_fill_count=False):
 
 def skeletonize(all_labels, teasar_params=DEFAULT_TEASAR_PARAMS, anisotropy=(1, 1, 1), object_ids=None,
                 dust_threshold=1000, fix_branching=True, fix_borders=True,
-                extra_targets_before=(), extra_targets_after=(), invalidation_mode="rounds",
+                extra_targets_before=(), extra_targets_after=(), invalidation_mode=None,
                 only_cc=None, timings=None, parallel=1, fill_holes=False, fix_avocados=False):
   """intake.py:58-221 + 434-517 (parallel==1 path).  Returns {orig id: skeleton dict}."""
   import time
+  invalidation_mode = invalidation_mode or DEFAULT_INVALIDATION_MODE
   t0 = time.time()
   anisotropy = np.array(anisotropy, dtype=np.float32)
   all_labels = format_labels(all_labels)

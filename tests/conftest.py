@@ -37,3 +37,12 @@ def gpu():
   from kimimaro_b200 import _lib
   _lib.require_device()
   return torch.device("cuda:0")
+
+
+def golden_name(stem, ext):
+  """tests/golden/<stem>[_<mode>]<ext> for the claim order the oracle (and so the engine under test) runs by default."""
+  import os
+  from oracle import teasar
+  mode = teasar.DEFAULT_INVALIDATION_MODE
+  suffix = "" if mode == "rounds" else "_" + mode.replace(":", "").replace(".", "p")
+  return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", stem + suffix + ext)

@@ -231,10 +231,14 @@ def test_reference_fix_borders(orc):
 
 
 # ---- golden fixtures (tests/golden, generated by tests/golden/make_golden.py) ----
-def test_golden_fixtures(orc):
+@pytest.mark.parametrize("mode", ["rounds", "window:1"])
+def test_golden_fixtures(orc, mode, monkeypatch):
+  """One set of vectors per claim order the engine can run; the one oracle.teasar.DEFAULT_INVALIDATION_MODE names is the
+  set the CUDA tests use (tests/conftest.py: golden_name)."""
   from oracle import teasar
   from tests.synth import sphere, synthetic_tubes
-  g = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+  monkeypatch.setattr(teasar, "DEFAULT_INVALIDATION_MODE", mode)
+  g = np.load(__import__("tests.conftest", fromlist=["golden_name"]).golden_name("golden_v1", ".npz"))
   cases = {"sphere": (sphere(64, 24), {}),
            "tubes": (synthetic_tubes((96, 96, 64), 12, seed=1), {"anisotropy": (16, 16, 40), "dust_threshold": 100})}
   for name, (lab, kw) in cases.items():

@@ -116,3 +116,48 @@ def test_fill_holes_and_fix_avocados(product):
   _compare(product.skeletonize(labels, progress=False, **kw), ref)
   kw["fill_holes"] = True
   _compare(product.skeletonize(labels, progress=False, **kw), teasar.skeletonize(labels, **kw))
+
+
+def test_key_ordered_claim_end_to_end(product):
+  """The claim_window variant of the library (trace.cu: invalidate_window, off in the shipped build) through the whole
+  product against the oracle's mode 'window:1' -- and against the hop-synchronous default to see that it matters."""
+  from kimimaro_b200 import _lib
+  from oracle import teasar
+  from tests.synth import synthetic_tubes
+  labels = synthetic_tubes((56, 48, 40), 6, seed=9)
+  kw = dict(anisotropy=(16, 16, 40), dust_threshold=100, teasar_params=dict(product.DEFAULT_TEASAR_PARAMS, scale=1.5, const=30))
+  try:
+    _lib.check(_lib.lib().b2t_set_claim_window(_lib.c_f32(1.0)))
+    res = product.skeletonize(labels, progress=False, **kw)
+  finally:
+    _lib.check(_lib.lib().b2t_set_claim_window(_lib.c_f32(0.0)))
+  _compare(res, teasar.skeletonize(labels, invalidation_mode="window:1", **kw))
+  _compare(product.skeletonize(labels, progress=False, **kw), teasar.skeletonize(labels, invalidation_mode="rounds", **kw))
+
+
+def test_more_of_the_api(product):
+  """Soma branch (detected and accepted: fill, re-EDT, free-space DAF, ball invalidation, cull), extra targets,
+  object_ids, fix_branching=False, max_paths, a 2-D image, uint64 labels."""
+  from oracle import teasar
+  from tests.synth import synthetic_tubes
+  ball = np.zeros((44, 44, 30), np.uint32, order="F")
+  x, y, z = np.ogrid[:44, :44, :30]
+  ball[(x - 22) ** 2 + (y - 22) ** 2 + ((z - 15) * 2.5) ** 2 <= 15 ** 2] = 3
+  ball[20:24, 20:24, :] = 3                                           # a process through the soma
+  ball[21:23, 21:23, 14:16] = 0                                       # and a void in its middle
+  tp = dict(product.DEFAULT_TEASAR_PARAMS, soma_detection_threshold=100, soma_acceptance_threshold=180)
+  kw = dict(anisotropy=(16, 16, 40), dust_threshold=100, teasar_params=tp)
+  _compare(product.skeletonize(ball, progress=False, **kw), teasar.skeletonize(ball, **kw))
+  tubes = synthetic_tubes((56, 48, 32), 5, seed=4)
+  ids = [int(v) for v in np.unique(tubes) if v][:3]
+  pt = tuple(int(v) for v in np.argwhere(tubes == ids[0])[7])
+  for extra in (dict(object_ids=ids[:2]), dict(extra_targets_after=[pt]), dict(extra_targets_before=[pt]),
+                dict(fix_branching=False), dict(fix_borders=False), dict(teasar_params=dict(product.DEFAULT_TEASAR_PARAMS, max_paths=2))):
+    kw = dict(dict(anisotropy=(16, 16, 40), dust_threshold=100), **extra)
+    _compare(product.skeletonize(tubes, progress=False, **kw), teasar.skeletonize(tubes, **kw))
+  kw = dict(anisotropy=(16, 16, 40), dust_threshold=100)
+  _compare(product.skeletonize(tubes.astype(np.uint64) * 10 ** 10, progress=False, **kw),
+           {k * 10 ** 10: v for k, v in teasar.skeletonize(tubes, **kw).items()})
+  plane = np.asfortranarray(tubes[:, :, 16])
+  kw = dict(anisotropy=(16, 16), dust_threshold=20) if False else dict(dust_threshold=20)
+  _compare(product.skeletonize(plane, progress=False, **kw), teasar.skeletonize(plane, **kw))

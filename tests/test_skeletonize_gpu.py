@@ -146,7 +146,7 @@ def test_golden_fixtures_cuda(gpu):
   import os
   import kimimaro_b200
   from tests.synth import sphere, synthetic_tubes
-  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
+  g = np.load(__import__("tests.conftest", fromlist=["golden_name"]).golden_name("golden_v1", ".npz"))
   cases = {"sphere": (sphere(64, 24), {}),
            "tubes": (synthetic_tubes((96, 96, 64), 12, seed=1), {"anisotropy": (16, 16, 40), "dust_threshold": 100})}
   for name, (lab, kw) in cases.items():
@@ -238,7 +238,7 @@ def test_full_size_512_against_oracle_digest(gpu):
   import hashlib, json, os
   import kimimaro_b200
   from bench import make_volume, ANISOTROPY
-  gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synth512_oracle_digest.json")))
+  gold = json.load(open(__import__("tests.conftest", fromlist=["golden_name"]).golden_name("synth512_oracle_digest", ".json")))
   vol = make_volume(512)
   a = kimimaro_b200.skeletonize(vol, anisotropy=ANISOTROPY, progress=False)
   b = kimimaro_b200.skeletonize(vol, anisotropy=ANISOTROPY, progress=False)
