@@ -44,25 +44,29 @@ class _Stream:
   cuda_stream = 0
 
 
-@pytest.fixture()
-def product(monkeypatch):
+def _emulate(setattr_, lib_path):
+  """Point kimimaro_b200 at the emulated library and stub the torch.cuda calls its host code makes."""
   import torch
   from kimimaro_b200 import _lib
   import kimimaro_b200.intake  # noqa: F401  (registers its entry points with _lib.declare)
   import kimimaro_b200.engine  # noqa: F401
-  lib_path = _build()
-  monkeypatch.setattr(_lib, "LIB_PATH", lib_path)
-  monkeypatch.setattr(_lib, "_lib", None)
-  monkeypatch.setattr(_lib, "_checked_devices", set())
-  monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
-  monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
-  monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
-  monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-  monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
-  monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
-  monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)   # ops.edt asserts it
+  setattr_(_lib, "LIB_PATH", lib_path)
+  setattr_(_lib, "_lib", None)
+  setattr_(_lib, "_checked_devices", set())
+  setattr_(torch.cuda, "is_available", lambda: True)
+  setattr_(torch.cuda, "current_device", lambda: 0)
+  setattr_(torch.cuda, "current_stream", lambda *a, **k: _Stream())
+  setattr_(torch.cuda, "synchronize", lambda *a, **k: None)
+  setattr_(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+  setattr_(torch.Tensor, "cuda", lambda self, *a, **k: self)
+  setattr_(torch.Tensor, "is_cuda", property(lambda self: True))   # ops.edt asserts it
   import kimimaro_b200
-  yield kimimaro_b200
+  return kimimaro_b200
+
+
+@pytest.fixture()
+def product(monkeypatch):
+  yield _emulate(lambda o, n, v: monkeypatch.setattr(o, n, v, raising=False), _build())
   monkeypatch.undo()
 
 
@@ -161,3 +165,51 @@ def test_more_of_the_api(product):
   plane = np.asfortranarray(tubes[:, :, 16])
   kw = dict(anisotropy=(16, 16), dust_threshold=20) if False else dict(dust_threshold=20)
   _compare(product.skeletonize(plane, progress=False, **kw), teasar.skeletonize(plane, **kw))
+
+
+# ---- N > 1: labels sharded over two ranks (gloo), one gather of packed skeleton buffers to rank 0 ----
+def _sharded_worker(rank, world, port, lib_path, q):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  import torch
+  import torch.distributed as dist
+  product = _emulate(setattr, lib_path)
+  from kimimaro_b200 import distributed as kd
+  from tests.synth import synthetic_tubes
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  labels = synthetic_tubes((56, 48, 32), 6, seed=12)
+  # skeletonize_sharded (kimimaro_b200/distributed.py) with the gather on CPU tensors
+  skels = product.skeletonize(labels, anisotropy=(16, 16, 40), dust_threshold=100, progress=False,
+                              label_subset=kd.make_label_subset(rank, world))
+  out = kd.gather_skeletons(skels, torch.device("cpu"))
+  if rank == 0:
+    q.put(({k: (v.vertices.copy(), v.edges.copy(), v.radii.copy()) for k, v in out.items()}, len(skels)))
+  else:
+    assert out is None
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_sharded_over_two_ranks_gloo():
+  """BASELINE.json configs[3] in miniature: every rank runs the replicated preamble and traces its LPT share of the
+  connected components; rank 0 ends up with exactly the skeletons one process computes."""
+  import torch.multiprocessing as mp
+  from oracle import teasar
+  from tests.synth import synthetic_tubes
+  from tests.test_distributed_cpu import _free_port
+  lib_path = _build()
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, lib_path, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  out, n_rank0 = q.get(timeout=600)
+  for p in procs:
+    p.join(timeout=600)
+    assert p.exitcode == 0
+  ref = teasar.skeletonize(synthetic_tubes((56, 48, 32), 6, seed=12), anisotropy=(16, 16, 40), dust_threshold=100)
+  assert sorted(out) == sorted(ref) and 0 < n_rank0 < len(ref)      # rank 0 traced only a share
+  for k in ref:
+    assert np.array_equal(out[k][0], ref[k]["vertices"]) and np.array_equal(out[k][1], ref[k]["edges"])
+    np.testing.assert_allclose(out[k][2], ref[k]["radii"], rtol=1e-4)
