@@ -1,6 +1,8 @@
 """Off-default options of skeletonize() on the CUDA path against the oracle.  Written in the
-session of round 1 that had no GPU time left: the host logic is covered on CPU tensors in tests/test_oracle_cpu.py,
-the kernels involved (b2t_fill_voids, the whole default path) by the files that run before this one."""
+session of round 1 that had no GPU time left.  Before their first run on a device the bodies of these tests ran on the
+CPU, through the whole product, on the library's kernels compiled against the SIMT emulation
+(`python scripts/run_gpu_tests_emulated.py tests.test_zz_options_gpu`: all passed); scaled-down versions are part of the
+CPU suite (tests/test_product_on_emulated_library_cpu.py)."""
 import numpy as np
 import pytest
 
