@@ -86,8 +86,9 @@ int b2t_edt_config_hybrid(int enable, int wy, int wz, int wr, int pf, int minb);
 int b2t_edt_config_roles(int enable, int stencil_v2, float predict_scale);
 /* Tuning hook of the hybrid's envelope kernel: query_prefetch = 4 keeps the next four stack entries of the write-out in
  * registers (the stack of a blob lives in local memory; its walk was one L2 round trip per row), 1 = the original loop.
- * Same result. */
-int b2t_edt_config_envelope(int query_prefetch);
+ * pop_ahead = 1 keeps the entry below the top of the stack in registers during the build (a pop then needs no load before
+ * the next intersection).  Same result. */
+int b2t_edt_config_envelope(int query_prefetch, int pop_ahead);
 
 
 /* N1  connected components ------------------------------------------------------------------------

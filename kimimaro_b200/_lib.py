@@ -32,7 +32,7 @@ _SIGNATURES = {
   "b2t_edt_config": [c_int, c_int, c_int, c_int, c_int],
   "b2t_edt_config_hybrid": [c_int, c_int, c_int, c_int, c_int, c_int],
   "b2t_edt_config_roles": [c_int, c_int, c_f32],
-  "b2t_edt_config_envelope": [c_int],
+  "b2t_edt_config_envelope": [c_int, c_int],
   "b2t_edt_workspace_bytes": [c_i64, c_i64, c_i64],
   "b2t_edt_ws": [c_vp, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_vp, c_vp, c_sz, c_vp],
 }

@@ -711,7 +711,7 @@ edt_pass_col_stencil_kernel(const T* __restrict__ labels, const float* __restric
 // envelope half of the hybrid pass: only the flagged 32-row blocks of a tile, extended to complete runs.
 // One WARP per CTA: most tiles have nothing flagged and leave at once, and a resident CTA that is one busy warp
 // plus three finished ones would waste three quarters of its slot.
-template <typename T, int C, int NMAX, int MINB, int R, int B, int QP = 1>
+template <typename T, int C, int NMAX, int MINB, int R, int B, int QP = 1, int PP = 0>
 __global__ void __launch_bounds__(32, MINB)
 edt_pass_col_fh3_range_kernel(const T* __restrict__ labels, const float* __restrict__ fin, float* __restrict__ fout, int n,
                               int64_t cstride, int nx, int64_t ostride, float w, int black_border, int last_pass,
@@ -738,7 +738,7 @@ edt_pass_col_fh3_range_kernel(const T* __restrict__ labels, const float* __restr
     fh3::extend_to_runs<T>(cx, labels + base, n, cstride, active, rlo, rhi, own_lo, own_hi);
     const int rb = cx.wmin(own_lo), re = cx.wmax(own_hi);
     if (rb < re)
-      fh3::column_range<T, C, R, B, true, false, QP>(cx, labels + base, fin + base, fout + base, n, cstride, w,
+      fh3::column_range<T, C, R, B, true, false, QP, PP>(cx, labels + base, fin + base, fout + base, n, cstride, w,
                                                      black_border != 0, last_pass != 0, active, rb, re, own_lo, own_hi);
   }
 }
@@ -823,10 +823,10 @@ edt_pass_col_fh3_kernel(const T* __restrict__ labels, float* __restrict__ f, int
 // Kernel selection (experiments and A/B timing; results are identical whatever is chosen).  Initialised from the
 // environment -- B2T_EDT_ALGO: 3 = shared-memory-ring F-H (default), 2 = local-memory F-H, w = windowed search;
 // B2T_FH3 = "C,MINB,R,B": one of the compiled instantiations -- and changeable at run time with b2t_edt_config().
-struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hwr, hpf, hminb; int ec, eminb, er, eb; int roles, sopt; float pscale; int eqp; };
+struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hwr, hpf, hminb; int ec, eminb, er, eb; int roles, sopt; float pscale; int eqp, epp; };
 static EdtCfg& edt_cfg() {
   static EdtCfg cfg = []() {
-    EdtCfg c{3, 16, 6, 32, 4, 1, 0, 0, 4, 11, 8, 32, 4, 32, 8, 0, 1, 1.0f, 1};   // hwy = 0: tap radii chosen from the anisotropy; stencil_column_v2 on
+    EdtCfg c{3, 16, 6, 32, 4, 1, 0, 0, 4, 11, 8, 32, 4, 32, 8, 0, 1, 1.0f, 1, 0};   // hwy = 0: tap radii chosen from the anisotropy; stencil_column_v2 on
     const char* a = getenv("B2T_EDT_ALGO");
     if (a) c.algo = (a[0] == 'w') ? 1 : (a[0] == '2' ? 2 : 3);
     const char* e = getenv("B2T_FH3");
@@ -837,6 +837,8 @@ static EdtCfg& edt_cfg() {
     if (r) c.roles = atoi(r);
     const char* q = getenv("B2T_EDT_QP");       // "4": the envelope kernel's write-out keeps 4 entries ahead in registers
     if (q) c.eqp = (atoi(q) == 4) ? 4 : 1;
+    const char* pp = getenv("B2T_EDT_PP");      // "1": the envelope kernel's build keeps the entry below the top in registers
+    if (pp) c.epp = atoi(pp) ? 1 : 0;
     const char* o = getenv("B2T_EDT_STENCIL");  // "1": the first stencil body; "2": stencil_column_v2 (default)
     if (o) c.sopt = (atoi(o) == 1) ? 0 : 1;
     return c;
@@ -1055,13 +1057,15 @@ static bool edt_launch_hybrid_pass(const uint32_t* labels, const float* fin, flo
         labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, flags, ntx);                             \
     done = true;                                                                                                          \
   }
-#define B2T_FR4_GO(NM_)                                                                                                   \
-  if (!done && n <= NM_ && c.eqp == 4 && c.ec == 32 && c.eminb == 4 && c.er == 32 && c.eb == 8) {                         \
-    edt_pass_col_fh3_range_kernel<uint32_t, 32, NM_, 16, 32, 8, 4><<<rgrid, 32, 0, st>>>(                                 \
+#define B2T_FR4_GO(NM_, QP_, PP_)                                                                                         \
+  if (!done && n <= NM_ && c.eqp == QP_ && c.epp == PP_ && c.ec == 32 && c.eminb == 4 && c.er == 32 && c.eb == 8) {        \
+    edt_pass_col_fh3_range_kernel<uint32_t, 32, NM_, 16, 32, 8, QP_, PP_><<<rgrid, 32, 0, st>>>(                          \
         labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, flags, ntx);                             \
     done = true;                                                                                                          \
   }
-  B2T_FR4_GO(256) B2T_FR4_GO(512) B2T_FR4_GO(1024) B2T_FR4_GO(2048)
+#define B2T_FR4_ALL(QP_, PP_) B2T_FR4_GO(256, QP_, PP_) B2T_FR4_GO(512, QP_, PP_) B2T_FR4_GO(1024, QP_, PP_) B2T_FR4_GO(2048, QP_, PP_)
+  B2T_FR4_ALL(4, 0) B2T_FR4_ALL(1, 1) B2T_FR4_ALL(4, 1)
+#undef B2T_FR4_ALL
 #undef B2T_FR4_GO
 #define B2T_FR_ALL(C_, MB_, R_, B_) B2T_FR_GO(256, C_, MB_, R_, B_) B2T_FR_GO(512, C_, MB_, R_, B_) B2T_FR_GO(1024, C_, MB_, R_, B_) B2T_FR_GO(2048, C_, MB_, R_, B_)
   B2T_FR_ALL(32, 4, 32, 8) B2T_FR_ALL(16, 6, 32, 4) B2T_FR_ALL(16, 8, 32, 4)
@@ -1106,13 +1110,15 @@ static bool edt_launch_roles_pass(const uint32_t* labels, const float* fin, floa
         labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, resid, ntx);                             \
     done = true;                                                                                                          \
   }
-#define B2T_FR4_GO(NM_)                                                                                                   \
-  if (!done && n <= NM_ && c.eqp == 4 && c.ec == 32 && c.eminb == 4 && c.er == 32 && c.eb == 8) {                         \
-    edt_pass_col_fh3_range_kernel<uint32_t, 32, NM_, 16, 32, 8, 4><<<rgrid, 32, 0, st>>>(                                 \
+#define B2T_FR4_GO(NM_, QP_, PP_)                                                                                         \
+  if (!done && n <= NM_ && c.eqp == QP_ && c.epp == PP_ && c.ec == 32 && c.eminb == 4 && c.er == 32 && c.eb == 8) {        \
+    edt_pass_col_fh3_range_kernel<uint32_t, 32, NM_, 16, 32, 8, QP_, PP_><<<rgrid, 32, 0, st>>>(                          \
         labels, fin, fout, n, cstride, (int)sx, ostride, w, black_border, last, resid, ntx);                             \
     done = true;                                                                                                          \
   }
-  B2T_FR4_GO(256) B2T_FR4_GO(512) B2T_FR4_GO(1024) B2T_FR4_GO(2048)
+#define B2T_FR4_ALL(QP_, PP_) B2T_FR4_GO(256, QP_, PP_) B2T_FR4_GO(512, QP_, PP_) B2T_FR4_GO(1024, QP_, PP_) B2T_FR4_GO(2048, QP_, PP_)
+  B2T_FR4_ALL(4, 0) B2T_FR4_ALL(1, 1) B2T_FR4_ALL(4, 1)
+#undef B2T_FR4_ALL
 #undef B2T_FR4_GO
 #define B2T_FR_ALL(C_, MB_, R_, B_) B2T_FR_GO(256, C_, MB_, R_, B_) B2T_FR_GO(512, C_, MB_, R_, B_) B2T_FR_GO(1024, C_, MB_, R_, B_) B2T_FR_GO(2048, C_, MB_, R_, B_)
   B2T_FR_ALL(32, 4, 32, 8) B2T_FR_ALL(16, 6, 32, 4) B2T_FR_ALL(16, 8, 32, 4)
@@ -1198,9 +1204,10 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
   return B2T_OK;
 }
 
-B2T_EXPORT int b2t_edt_config_envelope(int query_prefetch) {
+B2T_EXPORT int b2t_edt_config_envelope(int query_prefetch, int pop_ahead) {
   B2T_REQUIRE(query_prefetch == 1 || query_prefetch == 4, "b2t_edt_config_envelope: query_prefetch must be 1 or 4");
   edt_cfg().eqp = query_prefetch;
+  edt_cfg().epp = pop_ahead ? 1 : 0;
   return B2T_OK;
 }
 

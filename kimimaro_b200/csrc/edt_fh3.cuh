@@ -74,6 +74,10 @@ FH3_HD uint32_t brev32(uint32_t x) {
 // An entry is (v, h, z): row of the parabola's apex (absolute, kept as a float: rows < 2^24 are exact and the
 // hot loop then needs no int->float conversion), its height, and the left end of its reign (run-relative).
 
+// the entry below the top of the stack (PP of column_range); empty for the original loop
+template <int PP> struct PopAhead { float v, h, z; };
+template <> struct PopAhead<0> {};
+
 // query lookahead of column_range (QP > 1); empty for the original loop so that it compiles to the original code
 template <int QP> struct Lookahead { float v[QP], h[QP], z[QP]; };
 template <> struct Lookahead<1> {};
@@ -109,7 +113,9 @@ FH3_HD float intersect(Ctx& cx, float fi, float ir, float h, float v, float w2) 
 // of entries deep, far beyond the ring, and every row of the write-out walks one entry further, one L2 round trip at a
 // time.  With QP > 1 the next QP entries (apex, height, left end) are already in registers and each step only issues the
 // load of the entry QP steps ahead.  QP = 1 is the original code.
-template <typename T, int C, int R, int B, bool RANGE, bool NEXT = false, int QP = 1, typename Ctx>
+// PP: the entry BELOW the top of the stack is kept in registers too, so that a pop -- in a blob about one per row -- needs no
+// load before the next intersection; the entry below the new top is fetched after the pop, off the critical path.
+template <typename T, int C, int R, int B, bool RANGE, bool NEXT = false, int QP = 1, int PP = 0, typename Ctx>
 FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, int n, int64_t cstride, float w,
                          bool black_border, bool last_pass, bool active, int rb, int re, int own_lo, int own_hi,
                          float thr_next = 0.0f) {
@@ -126,6 +132,7 @@ FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, in
   int k_lo = 0;          // first entry of the open run
   int ring_lo = 0;       // entries below this index are in local memory (if still needed at all)
   float tv = 0.0f, th = 0.0f, tz = kNaN;   // top entry, cached (tv run-relative)
+  PopAhead<PP> pa;                         // PP: the entry below it, cached (v run-relative); only read when the top can pop
   int last_b = 0;        // end row of the most recent closed run
   // ---- query state: closed runs not written yet occupy entries [kn, kdone) ----
   int kn = 0;
@@ -180,11 +187,21 @@ FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, in
           s = intersect(cx, fi, ir, th, tv, w2);
           while (s <= tz) {                      // false on the run's first entry (its tz is a NaN)
             k--;
-            if (k < ring_lo) {
-              tv = cx.l_ld_v(k) - af; th = cx.l_ld_h(k); tz = cx.l_ld_z(k);
-              ring_lo = k + 1;
+            if constexpr (PP == 0) {
+              if (k < ring_lo) {
+                tv = cx.l_ld_v(k) - af; th = cx.l_ld_h(k); tz = cx.l_ld_z(k);
+                ring_lo = k + 1;
+              } else {
+                tv = cx.s_ld_v(FH3_SLOT(k)) - af; th = cx.s_ld_h(FH3_SLOT(k)); tz = cx.s_ld_z(FH3_SLOT(k));
+              }
             } else {
-              tv = cx.s_ld_v(FH3_SLOT(k)) - af; th = cx.s_ld_h(FH3_SLOT(k)); tz = cx.s_ld_z(FH3_SLOT(k));
+              tv = pa.v; th = pa.h; tz = pa.z;   // entry k, from registers
+              if (k < ring_lo) ring_lo = k + 1;  // the bookkeeping of the load that did not happen
+              if (k > k_lo) {                    // entry k-1 of the same run, for the pop after this one
+                const int b = k - 1;
+                if (b < ring_lo) { pa.v = cx.l_ld_v(b) - af; pa.h = cx.l_ld_h(b); pa.z = cx.l_ld_z(b); }
+                else { pa.v = cx.s_ld_v(FH3_SLOT(b)) - af; pa.h = cx.s_ld_h(FH3_SLOT(b)); pa.z = cx.s_ld_z(FH3_SLOT(b)); }
+              }
             }
             s = intersect(cx, fi, ir, th, tv, w2);
           }
@@ -199,6 +216,7 @@ FH3_HD void column_range(Ctx& cx, const T* lp, const float* fin, float* fout, in
           ring_lo = e + 1;
         }
         cx.s_st(FH3_SLOT(k), vf, fi, s);
+        if constexpr (PP != 0) { pa.v = tv; pa.h = th; pa.z = tz; }   // the old top is the entry below the new one
         tv = ir; th = fi; tz = s;
       }
     }

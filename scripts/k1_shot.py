@@ -81,16 +81,17 @@ def d2h(arr, src):
   cu(rt.cudaMemcpy(arr.ctypes.data_as(c_vp), src, arr.nbytes, 2), "d2h")
 
 
-# (name, hybrid on, roles on, stencil_column_v2 on, prediction scale, query prefetch of the envelope kernel)
+# (name, hybrid on, roles on, stencil_column_v2 on, prediction scale, (query prefetch, pop-ahead) of the envelope kernel)
 # the first form is the reference the others are compared with: the shipped default
 FORMS = [
-  ("hybrid + stencil v2 (shipped default)", 1, 0, 1, 1.0, 1),
-  ("hybrid + stencil v2 + envelope query prefetch 4", 1, 0, 1, 1.0, 4),
-  ("hybrid + stencil v1", 1, 0, 0, 1.0, 1),
-  ("hybrid + stencil v1 + envelope query prefetch 4", 1, 0, 0, 1.0, 4),
-  ("roles + stencil v2", 1, 1, 1, 1.0, 1),
-  ("roles + stencil v2 + envelope query prefetch 4", 1, 1, 1, 1.0, 4),
-  ("envelope only (b2t_edt path)", 0, 0, 1, 1.0, 1),
+  ("hybrid + stencil v2 (shipped default)", 1, 0, 1, 1.0, (1, 0)),
+  ("hybrid + stencil v2 + envelope query prefetch 4", 1, 0, 1, 1.0, (4, 0)),
+  ("hybrid + stencil v2 + envelope pop-ahead", 1, 0, 1, 1.0, (1, 1)),
+  ("hybrid + stencil v2 + envelope query prefetch 4 + pop-ahead", 1, 0, 1, 1.0, (4, 1)),
+  ("hybrid + stencil v1", 1, 0, 0, 1.0, (1, 0)),
+  ("roles + stencil v2", 1, 1, 1, 1.0, (1, 0)),
+  ("roles + stencil v2 + envelope query prefetch 4 + pop-ahead", 1, 1, 1, 1.0, (4, 1)),
+  ("envelope only (b2t_edt path)", 0, 0, 1, 1.0, (1, 0)),
 ]
 
 
@@ -175,7 +176,7 @@ def main():
     try:
       ok(b2t.b2t_edt_config_hybrid(hybrid, 0, 0, 4, 11, 8), "config_hybrid")
       ok(b2t.b2t_edt_config_roles(roles, sv2, c_f32(pscale)), "config_roles")
-      ok(b2t.b2t_edt_config_envelope(qp), "config_envelope")
+      ok(b2t.b2t_edt_config_envelope(qp[0], qp[1]), "config_envelope")
       dst = d_ref if first else d_out
       cu(rt.cudaMemset(dst, 0xff, V * 4), "poison")
       cu(rt.cudaMemset(d_ws, 0xff, V * 4), "poison")           # a voxel nobody writes stays a NaN

@@ -25,7 +25,7 @@ def sass(cu, out_dir, tag):
     m = re.search(r"Function : (\S+)", line)
     if m:
       cur = re.sub(r"_GLOBAL__N__[0-9a-f]+_\d+_[a-z_0-9]+_cu_[0-9a-f]+", "NS", m.group(1))
-      cur = re.sub(r"(fh3_range_kernelIjLi\d+ELi\d+ELi\d+ELi\d+ELi\d+E)Li1E", r"\1", cur)   # QP = 1 appended since
+      cur = re.sub(r"(fh3_range_kernelIjLi\d+ELi\d+ELi\d+ELi\d+ELi\d+E)Li1ELi0E", r"\1", cur)   # QP = 1, PP = 0 appended since
       funcs[cur] = []
     elif cur and line.strip() and not line.strip().startswith("."):
       funcs[cur].append(re.sub(r"/\*[0-9a-f]{4,}\*/", "", line).strip())

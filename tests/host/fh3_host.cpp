@@ -10,7 +10,7 @@
 
 static int g_stencil_v2 = 0;   // 1: the stencil passes run fh3::stencil_column_v2
 extern "C" void fh3_host_set_stencil(int v2) { g_stencil_v2 = v2; }
-static int g_query_prefetch = 1;   // 4: the envelope's write-out keeps four entries ahead (QP of fh3::column_range)
+static int g_query_prefetch = 1;   // 4: write-out lookahead 4 + pop-ahead (QP = 4, PP = 1 of fh3::column_range); 5: pop-ahead only
 extern "C" void fh3_host_set_query_prefetch(int qp) { g_query_prefetch = qp; }
 
 namespace {
@@ -172,8 +172,11 @@ void hybrid_pass(const uint32_t* labels, const float* fin, float* fout, int n, i
         fh3::extend_to_runs<uint32_t>(cx, labels + base, n, cstride, true, rlo, rhi, own_lo, own_hi);
         for (int q = 0; q < 64; q++) { cx.sv[q] = NAN; cx.sh[q] = NAN; cx.sz[q] = NAN; }
         if (g_query_prefetch == 4)
-          fh3::column_range<uint32_t, C, R, B, true, false, 4>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true,
-                                                               own_lo, own_hi, own_lo, own_hi);
+          fh3::column_range<uint32_t, C, R, B, true, false, 4, 1>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true,
+                                                                  own_lo, own_hi, own_lo, own_hi);
+        else if (g_query_prefetch == 5)
+          fh3::column_range<uint32_t, C, R, B, true, false, 1, 1>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true,
+                                                                  own_lo, own_hi, own_lo, own_hi);
         else
           fh3::column_range<uint32_t, C, R, B, true>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0, last != 0, true,
                                                      own_lo, own_hi, own_lo, own_hi);
@@ -262,8 +265,11 @@ void envelope_over(HostCtx& cx, const uint32_t* labels, const float* fin, float*
           for (int q = 0; q < 64; q++) { cx.sv[q] = NAN; cx.sh[q] = NAN; cx.sz[q] = NAN; }
           cx.nflag = next ? next + t : nullptr; cx.nstride = ntx; cx.nbit = 1ull << (o >> 5);
           if (g_query_prefetch == 4)
-            fh3::column_range<uint32_t, C, R, B, true, NEXT, 4>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0,
-                                                                last != 0, true, rb, re, lo[l], hi[l], thr_next);
+            fh3::column_range<uint32_t, C, R, B, true, NEXT, 4, 1>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0,
+                                                                   last != 0, true, rb, re, lo[l], hi[l], thr_next);
+          else if (g_query_prefetch == 5)
+            fh3::column_range<uint32_t, C, R, B, true, NEXT, 1, 1>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0,
+                                                                   last != 0, true, rb, re, lo[l], hi[l], thr_next);
           else
             fh3::column_range<uint32_t, C, R, B, true, NEXT>(cx, labels + base, fin + base, fout + base, n, cstride, w, bb != 0,
                                                              last != 0, true, rb, re, lo[l], hi[l], thr_next);

@@ -107,10 +107,10 @@ def test_non_integer_anisotropy(fh3):
 # ---- hybrid pass (b2t_edt_ws): stencil everywhere + envelope on the flagged blocks, out of place ----
 # variant = stencil windows (y, z) and prefetch, see fh3_host.cpp; every voxel of the result must have been
 # written by one of the two kernels (the harness poisons both buffers with NaN)
-@pytest.fixture(params=[(0, 1), (1, 1), (1, 4)], ids=["stencil_v1", "stencil_v2", "stencil_v2_qp4"])
+@pytest.fixture(params=[(0, 1), (1, 1), (1, 4), (1, 5)], ids=["stencil_v1", "stencil_v2", "stencil_v2_qp4_pp", "stencil_v2_pp"])
 def stencil(fh3, request):
   """The stencil bodies of edt_fh3.cuh -- stencil_column and stencil_column_v2 (leaner steady state) -- and the
-  envelope's write-out with four entries of lookahead (QP = 4 of column_range)."""
+  envelope's write-out with four entries of lookahead and the pop-ahead of its build (QP = 4, PP = 1 of column_range)."""
   fh3.fh3_host_set_stencil(request.param[0])
   fh3.fh3_host_set_query_prefetch(request.param[1])
   yield request.param
