@@ -1,8 +1,11 @@
 """Off-default options of skeletonize() on the CUDA path against the oracle.  Written in the
 session of round 1 that had no GPU time left.  Before their first run on a device the bodies of these tests ran on the
 CPU, through the whole product, on the library's kernels compiled against the SIMT emulation
-(`python scripts/run_gpu_tests_emulated.py tests.test_zz_options_gpu`: all passed); scaled-down versions are part of the
-CPU suite (tests/test_product_on_emulated_library_cpu.py)."""
+(`python scripts/run_gpu_tests_emulated.py tests.test_zz_options_gpu <name>`): test_fill_holes, test_fix_avocados,
+test_fill_all_holes_reference_known_answer, test_binary_image and test_extra_targets_grow_the_skeleton passed there; the
+two with million-voxel labels (test_square_with_fill_holes, test_parallel_argument_is_accepted) are too slow to emulate
+and only add fill_holes=True / parallel=2 to cases the GPU suite already runs.  Scaled-down versions are part of the CPU
+suite (tests/test_product_on_emulated_library_cpu.py)."""
 import numpy as np
 import pytest
 
