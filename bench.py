@@ -30,7 +30,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ANISOTROPY = (16.0, 16.0, 40.0)
+ANISOTROPY = (16.0, 16.0, 40.0)        # BASELINE.json configs[1..3] (benchmarks/benchmark.py:27)
+ANISOTROPY_1024 = (4.0, 4.0, 40.0)     # BASELINE.json configs[4]
 SEED = 0xB2002124
 SLAB = (160, 208)          # z-slab of the volume used as the bounded CPU sample (it cuts the lower cap of the soma)
 # The CPU legs run the oracle's LITERAL restatement of the reference: binary-heap Dijkstra fields and the heap-ordered
@@ -64,12 +65,38 @@ def make_volume(n):
   return vol
 
 
+def anisotropy_of(size):
+  return ANISOTROPY_1024 if size == 1024 else ANISOTROPY
+
+
 def workload_name(vol, size):
   shape = vol.shape
   extra = "one soma + one glia tree, " if size >= 512 else ""
+  an = anisotropy_of(size)
+  cfg = "configs[4]" if size == 1024 else "configs[2]"
   return (f"synthetic-{size}: {shape[0]}x{shape[1]}x{shape[2]} uint32, {int(len(np.unique(vol)) - 1)} labels, {extra}"
-          "anisotropy 16x16x40, DEFAULT_TEASAR_PARAMS, fix_borders (BASELINE.json configs[2] shape; the reference's "
-          "connectomics.npy.ckl.gz cannot be decoded in this image)")
+          f"anisotropy {an[0]:g}x{an[1]:g}x{an[2]:g}, DEFAULT_TEASAR_PARAMS, fix_borders (BASELINE.json {cfg} shape; the "
+          "reference's connectomics.npy.ckl.gz cannot be decoded in this image)")
+
+
+def skeleton_digests(sk):
+  """per skeleton: first 16 hex digits of sha256(vertices bytes + edges bytes) -- the format of tests/golden/*digest*.json"""
+  import hashlib
+  out = {}
+  for k, s in sk.items():
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(s.vertices).tobytes())
+    h.update(np.ascontiguousarray(s.edges).tobytes())
+    out[str(k)] = h.hexdigest()[:16]
+  return out
+
+
+def golden_digest(name):
+  p = os.path.join(ROOT, "tests", "golden", name)
+  if not os.path.exists(p):
+    return None
+  with open(p) as f:
+    return json.load(f)["sha256_16_of_vertices_then_edges"]
 
 
 class ClockSampler:
@@ -125,7 +152,9 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
-  """CPU arm: the oracle port of the reference on a bounded slab, all host cores."""
+  """CPU arm: the oracle port of the reference (literal restatement, heap-ordered invalidation), all host cores.
+  value = the WHOLE volume, one pass (the same configuration as the GPU arm: about a minute on 16 cores); the
+  --steps / --warmup repetitions run on a bounded z-slab of it and are reported next to it (cpu_baseline.slab)."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
@@ -133,27 +162,39 @@ def run_reference(args):
   from oracle import teasar
   oracle.build()
   vol = make_volume(args.size)
+  an = anisotropy_of(args.size)
+  cores = os.cpu_count() or 1
   z0, z1 = (SLAB if args.size >= 256 else (0, args.size))
   sample = np.asfortranarray(vol[:512, :512, z0:z1])
-  cores = os.cpu_count() or 1
   times = []
   for i in range(args.warmup + args.steps):
     t = time.perf_counter()
-    teasar.skeletonize(sample, anisotropy=ANISOTROPY, parallel=cores, invalidation_mode=CPU_MODE)
+    teasar.skeletonize(sample, anisotropy=an, parallel=cores, invalidation_mode=CPU_MODE)
     dt = time.perf_counter() - t
     if i >= args.warmup:
       times.append(dt)
-  ms = 1e3 * float(np.mean(times))
-  v = sample.size / (ms / 1e3)
+  slab_ms = 1e3 * float(np.mean(times))
+  slab_v = sample.size / (slab_ms / 1e3)
+  whole = args.size <= 512 and not args.slab_only
+  if whole:
+    t = time.perf_counter()
+    sk = teasar.skeletonize(vol, anisotropy=an, parallel=cores, invalidation_mode=CPU_MODE)
+    ms = 1e3 * (time.perf_counter() - t)
+    v = vol.size / (ms / 1e3)
+    what = f"the whole volume, one pass ({ms / 1e3:.1f} s, {len(sk)} skeletons)"
+  else:
+    ms, v = slab_ms, slab_v
+    what = f"z-slab [{z0}:{z1}) of the volume ({sample.shape[0]}x{sample.shape[1]}x{sample.shape[2]})"
   line = {
     "impl": "reference", "metric": "voxels/sec skeletonized", "value": v, "unit": "voxels/s", "n_gpus": args.gpus,
     "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-    "config": {"workload": workload_name(vol, args.size),
-               "sample": f"z-slab [{z0}:{z1}) of the volume ({sample.shape[0]}x{sample.shape[1]}x{sample.shape[2]})"},
+    "config": {"workload": workload_name(vol, args.size), "sample": what},
     "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port",
-                     "sample": f"z-slab [{z0}:{z1}) of the same volume, fork pool over labels, literal restatement "
-                               f"(heap-ordered invalidation like ext/skeletontricks)"},
+                     "sample": what + "; fork pool over labels, literal restatement (heap-ordered invalidation like "
+                                      "ext/skeletontricks)",
+                     "slab": {"value": slab_v, "ms_per_step": slab_ms, "steps": args.steps, "warmup": args.warmup,
+                              "sample": f"z-slab [{z0}:{z1}) of the same volume"}},
     "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
   }
   print(json.dumps(line), flush=True)
@@ -184,6 +225,7 @@ def run_b200(args):
     vol = make_volume(args.size)
   shape = vol.shape
   V = vol.size
+  AN = anisotropy_of(args.size)
   flat = vol.reshape(-1, order="F")
   pinned = torch.from_numpy(flat.view(np.uint32).view(np.int32)).pin_memory()
   host_view = pinned.numpy().view(np.uint32).reshape(shape, order="F")       # Fortran view of the pinned buffer
@@ -191,14 +233,14 @@ def run_b200(args):
   subset = kdist.make_label_subset(rank, world) if world > 1 else None
 
   def step_resident(edt_events=None):
-    sk = skeletonize(shape, device_labels=d_labels, anisotropy=ANISOTROPY, progress=False, label_subset=subset,
+    sk = skeletonize(shape, device_labels=d_labels, anisotropy=AN, progress=False, label_subset=subset,
                      edt_events=edt_events)
     if world > 1:
       sk = kdist.gather_skeletons(sk, dev)
     return sk
 
   def step_e2e():
-    sk = skeletonize(host_view, anisotropy=ANISOTROPY, progress=False, in_place=True, label_subset=subset)
+    sk = skeletonize(host_view, anisotropy=AN, progress=False, in_place=True, label_subset=subset)
     if world > 1:
       sk = kdist.gather_skeletons(sk, dev)
     return sk
@@ -258,11 +300,45 @@ def run_b200(args):
 
   # per-phase breakdowns (extra steps with synchronising laps, not part of the metric)
   tme = {}
-  skeletonize(host_view, anisotropy=ANISOTROPY, progress=False, in_place=True, label_subset=subset, timings=tme)
+  skeletonize(host_view, anisotropy=AN, progress=False, in_place=True, label_subset=subset, timings=tme)
   e2e_phases = {k: round(1e3 * v, 3) for k, v in tme.items() if isinstance(v, float)}
   tm = {}
-  skeletonize(shape, device_labels=d_labels, anisotropy=ANISOTROPY, progress=False, label_subset=subset, timings=tm)
+  skeletonize(shape, device_labels=d_labels, anisotropy=AN, progress=False, label_subset=subset, timings=tm)
   phases = {k: round(1e3 * v, 3) for k, v in tm.items() if isinstance(v, float)}
+
+  # parity with the REFERENCE's invalidation order, measured on this very run (outside the timed region): the timed
+  # steps' skeletons against the digest of the oracle's literal heap order (== the reference's compiled extension), then
+  # one pass in the engine's strict mode, which must hit all of them
+  parity = None
+  mode, window = _lib.invalidation_mode()
+  heap_gold = golden_digest("synth512_oracle_digest_heap.json") if args.size == 512 else None
+  if heap_gold is not None:
+    same_gold = golden_digest("synth512_oracle_digest_window1.json")
+    strict = None
+    if not args.no_strict:
+      _lib.set_invalidation_mode("strict")
+      try:
+        sync()
+        t = time.perf_counter()
+        sk_s = step_resident()
+        sync()
+        strict_ms = 1e3 * (time.perf_counter() - t)
+      finally:
+        _lib.set_invalidation_mode(mode, window)
+      if rank == 0:
+        ds = skeleton_digests(sk_s)
+        strict = {"identical_to_reference_order": int(sum(ds.get(k) == h for k, h in heap_gold.items())),
+                  "of": len(heap_gold), "ms_per_step": strict_ms}
+    if rank == 0:
+      dg = skeleton_digests(sk)
+      parity = {"mode": mode + (f":{window:g}" if mode == "window" else ""),
+                "identical_to_reference_order": int(sum(dg.get(k) == h for k, h in heap_gold.items())),
+                "of": len(heap_gold),
+                "tier_a_identical_to_oracle_in_same_mode": (int(sum(dg.get(k) == h for k, h in same_gold.items()))
+                                                            if (same_gold and mode == "window" and window == 1.0) else None),
+                "strict": strict,
+                "reference_order": "oracle mode 'heap' == ext/skeletontricks compiled (tests/test_oracle_cpu.py), "
+                                   "tests/golden/synth512_oracle_digest_heap.json"}
 
   if rank == 0:
     peak, how = peaks()
@@ -288,7 +364,7 @@ def run_b200(args):
       z0, z1 = (SLAB if args.size >= 256 else (0, args.size))
       sample = np.asfortranarray(vol[:512, :512, z0:z1])
       t = time.perf_counter()
-      teasar.skeletonize(sample, anisotropy=ANISOTROPY, invalidation_mode=CPU_MODE)
+      teasar.skeletonize(sample, anisotropy=AN, invalidation_mode=CPU_MODE)
       cdt = time.perf_counter() - t
       cpu = {"value": sample.size / cdt, "unit": "voxels/s", "cores": 1, "kind": "port",
              "sample": f"z-slab [{z0}:{z1}) of the same volume ({sample.shape[0]}x{sample.shape[1]}x{sample.shape[2]}), {cdt:.1f} s, "
@@ -302,7 +378,8 @@ def run_b200(args):
                  "parallelism": f"labels sharded over {world} rank(s)"},
       "e2e": {"value": V / (mse / 1e3), "unit": "voxels/s", "h2d_bytes_per_step": int(flat.nbytes),
               "d2h_bytes_per_step": d2h, "ms_per_step": mse},
-      "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "phases_ms": phases,
+      "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+      "phases_ms": phases,
       "e2e_phases_ms": e2e_phases, "per_step_ms": step_log,
     }
     print(json.dumps(line), flush=True)
@@ -319,6 +396,8 @@ def main():
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--size", type=int, default=512)
   ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+  ap.add_argument("--slab-only", action="store_true", help="--impl reference: skip the whole-volume pass")
+  ap.add_argument("--no-strict", action="store_true", help="skip the strict-mode pass (parity.strict)")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

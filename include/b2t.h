@@ -39,11 +39,15 @@ unsigned long long b2t_launch_count(int reset); /* kernels launched by this libr
 /* cap resident blocks per SM of the cooperative sweeps / of the path-loop kernel (0 = no cap) so that two
  * arenas can be traced concurrently on two streams */
 int b2t_set_launch_limits(int coop_blocks_per_sm, int trace_blocks_per_sm);
-/* Experimental, off by default: order the invalidation rounds of the path loop (b2t_trace_batch) by the reference's
- * heap key -- distance to the seed, dijkstra_invalidation.hpp:233-237 -- in windows of `voxels` smallest-voxel-edges
- * instead of by hop count; 0 restores the hop-synchronous rounds.  See DESIGN.md 4 (Tier B) and the oracle's
- * invalidation mode "window:<voxels>". */
-int b2t_set_claim_window(float voxels);
+/* Claim order of roll_invalidation_ball_inside_component inside the path loop (b2t_trace_batch), DESIGN.md 4:
+ *   WINDOW  parallel rounds ordered by the reference's heap key -- distance to the seed, dijkstra_invalidation.hpp:233-237
+ *           -- in windows of `claim_window_voxels` smallest-voxel-edges (the default of kimimaro_b200: 1)
+ *   STRICT  the reference's std::priority_queue literally, libstdc++'s order of equal keys included: identical to the
+ *           compiled reference voxel for voxel; sequential per label (one warp), needs the heap buffer
+ *   ROUNDS  hop-synchronous rounds (round 1's order) */
+#define B2T_INVALIDATE_ROUNDS 0
+#define B2T_INVALIDATE_WINDOW 1
+#define B2T_INVALIDATE_STRICT 2
 
 /* K1  anisotropic multi-label Euclidean distance transform ------------------------------------
  * replaces  edt.edt(labels, anisotropy, black_border)            kimimaro/intake.py:174-185
@@ -158,14 +162,21 @@ int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist
  *   segid, root, n_fg, region_off, path_off, path_cap, tb_off, tb_n, ta_off, ta_n, max_paths (0xffffffff =
  *   None), soma_mode, soma_radius (float32), bucket_row, soma_done, pre_invalid
  * d_scratch: 6*sum(n_fg) u32; d_paths: pool of voxel indices, each path [rail ... target] terminated by
- * 0xffffffff; d_out_len / d_out_npaths / d_out_status: n_desc; d_out_stats: 4*n_desc; d_work_counter: 1 u32. */
+ * 0xffffffff; d_out_len / d_out_npaths / d_out_status: n_desc; d_out_stats: 4*n_desc; d_work_counter: 1 u32.
+ * invalidation_mode: B2T_INVALIDATE_*; claim_window_voxels: width of a WINDOW round.  STRICT only: d_heap holds heap_words
+ * u32, of which the first heap_static_words = b2t_trace_heap_words(sum(n_fg), n_desc) are the labels' own heap regions
+ * (4 entries per voxel) and the rest a spill arena for heaps that outgrow theirs (up to 27 entries per voxel of the
+ * label); a label whose heap fits nowhere reports B2T_ERR_CAPACITY in d_out_status.  Other modes: NULL, 0, 0. */
+uint64_t b2t_trace_heap_words(uint64_t sum_n_fg, uint64_t n_desc);
 int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,
                     uint32_t* d_stamp, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
                     const void* d_desc, int n_desc, float scale, float konst, float soma_scale,
                     float soma_const, int fix_branching, int nbuckets, const uint64_t* d_keys, const uint32_t* d_hist,
                     const uint32_t* d_cursor, uint32_t* d_scratch, uint32_t* d_paths,
                     const uint32_t* d_targets, uint32_t* d_out_len, uint32_t* d_out_npaths,
-                    int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter, void* stream);
+                    int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter,
+                    int invalidation_mode, float claim_window_voxels, uint32_t* d_heap, uint64_t heap_words,
+                    uint64_t heap_static_words, void* stream);
 
 /* the same rolling-ball invalidation, grid-wide, for balls too large for one CTA (the one-off soma
  * invalidation, kimimaro/trace.py:160-168).  d_fv / d_fs: 2*cap u32 each; count left in d_ctrl[6]. */

@@ -27,7 +27,6 @@ _SIGNATURES = {
   "b2t_version": [],
   "b2t_last_error": [],
   "b2t_device_check": [],
-  "b2t_set_claim_window": [c_f32],
   "b2t_edt": [c_vp, c_int, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_vp, c_vp],
   "b2t_edt_config": [c_int, c_int, c_int, c_int, c_int],
   "b2t_edt_config_hybrid": [c_int, c_int, c_int, c_int, c_int, c_int],
@@ -86,6 +85,33 @@ def require_device():
     return
   check(lib().b2t_device_check(), "b2t_device_check")
   _checked_devices.add(dev)
+
+
+# ---- claim order of roll_invalidation_ball_inside_component in the path loop (include/b2t.h: B2T_INVALIDATE_*) ----
+INVALIDATE_ROUNDS, INVALIDATE_WINDOW, INVALIDATE_STRICT = 0, 1, 2
+_MODES = {"rounds": INVALIDATE_ROUNDS, "window": INVALIDATE_WINDOW, "strict": INVALIDATE_STRICT}
+_invalidation = None
+
+
+def set_invalidation_mode(mode, window=1.0):
+  """'window' (default): parallel rounds ordered by the reference's heap key in windows of `window` voxel edges;
+  'strict': the reference's priority queue literally (identical to the compiled reference, sequential per label);
+  'rounds': hop-synchronous rounds.  The environment variable B2T_INVALIDATION ('strict', 'rounds', 'window[:w]')
+  sets the initial value."""
+  global _invalidation
+  if mode not in _MODES:
+    raise ValueError(f"invalidation mode must be one of {sorted(_MODES)}, got {mode!r}")
+  if mode == "window" and not window > 0:
+    raise ValueError("the window mode needs a positive window")
+  _invalidation = (mode, float(window))
+
+
+def invalidation_mode():
+  """(mode name, window in voxel edges)"""
+  if _invalidation is None:
+    env = os.environ.get("B2T_INVALIDATION", "window").split(":")
+    set_invalidation_mode(env[0], float(env[1]) if len(env) > 1 else 1.0)
+  return _invalidation
 
 
 def stream_ptr():

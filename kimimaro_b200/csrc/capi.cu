@@ -19,24 +19,11 @@ void b2t_count_launches(int n) { g_launches += (unsigned long long)n; }
 static int g_coop_limit = 0, g_trace_limit = 0;
 int b2t_coop_limit() { return g_coop_limit; }
 int b2t_trace_limit() { return g_trace_limit; }
-static float g_claim_window = []() { const char* e = getenv("B2T_CLAIM_WINDOW"); return e ? (float)atof(e) : 0.0f; }();
-float b2t_claim_window() { return b2t_claim_window_built() ? g_claim_window : 0.0f; }
-
 // Cap the resident blocks per SM of the cooperative sweeps / of the path-loop kernel (0 = no cap), so that
 // a private-arena pipeline on a second stream can run next to the path loop of the main arena.
 B2T_EXPORT int b2t_set_launch_limits(int coop_blocks_per_sm, int trace_blocks_per_sm) {
   g_coop_limit = coop_blocks_per_sm < 0 ? 0 : coop_blocks_per_sm;
   g_trace_limit = trace_blocks_per_sm < 0 ? 0 : trace_blocks_per_sm;
-  return B2T_OK;
-}
-
-// Experimental (off by default, round-2 work): order the path loop's invalidation rounds by distance to the seed -- the
-// reference's heap key -- in windows of `voxels` smallest-voxel-edges instead of by hop count (trace.cu: invalidate_window;
-// oracle mode "window:<voxels>").  0 restores the hop-synchronous rounds.
-B2T_EXPORT int b2t_set_claim_window(float voxels) {
-  B2T_REQUIRE(!(voxels > 0.0f) || b2t_claim_window_built(),
-              "b2t_set_claim_window: this build of libb2t.so has no key-ordered invalidation (B2T_WITH_CLAIM_WINDOW)");
-  g_claim_window = voxels > 0.0f ? voxels : 0.0f;
   return B2T_OK;
 }
 

@@ -12,8 +12,6 @@ void b2t_set_error(const char* fmt, ...);
 void b2t_count_launches(int n);  // bookkeeping for b2t_launch_count()
 int b2t_coop_limit();    // max blocks per SM for cooperative kernels (0 = whatever fits), see b2t_set_launch_limits
 int b2t_trace_limit();   // max blocks per SM for the path-loop kernel (0 = whatever fits)
-bool b2t_claim_window_built();  // trace.cu compiled with B2T_WITH_CLAIM_WINDOW
-float b2t_claim_window();  // width of key-ordered invalidation rounds in smallest-voxel-edge units (0 = hop rounds), b2t_set_claim_window
 
 #define B2T_CUDA_TRY(expr)                                                                  \
   do {                                                                                      \

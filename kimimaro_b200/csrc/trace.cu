@@ -12,8 +12,12 @@
 //                       close as the best rail-adjacent voxel is final; parents by rule T3.
 //              cull     soma only (trace.py:246-251), float64 with the reference's uint32 wrap.
 //              erase    roll_invalidation_ball_inside_component (pyx:373-418 ->
-//                       dijkstra_invalidation.hpp:239-332) as a round-synchronous parallel claim:
-//                       packed (dist, seed) 64-bit atomicMin per candidate voxel, strict d < r.
+//                       dijkstra_invalidation.hpp:239-332), three claim orders (b2t_set_invalidation_mode):
+//                         window  parallel rounds ordered by the reference's heap key (distance to the seed) in
+//                                 windows of one voxel edge: packed (dist, seed) 64-bit atomicMin per candidate (default)
+//                         strict  the reference's std::priority_queue LITERALLY (libstdc++ push_heap / pop_heap order
+//                                 for equal keys included), one warp per label: identical to the compiled reference
+//                         rounds  hop-synchronous rounds (round 1's order; kept for A/B)
 //              rail     PDRF[path] = 0 (trace.py:261-263)
 //
 // Per-voxel fields are the dense arrays of field.cu (cc, dbf, pdrf, dist, claim, stamp); per-label
@@ -34,12 +38,12 @@ namespace {
 constexpr uint32_t kInfBits = 0x7f800000u;
 constexpr unsigned long long kValid = ~0ull;
 constexpr int kThreads = 512;   // 16 warps: a whole narrow batch expands in one pass
-// 1: compile the key-ordered invalidation rounds (invalidate_window) into the path-loop kernel.  Off in the shipped build so
-// that the kernel the round's numbers were measured with stays what it was (the extra call costs it spill traffic);
-// `python -m kimimaro_b200.build --variant claim_window` builds kimimaro_b200/_variants/claim_window.so with it.
-#ifndef B2T_WITH_CLAIM_WINDOW
-#define B2T_WITH_CLAIM_WINDOW 0
+#ifndef B2T_HEAP_PER_VOXEL
+#define B2T_HEAP_PER_VOXEL 4         // (the CPU harness builds with smaller numbers to exercise the spill path)
+#define B2T_HEAP_SLACK 4096
 #endif
+constexpr int kHeapPerVoxel = B2T_HEAP_PER_VOXEL;   // strict mode: static heap nodes per foreground voxel of a label ...
+constexpr int kHeapSlack = B2T_HEAP_SLACK;          // ... plus this many; a heap that outgrows it moves to the spill arena
 #ifndef B2T_TRACE_MINB
 #define B2T_TRACE_MINB 3        // resident CTAs per SM (42 registers per thread)
 #endif
@@ -85,9 +89,8 @@ struct Params {
   int nbuckets;
   int n_desc;
   int fix_branching;             // 0: paths come from the parental field already in A.dist (trace.py:154-158, 244)
-#if B2T_WITH_CLAIM_WINDOW
-  float claim_window;            // 0: hop-synchronous invalidation rounds; > 0: key-ordered rounds of this width (invalidate_window)
-#endif
+  int inval_mode;                // B2T_INVALIDATE_ROUNDS / _WINDOW / _STRICT
+  float claim_window;            // _WINDOW: width of a key-ordered round in physical units
 };
 
 struct Pools {
@@ -102,6 +105,10 @@ struct Pools {
   int32_t* out_status;             // per desc: 0 ok, <0 error
   uint32_t* out_stats;             // per desc x 4: relaxations, rounds, invalidated, elapsed microseconds
   uint32_t* work_counter;
+  uint32_t* heap;                  // strict mode: 3 u32 per heap node (key | voxel | seed, one array each per label)
+  unsigned long long heap_words;   // size of `heap`; words past the static regions are the spill arena
+  unsigned long long heap_static;  // words taken by the static regions
+  unsigned long long* heap_bump;   // spill arena: words handed out so far
 };
 
 __device__ __forceinline__ void unravel(uint32_t loc, const Dims& d, int& x, int& y, int& z) {
@@ -159,6 +166,8 @@ struct Shared {
   uint32_t job;
   int bucket;
   uint32_t relax, rounds, invalidated;
+  uint32_t* heap_k;          // strict mode: this label's heap (its own region, or the spill arena once it outgrew that)
+  uint32_t heap_cap;         // 0 = not set up yet
 };
 
 // ---- CachedTargetFinder.find_target ------------------------------------------------------------------
@@ -545,8 +554,7 @@ __device__ uint32_t invalidate(const Arena& A, const LabelDesc& L, const uint32_
   return total;
 }
 
-#if B2T_WITH_CLAIM_WINDOW
-// ---- the same, ordered by KEY instead of by hop count (off by default: b2t_set_claim_window) -----------
+// ---- the same, ordered by KEY instead of by hop count (the default: b2t_set_invalidation_mode) -----------
 // The reference pops its heap in order of ||w.(v - seed)|| (dijkstra_invalidation.hpp:233-237); the hop-synchronous
 // rounds above hand a voxel to whichever seed reaches it in the fewest steps.  Where balls of different radii overlap
 // that changes owners, and with them how far the claim spreads: on the CPU (oracle/oracle.c: orc_invalidate_heap is the
@@ -664,7 +672,200 @@ __device__ __noinline__ uint32_t invalidate_window(const Arena& A, const LabelDe
   __syncthreads();
   return total;
 }
-#endif  // B2T_WITH_CLAIM_WINDOW
+// ---- the same, LITERALLY: std::priority_queue<HeapDistanceNode, vector, HeapDistanceNodeCompare> on one warp ----------
+// dijkstra_invalidation.hpp:233-237, 291-329.  The reference's comparator `t1.dist >= t2.dist` is not a strict weak
+// order, so which of two entries with equal keys is popped first is whatever libstdc++'s push_heap / pop_heap
+// (bits/stl_heap.h: __push_heap, __adjust_heap) make of the array -- and with it which seed owns a voxel that two seeds
+// reach at the same distance, whose radius then governs how far the claim spreads.  Only the literal process reproduces
+// that, so this mode keeps the very array: three u32 planes (key = distance bits, voxel, seed order) in the label's heap
+// region.  It is sequential per label by nature; the warp is used for what is independent inside ONE heap operation:
+//   push   the ancestors of slot n are known in advance: every lane loads one, a ballot finds how far the new entry
+//          rises, the lanes shift their entries down together                       (one round trip instead of log n)
+//   pop    __adjust_heap walks the hole to the bottom along the smaller children: the 30 descendants of the next four
+//          levels are loaded at once and the four choices made by shuffles         (log n / 4 round trips); the entries
+//          on that path then move up together and the displaced last entry drops in where __push_heap would leave it
+//   visit  lanes = the 26 neighbours in the reference's order, with its aliasing at the x faces (a corner entry is gated
+//          on y and z only, hpp:116-123: at x = 0 / sx-1 it repeats the yz diagonal and that voxel is pushed twice)
+// Non-negative floats order like their bit patterns, so keys are compared as u32.
+struct WarpHeap {
+  uint32_t* k;
+  uint32_t* v;
+  uint32_t* s;
+  uint32_t n, cap;
+};
+
+__device__ __forceinline__ void heap_push(WarpHeap& H, uint32_t key, uint32_t vox, uint32_t seed, int lane) {
+  const uint32_t idx = H.n;
+  H.n = idx + 1;
+  // lane j: the ancestor j+1 levels above slot idx (1-based heap numbering: (idx+1) >> (j+1))
+  const uint32_t a1 = lane < 31 ? ((idx + 1u) >> (lane + 1)) : 0u;
+  const bool have = a1 != 0u;
+  const uint32_t anc = a1 - 1u;
+  const uint32_t ka = have ? H.k[anc] : 0u;
+  // __push_heap: while (hole > top && comp(parent, value)) -- comp(parent, value) = parent.dist >= value.dist
+  const uint32_t m = __ballot_sync(0xffffffffu, have && ka >= key);
+  const int t = __ffs((int)~m) - 1;                  // entries that move down: lanes 0 .. t-1
+  const uint32_t up = __shfl_up_sync(0xffffffffu, anc, 1);
+  const uint32_t hole = __shfl_sync(0xffffffffu, anc, t > 0 ? t - 1 : 0);
+  if (t > 0) {
+    uint32_t pv = 0, ps = 0;
+    if (lane < t) { pv = H.v[anc]; ps = H.s[anc]; }
+    __syncwarp();
+    if (lane < t) {
+      const uint32_t dest = lane == 0 ? idx : up;
+      H.k[dest] = ka; H.v[dest] = pv; H.s[dest] = ps;
+    }
+  }
+  if (lane == 0) {
+    const uint32_t at = t > 0 ? hole : idx;
+    H.k[at] = key; H.v[at] = vox; H.s[at] = seed;
+  }
+  __syncwarp();
+}
+
+// queue.top() + queue.pop(): returns the entry in (tk, tv, ts)
+__device__ __forceinline__ void heap_pop(WarpHeap& H, uint32_t& tk, uint32_t& tv, uint32_t& ts, int lane) {
+  tk = H.k[0]; tv = H.v[0]; ts = H.s[0];
+  const uint32_t len = H.n - 1u;                     // std::pop_heap: the last entry is re-inserted into [0, len)
+  H.n = len;
+  if (len == 0u) return;
+  const uint32_t vk = H.k[len], vv = H.v[len], vs = H.s[len];
+  __syncwarp();
+  uint32_t c = 0;                                    // the hole
+  int depth = 0;
+  uint32_t myidx = 0, mykey = 0;                     // lane d (>= 1): the entry on the hole's way down at depth d
+  const uint32_t lim = (len - 1u) / 2u;              // __adjust_heap: while (second < (len - 1) / 2)
+  // lane l < 30: descendant of the hole k levels down (k = 1..4), o-th of its level
+  const int kk = lane < 2 ? 1 : (lane < 6 ? 2 : (lane < 14 ? 3 : 4));
+  const uint32_t oo = (uint32_t)lane + 2u - (1u << kk);
+  while (c < lim) {
+    const unsigned long long di = (((unsigned long long)c + 1ull) << kk) - 1ull + oo;
+    const uint32_t key = (lane < 30 && di < (unsigned long long)len) ? H.k[di] : 0xffffffffu;
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 1; k <= 4; k++) {
+      if (c < lim) {                                 // uniform: both children exist
+        const int base = (1 << k) - 2;
+        const uint32_t kl = __shfl_sync(0xffffffffu, key, base + 2 * (int)r);
+        const uint32_t kr = __shfl_sync(0xffffffffu, key, base + 2 * (int)r + 1);
+        const bool left = kr >= kl;                  // comp(first + second, first + (second - 1)): take the left one
+        r = 2u * r + (left ? 0u : 1u);
+        c = 2u * c + (left ? 1u : 2u);
+        depth++;
+        if (lane == depth) { myidx = c; mykey = left ? kl : kr; }
+      }
+    }
+  }
+  if ((len & 1u) == 0u && c == (len - 2u) / 2u) {    // a last parent with a left child only
+    c = 2u * c + 1u;
+    depth++;
+    if (lane == depth) { myidx = c; mykey = H.k[c]; }
+  }
+  // __push_heap(first, hole, top = 0, value) along the same path: the entries at depth 1 .. j move up one level, where
+  // j is the deepest one whose key is strictly smaller than the value's; the value lands at depth j
+  const uint32_t lt = __ballot_sync(0xffffffffu, lane >= 1 && lane <= depth && mykey < vk);
+  const int j = lt ? 31 - __clz((int)lt) : 0;
+  const uint32_t up = __shfl_up_sync(0xffffffffu, myidx, 1);
+  const uint32_t hole = __shfl_sync(0xffffffffu, myidx, j);
+  uint32_t pv = 0, ps = 0;
+  const bool mover = lane >= 1 && lane <= j;
+  if (mover) { pv = H.v[myidx]; ps = H.s[myidx]; }
+  __syncwarp();
+  if (mover) { H.k[up] = mykey; H.v[up] = pv; H.s[up] = ps; }
+  if (lane == 0) { H.k[hole] = vk; H.v[hole] = vv; H.s[hole] = vs; }
+  __syncwarp();
+}
+
+// Returns the number of voxels invalidated; S.n_proc = 1 when the heap outgrew both its region and the spill arena.
+__device__ __noinline__ uint32_t invalidate_strict(const Arena& A, const LabelDesc& L, const Pools& P, uint32_t job,
+                                                   const uint32_t* seeds, uint32_t n_seeds, float scale, float konst,
+                                                   Shared& S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { S.n_next = 0; S.n_proc = 0; }
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t seg = L.segid;
+    WarpHeap H;
+    bool overflow = false;
+    if (S.heap_cap == 0) {                           // first call for this label: its own region
+      H.cap = (uint32_t)kHeapPerVoxel * L.n_fg + (uint32_t)kHeapSlack;
+      H.k = P.heap + 3ull * ((unsigned long long)kHeapPerVoxel * L.region_off + (unsigned long long)kHeapSlack * job);
+      overflow = (unsigned long long)(H.k + 3ull * H.cap - P.heap) > P.heap_static;   // the caller's buffer is for another batch
+    } else {
+      H.cap = S.heap_cap;
+      H.k = S.heap_k;
+    }
+    H.v = H.k + H.cap;
+    H.s = H.v + H.cap;
+    H.n = 0;
+    uint32_t total = 0;
+    auto grow = [&]() {     // the heap can hold 26 entries per claimed voxel plus the seeds: move it to the spill arena
+      const unsigned long long want = 27ull * L.n_fg + n_seeds + 64ull;
+      if (want <= H.cap || want >= 0x7fffffffull) { overflow = true; return; }
+      unsigned long long at = 0;
+      if (lane == 0) at = atomicAdd(P.heap_bump, 3ull * want);
+      at = __shfl_sync(0xffffffffu, at, 0);
+      if (P.heap_static + at + 3ull * want > P.heap_words) { overflow = true; return; }
+      uint32_t* nk = P.heap + P.heap_static + at;
+      uint32_t* nv = nk + want;
+      uint32_t* ns = nv + want;
+      for (uint32_t i = lane; i < H.n; i += 32) { nk[i] = H.k[i]; nv[i] = H.v[i]; ns[i] = H.s[i]; }
+      __syncwarp();
+      H.k = nk; H.v = nv; H.s = ns; H.cap = (uint32_t)want;
+    };
+    for (uint32_t i = 0; i < n_seeds && !overflow; i++) {           // queue.emplace(0.0, sources[i], sources[i], max_distances[i])
+      if (H.n == H.cap) grow();
+      if (!overflow) heap_push(H, 0u, seeds[i], i, lane);
+    }
+    const int fdx = lane < 26 ? kDX[lane] : 0, fdy = lane < 26 ? kDY[lane] : 0, fdz = lane < 26 ? kDZ[lane] : 0;
+    while (H.n > 0 && !overflow) {
+      uint32_t tk, loc, sd;
+      heap_pop(H, tk, loc, sd, lane);
+      if (__ldcg(&A.claim[loc]) != kValid) continue;                // if (!field[loc]) continue;
+      __syncwarp();
+      if (lane == 0) A.claim[loc] = 0ull;
+      total++;
+      const uint32_t o = seeds[sd];
+      const float r = __fadd_rn(__fmul_rn(scale, __ldg(&A.dbf[o])), konst);
+      int x, y, z, ox, oy, oz;
+      unravel(loc, A.d, x, y, z);
+      unravel(o, A.d, ox, oy, oz);
+      // compute_neighborhood (hpp:60-124): face terms are zero at the volume's border; an edge entry needs both of its
+      // terms, a corner entry only its y and z terms
+      const int tx = fdx < 0 ? (x > 0 ? -1 : 0) : (fdx > 0 ? (x < A.d.sx - 1 ? 1 : 0) : 0);
+      const int ty = fdy < 0 ? (y > 0 ? -1 : 0) : (fdy > 0 ? (y < A.d.sy - 1 ? 1 : 0) : 0);
+      const int tz = fdz < 0 ? (z > 0 ? -1 : 0) : (fdz > 0 ? (z < A.d.sz - 1 ? 1 : 0) : 0);
+      bool ok;
+      if (lane < 6) ok = (tx | ty | tz) != 0;
+      else if (lane < 18) ok = (fdx == 0 || tx != 0) && (fdy == 0 || ty != 0) && (fdz == 0 || tz != 0);
+      else ok = lane < 26 && ty != 0 && tz != 0;
+      bool push = false;
+      uint32_t nb = 0, dbits = 0;
+      if (ok) {
+        const int nx = x + tx, ny = y + ty, nz = z + tz;
+        nb = (uint32_t)((int64_t)loc + (int64_t)tx + (int64_t)ty * A.d.sx + (int64_t)tz * A.d.sxy);
+        if (__ldg(&A.cc[nb]) == seg && __ldcg(&A.claim[nb]) == kValid) {
+          const float a = __fmul_rn(A.wx, (float)(nx - ox)), b = __fmul_rn(A.wy, (float)(ny - oy)),
+                      c = __fmul_rn(A.wz, (float)(nz - oz));
+          const float dd = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));
+          dbits = __float_as_uint(dd);
+          push = dd < r;
+        }
+      }
+      uint32_t m = __ballot_sync(0xffffffffu, push);
+      while (m && !overflow) {                                      // in the reference's neighbour order
+        const int i = __ffs((int)m) - 1;
+        m &= m - 1u;
+        const uint32_t pk = __shfl_sync(0xffffffffu, dbits, i), pvx = __shfl_sync(0xffffffffu, nb, i);
+        if (H.n == H.cap) grow();
+        if (!overflow) heap_push(H, pk, pvx, sd, lane);
+      }
+    }
+    if (lane == 0) { S.n_next = total; S.n_proc = overflow ? 1u : 0u; S.heap_k = H.k; S.heap_cap = H.cap; }
+  }
+  __syncthreads();
+  return S.n_next;
+}
 
 // ---- dijkstra3d.path_from_parents on the parental field held in A.dist (fix_branching=False) ---------
 // parents follow rule T3 (neighbour with the smallest (dist, direction)); the path is returned in
@@ -734,6 +935,7 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
     B2T_GLOBALTIMER(t_start);
     S.bucket = prm.nbuckets - 1;
     S.relax = 0; S.rounds = 0; S.invalidated = 0;
+    S.heap_cap = 0;
     A.pdrf[L.root] = 0.0f;      // parents[root] = 0: the first rail (trace.py:220)
   }
   __syncthreads();
@@ -791,13 +993,15 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
       __syncthreads();
     }
     if (valid > 0) {
-#if B2T_WITH_CLAIM_WINDOW
-      const uint32_t n = prm.claim_window > 0.0f
-                             ? invalidate_window(A, L, pout, len, prm.scale, prm.konst, prm.claim_window, r0, r1, r2, r3, S)
-                             : invalidate(A, L, pout, len, prm.scale, prm.konst, r0, r1, r2, r3, S);
-#else
-      const uint32_t n = invalidate(A, L, pout, len, prm.scale, prm.konst, r0, r1, r2, r3, S);
-#endif
+      uint32_t n;
+      if (prm.inval_mode == B2T_INVALIDATE_STRICT) {
+        n = invalidate_strict(A, L, P, job, pout, len, prm.scale, prm.konst, S);
+        if (S.n_proc) { status = B2T_ERR_CAPACITY; break; }
+      } else if (prm.inval_mode == B2T_INVALIDATE_WINDOW) {
+        n = invalidate_window(A, L, pout, len, prm.scale, prm.konst, prm.claim_window, r0, r1, r2, r3, S);
+      } else {
+        n = invalidate(A, L, pout, len, prm.scale, prm.konst, r0, r1, r2, r3, S);
+      }
       valid -= min(valid, n);
       if (threadIdx.x == 0) S.invalidated += n;
     }
@@ -847,9 +1051,13 @@ __global__ void __launch_bounds__(kThreads, B2T_TRACE_MINB) trace_kernel(Arena A
 //   d_scratch    6 * sum(n_fg) u32;  d_paths: path pool;  d_targets: manual targets (linear indices)
 //   d_out_len / d_out_npaths / d_out_status: n_desc each; d_out_stats: 4 * n_desc; d_work_counter: 1 u32 (zeroed here)
 // =================================================================================================
-#ifndef B2T_HOST_EMU
-bool b2t_claim_window_built() { return B2T_WITH_CLAIM_WINDOW != 0; }
+// Words (u32) of the strict mode's static heap regions for a batch: b2t_trace_batch wants at least this many in d_heap
+// (after the two control words); everything beyond is the spill arena for heaps that outgrow their region.
+B2T_EXPORT uint64_t b2t_trace_heap_words(uint64_t sum_n_fg, uint64_t n_desc) {
+  return 2ull + 3ull * ((uint64_t)kHeapPerVoxel * sum_n_fg + (uint64_t)kHeapSlack * n_desc);
+}
 
+#ifndef B2T_HOST_EMU
 B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,
                                uint32_t* d_stamp, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
                                const void* d_desc, int n_desc, float scale, float konst, float soma_scale,
@@ -857,9 +1065,18 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
                                const uint32_t* d_hist,
                                const uint32_t* d_cursor, uint32_t* d_scratch, uint32_t* d_paths,
                                const uint32_t* d_targets, uint32_t* d_out_len, uint32_t* d_out_npaths,
-                               int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter, void* stream) {
+                               int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter,
+                               int invalidation_mode, float claim_window_voxels, uint32_t* d_heap, uint64_t heap_words,
+                               uint64_t heap_static_words, void* stream) {
   static_assert(sizeof(LabelDesc) == 64, "LabelDesc must stay 16 x 4 bytes (mirrored in kimimaro_b200/engine.py)");
   B2T_REQUIRE(sx > 0 && sy > 0 && sz > 0 && (double)sx * sy * sz < 4294967295.0, "bad volume shape");
+  B2T_REQUIRE(invalidation_mode == B2T_INVALIDATE_ROUNDS || invalidation_mode == B2T_INVALIDATE_WINDOW ||
+              invalidation_mode == B2T_INVALIDATE_STRICT, "b2t_trace_batch: unknown invalidation mode");
+  B2T_REQUIRE(invalidation_mode != B2T_INVALIDATE_WINDOW || claim_window_voxels > 0.0f,
+              "b2t_trace_batch: the window mode needs a positive window");
+  B2T_REQUIRE(invalidation_mode != B2T_INVALIDATE_STRICT ||
+                  (d_heap != nullptr && heap_static_words >= 2 && heap_words >= heap_static_words),
+              "b2t_trace_batch: the strict mode needs a heap buffer (b2t_trace_heap_words)");
   if (n_desc <= 0) return B2T_OK;
   cudaStream_t st = (cudaStream_t)stream;
   Arena A;
@@ -871,14 +1088,19 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
   P.keys = reinterpret_cast<const unsigned long long*>(d_keys); P.hist = d_hist; P.cursor = d_cursor;
   P.scratch = d_scratch; P.paths = d_paths; P.targets = d_targets; P.out_len = d_out_len; P.out_npaths = d_out_npaths;
   P.out_status = d_out_status; P.out_stats = d_out_stats; P.work_counter = d_work_counter;
-  // b2t_set_claim_window: width of the key-ordered invalidation rounds in units of the smallest voxel edge (0 = hop rounds)
+  P.heap = nullptr; P.heap_words = 0; P.heap_static = 0; P.heap_bump = nullptr;
+  if (invalidation_mode == B2T_INVALIDATE_STRICT) {
+    // the caller sized d_heap from the batch (b2t_trace_heap_words); the kernel checks every region against heap_words
+    P.heap_bump = reinterpret_cast<unsigned long long*>(d_heap);
+    P.heap = d_heap + 2;
+    P.heap_words = heap_words - 2;
+    P.heap_static = heap_static_words - 2;
+    B2T_CUDA_TRY(cudaMemsetAsync(d_heap, 0, 2 * sizeof(uint32_t), st));
+  }
+  // width of the key-ordered invalidation rounds: in units of the smallest voxel edge
   const float wmin = wx < wy ? (wx < wz ? wx : wz) : (wy < wz ? wy : wz);
-#if B2T_WITH_CLAIM_WINDOW
-  Params prm{scale, konst, soma_scale, soma_const, nbuckets, n_desc, fix_branching ? 1 : 0, b2t_claim_window() * wmin};
-#else
-  (void)wmin;
-  Params prm{scale, konst, soma_scale, soma_const, nbuckets, n_desc, fix_branching ? 1 : 0};
-#endif
+  Params prm{scale, konst, soma_scale, soma_const, nbuckets, n_desc, fix_branching ? 1 : 0, invalidation_mode,
+             claim_window_voxels * wmin};
   B2T_CUDA_TRY(cudaMemsetAsync(d_work_counter, 0, sizeof(uint32_t), st));
   int dev = 0, sms = 0, per_sm = 0;
   B2T_CUDA_TRY(cudaGetDevice(&dev));

@@ -33,7 +33,8 @@ _lib.declare("b2t_pdrf_and_buckets", [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64
                                       c_vp, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp])
 _lib.declare("b2t_trace_batch", [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32,
                                  c_vp, c_int, c_f32, c_f32, c_f32, c_f32, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp])
+                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_vp, c_u64, c_u64, c_vp])
+_lib.declare("b2t_trace_heap_words", [c_u64, c_u64], c_u64)
 _lib.declare("b2t_ccl26_roots", [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp])
 _lib.declare("b2t_ccl_relabel", [c_vp, c_vp, c_u64, c_vp])
 _lib.declare("b2t_invalidate_ball", [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_u32, c_f32, c_f32,
@@ -257,7 +258,7 @@ def compute_M_array(dbf_max):
     return np.array([np.float32(1 / (d ** 1.01)) for d in np.asarray(dbf_max, dtype=np.float32)], dtype=np.float32)
 
 
-def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=None):
+def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=None, pool_scale=1):
   """
   Everything up to and including the (asynchronous) launch of the path-loop kernel; returns the state that
   trace_arena_finish() needs.  jobs: a Jobs table.  n_rows: rows of the (label x bucket) tables minus one (= max cc id in this arena).
@@ -365,7 +366,12 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
       o = starts[slot_of[i]] + tb_n_eff[i]
       targets[o:o + len(lst)] = lst
   nfg = desc["n_fg"].astype(np.int64)
-  caps = 2 * nfg + 2 * cnt + 64
+  # Path pool.  fix_branching=True: every path voxel but the rail end is new to the rail, so sum(len - 1) <= n_fg, and a
+  # label has at most n_fg + (manual targets) paths of len + 1 slots each: 3 * n_fg + 2 * cnt bounds the pool.
+  # fix_branching=False: path_from_parents writes the whole root -> target walk for every target (about tips x depth);
+  # no bound short of n_fg^2 exists, so the pool starts at the same size and labels that report B2T_ERR_CAPACITY are
+  # traced again with a larger one (trace_arena_finish).
+  caps = (3 * nfg + 2 * cnt + 64) * int(pool_scale)
   desc["region_off"] = np.concatenate(([0], np.cumsum(nfg)[:-1]))
   desc["path_off"] = np.concatenate(([0], np.cumsum(caps)[:-1]))
   desc["path_cap"] = caps
@@ -373,7 +379,8 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   desc["bucket_row"] = desc["segid"]
   region = int(nfg.sum())
   path_off = int(caps.sum())
-  assert path_off < 2 ** 32 and 6 * region < 2 ** 34
+  if path_off >= 2 ** 32 or 6 * region >= 2 ** 34:
+    raise B2TError(f"arena too large for 32-bit pool offsets: path pool {path_off} slots, {region} foreground voxels")
   scratch = torch.empty(6 * max(region, 1), dtype=torch.int32, device=dev)
   # soma labels: the one-off ball around the root (trace.py:160-168) is far too large for one CTA
   for slot in np.flatnonzero(desc["soma_mode"]).tolist():
@@ -398,17 +405,42 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   out_stats = torch.zeros(4 * n_jobs, dtype=torch.int32, device=dev)
   counter = torch.zeros(1, dtype=torch.int32, device=dev)
   ws.stamp.zero_()
-  check(L.b2t_trace_batch(_p(d_cc), _p(d_dbf), _p(pdrf), _p(ws.dist), _p(claim), _p(ws.stamp), c_i64(sx), c_i64(sy),
-                          c_i64(sz), c_f32(anisotropy[0]), c_f32(anisotropy[1]), c_f32(anisotropy[2]), _p(d_desc),
+  launch = dict(d_cc=d_cc, d_dbf=d_dbf, pdrf=pdrf, ws=ws, claim=claim, shape=shape, anisotropy=anisotropy, params=params,
+                fix_branching=fix_branching, keys=keys, hist=hist, cursor=cursor, scratch=scratch, d_targets=d_targets)
+  heap = _launch_trace(launch, d_desc, n_jobs, int(nfg.sum()), int(nfg.max()) if n_jobs else 0, paths, out_len, out_np,
+                       out_status, out_stats, counter)
+  keep = (ws, pdrf, claim, keys, hist, cursor, scratch, d_desc, d_targets, counter, heap)   # alive until the kernel is done
+  return dict(desc=desc, paths=paths, out_len=out_len, out_np=out_np, out_status=out_status, out_stats=out_stats,
+              d_dbf=d_dbf, n_jobs=n_jobs, timings=timings, tmark=tmark, keep=keep,
+              again=(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings), pool_scale=int(pool_scale))
+
+
+def _launch_trace(la, d_desc, n_jobs, sum_nfg, max_nfg, paths, out_len, out_np, out_status, out_stats, counter):
+  """b2t_trace_batch with the invalidation mode of _lib.invalidation_mode(); returns the strict mode's heap buffer."""
+  L = lib()
+  mode, window = _lib.invalidation_mode()
+  heap, heap_words, heap_static = None, 0, 0
+  if mode == "strict":
+    # static regions (4 entries per voxel) + a spill arena that can take the 27-entries-per-voxel worst case of the
+    # largest label and a few dozen average ones besides
+    heap_static = int(L.b2t_trace_heap_words(c_u64(sum_nfg), c_u64(n_jobs)))
+    spill = 3 * (27 * max_nfg + 2 * max_nfg + 64) + 3 * 27 * min(sum_nfg, 8 * 2 ** 20)
+    heap_words = heap_static + spill
+    heap = torch.empty(heap_words, dtype=torch.int32, device=paths.device)
+  sx, sy, sz = la["shape"]
+  an, params = la["anisotropy"], la["params"]
+  check(L.b2t_trace_batch(_p(la["d_cc"]), _p(la["d_dbf"]), _p(la["pdrf"]), _p(la["ws"].dist), _p(la["claim"]),
+                          _p(la["ws"].stamp), c_i64(sx), c_i64(sy),
+                          c_i64(sz), c_f32(an[0]), c_f32(an[1]), c_f32(an[2]), _p(d_desc),
                           c_int(n_jobs), c_f32(params["scale"]), c_f32(params["const"]),
                           c_f32(params["soma_invalidation_scale"]), c_f32(params["soma_invalidation_const"]),
-                          c_int(1 if fix_branching else 0), c_int(NBUCKETS), _p(keys), _p(hist), _p(cursor), _p(scratch),
-                          _p(paths), _p(d_targets),
-                          _p(out_len), _p(out_np), _p(out_status), _p(out_stats), _p(counter), stream_ptr()),
+                          c_int(1 if la["fix_branching"] else 0), c_int(NBUCKETS), _p(la["keys"]), _p(la["hist"]),
+                          _p(la["cursor"]), _p(la["scratch"]), _p(paths), _p(la["d_targets"]),
+                          _p(out_len), _p(out_np), _p(out_status), _p(out_stats), _p(counter),
+                          c_int(_lib._MODES[mode]), c_f32(window), _p(heap), c_u64(heap_words), c_u64(heap_static),
+                          stream_ptr()),
         "b2t_trace_batch")
-  keep = (ws, pdrf, claim, keys, hist, cursor, scratch, d_desc, d_targets, counter)   # alive until the kernel is done
-  return dict(desc=desc, paths=paths, out_len=out_len, out_np=out_np, out_status=out_status, out_stats=out_stats,
-              d_dbf=d_dbf, n_jobs=n_jobs, timings=timings, tmark=tmark, keep=keep)
+  return heap
 
 
 def trace_arena_finish(st):
@@ -431,7 +463,16 @@ def trace_arena_finish(st):
   lap("paths")
   if (h_status != 0).any():
     bad = int(np.flatnonzero(h_status != 0)[0])
-    raise B2TError(f"trace kernel reported status {int(h_status[bad])} for cc label {int(desc[bad]['segid'])}")
+    params = st["again"][5]
+    if (h_status[h_status != 0] == -4).all() and not params.get("fix_branching", True) and st["pool_scale"] < 4096:
+      # fix_branching=False: root -> target walks outgrew the path pool (no a-priori bound, see trace_arena_start);
+      # trace the arena again with a pool 8x the size.  Roots are already in the job table.
+      st["keep"] = None
+      st["paths"] = None
+      return trace_arena_finish(trace_arena_start(*st["again"], pool_scale=8 * st["pool_scale"]))
+    what = ("a buffer was too small (B2T_ERR_CAPACITY: path pool, or the strict mode's heap arena)"
+            if int(h_status[bad]) == -4 else "an internal error")
+    raise B2TError(f"trace kernel reported status {int(h_status[bad])} for cc label {int(desc[bad]['segid'])}: {what}")
   seg_off = np.zeros(n_jobs + 1, dtype=np.int64)
   np.cumsum(h_len, out=seg_off[1:])
   total = int(seg_off[-1])

@@ -541,14 +541,17 @@ static void r_adjust_heap(rnode* first, int64_t hole, int64_t len, rnode value) 
   r_push_heap(first, hole, top, value);
 }
 
+/* statistics of the last orc_invalidate_heap call: peak heap size, pushes (sizing study for the engine's strict mode) */
+ORC_API int64_t orc_heap_stats[2] = {0, 0};
 ORC_API int64_t orc_invalidate_heap(uint8_t* mask, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
                                     const int64_t* seeds, const float* radii, int64_t n_seeds) {
   const int64_t sxy = sx * sy;
-  int64_t cap = 4096, n = 0;
+  int64_t cap = 4096, n = 0, peak = 0, pushes = 0;
   rnode* a = (rnode*)malloc(sizeof(rnode) * cap);
 #define HPUSH(D, O, VV, M) do { \
     if (n == cap) { cap *= 2; a = (rnode*)realloc(a, sizeof(rnode) * cap); } \
-    rnode xx = {(D), (O), (VV), (M)}; a[n++] = xx; r_push_heap(a, n - 1, 0, xx); } while (0)
+    rnode xx = {(D), (O), (VV), (M)}; a[n++] = xx; r_push_heap(a, n - 1, 0, xx); \
+    pushes++; if (n > peak) peak = n; } while (0)
   for (int64_t i = 0; i < n_seeds; i++) HPUSH(0.0f, seeds[i], seeds[i], radii[i]);
   int64_t invalidated = 0;
   while (n > 0) {
@@ -589,6 +592,7 @@ ORC_API int64_t orc_invalidate_heap(uint8_t* mask, int64_t sx, int64_t sy, int64
   }
 #undef HPUSH
   free(a);
+  orc_heap_stats[0] = peak; orc_heap_stats[1] = pushes;
   return invalidated;
 }
 

@@ -30,10 +30,11 @@ DEFAULT_TEASAR_PARAMS = {          # intake.py:47-56
 }
 
 # The claim order of roll_invalidation_ball_inside_component that the oracle runs when none is asked for: the ENGINE's
-# ("rounds": hop-synchronous; "window:1": ordered by the reference's heap key in windows of one voxel, the order the
-# claim_window build of the library runs).  "heap" is the reference's own order (== its compiled extension) and "seq" the
-# ordered process with canonical ties; see DESIGN.md 4.  tests/golden holds one set of vectors per engine order.
-DEFAULT_INVALIDATION_MODE = "rounds"
+# default ("window:1": rounds ordered by the reference's heap key in windows of one voxel).  "heap" is the reference's own
+# order (== its compiled extension voxel for voxel; the engine's strict mode), "rounds" the hop-synchronous order of
+# round 1 and "seq" the ordered process with canonical ties; see DESIGN.md 4.  tests/golden holds one set of vectors
+# per engine order.
+DEFAULT_INVALIDATION_MODE = "window:1"
 
 
 class DimensionError(Exception):

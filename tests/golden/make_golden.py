@@ -16,7 +16,8 @@ cases = {"sphere": (sphere(64, 24), {}),
          "tubes": (synthetic_tubes((96, 96, 64), 12, seed=1), {"anisotropy": (16, 16, 40), "dust_threshold": 100})}
 # one file per claim order the engine can run (oracle/teasar.py: DEFAULT_INVALIDATION_MODE names the current one);
 # tests/golden_name() picks the file
-for mode, fname in (("rounds", "golden_v1.npz"), ("window:1", "golden_v1_window1.npz")):
+# "heap" = the reference's own order (the engine's strict mode)
+for mode, fname in (("rounds", "golden_v1.npz"), ("window:1", "golden_v1_window1.npz"), ("heap", "golden_v1_heap.npz")):
   out = {}
   for name, (lab, kw) in cases.items():
     sk = teasar.skeletonize(lab, invalidation_mode=mode, **kw)

@@ -19,7 +19,6 @@ EMU_EXPORT const char* b2t_last_error(void) { return emu_last_error(); }
 EMU_EXPORT int b2t_device_check(void) { return 0; }
 EMU_EXPORT unsigned long long b2t_launch_count(int) { return 1; }
 EMU_EXPORT int b2t_set_launch_limits(int, int) { return 0; }
-EMU_EXPORT int b2t_set_claim_window(float voxels) { g_emu_claim_window = voxels > 0.0f ? voxels : 0.0f; return 0; }
 EMU_EXPORT int b2t_edt_config(int, int, int, int, int) { return 0; }
 EMU_EXPORT int b2t_edt_config_hybrid(int, int, int, int, int, int) { return 0; }
 EMU_EXPORT int b2t_edt_config_roles(int, int, float) { return 0; }

@@ -1,6 +1,8 @@
 // Test infrastructure, never shipped: a stand-in for <cuda_runtime.h> that lets g++ compile the DEVICE functions of
-// kimimaro_b200/csrc/*.cu for the CPU.  One CUDA block is emulated at a time with one OS thread per CUDA thread:
-//   __syncthreads                      -> a barrier over the block's threads
+// kimimaro_b200/csrc/*.cu for the CPU.  One CUDA block is emulated at a time with one FIBER per CUDA thread, all on the
+// calling OS thread and switched cooperatively at the synchronisation points (simt_impl.h: a 20-instruction context
+// switch, ~100x faster than OS threads meeting in pthread barriers, and deterministic):
+//   __syncthreads                      -> a barrier over the block's fibers
 //   __ballot_sync / __shfl*_sync       -> an exchange buffer and a barrier per warp (all 32 lanes must take part, which
 //                                         is also what the full masks in the sources promise)
 //   atomics                            -> GCC __atomic builtins (atomicMin by compare-and-swap)
@@ -35,24 +37,31 @@ static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 
 namespace simt {
 constexpr int kMaxThreads = 1024;
+struct Fiber;
+struct Barrier {
+  int expected = 0, arrived = 0;
+  Fiber* head = nullptr;   // fibers parked here until the last one arrives
+  Fiber* tail = nullptr;
+};
 struct Warp {
-  pthread_barrier_t bar;
+  Barrier bar;
   unsigned long long v[32];
 };
 struct Block {
-  pthread_barrier_t bar;
+  Barrier bar;
   Warp warps[kMaxThreads / 32];
   int n_threads = 0;
 };
 extern Block g_block;
+void barrier_wait(Barrier& b);
 }  // namespace simt
 
 extern thread_local uint3 threadIdx;
 extern thread_local uint3 blockIdx;
 extern uint3 blockDim, gridDim;
 
-static inline void __syncthreads() { pthread_barrier_wait(&simt::g_block.bar); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&simt::g_block.warps[threadIdx.x >> 5].bar); }
+static inline void __syncthreads() { simt::barrier_wait(simt::g_block.bar); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { simt::barrier_wait(simt::g_block.warps[threadIdx.x >> 5].bar); }
 static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
@@ -64,9 +73,9 @@ template <typename T, typename F> inline T exchange(T mine, F pick) {
   Warp& w = g_block.warps[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   w.v[lane] = to_bits(mine);
-  pthread_barrier_wait(&w.bar);
+  barrier_wait(w.bar);
   const T r = from_bits<T>(w.v[pick(lane) & 31]);
-  pthread_barrier_wait(&w.bar);
+  barrier_wait(w.bar);
   return r;
 }
 }  // namespace simt
@@ -75,10 +84,10 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   simt::Warp& w = simt::g_block.warps[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   w.v[lane] = pred ? 1ull : 0ull;
-  pthread_barrier_wait(&w.bar);
+  simt::barrier_wait(w.bar);
   unsigned m = 0;
   for (int l = 0; l < 32; l++) m |= (unsigned)(w.v[l] & 1ull) << l;
-  pthread_barrier_wait(&w.bar);
+  simt::barrier_wait(w.bar);
   return m;
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
@@ -155,7 +164,7 @@ static inline long long min(long long a, long long b) { return a < b ? a : b; }
 static inline long long max(long long a, long long b) { return a > b ? a : b; }
 
 namespace simt {
-// run fn(thread index) on n_threads OS threads as ONE block (threadIdx.x = 0 .. n_threads-1, blockIdx.x = block)
+// run fn(arg) on n_threads fibers as ONE block (threadIdx.x = 0 .. n_threads-1, blockIdx.x = block)
 void run_block(int n_threads, unsigned block, unsigned grid, void (*fn)(void*), void* arg);
 
 // kernels WITHOUT block-level synchronisation: a launch is a loop over blocks and threads on the calling thread (one
@@ -176,7 +185,7 @@ template <typename F> struct SeqLaunch {
 };
 template <typename F> SeqLaunch<F> seq_launch(unsigned long long g, unsigned b, F f) { return SeqLaunch<F>{(unsigned)g, b, f}; }
 
-// kernels WITH block-level synchronisation: every block, one after the other, on b OS threads
+// kernels WITH block-level synchronisation: every block, one after the other, on b fibers
 template <typename F> struct BlockLaunch {
   unsigned g, b;
   F f;

@@ -1,9 +1,12 @@
 // Test infrastructure, never shipped: the device functions of kimimaro_b200/csrc/trace.cu compiled for the CPU
 // against the SIMT emulation of emu_include/cuda_runtime.h, so that tests/test_trace_emu_cpu.py can run the engine's
-// invalidation -- the hop-synchronous one it ships and the key-ordered one of the claim_window variant -- on the very
-// source text the GPU runs and compare it with the oracle (orc_invalidate_rounds / orc_invalidate_window).
+// invalidation -- key-ordered rounds (the default), the literal heap of the strict mode and the hop-synchronous rounds --
+// on the very source text the GPU runs and compare it with the oracle (orc_invalidate_window / _heap / _rounds).
 #define B2T_HOST_EMU 1
-#define B2T_WITH_CLAIM_WINDOW 1
+#ifndef B2T_EMU_COMBINED        /* the stand-alone harness shrinks the strict heap's own region so that small labels spill */
+#define B2T_HEAP_PER_VOXEL 1
+#define B2T_HEAP_SLACK 64
+#endif
 #ifdef B2T_EMU_COMBINED
 #include <cuda_runtime.h>
 #else
@@ -14,25 +17,33 @@
 
 namespace {
 struct InvArgs {
-  Arena A; LabelDesc L; const uint32_t* seeds; uint32_t n_seeds; float scale, konst, delta;
-  uint32_t *r0, *r1, *r2, *r3; int mode; uint32_t result;
+  Arena A; LabelDesc L; Pools P; const uint32_t* seeds; uint32_t n_seeds; float scale, konst, delta;
+  uint32_t *r0, *r1, *r2, *r3; int mode; uint32_t result; uint32_t overflow;
 };
 Shared g_S;
 void inv_thread(void* p) {
   InvArgs* a = (InvArgs*)p;
-  const uint32_t n = a->mode ? invalidate_window(a->A, a->L, a->seeds, a->n_seeds, a->scale, a->konst, a->delta, a->r0, a->r1,
-                                                 a->r2, a->r3, g_S)
-                             : invalidate(a->A, a->L, a->seeds, a->n_seeds, a->scale, a->konst, a->r0, a->r1, a->r2, a->r3, g_S);
+  uint32_t n;
+  if (a->mode == B2T_INVALIDATE_STRICT) {
+    n = invalidate_strict(a->A, a->L, a->P, 0, a->seeds, a->n_seeds, a->scale, a->konst, g_S);
+    if (threadIdx.x == 0) a->overflow = g_S.n_proc;
+  } else if (a->mode == B2T_INVALIDATE_WINDOW) {
+    n = invalidate_window(a->A, a->L, a->seeds, a->n_seeds, a->scale, a->konst, a->delta, a->r0, a->r1, a->r2, a->r3, g_S);
+  } else {
+    n = invalidate(a->A, a->L, a->seeds, a->n_seeds, a->scale, a->konst, a->r0, a->r1, a->r2, a->r3, g_S);
+  }
   if (threadIdx.x == 0) a->result = n;
 }
 }  // namespace
 
 // One block of the engine's 512 threads runs roll_invalidation_ball_inside_component on a label of the dense arena.
 // claim: one 64-bit word per voxel, ~0 = valid (the engine's kValid), 0 = invalid; edited in place.
-// mode 0: invalidate (hop rounds); 1: invalidate_window with `delta` (already in physical units).
+// mode: B2T_INVALIDATE_ROUNDS (hop rounds), _WINDOW (invalidate_window with `delta`, already in physical units), _STRICT
+// (the literal heap; spill_words = size of the spill arena behind the label's own heap region, so that a test can make
+// the heap outgrow its region).  Returns -4 (B2T_ERR_CAPACITY) when the strict heap fits nowhere.
 extern "C" long emu_invalidate(const uint32_t* cc, const float* dbf, unsigned long long* claim, int sx, int sy, int sz,
                                float wx, float wy, float wz, uint32_t segid, uint32_t n_fg, const uint32_t* seeds,
-                               uint32_t n_seeds, float scale, float konst, float delta, int mode) {
+                               uint32_t n_seeds, float scale, float konst, float delta, int mode, long spill_words) {
   InvArgs a;
   memset(&a, 0, sizeof(a));
   a.A.cc = cc; a.A.dbf = dbf; a.A.claim = claim;
@@ -42,14 +53,23 @@ extern "C" long emu_invalidate(const uint32_t* cc, const float* dbf, unsigned lo
   a.seeds = seeds; a.n_seeds = n_seeds; a.scale = scale; a.konst = konst; a.delta = delta; a.mode = mode;
   uint32_t* scratch = (uint32_t*)malloc(sizeof(uint32_t) * 4 * (size_t)(n_fg + 1));
   a.r0 = scratch; a.r1 = scratch + n_fg; a.r2 = scratch + 2 * (size_t)n_fg; a.r3 = scratch + 3 * (size_t)n_fg;
+  unsigned long long bump = 0;
+  uint32_t* heap = nullptr;
+  g_S.heap_cap = 0;
+  if (mode == B2T_INVALIDATE_STRICT) {
+    const uint64_t stat = b2t_trace_heap_words(n_fg, 1) - 2;
+    heap = (uint32_t*)malloc(sizeof(uint32_t) * (stat + (uint64_t)spill_words));
+    a.P.heap = heap; a.P.heap_static = stat; a.P.heap_words = stat + (uint64_t)spill_words; a.P.heap_bump = &bump;
+  }
   simt::run_block(kThreads, 0, 1, inv_thread, &a);
   free(scratch);
-  return (long)a.result;
+  free(heap);
+  return a.overflow ? -4L : (long)a.result;
 }
 
 // The whole path loop (trace_kernel: find_target -> railroad -> invalidate -> rail, trace.py:196-267) for a batch of
 // labels on ONE emulated block, which pulls the labels one after another from the work counter like a CTA on the GPU.
-// Arguments as b2t_trace_batch (host arrays instead of device arrays); claim_window in physical units, 0 = hop rounds.
+// Arguments as b2t_trace_batch (host arrays instead of device arrays); claim_window in physical units.
 namespace {
 struct KArgs { Arena A; const LabelDesc* descs; Pools P; Params prm; };
 void kernel_thread(void* p) {
@@ -64,7 +84,8 @@ extern "C" int emu_trace_batch(const uint32_t* cc, const float* dbf, float* pdrf
                                int nbuckets, const unsigned long long* keys, const uint32_t* hist, const uint32_t* cursor,
                                uint32_t* scratch, uint32_t* paths, const uint32_t* targets, uint32_t* out_len,
                                uint32_t* out_npaths, int32_t* out_status, uint32_t* out_stats, uint32_t* work_counter,
-                               float claim_window) {
+                               int inval_mode, float claim_window, uint32_t* heap, uint64_t heap_words,
+                               uint64_t heap_static_words) {
   static_assert(sizeof(LabelDesc) == 64, "LabelDesc layout");
   KArgs k;
   memset(&k, 0, sizeof(k));
@@ -75,7 +96,12 @@ extern "C" int emu_trace_batch(const uint32_t* cc, const float* dbf, float* pdrf
   k.P.keys = keys; k.P.hist = hist; k.P.cursor = cursor; k.P.scratch = scratch; k.P.paths = paths; k.P.targets = targets;
   k.P.out_len = out_len; k.P.out_npaths = out_npaths; k.P.out_status = out_status; k.P.out_stats = out_stats;
   k.P.work_counter = work_counter;
-  k.prm = Params{scale, konst, soma_scale, soma_const, nbuckets, n_desc, fix_branching ? 1 : 0, claim_window};
+  k.prm = Params{scale, konst, soma_scale, soma_const, nbuckets, n_desc, fix_branching ? 1 : 0, inval_mode, claim_window};
+  unsigned long long bump = 0;
+  if (inval_mode == B2T_INVALIDATE_STRICT) {
+    if (!heap || heap_static_words < 2 || heap_words < heap_static_words) return -1;
+    k.P.heap = heap + 2; k.P.heap_words = heap_words - 2; k.P.heap_static = heap_static_words - 2; k.P.heap_bump = &bump;
+  }
   *work_counter = 0;
   simt::run_block(kThreads, 0, 1, kernel_thread, &k);
   return 0;
@@ -88,12 +114,14 @@ extern "C" __attribute__((visibility("default"))) int b2t_trace_batch(
     int64_t sy, int64_t sz, float wx, float wy, float wz, const void* d_desc, int n_desc, float scale, float konst,
     float soma_scale, float soma_const, int fix_branching, int nbuckets, const uint64_t* d_keys, const uint32_t* d_hist,
     const uint32_t* d_cursor, uint32_t* d_scratch, uint32_t* d_paths, const uint32_t* d_targets, uint32_t* d_out_len,
-    uint32_t* d_out_npaths, int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter, void*) {
+    uint32_t* d_out_npaths, int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter, int invalidation_mode,
+    float claim_window_voxels, uint32_t* d_heap, uint64_t heap_words, uint64_t heap_static_words, void*) {
   if (n_desc <= 0) return 0;
   const float wmin = wx < wy ? (wx < wz ? wx : wz) : (wy < wz ? wy : wz);
   return emu_trace_batch(d_cc, d_dbf, d_pdrf, d_dist, (unsigned long long*)d_claim, d_stamp, (int)sx, (int)sy, (int)sz, wx, wy,
                          wz, d_desc, n_desc, scale, konst, soma_scale, soma_const, fix_branching, nbuckets,
                          (const unsigned long long*)d_keys, d_hist, d_cursor, d_scratch, d_paths, d_targets, d_out_len,
-                         d_out_npaths, d_out_status, d_out_stats, d_work_counter, b2t_claim_window() * wmin);
+                         d_out_npaths, d_out_status, d_out_stats, d_work_counter, invalidation_mode,
+                         claim_window_voxels * wmin, d_heap, heap_words, heap_static_words);
 }
 #endif

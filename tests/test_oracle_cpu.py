@@ -108,7 +108,9 @@ def test_invalidation_vs_reference_ext(orc, ref_ext):
       b = vol.copy(order="F")
       nb, b = orc.roll_invalidation_ball_inside_component(b, dbf, scale, const, an, path, mode=mode)
       assert nb == int(vol.sum() - b.sum())
-      assert not np.any((a == 0) & (b != 0) & False)
+      assert np.all(b <= vol) and np.all(a <= vol)              # voxels are only ever cleared
+      pi = tuple(np.asarray(path).T)
+      assert not b[pi].any() and not np.asarray(a)[pi].any()    # every seed ends up invalid in every claim order
       diff = int((a != b).sum())
       same[mode] += diff == 0
       vox_diff[mode] += diff
@@ -231,7 +233,7 @@ def test_reference_fix_borders(orc):
 
 
 # ---- golden fixtures (tests/golden, generated by tests/golden/make_golden.py) ----
-@pytest.mark.parametrize("mode", ["rounds", "window:1"])
+@pytest.mark.parametrize("mode", ["rounds", "window:1", "heap"])
 def test_golden_fixtures(orc, mode, monkeypatch):
   """One set of vectors per claim order the engine can run; the one oracle.teasar.DEFAULT_INVALIDATION_MODE names is the
   set the CUDA tests use (tests/conftest.py: golden_name)."""

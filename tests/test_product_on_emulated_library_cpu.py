@@ -122,21 +122,42 @@ def test_fill_holes_and_fix_avocados(product):
   _compare(product.skeletonize(labels, progress=False, **kw), teasar.skeletonize(labels, **kw))
 
 
-def test_key_ordered_claim_end_to_end(product):
-  """The claim_window variant of the library (trace.cu: invalidate_window, off in the shipped build) through the whole
-  product against the oracle's mode 'window:1' -- and against the hop-synchronous default to see that it matters."""
+def test_claim_orders_end_to_end(product):
+  """The three claim orders of the path loop (b2t_trace_batch: invalidation_mode) through the whole product: the default
+  (key-ordered rounds of one voxel) against oracle mode 'window:1', the strict mode against oracle mode 'heap' -- which
+  is the reference's compiled extension voxel for voxel -- and the hop-synchronous rounds against 'rounds'."""
   from kimimaro_b200 import _lib
   from oracle import teasar
   from tests.synth import synthetic_tubes
   labels = synthetic_tubes((56, 48, 40), 6, seed=9)
   kw = dict(anisotropy=(16, 16, 40), dust_threshold=100, teasar_params=dict(product.DEFAULT_TEASAR_PARAMS, scale=1.5, const=30))
+  assert _lib.invalidation_mode() == ("window", 1.0)
+  _compare(product.skeletonize(labels, progress=False, **kw), teasar.skeletonize(labels, invalidation_mode="window:1", **kw))
   try:
-    _lib.check(_lib.lib().b2t_set_claim_window(_lib.c_f32(1.0)))
-    res = product.skeletonize(labels, progress=False, **kw)
+    for mode, omode in (("strict", "heap"), ("rounds", "rounds")):
+      _lib.set_invalidation_mode(mode)
+      _compare(product.skeletonize(labels, progress=False, **kw), teasar.skeletonize(labels, invalidation_mode=omode, **kw))
   finally:
-    _lib.check(_lib.lib().b2t_set_claim_window(_lib.c_f32(0.0)))
-  _compare(res, teasar.skeletonize(labels, invalidation_mode="window:1", **kw))
-  _compare(product.skeletonize(labels, progress=False, **kw), teasar.skeletonize(labels, invalidation_mode="rounds", **kw))
+    _lib.set_invalidation_mode("window", 1.0)
+
+
+def test_path_pool_bounds(product):
+  """(a) fix_branching=True with small radii on a slab: every voxel is its own path, 3 slots each -- the
+  pool bound is 3 * n_fg + 2 * targets; (b) fix_branching=False on a comb: every tooth's path is the whole root -> tip
+  walk, far beyond any multiple of n_fg that is affordable up front -- the arena is traced again with a larger pool."""
+  from oracle import teasar
+  slab = np.zeros((38, 38, 6), np.uint8, order="F")
+  slab[1:37, 1:37, 1:5] = 1
+  for tp in (dict(scale=0.5, const=0), dict(scale=0, const=1)):
+    kw = dict(dust_threshold=10, teasar_params=dict(product.DEFAULT_TEASAR_PARAMS, **tp))
+    _compare(product.skeletonize(slab, progress=False, **kw), teasar.skeletonize(slab, **kw))
+  comb = np.zeros((120, 44, 3), np.uint8, order="F")
+  comb[1:119, 1:3, 1] = 1                                             # the spine
+  for x in range(2, 118, 2):
+    comb[x, 3:42, 1] = 1                                              # 58 one-voxel-thin teeth
+  kw = dict(dust_threshold=10, fix_branching=False, fix_borders=False,
+            teasar_params=dict(product.DEFAULT_TEASAR_PARAMS, scale=1.5, const=2))
+  _compare(product.skeletonize(comb, progress=False, **kw), teasar.skeletonize(comb, **kw))
 
 
 def test_more_of_the_api(product):

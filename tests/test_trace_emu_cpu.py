@@ -1,9 +1,10 @@
-"""The engine's invalidation (kimimaro_b200/csrc/trace.cu: invalidate, invalidate_window) on the CPU: the device
-functions are compiled by g++ against a SIMT emulation (tests/host/emu_include/cuda_runtime.h: one OS thread per CUDA
-thread of a 512-thread block, barriers for __syncthreads and the warp intrinsics) and must reproduce the oracle's
-restatement of the same claim order voxel for voxel -- the hop-synchronous rounds the shipped kernel runs
-(orc_invalidate_rounds) and the key-ordered rounds of the claim_window variant (orc_invalidate_window).  This is the
-check the key-ordered kernel gets before its first GPU run."""
+"""The engine's invalidation (kimimaro_b200/csrc/trace.cu: invalidate_window, invalidate_strict, invalidate) on the CPU:
+the device functions are compiled by g++ against a SIMT emulation (tests/host/emu_include/cuda_runtime.h: one OS thread
+per CUDA thread of a 512-thread block, barriers for __syncthreads and the warp intrinsics) and must reproduce the
+oracle's restatement of the same claim order voxel for voxel -- the key-ordered rounds the engine runs by default
+(orc_invalidate_window), the literal heap of the strict mode (orc_invalidate_heap, which is the reference's compiled
+extension voxel for voxel: test_oracle_cpu.py::test_invalidation_vs_reference_ext) and the hop-synchronous rounds
+(orc_invalidate_rounds)."""
 import ctypes
 import os
 import subprocess
@@ -33,7 +34,10 @@ def emu():
   return lib
 
 
-def _engine(lib, vol, dbf, path, scale, const, an, window):
+ROUNDS, WINDOW, STRICT = 0, 1, 2
+
+
+def _engine(lib, vol, dbf, path, scale, const, an, window, mode=None, spill_words=0):
   sx, sy, sz = vol.shape
   cc = np.ascontiguousarray(vol.reshape(-1, order="F").astype(np.uint32))
   d = np.ascontiguousarray(dbf.reshape(-1, order="F").astype(np.float32))
@@ -41,9 +45,12 @@ def _engine(lib, vol, dbf, path, scale, const, an, window):
   p = np.asarray(path, dtype=np.int64).reshape(-1, 3)
   seeds = np.ascontiguousarray((p[:, 0] + sx * (p[:, 1] + sy * p[:, 2])).astype(np.uint32))
   delta = np.float32(window * min(an)) if window else np.float32(0)
+  if mode is None:
+    mode = WINDOW if window else ROUNDS
   n = lib.emu_invalidate(oracle._p(cc), oracle._p(d), oracle._p(claim), sx, sy, sz, ctypes.c_float(an[0]),
                          ctypes.c_float(an[1]), ctypes.c_float(an[2]), 1, int(vol.sum()), oracle._p(seeds), int(seeds.size),
-                         ctypes.c_float(scale), ctypes.c_float(const), ctypes.c_float(delta), 1 if window else 0)
+                         ctypes.c_float(scale), ctypes.c_float(const), ctypes.c_float(delta), mode,
+                         ctypes.c_long(spill_words))
   mask = ((claim != 0) & (cc == 1)).astype(np.uint8).reshape(vol.shape, order="F")
   return int(n), mask
 
@@ -68,8 +75,54 @@ def test_engine_invalidation_equals_oracle(emu, window):
     assert np.array_equal(mask, ref), (trial, int((mask != ref).sum()))
 
 
+def test_engine_strict_invalidation_equals_the_literal_heap(emu, ref_ext):
+  """invalidate_strict (one warp emulating std::priority_queue with libstdc++'s push_heap / pop_heap and the reference's
+  `>=` comparator) against the oracle's literal form AND, when it is built, against the reference's own compiled
+  extension: the same voxels, not merely the same count -- on shapes where tie order decides (isotropic grids, seeds at
+  equal distances, volumes whose x extent puts path voxels on the x faces where the corner entries alias)."""
+  rng = np.random.default_rng(23)
+  for trial in range(8):
+    vol, path = _tube(rng)
+    an = (16.0, 16.0, 40.0) if trial % 2 else (1.0, 1.0, 1.0)
+    if trial >= 6:                                  # crop so that the tube touches the x faces
+      xs = np.flatnonzero(vol.any(axis=(1, 2)))
+      lo, hi = xs[0] + 2, xs[-1] - 1
+      vol = np.asfortranarray(vol[lo:hi])
+      path = [(p[0] - lo, p[1], p[2]) for p in path if lo <= p[0] < hi]
+    dbf = oracle.edt(vol, an, False)
+    scale, const = float(rng.choice([1.0, 1.5, 4.0])), float(rng.choice([0, 1, 3])) * an[0]
+    ref = vol.copy(order="F")
+    n_ref, ref = oracle.roll_invalidation_ball_inside_component(ref, dbf, scale, const, an, path, mode="heap")
+    n, mask = _engine(emu, vol, dbf, path, scale, const, an, 0, mode=STRICT, spill_words=3 * (28 * int(vol.sum()) + 128))
+    assert n == n_ref, (trial, n, n_ref)
+    assert np.array_equal(mask, ref), (trial, int((mask != ref).sum()))
+    if ref_ext is not None:
+      ext = np.asfortranarray(vol.astype(bool))
+      n_ext, ext = ref_ext.roll_invalidation_ball_inside_component(ext, dbf, scale, const, np.asarray(an, np.float32),
+                                                                   [tuple(int(c) for c in p) for p in path])
+      assert n == int(n_ext) and np.array_equal(mask, ext.view(np.uint8)), trial
+
+
+def test_engine_strict_heap_spills_and_reports_capacity(emu):
+  """A fat label whose ball covers it entirely: the heap outgrows the label's own region (4 entries per voxel), moves to
+  the spill arena and the result is still the literal heap's; without a spill arena the call reports B2T_ERR_CAPACITY."""
+  vol = np.zeros((26, 26, 26), np.uint8, order="F")
+  vol[1:25, 1:25, 1:25] = 1
+  an = (1.0, 1.0, 1.0)
+  dbf = oracle.edt(vol, an, False)
+  path = [(12, 12, z) for z in range(4, 21)]
+  ref = vol.copy(order="F")
+  n_ref, ref = oracle.roll_invalidation_ball_inside_component(ref, dbf, 4.0, 10.0, an, path, mode="heap")
+  stats = (ctypes.c_int64 * 2).in_dll(oracle.lib(), "orc_heap_stats")
+  assert stats[0] > int(vol.sum()) + 64, "the case must outgrow the harness's static region (1 per voxel + 64)"
+  n, mask = _engine(emu, vol, dbf, path, 4.0, 10.0, an, 0, mode=STRICT, spill_words=3 * (28 * int(vol.sum()) + 128))
+  assert n == n_ref and np.array_equal(mask, ref)
+  n, _ = _engine(emu, vol, dbf, path, 4.0, 10.0, an, 0, mode=STRICT, spill_words=0)
+  assert n == -4
+
+
 # ---- the whole path loop (trace_kernel) on the emulated block against oracle.teasar.trace ----
-def _emulated_paths(lib, cc, n_cc, all_dbf, an, params, window, fix_borders_targets=None):
+def _emulated_paths(lib, cc, n_cc, all_dbf, an, params, window, fix_borders_targets=None, mode=None):
   """Mirrors kimimaro_b200/engine.py:trace_arena_start for host arrays: per-label root / DAF / PDRF from the oracle's
   pieces (the GPU gets them from field.cu, verified on the GPU), one DAF bucket per label, then trace_kernel."""
   from oracle import teasar
@@ -123,10 +176,16 @@ def _emulated_paths(lib, cc, n_cc, all_dbf, an, params, window, fix_borders_targ
   out_len, out_np, out_status = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.int32)
   out_stats, counter = np.zeros(4 * n, np.uint32), np.zeros(1, np.uint32)
   p, cf = oracle._p, ctypes.c_float
+  if mode is None:
+    mode = WINDOW if window else ROUNDS
+  lib.b2t_trace_heap_words.restype = ctypes.c_uint64
+  heap_static = int(lib.b2t_trace_heap_words(ctypes.c_uint64(region), ctypes.c_uint64(n))) if mode == STRICT else 0
+  heap = np.zeros(heap_static + 3 * 29 * int(sum(hist)) + 256, np.uint32) if mode == STRICT else np.zeros(1, np.uint32)
   lib.emu_trace_batch(p(ccf), p(dbf), p(pdrf), p(dist), p(claim), p(stamp), sx, sy, sz, cf(an[0]), cf(an[1]), cf(an[2]),
                       p(desc), n, cf(params["scale"]), cf(params["const"]), cf(0.5), cf(0.0), 1, 1, p(keys), p(hist),
                       p(cursor), p(scratch), p(paths), p(targets), p(out_len), p(out_np), p(out_status), p(out_stats),
-                      p(counter), cf(window * min(an)))
+                      p(counter), mode, cf(window * min(an)), p(heap), ctypes.c_uint64(heap.size if mode == STRICT else 0),
+                      ctypes.c_uint64(heap_static))
   assert (out_status == 0).all(), out_status
   got = {}
   for i in range(n):
@@ -138,14 +197,19 @@ def _emulated_paths(lib, cc, n_cc, all_dbf, an, params, window, fix_borders_targ
   return got
 
 
-@pytest.mark.parametrize("window", [0, 1.0])
+@pytest.mark.parametrize("window", [0, 1.0, "strict"])
 def test_engine_path_loop_equals_oracle(emu, window):
   """find_target -> railroad -> invalidate -> rail, label after label, on the source text the GPU runs: every path of
-  every label must be the oracle's, voxel for voxel and in the same order, under the shipped hop-synchronous claim
-  (window 0, what the GPU tests check on the device) and under the key-ordered one (window 1, oracle mode 'window:1')."""
+  every label must be the oracle's, voxel for voxel and in the same order, under the key-ordered claim the engine ships
+  (window 1, oracle mode 'window:1'), under the strict mode (oracle mode 'heap' == the compiled reference) and under the
+  hop-synchronous rounds (window 0)."""
   from oracle import teasar
   from tests.synth import synthetic_tubes
-  mode = f"window:{window:g}" if window else "rounds"
+  emode = None
+  if window == "strict":
+    mode, window, emode = "heap", 0, STRICT
+  else:
+    mode = f"window:{window:g}" if window else "rounds"
   params = dict(teasar.DEFAULT_TEASAR_PARAMS)
   params.update(scale=1.5, const=30)                       # small tubes: several paths per label
   n_paths = 0
@@ -156,7 +220,7 @@ def test_engine_path_loop_equals_oracle(emu, window):
     cc = np.asfortranarray(np.where(np.isin(cc, keep), cc, 0))
     cc, n_cc = oracle.connected_components(cc)
     all_dbf = oracle.edt(cc, an, False)
-    got = _emulated_paths(emu, cc, n_cc, all_dbf, an, params, window)
+    got = _emulated_paths(emu, cc, n_cc, all_dbf, an, params, window, mode=emode)
     sx, sy, sz = cc.shape
     for l in range(1, n_cc + 1):
       labels = np.asfortranarray(cc == l)
