@@ -158,9 +158,11 @@ int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist
  *           roll_invalidation_ball_inside_component         pyx:373-418 -> dijkstra_invalidation.hpp:239-332
  *           the soma cull and soma invalidation             kimimaro/trace.py:160-168, 246-251
  *           dijkstra3d.path_from_parents (fix_branching == 0: d_dist must hold the parental field) trace.py:244
- * d_desc: n_desc records of 64 bytes (16 little-endian 32-bit fields):
+ * d_desc: n_desc records of 80 bytes (20 little-endian 32-bit fields):
  *   segid, root, n_fg, region_off, path_off, path_cap, tb_off, tb_n, ta_off, ta_n, max_paths (0xffffffff =
- *   None), soma_mode, soma_radius (float32), bucket_row, soma_done, pre_invalid
+ *   None), soma_mode, soma_radius (float32), bucket_row, soma_done, pre_invalid, bbox_x0, bbox_x1 (x extent of the
+ *   label's bounding box: the reference runs on that crop, intake.py:463-466, and STRICT reproduces the duplicate
+ *   pushes of its neighbour table at the crop's x faces), two reserved words
  * d_scratch: 6*sum(n_fg) u32; d_paths: pool of voxel indices, each path [rail ... target] terminated by
  * 0xffffffff; d_out_len / d_out_npaths / d_out_status: n_desc; d_out_stats: 4*n_desc; d_work_counter: 1 u32.
  * invalidation_mode: B2T_INVALIDATE_*; claim_window_voxels: width of a WINDOW round.  STRICT only: d_heap holds heap_words

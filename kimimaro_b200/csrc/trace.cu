@@ -81,6 +81,10 @@ struct LabelDesc {
   uint32_t bucket_row;  // row of this label in the (label x bucket) tables = its cc id
   uint32_t soma_done;   // 1: the one-off soma invalidation already ran grid-wide (b2t_invalidate_ball)
   uint32_t pre_invalid; // voxels it invalidated
+  uint32_t bbox_x0, bbox_x1;  // x extent of the label's bounding box (inclusive): the reference runs on the bbox crop
+                              // (intake.py:463-466), and the x faces of THAT array are where the corner entries of its
+                              // neighbour table alias (strict mode reproduces the duplicate pushes)
+  uint32_t reserved0, reserved1;
 };
 
 struct Params {
@@ -821,7 +825,7 @@ __device__ __noinline__ uint32_t invalidate_strict(const Arena& A, const LabelDe
     while (H.n > 0 && !overflow) {
       uint32_t tk, loc, sd;
       heap_pop(H, tk, loc, sd, lane);
-      if (__ldcg(&A.claim[loc]) != kValid) continue;                // if (!field[loc]) continue;
+      if (__ldcg(&A.claim[loc]) != kValid || __ldg(&A.cc[loc]) != seg) continue;   // if (!field[loc]) continue;
       __syncwarp();
       if (lane == 0) A.claim[loc] = 0ull;
       total++;
@@ -832,7 +836,9 @@ __device__ __noinline__ uint32_t invalidate_strict(const Arena& A, const LabelDe
       unravel(o, A.d, ox, oy, oz);
       // compute_neighborhood (hpp:60-124): face terms are zero at the volume's border; an edge entry needs both of its
       // terms, a corner entry only its y and z terms
-      const int tx = fdx < 0 ? (x > 0 ? -1 : 0) : (fdx > 0 ? (x < A.d.sx - 1 ? 1 : 0) : 0);
+      // (the reference's array is the label's bounding-box crop: its x faces are the box's; in y and z the volume's
+      // faces do, what lies between them and the box is not this label)
+      const int tx = fdx < 0 ? (x > (int)L.bbox_x0 ? -1 : 0) : (fdx > 0 ? (x < (int)L.bbox_x1 ? 1 : 0) : 0);
       const int ty = fdy < 0 ? (y > 0 ? -1 : 0) : (fdy > 0 ? (y < A.d.sy - 1 ? 1 : 0) : 0);
       const int tz = fdz < 0 ? (z > 0 ? -1 : 0) : (fdz > 0 ? (z < A.d.sz - 1 ? 1 : 0) : 0);
       bool ok;
@@ -1047,7 +1053,7 @@ __global__ void __launch_bounds__(kThreads, B2T_TRACE_MINB) trace_kernel(Arena A
 // C ABI: the whole path loop for a batch of labels in one launch.
 // Replaces the body of kimimaro/trace.py:compute_paths (trace.py:196-267) and the native calls in
 // it: dijkstra3d.railroad, CachedTargetFinder.find_target, roll_invalidation_ball_inside_component.
-//   d_desc       n_desc records of 16 x u32/f32 (struct LabelDesc above, same field order)
+//   d_desc       n_desc records of 20 x u32/f32 (struct LabelDesc above, same field order)
 //   d_scratch    6 * sum(n_fg) u32;  d_paths: path pool;  d_targets: manual targets (linear indices)
 //   d_out_len / d_out_npaths / d_out_status: n_desc each; d_out_stats: 4 * n_desc; d_work_counter: 1 u32 (zeroed here)
 // =================================================================================================
@@ -1068,7 +1074,7 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
                                int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter,
                                int invalidation_mode, float claim_window_voxels, uint32_t* d_heap, uint64_t heap_words,
                                uint64_t heap_static_words, void* stream) {
-  static_assert(sizeof(LabelDesc) == 64, "LabelDesc must stay 16 x 4 bytes (mirrored in kimimaro_b200/engine.py)");
+  static_assert(sizeof(LabelDesc) == 80, "LabelDesc must stay 20 x 4 bytes (mirrored in kimimaro_b200/engine.py)");
   B2T_REQUIRE(sx > 0 && sy > 0 && sz > 0 && (double)sx * sy * sz < 4294967295.0, "bad volume shape");
   B2T_REQUIRE(invalidation_mode == B2T_INVALIDATE_ROUNDS || invalidation_mode == B2T_INVALIDATE_WINDOW ||
               invalidation_mode == B2T_INVALIDATE_STRICT, "b2t_trace_batch: unknown invalidation mode");

@@ -223,9 +223,10 @@ DESC_DTYPE = np.dtype([
   ("segid", "<u4"), ("root", "<u4"), ("n_fg", "<u4"), ("region_off", "<u4"), ("path_off", "<u4"),
   ("path_cap", "<u4"), ("tb_off", "<u4"), ("tb_n", "<u4"), ("ta_off", "<u4"), ("ta_n", "<u4"),
   ("max_paths", "<u4"), ("soma_mode", "<u4"), ("soma_radius", "<f4"), ("bucket_row", "<u4"),
-  ("soma_done", "<u4"), ("pre_invalid", "<u4"),
+  ("soma_done", "<u4"), ("pre_invalid", "<u4"), ("bbox_x0", "<u4"), ("bbox_x1", "<u4"), ("reserved0", "<u4"),
+  ("reserved1", "<u4"),
 ])
-assert DESC_DTYPE.itemsize == 64
+assert DESC_DTYPE.itemsize == 80
 
 
 class Jobs:
@@ -233,7 +234,7 @@ class Jobs:
   root == -1 means "find a root" (trace.py:128-129); tb / ta map a job index to its list of manual targets
   (linear voxel indices) and only hold the labels that have any."""
   def __init__(self, segid, n_fg, first, root, dbf_max, tb=None, ta=None, soma_mode=None, soma_radius=None,
-               free_space=None):
+               free_space=None, bbox_x=None):
     self.segid = np.asarray(segid, dtype=np.int64)
     n = self.segid.size
     self.n_fg = np.asarray(n_fg, dtype=np.int64)
@@ -245,6 +246,8 @@ class Jobs:
     self.soma_mode = np.zeros(n, dtype=bool) if soma_mode is None else np.asarray(soma_mode, dtype=bool)
     self.soma_radius = np.zeros(n, dtype=np.float32) if soma_radius is None else np.asarray(soma_radius, dtype=np.float32)
     self.free_space = np.zeros(n, dtype=np.float32) if free_space is None else np.asarray(free_space, dtype=np.float32)
+    # x extent (inclusive) of every label's bounding box: the array the reference's invalidation runs on
+    self.bbox_x = None if bbox_x is None else np.asarray(bbox_x, dtype=np.int64).reshape(n, 2)
 
   def __len__(self):
     return int(self.segid.size)
@@ -337,6 +340,10 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   desc["n_fg"] = jobs.n_fg[order]
   desc["soma_mode"] = jobs.soma_mode[order]
   desc["soma_radius"] = jobs.soma_radius[order]
+  if jobs.bbox_x is not None:
+    desc["bbox_x0"], desc["bbox_x1"] = jobs.bbox_x[order, 0], jobs.bbox_x[order, 1]
+  else:
+    desc["bbox_x0"], desc["bbox_x1"] = 0, sx - 1
   # manual targets: labels without any get the DAF arg-max appended unless in soma mode (trace.py:171-172)
   tb_n = np.zeros(n_jobs, dtype=np.int64)
   ta_n = np.zeros(n_jobs, dtype=np.int64)

@@ -517,7 +517,8 @@ def _skeletonize(
         tb_map[i] = [lin(p) for p in tb]
       if ta:
         ta_map[i] = [lin(p) for p in ta]
-  jobs = engine.Jobs(main, h_count[main], h_first[main], roots, h_dbfmax[main], tb=tb_map, ta=ta_map)
+  jobs = engine.Jobs(main, h_count[main], h_first[main], roots, h_dbfmax[main], tb=tb_map, ta=ta_map,
+                     bbox_x=h_bbox[main][:, [0, 3]])
 
   results = {}            # original label -> (vertices, edges, radii), all its ordinary components merged
   private_results = []    # (original label, arrays) of labels traced in a private arena

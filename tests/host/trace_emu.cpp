@@ -49,7 +49,7 @@ extern "C" long emu_invalidate(const uint32_t* cc, const float* dbf, unsigned lo
   a.A.cc = cc; a.A.dbf = dbf; a.A.claim = claim;
   a.A.d = Dims{sx, sy, sz, (uint32_t)(sx * sy)};
   a.A.wx = wx; a.A.wy = wy; a.A.wz = wz;
-  a.L.segid = segid; a.L.n_fg = n_fg;
+  a.L.segid = segid; a.L.n_fg = n_fg; a.L.bbox_x0 = 0; a.L.bbox_x1 = (uint32_t)(sx - 1);
   a.seeds = seeds; a.n_seeds = n_seeds; a.scale = scale; a.konst = konst; a.delta = delta; a.mode = mode;
   uint32_t* scratch = (uint32_t*)malloc(sizeof(uint32_t) * 4 * (size_t)(n_fg + 1));
   a.r0 = scratch; a.r1 = scratch + n_fg; a.r2 = scratch + 2 * (size_t)n_fg; a.r3 = scratch + 3 * (size_t)n_fg;
@@ -86,7 +86,7 @@ extern "C" int emu_trace_batch(const uint32_t* cc, const float* dbf, float* pdrf
                                uint32_t* out_npaths, int32_t* out_status, uint32_t* out_stats, uint32_t* work_counter,
                                int inval_mode, float claim_window, uint32_t* heap, uint64_t heap_words,
                                uint64_t heap_static_words) {
-  static_assert(sizeof(LabelDesc) == 64, "LabelDesc layout");
+  static_assert(sizeof(LabelDesc) == 80, "LabelDesc layout");
   KArgs k;
   memset(&k, 0, sizeof(k));
   k.A.cc = cc; k.A.dbf = dbf; k.A.pdrf = pdrf; k.A.dist = dist; k.A.claim = claim; k.A.stamp = stamp;

@@ -155,6 +155,7 @@ def _emulated_paths(lib, cc, n_cc, all_dbf, an, params, window, fix_borders_targ
     d["segid"], d["root"], d["n_fg"], d["region_off"], d["path_off"], d["path_cap"] = l, lin(root), n_fg, region, path_off, cap
     d["tb_off"], d["tb_n"], d["ta_off"], d["ta_n"] = len(targets), 1, len(targets) + 1, 0
     d["max_paths"], d["bucket_row"] = 0xFFFFFFFF, l - 1
+    d["bbox_x0"], d["bbox_x1"] = 0, sx - 1       # the array the oracle's trace() below runs on is the whole volume
     targets.append(lin(target))
     descs.append(d)
     hist.append(n_fg)
