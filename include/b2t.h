@@ -131,6 +131,15 @@ int b2t_edf_multi(const uint32_t* d_cc, int64_t sx, int64_t sy, int64_t sz, floa
                   uint32_t h_free_space_source, const float* d_node_weights, float* d_dist, uint32_t* d_stamp,
                   uint32_t* d_queue, uint64_t queue_cap, uint32_t* d_ctrl, void* stream);
 
+/* The same field, label by label instead of one grid-wide sweep: d_jobs holds n_jobs records of four u32
+ * (source voxel, cc id, voxel count n_fg, prefix sum of n_fg over the preceding records), sorted by n_fg descending.
+ * The first n_team jobs get a thread-block cluster (8 CTAs, hardware cluster barrier per relaxation round), the others one
+ * CTA each (block barrier); every label runs exactly its own number of rounds instead of the volume's maximum.
+ * d_queue: 2*sum(n_fg) u32; d_ctrl: 4*n_team u32; d_dist / d_stamp / d_node_weights as above.  Bit-identical result. */
+int b2t_edf_labels(const uint32_t* d_cc, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
+                   const uint32_t* d_jobs, uint32_t n_jobs, uint32_t n_team, const float* d_node_weights,
+                   float* d_dist, uint32_t* d_stamp, uint32_t* d_queue, uint32_t* d_ctrl, void* stream);
+
 /* return_max_location of the call above: d_best[l] = (dist_bits << 32) | (0xffffffff - index) of the
  * largest finite distance of label l, smallest index on ties; 0 if the label has none. */
 int b2t_field_argmax(const uint32_t* d_cc, const float* d_dist, int64_t sx, int64_t sy, int64_t sz,

@@ -199,6 +199,124 @@ __global__ void __launch_bounds__(1024, 2) edf_multi_kernel(EdfParams p) {
   if (improved) atomicAdd(&p.ctrl[4], improved);
 }
 
+// ------------------------------------------------------------------------------------------------
+// edf_label: the same sweep, but one TEAM per label instead of one grid for all of them.  A round of the grid-wide
+// kernel above costs a grid barrier (~9 us) and there are as many rounds as the longest geodesic of ANY label has hops
+// (~1500 on a 512^3 volume), whatever the label: 14-20 ms per sweep of which almost all is barrier latency.  Here a
+// label's rounds are private to its team:
+//   solo   one 512-thread CTA, __syncthreads() per round, frontier counters in shared memory      (labels below the team threshold:
+//          the median label has 10^4 voxels and a frontier of a few dozen)
+//   team   a thread-block cluster of kEdfCluster CTAs, one hardware cluster barrier per round, counters in global memory
+//          (the few labels whose frontier keeps 128 warps busy)
+// and every label stops after its OWN number of rounds.  One launch: cluster c < n_team is a team for job c, the CTAs of
+// the other clusters take one job each.  Same relaxation, same least fixed point, bit for bit.
+// ------------------------------------------------------------------------------------------------
+constexpr int kEdfCluster = 8;
+constexpr int kEdfThreads = 512;
+
+struct EdfJob {
+  uint32_t source;      // linear index of the source voxel
+  uint32_t segid;       // (informative: relaxation follows cc[source])
+  uint32_t n_fg;        // voxels of the label: its two queue buffers hold n_fg entries each
+  uint32_t region_off;  // prefix sum of n_fg over the jobs: the label's queue starts at 2 * region_off
+};
+
+template <bool TEAM>
+__device__ __forceinline__ void edf_team_barrier() {
+#ifdef B2T_HOST_EMU
+  __syncthreads();
+#else
+  if (TEAM) cg::this_cluster().sync(); else __syncthreads();
+#endif
+}
+
+template <bool TEAM, bool NODE_W>
+__device__ void edf_label_run(const EdfParams& p, const EdfJob J, uint32_t* cnt, uint32_t rank, uint32_t nranks) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t wpb = blockDim.x >> 5;
+  const uint32_t tw = rank * wpb + (threadIdx.x >> 5), ntw = nranks * wpb;
+  uint32_t* q = p.queue + 2ull * J.region_off;
+  int dx = 0, dy = 0, dz = 0;
+  float w = 0.0f;
+  if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; w = p.w[lane]; }
+  const int64_t off = (int64_t)dx + (int64_t)dy * p.d.sx + (int64_t)dz * p.d.sxy;
+  const uint32_t ltmask = (1u << lane) - 1u;
+  if (rank == 0 && threadIdx.x == 0) {
+    p.dist[J.source] = 0.0f;
+    q[J.n_fg] = J.source;          // round 1 reads buffer 1
+    cnt[0] = 0; cnt[1] = 1; cnt[2] = 0;
+  }
+  const uint32_t lab = __ldg(&p.cc[J.source]);
+  edf_team_barrier<TEAM>();
+  for (uint32_t round = 1;; round++) {
+    const uint32_t n = TEAM ? __ldcg(&cnt[round % 3]) : cnt[round % 3];
+    if (n == 0) break;
+    const uint32_t* qin = q + (uint64_t)(round & 1) * J.n_fg;
+    uint32_t* qout = q + (uint64_t)((round + 1) & 1) * J.n_fg;
+    uint32_t* cnt_out = &cnt[(round + 1) % 3];
+    for (uint32_t it = tw * 2; it < n; it += ntw * 2) {
+      uint32_t u[2], v[2], lv[2];
+      float du[2];
+      bool ok[2], push[2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        ok[e] = it + e < n;
+        u[e] = ok[e] ? __ldcg(&qin[it + e]) : 0u;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) du[e] = ok[e] ? __ldcg(&p.dist[u[e]]) : 0.0f;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int x, y, z;
+        unravel(u[e], p.d, x, y, z);
+        const int nx = x + dx, ny = y + dy, nz = z + dz;
+        ok[e] = ok[e] && lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < p.d.sx && ny < p.d.sy && nz < p.d.sz;
+        v[e] = ok[e] ? (uint32_t)((int64_t)u[e] + off) : 0u;
+        lv[e] = ok[e] ? __ldg(&p.cc[v[e]]) : 0xffffffffu;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        push[e] = false;
+        if (ok[e] && lv[e] == lab) {
+          const uint32_t nd = __float_as_uint(__fadd_rn(du[e], NODE_W ? __ldg(&p.node_w[v[e]]) : w));
+          const uint32_t old = atomicMin(reinterpret_cast<uint32_t*>(&p.dist[v[e]]), nd);
+          if (nd < old) push[e] = atomicExch(&p.stamp[v[e]], round) != round;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const uint32_t m = __ballot_sync(0xffffffffu, push[e]);
+        if (m) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(cnt_out, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (push[e]) qout[base + __popc(m & ltmask)] = v[e];
+        }
+      }
+    }
+    edf_team_barrier<TEAM>();
+    if (rank == 0 && threadIdx.x == 0) cnt[round % 3] = 0;   // read again in round + 3; two barriers lie in between
+  }
+}
+
+template <bool NODE_W>
+__global__ void __launch_bounds__(kEdfThreads, 4) edf_label_kernel(EdfParams p, const EdfJob* __restrict__ jobs,
+                                                                    uint32_t n_jobs, uint32_t n_team) {
+  __shared__ uint32_t s_cnt[4];
+#ifdef B2T_HOST_EMU
+  const uint32_t cid = blockIdx.x, rank = 0, csize = 1;      // emulated clusters have one CTA
+#else
+  const uint32_t csize = kEdfCluster;
+  const uint32_t cid = blockIdx.x / csize, rank = blockIdx.x % csize;
+#endif
+  if (cid < n_team) {
+    edf_label_run<true, NODE_W>(p, jobs[cid], p.ctrl + 4ull * cid, rank, csize);
+  } else {
+    const uint32_t job = n_team + (cid - n_team) * csize + rank;
+    if (job < n_jobs) edf_label_run<false, NODE_W>(p, jobs[job], s_cnt, 0, 1);
+  }
+}
+
 // soma free-space box (dijkstra3d free_space_radius): closed-form distances inside the box
 // inscribed in the sphere, interior frozen, shell voxels become the frontier.  One label, one source.
 __global__ void edf_freespace_seed_kernel(EdfParams p, uint32_t src, float radius, float wx, float wy, float wz) {
@@ -455,6 +573,47 @@ B2T_EXPORT int b2t_edf_multi(const uint32_t* d_cc, int64_t sx, int64_t sy, int64
   B2T_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(1024), args, 0, st));
 #endif
   b2t_count_launches(frozen ? 3 : 2);
+  return B2T_OK;
+}
+
+// The same field, label by label: job i = (source voxel, cc id, voxel count, prefix sum of the counts before it).
+// The first n_team jobs -- the caller sorts the jobs by size, largest first -- get a thread-block cluster each, the
+// others one CTA each; every label runs its own rounds (see edf_label above).  d_dist: +inf, d_stamp: 0 on entry;
+// d_queue: 2 * sum(n_fg) u32; d_ctrl: 4 * n_team u32.  d_node_weights as in b2t_edf_multi.
+B2T_EXPORT int b2t_edf_labels(const uint32_t* d_cc, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
+                              const uint32_t* d_jobs, uint32_t n_jobs, uint32_t n_team, const float* d_node_weights,
+                              float* d_dist, uint32_t* d_stamp, uint32_t* d_queue, uint32_t* d_ctrl, void* stream) {
+  if (int rc = check_dims(sx, sy, sz)) return rc;
+  B2T_REQUIRE(d_cc && d_dist && d_stamp && d_queue && (d_jobs || n_jobs == 0), "b2t_edf_labels: null pointer");
+  B2T_REQUIRE(n_team <= n_jobs && (n_team == 0 || d_ctrl), "b2t_edf_labels: n_team out of range or no d_ctrl");
+  if (n_jobs == 0) return B2T_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  EdfParams p;
+  p.cc = d_cc; p.node_w = d_node_weights; p.dist = d_dist; p.stamp = d_stamp; p.queue = d_queue; p.ctrl = d_ctrl;
+  p.cap = 0;
+  p.d = Dims{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
+  fill_weights(wx, wy, wz, p.w);
+  const EdfJob* jobs = reinterpret_cast<const EdfJob*>(d_jobs);
+#ifdef B2T_HOST_EMU
+  if (d_node_weights) simt::block_launch(n_jobs, kEdfThreads, [](auto... a_) { edf_label_kernel<true>(a_...); })(p, jobs, n_jobs, n_team);
+  else simt::block_launch(n_jobs, kEdfThreads, [](auto... a_) { edf_label_kernel<false>(a_...); })(p, jobs, n_jobs, n_team);
+#else
+  const uint32_t n_solo = n_jobs - n_team;
+  const uint32_t clusters = n_team + (n_solo + kEdfCluster - 1) / kEdfCluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * kEdfCluster);
+  cfg.blockDim = dim3(kEdfThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kEdfCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (d_node_weights) B2T_CUDA_TRY(cudaLaunchKernelEx(&cfg, edf_label_kernel<true>, p, jobs, n_jobs, n_team));
+  else B2T_CUDA_TRY(cudaLaunchKernelEx(&cfg, edf_label_kernel<false>, p, jobs, n_jobs, n_team));
+#endif
+  b2t_count_launches(1);
   return B2T_OK;
 }
 

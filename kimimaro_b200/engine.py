@@ -12,6 +12,7 @@ Data layout in HBM (per voxel of the [sx,sy,sz] Fortran-ordered volume, V voxels
 plus per foreground voxel: keys 8 B (DAF-bucketed target list), 16 B of queue scratch, path pool.
 """
 import ctypes
+import os
 import time
 from collections import defaultdict
 
@@ -28,6 +29,8 @@ c_u64 = ctypes.c_uint64
 _lib.declare("b2t_label_stats", [c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp])
 _lib.declare("b2t_edf_multi", [c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_u32, c_f32, c_u32,
                                c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, c_vp])
+_lib.declare("b2t_edf_labels", [c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_u32, c_u32, c_vp, c_vp, c_vp, c_vp,
+                                c_vp, c_vp])
 _lib.declare("b2t_field_argmax", [c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp])
 _lib.declare("b2t_pdrf_and_buckets", [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp,
                                       c_vp, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp])
@@ -125,6 +128,54 @@ def edf_multi(d_cc, shape, anisotropy, d_sources, n_sources, ws, free_space=None
                             c_f32(anisotropy[2]), _p(d_sources), c_u32(n_sources), c_f32(fsr), c_u32(fss),
                             _p(node_weights), _p(ws.dist), _p(ws.stamp), _p(ws.queue), c_u64(ws.queue.numel() // 2), _p(ws.ctrl),
                             stream_ptr()), "b2t_edf_multi")
+
+
+# labels above EDF_TEAM_MIN voxels get a thread-block cluster in b2t_edf_labels (at most EDF_TEAM_MAX of them), labels above
+# EDF_GRID_MIN the grid-wide cooperative sweep (b2t_edf_multi): one label that size keeps every SM busy by itself
+EDF_TEAM_MIN = int(os.environ.get("B2T_EDF_TEAM_MIN", 32768))
+EDF_TEAM_MAX = int(os.environ.get("B2T_EDF_TEAM_MAX", 96))
+EDF_GRID_MIN = int(os.environ.get("B2T_EDF_GRID_MIN", 4 << 20))
+
+
+def edf_labels(d_cc, shape, anisotropy, sources, segids, n_fg, ws, node_weights=None):
+  """dijkstra3d.euclidean_distance_field (or parental_field with node_weights) for many labels, each label with its own
+  relaxation rounds (b2t_edf_labels) -> ws.dist.  sources / segids / n_fg: one entry per label."""
+  sx, sy, sz = shape
+  sources = np.asarray(sources, dtype=np.int64)
+  n_fg = np.asarray(n_fg, dtype=np.int64)
+  segids = np.asarray(segids, dtype=np.int64)
+  ws.dist.fill_(float("inf"))
+  ws.stamp.zero_()
+  giant = n_fg > EDF_GRID_MIN
+  if giant.any() or os.environ.get("B2T_EDF_LABELS", "1") == "0":
+    sel = np.flatnonzero(giant) if os.environ.get("B2T_EDF_LABELS", "1") != "0" else np.arange(n_fg.size)
+    src = _dev(sources[sel].astype(np.uint32).view(np.int32))
+    check(lib().b2t_edf_multi(_p(d_cc), c_i64(sx), c_i64(sy), c_i64(sz), c_f32(anisotropy[0]), c_f32(anisotropy[1]),
+                              c_f32(anisotropy[2]), _p(src), c_u32(int(sel.size)), c_f32(0.0), c_u32(0),
+                              _p(node_weights), _p(ws.dist), _p(ws.stamp), _p(ws.queue), c_u64(ws.queue.numel() // 2),
+                              _p(ws.ctrl), stream_ptr()), "b2t_edf_multi")
+    rest = np.setdiff1d(np.arange(n_fg.size), sel)
+    if rest.size == 0:
+      return
+    if giant.any():
+      ws.stamp.zero_()             # round numbers restart per label; the giant labels' stamps are done with
+    sources, segids, n_fg = sources[rest], segids[rest], n_fg[rest]
+  order = np.argsort(-n_fg, kind="stable")
+  n = int(order.size)
+  tab = np.zeros((n, 4), dtype=np.uint32)
+  tab[:, 0] = sources[order]
+  tab[:, 1] = segids[order]
+  tab[:, 2] = n_fg[order]
+  tab[:, 3] = np.concatenate(([0], np.cumsum(n_fg[order])[:-1]))
+  n_team = min(int((n_fg > EDF_TEAM_MIN).sum()), EDF_TEAM_MAX)
+  if 2 * int(n_fg.sum()) > ws.queue.numel():
+    raise B2TError("edf_labels: queue too small for these labels")
+  d_tab = _dev(tab.view(np.int32))
+  ctrl = torch.zeros(4 * max(n_team, 1), dtype=torch.int32, device=d_cc.device)
+  check(lib().b2t_edf_labels(_p(d_cc), c_i64(sx), c_i64(sy), c_i64(sz), c_f32(anisotropy[0]), c_f32(anisotropy[1]),
+                             c_f32(anisotropy[2]), _p(d_tab), c_u32(n), c_u32(n_team), _p(node_weights), _p(ws.dist),
+                             _p(ws.stamp), _p(ws.queue), _p(ctrl), stream_ptr()), "b2t_edf_labels")
+  ws.keep = (d_tab, ctrl)          # alive until the stream gets there
 
 
 def field_argmax(d_cc, d_dist, shape, n):
@@ -287,8 +338,7 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   # ---- roots (trace.py:128-129, 291-308): one field sweep for every label that has no root yet ----
   need = np.flatnonzero(jobs.root < 0)
   if need.size:
-    src = _dev(jobs.first[need].astype(np.uint32).view(np.int32))
-    edf_multi(d_cc, shape, anisotropy, src, int(need.size), ws)
+    edf_labels(d_cc, shape, anisotropy, jobs.first[need], jobs.segid[need], jobs.n_fg[need], ws)
     _, idx = field_argmax(d_cc, ws.dist, shape, n_rows)
     jobs.root[need] = idx[jobs.segid[need]]
   lap("find_root")
@@ -300,7 +350,7 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   if has_free.any():
     edf_multi(d_cc, shape, anisotropy, src, 1, ws, free_space=(float(jobs.free_space[0]), int(jobs.root[0])))
   else:
-    edf_multi(d_cc, shape, anisotropy, src, n_jobs, ws)
+    edf_labels(d_cc, shape, anisotropy, jobs.root, jobs.segid, jobs.n_fg, ws)
   maxdaf, target_idx = field_argmax(d_cc, ws.dist, shape, n_rows)
   lap("daf")
 
@@ -329,7 +379,7 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   if not fix_branching:
     # parents = dijkstra3d.parental_field(PDRF, root) (trace.py:154-155), every label in one sweep; the
     # distances stay in ws.dist and the path kernel derives parents from them (rule T3)
-    edf_multi(d_cc, shape, anisotropy, src, n_jobs, ws, node_weights=pdrf)
+    edf_labels(d_cc, shape, anisotropy, jobs.root, jobs.segid, jobs.n_fg, ws, node_weights=pdrf)
     lap("parental_field")
 
   # ---- the path loop for every label (trace.py:196-267) ----

@@ -144,6 +144,47 @@ def test_distance_field_argmax_pdrf(emu, an):
   assert np.isinf(dist[ccf != 0]).all()                     # the scatter hands the distance field back as +inf
 
 
+@pytest.mark.parametrize("n_team,node_w", [(0, False), (2, False), (5, False), (1, True)])
+def test_distance_field_label_by_label(emu, n_team, node_w):
+  """b2t_edf_labels: every label sweeps its own rounds -- a CTA per label, or a team for the first n_team jobs (emulated
+  clusters have one CTA: what is checked is the team code path with its counters in global memory) -- and must give
+  exactly the field of the grid-wide sweep and of the oracle's Dijkstra; with node weights, dijkstra3d.parental_field."""
+  from oracle import teasar
+  an = (16.0, 16.0, 40.0)
+  cc, n = _volume(34, shape=(44, 40, 30), n=6)
+  sx, sy, sz = cc.shape
+  ccf = np.ascontiguousarray(cc.reshape(-1, order="F").astype(np.uint32))
+  V = ccf.size
+  counts = np.bincount(ccf, minlength=n + 1)
+  roots = {}
+  for l in range(1, n + 1):
+    r = teasar.find_root(np.asfortranarray(cc == l).view(np.uint8), an)
+    roots[l] = int(r[0]) + sx * (int(r[1]) + sy * int(r[2]))
+  order = sorted(range(1, n + 1), key=lambda l: -counts[l])
+  tab = np.zeros((n, 4), np.uint32)
+  off = 0
+  for i, l in enumerate(order):
+    tab[i] = (roots[l], l, counts[l], off)
+    off += counts[l]
+  rng = np.random.default_rng(5)
+  w = np.ascontiguousarray((rng.random(V) * 10 + 0.5).astype(np.float32)) if node_w else None
+  dist = np.full(V, np.inf, np.float32)
+  stamp = np.zeros(V, np.uint32)
+  queue = np.zeros(2 * off + 8, np.uint32)
+  ctrl = np.zeros(4 * max(n_team, 1), np.uint32)
+  n_team = min(n_team, n)
+  assert emu.b2t_edf_labels(p(ccf), c_i64(sx), c_i64(sy), c_i64(sz), c_f32(an[0]), c_f32(an[1]), c_f32(an[2]), p(tab), c_u32(n),
+                            c_u32(n_team), p(w) if node_w else None, p(dist), p(stamp), p(queue), p(ctrl), None) == 0
+  ref = _edf(emu, ccf, cc.shape, an, [roots[l] for l in range(1, n + 1)], node_w=w)
+  assert np.array_equal(dist, ref)
+  if not node_w:
+    got = dist.reshape(cc.shape, order="F")
+    for l in range(1, n + 1):
+      labels = np.asfortranarray(cc == l).view(np.uint8)
+      daf = oracle.euclidean_distance_field(labels, np.unravel_index(roots[l], cc.shape, order="F"), anisotropy=an)
+      assert np.array_equal(got[cc == l], daf[cc == l]), l
+
+
 def test_ball_invalidation(emu):
   """b2t_invalidate_ball (the soma's one-off ball, trace.py:160-168): one seed and several seeds against the oracle's
   literal heap-ordered form -- with one seed every claim order gives the same set."""
