@@ -177,7 +177,10 @@ int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist
  * invalidation_mode: B2T_INVALIDATE_*; claim_window_voxels: width of a WINDOW round.  STRICT only: d_heap holds heap_words
  * u32, of which the first heap_static_words = b2t_trace_heap_words(sum(n_fg), n_desc) are the labels' own heap regions
  * (4 entries per voxel) and the rest a spill arena for heaps that outgrow theirs (up to 27 entries per voxel of the
- * label); a label whose heap fits nowhere reports B2T_ERR_CAPACITY in d_out_status.  Other modes: NULL, 0, 0. */
+ * label); a label whose heap fits nowhere reports B2T_ERR_CAPACITY in d_out_status.  Other modes: NULL, 0, 0.
+ * n_team: the first n_team records (the caller sorts by n_fg, largest first) are traced by a thread-block cluster of
+ * 8 CTAs each instead of one CTA -- a label's paths are sequential, so the largest label is the tail of the launch;
+ * d_team: n_team * b2t_trace_team_bytes() bytes of device memory for the teams' shared state. */
 uint64_t b2t_trace_heap_words(uint64_t sum_n_fg, uint64_t n_desc);
 int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,
                     uint32_t* d_stamp, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
@@ -187,7 +190,8 @@ int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, flo
                     const uint32_t* d_targets, uint32_t* d_out_len, uint32_t* d_out_npaths,
                     int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter,
                     int invalidation_mode, float claim_window_voxels, uint32_t* d_heap, uint64_t heap_words,
-                    uint64_t heap_static_words, void* stream);
+                    uint64_t heap_static_words, int n_team, void* d_team, void* stream);
+uint64_t b2t_trace_team_bytes(void);
 
 /* the same rolling-ball invalidation, grid-wide, for balls too large for one CTA (the one-off soma
  * invalidation, kimimaro/trace.py:160-168).  d_fv / d_fs: 2*cap u32 each; count left in d_ctrl[6]. */

@@ -22,6 +22,9 @@
 //
 // Per-voxel fields are the dense arrays of field.cu (cc, dbf, pdrf, dist, claim, stamp); per-label
 // queues live in a scratch pool indexed by the label's foreground-count prefix sum.
+#ifndef B2T_HOST_EMU
+#include <cooperative_groups.h>
+#endif
 #include "common.cuh"
 
 // B2T_HOST_EMU: tests/host/trace_emu.cpp compiles this file with g++ against a SIMT emulation (one OS thread per CUDA
@@ -122,6 +125,39 @@ __device__ __forceinline__ void unravel(uint32_t loc, const Dims& d, int& x, int
   x = r - (uint32_t)y * d.sx;
 }
 
+// ---- the team that traces one label -----------------------------------------------------------------
+// solo: one CTA (what every label but the largest few gets); team: the kCluster CTAs of a thread-block cluster, for the
+// labels whose searches keep 128 warps busy -- the path loop of a label is sequential, so the largest label IS the tail of
+// the kernel (45 ms of a 45 ms launch on the benchmark volume when one CTA has it to itself).  The code below is written
+// against the team: strides, barriers and reductions go through these helpers, the per-label state `Shared` lives in
+// shared memory (solo) or in a global-memory slot all CTAs of the cluster see (team), the work lists are in global
+// scratch either way.
+#ifdef B2T_HOST_EMU
+constexpr int kCluster = 1;        // the CPU harness runs one CTA at a time: a "cluster" of one exercises the team code path
+#else
+constexpr int kCluster = 8;
+#endif
+
+struct Team {
+  uint32_t rank;      // this CTA within the team
+  uint32_t par;       // parity of the team reductions' exchange slots
+};
+
+template <bool TEAM> __device__ __forceinline__ uint32_t t_threads() { return TEAM ? kCluster * kThreads : kThreads; }
+template <bool TEAM> __device__ __forceinline__ uint32_t t_warps() { return TEAM ? kCluster * kWarps : kWarps; }
+template <bool TEAM> __device__ __forceinline__ uint32_t t_tid(const Team& T) { return TEAM ? T.rank * kThreads + threadIdx.x : threadIdx.x; }
+template <bool TEAM> __device__ __forceinline__ uint32_t t_warp(const Team& T) { return TEAM ? T.rank * kWarps + (threadIdx.x >> 5) : (threadIdx.x >> 5); }
+
+template <bool TEAM> __device__ __forceinline__ void team_sync() {
+#ifdef B2T_HOST_EMU
+  __syncthreads();
+#else
+  if (TEAM) cooperative_groups::this_cluster().sync(); else __syncthreads();
+#endif
+}
+// a value of the team's shared state that other threads change between barriers
+template <bool TEAM, typename V> __device__ __forceinline__ V t_peek(const V* p) { return TEAM ? __ldcg(p) : *p; }
+
 // ---- block-wide reductions (all threads must call) ------------------------------------------------
 __device__ __forceinline__ uint32_t block_min_u32(uint32_t v, uint32_t* s_red) {
 #pragma unroll
@@ -162,11 +198,19 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* s_red) {
   return r;
 }
 
-struct Shared {
+// Per-CTA scratch of the block reductions (always shared memory).
+struct Local {
   uint32_t red32[kWarps];
   unsigned long long red64[kWarps];
+  unsigned long long bcast;
+};
+
+// Per-label state: shared memory (solo) or a global-memory slot of the team.
+struct Shared {
   unsigned long long best;   // railroad: (dist_bits << 32) | voxel of the best rail-adjacent voxel
+  unsigned long long x64[2][kCluster];   // team reductions: one value per CTA, two parities
   uint32_t n_keep, n_proc, n_next, n_touched;
+  uint32_t r32[2];           // small results handed from one thread to the team
   uint32_t job;
   int bucket;
   uint32_t relax, rounds, invalidated;
@@ -174,8 +218,45 @@ struct Shared {
   uint32_t heap_cap;         // 0 = not set up yet
 };
 
+// team-wide reductions (all threads of the team must call): block reduction, then one value per CTA through `S`
+template <bool TEAM, int OP>   // OP 0: min u32, 1: max u64, 2: sum u32
+__device__ __forceinline__ unsigned long long team_reduce(unsigned long long v, Shared& S, Local& Lc, Team& T) {
+  unsigned long long r;
+  if (OP == 0) r = block_min_u32((uint32_t)v, Lc.red32);
+  else if (OP == 1) r = block_max_u64(v, Lc.red64);
+  else r = block_sum_u32((uint32_t)v, Lc.red32);
+  if (!TEAM) return r;
+  T.par ^= 1u;
+  if (threadIdx.x == 0) S.x64[T.par][T.rank] = r;
+  team_sync<TEAM>();
+  if (threadIdx.x < 32) {
+    unsigned long long x = threadIdx.x < kCluster ? __ldcg(&S.x64[T.par][threadIdx.x]) : (OP == 0 ? 0xffffffffull : 0ull);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, o);
+      x = OP == 0 ? (y < x ? y : x) : (OP == 1 ? (y > x ? y : x) : x + y);
+    }
+    if (threadIdx.x == 0) Lc.bcast = x;
+  }
+  __syncthreads();
+  r = Lc.bcast;
+  __syncthreads();
+  return r;
+}
+template <bool TEAM> __device__ __forceinline__ uint32_t team_min_u32(uint32_t v, Shared& S, Local& Lc, Team& T) {
+  return (uint32_t)team_reduce<TEAM, 0>(v, S, Lc, T);
+}
+template <bool TEAM> __device__ __forceinline__ unsigned long long team_max_u64(unsigned long long v, Shared& S, Local& Lc, Team& T) {
+  return team_reduce<TEAM, 1>(v, S, Lc, T);
+}
+template <bool TEAM> __device__ __forceinline__ uint32_t team_sum_u32(uint32_t v, Shared& S, Local& Lc, Team& T) {
+  return (uint32_t)team_reduce<TEAM, 2>(v, S, Lc, T);
+}
+
 // ---- CachedTargetFinder.find_target ------------------------------------------------------------------
-__device__ uint32_t find_target(const Arena& A, const LabelDesc& L, const Pools& P, const Params& prm, Shared& S) {
+template <bool TEAM>
+__device__ uint32_t find_target(const Arena& A, const LabelDesc& L, const Pools& P, const Params& prm, Shared& S, Local& Lc,
+                                Team& T) {
   for (;;) {
     const int b = S.bucket;
     if (b < 0) return 0xffffffffu;
@@ -183,29 +264,31 @@ __device__ uint32_t find_target(const Arena& A, const LabelDesc& L, const Pools&
     const uint32_t end = P.cursor[row], n = P.hist[row];
     const unsigned long long* k = P.keys + (end - n);
     unsigned long long best = 0;
-    for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+    for (uint32_t i = t_tid<TEAM>(T); i < n; i += t_threads<TEAM>()) {
       const unsigned long long key = k[i];
       const uint32_t v = (uint32_t)key;
       if (__ldcg(&A.claim[v]) == kValid && key + 1 > best) best = key + 1;  // +1 so that key 0 is distinguishable from "none"
     }
-    best = block_max_u64(best, S.red64);
+    best = team_max_u64<TEAM>(best, S, Lc, T);
     if (best != 0) return (uint32_t)(best - 1);
-    __syncthreads();
-    if (threadIdx.x == 0) S.bucket = b - 1;
-    __syncthreads();
+    team_sync<TEAM>();
+    if (t_tid<TEAM>(T) == 0) S.bucket = b - 1;
+    team_sync<TEAM>();
   }
 }
 
 // ---- dijkstra3d.railroad ----------------------------------------------------------------------------
 // Returns the path length written to out[0..): out[0] = rail voxel ... out[len-1] = target.
+template <bool TEAM>
 __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target, uint32_t* actA, uint32_t* actB,
                              uint32_t* proc, uint32_t* farA, uint32_t* farB, uint32_t* touched, uint32_t* out,
-                             uint32_t out_cap, Shared& S) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                             uint32_t out_cap, Shared& S, Local& Lc, Team& T) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t tid = t_tid<TEAM>(T), nth = t_threads<TEAM>(), tw = t_warp<TEAM>(T), ntw = t_warps<TEAM>();
   const uint32_t seg = L.segid;
   if (__ldcg(&A.pdrf[target]) == 0.0f) {
-    if (threadIdx.x == 0 && out_cap > 0) out[0] = target;
-    __syncthreads();
+    if (tid == 0 && out_cap > 0) out[0] = target;
+    team_sync<TEAM>();
     return out_cap > 0 ? 1 : 0;
   }
   int dx = 0, dy = 0, dz = 0;
@@ -221,7 +304,7 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
   uint32_t* mid2 = actB;
   uint32_t* far = farA;
   uint32_t* far2 = farB;
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     A.dist[target] = 0.0f;
     A.stamp[target] = 1;
     mid[0] = target;
@@ -230,13 +313,15 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
     S.best = ~0ull;
     S.n_keep = 0; S.n_proc = 0; S.n_next = 0;
   }
-  __syncthreads();
+  team_sync<TEAM>();
   uint32_t n_mid = 1, n_far = 0;
   float delta = __ldcg(&A.pdrf[target]);                      // width of the near batch
   if (!(delta > 0.0f) || __float_as_uint(delta) >= kInfBits) delta = 1.0f;
   float delta_mid = __fmul_rn(delta, 16.0f);                   // width of the mid band
   uint32_t thr_mid = __float_as_uint(delta_mid);
   uint32_t relax = 0, rounds = 0;
+  const uint32_t lo_proc = TEAM ? 2u * kWarps * kCluster : 2u * kWarps, hi_proc = 4u * lo_proc;   // batch-size feedback
+  const uint32_t lo_mid = TEAM ? 256u * kCluster : 256u, hi_mid = 4u * lo_mid;
 
   for (;;) {
     if (n_mid == 0) {
@@ -244,13 +329,13 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
       if (n_far == 0) break;
       const uint32_t bound = (uint32_t)(S.best >> 32);
       uint32_t mn = 0xffffffffu;
-      for (uint32_t i = threadIdx.x; i < n_far; i += kThreads) mn = min(mn, __float_as_uint(__ldcg(&A.dist[far[i]])));
-      mn = block_min_u32(mn, S.red32);
+      for (uint32_t i = tid; i < n_far; i += nth) mn = min(mn, __float_as_uint(__ldcg(&A.dist[far[i]])));
+      mn = team_min_u32<TEAM>(mn, S, Lc, T);
       if (mn > bound) break;                                  // nothing left that could beat the rail we have
       thr_mid = __float_as_uint(__fadd_rn(__uint_as_float(mn), delta_mid));
       if (thr_mid > bound) thr_mid = bound;
-      for (uint32_t i0 = 0; i0 < n_far; i0 += kThreads) {
-        const uint32_t i = i0 + threadIdx.x;
+      for (uint32_t i0 = 0; i0 < n_far; i0 += nth) {
+        const uint32_t i = i0 + tid;
         bool tomid = false, tokeep = false;
         uint32_t u = 0;
         if (i < n_far) {
@@ -271,35 +356,35 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
         if (tomid) mid[bp + __popc(mp & ltmask)] = u;
         if (tokeep) far2[bk + __popc(mk & ltmask)] = u;
       }
-      __syncthreads();
+      team_sync<TEAM>();
       n_mid = S.n_keep;
       n_far = S.n_next;
       { uint32_t* t = far; far = far2; far2 = t; }
-      if (n_mid < 256) delta_mid = __fmul_rn(delta_mid, 2.0f);                  // aim at 256..1024 candidates
-      else if (n_mid > 1024) delta_mid = __fmul_rn(delta_mid, 0.5f);
-      __syncthreads();
-      if (threadIdx.x == 0) { S.n_keep = 0; S.n_next = 0; }
-      __syncthreads();
+      if (n_mid < lo_mid) delta_mid = __fmul_rn(delta_mid, 2.0f);                  // aim at 256..1024 candidates per CTA
+      else if (n_mid > hi_mid) delta_mid = __fmul_rn(delta_mid, 0.5f);
+      team_sync<TEAM>();
+      if (tid == 0) { S.n_keep = 0; S.n_next = 0; }
+      team_sync<TEAM>();
       continue;
     }
     // ---- (a) smallest tentative distance in the mid band ----
     uint32_t mn = 0xffffffffu;
-    for (uint32_t i0 = threadIdx.x; i0 < n_mid; i0 += 4 * kThreads) {
+    for (uint32_t i0 = tid; i0 < n_mid; i0 += 4 * nth) {
       uint32_t id[4], dv[4];
 #pragma unroll
-      for (int q = 0; q < 4; q++) { const uint32_t i = i0 + q * kThreads; id[q] = (i < n_mid) ? mid[i] : 0xffffffffu; }
+      for (int q = 0; q < 4; q++) { const uint32_t i = i0 + q * nth; id[q] = (i < n_mid) ? mid[i] : 0xffffffffu; }
 #pragma unroll
       for (int q = 0; q < 4; q++) dv[q] = (id[q] != 0xffffffffu) ? __float_as_uint(__ldcg(&A.dist[id[q]])) : 0xffffffffu;
 #pragma unroll
       for (int q = 0; q < 4; q++) mn = min(mn, dv[q]);
     }
-    mn = block_min_u32(mn, S.red32);
+    mn = team_min_u32<TEAM>(mn, S, Lc, T);
     const uint32_t bound = (uint32_t)(S.best >> 32);
     uint32_t thr = __float_as_uint(__fadd_rn(__uint_as_float(mn), delta));
     if (thr > bound) thr = bound;
     // ---- (b) split the band: <= thr expand now, <= bound keep, else drop ----
-    for (uint32_t i0 = 0; i0 < n_mid; i0 += kThreads) {
-      const uint32_t i = i0 + threadIdx.x;
+    for (uint32_t i0 = 0; i0 < n_mid; i0 += nth) {
+      const uint32_t i = i0 + tid;
       bool toproc = false, tokeep = false;
       uint32_t u = 0;
       if (i < n_mid) {
@@ -320,18 +405,18 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
       if (toproc) proc[bp + __popc(mp & ltmask)] = u;
       if (tokeep) mid2[bk + __popc(mk & ltmask)] = u;
     }
-    __syncthreads();
+    team_sync<TEAM>();
     const uint32_t n_proc = S.n_proc;
     // ---- (c) expand the batch: lane per neighbour, TWO voxels per warp iteration so that their chains of
     //          dependent global accesses (stamp/dist of u -> label/weight of v -> atomicMin -> stamp of v) overlap ----
-    for (uint32_t it = warp; it < n_proc; it += 2 * kWarps) {
+    for (uint32_t it = tw; it < n_proc; it += 2 * ntw) {
       uint32_t u[2], v[2], lv[2], nd[2], old[2];
       float du[2], c[2];
       bool ok[2], relaxed[2], push_mid[2], push_far[2];
 #pragma unroll
       for (int e = 0; e < 2; e++) {
-        ok[e] = it + e * kWarps < n_proc;
-        u[e] = ok[e] ? proc[it + e * kWarps] : 0u;
+        ok[e] = it + e * ntw < n_proc;
+        u[e] = ok[e] ? proc[it + e * ntw] : 0u;
         if (ok[e] && lane == 0) atomicExch(&A.stamp[u[e]], 0u);   // from here on an improvement of u re-queues it
       }
       __syncwarp();
@@ -356,7 +441,7 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
             atomicMin(&S.best, ((unsigned long long)__float_as_uint(du[e]) << 32) | u[e]);   // rule T4 candidate
           } else {
             nd[e] = __float_as_uint(__fadd_rn(du[e], c[e]));
-            if (nd[e] <= (uint32_t)(S.best >> 32)) {
+            if (nd[e] <= (uint32_t)(t_peek<TEAM>(&S.best) >> 32)) {
               old[e] = atomicMin(reinterpret_cast<uint32_t*>(&A.dist[v[e]]), nd[e]);
               relaxed[e] = nd[e] < old[e];
             }
@@ -365,10 +450,17 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
       }
 #pragma unroll
       for (int e = 0; e < 2; e++) {
+        const bool fresh = relaxed[e] && old[e] == kInfBits;            // first time this search reaches v
+        const uint32_t mt = __ballot_sync(0xffffffffu, fresh);
+        if (mt) {
+          uint32_t bt = 0;
+          if (lane == 0) bt = atomicAdd(&S.n_touched, __popc(mt));
+          bt = __shfl_sync(0xffffffffu, bt, 0);
+          if (fresh) touched[bt + __popc(mt & ltmask)] = v[e];
+        }
         if (relaxed[e]) {
           relax++;
-          if (old[e] == kInfBits) touched[atomicAdd(&S.n_touched, 1u)] = v[e];
-          __threadfence_block();
+          if (TEAM) __threadfence(); else __threadfence_block();
           if (atomicExch(&A.stamp[v[e]], 1u) == 0u) { push_mid[e] = nd[e] <= thr_mid; push_far[e] = !push_mid[e]; }
         }
       }
@@ -388,24 +480,24 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
         }
       }
     }
-    __syncthreads();
+    team_sync<TEAM>();
     n_mid = S.n_keep;
     n_far += S.n_next;
     { uint32_t* t = mid; mid = mid2; mid2 = t; }
     // batch-size feedback: keep roughly 2..8 voxels per warp in flight
-    if (n_proc < 2 * kWarps) delta = __fmul_rn(delta, 2.0f);
-    else if (n_proc > 8 * kWarps) delta = __fmul_rn(delta, 0.5f);
+    if (n_proc < lo_proc) delta = __fmul_rn(delta, 2.0f);
+    else if (n_proc > hi_proc) delta = __fmul_rn(delta, 0.5f);
     rounds++;
-    __syncthreads();
-    if (threadIdx.x == 0) { S.n_keep = 0; S.n_proc = 0; S.n_next = 0; }
-    __syncthreads();
+    team_sync<TEAM>();
+    if (tid == 0) { S.n_keep = 0; S.n_proc = 0; S.n_next = 0; }
+    team_sync<TEAM>();
   }
   // anything still queued keeps stamp = 1; it is in `touched`, which resets it below
 
   // (d) walk back: rail voxel, then parents by rule T3
   uint32_t len = 0;
   const unsigned long long best = S.best;
-  if (warp == 0) {
+  if (tw == 0) {
     if (best == ~0ull) {
       if (lane == 0 && out_cap > 0) out[0] = target;
       len = 1;
@@ -455,39 +547,42 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
       if (lane == 0 && len < out_cap) out[len] = target;
       len++;
     }
-    if (lane == 0) S.red32[0] = len;
+    if (lane == 0) S.r32[0] = len;
   }
-  __syncthreads();
-  len = S.red32[0];
+  team_sync<TEAM>();
+  len = S.r32[0];
   // (e) reset the scratch fields of every voxel this search touched
   const uint32_t nt = S.n_touched;
-  for (uint32_t i = threadIdx.x; i < nt; i += kThreads) {
+  for (uint32_t i = tid; i < nt; i += nth) {
     const uint32_t v = touched[i];
     A.dist[v] = __int_as_float(kInfBits);
     A.stamp[v] = 0;
   }
-  relax = block_sum_u32(relax, S.red32);
-  if (threadIdx.x == 0) { S.relax += relax; S.rounds += rounds; }
-  __syncthreads();
+  relax = team_sum_u32<TEAM>(relax, S, Lc, T);
+  if (tid == 0) { S.relax += relax; S.rounds += rounds; }
+  team_sync<TEAM>();
   return len;
 }
 
 // ---- roll_invalidation_ball_inside_component ---------------------------------------------------------
 // seeds[0..n_seeds) are path voxels in path order; radius_i = fl32(fl32(scale * DBF[seed]) + const)
 // (skeletontricks.pyx:393-395 under NumPy-2 scalar rules).  Returns the number of voxels invalidated.
+template <bool TEAM>
 __device__ uint32_t invalidate(const Arena& A, const LabelDesc& L, const uint32_t* seeds, uint32_t n_seeds, float scale,
-                               float konst, uint32_t* fvA, uint32_t* fsA, uint32_t* fvB, uint32_t* fsB, Shared& S) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                               float konst, uint32_t* fvA, uint32_t* fsA, uint32_t* fvB, uint32_t* fsB, Shared& S,
+                               Team& T) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t tid = t_tid<TEAM>(T), nth = t_threads<TEAM>(), tw = t_warp<TEAM>(T), ntw = t_warps<TEAM>();
   const uint32_t seg = L.segid;
   int dx = 0, dy = 0, dz = 0;
   if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; }
   const int64_t off = (int64_t)dx + (int64_t)dy * A.d.sx + (int64_t)dz * A.d.sxy;
   const uint32_t ltmask = (1u << lane) - 1u;
-  if (threadIdx.x == 0) { S.n_next = 0; }
-  __syncthreads();
+  if (tid == 0) { S.n_next = 0; }
+  team_sync<TEAM>();
   // round 0: every still-valid seed claims itself
-  for (uint32_t i0 = 0; i0 < n_seeds; i0 += kThreads) {
-    const uint32_t i = i0 + threadIdx.x;
+  for (uint32_t i0 = 0; i0 < n_seeds; i0 += nth) {
+    const uint32_t i = i0 + tid;
     bool won = false;
     uint32_t v = 0;
     if (i < n_seeds) {
@@ -500,14 +595,14 @@ __device__ uint32_t invalidate(const Arena& A, const LabelDesc& L, const uint32_
     base = __shfl_sync(0xffffffffu, base, 0);
     if (won) { const uint32_t p = base + __popc(m & ltmask); fvA[p] = v; fsA[p] = i; }
   }
-  __syncthreads();
+  team_sync<TEAM>();
   uint32_t n_cur = S.n_next, total = n_cur;
   uint32_t *fv = fvA, *fs = fsA, *nv = fvB, *ns = fsB;
   while (n_cur > 0) {
-    __syncthreads();
-    if (threadIdx.x == 0) S.n_next = 0;
-    __syncthreads();
-    for (uint32_t it = warp; it < n_cur; it += kWarps) {
+    team_sync<TEAM>();
+    if (tid == 0) S.n_next = 0;
+    team_sync<TEAM>();
+    for (uint32_t it = tw; it < n_cur; it += ntw) {
       const uint32_t u = fv[it], s = fs[it];
       const uint32_t o = seeds[s];
       const float r = __fadd_rn(__fmul_rn(scale, __ldg(&A.dbf[o])), konst);
@@ -541,10 +636,10 @@ __device__ uint32_t invalidate(const Arena& A, const LabelDesc& L, const uint32_
         if (push) nv[base + __popc(m & ltmask)] = v;
       }
     }
-    __syncthreads();
+    team_sync<TEAM>();
     const uint32_t n_next = S.n_next;
     // end of round: winners become claimed (0) and carry their owner into the next frontier
-    for (uint32_t i = threadIdx.x; i < n_next; i += kThreads) {
+    for (uint32_t i = tid; i < n_next; i += nth) {
       const uint32_t v = nv[i];
       const unsigned long long c = __ldcg(&A.claim[v]);
       ns[i] = (uint32_t)c;
@@ -553,7 +648,7 @@ __device__ uint32_t invalidate(const Arena& A, const LabelDesc& L, const uint32_
     total += n_next;
     n_cur = n_next;
     { uint32_t* t = fv; fv = nv; nv = t; t = fs; fs = ns; ns = t; }
-    __syncthreads();
+    team_sync<TEAM>();
   }
   return total;
 }
@@ -568,20 +663,22 @@ __device__ uint32_t invalidate(const Arena& A, const LabelDesc& L, const uint32_
 // all open candidates whose key is the smallest one or below (smallest + delta), then the new owners push candidates
 // to their neighbours with atomicMin -- a min-reduction, so the order inside a round does not matter.
 // act / act2: open candidates (ping-pong), fv / fs: the voxels claimed in this round and their seeds.
+template <bool TEAM>
 __device__ __noinline__ uint32_t invalidate_window(const Arena& A, const LabelDesc& L, const uint32_t* seeds, uint32_t n_seeds,
                                                    float scale, float konst, float delta, uint32_t* act, uint32_t* fv,
-                                                   uint32_t* fs, uint32_t* act2, Shared& S) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                                   uint32_t* fs, uint32_t* act2, Shared& S, Local& Lc, Team& T) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t tid = t_tid<TEAM>(T), nth = t_threads<TEAM>(), tw = t_warp<TEAM>(T), ntw = t_warps<TEAM>();
   const uint32_t seg = L.segid;
   int dx = 0, dy = 0, dz = 0;
   if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; }
   const int64_t off = (int64_t)dx + (int64_t)dy * A.d.sx + (int64_t)dz * A.d.sxy;
   const uint32_t ltmask = (1u << lane) - 1u;
-  if (threadIdx.x == 0) { S.n_next = 0; S.n_keep = 0; }
-  __syncthreads();
+  if (tid == 0) { S.n_next = 0; S.n_keep = 0; }
+  team_sync<TEAM>();
   // round 0: every still-valid seed claims itself (key 0)
-  for (uint32_t i0 = 0; i0 < n_seeds; i0 += kThreads) {
-    const uint32_t i = i0 + threadIdx.x;
+  for (uint32_t i0 = 0; i0 < n_seeds; i0 += nth) {
+    const uint32_t i = i0 + tid;
     bool won = false;
     uint32_t v = 0;
     if (i < n_seeds) {
@@ -594,11 +691,11 @@ __device__ __noinline__ uint32_t invalidate_window(const Arena& A, const LabelDe
     base = __shfl_sync(0xffffffffu, base, 0);
     if (won) { const uint32_t p = base + __popc(m & ltmask); fv[p] = v; fs[p] = i; }
   }
-  __syncthreads();
+  team_sync<TEAM>();
   uint32_t n_cur = S.n_next, n_act = 0, total = n_cur;
   while (n_cur > 0) {
     // the voxels claimed in the last round push candidates; a voxel that gets its first one joins the open list
-    for (uint32_t it = warp; it < n_cur; it += kWarps) {
+    for (uint32_t it = tw; it < n_cur; it += ntw) {
       const uint32_t u = fv[it], s = fs[it];
       const uint32_t o = seeds[s];
       const float r = __fadd_rn(__fmul_rn(scale, __ldg(&A.dbf[o])), konst);
@@ -631,19 +728,19 @@ __device__ __noinline__ uint32_t invalidate_window(const Arena& A, const LabelDe
         if (push) act[n_act + base + __popc(m & ltmask)] = v;
       }
     }
-    __syncthreads();
+    team_sync<TEAM>();
     n_act += S.n_keep;
-    __syncthreads();
-    if (threadIdx.x == 0) { S.n_next = 0; S.n_keep = 0; S.n_proc = 0; }
+    team_sync<TEAM>();
+    if (tid == 0) { S.n_next = 0; S.n_keep = 0; S.n_proc = 0; }
     if (n_act == 0) break;
     // smallest open key (non-negative floats order like their bit patterns)
     uint32_t kmin = 0xffffffffu;
-    for (uint32_t i = threadIdx.x; i < n_act; i += kThreads) kmin = min(kmin, (uint32_t)(__ldcg(&A.claim[act[i]]) >> 32));
-    kmin = block_min_u32(kmin, S.red32);           // also orders the counter reset above before the appends below
+    for (uint32_t i = tid; i < n_act; i += nth) kmin = min(kmin, (uint32_t)(__ldcg(&A.claim[act[i]]) >> 32));
+    kmin = team_min_u32<TEAM>(kmin, S, Lc, T);     // also orders the counter reset above before the appends below
     const float lim = __fadd_rn(__uint_as_float(kmin), delta);
     // claim what is inside the window, keep the rest open
-    for (uint32_t i0 = 0; i0 < n_act; i0 += kThreads) {
-      const uint32_t i = i0 + threadIdx.x;
+    for (uint32_t i0 = 0; i0 < n_act; i0 += nth) {
+      const uint32_t i = i0 + tid;
       bool take = false, keep = false;
       uint32_t v = 0, owner = 0;
       if (i < n_act) {
@@ -664,18 +761,19 @@ __device__ __noinline__ uint32_t invalidate_window(const Arena& A, const LabelDe
       if (take) { const uint32_t p = bt + __popc(mt & ltmask); fv[p] = v; fs[p] = owner; }
       if (keep) act2[bk + __popc(mk & ltmask)] = v;
     }
-    __syncthreads();
+    team_sync<TEAM>();
     n_cur = S.n_next;
     n_act = S.n_proc;
     total += n_cur;
     { uint32_t* t = act; act = act2; act2 = t; }
-    __syncthreads();
-    if (threadIdx.x == 0) { S.n_keep = 0; }
-    __syncthreads();
+    team_sync<TEAM>();
+    if (tid == 0) { S.n_keep = 0; }
+    team_sync<TEAM>();
   }
-  __syncthreads();
+  team_sync<TEAM>();
   return total;
 }
+
 // ---- the same, LITERALLY: std::priority_queue<HeapDistanceNode, vector, HeapDistanceNodeCompare> on one warp ----------
 // dijkstra_invalidation.hpp:233-237, 291-329.  The reference's comparator `t1.dist >= t2.dist` is not a strict weak
 // order, so which of two entries with equal keys is popped first is whatever libstdc++'s push_heap / pop_heap
@@ -781,13 +879,14 @@ __device__ __forceinline__ void heap_pop(WarpHeap& H, uint32_t& tk, uint32_t& tv
 }
 
 // Returns the number of voxels invalidated; S.n_proc = 1 when the heap outgrew both its region and the spill arena.
+template <bool TEAM>
 __device__ __noinline__ uint32_t invalidate_strict(const Arena& A, const LabelDesc& L, const Pools& P, uint32_t job,
                                                    const uint32_t* seeds, uint32_t n_seeds, float scale, float konst,
-                                                   Shared& S) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { S.n_next = 0; S.n_proc = 0; }
-  __syncthreads();
-  if (warp == 0) {
+                                                   Shared& S, Team& T) {
+  const int lane = threadIdx.x & 31;
+  if (t_tid<TEAM>(T) == 0) { S.n_next = 0; S.n_proc = 0; }
+  team_sync<TEAM>();
+  if (t_warp<TEAM>(T) == 0) {
     const uint32_t seg = L.segid;
     WarpHeap H;
     bool overflow = false;
@@ -869,16 +968,18 @@ __device__ __noinline__ uint32_t invalidate_strict(const Arena& A, const LabelDe
     }
     if (lane == 0) { S.n_next = total; S.n_proc = overflow ? 1u : 0u; S.heap_k = H.k; S.heap_cap = H.cap; }
   }
-  __syncthreads();
+  team_sync<TEAM>();
   return S.n_next;
 }
 
 // ---- dijkstra3d.path_from_parents on the parental field held in A.dist (fix_branching=False) ---------
 // parents follow rule T3 (neighbour with the smallest (dist, direction)); the path is returned in
 // source -> target order like the library does: out[0] = root ... out[len-1] = target.
+template <bool TEAM>
 __device__ uint32_t path_from_parents(const Arena& A, const LabelDesc& L, uint32_t target, uint32_t* out,
-                                      uint32_t out_cap, Shared& S) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                      uint32_t out_cap, Shared& S, Team& T) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = t_warp<TEAM>(T);
   const uint32_t seg = L.segid;
   int dx = 0, dy = 0, dz = 0;
   if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; }
@@ -911,23 +1012,25 @@ __device__ uint32_t path_from_parents(const Arena& A, const LabelDesc& L, uint32
       loc = (uint32_t)((int64_t)loc + (int64_t)kDX[dir] + (int64_t)kDY[dir] * A.d.sx + (int64_t)kDZ[dir] * A.d.sxy);
       guard++;
     }
-    if (lane == 0) S.red32[0] = len;
+    if (lane == 0) S.r32[0] = len;
   }
-  __syncthreads();
-  const uint32_t len = S.red32[0];
+  team_sync<TEAM>();
+  const uint32_t len = S.r32[0];
   const uint32_t n = len < out_cap ? len : out_cap;
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < n / 2; i += kThreads) {   // reverse: source first
+  team_sync<TEAM>();
+  for (uint32_t i = t_tid<TEAM>(T); i < n / 2; i += t_threads<TEAM>()) {   // reverse: source first
     const uint32_t a = out[i], b = out[n - 1 - i];
     out[i] = b; out[n - 1 - i] = a;
   }
-  __syncthreads();
+  team_sync<TEAM>();
   return len;
 }
 
 // ---- the per-label conductor (trace.py:196-267) ----------------------------------------------------
-__device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, const Params& prm, Shared& S,
-                            uint32_t job) {
+template <bool TEAM>
+__device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, const Params& prm, Shared& S, Local& Lc,
+                            Team& T, uint32_t job) {
+  const uint32_t tid = t_tid<TEAM>(T), nth = t_threads<TEAM>();
   uint32_t* scr = P.scratch + 6ull * L.region_off;
   uint32_t* r0 = scr;
   uint32_t* r1 = scr + L.n_fg;
@@ -937,20 +1040,20 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
   uint32_t* r5 = scr + 5ull * L.n_fg;
   uint32_t* out = P.paths + L.path_off;
   unsigned long long t_start = 0;
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     B2T_GLOBALTIMER(t_start);
     S.bucket = prm.nbuckets - 1;
     S.relax = 0; S.rounds = 0; S.invalidated = 0;
     S.heap_cap = 0;
     A.pdrf[L.root] = 0.0f;      // parents[root] = 0: the first rail (trace.py:220)
   }
-  __syncthreads();
+  team_sync<TEAM>();
   uint32_t valid = L.n_fg;
   int32_t status = 0;
   if (L.soma_mode) {            // one-off soma invalidation around the root (trace.py:160-168)
-    // a single seed has no competitor: both claim orders give the same set
+    // a single seed has no competitor: every claim order gives the same set
     const uint32_t n = L.soma_done ? L.pre_invalid
-                                   : invalidate(A, L, &L.root, 1, prm.soma_scale, prm.soma_const, r0, r1, r2, r3, S);
+                                   : invalidate<TEAM>(A, L, &L.root, 1, prm.soma_scale, prm.soma_const, r0, r1, r2, r3, S, T);
     valid -= min(valid, n);
   }
   uint32_t tb_n = L.tb_n, ta_n = L.ta_n;
@@ -962,20 +1065,20 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
     if (tb_n > 0) target = P.targets[L.tb_off + (--tb_n)];
     else if (valid == 0) target = P.targets[L.ta_off + (--ta_n)];
     else {
-      target = find_target(A, L, P, prm, S);
+      target = find_target<TEAM>(A, L, P, prm, S, Lc, T);
       if (target == 0xffffffffu) { status = -10; break; }   // bookkeeping mismatch: valid > 0 but no valid voxel
     }
     if (used + 2 > L.path_cap) { status = B2T_ERR_CAPACITY; break; }
     uint32_t* pout = out + used;
     const uint32_t cap = L.path_cap - used - 1;
-    uint32_t len = prm.fix_branching ? railroad(A, L, target, r0, r1, r2, r4, r5, r3, pout, cap, S)
-                                     : path_from_parents(A, L, target, pout, cap, S);
+    uint32_t len = prm.fix_branching ? railroad<TEAM>(A, L, target, r0, r1, r2, r4, r5, r3, pout, cap, S, Lc, T)
+                                     : path_from_parents<TEAM>(A, L, target, pout, cap, S, T);
     if (len > cap) { status = B2T_ERR_CAPACITY; break; }
     if (L.soma_mode) {
       // keep path[:1] + points farther than soma_radius from the root; float64, uint32 wrap
       int rx, ry, rz;
       unravel(L.root, A.d, rx, ry, rz);
-      if (threadIdx.x == 0) {
+      if (tid == 0) {
         uint32_t k = 0;
         r0[k++] = pout[0];
         for (uint32_t i = 0; i < len; i++) {
@@ -989,36 +1092,36 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
             k++;
           }
         }
-        S.red32[1] = k;
+        S.r32[1] = k;
       }
-      __syncthreads();
-      const uint32_t k = S.red32[1];
+      team_sync<TEAM>();
+      const uint32_t k = S.r32[1];
       if (k > cap || k > L.n_fg) { status = B2T_ERR_CAPACITY; break; }
-      for (uint32_t i = threadIdx.x; i < k; i += kThreads) pout[i] = r0[i];
+      for (uint32_t i = tid; i < k; i += nth) pout[i] = r0[i];
       len = k;
-      __syncthreads();
+      team_sync<TEAM>();
     }
     if (valid > 0) {
       uint32_t n;
       if (prm.inval_mode == B2T_INVALIDATE_STRICT) {
-        n = invalidate_strict(A, L, P, job, pout, len, prm.scale, prm.konst, S);
+        n = invalidate_strict<TEAM>(A, L, P, job, pout, len, prm.scale, prm.konst, S, T);
         if (S.n_proc) { status = B2T_ERR_CAPACITY; break; }
       } else if (prm.inval_mode == B2T_INVALIDATE_WINDOW) {
-        n = invalidate_window(A, L, pout, len, prm.scale, prm.konst, prm.claim_window, r0, r1, r2, r3, S);
+        n = invalidate_window<TEAM>(A, L, pout, len, prm.scale, prm.konst, prm.claim_window, r0, r1, r2, r3, S, Lc, T);
       } else {
-        n = invalidate(A, L, pout, len, prm.scale, prm.konst, r0, r1, r2, r3, S);
+        n = invalidate<TEAM>(A, L, pout, len, prm.scale, prm.konst, r0, r1, r2, r3, S, T);
       }
       valid -= min(valid, n);
-      if (threadIdx.x == 0) S.invalidated += n;
+      if (tid == 0) S.invalidated += n;
     }
     if (prm.fix_branching)
-      for (uint32_t i = threadIdx.x; i < len; i += kThreads) A.pdrf[pout[i]] = 0.0f;   // trace.py:261-263
-    if (threadIdx.x == 0) pout[len] = 0xffffffffu;
+      for (uint32_t i = tid; i < len; i += nth) A.pdrf[pout[i]] = 0.0f;   // trace.py:261-263
+    if (tid == 0) pout[len] = 0xffffffffu;
     used += len + 1;
     npaths++;
-    __syncthreads();
+    team_sync<TEAM>();
   }
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     P.out_len[job] = used;
     P.out_npaths[job] = npaths;
     P.out_status[job] = status;
@@ -1027,23 +1130,36 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
     P.out_stats[4 * job + 2] = S.invalidated;
     unsigned long long t_end;
     B2T_GLOBALTIMER(t_end);
-    P.out_stats[4 * job + 3] = (uint32_t)((t_end - t_start) / 1000ull);   // microseconds this label held its CTA
+    P.out_stats[4 * job + 3] = (uint32_t)((t_end - t_start) / 1000ull);   // microseconds this label held its team
   }
-  __syncthreads();
+  team_sync<TEAM>();
 }
 
-__global__ void __launch_bounds__(kThreads, B2T_TRACE_MINB) trace_kernel(Arena A, const LabelDesc* __restrict__ descs, Pools P, Params prm) {
+// Grid: n_team clusters, each a team for job c (the caller sorts the jobs by size, largest first), then clusters whose
+// CTAs work alone and pull the remaining jobs from the work counter.  d_team: one Shared slot per team in global memory.
+__global__ void __launch_bounds__(kThreads, B2T_TRACE_MINB) trace_kernel(Arena A, const LabelDesc* __restrict__ descs, Pools P,
+                                                                         Params prm, uint32_t n_team, Shared* d_team) {
   __shared__ Shared S;
+  __shared__ Local Lc;
   __shared__ LabelDesc L;
+  const uint32_t cid = blockIdx.x / kCluster;
+  Team T{blockIdx.x % kCluster, 0u};
+  if (cid < n_team) {
+    if (threadIdx.x == 0) L = descs[cid];
+    __syncthreads();
+    trace_label<true>(A, L, P, prm, d_team[cid], Lc, T, cid);
+    return;
+  }
+  T.rank = 0;
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) S.job = atomicAdd(P.work_counter, 1u);
+    if (threadIdx.x == 0) S.job = n_team + atomicAdd(P.work_counter, 1u);
     __syncthreads();
     const uint32_t job = S.job;
     if (job >= (uint32_t)prm.n_desc) return;
     if (threadIdx.x == 0) L = descs[job];
     __syncthreads();
-    trace_label(A, L, P, prm, S, job);
+    trace_label<false>(A, L, P, prm, S, Lc, T, job);
   }
 }
 
@@ -1063,6 +1179,9 @@ B2T_EXPORT uint64_t b2t_trace_heap_words(uint64_t sum_n_fg, uint64_t n_desc) {
   return 2ull + 3ull * ((uint64_t)kHeapPerVoxel * sum_n_fg + (uint64_t)kHeapSlack * n_desc);
 }
 
+// bytes of one team slot (d_team of b2t_trace_batch holds n_team of them)
+B2T_EXPORT uint64_t b2t_trace_team_bytes(void) { return sizeof(Shared); }
+
 #ifndef B2T_HOST_EMU
 B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,
                                uint32_t* d_stamp, int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
@@ -1073,7 +1192,7 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
                                const uint32_t* d_targets, uint32_t* d_out_len, uint32_t* d_out_npaths,
                                int32_t* d_out_status, uint32_t* d_out_stats, uint32_t* d_work_counter,
                                int invalidation_mode, float claim_window_voxels, uint32_t* d_heap, uint64_t heap_words,
-                               uint64_t heap_static_words, void* stream) {
+                               uint64_t heap_static_words, int n_team, void* d_team, void* stream) {
   static_assert(sizeof(LabelDesc) == 80, "LabelDesc must stay 20 x 4 bytes (mirrored in kimimaro_b200/engine.py)");
   B2T_REQUIRE(sx > 0 && sy > 0 && sz > 0 && (double)sx * sy * sz < 4294967295.0, "bad volume shape");
   B2T_REQUIRE(invalidation_mode == B2T_INVALIDATE_ROUNDS || invalidation_mode == B2T_INVALIDATE_WINDOW ||
@@ -1083,6 +1202,8 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
   B2T_REQUIRE(invalidation_mode != B2T_INVALIDATE_STRICT ||
                   (d_heap != nullptr && heap_static_words >= 2 && heap_words >= heap_static_words),
               "b2t_trace_batch: the strict mode needs a heap buffer (b2t_trace_heap_words)");
+  B2T_REQUIRE(n_team >= 0 && n_team <= n_desc && (n_team == 0 || d_team != nullptr),
+              "b2t_trace_batch: n_team out of range or no d_team (b2t_trace_team_bytes)");
   if (n_desc <= 0) return B2T_OK;
   cudaStream_t st = (cudaStream_t)stream;
   Arena A;
@@ -1114,10 +1235,21 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
   B2T_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel, kThreads, 0));
   if (per_sm < 1) per_sm = 1;
   if (b2t_trace_limit() > 0 && per_sm > b2t_trace_limit()) per_sm = b2t_trace_limit();
-  int blocks = sms * per_sm;
-  if (blocks > n_desc) blocks = n_desc;
-  trace_kernel<<<blocks, kThreads, 0, st>>>(A, reinterpret_cast<const LabelDesc*>(d_desc), P, prm);
-  B2T_CUDA_TRY(cudaGetLastError());
+  int solo = sms * per_sm;
+  if (solo > n_desc - n_team) solo = n_desc - n_team;
+  const int clusters = n_team + (solo + kCluster - 1) / kCluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * kCluster));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B2T_CUDA_TRY(cudaLaunchKernelEx(&cfg, trace_kernel, A, reinterpret_cast<const LabelDesc*>(d_desc), P, prm,
+                                  (uint32_t)n_team, reinterpret_cast<Shared*>(d_team)));
   b2t_count_launches(1);
   return B2T_OK;
 }

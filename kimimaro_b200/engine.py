@@ -36,8 +36,9 @@ _lib.declare("b2t_pdrf_and_buckets", [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64
                                       c_vp, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp])
 _lib.declare("b2t_trace_batch", [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32,
                                  c_vp, c_int, c_f32, c_f32, c_f32, c_f32, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_vp, c_u64, c_u64, c_vp])
+                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_vp, c_u64, c_u64, c_int, c_vp, c_vp])
 _lib.declare("b2t_trace_heap_words", [c_u64, c_u64], c_u64)
+_lib.declare("b2t_trace_team_bytes", [], c_u64)
 _lib.declare("b2t_ccl26_roots", [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp])
 _lib.declare("b2t_ccl_relabel", [c_vp, c_vp, c_u64, c_vp])
 _lib.declare("b2t_invalidate_ball", [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_u32, c_f32, c_f32,
@@ -463,7 +464,8 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   counter = torch.zeros(1, dtype=torch.int32, device=dev)
   ws.stamp.zero_()
   launch = dict(d_cc=d_cc, d_dbf=d_dbf, pdrf=pdrf, ws=ws, claim=claim, shape=shape, anisotropy=anisotropy, params=params,
-                fix_branching=fix_branching, keys=keys, hist=hist, cursor=cursor, scratch=scratch, d_targets=d_targets)
+                fix_branching=fix_branching, keys=keys, hist=hist, cursor=cursor, scratch=scratch, d_targets=d_targets,
+                nfg_sorted=nfg)
   heap = _launch_trace(launch, d_desc, n_jobs, int(nfg.sum()), int(nfg.max()) if n_jobs else 0, paths, out_len, out_np,
                        out_status, out_stats, counter)
   keep = (ws, pdrf, claim, keys, hist, cursor, scratch, d_desc, d_targets, counter, heap)   # alive until the kernel is done
@@ -472,10 +474,18 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
               again=(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings), pool_scale=int(pool_scale))
 
 
+# the path loop of a label above TRACE_TEAM_MIN voxels runs on a thread-block cluster (at most TRACE_TEAM_MAX of them)
+TRACE_TEAM_MIN = int(os.environ.get("B2T_TRACE_TEAM_MIN", 100000))
+TRACE_TEAM_MAX = int(os.environ.get("B2T_TRACE_TEAM_MAX", 24))
+
+
 def _launch_trace(la, d_desc, n_jobs, sum_nfg, max_nfg, paths, out_len, out_np, out_status, out_stats, counter):
-  """b2t_trace_batch with the invalidation mode of _lib.invalidation_mode(); returns the strict mode's heap buffer."""
+  """b2t_trace_batch with the invalidation mode of _lib.invalidation_mode(); returns the buffers the kernel needs alive
+  (the strict mode's heap, the teams' state)."""
   L = lib()
   mode, window = _lib.invalidation_mode()
+  n_team = min(int((la["nfg_sorted"] >= TRACE_TEAM_MIN).sum()), TRACE_TEAM_MAX, n_jobs)
+  team = torch.zeros(max(n_team, 1) * int(L.b2t_trace_team_bytes()), dtype=torch.uint8, device=paths.device)
   heap, heap_words, heap_static = None, 0, 0
   if mode == "strict":
     # static regions (4 entries per voxel) + a spill arena that can take the 27-entries-per-voxel worst case of the
@@ -495,9 +505,9 @@ def _launch_trace(la, d_desc, n_jobs, sum_nfg, max_nfg, paths, out_len, out_np, 
                           _p(la["cursor"]), _p(la["scratch"]), _p(paths), _p(la["d_targets"]),
                           _p(out_len), _p(out_np), _p(out_status), _p(out_stats), _p(counter),
                           c_int(_lib._MODES[mode]), c_f32(window), _p(heap), c_u64(heap_words), c_u64(heap_static),
-                          stream_ptr()),
+                          c_int(n_team), _p(team), stream_ptr()),
         "b2t_trace_batch")
-  return heap
+  return heap, team
 
 
 def trace_arena_finish(st):

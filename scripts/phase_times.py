@@ -37,6 +37,13 @@ free = (time.perf_counter() - t) / reps
 rec = {"env": {k: v for k, v in os.environ.items() if k.startswith("B2T_")}, "pass_ms_with_laps": round(1e3 * best[0], 2),
        "pass_ms": round(1e3 * free, 2),
        "phases_ms": {k: round(1e3 * v, 2) for k, v in best[1].items() if isinstance(v, float)}}
+st = best[1].get("kernel_stats")
+if st:
+  s0 = st[0]
+  top = np.argsort(-s0["stats"][:, 3].astype(np.int64))[:8]
+  rec["slowest_labels"] = [{"job": int(i), "us": int(s0["stats"][i, 3]), "npaths": int(s0["npaths"][i]),
+                           "rounds": int(s0["stats"][i, 1]), "relax": int(s0["stats"][i, 0]),
+                           "invalidated": int(s0["stats"][i, 2])} for i in top]
 gold = golden_digest("synth512_oracle_digest_window1.json") if n == 512 else None
 if gold:
   dg = skeleton_digests(sk)

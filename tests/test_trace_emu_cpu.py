@@ -37,7 +37,7 @@ def emu():
 ROUNDS, WINDOW, STRICT = 0, 1, 2
 
 
-def _engine(lib, vol, dbf, path, scale, const, an, window, mode=None, spill_words=0):
+def _engine(lib, vol, dbf, path, scale, const, an, window, mode=None, spill_words=0, team=0):
   sx, sy, sz = vol.shape
   cc = np.ascontiguousarray(vol.reshape(-1, order="F").astype(np.uint32))
   d = np.ascontiguousarray(dbf.reshape(-1, order="F").astype(np.float32))
@@ -50,13 +50,14 @@ def _engine(lib, vol, dbf, path, scale, const, an, window, mode=None, spill_word
   n = lib.emu_invalidate(oracle._p(cc), oracle._p(d), oracle._p(claim), sx, sy, sz, ctypes.c_float(an[0]),
                          ctypes.c_float(an[1]), ctypes.c_float(an[2]), 1, int(vol.sum()), oracle._p(seeds), int(seeds.size),
                          ctypes.c_float(scale), ctypes.c_float(const), ctypes.c_float(delta), mode,
-                         ctypes.c_long(spill_words))
+                         ctypes.c_long(spill_words), team)
   mask = ((claim != 0) & (cc == 1)).astype(np.uint8).reshape(vol.shape, order="F")
   return int(n), mask
 
 
+@pytest.mark.parametrize("team", [0, 1])
 @pytest.mark.parametrize("window", [0, 1.0, 0.5])
-def test_engine_invalidation_equals_oracle(emu, window):
+def test_engine_invalidation_equals_oracle(emu, window, team):
   rng = np.random.default_rng(17)
   mode = f"window:{window:g}" if window else "rounds"
   for trial in range(10):
@@ -70,7 +71,7 @@ def test_engine_invalidation_equals_oracle(emu, window):
       vol[hole] = 0
     ref = vol.copy(order="F")
     n_ref, ref = oracle.roll_invalidation_ball_inside_component(ref, dbf, scale, const, an, path, mode=mode)
-    n, mask = _engine(emu, vol, dbf, path, scale, const, an, window)
+    n, mask = _engine(emu, vol, dbf, path, scale, const, an, window, team=team)
     assert n == n_ref, (trial, n, n_ref)
     assert np.array_equal(mask, ref), (trial, int((mask != ref).sum()))
 
@@ -122,7 +123,7 @@ def test_engine_strict_heap_spills_and_reports_capacity(emu):
 
 
 # ---- the whole path loop (trace_kernel) on the emulated block against oracle.teasar.trace ----
-def _emulated_paths(lib, cc, n_cc, all_dbf, an, params, window, fix_borders_targets=None, mode=None):
+def _emulated_paths(lib, cc, n_cc, all_dbf, an, params, window, fix_borders_targets=None, mode=None, n_team=0):
   """Mirrors kimimaro_b200/engine.py:trace_arena_start for host arrays: per-label root / DAF / PDRF from the oracle's
   pieces (the GPU gets them from field.cu, verified on the GPU), one DAF bucket per label, then trace_kernel."""
   from oracle import teasar
@@ -186,7 +187,7 @@ def _emulated_paths(lib, cc, n_cc, all_dbf, an, params, window, fix_borders_targ
                       p(desc), n, cf(params["scale"]), cf(params["const"]), cf(0.5), cf(0.0), 1, 1, p(keys), p(hist),
                       p(cursor), p(scratch), p(paths), p(targets), p(out_len), p(out_np), p(out_status), p(out_stats),
                       p(counter), mode, cf(window * min(an)), p(heap), ctypes.c_uint64(heap.size if mode == STRICT else 0),
-                      ctypes.c_uint64(heap_static))
+                      ctypes.c_uint64(heap_static), n_team)
   assert (out_status == 0).all(), out_status
   got = {}
   for i in range(n):
@@ -198,8 +199,9 @@ def _emulated_paths(lib, cc, n_cc, all_dbf, an, params, window, fix_borders_targ
   return got
 
 
+@pytest.mark.parametrize("n_team", [0, 2])
 @pytest.mark.parametrize("window", [0, 1.0, "strict"])
-def test_engine_path_loop_equals_oracle(emu, window):
+def test_engine_path_loop_equals_oracle(emu, window, n_team):
   """find_target -> railroad -> invalidate -> rail, label after label, on the source text the GPU runs: every path of
   every label must be the oracle's, voxel for voxel and in the same order, under the key-ordered claim the engine ships
   (window 1, oracle mode 'window:1'), under the strict mode (oracle mode 'heap' == the compiled reference) and under the
@@ -221,7 +223,7 @@ def test_engine_path_loop_equals_oracle(emu, window):
     cc = np.asfortranarray(np.where(np.isin(cc, keep), cc, 0))
     cc, n_cc = oracle.connected_components(cc)
     all_dbf = oracle.edt(cc, an, False)
-    got = _emulated_paths(emu, cc, n_cc, all_dbf, an, params, window, mode=emode)
+    got = _emulated_paths(emu, cc, n_cc, all_dbf, an, params, window, mode=emode, n_team=min(n_team, n_cc))
     sx, sy, sz = cc.shape
     for l in range(1, n_cc + 1):
       labels = np.asfortranarray(cc == l)
