@@ -172,7 +172,7 @@ int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist
  *   None), soma_mode, soma_radius (float32), bucket_row, soma_done, pre_invalid, bbox_x0, bbox_x1 (x extent of the
  *   label's bounding box: the reference runs on that crop, intake.py:463-466, and STRICT reproduces the duplicate
  *   pushes of its neighbour table at the crop's x faces), two reserved words
- * d_scratch: 6*sum(n_fg) u32; d_paths: pool of voxel indices, each path [rail ... target] terminated by
+ * d_scratch: b2t_trace_scratch_words(sum(n_fg)) u32; d_paths: pool of voxel indices, each path [rail ... target] terminated by
  * 0xffffffff; d_out_len / d_out_npaths / d_out_status: n_desc; d_out_stats: 4*n_desc; d_work_counter: 1 u32.
  * invalidation_mode: B2T_INVALIDATE_*; claim_window_voxels: width of a WINDOW round.  STRICT only: d_heap holds heap_words
  * u32, of which the first heap_static_words = b2t_trace_heap_words(sum(n_fg), n_desc) are the labels' own heap regions
@@ -192,6 +192,7 @@ int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, flo
                     int invalidation_mode, float claim_window_voxels, uint32_t* d_heap, uint64_t heap_words,
                     uint64_t heap_static_words, int n_team, void* d_team, void* stream);
 uint64_t b2t_trace_team_bytes(void);
+uint64_t b2t_trace_scratch_words(uint64_t sum_n_fg);
 
 /* the same rolling-ball invalidation, grid-wide, for balls too large for one CTA (the one-off soma
  * invalidation, kimimaro/trace.py:160-168).  d_fv / d_fs: 2*cap u32 each; count left in d_ctrl[6]. */

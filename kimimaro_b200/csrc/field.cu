@@ -52,13 +52,14 @@ __global__ void label_stats_kernel(const uint32_t* __restrict__ cc, const float*
                                    uint32_t nseg_x, uint64_t nsegs, uint32_t n_labels, uint32_t* __restrict__ count,
                                    int* __restrict__ bbox, uint32_t* __restrict__ dbfmax_bits,
                                    uint32_t* __restrict__ first) {
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nsegs) return;
-  const uint32_t row = (uint32_t)(t / nseg_x);
-  const int x0 = (int)(t - (uint64_t)row * nseg_x) * kSeg;
+  const int lane = threadIdx.x & 31;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // blocks are whole warps: t - lane is warp-uniform
+  const bool have = t < nsegs;
+  const uint32_t row = have ? (uint32_t)(t / nseg_x) : 0u;
+  const int x0 = have ? (int)(t - (uint64_t)row * nseg_x) * kSeg : 0;
   const int y = row % (uint32_t)d.sy, z = row / (uint32_t)d.sy;
   const uint32_t base = row * (uint32_t)d.sx;
-  const int x1 = min(x0 + kSeg, d.sx);
+  const int x1 = have ? min(x0 + kSeg, d.sx) : 0;
   uint32_t cur = 0, cnt = 0;
   int xa = 0, xb = 0;
   float mx = 0.0f;
@@ -73,16 +74,39 @@ __global__ void label_stats_kernel(const uint32_t* __restrict__ cc, const float*
       atomicMin(&first[cur], base + (uint32_t)xa);
     }
   };
+  int nruns = 0;
   for (int x = x0; x < x1; x++) {
     const uint32_t l = cc[base + x];
     if (l != cur) {
       flush();
-      cur = l; cnt = 0; xa = x; mx = 0.0f;
+      cur = l; cnt = 0; xa = x; mx = 0.0f; nruns++;
     }
     cnt++; xb = x;
     if (dbf && l) mx = fmaxf(mx, dbf[base + x]);
   }
-  flush();
+  // The last run of every segment is settled together with the other lanes': the lanes of a warp are neighbouring segments
+  // (a whole 512-voxel row when sx = 512), so inside a large label they all carry the same label and one lane does the ten
+  // table atomics for the group instead of all of them.
+  const bool pending = have && cur != 0 && cur <= n_labels;
+  const uint32_t g = __match_any_sync(0xffffffffu, pending ? cur : 0xffffffffu);
+  if (pending) {
+    const uint32_t c_sum = __reduce_add_sync(g, cnt);
+    const int xa_min = (int)__reduce_min_sync(g, (uint32_t)xa), xb_max = (int)__reduce_max_sync(g, (uint32_t)xb);
+    const int y_min = (int)__reduce_min_sync(g, (uint32_t)y), y_max = (int)__reduce_max_sync(g, (uint32_t)y);
+    const int z_min = (int)__reduce_min_sync(g, (uint32_t)z), z_max = (int)__reduce_max_sync(g, (uint32_t)z);
+    const uint32_t mx_max = __reduce_max_sync(g, __float_as_uint(mx));      // non-negative floats order like their bits
+    const uint32_t f_min = __reduce_min_sync(g, base + (uint32_t)xa);
+    if (lane == __ffs((int)g) - 1) {
+      atomicAdd(&count[cur], c_sum);
+      int* b = bbox + 6 * (size_t)cur;
+      atomicMin(&b[0], xa_min); atomicMax(&b[3], xb_max);
+      atomicMin(&b[1], y_min); atomicMax(&b[4], y_max);
+      atomicMin(&b[2], z_min); atomicMax(&b[5], z_max);
+      if (dbf) atomicMax(&dbfmax_bits[cur], mx_max);
+      atomicMin(&first[cur], f_min);
+    }
+  }
+  (void)nruns;
 }
 
 __global__ void bbox_init_kernel(int* bbox, uint32_t n) {
@@ -407,26 +431,52 @@ __device__ __forceinline__ int daf_bucket(float daf, float inv, int nb) {
   return b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b);
 }
 
+// Lanes of a warp that hit the same table slot (key) elect a leader and tell every lane its rank and the group's size:
+// one atomic per distinct slot and warp instead of one per voxel.  The inside of a large label is thousands of
+// consecutive voxels with the same (label, bucket): without this, a soma's 19 M voxels queue up on 256 addresses.
+__device__ __forceinline__ void warp_group(bool valid, uint32_t key, int lane, bool& leader, uint32_t& rank, uint32_t& size,
+                                           int& leader_lane) {
+  const uint32_t g = __match_any_sync(0xffffffffu, valid ? key : 0xffffffffu);
+  leader_lane = __ffs((int)g) - 1;
+  leader = valid && lane == leader_lane;
+  rank = __popc(g & ((1u << lane) - 1u));
+  size = __popc(g);
+}
+
 __global__ void pdrf_kernel(PdrfParams p) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.V; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t l = p.cc[i];
-    if (l == 0 || l > p.n_labels || !p.active[l]) continue;
-    float dbf = p.dbf[i];
-    if (dbf == 0.0f) dbf = __int_as_float(kInfBits);           // zero2inf (trace.py:138)
-    float daf = p.daf[i];
-    if (__float_as_uint(daf) >= kInfBits) daf = 0.0f;           // inf2zero (trace.py:146)
-    float P = __fsub_rn(1.0f, __fmul_rn(dbf, p.M[l]));
-    if (p.n_squarings >= 0) {
-      for (int k = 0; k < p.n_squarings; k++) P = __fmul_rn(P, P);
-    } else {
-      P = powf(P, p.exponent);
+  const int lane = threadIdx.x & 31;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t i_first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint64_t base = i_first - lane; base < p.V; base += stride) {      // warp-uniform loop: the group vote needs all lanes
+    const uint64_t i = base + lane;
+    uint32_t l = 0;
+    bool valid = false;
+    if (i < p.V) {
+      l = p.cc[i];
+      valid = l != 0 && l <= p.n_labels && p.active[l];
     }
-    P = __fmul_rn(P, p.pdrf_scale);
-    const float inv = p.inv_maxdaf[l];
-    if (inv != 0.0f) P = __fadd_rn(P, __fmul_rn(daf, inv));
-    p.pdrf[i] = P;
-    p.claim[i] = ~0ull;
-    atomicAdd(&p.hist[(size_t)l * p.nbuckets + daf_bucket(daf, inv, p.nbuckets)], 1u);
+    uint32_t key = 0;
+    if (valid) {
+      float dbf = p.dbf[i];
+      if (dbf == 0.0f) dbf = __int_as_float(kInfBits);           // zero2inf (trace.py:138)
+      float daf = p.daf[i];
+      if (__float_as_uint(daf) >= kInfBits) daf = 0.0f;           // inf2zero (trace.py:146)
+      float P = __fsub_rn(1.0f, __fmul_rn(dbf, p.M[l]));
+      if (p.n_squarings >= 0) {
+        for (int k = 0; k < p.n_squarings; k++) P = __fmul_rn(P, P);
+      } else {
+        P = powf(P, p.exponent);
+      }
+      P = __fmul_rn(P, p.pdrf_scale);
+      const float inv = p.inv_maxdaf[l];
+      if (inv != 0.0f) P = __fadd_rn(P, __fmul_rn(daf, inv));
+      p.pdrf[i] = P;
+      p.claim[i] = ~0ull;
+      key = l * (uint32_t)p.nbuckets + (uint32_t)daf_bucket(daf, inv, p.nbuckets);
+    }
+    bool leader; uint32_t rank, size; int ll;
+    warp_group(valid, key, lane, leader, rank, size, ll);
+    if (leader) atomicAdd(&p.hist[key], size);
   }
 }
 
@@ -443,14 +493,33 @@ struct ScatterParams {
 };
 
 __global__ void bucket_scatter_kernel(ScatterParams p) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.V; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t l = p.cc[i];
-    if (l == 0 || l > p.n_labels || !p.active[l]) continue;
-    float daf = p.dist[i];
-    if (__float_as_uint(daf) >= kInfBits) daf = 0.0f;
-    const uint32_t pos = atomicAdd(&p.cursor[(size_t)l * p.nbuckets + daf_bucket(daf, p.inv_maxdaf[l], p.nbuckets)], 1u);
-    p.keys[pos] = ((unsigned long long)__float_as_uint(daf) << 32) | (unsigned long long)i;
-    p.dist[i] = __int_as_float(kInfBits);
+  const int lane = threadIdx.x & 31;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t i_first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint64_t base = i_first - lane; base < p.V; base += stride) {
+    const uint64_t i = base + lane;
+    uint32_t l = 0;
+    bool valid = false;
+    if (i < p.V) {
+      l = p.cc[i];
+      valid = l != 0 && l <= p.n_labels && p.active[l];
+    }
+    float daf = 0.0f;
+    uint32_t key = 0;
+    if (valid) {
+      daf = p.dist[i];
+      if (__float_as_uint(daf) >= kInfBits) daf = 0.0f;
+      key = l * (uint32_t)p.nbuckets + (uint32_t)daf_bucket(daf, p.inv_maxdaf[l], p.nbuckets);
+    }
+    bool leader; uint32_t rank, size; int ll;
+    warp_group(valid, key, lane, leader, rank, size, ll);
+    uint32_t pos = 0;
+    if (leader) pos = atomicAdd(&p.cursor[key], size);
+    pos = __shfl_sync(0xffffffffu, pos, ll);
+    if (valid) {
+      p.keys[pos + rank] = ((unsigned long long)__float_as_uint(daf) << 32) | (unsigned long long)i;
+      p.dist[i] = __int_as_float(kInfBits);
+    }
   }
 }
 
@@ -526,7 +595,7 @@ B2T_EXPORT int b2t_label_stats(const uint32_t* d_cc, const float* d_dbf, int64_t
   const uint32_t nseg_x = (uint32_t)((sx + kSeg - 1) / kSeg);
   const uint64_t nsegs = (uint64_t)nseg_x * sy * sz;
   const unsigned blocks = (unsigned)((nsegs + 255) / 256);
-  B2T_LAUNCH(label_stats_kernel, blocks, 256, st)(d_cc, d_dbf, d, nseg_x, nsegs, n_labels, d_count, d_bbox,
+  B2T_LAUNCH_SYNC(label_stats_kernel, blocks, 256, st)(d_cc, d_dbf, d, nseg_x, nsegs, n_labels, d_count, d_bbox,
                                              reinterpret_cast<uint32_t*>(d_dbfmax), d_first);
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(2);
@@ -665,12 +734,13 @@ B2T_EXPORT int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, fl
   p.V = V;
   const uint64_t want = (V + 255) / 256;
   const unsigned blocks = (unsigned)(want < 148ull * 32 ? want : 148ull * 32);
-  B2T_LAUNCH(pdrf_kernel, blocks, 256, st)(p);
+  B2T_REQUIRE(ntab < 0xffffffffull, "b2t_pdrf_and_buckets: (labels + 1) * nbuckets must stay below 2^32");
+  B2T_LAUNCH_SYNC(pdrf_kernel, blocks, 256, st)(p);
   B2T_LAUNCH_SYNC(exclusive_scan_kernel, 1, 1024, st)(d_hist, d_cursor, ntab);
   ScatterParams s;
   s.cc = d_cc; s.dist = d_dist; s.inv_maxdaf = d_inv_maxdaf; s.active = d_active; s.cursor = d_cursor;
   s.keys = reinterpret_cast<unsigned long long*>(d_keys); s.n_labels = n_labels; s.nbuckets = nbuckets; s.V = V;
-  B2T_LAUNCH(bucket_scatter_kernel, blocks, 256, st)(s);
+  B2T_LAUNCH_SYNC(bucket_scatter_kernel, blocks, 256, st)(s);
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(3);
   return B2T_OK;

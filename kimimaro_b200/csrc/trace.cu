@@ -51,6 +51,10 @@ constexpr int kHeapSlack = B2T_HEAP_SLACK;          // ... plus this many; a hea
 #define B2T_TRACE_MINB 3        // resident CTAs per SM (42 registers per thread)
 #endif
 constexpr int kWarps = kThreads / 32;
+constexpr int kScratchPerVoxel = 22;   // u32 of queue scratch per foreground voxel of a label (see trace_label); even
+#ifndef B2T_RR_CAP_SHIFT
+#define B2T_RR_CAP_SHIFT 0             // (the CPU harness shrinks railroad's lists to exercise the overflow rebuild)
+#endif
 
 struct Dims {
   int sx, sy, sz;
@@ -73,7 +77,7 @@ struct LabelDesc {
   uint32_t segid;       // value of this label in cc
   uint32_t root;        // linear index of the root voxel
   uint32_t n_fg;        // foreground voxels (np.count_nonzero(labels), trace.py:211)
-  uint32_t region_off;  // prefix sum of n_fg over the batch: scratch region starts at 6 * region_off
+  uint32_t region_off;  // prefix sum of n_fg over the batch: scratch region starts at kScratchPerVoxel * region_off
   uint32_t path_off;    // first slot of this label in the path pool
   uint32_t path_cap;    // slots available
   uint32_t tb_off, tb_n;  // manual_targets_before: targets[tb_off .. tb_off+tb_n), popped from the end
@@ -104,7 +108,7 @@ struct Pools {
   const unsigned long long* keys;  // bucket-partitioned (daf_bits << 32 | index)
   const uint32_t* hist;            // bucket sizes
   const uint32_t* cursor;          // bucket ends
-  uint32_t* scratch;               // 6 * sum(n_fg) u32
+  uint32_t* scratch;               // kScratchPerVoxel * sum(n_fg) u32
   uint32_t* paths;                 // path pool: voxel indices, each path terminated by 0xffffffff
   const uint32_t* targets;         // manual targets (linear indices)
   uint32_t* out_len;               // per desc: slots written
@@ -279,13 +283,33 @@ __device__ uint32_t find_target(const Arena& A, const LabelDesc& L, const Pools&
 
 // ---- dijkstra3d.railroad ----------------------------------------------------------------------------
 // Returns the path length written to out[0..): out[0] = rail voxel ... out[len-1] = target.
+//
+// Delta-stepping with a three-level pile of (tentative distance, voxel) PAIRS and lazy deletion:
+//   proc   the batch expanded this round: every entry at most `delta` above the smallest open distance
+//   mid    a bounded band (<= thr_mid) that is split every round into proc / keep
+//   far    everything beyond; scanned only when the band drains
+// A relaxation that improves a voxel appends a NEW pair; the pair it supersedes stays where it is and is recognised as
+// stale when its turn comes (its key is no longer the voxel's distance).  Selecting a batch therefore streams 8-byte pairs
+// instead of gathering one 32-byte sector per candidate and round from the distance field -- that gather was 25 of the
+// 31 GB of DRAM traffic of this kernel in round 1 -- and no "is queued" flag per voxel is needed.  Relaxation order never
+// changes the result (the distances are the least fixed point of d[v] = min_u fl(d[u] + w[v])).
+// A list that would overflow (stale pairs pile up; live ones are at most one per voxel) raises a flag, and the pile is
+// rebuilt from the list of touched voxels: every voxel whose distance is not yet final gets one fresh pair.
+#ifdef B2T_HOST_EMU
+extern "C" { int g_emu_rr_rebuilds = 0; }      // how often the CPU harness saw the pile rebuilt
+#endif
+__device__ __forceinline__ unsigned long long rr_pair(uint32_t dbits, uint32_t v) { return ((unsigned long long)dbits << 32) | v; }
+
 template <bool TEAM>
-__device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target, uint32_t* actA, uint32_t* actB,
-                             uint32_t* proc, uint32_t* farA, uint32_t* farB, uint32_t* touched, uint32_t* out,
-                             uint32_t out_cap, Shared& S, Local& Lc, Team& T) {
+__device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target, unsigned long long* midA,
+                             unsigned long long* midB, unsigned long long* proc, unsigned long long* farA,
+                             unsigned long long* farB, uint32_t* touched, uint32_t* out, uint32_t out_cap, Shared& S,
+                             Local& Lc, Team& T) {
   const int lane = threadIdx.x & 31;
   const uint32_t tid = t_tid<TEAM>(T), nth = t_threads<TEAM>(), tw = t_warp<TEAM>(T), ntw = t_warps<TEAM>();
   const uint32_t seg = L.segid;
+  // entries per list: twice the voxel count, so that a rebuilt pile (one pair per voxel at most) leaves room to go on
+  const uint32_t cap = B2T_RR_CAP_SHIFT ? max(64u, (2u * L.n_fg) >> B2T_RR_CAP_SHIFT) : 2u * L.n_fg;
   if (__ldcg(&A.pdrf[target]) == 0.0f) {
     if (tid == 0 && out_cap > 0) out[0] = target;
     team_sync<TEAM>();
@@ -296,22 +320,17 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
   const int64_t off = (int64_t)dx + (int64_t)dy * A.d.sx + (int64_t)dz * A.d.sxy;
   const uint32_t ltmask = (1u << lane) - 1u;
 
-  // Three-level pile.  `mid` is a bounded band of candidates (tentative distance <= thr_mid) that is
-  // rescanned every round to pull the next narrow batch (<= thr_near) into `proc`; everything farther
-  // waits in `far`, which is scanned only when `mid` drains.  Relaxation order never changes the result
-  // (the distances are a least fixed point); narrow batches keep the re-relaxation work near Dijkstra's.
-  uint32_t* mid = actA;
-  uint32_t* mid2 = actB;
-  uint32_t* far = farA;
-  uint32_t* far2 = farB;
+  unsigned long long* mid = midA;
+  unsigned long long* mid2 = midB;
+  unsigned long long* far = farA;
+  unsigned long long* far2 = farB;
   if (tid == 0) {
     A.dist[target] = 0.0f;
-    A.stamp[target] = 1;
-    mid[0] = target;
+    mid[0] = rr_pair(0u, target);
     touched[0] = target;
     S.n_touched = 1;
     S.best = ~0ull;
-    S.n_keep = 0; S.n_proc = 0; S.n_next = 0;
+    S.n_keep = 0; S.n_proc = 0; S.n_next = 0; S.r32[1] = 0;
   }
   team_sync<TEAM>();
   uint32_t n_mid = 1, n_far = 0;
@@ -329,7 +348,7 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
       if (n_far == 0) break;
       const uint32_t bound = (uint32_t)(S.best >> 32);
       uint32_t mn = 0xffffffffu;
-      for (uint32_t i = tid; i < n_far; i += nth) mn = min(mn, __float_as_uint(__ldcg(&A.dist[far[i]])));
+      for (uint32_t i = tid; i < n_far; i += nth) mn = min(mn, (uint32_t)(far[i] >> 32));
       mn = team_min_u32<TEAM>(mn, S, Lc, T);
       if (mn > bound) break;                                  // nothing left that could beat the rail we have
       thr_mid = __float_as_uint(__fadd_rn(__uint_as_float(mn), delta_mid));
@@ -337,13 +356,12 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
       for (uint32_t i0 = 0; i0 < n_far; i0 += nth) {
         const uint32_t i = i0 + tid;
         bool tomid = false, tokeep = false;
-        uint32_t u = 0;
+        unsigned long long e = 0;
         if (i < n_far) {
-          u = far[i];
-          const uint32_t du = __float_as_uint(__ldcg(&A.dist[u]));
+          e = far[i];
+          const uint32_t du = (uint32_t)(e >> 32);
           tomid = du <= thr_mid;
-          tokeep = !tomid && du <= bound;
-          if (!tomid && !tokeep) A.stamp[u] = 0;              // dropped: a later improvement must re-queue it
+          tokeep = !tomid && du <= bound;                     // beyond the bound: dropped for good
         }
         const uint32_t mp = __ballot_sync(0xffffffffu, tomid), mk = __ballot_sync(0xffffffffu, tokeep);
         uint32_t bp = 0, bk = 0;
@@ -353,13 +371,13 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
         }
         bp = __shfl_sync(0xffffffffu, bp, 0);
         bk = __shfl_sync(0xffffffffu, bk, 0);
-        if (tomid) mid[bp + __popc(mp & ltmask)] = u;
-        if (tokeep) far2[bk + __popc(mk & ltmask)] = u;
+        if (tomid) mid[bp + __popc(mp & ltmask)] = e;
+        if (tokeep) far2[bk + __popc(mk & ltmask)] = e;
       }
       team_sync<TEAM>();
       n_mid = S.n_keep;
       n_far = S.n_next;
-      { uint32_t* t = far; far = far2; far2 = t; }
+      { unsigned long long* t = far; far = far2; far2 = t; }
       if (n_mid < lo_mid) delta_mid = __fmul_rn(delta_mid, 2.0f);                  // aim at 256..1024 candidates per CTA
       else if (n_mid > hi_mid) delta_mid = __fmul_rn(delta_mid, 0.5f);
       team_sync<TEAM>();
@@ -369,15 +387,7 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
     }
     // ---- (a) smallest tentative distance in the mid band ----
     uint32_t mn = 0xffffffffu;
-    for (uint32_t i0 = tid; i0 < n_mid; i0 += 4 * nth) {
-      uint32_t id[4], dv[4];
-#pragma unroll
-      for (int q = 0; q < 4; q++) { const uint32_t i = i0 + q * nth; id[q] = (i < n_mid) ? mid[i] : 0xffffffffu; }
-#pragma unroll
-      for (int q = 0; q < 4; q++) dv[q] = (id[q] != 0xffffffffu) ? __float_as_uint(__ldcg(&A.dist[id[q]])) : 0xffffffffu;
-#pragma unroll
-      for (int q = 0; q < 4; q++) mn = min(mn, dv[q]);
-    }
+    for (uint32_t i = tid; i < n_mid; i += nth) mn = min(mn, (uint32_t)(mid[i] >> 32));
     mn = team_min_u32<TEAM>(mn, S, Lc, T);
     const uint32_t bound = (uint32_t)(S.best >> 32);
     uint32_t thr = __float_as_uint(__fadd_rn(__uint_as_float(mn), delta));
@@ -386,13 +396,12 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
     for (uint32_t i0 = 0; i0 < n_mid; i0 += nth) {
       const uint32_t i = i0 + tid;
       bool toproc = false, tokeep = false;
-      uint32_t u = 0;
+      unsigned long long e = 0;
       if (i < n_mid) {
-        u = mid[i];
-        const uint32_t du = __float_as_uint(__ldcg(&A.dist[u]));
+        e = mid[i];
+        const uint32_t du = (uint32_t)(e >> 32);
         toproc = du <= thr;
         tokeep = !toproc && du <= bound;
-        if (!toproc && !tokeep) A.stamp[u] = 0;
       }
       const uint32_t mp = __ballot_sync(0xffffffffu, toproc), mk = __ballot_sync(0xffffffffu, tokeep);
       uint32_t bp = 0, bk = 0;
@@ -402,27 +411,29 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
       }
       bp = __shfl_sync(0xffffffffu, bp, 0);
       bk = __shfl_sync(0xffffffffu, bk, 0);
-      if (toproc) proc[bp + __popc(mp & ltmask)] = u;
-      if (tokeep) mid2[bk + __popc(mk & ltmask)] = u;
+      if (toproc) proc[bp + __popc(mp & ltmask)] = e;
+      if (tokeep) mid2[bk + __popc(mk & ltmask)] = e;
     }
     team_sync<TEAM>();
     const uint32_t n_proc = S.n_proc;
     // ---- (c) expand the batch: lane per neighbour, TWO voxels per warp iteration so that their chains of
-    //          dependent global accesses (stamp/dist of u -> label/weight of v -> atomicMin -> stamp of v) overlap ----
+    //          dependent global accesses (dist of u -> label/weight of v -> atomicMin) overlap ----
     for (uint32_t it = tw; it < n_proc; it += 2 * ntw) {
-      uint32_t u[2], v[2], lv[2], nd[2], old[2];
+      uint32_t u[2], v[2], lv[2], nd[2], old[2], dq[2];
       float du[2], c[2];
       bool ok[2], relaxed[2], push_mid[2], push_far[2];
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         ok[e] = it + e * ntw < n_proc;
-        u[e] = ok[e] ? proc[it + e * ntw] : 0u;
-        if (ok[e] && lane == 0) atomicExch(&A.stamp[u[e]], 0u);   // from here on an improvement of u re-queues it
+        const unsigned long long pe = ok[e] ? proc[it + e * ntw] : 0ull;
+        u[e] = (uint32_t)pe;
+        dq[e] = (uint32_t)(pe >> 32);
       }
-      __syncwarp();
-      __threadfence_block();
 #pragma unroll
-      for (int e = 0; e < 2; e++) du[e] = ok[e] ? __ldcg(&A.dist[u[e]]) : 0.0f;
+      for (int e = 0; e < 2; e++) {
+        du[e] = ok[e] ? __ldcg(&A.dist[u[e]]) : 0.0f;
+        ok[e] = ok[e] && __float_as_uint(du[e]) == dq[e];        // a superseded pair: its voxel has (had) a closer one
+      }
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         int x, y, z;
@@ -460,12 +471,9 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
         }
         if (relaxed[e]) {
           relax++;
-          if (TEAM) __threadfence(); else __threadfence_block();
-          if (atomicExch(&A.stamp[v[e]], 1u) == 0u) { push_mid[e] = nd[e] <= thr_mid; push_far[e] = !push_mid[e]; }
+          push_mid[e] = nd[e] <= thr_mid;
+          push_far[e] = !push_mid[e];
         }
-      }
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
         const uint32_t mm = __ballot_sync(0xffffffffu, push_mid[e]), mf = __ballot_sync(0xffffffffu, push_far[e]);
         if (mm | mf) {
           uint32_t bm = 0, bf = 0;
@@ -475,24 +483,55 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
           }
           bm = __shfl_sync(0xffffffffu, bm, 0);
           bf = __shfl_sync(0xffffffffu, bf, 0);
-          if (push_mid[e]) mid2[bm + __popc(mm & ltmask)] = v[e];
-          if (push_far[e]) far[n_far + bf + __popc(mf & ltmask)] = v[e];
+          const uint32_t pm = bm + __popc(mm & ltmask), pf = n_far + bf + __popc(mf & ltmask);
+          if (push_mid[e]) { if (pm < cap) mid2[pm] = rr_pair(nd[e], v[e]); else S.r32[1] = 1u; }
+          if (push_far[e]) { if (pf < cap) far[pf] = rr_pair(nd[e], v[e]); else S.r32[1] = 1u; }
         }
       }
     }
     team_sync<TEAM>();
     n_mid = S.n_keep;
     n_far += S.n_next;
-    { uint32_t* t = mid; mid = mid2; mid2 = t; }
+    const bool overflow = S.r32[1] != 0u;
+    { unsigned long long* t = mid; mid = mid2; mid2 = t; }
     // batch-size feedback: keep roughly 2..8 voxels per warp in flight
     if (n_proc < lo_proc) delta = __fmul_rn(delta, 2.0f);
     else if (n_proc > hi_proc) delta = __fmul_rn(delta, 0.5f);
     rounds++;
     team_sync<TEAM>();
-    if (tid == 0) { S.n_keep = 0; S.n_proc = 0; S.n_next = 0; }
+    if (tid == 0) { S.n_keep = 0; S.n_proc = 0; S.n_next = 0; S.r32[1] = 0; }
     team_sync<TEAM>();
+    if (overflow) {
+      // a list filled up with superseded pairs (and lost some new ones): rebuild the pile from the voxels this search has
+      // touched -- one fresh pair for every voxel that is not final yet (everything below this round's smallest open
+      // distance `mn` is; expanding a final voxel again would change nothing anyway)
+#ifdef B2T_HOST_EMU
+      if (tid == 0) g_emu_rr_rebuilds++;
+#endif
+      const uint32_t nt = S.n_touched;
+      for (uint32_t i0 = 0; i0 < nt; i0 += nth) {
+        const uint32_t i = i0 + tid;
+        bool keep = false;
+        uint32_t v = 0, dv = 0;
+        if (i < nt) {
+          v = touched[i];
+          dv = __float_as_uint(__ldcg(&A.dist[v]));
+          keep = dv >= mn && dv <= (uint32_t)(S.best >> 32);
+        }
+        const uint32_t mk = __ballot_sync(0xffffffffu, keep);
+        uint32_t bk = 0;
+        if (lane == 0 && mk) bk = atomicAdd(&S.n_next, __popc(mk));
+        bk = __shfl_sync(0xffffffffu, bk, 0);
+        if (keep) far[bk + __popc(mk & ltmask)] = rr_pair(dv, v);
+      }
+      team_sync<TEAM>();
+      n_mid = 0;
+      n_far = S.n_next;
+      team_sync<TEAM>();
+      if (tid == 0) S.n_next = 0;
+      team_sync<TEAM>();
+    }
   }
-  // anything still queued keeps stamp = 1; it is in `touched`, which resets it below
 
   // (d) walk back: rail voxel, then parents by rule T3
   uint32_t len = 0;
@@ -551,13 +590,9 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
   }
   team_sync<TEAM>();
   len = S.r32[0];
-  // (e) reset the scratch fields of every voxel this search touched
+  // (e) reset the distance field on every voxel this search touched
   const uint32_t nt = S.n_touched;
-  for (uint32_t i = tid; i < nt; i += nth) {
-    const uint32_t v = touched[i];
-    A.dist[v] = __int_as_float(kInfBits);
-    A.stamp[v] = 0;
-  }
+  for (uint32_t i = tid; i < nt; i += nth) A.dist[touched[i]] = __int_as_float(kInfBits);
   relax = team_sum_u32<TEAM>(relax, S, Lc, T);
   if (tid == 0) { S.relax += relax; S.rounds += rounds; }
   team_sync<TEAM>();
@@ -1031,13 +1066,20 @@ template <bool TEAM>
 __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, const Params& prm, Shared& S, Local& Lc,
                             Team& T, uint32_t job) {
   const uint32_t tid = t_tid<TEAM>(T), nth = t_threads<TEAM>();
-  uint32_t* scr = P.scratch + 6ull * L.region_off;
+  // scratch of the label: kScratchPerVoxel u32 per voxel.  Four pair lists and the batch of railroad (2 n_fg entries of
+  // 2 words each), the touched list; the invalidation's four voxel lists alias the first pair list between searches.
+  uint32_t* scr = P.scratch + (unsigned long long)kScratchPerVoxel * L.region_off;
+  const unsigned long long n = L.n_fg;
+  unsigned long long* pl0 = reinterpret_cast<unsigned long long*>(scr);
+  unsigned long long* pl1 = reinterpret_cast<unsigned long long*>(scr + 4 * n);
+  unsigned long long* pl2 = reinterpret_cast<unsigned long long*>(scr + 8 * n);
+  unsigned long long* pl3 = reinterpret_cast<unsigned long long*>(scr + 12 * n);
+  unsigned long long* pl4 = reinterpret_cast<unsigned long long*>(scr + 16 * n);
+  uint32_t* touched = scr + 20 * n;
   uint32_t* r0 = scr;
-  uint32_t* r1 = scr + L.n_fg;
-  uint32_t* r2 = scr + 2ull * L.n_fg;
-  uint32_t* r3 = scr + 3ull * L.n_fg;
-  uint32_t* r4 = scr + 4ull * L.n_fg;
-  uint32_t* r5 = scr + 5ull * L.n_fg;
+  uint32_t* r1 = scr + n;
+  uint32_t* r2 = scr + 2 * n;
+  uint32_t* r3 = scr + 3 * n;
   uint32_t* out = P.paths + L.path_off;
   unsigned long long t_start = 0;
   if (tid == 0) {
@@ -1071,7 +1113,7 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
     if (used + 2 > L.path_cap) { status = B2T_ERR_CAPACITY; break; }
     uint32_t* pout = out + used;
     const uint32_t cap = L.path_cap - used - 1;
-    uint32_t len = prm.fix_branching ? railroad<TEAM>(A, L, target, r0, r1, r2, r4, r5, r3, pout, cap, S, Lc, T)
+    uint32_t len = prm.fix_branching ? railroad<TEAM>(A, L, target, pl0, pl1, pl4, pl2, pl3, touched, pout, cap, S, Lc, T)
                                      : path_from_parents<TEAM>(A, L, target, pout, cap, S, T);
     if (len > cap) { status = B2T_ERR_CAPACITY; break; }
     if (L.soma_mode) {
@@ -1170,7 +1212,7 @@ __global__ void __launch_bounds__(kThreads, B2T_TRACE_MINB) trace_kernel(Arena A
 // Replaces the body of kimimaro/trace.py:compute_paths (trace.py:196-267) and the native calls in
 // it: dijkstra3d.railroad, CachedTargetFinder.find_target, roll_invalidation_ball_inside_component.
 //   d_desc       n_desc records of 20 x u32/f32 (struct LabelDesc above, same field order)
-//   d_scratch    6 * sum(n_fg) u32;  d_paths: path pool;  d_targets: manual targets (linear indices)
+//   d_scratch    b2t_trace_scratch_words(sum(n_fg)) u32;  d_paths: path pool;  d_targets: manual targets (linear indices)
 //   d_out_len / d_out_npaths / d_out_status: n_desc each; d_out_stats: 4 * n_desc; d_work_counter: 1 u32 (zeroed here)
 // =================================================================================================
 // Words (u32) of the strict mode's static heap regions for a batch: b2t_trace_batch wants at least this many in d_heap
@@ -1178,6 +1220,10 @@ __global__ void __launch_bounds__(kThreads, B2T_TRACE_MINB) trace_kernel(Arena A
 B2T_EXPORT uint64_t b2t_trace_heap_words(uint64_t sum_n_fg, uint64_t n_desc) {
   return 2ull + 3ull * ((uint64_t)kHeapPerVoxel * sum_n_fg + (uint64_t)kHeapSlack * n_desc);
 }
+
+// u32 words of d_scratch for a batch whose labels have sum_n_fg voxels together (region_off of a label = the prefix sum
+// of n_fg before it; a label's lists start at an even word, so pairs are 8-byte aligned)
+B2T_EXPORT uint64_t b2t_trace_scratch_words(uint64_t sum_n_fg) { return (uint64_t)kScratchPerVoxel * sum_n_fg + 16; }
 
 // bytes of one team slot (d_team of b2t_trace_batch holds n_team of them)
 B2T_EXPORT uint64_t b2t_trace_team_bytes(void) { return sizeof(Shared); }

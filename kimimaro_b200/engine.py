@@ -9,7 +9,7 @@ Data layout in HBM (per voxel of the [sx,sy,sz] Fortran-ordered volume, V voxels
   dbf     4 B  distance-to-boundary (K1)           dist    4 B  DAF, then railroad scratch (+inf at rest)
   pdrf    4 B  penalised distance field            claim   8 B  ~0 = valid; 0 = invalidated; else pending (dist,seed)
   stamp   4 B  frontier de-duplication flags
-plus per foreground voxel: keys 8 B (DAF-bucketed target list), 16 B of queue scratch, path pool.
+plus per foreground voxel: keys 8 B (DAF-bucketed target list), 88 B of queue scratch, path pool.
 """
 import ctypes
 import os
@@ -39,6 +39,7 @@ _lib.declare("b2t_trace_batch", [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i6
                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_vp, c_u64, c_u64, c_int, c_vp, c_vp])
 _lib.declare("b2t_trace_heap_words", [c_u64, c_u64], c_u64)
 _lib.declare("b2t_trace_team_bytes", [], c_u64)
+_lib.declare("b2t_trace_scratch_words", [c_u64], c_u64)
 _lib.declare("b2t_ccl26_roots", [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp])
 _lib.declare("b2t_ccl_relabel", [c_vp, c_vp, c_u64, c_vp])
 _lib.declare("b2t_invalidate_ball", [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_u32, c_f32, c_f32,
@@ -437,14 +438,15 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   desc["bucket_row"] = desc["segid"]
   region = int(nfg.sum())
   path_off = int(caps.sum())
-  if path_off >= 2 ** 32 or 6 * region >= 2 ** 34:
+  if path_off >= 2 ** 32 or region >= 2 ** 32:
     raise B2TError(f"arena too large for 32-bit pool offsets: path pool {path_off} slots, {region} foreground voxels")
-  scratch = torch.empty(6 * max(region, 1), dtype=torch.int32, device=dev)
+  SCR = 22                                                    # u32 of scratch per voxel (b2t_trace_scratch_words)
+  scratch = torch.empty(int(L.b2t_trace_scratch_words(c_u64(max(region, 1)))), dtype=torch.int32, device=dev)
   # soma labels: the one-off ball around the root (trace.py:160-168) is far too large for one CTA
   for slot in np.flatnonzero(desc["soma_mode"]).tolist():
     if desc[slot]["soma_mode"]:
       n = int(desc[slot]["n_fg"])
-      base = 6 * int(desc[slot]["region_off"])
+      base = SCR * int(desc[slot]["region_off"])
       seeds = _dev(np.array([desc[slot]["root"]], dtype=np.uint32).view(np.int32))
       check(L.b2t_invalidate_ball(_p(d_cc), _p(d_dbf), _p(claim), c_i64(sx), c_i64(sy), c_i64(sz),
                                   c_f32(anisotropy[0]), c_f32(anisotropy[1]), c_f32(anisotropy[2]), _p(seeds), c_u32(1),
@@ -462,7 +464,6 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   out_status = torch.zeros(n_jobs, dtype=torch.int32, device=dev)
   out_stats = torch.zeros(4 * n_jobs, dtype=torch.int32, device=dev)
   counter = torch.zeros(1, dtype=torch.int32, device=dev)
-  ws.stamp.zero_()
   launch = dict(d_cc=d_cc, d_dbf=d_dbf, pdrf=pdrf, ws=ws, claim=claim, shape=shape, anisotropy=anisotropy, params=params,
                 fix_branching=fix_branching, keys=keys, hist=hist, cursor=cursor, scratch=scratch, d_targets=d_targets,
                 nfg_sorted=nfg)

@@ -91,6 +91,24 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   return m;
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+// all 32 lanes take part (full mask): the lanes holding the same value
+static inline unsigned __match_any_sync(unsigned, unsigned value) {
+  simt::Warp& w = simt::g_block.warps[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  w.v[lane] = value;
+  simt::barrier_wait(w.bar);
+  unsigned m = 0;
+  for (int l = 0; l < 32; l++) m |= (unsigned)(w.v[l] == (unsigned long long)value) << l;
+  simt::barrier_wait(w.bar);
+  return m;
+}
+// redux.sync over the lanes of `mask`.  On the GPU only those lanes execute it; here they are the lanes of one
+// __match_any_sync group calling from inside a branch, so the exchange uses a barrier sized to the group: every member
+// publishes, the members meet, every member folds the group's values.
+namespace simt { unsigned reduce_group(unsigned mask, unsigned v, int op); }
+static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) { return simt::reduce_group(mask, v, 0); }
+static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) { return simt::reduce_group(mask, v, 1); }
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { return simt::reduce_group(mask, v, 2); }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int src) { return simt::exchange(v, [src](int) { return src; }); }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lm) { return simt::exchange(v, [lm](int l) { return l ^ lm; }); }
 template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d) {

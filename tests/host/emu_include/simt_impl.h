@@ -91,6 +91,23 @@ void barrier_wait(Barrier& b) {
   b.tail = me;
   park();
 }
+// Group reduction for lanes inside a divergent branch.  Fibers run one at a time and only switch at barriers, so a group
+// can meet through a per-warp table keyed by its member mask: every member adds itself to its group's entry and parks
+// until the last one has arrived.
+struct GroupSlot { unsigned mask = 0, arrived = 0, phase = 0; unsigned vals[32]; Barrier bar; };
+static GroupSlot g_groups[kMaxThreads / 32][32];
+unsigned reduce_group(unsigned mask, unsigned v, int op) {
+  const int lane = threadIdx.x & 31;
+  GroupSlot& s = g_groups[threadIdx.x >> 5][__builtin_ctz(mask)];     // the group's lowest lane names its slot
+  if (s.bar.expected != __builtin_popcount(mask)) { s.bar = Barrier(); s.bar.expected = __builtin_popcount(mask); }
+  s.vals[lane] = v;
+  barrier_wait(s.bar);
+  unsigned r = op == 0 ? 0u : (op == 1 ? 0xffffffffu : 0u);
+  for (int l = 0; l < 32; l++)
+    if (mask >> l & 1u) r = op == 0 ? r + s.vals[l] : (op == 1 ? (s.vals[l] < r ? s.vals[l] : r) : (s.vals[l] > r ? s.vals[l] : r));
+  barrier_wait(s.bar);
+  return r;
+}
 static void fiber_entry() {
   Fiber* me = g_cur;
   threadIdx = uint3{me->tid, 0, 0};

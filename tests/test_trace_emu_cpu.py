@@ -37,6 +37,19 @@ def emu():
 ROUNDS, WINDOW, STRICT = 0, 1, 2
 
 
+@pytest.fixture(scope="module")
+def emu_tight():
+  """The same harness with railroad's pair lists shrunk 32-fold (B2T_RR_CAP_SHIFT): lists overflow and the pile is rebuilt
+  from the touched voxels again and again."""
+  out = OUT.replace("trace_emu.so", "trace_emu_tight.so")
+  if (not os.path.exists(out)) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in DEPS):
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-attributes",
+                           "-DB2T_RR_CAP_SHIFT=5", "-I" + os.path.join(HERE, "host", "emu_include"), SRC, "-o", out])
+  lib = ctypes.CDLL(out)
+  lib.emu_invalidate.restype = ctypes.c_long
+  return lib
+
+
 def _engine(lib, vol, dbf, path, scale, const, an, window, mode=None, spill_words=0, team=0):
   sx, sy, sz = vol.shape
   cc = np.ascontiguousarray(vol.reshape(-1, order="F").astype(np.uint32))
@@ -172,7 +185,7 @@ def _emulated_paths(lib, cc, n_cc, all_dbf, an, params, window, fix_borders_targ
   dist = np.full(V, np.inf, np.float32)
   claim = np.full(V, 0xFFFFFFFFFFFFFFFF, np.uint64)
   stamp = np.zeros(V, np.uint32)
-  scratch = np.zeros(6 * region + 8, np.uint32)
+  scratch = np.zeros(22 * region + 16, np.uint32)
   paths = np.zeros(path_off + 8, np.uint32)
   n = len(desc)
   out_len, out_np, out_status = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.int32)
@@ -236,3 +249,33 @@ def test_engine_path_loop_equals_oracle(emu, window, n_team):
         assert np.array_equal(a, b), (seed, l)
       n_paths += len(ref)
   assert n_paths >= 10
+
+
+def test_railroad_pile_rebuild_after_overflow(emu_tight):
+  """railroad keeps superseded pairs in its lists (lazy deletion); when a list fills up the pile is rebuilt from the touched
+  voxels.  With the lists shrunk 32-fold that happens many times per search, and the paths still have to be the oracle's."""
+  from oracle import teasar
+  from tests.synth import synthetic_tubes
+  params = dict(teasar.DEFAULT_TEASAR_PARAMS)
+  params.update(scale=1.5, const=30)
+  an = (16.0, 16.0, 40.0)
+  lab = synthetic_tubes((64, 56, 40), 4, seed=8)
+  cc, n_cc = oracle.connected_components(lab)
+  keep = [l for l in range(1, n_cc + 1) if (cc == l).sum() > 1500]
+  cc = np.asfortranarray(np.where(np.isin(cc, keep), cc, 0))
+  cc, n_cc = oracle.connected_components(cc)
+  assert n_cc >= 1
+  all_dbf = oracle.edt(cc, an, False)
+  before = ctypes.c_int.in_dll(emu_tight, "g_emu_rr_rebuilds").value
+  got = _emulated_paths(emu_tight, cc, n_cc, all_dbf, an, params, 1.0)
+  assert ctypes.c_int.in_dll(emu_tight, "g_emu_rr_rebuilds").value > before, "the case must overflow to test anything"
+  sx, sy, sz = cc.shape
+  for l in range(1, n_cc + 1):
+    labels = np.asfortranarray(cc == l)
+    DBF = np.where(labels, all_dbf, 0).astype(np.float32, order="F")
+    _, ref = teasar.trace(labels, DBF, anisotropy=an, invalidation_mode="window:1", return_paths=True, **params)
+    ref = [(np.asarray(q, np.int64)[:, 0] + sx * (np.asarray(q, np.int64)[:, 1] + sy * np.asarray(q, np.int64)[:, 2]))
+           for q in ref if len(q) > 0]
+    assert len(got[l]) == len(ref)
+    for a, b in zip(got[l], ref):
+      assert np.array_equal(a, b), l
