@@ -201,6 +201,17 @@ int b2t_invalidate_ball(const uint32_t* d_cc, const float* d_dbf, uint64_t* d_cl
                         float scale, float konst, uint32_t* d_fv, uint32_t* d_fs, uint64_t cap,
                         uint32_t* d_ctrl, void* stream);
 
+/* N2  fix_borders, the per-component reductions of one face -------------------------------------------------------
+ * replaces  skeletontricks.find_border_targets (DT maximum per face component, the voxels that attain it, first raster
+ *           position; pyx:591-648), compute_centroids (coordinate sums and counts; pyx:528-588) and get_mapping (the
+ *           volume label under a face component; pyx:490-525) as called from kimimaro/intake.py:544-585.
+ * d_cc_plane / d_dt / d_plane: [p0*p1] face components (b2t_ccl26_roots with sz = 1), their 2-D EDT, the volume's cc labels
+ * on the face.  d_tab: 6*(P+1) u32 scratch; d_cand: 2*P u32 (position, component) pairs; d_rec: 7*P u32 records
+ * (component, max DT bits, first position, count, sum x, sum y, volume label); d_count: candidates, records.  The tie-break
+ * among a component's candidates stays on the host (float32 / float64 expression order of pyx:650-760). */
+int b2t_face_stats(const uint32_t* d_cc_plane, const float* d_dt, const uint32_t* d_plane, int64_t p0, int64_t p1,
+                   uint32_t* d_tab, uint32_t* d_cand, uint32_t* d_rec, uint32_t* d_count, void* stream);
+
 /* N2 helper: strictly sequential float32 sums per segment (label centroids of a face in the reference's
  * accumulation order, ext/skeletontricks/skeletontricks.pyx:528-588 compute_centroids). */
 int b2t_segment_seqsum(const float* d_xs, const float* d_ys, const int64_t* d_off, uint32_t n_seg,

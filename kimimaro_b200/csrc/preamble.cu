@@ -286,6 +286,84 @@ B2T_EXPORT int b2t_segment_seqsum(const float* d_xs, const float* d_ys, const in
   return B2T_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fix_borders, per face (kimimaro/intake.py:544-585): the per-component reductions of find_border_targets
+// (pyx:591-648: DT maximum, every voxel that attains it, first raster position), compute_centroids (pyx:528-588:
+// coordinate sums, voxel count) and get_mapping (pyx:490-525: the volume label under a face component) in three small
+// launches, compacted on the device so that the host reads a few thousand numbers per face in one go.
+//   d_tab    6 * (P + 1) u32 scratch: max DT bits | first position | count | sum x | sum y | volume label
+//   d_cand   2 * P u32: (position, face component) of every voxel that attains its component's DT maximum, any order
+//   d_rec    7 * P u32: per face component present: id, max DT bits, first position, count, sum x, sum y, volume label
+//   d_count  2 u32: number of candidates, number of records (zeroed here)
+// Coordinate sums are integers: as float32 they equal the reference's sequential float32 sums whenever they stay below
+// 2^24 (every partial sum is then exact); the host redoes the rare larger component in the reference's order.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void face_reduce_kernel(const uint32_t* __restrict__ ccp, const float* __restrict__ dt,
+                                   const uint32_t* __restrict__ plane, uint32_t p0, uint32_t P, uint32_t* __restrict__ tab) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const uint32_t l = ccp[i];
+  if (l == 0 || l > P) return;
+  const size_t T = (size_t)P + 1;
+  const float d = dt[i];
+  if (d != 0.0f) {
+    atomicMax(&tab[l], __float_as_uint(d));
+    atomicMin(&tab[T + l], i);
+  }
+  atomicAdd(&tab[2 * T + l], 1u);
+  atomicAdd(&tab[3 * T + l], i % p0);
+  atomicAdd(&tab[4 * T + l], i / p0);
+  tab[5 * T + l] = plane[i];          // every voxel of a face component lies in the same volume component
+}
+
+__global__ void face_candidates_kernel(const uint32_t* __restrict__ ccp, const float* __restrict__ dt, uint32_t P,
+                                       const uint32_t* __restrict__ tab, uint32_t* __restrict__ cand,
+                                       uint32_t* __restrict__ count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const uint32_t l = ccp[i];
+  if (l == 0 || l > P) return;
+  const float d = dt[i];
+  if (d != 0.0f && __float_as_uint(d) == tab[l]) {
+    const uint32_t k = atomicAdd(&count[0], 1u);
+    cand[2 * (size_t)k] = i;
+    cand[2 * (size_t)k + 1] = l;
+  }
+}
+
+__global__ void face_records_kernel(uint32_t P, const uint32_t* __restrict__ tab, uint32_t* __restrict__ rec,
+                                    uint32_t* __restrict__ count) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (l > P) return;
+  const size_t T = (size_t)P + 1;
+  if (tab[2 * T + l] == 0 || tab[l] == 0) return;     // absent, or no voxel with a non-zero DT
+  const uint32_t k = atomicAdd(&count[1], 1u);
+  uint32_t* r = rec + 7 * (size_t)k;
+  r[0] = l; r[1] = tab[l]; r[2] = tab[T + l]; r[3] = tab[2 * T + l]; r[4] = tab[3 * T + l]; r[5] = tab[4 * T + l];
+  r[6] = tab[5 * T + l];
+}
+}  // namespace
+
+B2T_EXPORT int b2t_face_stats(const uint32_t* d_cc_plane, const float* d_dt, const uint32_t* d_plane, int64_t p0, int64_t p1,
+                              uint32_t* d_tab, uint32_t* d_cand, uint32_t* d_rec, uint32_t* d_count, void* stream) {
+  B2T_REQUIRE(p0 > 0 && p1 > 0 && (double)p0 * (double)p1 < 2147483647.0, "b2t_face_stats: bad plane shape");
+  B2T_REQUIRE(d_cc_plane && d_dt && d_plane && d_tab && d_cand && d_rec && d_count, "b2t_face_stats: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint32_t P = (uint32_t)(p0 * p1);
+  const size_t T = (size_t)P + 1;
+  B2T_CUDA_TRY(cudaMemsetAsync(d_tab, 0, 6 * T * sizeof(uint32_t), st));
+  B2T_CUDA_TRY(cudaMemsetAsync(d_tab + T, 0xff, T * sizeof(uint32_t), st));     // first position: minimum
+  B2T_CUDA_TRY(cudaMemsetAsync(d_count, 0, 2 * sizeof(uint32_t), st));
+  const unsigned blocks = (P + 255) / 256;
+  B2T_LAUNCH(face_reduce_kernel, blocks, 256, st)(d_cc_plane, d_dt, d_plane, (uint32_t)p0, P, d_tab);
+  B2T_LAUNCH(face_candidates_kernel, blocks, 256, st)(d_cc_plane, d_dt, P, d_tab, d_cand, d_count);
+  B2T_LAUNCH(face_records_kernel, blocks, 256, st)(P, d_tab, d_rec, d_count);
+  B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(3);
+  return B2T_OK;
+}
+
 // Compact n_seg path segments (pool[src_off[j] .. +len[j])) to dst[dst_off[j] ..) and fetch DBF at each vertex.
 B2T_EXPORT int b2t_gather_paths(const uint32_t* d_pool, const uint32_t* d_src_off, const uint32_t* d_len,
                                 const uint64_t* d_dst_off, uint32_t n_seg, const float* d_dbf, uint32_t* d_dst_vox,

@@ -44,6 +44,7 @@ _lib.declare("b2t_ccl26_roots", [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c
 _lib.declare("b2t_ccl_relabel", [c_vp, c_vp, c_u64, c_vp])
 _lib.declare("b2t_invalidate_ball", [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_u32, c_f32, c_f32,
                                      c_vp, c_vp, c_u64, c_vp, c_vp])
+_lib.declare("b2t_face_stats", [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp])
 _lib.declare("b2t_segment_seqsum", [c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp])
 _lib.declare("b2t_set_launch_limits", [c_int, c_int])
 _lib.declare("b2t_gather_paths", [c_vp, c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp])
@@ -207,60 +208,62 @@ def compute_border_targets(d_cc, shape, anisotropy):
     (cc3[:, :, 0], (sy, sz), (1, 2), lambda y, z: (0, y, z)),
     (cc3[:, :, sx - 1], (sy, sz), (1, 2), lambda y, z: (sx - 1, y, z)),
   )
-  # Per face, on the device: 2-D connected components, 2-D EDT (both through the C ABI), then the
-  # per-label reductions of find_border_targets / compute_centroids / get_mapping as torch plumbing
-  # (scatter-reduce, sort, searchsorted) plus b2t_segment_seqsum for the reference's sequential float32
-  # centroid sums.  Only the candidates that tie for a label's DT maximum (a few thousand numbers per face)
-  # go to the host, where the reference's tie-break order is applied (border.targets_from_candidates).
+  # Per face, on the device and without a host round trip: 2-D connected components, 2-D EDT, then b2t_face_stats (the
+  # per-component reductions of find_border_targets / compute_centroids / get_mapping, compacted).  The six faces are
+  # queued back to back; the host then reads the two counters of every face at once and the few thousand candidate /
+  # record words they announce, and applies the reference's tie-break order (border.targets_from_candidates).
   L = lib()
-  staged = []
-  for face, pshape, dims, rotatefn in faces:
+  dev = d_cc.device
+  pmax = max(sx * sy, sx * sz, sy * sz)
+  tab = torch.empty(6 * (pmax + 1), dtype=torch.int32, device=dev)
+  cand = torch.empty((6, 2 * pmax), dtype=torch.int32, device=dev)
+  rec = torch.empty((6, 7 * pmax), dtype=torch.int32, device=dev)
+  counts = torch.zeros((6, 2), dtype=torch.int32, device=dev)
+  planes = []
+  for f, (face, pshape, dims, rotatefn) in enumerate(faces):
     wx, wy = float(anisotropy[dims[0]]), float(anisotropy[dims[1]])
     p0, p1 = int(pshape[0]), int(pshape[1])
-    P = p0 * p1
-    dev = face.device
     plane = face.contiguous().view(-1)                     # flat Fortran order of the 2-D plane: x + p0*y
     cc_plane = _ccl_nosync(plane, (p0, p1, 1))             # 8-connected in 2-D (intake.py:564)
     dt = edt(cc_plane, pshape, anisotropy=(wx, wy), black_border=True)       # intake.py:565
-    cc64 = cc_plane.to(torch.int64)
-    idx_sel = torch.nonzero((cc64 != 0) & (dt != 0)).view(-1)
-    if idx_sel.numel() == 0:
-      continue
-    lab_sel = cc64[idx_sel]
-    dt_sel = dt[idx_sel]
-    mx = torch.zeros(P + 1, dtype=torch.float32, device=dev).scatter_reduce_(0, lab_sel, dt_sel, "amax")
-    is_max = dt_sel == mx[lab_sel]
-    cand_idx, cand_lab = idx_sel[is_max], lab_sel[is_max]
-    present = torch.unique(cand_lab)
-    first_pos = torch.full((P + 1,), P, dtype=torch.int64, device=dev).scatter_reduce_(0, lab_sel, idx_sel, "amin")
-    vol_of = torch.zeros(P + 1, dtype=torch.int32, device=dev)
-    vol_of[cc64] = plane                                   # get_mapping: every voxel of a component agrees
-    # centroid sums in the reference's scan order (x outer, y inner), strictly sequential in float32
-    cc_c = cc_plane.view(p1, p0).t().contiguous().view(-1)                   # index = x*p1 + y
-    vals, order = torch.sort(cc_c, stable=True)
-    xs = (order // p1).to(torch.float32)
-    ys = (order % p1).to(torch.float32)
-    seg_lo = torch.searchsorted(vals, present.to(vals.dtype))
-    seg_hi = torch.searchsorted(vals, present.to(vals.dtype), right=True)
-    n_seg = int(present.numel())
-    # segments are not adjacent (labels absent from `present` sit in between): gather them into one run
-    lens = seg_hi - seg_lo
-    off = torch.zeros(n_seg + 1, dtype=torch.int64, device=dev)
-    off[1:] = torch.cumsum(lens, 0)
-    pos = torch.repeat_interleave(seg_lo - off[:-1], lens) + torch.arange(int(off[-1].item()), device=dev)
-    gx, gy = xs[pos].contiguous(), ys[pos].contiguous()
-    sumx = torch.empty(n_seg, dtype=torch.float32, device=dev)
-    sumy = torch.empty(n_seg, dtype=torch.float32, device=dev)
-    check(L.b2t_segment_seqsum(_p(gx), _p(gy), _p(off), c_u32(n_seg), _p(sumx), _p(sumy), stream_ptr()),
-          "b2t_segment_seqsum")
-    staged.append((cand_idx.cpu().numpy(), cand_lab.cpu().numpy(), present.cpu().numpy(),
-                   first_pos[present].cpu().numpy(), sumx.cpu().numpy(), sumy.cpu().numpy(), lens.cpu().numpy(),
-                   vol_of[present].cpu().numpy(), p0, p1, wx, wy, rotatefn))
+    check(L.b2t_face_stats(_p(cc_plane), _p(dt), _p(plane), c_i64(p0), c_i64(p1), _p(tab), _p(cand[f]), _p(rec[f]),
+                           _p(counts[f]), stream_ptr()), "b2t_face_stats")
+    planes.append((cc_plane, p0, p1, wx, wy, rotatefn))
+  h_counts = counts.cpu().numpy()                          # the one synchronising read
+  parts = []
+  for f in range(6):
+    parts.append(cand[f, :2 * int(h_counts[f, 0])])
+    parts.append(rec[f, :7 * int(h_counts[f, 1])])
+  h_all = torch.cat(parts).cpu().numpy().view(np.uint32)
   target_list = defaultdict(set)
-  for (cand_idx, cand_lab, present, first_pos, sumx, sumy, cnt, vol_of, p0, p1, wx, wy, rotatefn) in staged:
-    plane_targets = border.targets_from_candidates(cand_idx, cand_lab, present, first_pos, sumx, sumy, cnt,
+  o = 0
+  for f, (cc_plane, p0, p1, wx, wy, rotatefn) in enumerate(planes):
+    nc, nr = int(h_counts[f, 0]), int(h_counts[f, 1])
+    c = h_all[o:o + 2 * nc].reshape(-1, 2).astype(np.int64)
+    o += 2 * nc
+    r = h_all[o:o + 7 * nr].reshape(-1, 7).astype(np.int64)
+    o += 7 * nr
+    if nr == 0:
+      continue
+    order = np.lexsort((c[:, 0], c[:, 1]))                 # by component, raster order inside (find_border_targets' scan)
+    cand_idx, cand_lab = c[order, 0], c[order, 1]
+    labels, first_pos, cnt, vol_of = r[:, 0], r[:, 2], r[:, 3], r[:, 6]
+    sumx, sumy = r[:, 4].astype(np.float32), r[:, 5].astype(np.float32)
+    # integer sums equal the reference's sequential float32 sums while every partial sum is exact in float32; a larger
+    # component whose maximum is tied (only those use the centroid) is summed again in the reference's order
+    big = cnt * max(p0 - 1, p1 - 1, 1) >= (1 << 24)
+    if big.any():
+      tied = set(np.unique(cand_lab[np.flatnonzero(np.diff(cand_lab) == 0)]).tolist())
+      redo = [k for k in np.flatnonzero(big).tolist() if int(labels[k]) in tied]
+      if redo:
+        h_plane = cc_plane.cpu().numpy().view(np.uint32).reshape(p1, p0).T      # [x, y]
+        for k in redo:
+          xs, ys = np.nonzero(h_plane == labels[k])        # C order of [x, y]: x outer, y inner (pyx:551-560)
+          sumx[k] = np.add.accumulate(xs.astype(np.float32), dtype=np.float32)[-1]
+          sumy[k] = np.add.accumulate(ys.astype(np.float32), dtype=np.float32)[-1]
+    plane_targets = border.targets_from_candidates(cand_idx, cand_lab, labels, first_pos, sumx, sumy, cnt,
                                                    p0, p1, wx, wy)
-    vol = {int(l): int(v) for l, v in zip(present.tolist(), vol_of.tolist())}
+    vol = {int(l): int(v) for l, v in zip(labels.tolist(), vol_of.tolist())}
     for label, pt in plane_targets.items():
       target_list[vol[label]].add(rotatefn(int(pt[0]), int(pt[1])))
   out = {}
