@@ -201,6 +201,13 @@ int b2t_invalidate_ball(const uint32_t* d_cc, const float* d_dbf, uint64_t* d_cl
                         float scale, float konst, uint32_t* d_fv, uint32_t* d_fs, uint64_t cap,
                         uint32_t* d_ctrl, void* stream);
 
+/* the same for ONE seed (what the soma call is), as a connected-components problem instead of a frontier sweep: the
+ * claimed set is the component of {label voxels closer to the seed than its radius} that holds the seed.
+ * d_mark [V] u8, d_parent [V] u32, d_is_root [V] u8: scratch; count left in d_ctrl[6] (d_ctrl >= 8 u32). */
+int b2t_invalidate_ball_single(const uint32_t* d_cc, const float* d_dbf, uint64_t* d_claim, int64_t sx, int64_t sy,
+                               int64_t sz, float wx, float wy, float wz, uint32_t h_seed, float scale, float konst,
+                               uint8_t* d_mark, uint32_t* d_parent, uint8_t* d_is_root, uint32_t* d_ctrl, void* stream);
+
 /* N2  fix_borders, the per-component reductions of one face -------------------------------------------------------
  * replaces  skeletontricks.find_border_targets (DT maximum per face component, the voxels that attain it, first raster
  *           position; pyx:591-648), compute_centroids (coordinate sums and counts; pyx:528-588) and get_mapping (the

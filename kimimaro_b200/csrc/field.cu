@@ -904,6 +904,71 @@ __global__ void __launch_bounds__(1024, 2) ball_flood_kernel(BallParams p) {
 
 }  // namespace
 
+// The same call with ONE seed (the soma's one-off ball, trace.py:160-168) without a frontier: with a single seed the
+// claimed set does not depend on any order -- it is the 26-connected component, inside {voxels of the label closer to the
+// seed than its radius}, that holds the seed -- so it is computed as a connected-components problem: mark the set,
+// union-find over it (b2t_ccl26_roots, lock-free, no rounds), claim the seed's component.  The frontier version needs
+// one grid barrier per hop of the ball's radius (11 ms for a 19 M voxel soma); this one is three streaming passes.
+//   d_mark: [V] u8 scratch; d_parent: [V] u32 scratch; d_is_root: [V] u8 scratch; the count is left in d_ctrl[6]
+namespace {
+__global__ void ball_mark_kernel(BallParams p, uint32_t seed, uint8_t* __restrict__ mark, uint64_t V) {
+  const uint32_t seg = __ldg(&p.cc[seed]);
+  const float r = __fadd_rn(__fmul_rn(p.scale, __ldg(&p.dbf[seed])), p.konst);
+  int ox, oy, oz;
+  unravel(seed, p.d, ox, oy, oz);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint8_t m = 0;
+    if (__ldg(&p.cc[i]) == seg && p.claim[i] == ~0ull) {
+      int x, y, z;
+      unravel((uint32_t)i, p.d, x, y, z);
+      const float a = __fmul_rn(p.wx, (float)(x - ox)), b = __fmul_rn(p.wy, (float)(y - oy)), c = __fmul_rn(p.wz, (float)(z - oz));
+      const float dd = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));
+      m = (dd < r || i == seed) ? 1 : 0;            // the seed itself is claimed whatever its radius (hpp:297-303)
+    }
+    mark[i] = m;
+  }
+}
+
+__global__ void ball_claim_kernel(unsigned long long* __restrict__ claim, const uint32_t* __restrict__ parent, uint32_t seed,
+                                  uint64_t V, uint32_t* __restrict__ count) {
+  const uint32_t want = parent[seed];
+  uint32_t n = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (parent[i] == want && want != 0xffffffffu) { claim[i] = 0ull; n++; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, n);
+}
+}  // namespace
+
+B2T_EXPORT int b2t_invalidate_ball_single(const uint32_t* d_cc, const float* d_dbf, uint64_t* d_claim, int64_t sx, int64_t sy,
+                                          int64_t sz, float wx, float wy, float wz, uint32_t h_seed, float scale,
+                                          float konst, uint8_t* d_mark, uint32_t* d_parent, uint8_t* d_is_root,
+                                          uint32_t* d_ctrl, void* stream) {
+  if (int rc = check_dims(sx, sy, sz)) return rc;
+  B2T_REQUIRE(d_cc && d_dbf && d_claim && d_mark && d_parent && d_is_root && d_ctrl, "b2t_invalidate_ball_single: null pointer");
+  const uint64_t V = (uint64_t)sx * sy * sz;
+  B2T_REQUIRE(h_seed < V, "b2t_invalidate_ball_single: seed outside the volume");
+  cudaStream_t st = (cudaStream_t)stream;
+  B2T_CUDA_TRY(cudaMemsetAsync(d_ctrl, 0, 8 * sizeof(uint32_t), st));
+  BallParams p;
+  p.cc = d_cc; p.dbf = d_dbf; p.claim = reinterpret_cast<unsigned long long*>(d_claim); p.seeds = nullptr;
+  p.n_seeds = 1; p.fv = nullptr; p.fs = nullptr; p.ctrl = d_ctrl; p.cap = 0;
+  p.d = Dims{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
+  p.wx = wx; p.wy = wy; p.wz = wz; p.scale = scale; p.konst = konst;
+  const uint64_t want = (V + 255) / 256;
+  const unsigned blocks = (unsigned)(want < 148ull * 16 ? want : 148ull * 16);
+  B2T_LAUNCH(ball_mark_kernel, blocks, 256, st)(p, h_seed, d_mark, V);
+  B2T_CUDA_TRY(cudaGetLastError());
+  if (int rc = b2t_ccl26_roots(d_mark, 1, sx, sy, sz, d_parent, d_is_root, stream)) return rc;
+  B2T_LAUNCH_SYNC(ball_claim_kernel, blocks, 256, st)(reinterpret_cast<unsigned long long*>(d_claim), d_parent, h_seed, V,
+                                                      d_ctrl + 6);
+  B2T_CUDA_TRY(cudaGetLastError());
+  b2t_count_launches(2);
+  return B2T_OK;
+}
+
 B2T_EXPORT int b2t_invalidate_ball(const uint32_t* d_cc, const float* d_dbf, uint64_t* d_claim, int64_t sx, int64_t sy,
                                    int64_t sz, float wx, float wy, float wz, const uint32_t* d_seeds, uint32_t n_seeds,
                                    float scale, float konst, uint32_t* d_fv, uint32_t* d_fs, uint64_t cap,

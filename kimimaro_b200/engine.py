@@ -45,6 +45,8 @@ _lib.declare("b2t_ccl_relabel", [c_vp, c_vp, c_u64, c_vp])
 _lib.declare("b2t_invalidate_ball", [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_vp, c_u32, c_f32, c_f32,
                                      c_vp, c_vp, c_u64, c_vp, c_vp])
 _lib.declare("b2t_face_stats", [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp])
+_lib.declare("b2t_invalidate_ball_single", [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_u32, c_f32, c_f32,
+                                            c_vp, c_vp, c_vp, c_vp, c_vp])
 _lib.declare("b2t_segment_seqsum", [c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp])
 _lib.declare("b2t_set_launch_limits", [c_int, c_int])
 _lib.declare("b2t_gather_paths", [c_vp, c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp])
@@ -450,12 +452,23 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
     if desc[slot]["soma_mode"]:
       n = int(desc[slot]["n_fg"])
       base = SCR * int(desc[slot]["region_off"])
-      seeds = _dev(np.array([desc[slot]["root"]], dtype=np.uint32).view(np.int32))
-      check(L.b2t_invalidate_ball(_p(d_cc), _p(d_dbf), _p(claim), c_i64(sx), c_i64(sy), c_i64(sz),
-                                  c_f32(anisotropy[0]), c_f32(anisotropy[1]), c_f32(anisotropy[2]), _p(seeds), c_u32(1),
-                                  c_f32(params["soma_invalidation_scale"]), c_f32(params["soma_invalidation_const"]),
-                                  c_vp(scratch.data_ptr() + 4 * base), c_vp(scratch.data_ptr() + 4 * (base + 2 * n)),
-                                  c_u64(n), _p(ws.ctrl), stream_ptr()), "b2t_invalidate_ball")
+      if os.environ.get("B2T_BALL_CCL", "1") == "1":
+        # one seed: the claimed set is a connected component, no frontier sweep needed (b2t_invalidate_ball_single)
+        mark = torch.empty(V, dtype=torch.uint8, device=dev)
+        parent = torch.empty(V, dtype=torch.int32, device=dev)
+        is_root = torch.empty(V, dtype=torch.uint8, device=dev)
+        check(L.b2t_invalidate_ball_single(_p(d_cc), _p(d_dbf), _p(claim), c_i64(sx), c_i64(sy), c_i64(sz),
+                                           c_f32(anisotropy[0]), c_f32(anisotropy[1]), c_f32(anisotropy[2]),
+                                           c_u32(int(desc[slot]["root"])), c_f32(params["soma_invalidation_scale"]),
+                                           c_f32(params["soma_invalidation_const"]), _p(mark), _p(parent), _p(is_root),
+                                           _p(ws.ctrl), stream_ptr()), "b2t_invalidate_ball_single")
+      else:
+        seeds = _dev(np.array([desc[slot]["root"]], dtype=np.uint32).view(np.int32))
+        check(L.b2t_invalidate_ball(_p(d_cc), _p(d_dbf), _p(claim), c_i64(sx), c_i64(sy), c_i64(sz),
+                                    c_f32(anisotropy[0]), c_f32(anisotropy[1]), c_f32(anisotropy[2]), _p(seeds), c_u32(1),
+                                    c_f32(params["soma_invalidation_scale"]), c_f32(params["soma_invalidation_const"]),
+                                    c_vp(scratch.data_ptr() + 4 * base), c_vp(scratch.data_ptr() + 4 * (base + 2 * n)),
+                                    c_u64(n), _p(ws.ctrl), stream_ptr()), "b2t_invalidate_ball")
       desc[slot]["soma_done"] = 1
       desc[slot]["pre_invalid"] = int(ws.ctrl[6].item())
   lap("soma_ball")

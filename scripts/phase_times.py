@@ -13,6 +13,9 @@ import torch
 import kimimaro_b200
 from bench import make_volume, anisotropy_of, skeleton_digests, golden_digest
 
+if os.environ.get("B2T_TRACE_LIMIT"):        # resident path-loop CTAs per SM (b2t_set_launch_limits)
+  from kimimaro_b200 import _lib, engine  # noqa: F401
+  _lib.lib().b2t_set_launch_limits(0, int(os.environ["B2T_TRACE_LIMIT"]))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 vol = make_volume(n)

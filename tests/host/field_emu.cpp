@@ -10,3 +10,12 @@
 #endif
 
 #include "../../kimimaro_b200/csrc/field.cu"
+
+#ifndef B2T_EMU_COMBINED
+// b2t_invalidate_ball_single calls the connected-components entry point of preamble.cu; the stand-alone harness of this
+// file has no preamble.cu, so that one call is only exercised through the combined library (the product tests' soma case)
+extern "C" __attribute__((visibility("default"))) int b2t_ccl26_roots(const void*, int, int64_t, int64_t, int64_t, uint32_t*,
+                                                                      uint8_t*, void*) {
+  return B2T_ERR_ARG;
+}
+#endif
