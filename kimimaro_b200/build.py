@@ -66,6 +66,9 @@ def _compile(extra, out, verbose=False, force=False):
 
 # other builds of the same sources for kernel A/B runs (B2T_LIB=kimimaro_b200/_variants/<name>.so selects one)
 VARIANTS = {
+  "batch2": ["-DB2T_RR_BATCH=2"],     # railroad expands twice / four times as many voxels per round
+  "batch4": ["-DB2T_RR_BATCH=4"],
+  "prof": ["-DB2T_TRACE_PROF"],       # per-phase cycle counters in the path loop (scripts/trace_prof.py)
 }
 
 

@@ -36,7 +36,25 @@
 #define B2T_GLOBALTIMER(v_) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v_))
 #endif
 
+// B2T_TRACE_PROF (variant build "prof"): thread 0 of a label's team accumulates SM cycles per phase of the path loop;
+// b2t_trace_prof_read copies the table of the first 64 jobs (the largest labels) to the host.  Off in the shipped build.
+#ifdef B2T_TRACE_PROF
+#define PROF_START() long long pt_ = 0; if (tid == 0) pt_ = clock64()
+#define PROF_LAP(k_) do { if (tid == 0) { const long long n_ = clock64(); S.prof[k_] += (unsigned long long)(n_ - pt_); pt_ = n_; } } while (0)
+#define PROF_COUNT(k_) do { if (tid == 0) S.prof[k_] += 1ull; } while (0)
+#define PROF_RESET() do { if (tid == 0) pt_ = clock64(); } while (0)
+#else
+#define PROF_RESET() do { } while (0)
+#define PROF_START() do { } while (0)
+#define PROF_LAP(k_) do { } while (0)
+#define PROF_COUNT(k_) do { } while (0)
+#endif
+
 namespace {
+
+#ifdef B2T_TRACE_PROF
+__device__ unsigned long long g_prof[64][16];
+#endif
 
 constexpr uint32_t kInfBits = 0x7f800000u;
 constexpr unsigned long long kValid = ~0ull;
@@ -52,6 +70,9 @@ constexpr int kHeapSlack = B2T_HEAP_SLACK;          // ... plus this many; a hea
 #endif
 constexpr int kWarps = kThreads / 32;
 constexpr int kScratchPerVoxel = 22;   // u32 of queue scratch per foreground voxel of a label (see trace_label); even
+#ifndef B2T_RR_BATCH
+#define B2T_RR_BATCH 1                 // railroad's batch target in units of (2 .. 8) voxels per warp and round
+#endif
 #ifndef B2T_RR_CAP_SHIFT
 #define B2T_RR_CAP_SHIFT 0             // (the CPU harness shrinks railroad's lists to exercise the overflow rebuild)
 #endif
@@ -220,6 +241,9 @@ struct Shared {
   uint32_t relax, rounds, invalidated;
   uint32_t* heap_k;          // strict mode: this label's heap (its own region, or the spill arena once it outgrew that)
   uint32_t heap_cap;         // 0 = not set up yet
+#ifdef B2T_TRACE_PROF
+  unsigned long long prof[16];
+#endif
 };
 
 // team-wide reductions (all threads of the team must call): block reduction, then one value per CTA through `S`
@@ -333,13 +357,14 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
     S.n_keep = 0; S.n_proc = 0; S.n_next = 0; S.r32[1] = 0;
   }
   team_sync<TEAM>();
+  PROF_START();
   uint32_t n_mid = 1, n_far = 0;
   float delta = __ldcg(&A.pdrf[target]);                      // width of the near batch
   if (!(delta > 0.0f) || __float_as_uint(delta) >= kInfBits) delta = 1.0f;
   float delta_mid = __fmul_rn(delta, 16.0f);                   // width of the mid band
   uint32_t thr_mid = __float_as_uint(delta_mid);
   uint32_t relax = 0, rounds = 0;
-  const uint32_t lo_proc = TEAM ? 2u * kWarps * kCluster : 2u * kWarps, hi_proc = 4u * lo_proc;   // batch-size feedback
+  const uint32_t lo_proc = (TEAM ? 2u * kWarps * kCluster : 2u * kWarps) * B2T_RR_BATCH, hi_proc = 4u * lo_proc;   // batch-size feedback
   const uint32_t lo_mid = TEAM ? 256u * kCluster : 256u, hi_mid = 4u * lo_mid;
 
   for (;;) {
@@ -383,12 +408,14 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
       team_sync<TEAM>();
       if (tid == 0) { S.n_keep = 0; S.n_next = 0; }
       team_sync<TEAM>();
+      PROF_LAP(5); PROF_COUNT(13);
       continue;
     }
     // ---- (a) smallest tentative distance in the mid band ----
     uint32_t mn = 0xffffffffu;
     for (uint32_t i = tid; i < n_mid; i += nth) mn = min(mn, (uint32_t)(mid[i] >> 32));
     mn = team_min_u32<TEAM>(mn, S, Lc, T);
+    PROF_LAP(1);
     const uint32_t bound = (uint32_t)(S.best >> 32);
     uint32_t thr = __float_as_uint(__fadd_rn(__uint_as_float(mn), delta));
     if (thr > bound) thr = bound;
@@ -415,6 +442,7 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
       if (tokeep) mid2[bk + __popc(mk & ltmask)] = e;
     }
     team_sync<TEAM>();
+    PROF_LAP(2);
     const uint32_t n_proc = S.n_proc;
     // ---- (c) expand the batch: lane per neighbour, TWO voxels per warp iteration so that their chains of
     //          dependent global accesses (dist of u -> label/weight of v -> atomicMin) overlap ----
@@ -490,6 +518,7 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
       }
     }
     team_sync<TEAM>();
+    PROF_LAP(3);
     n_mid = S.n_keep;
     n_far += S.n_next;
     const bool overflow = S.r32[1] != 0u;
@@ -501,6 +530,7 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
     team_sync<TEAM>();
     if (tid == 0) { S.n_keep = 0; S.n_proc = 0; S.n_next = 0; S.r32[1] = 0; }
     team_sync<TEAM>();
+    PROF_LAP(4);
     if (overflow) {
       // a list filled up with superseded pairs (and lost some new ones): rebuild the pile from the voxels this search has
       // touched -- one fresh pair for every voxel that is not final yet (everything below this round's smallest open
@@ -589,6 +619,7 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
     if (lane == 0) S.r32[0] = len;
   }
   team_sync<TEAM>();
+  PROF_LAP(6);
   len = S.r32[0];
   // (e) reset the distance field on every voxel this search touched
   const uint32_t nt = S.n_touched;
@@ -596,6 +627,7 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
   relax = team_sum_u32<TEAM>(relax, S, Lc, T);
   if (tid == 0) { S.relax += relax; S.rounds += rounds; }
   team_sync<TEAM>();
+  PROF_LAP(7);
   return len;
 }
 
@@ -711,6 +743,7 @@ __device__ __noinline__ uint32_t invalidate_window(const Arena& A, const LabelDe
   const uint32_t ltmask = (1u << lane) - 1u;
   if (tid == 0) { S.n_next = 0; S.n_keep = 0; }
   team_sync<TEAM>();
+  PROF_START();
   // round 0: every still-valid seed claims itself (key 0)
   for (uint32_t i0 = 0; i0 < n_seeds; i0 += nth) {
     const uint32_t i = i0 + tid;
@@ -767,11 +800,13 @@ __device__ __noinline__ uint32_t invalidate_window(const Arena& A, const LabelDe
     n_act += S.n_keep;
     team_sync<TEAM>();
     if (tid == 0) { S.n_next = 0; S.n_keep = 0; S.n_proc = 0; }
+    PROF_LAP(8);
     if (n_act == 0) break;
     // smallest open key (non-negative floats order like their bit patterns)
     uint32_t kmin = 0xffffffffu;
     for (uint32_t i = tid; i < n_act; i += nth) kmin = min(kmin, (uint32_t)(__ldcg(&A.claim[act[i]]) >> 32));
     kmin = team_min_u32<TEAM>(kmin, S, Lc, T);     // also orders the counter reset above before the appends below
+    PROF_LAP(9);
     const float lim = __fadd_rn(__uint_as_float(kmin), delta);
     // claim what is inside the window, keep the rest open
     for (uint32_t i0 = 0; i0 < n_act; i0 += nth) {
@@ -804,6 +839,7 @@ __device__ __noinline__ uint32_t invalidate_window(const Arena& A, const LabelDe
     team_sync<TEAM>();
     if (tid == 0) { S.n_keep = 0; }
     team_sync<TEAM>();
+    PROF_LAP(10); PROF_COUNT(12);
   }
   team_sync<TEAM>();
   return total;
@@ -1088,8 +1124,12 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
     S.relax = 0; S.rounds = 0; S.invalidated = 0;
     S.heap_cap = 0;
     A.pdrf[L.root] = 0.0f;      // parents[root] = 0: the first rail (trace.py:220)
+#ifdef B2T_TRACE_PROF
+    for (int i = 0; i < 16; i++) S.prof[i] = 0ull;
+#endif
   }
   team_sync<TEAM>();
+  PROF_START();
   uint32_t valid = L.n_fg;
   int32_t status = 0;
   if (L.soma_mode) {            // one-off soma invalidation around the root (trace.py:160-168)
@@ -1107,7 +1147,9 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
     if (tb_n > 0) target = P.targets[L.tb_off + (--tb_n)];
     else if (valid == 0) target = P.targets[L.ta_off + (--ta_n)];
     else {
+      PROF_LAP(11);
       target = find_target<TEAM>(A, L, P, prm, S, Lc, T);
+      PROF_LAP(0);
       if (target == 0xffffffffu) { status = -10; break; }   // bookkeeping mismatch: valid > 0 but no valid voxel
     }
     if (used + 2 > L.path_cap) { status = B2T_ERR_CAPACITY; break; }
@@ -1115,6 +1157,7 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
     const uint32_t cap = L.path_cap - used - 1;
     uint32_t len = prm.fix_branching ? railroad<TEAM>(A, L, target, pl0, pl1, pl4, pl2, pl3, touched, pout, cap, S, Lc, T)
                                      : path_from_parents<TEAM>(A, L, target, pout, cap, S, T);
+    PROF_RESET();
     if (len > cap) { status = B2T_ERR_CAPACITY; break; }
     if (L.soma_mode) {
       // keep path[:1] + points farther than soma_radius from the root; float64, uint32 wrap
@@ -1155,6 +1198,7 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
       }
       valid -= min(valid, n);
       if (tid == 0) S.invalidated += n;
+      PROF_RESET();
     }
     if (prm.fix_branching)
       for (uint32_t i = tid; i < len; i += nth) A.pdrf[pout[i]] = 0.0f;   // trace.py:261-263
@@ -1173,6 +1217,9 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
     unsigned long long t_end;
     B2T_GLOBALTIMER(t_end);
     P.out_stats[4 * job + 3] = (uint32_t)((t_end - t_start) / 1000ull);   // microseconds this label held its team
+#ifdef B2T_TRACE_PROF
+    if (job < 64) for (int i = 0; i < 16; i++) g_prof[job][i] = S.prof[i];
+#endif
   }
   team_sync<TEAM>();
 }
@@ -1227,6 +1274,15 @@ B2T_EXPORT uint64_t b2t_trace_scratch_words(uint64_t sum_n_fg) { return (uint64_
 
 // bytes of one team slot (d_team of b2t_trace_batch holds n_team of them)
 B2T_EXPORT uint64_t b2t_trace_team_bytes(void) { return sizeof(Shared); }
+
+#if defined(B2T_TRACE_PROF) && !defined(B2T_HOST_EMU)
+// variant build only: 64 x 16 u64 (cycles per phase, rows = the first 64 jobs of the last batch)
+B2T_EXPORT int b2t_trace_prof_read(unsigned long long* h_out) {
+  B2T_CUDA_TRY(cudaDeviceSynchronize());
+  B2T_CUDA_TRY(cudaMemcpyFromSymbol(h_out, g_prof, sizeof(unsigned long long) * 64 * 16));
+  return B2T_OK;
+}
+#endif
 
 #ifndef B2T_HOST_EMU
 B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* d_pdrf, float* d_dist, uint64_t* d_claim,
