@@ -66,9 +66,12 @@ def _compile(extra, out, verbose=False, force=False):
 
 # other builds of the same sources for kernel A/B runs (B2T_LIB=kimimaro_b200/_variants/<name>.so selects one)
 VARIANTS = {
-  "batch2": ["-DB2T_RR_BATCH=2"],     # railroad expands twice / four times as many voxels per round
-  "batch4": ["-DB2T_RR_BATCH=4"],
   "prof": ["-DB2T_TRACE_PROF"],       # per-phase cycle counters in the path loop (scripts/trace_prof.py)
+  "rr_global": ["-DB2T_RR_SOLO=0"],   # solo CTAs keep railroad's near lists in global memory (the form before railroad_solo)
+  "minb2": ["-DB2T_TRACE_MINB=2"],    # 64 registers per thread in the path loop instead of 42 (two resident CTAs per SM)
+  "minb1": ["-DB2T_TRACE_MINB=1"],    # 128 registers, one resident CTA per SM
+  "batch2": ["-DB2T_RR_BATCH=2"],     # railroad aims at 64..256 voxels per round instead of 32..128
+  "minb2_batch2": ["-DB2T_TRACE_MINB=2", "-DB2T_RR_BATCH=2"],
 }
 
 

@@ -231,8 +231,14 @@ struct Local {
 };
 
 // Per-label state: shared memory (solo) or a global-memory slot of the team.
+// railroad_solo: the counters of one round (two sets, used alternately)
+struct RoundCounters {
+  uint32_t n_keep, n_proc, n_next, min_next, min_far, overflow;
+};
+
 struct Shared {
   unsigned long long best;   // railroad: (dist_bits << 32) | voxel of the best rail-adjacent voxel
+  RoundCounters rc[2];
   unsigned long long x64[2][kCluster];   // team reductions: one value per CTA, two parities
   uint32_t n_keep, n_proc, n_next, n_touched;
   uint32_t r32[2];           // small results handed from one thread to the team
@@ -303,6 +309,87 @@ __device__ uint32_t find_target(const Arena& A, const LabelDesc& L, const Pools&
     if (t_tid<TEAM>(T) == 0) S.bucket = b - 1;
     team_sync<TEAM>();
   }
+}
+
+// (d) + (e) of railroad: walk back from the best rail-adjacent voxel (rule T4) along parents by rule T3, then put the
+// distance field back to +inf on every voxel the search touched.  Shared by the team form and the solo form below.
+template <bool TEAM>
+__device__ __forceinline__ uint32_t railroad_finish(const Arena& A, const LabelDesc& L, uint32_t target, const uint32_t* touched,
+                                                    uint32_t* out, uint32_t out_cap, uint32_t relax, uint32_t rounds, Shared& S,
+                                                    Local& Lc, Team& T) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t tid = t_tid<TEAM>(T), nth = t_threads<TEAM>(), tw = t_warp<TEAM>(T);
+  const uint32_t seg = L.segid;
+  int dx = 0, dy = 0, dz = 0;
+  if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; }
+  const int64_t off = (int64_t)dx + (int64_t)dy * A.d.sx + (int64_t)dz * A.d.sxy;
+  PROF_START();
+  // (d) walk back: rail voxel, then parents by rule T3
+  uint32_t len = 0;
+  const unsigned long long best = S.best;
+  if (tw == 0) {
+    if (best == ~0ull) {
+      if (lane == 0 && out_cap > 0) out[0] = target;
+      len = 1;
+    } else {
+      uint32_t loc = (uint32_t)best;
+      {
+        int x, y, z;
+        unravel(loc, A.d, x, y, z);
+        const int nx = x + dx, ny = y + dy, nz = z + dz;
+        bool israil = false;
+        uint32_t v = 0;
+        if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
+          v = (uint32_t)((int64_t)loc + off);
+          israil = (__ldg(&A.cc[v]) == seg) && (__ldcg(&A.pdrf[v]) == 0.0f);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, israil);
+        const int first = __ffs(m) - 1;
+        const uint32_t rail = __shfl_sync(0xffffffffu, v, first < 0 ? 0 : first);
+        if (lane == 0 && len < out_cap) out[len] = rail;
+        len++;
+      }
+      uint32_t guard = 0;
+      while (loc != target && guard <= L.n_fg) {
+        if (lane == 0 && len < out_cap) out[len] = loc;
+        len++;
+        int x, y, z;
+        unravel(loc, A.d, x, y, z);
+        const int nx = x + dx, ny = y + dy, nz = z + dz;
+        unsigned long long key = ~0ull;
+        if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
+          const uint32_t v = (uint32_t)((int64_t)loc + off);
+          if (__ldg(&A.cc[v]) == seg) {
+            const uint32_t dv = __float_as_uint(__ldcg(&A.dist[v]));
+            if (dv < kInfBits) key = ((unsigned long long)dv << 32) | (unsigned long long)lane;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o);
+          key = t < key ? t : key;
+        }
+        if (key == ~0ull) break;  // cannot happen for a settled voxel
+        const int dir = (int)(key & 31u);
+        loc = (uint32_t)((int64_t)loc + (int64_t)kDX[dir] + (int64_t)kDY[dir] * A.d.sx + (int64_t)kDZ[dir] * A.d.sxy);
+        guard++;
+      }
+      if (lane == 0 && len < out_cap) out[len] = target;
+      len++;
+    }
+    if (lane == 0) S.r32[0] = len;
+  }
+  team_sync<TEAM>();
+  PROF_LAP(6);
+  len = S.r32[0];
+  // (e) reset the distance field on every voxel this search touched
+  const uint32_t nt = S.n_touched;
+  for (uint32_t i = tid; i < nt; i += nth) A.dist[touched[i]] = __int_as_float(kInfBits);
+  relax = team_sum_u32<TEAM>(relax, S, Lc, T);
+  if (tid == 0) { S.relax += relax; S.rounds += rounds; }
+  team_sync<TEAM>();
+  PROF_LAP(7);
+  return len;
 }
 
 // ---- dijkstra3d.railroad ----------------------------------------------------------------------------
@@ -563,72 +650,292 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
     }
   }
 
-  // (d) walk back: rail voxel, then parents by rule T3
-  uint32_t len = 0;
-  const unsigned long long best = S.best;
-  if (tw == 0) {
-    if (best == ~0ull) {
-      if (lane == 0 && out_cap > 0) out[0] = target;
-      len = 1;
-    } else {
-      uint32_t loc = (uint32_t)best;
-      {
-        int x, y, z;
-        unravel(loc, A.d, x, y, z);
-        const int nx = x + dx, ny = y + dy, nz = z + dz;
-        bool israil = false;
-        uint32_t v = 0;
-        if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
-          v = (uint32_t)((int64_t)loc + off);
-          israil = (__ldg(&A.cc[v]) == seg) && (__ldcg(&A.pdrf[v]) == 0.0f);
+  return railroad_finish<TEAM>(A, L, target, touched, out, out_cap, relax, rounds, S, Lc, T);
+}
+
+// ---- railroad for a solo CTA: the near lists live in SHARED memory ------------------------------------------------
+// Same search, same result (the least fixed point does not depend on the order of the relaxations); what changes is
+// where a round's time goes.  A label's path loop is a chain of ~100 rounds per path and the profile of the global-
+// memory form (profiles/r02_trace_prof_before.jsonl) shows ~20 us per round, spent on dependent round trips to L2:
+// the band is streamed twice (min, split), the batch is read back, then dist[u] -> cc/pdrf[v] -> atomicMin.  Here
+//   * the mid band (both halves) and the batch are shared-memory arrays; entries that do not fit go to the far pile,
+//   * the smallest key of the next band is tracked while the band is written (split and push), so no min pass,
+//   * the counters of a round come in two sets used alternately, so nothing has to be reset between two barriers,
+//   * dist[u] is loaded together with the neighbours' label / weight instead of before them,
+// which leaves two block barriers and two global round trips (loads, atomicMin) per round.
+#ifndef B2T_RR_SOLO_CAP
+#define B2T_RR_SOLO_CAP 2048           // entries per shared-memory list (three lists of 8-byte pairs: 48 KB per CTA)
+#endif
+#ifndef B2T_RR_SOLO
+#define B2T_RR_SOLO 1                  // solo CTAs use railroad_solo (0: the global-memory form everywhere)
+#endif
+#ifndef B2T_RR_E
+#define B2T_RR_E 2                     // voxels a warp expands together (their global round trips overlap)
+#endif
+constexpr uint32_t kSoloCap = B2T_RR_SOLO_CAP;
+struct RrLists {
+  unsigned long long mid[2][kSoloCap];
+  unsigned long long proc[kSoloCap];
+};
+
+__device__ uint32_t railroad_solo(const Arena& A, const LabelDesc& L, uint32_t target, RrLists& R, unsigned long long* farA,
+                                  unsigned long long* farB, uint32_t* touched, uint32_t* out, uint32_t out_cap, Shared& S,
+                                  Local& Lc, Team& T) {
+  constexpr int E = B2T_RR_E;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tid = threadIdx.x, nth = kThreads, tw = threadIdx.x >> 5;
+  const uint32_t seg = L.segid;
+  const uint32_t cap = B2T_RR_CAP_SHIFT ? max(64u, (2u * L.n_fg) >> B2T_RR_CAP_SHIFT) : 2u * L.n_fg;   // far lists (global)
+#ifndef B2T_RR_SCAP_SHIFT
+#define B2T_RR_SCAP_SHIFT B2T_RR_CAP_SHIFT
+#endif
+  const uint32_t scap = B2T_RR_SCAP_SHIFT ? max(64u, kSoloCap >> B2T_RR_SCAP_SHIFT) : kSoloCap;         // shared lists
+  if (__ldcg(&A.pdrf[target]) == 0.0f) {
+    if (tid == 0 && out_cap > 0) out[0] = target;
+    __syncthreads();
+    return out_cap > 0 ? 1 : 0;
+  }
+  int dx = 0, dy = 0, dz = 0;
+  if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; }
+  const int64_t off = (int64_t)dx + (int64_t)dy * A.d.sx + (int64_t)dz * A.d.sxy;
+  const uint32_t ltmask = (1u << lane) - 1u;
+
+  unsigned long long* far = farA;
+  unsigned long long* far2 = farB;
+  int cur = 0;                                   // R.mid[cur] is the band of this round, R.mid[cur ^ 1] the next one
+  uint32_t par = 0;                              // S.rc[par]: the counters of this round
+  if (tid == 0) {
+    A.dist[target] = 0.0f;
+    R.mid[0][0] = rr_pair(0u, target);
+    touched[0] = target;
+    S.n_touched = 1;
+    S.best = ~0ull;
+    S.rc[0] = RoundCounters{0u, 0u, 0u, 0xffffffffu, 0xffffffffu, 0u};
+    S.rc[1] = RoundCounters{0u, 0u, 0u, 0xffffffffu, 0xffffffffu, 0u};
+  }
+  __syncthreads();
+  PROF_START();
+  uint32_t n_mid = 1, n_far = 0, mn = 0u;        // mn: smallest key in the band
+  uint32_t far_low = 0xffffffffu;                // a lower bound of every key in the far pile
+  float delta = __ldcg(&A.pdrf[target]);
+  if (!(delta > 0.0f) || __float_as_uint(delta) >= kInfBits) delta = 1.0f;
+  float delta_mid = __fmul_rn(delta, 16.0f);
+  uint32_t thr_mid = __float_as_uint(delta_mid);
+  uint32_t relax = 0, rounds = 0;
+  const uint32_t lo_proc = 32u * B2T_RR_BATCH, hi_proc = 4u * lo_proc;    // voxels per round: up to 170 expand in one pass of the CTA
+  const uint32_t lo_mid = 256u, hi_mid = 1024u;
+
+  for (;;) {
+    RoundCounters& C = S.rc[par];
+    if (n_mid == 0) {
+      // ---- refill the band from the far pile (global memory; rare) ----
+      if (n_far == 0) break;
+      const uint32_t bound = (uint32_t)(S.best >> 32);
+      uint32_t fm = 0xffffffffu;
+      for (uint32_t i = tid; i < n_far; i += nth) fm = min(fm, (uint32_t)(far[i] >> 32));
+      fm = block_min_u32(fm, Lc.red32);
+      if (fm > bound) break;                                  // nothing left that could beat the rail we have
+      thr_mid = __float_as_uint(__fadd_rn(__uint_as_float(fm), delta_mid));
+      if (thr_mid > bound) thr_mid = bound;
+      for (uint32_t i0 = 0; i0 < n_far; i0 += nth) {
+        const uint32_t i = i0 + tid;
+        bool tomid = false, tokeep = false;
+        unsigned long long e = 0;
+        if (i < n_far) {
+          e = far[i];
+          const uint32_t du = (uint32_t)(e >> 32);
+          tomid = du <= thr_mid;
+          tokeep = !tomid && du <= bound;                     // beyond the bound: dropped for good
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, israil);
-        const int first = __ffs(m) - 1;
-        const uint32_t rail = __shfl_sync(0xffffffffu, v, first < 0 ? 0 : first);
-        if (lane == 0 && len < out_cap) out[len] = rail;
-        len++;
+        const uint32_t mp = __ballot_sync(0xffffffffu, tomid);
+        uint32_t bp = 0;
+        if (lane == 0 && mp) bp = atomicAdd(&C.n_keep, __popc(mp));
+        bp = __shfl_sync(0xffffffffu, bp, 0);
+        if (tomid) {
+          const uint32_t pm = bp + __popc(mp & ltmask);
+          if (pm < scap) R.mid[cur][pm] = e; else { tomid = false; tokeep = true; }   // band full: stays in the pile
+        }
+        const uint32_t mk = __ballot_sync(0xffffffffu, tokeep);
+        uint32_t bk = 0;
+        if (lane == 0 && mk) bk = atomicAdd(&C.n_next, __popc(mk));
+        bk = __shfl_sync(0xffffffffu, bk, 0);
+        if (tokeep) far2[bk + __popc(mk & ltmask)] = e;
       }
-      uint32_t guard = 0;
-      while (loc != target && guard <= L.n_fg) {
-        if (lane == 0 && len < out_cap) out[len] = loc;
-        len++;
-        int x, y, z;
-        unravel(loc, A.d, x, y, z);
-        const int nx = x + dx, ny = y + dy, nz = z + dz;
-        unsigned long long key = ~0ull;
-        if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
-          const uint32_t v = (uint32_t)((int64_t)loc + off);
-          if (__ldg(&A.cc[v]) == seg) {
-            const uint32_t dv = __float_as_uint(__ldcg(&A.dist[v]));
-            if (dv < kInfBits) key = ((unsigned long long)dv << 32) | (unsigned long long)lane;
+      __syncthreads();
+      n_mid = min(C.n_keep, scap);
+      n_far = C.n_next;
+      mn = fm;                                                // the smallest key moved with the others
+      far_low = fm;
+      { unsigned long long* t = far; far = far2; far2 = t; }
+      if (n_mid < lo_mid) delta_mid = __fmul_rn(delta_mid, 2.0f);
+      else if (n_mid > hi_mid) delta_mid = __fmul_rn(delta_mid, 0.5f);
+      __syncthreads();
+      if (tid == 0) { C.n_keep = 0; C.n_next = 0; }
+      __syncthreads();
+      PROF_LAP(5); PROF_COUNT(13);
+      continue;
+    }
+    const uint32_t bound = (uint32_t)(S.best >> 32);
+    uint32_t thr = __float_as_uint(__fadd_rn(__uint_as_float(mn), delta));
+    if (thr > bound) thr = bound;
+    // ---- (b) split the band: <= thr expand now, <= thr_mid keep, <= bound to the far pile, else drop ----
+    uint32_t pmin = 0xffffffffu, fmin = 0xffffffffu;
+    {
+      const unsigned long long* midc = R.mid[cur];
+      unsigned long long* midn = R.mid[cur ^ 1];
+      const bool can_shed = n_far + n_mid <= cap;              // shedding never overflows the pile: only a relaxation may
+      for (uint32_t i0 = 0; i0 < n_mid; i0 += nth) {
+        const uint32_t i = i0 + tid;
+        bool toproc = false, tokeep = false, tofar = false;
+        unsigned long long e = 0;
+        if (i < n_mid) {
+          e = midc[i];
+          const uint32_t du = (uint32_t)(e >> 32);
+          toproc = du <= thr;
+          tokeep = !toproc && (du <= thr_mid || !can_shed) && du <= bound;
+          tofar = !toproc && !tokeep && du <= bound;            // the band was narrowed after this pair came in
+          if (tokeep) pmin = min(pmin, du);
+        }
+        const uint32_t mp = __ballot_sync(0xffffffffu, toproc), mk = __ballot_sync(0xffffffffu, tokeep);
+        uint32_t bp = 0, bk = 0;
+        if (lane == 0) {
+          if (mp) bp = atomicAdd(&C.n_proc, __popc(mp));
+          if (mk) bk = atomicAdd(&C.n_keep, __popc(mk));
+        }
+        bp = __shfl_sync(0xffffffffu, bp, 0);
+        bk = __shfl_sync(0xffffffffu, bk, 0);
+        if (toproc) R.proc[bp + __popc(mp & ltmask)] = e;      // at most n_mid <= scap entries
+        if (tokeep) midn[bk + __popc(mk & ltmask)] = e;        // likewise
+        if (tofar) {
+          far[n_far + atomicAdd(&C.n_next, 1u)] = e;
+          fmin = min(fmin, (uint32_t)(e >> 32));
+        }
+      }
+    }
+    __syncthreads();
+    PROF_LAP(2);
+    if (tid == 0) S.rc[par ^ 1] = RoundCounters{0u, 0u, 0u, 0xffffffffu, 0xffffffffu, 0u};   // the next round's set: idle until the barrier below
+    const uint32_t n_proc = C.n_proc;
+    // ---- (c) expand the batch: one thread per (voxel, z-plane of its neighbourhood), nine neighbours each.  The order of
+    //          the relaxations does not matter (least fixed point; rule T4 is an atomicMin), so the neighbours are taken in
+    //          memory order: three rows of three per thread, all loads in flight before the first atomic ----
+    const uint32_t bound_now = (uint32_t)(S.best >> 32);
+    for (uint32_t task = tid; task < 3u * n_proc; task += nth) {
+      const uint32_t i = task / 3u, q = task - 3u * i;
+      const unsigned long long pe = R.proc[i];
+      const uint32_t u = (uint32_t)pe, dq = (uint32_t)(pe >> 32);
+      int x, y, z;
+      unravel(u, A.d, x, y, z);
+      const int nz = z + (int)q - 1;
+      const float du = __ldcg(&A.dist[u]);
+      const bool planeok = nz >= 0 && nz < A.d.sz;
+      const int64_t base = (int64_t)u + ((int64_t)q - 1) * (int64_t)A.d.sxy;
+      uint32_t lv[9];
+      float c[9];
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        const int ddx = j % 3 - 1, ddy = j / 3 - 1;
+        const int nx = x + ddx, ny = y + ddy;
+        const bool ok = planeok && nx >= 0 && nx < A.d.sx && ny >= 0 && ny < A.d.sy && !(j == 4 && q == 1u);
+        const uint32_t v = (uint32_t)(base + (int64_t)ddy * A.d.sx + ddx);
+        lv[j] = ok ? __ldg(&A.cc[v]) : seg + 1u;                          // never equal to seg
+        c[j] = ok ? __ldcg(&A.pdrf[v]) : 0.0f;
+      }
+      if (__float_as_uint(du) != dq) continue;                            // a superseded pair: its voxel has (had) a closer one
+      uint32_t nd[9], old[9];
+      bool rail = false;
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        nd[j] = 0u; old[j] = 0u;
+        if (lv[j] == seg) {
+          if (c[j] == 0.0f) rail = true;
+          else {
+            nd[j] = __float_as_uint(__fadd_rn(du, c[j]));
+            if (nd[j] <= bound_now) {
+              const int ddx = j % 3 - 1, ddy = j / 3 - 1;
+              const uint32_t v = (uint32_t)(base + (int64_t)ddy * A.d.sx + ddx);
+              old[j] = atomicMin(reinterpret_cast<uint32_t*>(&A.dist[v]), nd[j]);
+            }
           }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o);
-          key = t < key ? t : key;
-        }
-        if (key == ~0ull) break;  // cannot happen for a settled voxel
-        const int dir = (int)(key & 31u);
-        loc = (uint32_t)((int64_t)loc + (int64_t)kDX[dir] + (int64_t)kDY[dir] * A.d.sx + (int64_t)kDZ[dir] * A.d.sxy);
-        guard++;
       }
-      if (lane == 0 && len < out_cap) out[len] = target;
-      len++;
+      if (rail) atomicMin(&S.best, ((unsigned long long)dq << 32) | u);  // rule T4 candidate
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        if (nd[j] < old[j]) {                                             // relaxed (old stays 0 where nothing was tried)
+          const int ddx = j % 3 - 1, ddy = j / 3 - 1;
+          const uint32_t v = (uint32_t)(base + (int64_t)ddy * A.d.sx + ddx);
+          relax++;
+          if (old[j] == kInfBits) touched[atomicAdd(&S.n_touched, 1u)] = v;   // first time this search reaches v
+          bool tofar = nd[j] > thr_mid;
+          if (!tofar) {
+            const uint32_t pm = atomicAdd(&C.n_keep, 1u);
+            if (pm < scap) { R.mid[cur ^ 1][pm] = rr_pair(nd[j], v); pmin = min(pmin, nd[j]); }
+            else tofar = true;                                            // band full: to the pile
+          }
+          if (tofar) {
+            const uint32_t pf = n_far + atomicAdd(&C.n_next, 1u);
+            if (pf < cap) { far[pf] = rr_pair(nd[j], v); fmin = min(fmin, nd[j]); } else C.overflow = 1u;
+          }
+        }
+      }
     }
-    if (lane == 0) S.r32[0] = len;
+    if (pmin != 0xffffffffu) atomicMin(&C.min_next, pmin);
+    if (fmin != 0xffffffffu) atomicMin(&C.min_far, fmin);
+    __syncthreads();
+    PROF_LAP(3);
+    n_mid = min(C.n_keep, scap);
+    n_far += C.n_next;                                        // exact unless a push was lost (then the pile is rebuilt below)
+    const uint32_t mn_round = mn;                             // every open key of this round was >= min(mn_round, far_low)
+    const uint32_t low = min(mn_round, far_low);
+    mn = C.min_next;
+    far_low = min(far_low, C.min_far);
+    const bool overflow = C.overflow != 0u;
+    cur ^= 1;
+    par ^= 1u;
+    if (n_proc < lo_proc) delta = __fmul_rn(delta, 2.0f);
+    else if (n_proc > hi_proc) delta = __fmul_rn(delta, 0.5f);
+    if (n_mid > hi_mid || C.n_keep > scap) {                  // the band outgrew its list: narrow it, the next split sheds the rest
+      delta_mid = __fmul_rn(delta_mid, 0.5f);
+      const uint32_t t = __float_as_uint(__fadd_rn(__uint_as_float(mn), delta_mid));
+      if (t < thr_mid) thr_mid = t;
+    }
+    rounds++;
+    if (overflow) {
+      // the far pile filled up with superseded pairs (and lost some new ones): rebuild it from the voxels this search has
+      // touched -- one fresh pair for every voxel that may not be final yet; the band is dropped, its live pairs come back
+      // with the others
+#ifdef B2T_HOST_EMU
+      if (tid == 0) g_emu_rr_rebuilds++;
+#endif
+      RoundCounters& C2 = S.rc[par];                          // reset after the split barrier of the round that just ended
+      const uint32_t nt = S.n_touched;                        // below `low`: expanded with its final distance already
+      for (uint32_t i0 = 0; i0 < nt; i0 += nth) {
+        const uint32_t i = i0 + tid;
+        bool keep = false;
+        uint32_t v = 0, dv = 0;
+        if (i < nt) {
+          v = touched[i];
+          dv = __float_as_uint(__ldcg(&A.dist[v]));
+          keep = dv >= low && dv <= (uint32_t)(S.best >> 32);
+        }
+        const uint32_t mk = __ballot_sync(0xffffffffu, keep);
+        uint32_t bk = 0;
+        if (lane == 0 && mk) bk = atomicAdd(&C2.n_next, __popc(mk));
+        bk = __shfl_sync(0xffffffffu, bk, 0);
+        if (keep) far[bk + __popc(mk & ltmask)] = rr_pair(dv, v);
+      }
+      __syncthreads();
+      n_mid = 0;
+      n_far = C2.n_next;
+      far_low = low;
+      __syncthreads();
+      if (tid == 0) { C2.n_next = 0; }
+      __syncthreads();
+    }
+    PROF_LAP(4);
   }
-  team_sync<TEAM>();
-  PROF_LAP(6);
-  len = S.r32[0];
-  // (e) reset the distance field on every voxel this search touched
-  const uint32_t nt = S.n_touched;
-  for (uint32_t i = tid; i < nt; i += nth) A.dist[touched[i]] = __int_as_float(kInfBits);
-  relax = team_sum_u32<TEAM>(relax, S, Lc, T);
-  if (tid == 0) { S.relax += relax; S.rounds += rounds; }
-  team_sync<TEAM>();
-  PROF_LAP(7);
-  return len;
+  return railroad_finish<false>(A, L, target, touched, out, out_cap, relax, rounds, S, Lc, T);
 }
 
 // ---- roll_invalidation_ball_inside_component ---------------------------------------------------------
@@ -762,38 +1069,48 @@ __device__ __noinline__ uint32_t invalidate_window(const Arena& A, const LabelDe
   team_sync<TEAM>();
   uint32_t n_cur = S.n_next, n_act = 0, total = n_cur;
   while (n_cur > 0) {
-    // the voxels claimed in the last round push candidates; a voxel that gets its first one joins the open list
-    for (uint32_t it = tw; it < n_cur; it += ntw) {
-      const uint32_t u = fv[it], s = fs[it];
+    // the voxels claimed in the last round push candidates; a voxel that gets its first one joins the open list.
+    // One thread per (voxel, z-plane of its neighbourhood): the winner of a voxel is the smallest (distance, seed) pair
+    // whatever the order of the pushes, so the nine neighbours are taken in memory order with all loads in flight together.
+    for (uint32_t task = tid; task < 3u * n_cur; task += nth) {
+      const uint32_t i = task / 3u, q = task - 3u * i;
+      const uint32_t u = fv[i], s = fs[i];
       const uint32_t o = seeds[s];
       const float r = __fadd_rn(__fmul_rn(scale, __ldg(&A.dbf[o])), konst);
       int x, y, z, ox, oy, oz;
       unravel(u, A.d, x, y, z);
       unravel(o, A.d, ox, oy, oz);
-      const int nx = x + dx, ny = y + dy, nz = z + dz;
-      bool push = false;
-      uint32_t v = 0;
-      if (lane < 26 && nx >= 0 && ny >= 0 && nz >= 0 && nx < A.d.sx && ny < A.d.sy && nz < A.d.sz) {
-        v = (uint32_t)((int64_t)u + off);
-        const uint32_t lv = __ldg(&A.cc[v]);
-        const unsigned long long cl = __ldcg(&A.claim[v]);
-        if (lv == seg && cl != 0ull) {
-          const float a = __fmul_rn(A.wx, (float)(nx - ox)), b = __fmul_rn(A.wy, (float)(ny - oy)),
-                      c = __fmul_rn(A.wz, (float)(nz - oz));
-          const float dd = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));
+      const int nz = z + (int)q - 1;
+      if (nz < 0 || nz >= A.d.sz) continue;
+      const int64_t base = (int64_t)u + ((int64_t)q - 1) * (int64_t)A.d.sxy;
+      uint32_t lv[9];
+      unsigned long long cl[9];
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        const int ddx = j % 3 - 1, ddy = j / 3 - 1;
+        const int nx = x + ddx, ny = y + ddy;
+        const bool ok = nx >= 0 && nx < A.d.sx && ny >= 0 && ny < A.d.sy && !(j == 4 && q == 1u);
+        const uint32_t v = (uint32_t)(base + (int64_t)ddy * A.d.sx + ddx);
+        lv[j] = ok ? __ldg(&A.cc[v]) : seg + 1u;                          // never equal to seg
+        cl[j] = ok ? __ldcg(&A.claim[v]) : 0ull;
+      }
+      const float c = __fmul_rn(A.wz, (float)(nz - oz));
+      const float cc2 = __fmul_rn(c, c);
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        if (lv[j] == seg && cl[j] != 0ull) {
+          const int ddx = j % 3 - 1, ddy = j / 3 - 1;
+          const float a = __fmul_rn(A.wx, (float)(x + ddx - ox)), b = __fmul_rn(A.wy, (float)(y + ddy - oy));
+          const float dd = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), cc2));
           if (dd < r) {
+            const uint32_t v = (uint32_t)(base + (int64_t)ddy * A.d.sx + ddx);
             const unsigned long long cand = ((unsigned long long)__float_as_uint(dd) << 32) | s;
-            const unsigned long long old = atomicMin(&A.claim[v], cand);
-            push = old == kValid;
+            if (cand < cl[j]) {                                           // cannot win otherwise: claims only ever decrease
+              const unsigned long long old = atomicMin(&A.claim[v], cand);
+              if (old == kValid) act[n_act + atomicAdd(&S.n_keep, 1u)] = v;
+            }
           }
         }
-      }
-      const uint32_t m = __ballot_sync(0xffffffffu, push);
-      if (m) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&S.n_keep, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (push) act[n_act + base + __popc(m & ltmask)] = v;
       }
     }
     team_sync<TEAM>();
@@ -1100,7 +1417,7 @@ __device__ uint32_t path_from_parents(const Arena& A, const LabelDesc& L, uint32
 // ---- the per-label conductor (trace.py:196-267) ----------------------------------------------------
 template <bool TEAM>
 __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, const Params& prm, Shared& S, Local& Lc,
-                            Team& T, uint32_t job) {
+                            Team& T, uint32_t job, RrLists* R) {
   const uint32_t tid = t_tid<TEAM>(T), nth = t_threads<TEAM>();
   // scratch of the label: kScratchPerVoxel u32 per voxel.  Four pair lists and the batch of railroad (2 n_fg entries of
   // 2 words each), the touched list; the invalidation's four voxel lists alias the first pair list between searches.
@@ -1155,8 +1472,10 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
     if (used + 2 > L.path_cap) { status = B2T_ERR_CAPACITY; break; }
     uint32_t* pout = out + used;
     const uint32_t cap = L.path_cap - used - 1;
-    uint32_t len = prm.fix_branching ? railroad<TEAM>(A, L, target, pl0, pl1, pl4, pl2, pl3, touched, pout, cap, S, Lc, T)
-                                     : path_from_parents<TEAM>(A, L, target, pout, cap, S, T);
+    uint32_t len;
+    if (!prm.fix_branching) len = path_from_parents<TEAM>(A, L, target, pout, cap, S, T);
+    else if (!TEAM && B2T_RR_SOLO) len = railroad_solo(A, L, target, *R, pl2, pl3, touched, pout, cap, S, Lc, T);
+    else len = railroad<TEAM>(A, L, target, pl0, pl1, pl4, pl2, pl3, touched, pout, cap, S, Lc, T);
     PROF_RESET();
     if (len > cap) { status = B2T_ERR_CAPACITY; break; }
     if (L.soma_mode) {
@@ -1231,12 +1550,19 @@ __global__ void __launch_bounds__(kThreads, B2T_TRACE_MINB) trace_kernel(Arena A
   __shared__ Shared S;
   __shared__ Local Lc;
   __shared__ LabelDesc L;
+#ifdef B2T_HOST_EMU
+  static RrLists rr_lists;                       // one emulated block at a time
+  RrLists* R = &rr_lists;
+#else
+  extern __shared__ __align__(16) unsigned char b2t_trace_dyn_smem[];
+  RrLists* R = reinterpret_cast<RrLists*>(b2t_trace_dyn_smem);
+#endif
   const uint32_t cid = blockIdx.x / kCluster;
   Team T{blockIdx.x % kCluster, 0u};
   if (cid < n_team) {
     if (threadIdx.x == 0) L = descs[cid];
     __syncthreads();
-    trace_label<true>(A, L, P, prm, d_team[cid], Lc, T, cid);
+    trace_label<true>(A, L, P, prm, d_team[cid], Lc, T, cid, R);
     return;
   }
   T.rank = 0;
@@ -1248,7 +1574,7 @@ __global__ void __launch_bounds__(kThreads, B2T_TRACE_MINB) trace_kernel(Arena A
     if (job >= (uint32_t)prm.n_desc) return;
     if (threadIdx.x == 0) L = descs[job];
     __syncthreads();
-    trace_label<false>(A, L, P, prm, S, Lc, T, job);
+    trace_label<false>(A, L, P, prm, S, Lc, T, job, R);
   }
 }
 
@@ -1334,7 +1660,13 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
   int dev = 0, sms = 0, per_sm = 0;
   B2T_CUDA_TRY(cudaGetDevice(&dev));
   B2T_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  B2T_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel, kThreads, 0));
+  const size_t dyn_smem = B2T_RR_SOLO ? sizeof(RrLists) : 0;
+  static bool smem_set = false;
+  if (!smem_set && dyn_smem) {
+    B2T_CUDA_TRY(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    smem_set = true;
+  }
+  B2T_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel, kThreads, dyn_smem));
   if (per_sm < 1) per_sm = 1;
   if (b2t_trace_limit() > 0 && per_sm > b2t_trace_limit()) per_sm = b2t_trace_limit();
   int solo = sms * per_sm;
@@ -1343,7 +1675,7 @@ B2T_EXPORT int b2t_trace_batch(const uint32_t* d_cc, const float* d_dbf, float* 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * kCluster));
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = dyn_smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
