@@ -68,10 +68,13 @@ def _compile(extra, out, verbose=False, force=False):
 VARIANTS = {
   "prof": ["-DB2T_TRACE_PROF"],       # per-phase cycle counters in the path loop (scripts/trace_prof.py)
   "rr_global": ["-DB2T_RR_SOLO=0"],   # solo CTAs keep railroad's near lists in global memory (the form before railroad_solo)
-  "minb2": ["-DB2T_TRACE_MINB=2"],    # 64 registers per thread in the path loop instead of 42 (two resident CTAs per SM)
+  "minb3": ["-DB2T_TRACE_MINB=3"],    # 42 registers per thread in the path loop (three resident CTAs per SM; the default until call 25)
+  "minb2_cap1k": ["-DB2T_RR_SOLO_CAP=1024"],                         # smaller shared-memory lists: more L1 for the spills
+  "t256_minb3_cap1k": ["-DB2T_TRACE_THREADS=256", "-DB2T_TRACE_MINB=3", "-DB2T_RR_SOLO_CAP=1024"],
+  "batch2": ["-DB2T_RR_BATCH=2"],
   "minb1": ["-DB2T_TRACE_MINB=1"],    # 128 registers, one resident CTA per SM
-  "batch2": ["-DB2T_RR_BATCH=2"],     # railroad aims at 64..256 voxels per round instead of 32..128
-  "minb2_batch2": ["-DB2T_TRACE_MINB=2", "-DB2T_RR_BATCH=2"],
+  "t256_minb3": ["-DB2T_TRACE_THREADS=256", "-DB2T_TRACE_MINB=3"],   # 85 registers
+  "t256_minb2": ["-DB2T_TRACE_THREADS=256", "-DB2T_TRACE_MINB=2"],   # 128 registers
 }
 
 

@@ -58,7 +58,10 @@ __device__ unsigned long long g_prof[64][16];
 
 constexpr uint32_t kInfBits = 0x7f800000u;
 constexpr unsigned long long kValid = ~0ull;
-constexpr int kThreads = 512;   // 16 warps: a whole narrow batch expands in one pass
+#ifndef B2T_TRACE_THREADS
+#define B2T_TRACE_THREADS 512   // 16 warps: a whole narrow batch expands in one pass
+#endif
+constexpr int kThreads = B2T_TRACE_THREADS;
 #ifndef B2T_HEAP_PER_VOXEL
 #define B2T_HEAP_PER_VOXEL 4         // (the CPU harness builds with smaller numbers to exercise the spill path)
 #define B2T_HEAP_SLACK 4096
@@ -66,7 +69,10 @@ constexpr int kThreads = 512;   // 16 warps: a whole narrow batch expands in one
 constexpr int kHeapPerVoxel = B2T_HEAP_PER_VOXEL;   // strict mode: static heap nodes per foreground voxel of a label ...
 constexpr int kHeapSlack = B2T_HEAP_SLACK;          // ... plus this many; a heap that outgrows it moves to the spill arena
 #ifndef B2T_TRACE_MINB
-#define B2T_TRACE_MINB 3        // resident CTAs per SM (42 registers per thread)
+#define B2T_TRACE_MINB 2        // resident CTAs per SM: 64 registers per thread.  Measured on synthetic-512 (profiles/
+                                // r02_trace_occupancy_ab.jsonl): 3 CTAs (42 registers, spills in the 9-neighbour tasks) 47 ms,
+                                // 2 CTAs 27 ms, 1 CTA (128 registers, no spills) 44 ms -- the loop is latency-bound per label
+                                // and throughput-bound over labels, so resident labels and spill-free code both count
 #endif
 constexpr int kWarps = kThreads / 32;
 constexpr int kScratchPerVoxel = 22;   // u32 of queue scratch per foreground voxel of a label (see trace_label); even
@@ -1545,8 +1551,20 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
 
 // Grid: n_team clusters, each a team for job c (the caller sorts the jobs by size, largest first), then clusters whose
 // CTAs work alone and pull the remaining jobs from the work counter.  d_team: one Shared slot per team in global memory.
-__global__ void __launch_bounds__(kThreads, B2T_TRACE_MINB) trace_kernel(Arena A, const LabelDesc* __restrict__ descs, Pools P,
-                                                                         Params prm, uint32_t n_team, Shared* d_team) {
+// The argument structs are __grid_constant__: device functions below take them by reference, and a reference to an ordinary
+// by-value kernel parameter makes the compiler copy all of them to local memory at kernel entry (25 64-bit stores) and
+// read every field back from there (the pointers of cc / pdrf / dist were re-loaded before each of the nine neighbour
+// loads of an expansion task).  A grid constant may have its address taken: the fields stay in the constant bank.
+#ifdef B2T_HOST_EMU
+#define B2T_GRID_CONSTANT
+#else
+#define B2T_GRID_CONSTANT __grid_constant__
+#endif
+__global__ void __launch_bounds__(kThreads, B2T_TRACE_MINB) trace_kernel(const B2T_GRID_CONSTANT Arena A,
+                                                                         const LabelDesc* __restrict__ descs,
+                                                                         const B2T_GRID_CONSTANT Pools P,
+                                                                         const B2T_GRID_CONSTANT Params prm, uint32_t n_team,
+                                                                         Shared* d_team) {
   __shared__ Shared S;
   __shared__ Local Lc;
   __shared__ LabelDesc L;

@@ -217,77 +217,95 @@ def _default_stats(d_cc, d_dbf, shape, n_cc):
   return count.cpu().numpy(), bbox.cpu().numpy().reshape(-1, 6)
 
 
+# The six faces of a [z, y, x] crop in the order the reference paints them (paint_walls, intake.py:666-677):
+# z faces, then y faces, then x faces.
+_WALLS = tuple((axis, end) for axis in (0, 1, 2) for end in (0, -1))
+
+
+def _wall(img, axis, end):
+  sl = [slice(None)] * 3
+  sl[axis] = end
+  return tuple(sl)
+
+
+def _sealed_pit_image(crop, label, fill_fn):
+  """Mask of `label` in its bounding-box crop with every face closed by a 2-D fill, so that a pit which touches the
+  box's faces still encloses its interior for the 3-D fill that follows."""
+  img = (crop == label)
+  for axis, end in _WALLS:
+    sl = _wall(img, axis, end)
+    img[sl] = _fill_voids_2d(img[sl], fill_fn)
+  return img
+
+
+def _deepest_voxel(img, dbf_crop, origin):
+  """Voxel of the mask with the largest DBF, first one in Fortran raster order (intake.py:595-598); volume coordinates."""
+  ez, ey, ex = img.shape
+  k = int(torch.argmax((img.to(torch.float32) * dbf_crop).reshape(-1)).item())
+  kz, rem = divmod(k, ex * ey)
+  ky, kx = divmod(rem, ex)
+  return kx + origin[0], ky + origin[1], kz + origin[2]
+
+
+class _PitLedger:
+  """Which labels a pass left alone and which it merged (the two sets of intake.py:646-704).  A label that has taken
+  part in a merge can no longer count as left alone, whichever side of the merge it was on."""
+  def __init__(self):
+    self.settled, self.merged = set(), set()
+
+  def record(self, pit, fruit):
+    """True when `pit` is absorbed by `fruit`."""
+    if pit == fruit and pit not in self.merged:
+      self.settled.add(pit)
+      return False
+    self.settled -= {pit, fruit}
+    self.merged |= {pit, fruit}
+    return True
+
+
 def engage_avocado_protection_single_pass(d_cc, d_dbf, shape, n_cc, candidates, stats_fn, fill_fn):
-  """intake.py:646-704 on the device-resident volumes.  candidates: labels in the reference's iteration order."""
-  candidates = [label for label in candidates if label != 0]
-  unchanged, changed = set(), set()
-  if len(candidates) == 0:
-    return unchanged, changed
+  """One pass of the avocado protection (intake.py:646-704) on the device-resident volumes; `candidates` come in the
+  reference's iteration order.  Returns (labels left alone, labels that took part in a merge)."""
+  book = _PitLedger()
+  todo = [c for c in candidates if c != 0]
+  if not todo:
+    return book.settled, book.merged
   sx, sy, sz = shape
   d_cc3 = d_cc.view(sz, sy, sx)
   d_dbf3 = d_dbf.view(sz, sy, sx)
-  h_count, h_bbox = stats_fn(d_cc, d_dbf, shape, n_cc)        # boxes as they are when the pass starts (intake.py:679)
-  for label in candidates:
-    x0, y0, z0, x1, y1, z1 = (int(v) for v in h_bbox[label])
-    ex, ey, ez = x1 - x0 + 1, y1 - y0 + 1, z1 - z0 + 1
-    crop = d_cc3[z0:z1 + 1, y0:y1 + 1, x0:x1 + 1]
-    binimg = (crop == label)                                   # image of the pit, [z, y, x]
-    # paint_walls: 2-D fills of the six faces, in the reference's order (z, y, x faces)
-    binimg[0] = _fill_voids_2d(binimg[0], fill_fn)
-    binimg[-1] = _fill_voids_2d(binimg[-1], fill_fn)
-    binimg[:, 0, :] = _fill_voids_2d(binimg[:, 0, :], fill_fn)
-    binimg[:, -1, :] = _fill_voids_2d(binimg[:, -1, :], fill_fn)
-    binimg[:, :, 0] = _fill_voids_2d(binimg[:, :, 0], fill_fn)
-    binimg[:, :, -1] = _fill_voids_2d(binimg[:, :, -1], fill_fn)
-    prod = binimg.to(torch.float32) * d_dbf3[z0:z1 + 1, y0:y1 + 1, x0:x1 + 1]
-    idx = int(torch.argmax(prod.reshape(-1)).item())           # first maximum in Fortran raster order (intake.py:595-598)
-    cz, r = divmod(idx, ex * ey)
-    cy, cx = divmod(r, ex)
-    cx, cy, cz = cx + x0, cy + y0, cz + z0
+  _, h_bbox = stats_fn(d_cc, d_dbf, shape, n_cc)              # boxes as they are when the pass starts (intake.py:679)
+  for pit_label in todo:
+    x0, y0, z0, x1, y1, z1 = (int(v) for v in h_bbox[pit_label])
+    box = (slice(z0, z1 + 1), slice(y0, y1 + 1), slice(x0, x1 + 1))
+    crop = d_cc3[box]
+    img = _sealed_pit_image(crop, pit_label, fill_fn)
+    cx, cy, cz = _deepest_voxel(img, d_dbf3[box], (x0, y0, z0))
     pit, fruit = find_avocado_fruit(d_cc3[cz, cy, :].cpu().numpy(), d_cc3[cz, :, cx].cpu().numpy(),
                                     d_cc3[:, cy, cx].cpu().numpy(), cx, cy, cz)
-    if pit == fruit and pit not in changed:
-      unchanged.add(pit)
-    else:
-      unchanged.discard(pit)
-      unchanged.discard(fruit)
-      changed.add(pit)
-      changed.add(fruit)
-      binimg |= (crop == fruit)
-    mask = binimg.to(torch.uint8).contiguous().view(-1)
-    fill_fn(mask, (ex, ey, ez))
-    crop[mask.view(ez, ey, ex) != 0] = fruit                   # writes through to d_cc
-  return unchanged, changed
+    if book.record(pit, fruit):
+      img |= (crop == fruit)
+    flat = img.to(torch.uint8).contiguous().view(-1)
+    fill_fn(flat, (x1 - x0 + 1, y1 - y0 + 1, z1 - z0 + 1))
+    crop[flat.view(img.shape) != 0] = fruit                    # writes through to d_cc
+  return book.settled, book.merged
 
 
-def engage_avocado_protection(d_cc, d_dbf, shape, n_cc, soma_detection_threshold, edtfn, stats_fn=None, fill_fn=None):
-  """engage_avocado_protection (kimimaro/intake.py:600-644): a nucleus segmented apart from its cell -- the pit of an
-  avocado -- takes the label of the fruit around it; up to 20 passes for nested cases, the EDT redone after every pass
-  that changed something.  d_cc is edited in place.  Instead of renumbering (intake.py:636, not visible in the result)
-  the surviving labels keep their numbers; returns (d_dbf, last) where last[L] is the pre-protection component that
-  get_mapping(orig_cc_labels, cc_labels) (pyx:490-525: the last run start of L in raster order decides) would name for
-  the surviving component L, -1 for labels that are gone."""
-  stats_fn = stats_fn or _default_stats
-  fill_fn = fill_fn or _fill_voids
-  d_orig_cc = d_cc.clone()
-  unchanged = set()
-  t = soma_detection_threshold / 2.5
-  for _ in range(20):
-    hot = d_dbf > t
-    vals = torch.unique(d_cc[hot]).cpu().tolist()              # sorted, like fastremap.unique
-    # set(fastremap.unique(cc_labels * (all_dbf > t))): the product is 0 wherever the test fails or on background
-    has_zero = bool(((d_cc == 0) | ~hot).any().item())
-    candidates = set()
-    for v in ([0] if has_zero else []) + [int(v) for v in vals if v != 0]:
-      candidates.add(v)
-    candidates -= unchanged
-    candidates.discard(0)
-    unchanged_this_cycle, changes = engage_avocado_protection_single_pass(
-      d_cc, d_dbf, shape, n_cc, candidates, stats_fn, fill_fn)
-    unchanged |= unchanged_this_cycle
-    if len(changes) == 0:
-      break
-    d_dbf = edtfn(d_cc)
+def _hot_labels(d_cc, hot):
+  """set(fastremap.unique(cc_labels * (all_dbf > t))) (intake.py:617) without forming the product.  The reference then
+  ITERATES this Python set, and a set's order depends on how it was filled (table growth, tombstones), so the set is
+  built by the same sequence of insertions: the sorted unique values of the product, 0 included when the product has a
+  zero anywhere.  The caller removes entries in place, like the reference's `-=` and discard."""
+  seen = torch.unique(d_cc[hot]).cpu().tolist()
+  zero_somewhere = bool(((d_cc == 0) | ~hot).any().item())
+  out = set()
+  for v in ([0] if zero_somewhere else []) + [int(v) for v in seen if v != 0]:
+    out.add(v)
+  return out
+
+
+def _last_run_owner(d_cc, d_before, n_cc):
+  """get_mapping(orig_cc_labels, cc_labels) (pyx:490-525) for the surviving labels: the START of the last run of a label
+  in raster order names its pre-protection component; -1 for labels that are gone."""
   starts = torch.nonzero(d_cc[1:] != d_cc[:-1]).view(-1) + 1
   starts = torch.cat([torch.zeros(1, dtype=starts.dtype, device=starts.device), starts])
   last = torch.full((n_cc + 1,), -1, dtype=torch.int64, device=d_cc.device)
@@ -295,8 +313,33 @@ def engage_avocado_protection(d_cc, d_dbf, shape, n_cc, soma_detection_threshold
   h_last = last.cpu().numpy()
   h_src = np.full(n_cc + 1, -1, dtype=np.int64)
   ok = h_last >= 0
-  h_src[ok] = d_orig_cc[torch.as_tensor(h_last[ok], device=d_cc.device)].cpu().numpy().astype(np.int64)
-  return d_dbf, h_src
+  h_src[ok] = d_before[torch.as_tensor(h_last[ok], device=d_cc.device)].cpu().numpy().astype(np.int64)
+  return h_src
+
+
+def engage_avocado_protection(d_cc, d_dbf, shape, n_cc, soma_detection_threshold, edtfn, stats_fn=None, fill_fn=None,
+                              max_passes=20):
+  """engage_avocado_protection (kimimaro/intake.py:600-644): a nucleus segmented apart from its cell -- the pit of an
+  avocado -- takes the label of the fruit around it; up to 20 passes for nested cases, the EDT redone after every pass
+  that changed something.  d_cc is edited in place.  Instead of renumbering (intake.py:636, not visible in the result)
+  the surviving labels keep their numbers; returns (d_dbf, last) where last[L] is the pre-protection component that
+  get_mapping would name for the surviving component L, -1 for labels that are gone."""
+  stats_fn = stats_fn or _default_stats
+  fill_fn = fill_fn or _fill_voids
+  d_before = d_cc.clone()
+  left_alone = set()
+  cutoff = soma_detection_threshold / 2.5
+  for _ in range(max_passes):
+    # labels a previous pass left alone are not looked at again
+    todo = _hot_labels(d_cc, d_dbf > cutoff)
+    todo -= left_alone
+    todo.discard(0)
+    settled, merged = engage_avocado_protection_single_pass(d_cc, d_dbf, shape, n_cc, todo, stats_fn, fill_fn)
+    left_alone |= settled
+    if not merged:
+      break
+    d_dbf = edtfn(d_cc)
+  return d_dbf, _last_run_owner(d_cc, d_before, n_cc)
 
 
 def _private_arena(d_cc3, d_dbf3, segid, bbox, anisotropy, params, root, targets_before, targets_after,
@@ -389,10 +432,12 @@ def _skeletonize(
       shape = shape + (1,)
     d_labels = device_labels
     size = int(np.prod(shape))
+    key_dtype = _NP_OF_TORCH.get(device_labels.dtype)         # ids come back in the dtype the caller's tensor has
   else:
     all_labels = format_labels(all_labels, in_place=in_place)
     shape = all_labels.shape
     size = all_labels.size
+    key_dtype = all_labels.dtype
     if size <= dust_threshold:
       return {}
     flat = all_labels.reshape(-1, order="F")
@@ -452,8 +497,8 @@ def _skeletonize(
     ok = avocado_src >= 0
     h_orig = h_orig.copy()
     h_orig[ok] = h_orig0[avocado_src[ok]]
-  if h_orig.dtype.kind == "i" and all_labels is not None and device_labels is None and all_labels.dtype.kind == "u":
-    h_orig = h_orig.view(all_labels.dtype)
+  if key_dtype is not None and h_orig.dtype != key_dtype and h_orig.dtype.itemsize == np.dtype(key_dtype).itemsize:
+    h_orig = h_orig.view(key_dtype)                            # signed <-> unsigned bit casts of the upload undone
   t0 = lap("stats", t0)
 
   cc_segids = [int(s) for s in np.flatnonzero(h_count > dust_threshold) if s != 0]

@@ -47,6 +47,10 @@ if st:
   rec["slowest_labels"] = [{"job": int(i), "us": int(s0["stats"][i, 3]), "npaths": int(s0["npaths"][i]),
                            "rounds": int(s0["stats"][i, 1]), "relax": int(s0["stats"][i, 0]),
                            "invalidated": int(s0["stats"][i, 2])} for i in top]
+  us = np.sort(s0["stats"][:, 3].astype(np.int64))[::-1]
+  rec["label_us"] = {"n": int(us.size), "sum": int(us.sum()), "max": int(us[0]) if us.size else 0,
+                     "top16_sum": int(us[:16].sum()), "top148_sum": int(us[:148].sum()),
+                     "q": [int(v) for v in np.quantile(us, [0.5, 0.9, 0.99])] if us.size else []}
 gold = golden_digest("synth512_oracle_digest_window1.json") if n == 512 else None
 if gold:
   dg = skeleton_digests(sk)
