@@ -49,6 +49,8 @@ DEFAULT_TEASAR_PARAMS = {       # kimimaro/intake.py:47-56
 
 _VIEW = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}
 _TVIEW = {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}
+_NP_OF_TORCH = {torch.uint8: np.uint8, torch.int8: np.int8, torch.int16: np.int16, torch.int32: np.int32,
+                torch.int64: np.int64, torch.uint16: np.uint16, torch.uint32: np.uint32, torch.uint64: np.uint64}
 
 
 def format_labels(labels, in_place):
@@ -397,7 +399,7 @@ def _skeletonize(
   fix_borders=True, parallel=1, parallel_chunk_size=100,
   extra_targets_before=[], extra_targets_after=[],
   fill_holes=False, fix_avocados=False,
-  voxel_graph=None, timings=None, label_subset=None, device_labels=None, edt_events=None,
+  voxel_graph=None, timings=None, label_subset=None, device_labels=None, edt_events=None, label_dtype=None,
 ):
   """
   Skeletonize all non-zero labels in a 2D or 3D image (kimimaro/intake.py:58-143).
@@ -432,7 +434,9 @@ def _skeletonize(
       shape = shape + (1,)
     d_labels = device_labels
     size = int(np.prod(shape))
-    key_dtype = _NP_OF_TORCH.get(device_labels.dtype)         # ids come back in the dtype the caller's tensor has
+    # ids come back in the dtype the caller's tensor has, or in label_dtype (the host array's dtype when the multi-GPU
+    # launcher uploaded it: torch has no kernels for the unsigned types, so the device tensor carries signed bit patterns)
+    key_dtype = np.dtype(label_dtype) if label_dtype is not None else _NP_OF_TORCH.get(device_labels.dtype)
   else:
     all_labels = format_labels(all_labels, in_place=in_place)
     shape = all_labels.shape

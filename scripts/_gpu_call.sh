@@ -1,16 +1,8 @@
 set -x
 mkdir -p gpurun_out
-: > gpurun_out/phase_ab.jsonl
-for rep in 1 2; do
-  for v in t256_minb2 t256_minb3 minb2 minb1 t384_minb1; do
-    L=$PWD/kimimaro_b200/_variants/$v.so
-    B2T_LIB=$L B2T_X=$v timeout 300 python scripts/phase_times.py 512 3 >> gpurun_out/phase_ab.jsonl 2>> gpurun_out/phase_ab.err
-  done
+: > gpurun_out/ccl_ab.jsonl
+for v in default ccl_old; do
+  if [ $v = default ]; then L=$PWD/kimimaro_b200/libb2t.so; else L=$PWD/kimimaro_b200/_variants/$v.so; fi
+  B2T_LIB=$L B2T_X=$v timeout 300 python scripts/ccl_time.py 512 5 >> gpurun_out/ccl_ab.jsonl 2>> gpurun_out/ccl_ab.err
 done
-
-python - <<'PY'
-import json
-for l in open("gpurun_out/phase_ab.jsonl"):
-  r = json.loads(l)
-  print(r["env"].get("B2T_X"), r["pass_ms"], r["phases_ms"]["paths"], r.get("identical_to_oracle_same_mode"), r.get("label_us"), [ (s["job"], s["us"]) for s in r.get("slowest_labels", [])[:3]])
-PY
+cat gpurun_out/ccl_ab.jsonl; tail -3 gpurun_out/ccl_ab.err
