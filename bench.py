@@ -233,17 +233,14 @@ def run_b200(args):
   subset = kdist.make_label_subset(rank, world) if world > 1 else None
 
   def step_resident(edt_events=None):
-    sk = skeletonize(shape, device_labels=d_labels, anisotropy=AN, progress=False, label_subset=subset,
-                     edt_events=edt_events)
     if world > 1:
-      sk = kdist.gather_skeletons(sk, dev)
-    return sk
+      return kdist.skeletonize_sharded(shape, device_labels=d_labels, anisotropy=AN, progress=False, edt_events=edt_events)
+    return skeletonize(shape, device_labels=d_labels, anisotropy=AN, progress=False, edt_events=edt_events)
 
   def step_e2e():
-    sk = skeletonize(host_view, anisotropy=AN, progress=False, in_place=True, label_subset=subset)
-    if world > 1:
-      sk = kdist.gather_skeletons(sk, dev)
-    return sk
+    if world > 1:      # every rank copies 1/world of the pinned volume, NCCL all-gather, sharded trace, one gather to rank 0
+      return kdist.skeletonize_sharded(host_view, anisotropy=AN, progress=False, in_place=True)
+    return skeletonize(host_view, anisotropy=AN, progress=False, in_place=True)
 
   def sync():
     torch.cuda.synchronize()
@@ -305,6 +302,10 @@ def run_b200(args):
   tm = {}
   skeletonize(shape, device_labels=d_labels, anisotropy=AN, progress=False, label_subset=subset, timings=tm)
   phases = {k: round(1e3 * v, 3) for k, v in tm.items() if isinstance(v, float)}
+  phases_per_rank = None
+  if world > 1:              # what every rank spends where (its share of the labels): the limiter of the strong scaling
+    phases_per_rank = [None] * world
+    dist.all_gather_object(phases_per_rank, phases)
 
   # parity with the REFERENCE's invalidation order, measured on this very run (outside the timed region): the timed
   # steps' skeletons against the digest of the oracle's literal heap order (== the reference's compiled extension), then
@@ -379,7 +380,7 @@ def run_b200(args):
       "e2e": {"value": V / (mse / 1e3), "unit": "voxels/s", "h2d_bytes_per_step": int(flat.nbytes),
               "d2h_bytes_per_step": d2h, "ms_per_step": mse},
       "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
-      "phases_ms": phases,
+      "phases_ms": phases, "phases_ms_per_rank": phases_per_rank,
       "e2e_phases_ms": e2e_phases, "per_step_ms": step_log,
     }
     print(json.dumps(line), flush=True)

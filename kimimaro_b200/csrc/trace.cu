@@ -675,9 +675,6 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
 #ifndef B2T_RR_SOLO
 #define B2T_RR_SOLO 1                  // solo CTAs use railroad_solo (0: the global-memory form everywhere)
 #endif
-#ifndef B2T_RR_E
-#define B2T_RR_E 2                     // voxels a warp expands together (their global round trips overlap)
-#endif
 constexpr uint32_t kSoloCap = B2T_RR_SOLO_CAP;
 struct RrLists {
   unsigned long long mid[2][kSoloCap];
@@ -687,9 +684,8 @@ struct RrLists {
 __device__ uint32_t railroad_solo(const Arena& A, const LabelDesc& L, uint32_t target, RrLists& R, unsigned long long* farA,
                                   unsigned long long* farB, uint32_t* touched, uint32_t* out, uint32_t out_cap, Shared& S,
                                   Local& Lc, Team& T) {
-  constexpr int E = B2T_RR_E;
   const int lane = threadIdx.x & 31;
-  const uint32_t tid = threadIdx.x, nth = kThreads, tw = threadIdx.x >> 5;
+  const uint32_t tid = threadIdx.x, nth = kThreads;
   const uint32_t seg = L.segid;
   const uint32_t cap = B2T_RR_CAP_SHIFT ? max(64u, (2u * L.n_fg) >> B2T_RR_CAP_SHIFT) : 2u * L.n_fg;   // far lists (global)
 #ifndef B2T_RR_SCAP_SHIFT
@@ -701,9 +697,6 @@ __device__ uint32_t railroad_solo(const Arena& A, const LabelDesc& L, uint32_t t
     __syncthreads();
     return out_cap > 0 ? 1 : 0;
   }
-  int dx = 0, dy = 0, dz = 0;
-  if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; }
-  const int64_t off = (int64_t)dx + (int64_t)dy * A.d.sx + (int64_t)dz * A.d.sxy;
   const uint32_t ltmask = (1u << lane) - 1u;
 
   unsigned long long* far = farA;
@@ -1048,11 +1041,8 @@ __device__ __noinline__ uint32_t invalidate_window(const Arena& A, const LabelDe
                                                    float scale, float konst, float delta, uint32_t* act, uint32_t* fv,
                                                    uint32_t* fs, uint32_t* act2, Shared& S, Local& Lc, Team& T) {
   const int lane = threadIdx.x & 31;
-  const uint32_t tid = t_tid<TEAM>(T), nth = t_threads<TEAM>(), tw = t_warp<TEAM>(T), ntw = t_warps<TEAM>();
+  const uint32_t tid = t_tid<TEAM>(T), nth = t_threads<TEAM>();
   const uint32_t seg = L.segid;
-  int dx = 0, dy = 0, dz = 0;
-  if (lane < 26) { dx = kDX[lane]; dy = kDY[lane]; dz = kDZ[lane]; }
-  const int64_t off = (int64_t)dx + (int64_t)dy * A.d.sx + (int64_t)dz * A.d.sxy;
   const uint32_t ltmask = (1u << lane) - 1u;
   if (tid == 0) { S.n_next = 0; S.n_keep = 0; }
   team_sync<TEAM>();

@@ -106,6 +106,49 @@ def gather_skeletons(skels, device, group=None, dst=0):
   return out
 
 
+def gather_raw(bundle, device, group=None, dst=0):
+  """One gather of the ranks' PATH BUFFERS (engine output before skeleton assembly: voxels i32, radii f32, segment
+  lengths, original label per segment) to `dst`; returns the concatenated bundle there, None elsewhere.  The skeletons
+  of all ranks are then assembled in one device-side pass on dst (intake.skeletons_from_raw), which also consolidates
+  labels whose connected components were traced on different ranks -- no per-skeleton Python work on either side."""
+  rank, world = dist.get_rank(group), dist.get_world_size(group)
+  vox, rad, lens, gids = bundle
+  id_dtype = gids.dtype
+  meta = np.concatenate([np.asarray(lens, dtype=np.int64), np.asarray(gids).astype(id_dtype).view(
+    np.int64 if id_dtype.itemsize == 8 else id_dtype).astype(np.int64)])
+  sizes = torch.tensor([int(vox.numel()), int(lens.size)], dtype=torch.int64, device=device)
+  all_sizes = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
+  dist.all_gather(all_sizes, sizes, group=group)
+  all_sizes = [s.cpu().numpy() for s in all_sizes]
+  d_meta = torch.from_numpy(meta).to(device)
+  mine = [vox.to(device), rad.to(device), d_meta]
+  if rank != dst:
+    ops = [dist.P2POp(dist.isend, t.contiguous(), dst, group=group) for t in mine if t.numel() > 0]
+    if ops:
+      for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return None
+  parts = {dst: mine}
+  ops = []
+  for r in range(world):
+    if r == dst:
+      continue
+    nv, ns = (int(v) for v in all_sizes[r])
+    b = [torch.empty(nv, dtype=torch.int32, device=device), torch.empty(nv, dtype=torch.float32, device=device),
+         torch.empty(2 * ns, dtype=torch.int64, device=device)]
+    parts[r] = b
+    ops += [dist.P2POp(dist.irecv, t, r, group=group) for t in b if t.numel() > 0]
+  if ops:
+    for req in dist.batch_isend_irecv(ops):
+      req.wait()
+  order = sorted(parts)
+  metas = [parts[r][2].cpu().numpy() for r in order]
+  lens_all = np.concatenate([m[:m.size // 2] for m in metas])
+  gid_all = np.concatenate([m[m.size // 2:] for m in metas])
+  gid_all = gid_all.view(id_dtype) if id_dtype.itemsize == 8 else gid_all.astype(id_dtype)
+  return torch.cat([parts[r][0] for r in order]), torch.cat([parts[r][1] for r in order]), lens_all, gid_all
+
+
 def upload_sharded(all_labels, device, group=None):
   """The label volume on every rank's device with ONE pass over the host link in total: rank r copies the r-th of
   world_size contiguous pieces of the Fortran-ordered volume (a z-slab) from host memory, the pieces are exchanged
@@ -137,7 +180,7 @@ def upload_sharded(all_labels, device, group=None):
   return whole[:V], labels.shape, labels.dtype
 
 
-def skeletonize_sharded(all_labels, group=None, device_labels=None, **kwargs):
+def skeletonize_sharded(all_labels, group=None, device_labels=None, device=None, **kwargs):
   """skeletonize() with the connected components sharded over the ranks of `group`; result on rank 0, None elsewhere.
   all_labels: the same host array on every rank (each rank uploads 1/world_size of it, see upload_sharded), or, with
   device_labels, the volume's shape like in skeletonize()."""
@@ -145,7 +188,8 @@ def skeletonize_sharded(all_labels, group=None, device_labels=None, **kwargs):
   from .intake import skeletonize
   rank = dist.get_rank(group)
   world = dist.get_world_size(group)
-  device = torch.device("cuda", torch.cuda.current_device())
+  if device is None:
+    device = torch.device("cuda", torch.cuda.current_device())
   was_enabled = gc.isenabled()
   gc.disable()          # the gather's host work belongs to the same collector-free window as the call itself (intake.skeletonize)
   try:
@@ -153,8 +197,19 @@ def skeletonize_sharded(all_labels, group=None, device_labels=None, **kwargs):
       device_labels, shape, key_dtype = upload_sharded(all_labels, device, group)
       kwargs["label_dtype"] = key_dtype
       all_labels = shape
-    skels = skeletonize(all_labels, label_subset=make_label_subset(rank, world), device_labels=device_labels, **kwargs)
-    return gather_skeletons(skels, device, group=group)
+    shape = tuple(int(v) for v in (all_labels if device_labels is not None else np.shape(all_labels)))
+    shape = shape + (1,) * (3 - len(shape))
+    anisotropy = kwargs.get("anisotropy", (1, 1, 1))
+    bundle = skeletonize(all_labels, label_subset=make_label_subset(rank, world), device_labels=device_labels,
+                         raw_paths=True, **kwargs)
+    if isinstance(bundle, dict):                               # nothing to trace on this rank (empty / all dust)
+      from .intake import join_raw
+      bundle = join_raw([], device, np.dtype(np.int64))
+    whole = gather_raw(bundle, device, group=group)
+    if whole is None:
+      return None
+    from .intake import skeletons_from_raw
+    return skeletons_from_raw(whole, shape, anisotropy)
   finally:
     if was_enabled:
       gc.enable()

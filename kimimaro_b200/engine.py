@@ -185,15 +185,53 @@ def edf_labels(d_cc, shape, anisotropy, sources, segids, n_fg, ws, node_weights=
 
 def field_argmax(d_cc, d_dist, shape, n):
   """per label (max finite distance, smallest index attaining it) -> (values f32[n+1], index i64[n+1])."""
+  return field_argmax_read(field_argmax_launch(d_cc, d_dist, shape, n))
+
+
+def field_argmax_launch(d_cc, d_dist, shape, n):
   sx, sy, sz = shape
   best = torch.empty(n + 1, dtype=torch.int64, device=d_cc.device)
   check(lib().b2t_field_argmax(_p(d_cc), _p(d_dist), c_i64(sx), c_i64(sy), c_i64(sz), c_u32(n), _p(best),
                                stream_ptr()), "b2t_field_argmax")
+  return best
+
+
+def field_argmax_read(best):
   b = best.cpu().numpy().view(np.uint64)
   vals = (b >> np.uint64(32)).astype(np.uint32).view(np.float32)
   idx = (np.uint64(0xFFFFFFFF) - (b & np.uint64(0xFFFFFFFF))).astype(np.int64)
   idx[b == 0] = -1
   return vals, idx
+
+
+class RootSweep:
+  """find_root (trace.py:128-129, 291-308) for the labels of the main arena, started BEFORE the border targets are
+  computed and collected after: the sweep is a latency-bound chain of per-label rounds that leaves most of the GPU idle,
+  compute_border_targets is a sequence of small launches and host reads -- on two streams they overlap (5.7 + 5.9 ms in
+  a row on synthetic-512).  Labels that get their root from a border target simply ignore the result."""
+  def __init__(self, d_cc, shape, anisotropy, first, segids, n_fg, n_rows):
+    V = shape[0] * shape[1] * shape[2]
+    self.ws = Workspace(V, int(np.asarray(n_fg).sum()), d_cc.device)
+    self.segids = np.asarray(segids, dtype=np.int64)
+    self.side = None
+    if d_cc.device.type == "cuda":
+      self.main = torch.cuda.current_stream()
+      self.side = torch.cuda.Stream()
+      self.side.wait_stream(self.main)
+      with torch.cuda.stream(self.side):
+        edf_labels(d_cc, shape, anisotropy, first, segids, n_fg, self.ws)
+        self.best = field_argmax_launch(d_cc, self.ws.dist, shape, n_rows)
+    else:
+      edf_labels(d_cc, shape, anisotropy, first, segids, n_fg, self.ws)
+      self.best = field_argmax_launch(d_cc, self.ws.dist, shape, n_rows)
+
+  def roots(self):
+    """linear index of the root of every label handed to the constructor (same order)"""
+    if self.side is not None:
+      self.main.wait_stream(self.side)         # the workspace goes back to the main stream (the DAF sweep reuses it)
+      self.side.synchronize()
+    _, idx = field_argmax_read(self.best)
+    return idx[self.segids]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -319,7 +357,7 @@ def compute_M_array(dbf_max):
     return np.array([np.float32(1 / (d ** 1.01)) for d in np.asarray(dbf_max, dtype=np.float32)], dtype=np.float32)
 
 
-def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=None, pool_scale=1):
+def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=None, pool_scale=1, ws=None):
   """
   Everything up to and including the (asynchronous) launch of the path-loop kernel; returns the state that
   trace_arena_finish() needs.  jobs: a Jobs table.  n_rows: rows of the (label x bucket) tables minus one (= max cc id in this arena).
@@ -340,7 +378,8 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
       tmark = now
 
   n_fg_total = int(jobs.n_fg.sum())
-  ws = Workspace(V, n_fg_total, dev)
+  if ws is None or ws.V != V or ws.n_fg < n_fg_total:
+    ws = Workspace(V, n_fg_total, dev)
 
   # ---- roots (trace.py:128-129, 291-308): one field sweep for every label that has no root yet ----
   need = np.flatnonzero(jobs.root < 0)
@@ -630,8 +669,12 @@ def assemble(d_vox, d_rad, seg_off, seg_ids, shape, anisotropy, offset=(0, 0, 0)
   used[ea] = True
   used[eb] = True
   newid = torch.cumsum(used, 0) - 1
-  urad = torch.empty(nu, dtype=torch.float32, device=dev)
-  urad[inverse] = d_rad[vi]                                  # every occurrence of a vertex carries the same DBF
+  # radius of a vertex = the DBF at its FIRST occurrence (consolidate keeps the first).  Within one arena every
+  # occurrence carries the same value; a vertex that a private arena (its own EDT after fill_voids) shares with another
+  # component of the same label does not, and a plain scatter would pick one at random.
+  first = torch.full((nu,), n, dtype=torch.int64, device=dev)
+  first.scatter_reduce_(0, inverse, vi, reduce="amin")
+  urad = d_rad[first]
   ulab = uniq // V
   ck = uniq - ulab * V
   ux = ck // (sy * sz)

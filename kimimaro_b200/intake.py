@@ -388,8 +388,16 @@ def _private_arena(d_cc3, d_dbf3, segid, bbox, anisotropy, params, root, targets
                      soma_mode=[soma_mode], soma_radius=[soma_radius], free_space=[free_space])
   cc1 = mask.to(torch.int32)
   vox, rad, seg_off, seg_ids, stats = engine.trace_arena(cc1, dbf, shape, anisotropy, jobs, params, 1, timings)
-  res = engine.assemble(vox, rad, seg_off, seg_ids, shape, anisotropy, offset=(x0, y0, z0))
-  return res.get(1), stats
+  # path voxels as linear indices of the whole volume (terminators stay -1), so that they join the other labels' paths
+  full = d_cc3.shape[2], d_cc3.shape[1], d_cc3.shape[0]
+  v = vox.to(torch.int64) & 0xFFFFFFFF
+  lz = v // (shape[0] * shape[1])
+  r = v - lz * (shape[0] * shape[1])
+  ly = r // shape[0]
+  lx = r - ly * shape[0]
+  g = (lx + x0) + full[0] * ((ly + y0) + full[1] * (lz + z0))
+  vox_g = torch.where(vox == -1, vox, g.to(torch.int32))
+  return (vox_g, rad, np.diff(seg_off)), stats
 
 
 def _skeletonize(
@@ -399,7 +407,7 @@ def _skeletonize(
   fix_borders=True, parallel=1, parallel_chunk_size=100,
   extra_targets_before=[], extra_targets_after=[],
   fill_holes=False, fix_avocados=False,
-  voxel_graph=None, timings=None, label_subset=None, device_labels=None, edt_events=None, label_dtype=None,
+  voxel_graph=None, timings=None, label_subset=None, device_labels=None, edt_events=None, label_dtype=None, raw_paths=False,
 ):
   """
   Skeletonize all non-zero labels in a 2D or 3D image (kimimaro/intake.py:58-143).
@@ -522,17 +530,22 @@ def _skeletonize(
   extra_before = points_to_labels(extra_targets_before)
   extra_after = points_to_labels(extra_targets_after)
 
-  border_targets = {}
-  if fix_borders:
-    border_targets = engine.compute_border_targets(d_cc, shape, anisotropy)
-  t0 = lap("border_targets", t0)
-
   # ---- per label arguments of trace() (intake.py:445-504), as one table ----
   segs = np.asarray(cc_segids, dtype=np.int64)
   if segs.size:
     ext = (h_bbox[segs, 3:6].astype(np.int64) - h_bbox[segs, 0:3].astype(np.int64) + 1)
     segs = segs[np.prod(ext, axis=1) > 1]                       # roi.volume() <= 1 is skipped (intake.py:455-456)
   is_private = h_dbfmax[segs] > params["soma_detection_threshold"]   # trace.py:108: takes the fill / re-EDT branch
+
+  border_targets = {}
+  early_roots = None
+  if fix_borders:
+    m0 = segs[~is_private]
+    if m0.size and os.environ.get("B2T_EARLY_ROOTS", "1") == "1":
+      # find_root for the main arena runs on a second stream while the border targets are computed (engine.RootSweep)
+      early_roots = engine.RootSweep(d_cc, shape, an, h_first[m0], m0, h_count[m0], n_cc)
+    border_targets = engine.compute_border_targets(d_cc, shape, anisotropy)
+  t0 = lap("border_targets", t0)
   lin = lambda p: int(p[0]) + sx * (int(p[1]) + sy * int(p[2]))
 
   def manual_targets(segid):
@@ -566,11 +579,16 @@ def _skeletonize(
         tb_map[i] = [lin(p) for p in tb]
       if ta:
         ta_map[i] = [lin(p) for p in ta]
+  ws = None
+  if early_roots is not None:
+    swept = early_roots.roots()
+    roots = np.where(roots < 0, swept, roots)
+    ws = early_roots.ws
+    t0 = lap("find_root", t0)
   jobs = engine.Jobs(main, h_count[main], h_first[main], roots, h_dbfmax[main], tb=tb_map, ta=ta_map,
                      bbox_x=h_bbox[main][:, [0, 3]])
 
-  results = {}            # original label -> (vertices, edges, radii), all its ordinary components merged
-  private_results = []    # (original label, arrays) of labels traced in a private arena
+  raw = []                # (path voxels i32 device, radii f32 device, segment lengths, original label per segment)
   stats_all = []
   # The path loop of the main arena is latency-bound (one CTA per label), the private arenas (soma branch)
   # are throughput kernels: run them side by side -- the main path kernel is launched asynchronously with
@@ -582,14 +600,12 @@ def _skeletonize(
   if len(jobs):
     if overlap:
       lib().b2t_set_launch_limits(0, 2)
-    handle = engine.trace_arena_start(d_cc, d_dbf, shape, an, jobs, params, n_cc, tm)
+    handle = engine.trace_arena_start(d_cc, d_dbf, shape, an, jobs, params, n_cc, tm, ws=ws)
     if not overlap:
       vox, rad, seg_off, seg_ids, stats = engine.trace_arena_finish(handle)
       handle = None
-      t0 = time.perf_counter()
-      results.update(engine.assemble(vox, rad, seg_off, seg_ids, shape, anisotropy, group_ids=h_orig[seg_ids]))
+      raw.append((vox, rad, np.diff(seg_off), h_orig[seg_ids]))
       stats_all.append(stats)
-      t0 = lap("assemble", t0)
   if private:
     d_cc3 = d_cc.view(sz, sy, sx)
     d_dbf3 = d_dbf.view(sz, sy, sx)
@@ -603,9 +619,8 @@ def _skeletonize(
         for segid, bb, root, tb, ta in private:
           t0 = time.perf_counter()
           ptm = {} if tm is not None else None
-          res, stats = _private_arena(d_cc3, d_dbf3, segid, bb, an, params, root, tb, ta, ptm)
-          if res is not None:
-            private_results.append((h_orig[segid].item(), res))
+          (pvox, prad, plens), stats = _private_arena(d_cc3, d_dbf3, segid, bb, an, params, root, tb, ta, ptm)
+          raw.append((pvox, prad, plens, np.full(plens.size, h_orig[segid], dtype=h_orig.dtype)))
           stats_all.append(stats)
           if tm is not None:
             tm["soma"] = tm.get("soma", 0.0) + time.perf_counter() - t0
@@ -617,30 +632,55 @@ def _skeletonize(
       main_stream.wait_stream(side)
   if handle is not None:
     vox, rad, seg_off, seg_ids, stats = engine.trace_arena_finish(handle)
-    results.update(engine.assemble(vox, rad, seg_off, seg_ids, shape, anisotropy, group_ids=h_orig[seg_ids]))
+    raw.insert(0, (vox, rad, np.diff(seg_off), h_orig[seg_ids]))
     stats_all.insert(0, stats)
-
-  # ---- Skeleton objects, merged per original id (intake.py:509-517, 587-593) ----
-  t0 = time.perf_counter()
-  transform = np.array([[an[0], 0, 0, 0], [0, an[1], 0, 0], [0, 0, an[2], 0]], dtype=np.float32)
-  by_orig = defaultdict(list)
-  for orig, (verts, edges, radii) in results.items():
-    if verts.shape[0] == 0 or edges.shape[0] == 0:
-      continue
-    by_orig[orig].append(Skeleton._from_arrays(verts, edges, radii, orig, transform, "physical"))
-  for orig, (verts, edges, radii) in private_results:
-    if verts.shape[0] == 0 or edges.shape[0] == 0:
-      continue
-    by_orig[orig].append(Skeleton._from_arrays(verts, edges, radii, orig, transform, "physical"))
-  out = {}
-  for orig, skels in by_orig.items():
-    out[orig] = skels[0] if len(skels) == 1 else Skeleton.simple_merge(skels).consolidate()
   if tm is not None:
-    tm["finalize"] = tm.get("finalize", 0.0) + time.perf_counter() - t0
-    tm["total"] = time.perf_counter() - t_all
     tm["n_cc"] = n_cc
     tm["n_traced"] = len(jobs) + len(private)
     tm["kernel_stats"] = stats_all
+  bundle = join_raw(raw, d_labels.device, h_orig.dtype)
+  if raw_paths:
+    return bundle
+  out = skeletons_from_raw(bundle, shape, anisotropy, tm)
+  if tm is not None:
+    tm["total"] = time.perf_counter() - t_all
+  return out
+
+
+def join_raw(raw, device, id_dtype):
+  """Concatenate per-arena path buffers: (voxels i32 [N] device with -1 terminators, radii f32 [N] device, segment
+  lengths int64 [S], original label of every segment [S])."""
+  if not raw:
+    return (torch.empty(0, dtype=torch.int32, device=device), torch.empty(0, dtype=torch.float32, device=device),
+            np.zeros(0, dtype=np.int64), np.zeros(0, dtype=id_dtype))
+  if len(raw) == 1:
+    return raw[0][0], raw[0][1], np.asarray(raw[0][2], dtype=np.int64), np.asarray(raw[0][3])
+  return (torch.cat([r[0] for r in raw]), torch.cat([r[1] for r in raw]),
+          np.concatenate([np.asarray(r[2], dtype=np.int64) for r in raw]), np.concatenate([np.asarray(r[3]) for r in raw]))
+
+
+def skeletons_from_raw(bundle, shape, anisotropy, tm=None):
+  """Path buffers -> {original label: Skeleton}: one device-side assembly for every label of every arena (the connected
+  components of one original label are consolidated together, which is what the reference's merge per id does,
+  intake.py:509-517, 587-593), then one Skeleton object per label."""
+  vox, rad, lens, gids = bundle
+  an = tuple(float(a) for a in anisotropy)
+  t0 = time.perf_counter()
+  seg_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+  results = engine.assemble(vox, rad, seg_off, np.arange(lens.size, dtype=np.int64), shape, an, group_ids=gids)
+  if tm is not None:
+    if vox.device.type == "cuda":
+      torch.cuda.synchronize()
+    tm["assemble"] = tm.get("assemble", 0.0) + time.perf_counter() - t0
+  t0 = time.perf_counter()
+  transform = np.array([[an[0], 0, 0, 0], [0, an[1], 0, 0], [0, 0, an[2], 0]], dtype=np.float32)
+  out = {}
+  for orig, (verts, edges, radii) in results.items():
+    if verts.shape[0] == 0 or edges.shape[0] == 0:
+      continue
+    out[orig] = Skeleton._from_arrays(verts, edges, radii, orig, transform, "physical")
+  if tm is not None:
+    tm["finalize"] = tm.get("finalize", 0.0) + time.perf_counter() - t0
   return out
 
 

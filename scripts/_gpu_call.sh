@@ -1,8 +1,14 @@
 set -x
 mkdir -p gpurun_out
-: > gpurun_out/ccl_ab.jsonl
-for v in default ccl_old; do
-  if [ $v = default ]; then L=$PWD/kimimaro_b200/libb2t.so; else L=$PWD/kimimaro_b200/_variants/$v.so; fi
-  B2T_LIB=$L B2T_X=$v timeout 300 python scripts/ccl_time.py 512 5 >> gpurun_out/ccl_ab.jsonl 2>> gpurun_out/ccl_ab.err
-done
-cat gpurun_out/ccl_ab.jsonl; tail -3 gpurun_out/ccl_ab.err
+nvidia-smi --query-gpu=name --format=csv,noheader
+timeout 600 python -m pytest tests/test_multi_gpu.py -x -q -m gpu > gpurun_out/gpu_tests_n2.log 2>&1; tail -3 gpurun_out/gpu_tests_n2.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 400 gpurun_out/bench_n2.err
+timeout 600 python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 300 gpurun_out/bench_n1.err
+python - <<'PY'
+import json
+for f in ("gpurun_out/bench_n1.json","gpurun_out/bench_n2.json"):
+  try:
+    r=json.loads(open(f).read().strip().splitlines()[-1])
+    print(f, r["n_gpus"], round(r["ms_per_step"],2), round(r["e2e"]["ms_per_step"],2), r["parity"]["tier_a_identical_to_oracle_in_same_mode"], r["phases_ms"]); print(r.get("phases_ms_per_rank")); print(r["per_step_ms"])
+  except Exception as e: print(f, "ERR", e)
+PY

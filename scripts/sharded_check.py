@@ -1,6 +1,6 @@
 """On-hardware multi-GPU parity (the analogue of the reference's test_parallel, automated_test.py:234-259):
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P scripts/sharded_check.py
-Every rank traces its LPT share of the connected components, rank 0 gathers the packed skeleton buffers over NCCL and
+Every rank traces its LPT share of the connected components, rank 0 gathers the path buffers over NCCL, assembles the skeletons and
 compares the merged result with what it computes alone on the same volume: identical ids, vertices, edges, radii."""
 import json
 import os
@@ -24,8 +24,9 @@ def main():
   dist.init_process_group("nccl", device_id=dev)
   lab = synthetic_tubes((256, 256, 128), 120, seed=31, anisotropy=(16, 16, 40))
   kw = dict(anisotropy=(16, 16, 40), progress=False, dust_threshold=300)
-  mine = kimimaro_b200.skeletonize(lab, label_subset=kd.make_label_subset(rank, world), **kw)
-  out = kd.gather_skeletons(mine, dev)
+  tm = {}
+  out = kd.skeletonize_sharded(lab, timings=tm, **kw)        # slab upload + all-gather, LPT share, one gather of path buffers
+  mine = range(tm.get("n_traced", 0))
   ok = True
   if rank == 0:
     alone = kimimaro_b200.skeletonize(lab, **kw)

@@ -199,12 +199,13 @@ def _sharded_worker(rank, world, port, lib_path, q):
   from tests.synth import synthetic_tubes
   dist.init_process_group("gloo", rank=rank, world_size=world)
   labels = synthetic_tubes((56, 48, 32), 6, seed=12)
-  # skeletonize_sharded (kimimaro_b200/distributed.py) with the gather on CPU tensors
-  skels = product.skeletonize(labels, anisotropy=(16, 16, 40), dust_threshold=100, progress=False,
-                              label_subset=kd.make_label_subset(rank, world))
-  out = kd.gather_skeletons(skels, torch.device("cpu"))
+  # skeletonize_sharded (kimimaro_b200/distributed.py) as it runs on GPUs, on CPU tensors: every rank uploads its piece of
+  # the volume, all-gather, LPT share of the components, ONE gather of the raw path buffers, one assembly on rank 0
+  tm = {}
+  out = kd.skeletonize_sharded(labels, device=torch.device("cpu"), anisotropy=(16, 16, 40), dust_threshold=100,
+                               progress=False, timings=tm)
   if rank == 0:
-    q.put(({k: (v.vertices.copy(), v.edges.copy(), v.radii.copy()) for k, v in out.items()}, len(skels)))
+    q.put(({k: (v.vertices.copy(), v.edges.copy(), v.radii.copy()) for k, v in out.items()}, tm["n_traced"]))
   else:
     assert out is None
   dist.barrier()
