@@ -131,6 +131,7 @@ struct EdfParams {
   uint64_t cap;
   Dims d;
   float w[26];
+  float wc[8];           // the same edge lengths by class: bit 0 = steps in x, bit 1 = y, bit 2 = z
 };
 
 __global__ void edf_seed_kernel(EdfParams p, const uint32_t* __restrict__ src, uint32_t n_src) {
@@ -237,6 +238,9 @@ __global__ void __launch_bounds__(1024, 2) edf_multi_kernel(EdfParams p) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kEdfCluster = 8;
 constexpr int kEdfThreads = 512;
+#ifndef B2T_EDF_MINB
+#define B2T_EDF_MINB (B2T_EDF_SOLO ? 2 : 4)   // resident CTAs per SM (the solo form's nine-neighbour tasks want 64 registers)
+#endif
 
 struct EdfJob {
   uint32_t source;      // linear index of the source voxel
@@ -323,10 +327,108 @@ __device__ void edf_label_run(const EdfParams& p, const EdfJob J, uint32_t* cnt,
   }
 }
 
+// ---- the solo form: frontier in SHARED memory, (distance, voxel) pairs, no stamps ---------------------------------
+// A round of the form above is a chain of five dependent global accesses (queue -> dist[u] -> cc[v] -> atomicMin ->
+// stamp exchange -> queue) behind one barrier, ~5 us, and a label has as many rounds as its longest geodesic has hops.
+// Here the frontier of a CTA's label lives in two shared-memory lists of (tentative distance, voxel) pairs: a pair whose
+// distance is no longer the voxel's is stale and skipped, so no stamp is needed to keep a voxel from entering a round
+// twice, and dist[u] is loaded together with the neighbours' labels -- two global round trips per round (loads,
+// atomicMin).  One thread per (voxel, z-plane of its neighbourhood) takes nine neighbours in memory order.  A frontier
+// that outgrows the list spills into the label's global queue, voxel by voxel with the stamp rule of the form above
+// (capacity n_fg: a voxel enters a round's spill at most once).  Same relaxation, same least fixed point.
+#ifndef B2T_EDF_SOLO_CAP
+#define B2T_EDF_SOLO_CAP 2048
+#endif
+#ifndef B2T_EDF_SOLO
+#define B2T_EDF_SOLO 0      // off: measured on synthetic-512 (calls 31/32, profiles/r02_edf_solo_ab.jsonl) the solo form is SLOWER,
+#endif                      // find_root 7.7 vs 5.8 ms, DAF 11.1 vs 8.6 ms -- with ~2000 labels the sweep is bound by how many
+                            // labels are resident (4 CTAs per SM at 32 registers, no shared memory), not by a label's round
+constexpr uint32_t kEdfSoloCap = B2T_EDF_SOLO_CAP;
+struct EdfSoloLists {
+  unsigned long long q[2][kEdfSoloCap];
+  uint32_t cs[3], cg[3];         // entries of a round in the shared list / in the global spill, rotating like cnt above
+};
+
 template <bool NODE_W>
-__global__ void __launch_bounds__(kEdfThreads, 4) edf_label_kernel(EdfParams p, const EdfJob* __restrict__ jobs,
+__device__ void edf_label_solo(const EdfParams& p, const EdfJob J, EdfSoloLists& R) {
+  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  uint32_t* gq = p.queue + 2ull * J.region_off;
+  const uint32_t lab = __ldg(&p.cc[J.source]);
+  if (tid == 0) {
+    p.dist[J.source] = 0.0f;
+    R.q[1][0] = (unsigned long long)J.source;          // key 0: round 1 reads list 1
+    R.cs[0] = 0; R.cs[1] = 1; R.cs[2] = 0;
+    R.cg[0] = 0; R.cg[1] = 0; R.cg[2] = 0;
+  }
+  __syncthreads();
+  for (uint32_t round = 1;; round++) {
+    const uint32_t ci = round % 3, co = (round + 1) % 3;
+    const uint32_t ns = min(R.cs[ci], kEdfSoloCap), ng = R.cg[ci];
+    if (ns + ng == 0) break;
+    const unsigned long long* qin = R.q[round & 1];
+    unsigned long long* qout = R.q[(round + 1) & 1];
+    const uint32_t* gin = gq + (uint64_t)(round & 1) * J.n_fg;
+    uint32_t* gout = gq + (uint64_t)((round + 1) & 1) * J.n_fg;
+    for (uint32_t task = tid; task < 3u * (ns + ng); task += nth) {
+      const uint32_t i = task / 3u, q = task - 3u * i;
+      uint32_t u, dq = 0;
+      const bool paired = i < ns;
+      if (paired) { const unsigned long long pe = qin[i]; u = (uint32_t)pe; dq = (uint32_t)(pe >> 32); }
+      else u = __ldcg(&gin[i - ns]);
+      int x, y, z;
+      unravel(u, p.d, x, y, z);
+      const int nz = z + (int)q - 1;
+      const float du = __ldcg(&p.dist[u]);
+      const bool planeok = nz >= 0 && nz < p.d.sz;
+      const int64_t base = (int64_t)u + ((int64_t)q - 1) * (int64_t)p.d.sxy;
+      uint32_t lv[9];
+      float wv[9];
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        const int ddx = j % 3 - 1, ddy = j / 3 - 1;
+        const int nx = x + ddx, ny = y + ddy;
+        const bool ok = planeok && nx >= 0 && nx < p.d.sx && ny >= 0 && ny < p.d.sy && !(j == 4 && q == 1u);
+        const uint32_t v = (uint32_t)(base + (int64_t)ddy * p.d.sx + ddx);
+        lv[j] = ok ? __ldg(&p.cc[v]) : lab + 1u;                            // never equal to lab
+        if (NODE_W) wv[j] = ok ? __ldg(&p.node_w[v]) : 0.0f;
+        else wv[j] = p.wc[(ddx != 0 ? 1 : 0) | (ddy != 0 ? 2 : 0) | (q != 1u ? 4 : 0)];
+      }
+      if (paired && __float_as_uint(du) != dq) continue;                    // a superseded pair
+      uint32_t nd[9], old[9];
+#pragma unroll
+      for (int j = 0; j < 9; j++) {                                         // all nine atomics in flight before any result is used
+        nd[j] = 0u; old[j] = 0u;
+        if (lv[j] == lab) {
+          const int ddx = j % 3 - 1, ddy = j / 3 - 1;
+          const uint32_t v = (uint32_t)(base + (int64_t)ddy * p.d.sx + ddx);
+          nd[j] = __float_as_uint(__fadd_rn(du, wv[j]));
+          old[j] = atomicMin(reinterpret_cast<uint32_t*>(&p.dist[v]), nd[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        if (nd[j] < old[j]) {                                               // relaxed (old stays 0 where nothing was tried)
+          const int ddx = j % 3 - 1, ddy = j / 3 - 1;
+          const uint32_t v = (uint32_t)(base + (int64_t)ddy * p.d.sx + ddx);
+          const uint32_t pos = atomicAdd(&R.cs[co], 1u);
+          if (pos < kEdfSoloCap) qout[pos] = ((unsigned long long)nd[j] << 32) | v;
+          else if (atomicExch(&p.stamp[v], round) != round) gout[atomicAdd(&R.cg[co], 1u)] = v;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { R.cs[ci] = 0; R.cg[ci] = 0; }   // written again in round + 2; the barrier of round + 1 lies in between
+  }
+}
+
+template <bool NODE_W>
+__global__ void __launch_bounds__(kEdfThreads, B2T_EDF_MINB) edf_label_kernel(EdfParams p, const EdfJob* __restrict__ jobs,
                                                                     uint32_t n_jobs, uint32_t n_team) {
+#if B2T_EDF_SOLO
+  __shared__ EdfSoloLists s_lists;
+#else
   __shared__ uint32_t s_cnt[4];
+#endif
 #ifdef B2T_HOST_EMU
   const uint32_t cid = blockIdx.x, rank = 0, csize = 1;      // emulated clusters have one CTA
 #else
@@ -337,7 +439,11 @@ __global__ void __launch_bounds__(kEdfThreads, 4) edf_label_kernel(EdfParams p, 
     edf_label_run<true, NODE_W>(p, jobs[cid], p.ctrl + 4ull * cid, rank, csize);
   } else {
     const uint32_t job = n_team + (cid - n_team) * csize + rank;
+#if B2T_EDF_SOLO
+    if (job < n_jobs) edf_label_solo<NODE_W>(p, jobs[job], s_lists);
+#else
     if (job < n_jobs) edf_label_run<false, NODE_W>(p, jobs[job], s_cnt, 0, 1);
+#endif
   }
 }
 
@@ -569,6 +675,12 @@ void fill_weights(float wx, float wy, float wz, float* w) {
   for (int i = 18; i < 26; i++) w[i] = c;
 }
 
+void fill_weights(float wx, float wy, float wz, EdfParams& p) {
+  fill_weights(wx, wy, wz, p.w);
+  p.wc[0] = 0.0f; p.wc[1] = p.w[0]; p.wc[2] = p.w[2]; p.wc[4] = p.w[4];
+  p.wc[3] = p.w[6]; p.wc[6] = p.w[10]; p.wc[5] = p.w[14]; p.wc[7] = p.w[18];
+}
+
 int check_dims(int64_t sx, int64_t sy, int64_t sz) {
   B2T_REQUIRE(sx > 0 && sy > 0 && sz > 0, "empty volume");
   B2T_REQUIRE((double)sx * (double)sy * (double)sz < 4294967295.0, "volumes of 2^32 voxels or more are not supported");
@@ -616,7 +728,7 @@ B2T_EXPORT int b2t_edf_multi(const uint32_t* d_cc, int64_t sx, int64_t sy, int64
   p.cc = d_cc; p.node_w = d_node_weights; p.dist = d_dist; p.stamp = d_stamp; p.queue = d_queue; p.ctrl = d_ctrl;
   p.cap = queue_cap;
   p.d = Dims{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
-  fill_weights(wx, wy, wz, p.w);
+  fill_weights(wx, wy, wz, p);
   const bool frozen = free_space_radius > 0.0f;
   if (frozen) {
     B2T_REQUIRE(n_sources == 1, "free_space_radius needs exactly one source");
@@ -661,7 +773,7 @@ B2T_EXPORT int b2t_edf_labels(const uint32_t* d_cc, int64_t sx, int64_t sy, int6
   p.cc = d_cc; p.node_w = d_node_weights; p.dist = d_dist; p.stamp = d_stamp; p.queue = d_queue; p.ctrl = d_ctrl;
   p.cap = 0;
   p.d = Dims{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
-  fill_weights(wx, wy, wz, p.w);
+  fill_weights(wx, wy, wz, p);
   const EdfJob* jobs = reinterpret_cast<const EdfJob*>(d_jobs);
 #ifdef B2T_HOST_EMU
   if (d_node_weights) simt::block_launch(n_jobs, kEdfThreads, [](auto... a_) { edf_label_kernel<true>(a_...); })(p, jobs, n_jobs, n_team);

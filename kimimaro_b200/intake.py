@@ -541,8 +541,10 @@ def _skeletonize(
   early_roots = None
   if fix_borders:
     m0 = segs[~is_private]
-    if m0.size and os.environ.get("B2T_EARLY_ROOTS", "1") == "1":
-      # find_root for the main arena runs on a second stream while the border targets are computed (engine.RootSweep)
+    if m0.size and os.environ.get("B2T_EARLY_ROOTS", "0") == "1":
+      # find_root for the main arena on a second stream while the border targets are computed (engine.RootSweep).  Off:
+      # measured on synthetic-512 (call 31) the sweep's ~2000 CTAs keep every SM slot taken, the border targets' small
+      # launches queue behind them and the pass gets slower and erratic (82 -> 92..150 ms)
       early_roots = engine.RootSweep(d_cc, shape, an, h_first[m0], m0, h_count[m0], n_cc)
     border_targets = engine.compute_border_targets(d_cc, shape, anisotropy)
   t0 = lap("border_targets", t0)

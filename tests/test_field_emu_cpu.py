@@ -22,13 +22,25 @@ c_i64, c_u64, c_u32, c_f32 = ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint32, c
 p = oracle._p
 
 
+def _build(out, extra=()):
+  os.makedirs(os.path.dirname(out), exist_ok=True)
+  if (not os.path.exists(out)) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in DEPS):
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-attributes",
+                           *extra, "-I" + os.path.join(HERE, "host", "emu_include"), "-I" + os.path.join(HERE, "host"), SRC,
+                           "-o", out])
+  return ctypes.CDLL(out)
+
+
 @pytest.fixture(scope="module")
 def emu():
-  os.makedirs(os.path.dirname(OUT), exist_ok=True)
-  if (not os.path.exists(OUT)) or os.path.getmtime(OUT) < max(os.path.getmtime(d) for d in DEPS):
-    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-attributes",
-                           "-I" + os.path.join(HERE, "host", "emu_include"), "-I" + os.path.join(HERE, "host"), SRC, "-o", OUT])
-  return ctypes.CDLL(OUT)
+  return _build(OUT)
+
+
+@pytest.fixture(scope="module")
+def emu_tiny_lists():
+  """the same library with the solo sweep's shared-memory frontier shrunk to 8 pairs: almost every round spills into the
+  label's global queue (the stamp-deduplicated path)"""
+  return _build(OUT.replace(".so", "_cap8.so"), extra=("-DB2T_EDF_SOLO=1", "-DB2T_EDF_SOLO_CAP=8"))
 
 
 def _volume(seed, shape=(40, 36, 28), n=5):
@@ -183,6 +195,32 @@ def test_distance_field_label_by_label(emu, n_team, node_w):
       labels = np.asfortranarray(cc == l).view(np.uint8)
       daf = oracle.euclidean_distance_field(labels, np.unravel_index(roots[l], cc.shape, order="F"), anisotropy=an)
       assert np.array_equal(got[cc == l], daf[cc == l]), l
+
+
+def test_distance_field_solo_spill(emu, emu_tiny_lists):
+  """edf_label_solo with a frontier list of 8 pairs: pairs in shared memory and spilled voxels in the global queue mix
+  in almost every round, and the field must still be the one the full-size build computes, bit for bit."""
+  an = (16.0, 16.0, 40.0)
+  cc, n = _volume(35, shape=(44, 40, 30), n=6)
+  sx, sy, sz = cc.shape
+  ccf = np.ascontiguousarray(cc.reshape(-1, order="F").astype(np.uint32))
+  counts = np.bincount(ccf, minlength=n + 1)
+  order = sorted(range(1, n + 1), key=lambda l: -counts[l])
+  tab = np.zeros((n, 4), np.uint32)
+  off = 0
+  for i, l in enumerate(order):
+    tab[i] = (int(np.flatnonzero(ccf == l)[0]), l, counts[l], off)
+    off += counts[l]
+  out = []
+  for lib_ in (emu, emu_tiny_lists):
+    dist = np.full(ccf.size, np.inf, np.float32)
+    stamp = np.zeros(ccf.size, np.uint32)
+    queue = np.zeros(2 * off + 8, np.uint32)
+    ctrl = np.zeros(4, np.uint32)
+    assert lib_.b2t_edf_labels(p(ccf), c_i64(sx), c_i64(sy), c_i64(sz), c_f32(an[0]), c_f32(an[1]), c_f32(an[2]), p(tab),
+                               c_u32(n), c_u32(0), None, p(dist), p(stamp), p(queue), p(ctrl), None) == 0
+    out.append(dist)
+  assert np.isfinite(out[0][ccf != 0]).all() and np.array_equal(out[0], out[1])
 
 
 def test_ball_invalidation(emu):
