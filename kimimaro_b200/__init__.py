@@ -18,4 +18,10 @@ def __getattr__(name):
   if name in ("skeletonize", "DimensionError", "DEFAULT_TEASAR_PARAMS", "synapses_to_targets"):
     from . import intake
     return getattr(intake, name)
+  if name in ("set_invalidation_mode", "invalidation_mode"):    # "window" (default) | "strict" (the reference's heap order)
+    from . import _lib
+    return getattr(_lib, name)
+  if name == "skeletonize_sharded":                             # one process per GPU, labels sharded over the ranks
+    from . import distributed
+    return distributed.skeletonize_sharded
   raise AttributeError(name)

@@ -87,8 +87,8 @@ def _edf(emu, ccf, shape, an, sources, node_w=None):
   return dist
 
 
-@pytest.mark.parametrize("an", [(16.0, 16.0, 40.0), (1.0, 1.0, 1.0)])
-def test_distance_field_argmax_pdrf(emu, an):
+@pytest.mark.parametrize("an,nb", [((16.0, 16.0, 40.0), 16), ((1.0, 1.0, 1.0), 16), ((16.0, 16.0, 40.0), 1024)])
+def test_distance_field_argmax_pdrf(emu, an, nb):
   """One sweep for ALL labels (each from its own source) must equal the oracle's Dijkstra field label by label, bit for
   bit; then the per-label arg-max (rule T2) and the fused PDRF against the oracle's numpy compute_pdrf."""
   from oracle import teasar
@@ -124,8 +124,7 @@ def test_distance_field_argmax_pdrf(emu, an):
   with np.errstate(all="ignore"):                          # trace.py:352-354: only when max DAF is not 0
     inv[1:] = np.where(vals[1:] != 0, np.float32(1) / vals[1:], np.float32(0)).astype(np.float32)
   active = np.ones(n + 1, np.uint8)
-  V = ccf.size
-  nb = 16
+  V = ccf.size               # nb = 1024: the (label x bucket) table spans two tiles of the multi-block scan
   pdrf, claim = np.zeros(V, np.float32), np.zeros(V, np.uint64)
   hist, cursor = np.zeros((n + 1) * nb + 1, np.uint32), np.zeros((n + 1) * nb + 1, np.uint32)
   keys = np.zeros(int((ccf != 0).sum()) + 1, np.uint64)
