@@ -18,13 +18,13 @@ from .skeleton import Skeleton
 
 def lpt_assign(segids, counts, world_size):
   """Greedy LPT: returns a list (per rank) of cc ids; deterministic on every rank."""
-  order = sorted(segids, key=lambda s: (-int(counts[s]), int(s)))
-  load = [0] * world_size
+  order = sorted(segids, key=lambda s: (-float(counts[s]), int(s)))
+  load = [0.0] * world_size
   shards = [[] for _ in range(world_size)]
   for s in order:
     r = min(range(world_size), key=lambda i: (load[i], i))
     shards[r].append(s)
-    load[r] += int(counts[s])
+    load[r] += float(counts[s])
   return shards
 
 
