@@ -201,7 +201,7 @@ def skeletonize_sharded(all_labels, group=None, device_labels=None, device=None,
     shape = shape + (1,) * (3 - len(shape))
     anisotropy = kwargs.get("anisotropy", (1, 1, 1))
     bundle = skeletonize(all_labels, label_subset=make_label_subset(rank, world), device_labels=device_labels,
-                         raw_paths=True, **kwargs)
+                         raw_paths=True, border_shard=(rank, world, group) if world > 1 else None, **kwargs)
     if isinstance(bundle, dict):                               # nothing to trace on this rank (empty / all dust)
       from .intake import join_raw
       bundle = join_raw([], device, np.dtype(np.int64))

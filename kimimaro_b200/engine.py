@@ -237,7 +237,11 @@ class RootSweep:
 # ------------------------------------------------------------------------------------------------
 # fix_borders (intake.py:544-585)
 # ------------------------------------------------------------------------------------------------
-def compute_border_targets(d_cc, shape, anisotropy):
+def compute_border_targets(d_cc, shape, anisotropy, shard=None):
+  """intake.py:544-585.  shard = (rank, world_size, group) of a multi-GPU run: face f is computed on rank f % world_size
+  only, the per-face target lists are exchanged (one all_gather_object of a few hundred tuples) and every rank replays
+  the insertions in face order -- the per-label SETS come out with the same insertion history, hence the same iteration
+  order (rule B.6), as on one GPU.  The six faces cost 6-9 ms of launches and host work that does not shrink otherwise."""
   sx, sy, sz = shape
   cc3 = d_cc.view(sz, sy, sx)
   faces = (
@@ -260,7 +264,11 @@ def compute_border_targets(d_cc, shape, anisotropy):
   rec = torch.empty((6, 7 * pmax), dtype=torch.int32, device=dev)
   counts = torch.zeros((6, 2), dtype=torch.int32, device=dev)
   planes = []
+  mine = [f for f in range(6) if shard is None or f % shard[1] == shard[0]]
   for f, (face, pshape, dims, rotatefn) in enumerate(faces):
+    if f not in mine:
+      planes.append(None)
+      continue
     wx, wy = float(anisotropy[dims[0]]), float(anisotropy[dims[1]])
     p0, p1 = int(pshape[0]), int(pshape[1])
     plane = face.contiguous().view(-1)                     # flat Fortran order of the 2-D plane: x + p0*y
@@ -271,13 +279,14 @@ def compute_border_targets(d_cc, shape, anisotropy):
     planes.append((cc_plane, p0, p1, wx, wy, rotatefn))
   h_counts = counts.cpu().numpy()                          # the one synchronising read
   parts = []
-  for f in range(6):
+  for f in mine:
     parts.append(cand[f, :2 * int(h_counts[f, 0])])
     parts.append(rec[f, :7 * int(h_counts[f, 1])])
-  h_all = torch.cat(parts).cpu().numpy().view(np.uint32)
-  target_list = defaultdict(set)
+  h_all = torch.cat(parts).cpu().numpy().view(np.uint32) if parts else np.zeros(0, np.uint32)
+  face_lists = {f: [] for f in mine}                       # per face: (volume label, point) in insertion order
   o = 0
-  for f, (cc_plane, p0, p1, wx, wy, rotatefn) in enumerate(planes):
+  for f in mine:
+    cc_plane, p0, p1, wx, wy, rotatefn = planes[f]
     nc, nr = int(h_counts[f, 0]), int(h_counts[f, 1])
     c = h_all[o:o + 2 * nc].reshape(-1, 2).astype(np.int64)
     o += 2 * nc
@@ -305,7 +314,18 @@ def compute_border_targets(d_cc, shape, anisotropy):
                                                    p0, p1, wx, wy)
     vol = {int(l): int(v) for l, v in zip(labels.tolist(), vol_of.tolist())}
     for label, pt in plane_targets.items():
-      target_list[vol[label]].add(rotatefn(int(pt[0]), int(pt[1])))
+      face_lists[f].append((vol[label], rotatefn(int(pt[0]), int(pt[1]))))
+  if shard is not None and shard[1] > 1:
+    import torch.distributed as dist
+    gathered = [None] * shard[1]
+    dist.all_gather_object(gathered, face_lists, group=shard[2])
+    face_lists = {}
+    for part in gathered:
+      face_lists.update(part)
+  target_list = defaultdict(set)
+  for f in range(6):
+    for label, pt in face_lists.get(f, []):
+      target_list[label].add(tuple(pt))
   out = {}
   for label, pts in target_list.items():
     out[label] = np.array(list(pts), dtype=np.uint32)

@@ -407,7 +407,7 @@ def _skeletonize(
   fix_borders=True, parallel=1, parallel_chunk_size=100,
   extra_targets_before=[], extra_targets_after=[],
   fill_holes=False, fix_avocados=False,
-  voxel_graph=None, timings=None, label_subset=None, device_labels=None, edt_events=None, label_dtype=None, raw_paths=False,
+  voxel_graph=None, timings=None, label_subset=None, device_labels=None, edt_events=None, label_dtype=None, raw_paths=False, border_shard=None,
 ):
   """
   Skeletonize all non-zero labels in a 2D or 3D image (kimimaro/intake.py:58-143).
@@ -552,7 +552,7 @@ def _skeletonize(
       early_roots = engine.RootSweep(d_cc, shape, an, h_first[m0], m0, h_count[m0], n_cc)
     # (computing them on a second stream under the volume's EDT and the label statistics was measured: 81.8 vs 81.3 ms
     # per pass on synthetic-512, no gain -- the EDT is over before the first face is queued)
-    border_targets = engine.compute_border_targets(d_cc, shape, anisotropy)
+    border_targets = engine.compute_border_targets(d_cc, shape, anisotropy, shard=border_shard)
   t0 = lap("border_targets", t0)
   lin = lambda p: int(p[0]) + sx * (int(p[1]) + sy * int(p[2]))
 
