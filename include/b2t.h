@@ -229,6 +229,19 @@ int b2t_gather_paths(const uint32_t* d_pool, const uint32_t* d_src_off, const ui
                      const uint64_t* d_dst_off, uint32_t n_seg, const float* d_dbf, uint32_t* d_dst_vox,
                      float* d_dst_radius, void* stream);
 
+/* Skeleton assembly for groups of path segments (kimimaro/trace.py:182-192 Skeleton.from_path / simple_merge /
+ * consolidate, kimimaro/intake.py:509-517, 587-593): per group the distinct path voxels in lexicographic (x, y, z)
+ * order as float32 physical coordinates ((voxel + offset) * anisotropy), their radii (DBF at the first occurrence),
+ * the distinct sorted edges between consecutive path voxels, vertices without an edge dropped.  d_stamp: one u32 per
+ * voxel of the volume, 0xffffffff on entry and on return.  Groups of one call must not share voxels.  A group with more
+ * than b2t_assemble_group_cap() entries reports n_vertices = 0xffffffff and is left to the caller. */
+uint32_t b2t_assemble_group_cap(void);
+int b2t_assemble(const uint32_t* d_vox, const float* d_rad, const uint32_t* d_seg_start, const uint32_t* d_seg_len,
+                 const uint32_t* d_grp_seg, const uint32_t* d_grp_out, const uint32_t* d_grp_list, uint32_t n_list,
+                 uint32_t* d_stamp, int64_t sx, int64_t sy, int64_t sz, float ax, float ay, float az, float ox,
+                 float oy, float oz, float* d_out_verts, float* d_out_rad, uint32_t* d_out_edges,
+                 uint32_t* d_out_count, void* stream);
+
 /* K6  hole filling (soma labels only) -----------------------------------------------------------------------
  * replaces  fill_voids.fill(labels, in_place=True, return_fill_count=True)    kimimaro/trace.py:109
  * d_mask uint8 [V] edited in place; d_reach [V] u32 scratch; d_queue >= V u32 scratch (queue_cap >= V);

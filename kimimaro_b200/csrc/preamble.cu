@@ -440,3 +440,217 @@ B2T_EXPORT int b2t_gather_paths(const uint32_t* d_pool, const uint32_t* d_src_of
   b2t_count_launches(1);
   return B2T_OK;
 }
+
+// =================================================================================================
+// Skeleton assembly (kimimaro/trace.py:182-192: Skeleton.from_path per path, simple_merge, consolidate; intake.py:509-517,
+// 587-593: the components of one original label merged and consolidated again) for one GROUP of path segments per CTA:
+//   vertices   the distinct path voxels of the group in lexicographic (x, y, z) order (np.unique(vertices, axis=0)),
+//              radius = DBF at the first occurrence in the group's path buffer (consolidate keeps the first)
+//   edges      consecutive path voxels, as (smaller, larger) vertex ranks, distinct, sorted, no self loops
+//   then vertices without an edge are dropped and the ranks renumbered (the order of both lists is kept).
+// A dense u32 scratch volume (0xffffffff everywhere on entry, restored on exit) is the hash set: atomicMin of the entry
+// position finds the first occurrence of a voxel, later it holds the voxel's vertex rank for the edge pass.  Both sorts
+// are shared-memory bitonic sorts over the next power of two.  Groups with more than kAsmCap entries (the caller sends
+// those down its general path) report n_vertices = 0xffffffff and are left alone.
+//   d_vox / d_rad      the path buffer: voxel indices (0xffffffff = end of a path) and DBF per entry
+//   d_seg_start/_len   per segment: first entry and number of entries; segments of a group are consecutive
+//   d_grp_seg          [n_grp + 1] first segment of every group;  d_grp_out [n_grp + 1] first output slot of every group
+//                      (prefix sum of the groups' entry counts: a group never has more vertices or edges than entries)
+//   d_out_verts [3 * N] f32 physical coordinates, d_out_rad [N], d_out_edges [2 * N] u32, d_out_count [2 * n_grp]
+// =================================================================================================
+namespace {
+
+constexpr uint32_t kAsmCap = 8192;
+constexpr int kAsmThreads = 256;
+
+struct AsmShared {
+  unsigned long long vk[kAsmCap];     // (lexicographic key << 32) | position of the first occurrence
+  uint32_t ek[kAsmCap];               // edge keys (lo rank << 13) | hi rank ... ranks < kAsmCap = 2^13
+  uint32_t n_v, n_e, n_used;
+};
+
+template <typename K>
+__device__ void asm_bitonic(K* a, uint32_t n_pow2) {          // ascending; all kAsmThreads threads call
+  for (uint32_t k = 2; k <= n_pow2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < n_pow2; i += kAsmThreads) {
+        const uint32_t l = i ^ j;
+        if (l > i) {
+          const K x = a[i], y = a[l];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { a[i] = y; a[l] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t asm_pow2(uint32_t n) { uint32_t p = 1; while (p < n) p <<= 1; return p; }
+
+__global__ void __launch_bounds__(kAsmThreads) assemble_kernel(
+    const uint32_t* __restrict__ vox, const float* __restrict__ rad, const uint32_t* __restrict__ seg_start,
+    const uint32_t* __restrict__ seg_len, const uint32_t* __restrict__ grp_seg, const uint32_t* __restrict__ grp_out,
+    const uint32_t* __restrict__ grp_list, uint32_t* __restrict__ stamp, Dims d, float ax, float ay, float az, float ox, float oy,
+    float oz, float* __restrict__ out_verts, float* __restrict__ out_rad, uint32_t* __restrict__ out_edges,
+    uint32_t* __restrict__ out_count) {
+#ifdef B2T_HOST_EMU
+  static AsmShared S;
+#else
+  extern __shared__ __align__(16) unsigned char b2t_asm_smem[];
+  AsmShared& S = *reinterpret_cast<AsmShared*>(b2t_asm_smem);
+#endif
+  const uint32_t g = grp_list[blockIdx.x];
+  const uint32_t s0 = grp_seg[g], s1 = grp_seg[g + 1];
+  const uint32_t o0 = grp_out[g], n_ent = grp_out[g + 1] - o0;
+  if (n_ent > kAsmCap) {
+    if (threadIdx.x == 0) { out_count[2 * g] = 0xffffffffu; out_count[2 * g + 1] = 0; }
+    return;
+  }
+  if (threadIdx.x == 0) { S.n_v = 0; S.n_e = 0; S.n_used = 0; }
+  __syncthreads();
+  const uint32_t sxy = d.sxy, sx = (uint32_t)d.sx, sy = (uint32_t)d.sy, sz = (uint32_t)d.sz;
+  // 1. first occurrence of every voxel: smallest entry position wins
+  for (uint32_t s = s0; s < s1; s++) {
+    const uint32_t b = seg_start[s], n = seg_len[s];
+    for (uint32_t i = threadIdx.x; i < n; i += kAsmThreads) {
+      const uint32_t v = vox[b + i];
+      if (v != kNone) atomicMin(&stamp[v], b + i);
+    }
+  }
+  __syncthreads();
+  for (uint32_t s = s0; s < s1; s++) {
+    const uint32_t b = seg_start[s], n = seg_len[s];
+    for (uint32_t i = threadIdx.x; i < n; i += kAsmThreads) {
+      const uint32_t v = vox[b + i];
+      if (v != kNone && stamp[v] == b + i) {
+        const uint32_t z = v / sxy, r = v - z * sxy, y = r / sx, x = r - y * sx;
+        const uint32_t key = (x * sy + y) * sz + z;                    // < V < 2^32
+        S.vk[atomicAdd(&S.n_v, 1u)] = ((unsigned long long)key << 32) | (unsigned long long)(b + i);
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t nv = S.n_v;
+  const uint32_t pv = asm_pow2(nv);
+  for (uint32_t i = nv + threadIdx.x; i < pv; i += kAsmThreads) S.vk[i] = ~0ull;
+  __syncthreads();
+  asm_bitonic(S.vk, pv);
+  // 2. the dense volume now holds the vertex rank of every voxel of the group
+  for (uint32_t p = threadIdx.x; p < nv; p += kAsmThreads) stamp[vox[(uint32_t)S.vk[p]]] = p;
+  __syncthreads();
+  // 3. edges between consecutive path entries
+  for (uint32_t s = s0; s < s1; s++) {
+    const uint32_t b = seg_start[s], n = seg_len[s];
+    for (uint32_t i = threadIdx.x; i + 1 < n; i += kAsmThreads) {
+      const uint32_t va = vox[b + i], vb = vox[b + i + 1];
+      if (va != kNone && vb != kNone) {
+        const uint32_t ra = stamp[va], rb = stamp[vb];
+        if (ra != rb) S.ek[atomicAdd(&S.n_e, 1u)] = (min(ra, rb) << 13) | max(ra, rb);
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t ne_all = S.n_e;
+  const uint32_t pe = asm_pow2(ne_all);
+  for (uint32_t i = ne_all + threadIdx.x; i < pe; i += kAsmThreads) S.ek[i] = 0xffffffffu;
+  __syncthreads();
+  asm_bitonic(S.ek, pe);
+  // 4. distinct edges (compacted in place, order kept) and a bitset of the vertices they use
+  __shared__ uint32_t s_scan[kAsmThreads];
+  __shared__ uint32_t s_used[kAsmCap / 32];
+  for (uint32_t i = threadIdx.x; i < kAsmCap / 32; i += kAsmThreads) s_used[i] = 0;
+  __syncthreads();
+  // unique count + compaction by a block scan over chunks of kAsmThreads sorted edges
+  uint32_t ne = 0;
+  for (uint32_t base = 0; base < ne_all; base += kAsmThreads) {
+    const uint32_t i = base + threadIdx.x;
+    uint32_t e = 0;
+    bool keep = false;
+    if (i < ne_all) {
+      e = S.ek[i];
+      keep = i == 0 || S.ek[i - 1] != e;
+    }
+    __syncthreads();                                                 // every thread has read its neighbours before the writes
+    s_scan[threadIdx.x] = keep ? 1u : 0u;
+    __syncthreads();
+    for (int o = 1; o < kAsmThreads; o <<= 1) {
+      const uint32_t t = threadIdx.x >= (uint32_t)o ? s_scan[threadIdx.x - o] : 0u;
+      __syncthreads();
+      s_scan[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (keep) {
+      S.ek[ne + s_scan[threadIdx.x] - 1] = e;                        // ne + rank <= i: never overtakes an unread entry
+      atomicOr(&s_used[(e >> 13) >> 5], 1u << ((e >> 13) & 31u));
+      atomicOr(&s_used[(e & 0x1fffu) >> 5], 1u << (e & 31u));
+    }
+    ne += s_scan[kAsmThreads - 1];
+    __syncthreads();
+  }
+  // 5. new rank of a used vertex = number of used vertices before it (exclusive scan over the bitset words)
+  __shared__ uint32_t s_wpre[kAsmCap / 32 + 1];
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (uint32_t w = 0; w < kAsmCap / 32; w++) { s_wpre[w] = run; run += __popc(s_used[w]); }
+    s_wpre[kAsmCap / 32] = run;
+  }
+  __syncthreads();
+  const uint32_t n_used = s_wpre[kAsmCap / 32];
+  auto newrank = [&](uint32_t r) { return s_wpre[r >> 5] + __popc(s_used[r >> 5] & ((1u << (r & 31u)) - 1u)); };
+  // 6. outputs; the dense volume goes back to 0xffffffff
+  for (uint32_t p = threadIdx.x; p < nv; p += kAsmThreads) {
+    const unsigned long long e = S.vk[p];
+    const uint32_t pos = (uint32_t)e, key = (uint32_t)(e >> 32);
+    const uint32_t v = vox[pos];
+    if ((s_used[p >> 5] >> (p & 31u)) & 1u) {
+      const uint32_t q = o0 + newrank(p);
+      const uint32_t z = key % sz, xy = key / sz, y = xy % sy, x = xy / sy;
+      out_verts[3ull * q + 0] = __fmul_rn(__fadd_rn((float)x, ox), ax);   // float32 like intake.py:509-513
+      out_verts[3ull * q + 1] = __fmul_rn(__fadd_rn((float)y, oy), ay);
+      out_verts[3ull * q + 2] = __fmul_rn(__fadd_rn((float)z, oz), az);
+      out_rad[q] = rad[pos];
+    }
+    stamp[v] = kNone;
+  }
+  for (uint32_t k = threadIdx.x; k < ne; k += kAsmThreads) {
+    const uint32_t e = S.ek[k];
+    out_edges[2ull * (o0 + k) + 0] = newrank(e >> 13);
+    out_edges[2ull * (o0 + k) + 1] = newrank(e & 0x1fffu);
+  }
+  if (threadIdx.x == 0) { out_count[2 * g] = n_used; out_count[2 * g + 1] = ne; }
+}
+
+}  // namespace
+
+B2T_EXPORT uint32_t b2t_assemble_group_cap(void) { return kAsmCap; }
+
+// d_grp_list: the n_list groups to assemble in this launch (groups of one launch must not share voxels: see above).
+B2T_EXPORT int b2t_assemble(const uint32_t* d_vox, const float* d_rad, const uint32_t* d_seg_start, const uint32_t* d_seg_len,
+                            const uint32_t* d_grp_seg, const uint32_t* d_grp_out, const uint32_t* d_grp_list, uint32_t n_list,
+                            uint32_t* d_stamp, int64_t sx, int64_t sy, int64_t sz, float ax, float ay, float az, float ox,
+                            float oy, float oz, float* d_out_verts, float* d_out_rad, uint32_t* d_out_edges,
+                            uint32_t* d_out_count, void* stream) {
+  if (n_list == 0) return B2T_OK;
+  B2T_REQUIRE(d_vox && d_rad && d_seg_start && d_seg_len && d_grp_seg && d_grp_out && d_grp_list && d_stamp && d_out_verts &&
+              d_out_rad && d_out_edges && d_out_count, "b2t_assemble: null pointer");
+  B2T_REQUIRE(sx > 0 && sy > 0 && sz > 0 && (double)sx * sy * sz < 4294967295.0, "bad volume shape");
+  Dims d{(int)sx, (int)sy, (int)sz, (uint32_t)(sx * sy)};
+#ifdef B2T_HOST_EMU
+  simt::block_launch(n_list, kAsmThreads, [](auto... a_) { assemble_kernel(a_...); })(
+      d_vox, d_rad, d_seg_start, d_seg_len, d_grp_seg, d_grp_out, d_grp_list, d_stamp, d, ax, ay, az, ox, oy, oz, d_out_verts,
+      d_out_rad, d_out_edges, d_out_count);
+#else
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2T_CUDA_TRY(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AsmShared)));
+    attr_set = true;
+  }
+  assemble_kernel<<<n_list, kAsmThreads, sizeof(AsmShared), (cudaStream_t)stream>>>(
+      d_vox, d_rad, d_seg_start, d_seg_len, d_grp_seg, d_grp_out, d_grp_list, d_stamp, d, ax, ay, az, ox, oy, oz, d_out_verts,
+      d_out_rad, d_out_edges, d_out_count);
+  B2T_CUDA_TRY(cudaGetLastError());
+#endif
+  b2t_count_launches(1);
+  return B2T_OK;
+}

@@ -112,10 +112,10 @@ def gather_raw(bundle, device, group=None, dst=0):
   of all ranks are then assembled in one device-side pass on dst (intake.skeletons_from_raw), which also consolidates
   labels whose connected components were traced on different ranks -- no per-skeleton Python work on either side."""
   rank, world = dist.get_rank(group), dist.get_world_size(group)
-  vox, rad, lens, gids = bundle
+  vox, rad, lens, gids, priv = bundle
   id_dtype = gids.dtype
   meta = np.concatenate([np.asarray(lens, dtype=np.int64), np.asarray(gids).astype(id_dtype).view(
-    np.int64 if id_dtype.itemsize == 8 else id_dtype).astype(np.int64)])
+    np.int64 if id_dtype.itemsize == 8 else id_dtype).astype(np.int64), np.asarray(priv, dtype=np.int64)])
   sizes = torch.tensor([int(vox.numel()), int(lens.size)], dtype=torch.int64, device=device)
   all_sizes = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
   dist.all_gather(all_sizes, sizes, group=group)
@@ -135,7 +135,7 @@ def gather_raw(bundle, device, group=None, dst=0):
       continue
     nv, ns = (int(v) for v in all_sizes[r])
     b = [torch.empty(nv, dtype=torch.int32, device=device), torch.empty(nv, dtype=torch.float32, device=device),
-         torch.empty(2 * ns, dtype=torch.int64, device=device)]
+         torch.empty(3 * ns, dtype=torch.int64, device=device)]
     parts[r] = b
     ops += [dist.P2POp(dist.irecv, t, r, group=group) for t in b if t.numel() > 0]
   if ops:
@@ -143,10 +143,11 @@ def gather_raw(bundle, device, group=None, dst=0):
       req.wait()
   order = sorted(parts)
   metas = [parts[r][2].cpu().numpy() for r in order]
-  lens_all = np.concatenate([m[:m.size // 2] for m in metas])
-  gid_all = np.concatenate([m[m.size // 2:] for m in metas])
+  lens_all = np.concatenate([m[:m.size // 3] for m in metas])
+  gid_all = np.concatenate([m[m.size // 3:2 * (m.size // 3)] for m in metas])
+  priv_all = np.concatenate([m[2 * (m.size // 3):] for m in metas]).astype(bool)
   gid_all = gid_all.view(id_dtype) if id_dtype.itemsize == 8 else gid_all.astype(id_dtype)
-  return torch.cat([parts[r][0] for r in order]), torch.cat([parts[r][1] for r in order]), lens_all, gid_all
+  return torch.cat([parts[r][0] for r in order]), torch.cat([parts[r][1] for r in order]), lens_all, gid_all, priv_all
 
 
 def upload_sharded(all_labels, device, group=None):

@@ -50,6 +50,9 @@ _lib.declare("b2t_invalidate_ball_single", [c_vp, c_vp, c_vp, c_i64, c_i64, c_i6
 _lib.declare("b2t_segment_seqsum", [c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp])
 _lib.declare("b2t_set_launch_limits", [c_int, c_int])
 _lib.declare("b2t_gather_paths", [c_vp, c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp])
+_lib.declare("b2t_assemble_group_cap", [], c_u32)
+_lib.declare("b2t_assemble", [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32,
+                              c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp])
 
 NBUCKETS = 256
 NONE = 0xFFFFFFFF
@@ -641,7 +644,90 @@ def trace_arena(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timings=No
 # ------------------------------------------------------------------------------------------------
 # skeleton assembly (trace.py:182-192, intake.py:509-517, 587-593) for all labels at once
 # ------------------------------------------------------------------------------------------------
-def assemble(d_vox, d_rad, seg_off, seg_ids, shape, anisotropy, offset=(0, 0, 0), group_ids=None):
+def assemble(d_vox, d_rad, seg_off, seg_ids, shape, anisotropy, offset=(0, 0, 0), group_ids=None, seg_private=None):
+  """
+  Skeleton.from_path / simple_merge / consolidate (trace.py:182-184) for ALL labels at once on the device:
+  unique vertices per label in lexicographic (x,y,z) order, edges remapped / sorted / unique / no self loops, vertices
+  without edges dropped, radii of the vertex (first occurrence), then voxel -> physical units in float32 exactly like
+  intake.py:509-513.  group_ids (one id per segment, default: the segment's own cc id) lets several connected components
+  of one original label be consolidated together, which is what intake.py:587-593 (merge) does afterwards: components
+  are disjoint voxel sets, so merging is the same sort over the union.
+  One CTA per group (b2t_assemble: a dense u32 volume as the hash set, two shared-memory bitonic sorts); a group above
+  b2t_assemble_group_cap() path entries -- a handful of giant labels -- goes through _assemble_general (torch sort /
+  unique as plumbing).  seg_private marks segments traced in a private arena: their paths may run through filled voids,
+  i.e. voxels of OTHER labels, so a group holding any is assembled in a launch of its own.
+  Returns {group id: (vertices f32 [N,3] physical, edges u32 [M,2], radii f32 [N])} (numpy views).
+  """
+  n = int(d_vox.numel())
+  if n == 0:
+    return {}
+  L = lib()
+  if not hasattr(L, "b2t_assemble") or os.environ.get("B2T_ASSEMBLE", "1") == "0":
+    return _assemble_general(d_vox, d_rad, seg_off, seg_ids, shape, anisotropy, offset, group_ids)
+  sx, sy, sz = shape
+  V = sx * sy * sz
+  dev = d_vox.device
+  seg_off = np.asarray(seg_off, dtype=np.int64)
+  n_seg = int(seg_off.size - 1)
+  if group_ids is None:
+    group_ids = seg_ids
+  groups, grank = np.unique(np.asarray(group_ids), return_inverse=True)
+  n_grp = int(groups.size)
+  order = np.argsort(grank, kind="stable")                   # segments of a group consecutive, path order kept inside
+  lens = np.diff(seg_off)
+  seg_start = seg_off[:-1][order]
+  seg_len = lens[order]
+  grp_seg = np.searchsorted(grank[order], np.arange(n_grp + 1))
+  ent = np.zeros(n_grp, dtype=np.int64)
+  np.add.at(ent, grank, lens)
+  grp_out = np.concatenate(([0], np.cumsum(ent)))
+  cap = int(L.b2t_assemble_group_cap())
+  priv = np.zeros(n_grp, dtype=bool)
+  if seg_private is not None and np.any(seg_private):
+    priv[np.unique(grank[np.asarray(seg_private, dtype=bool)])] = True
+  small = ent <= cap
+  launches = [np.flatnonzero(small & ~priv)] + [np.array([g]) for g in np.flatnonzero(small & priv)]
+  tab = np.concatenate([seg_start, seg_len, grp_seg, grp_out] + launches).astype(np.uint32)
+  d_tab = _dev(tab.view(np.int32))
+  o_ss, o_sl, o_gs, o_go, o_l = (int(v) * 4 for v in np.cumsum([0, n_seg, n_seg, n_grp + 1, n_grp + 1]))
+  stamp = torch.full((V,), -1, dtype=torch.int32, device=dev)
+  out_f = torch.empty(4 * n, dtype=torch.float32, device=dev)          # vertices [3n] | radii [n]
+  out_u = torch.zeros(2 * n + 2 * n_grp, dtype=torch.int32, device=dev)  # edges [2n] | counts [2 * n_grp]
+  an = [float(a) for a in anisotropy]
+  base = int(d_tab.data_ptr())
+  lo = 0
+  for lst in launches:
+    if lst.size:
+      check(L.b2t_assemble(_p(d_vox), _p(d_rad), c_vp(base + o_ss), c_vp(base + o_sl), c_vp(base + o_gs), c_vp(base + o_go),
+                           c_vp(base + o_l + 4 * lo), c_u32(int(lst.size)), _p(stamp), c_i64(sx), c_i64(sy), c_i64(sz),
+                           c_f32(an[0]), c_f32(an[1]), c_f32(an[2]), c_f32(float(offset[0])), c_f32(float(offset[1])),
+                           c_f32(float(offset[2])), _p(out_f), c_vp(out_f.data_ptr() + 12 * n), _p(out_u),
+                           c_vp(out_u.data_ptr() + 8 * n), stream_ptr()), "b2t_assemble")
+    lo += int(lst.size)
+  h_f = out_f.cpu().numpy()
+  h_u = out_u.cpu().numpy().view(np.uint32)
+  h_verts, h_rad = h_f[:3 * n].reshape(-1, 3), h_f[3 * n:]
+  h_edges, h_cnt = h_u[:2 * n].reshape(-1, 2), h_u[2 * n:].reshape(-1, 2)
+  out = {}
+  gl, offs, cnts = groups.tolist(), grp_out.tolist(), h_cnt.tolist()
+  for k in np.flatnonzero(small).tolist():
+    nv, ne = cnts[k]
+    if nv == 0:
+      continue
+    o = offs[k]
+    out[gl[k]] = (h_verts[o:o + nv], h_edges[o:o + ne], h_rad[o:o + nv])
+  big = np.flatnonzero(~small)
+  if big.size:                                                # the few giant groups: general path on their segments only
+    sel = np.flatnonzero(np.isin(grank, big))
+    parts_v = [d_vox[int(seg_off[i]):int(seg_off[i + 1])] for i in sel]
+    parts_r = [d_rad[int(seg_off[i]):int(seg_off[i + 1])] for i in sel]
+    sub_off = np.concatenate(([0], np.cumsum(lens[sel])))
+    out.update(_assemble_general(torch.cat(parts_v), torch.cat(parts_r), sub_off, np.asarray(seg_ids)[sel], shape, anisotropy,
+                                 offset, np.asarray(group_ids)[sel]))
+  return out
+
+
+def _assemble_general(d_vox, d_rad, seg_off, seg_ids, shape, anisotropy, offset=(0, 0, 0), group_ids=None):
   """
   Skeleton.from_path / simple_merge / consolidate (trace.py:182-184) for ALL labels at once,
   on the device, with torch sort/unique/cumsum as plumbing (the reference's counterpart is np.unique on

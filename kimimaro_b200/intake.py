@@ -612,7 +612,7 @@ def _skeletonize(
     if not overlap:
       vox, rad, seg_off, seg_ids, stats = engine.trace_arena_finish(handle)
       handle = None
-      raw.append((vox, rad, np.diff(seg_off), h_orig[seg_ids]))
+      raw.append((vox, rad, np.diff(seg_off), h_orig[seg_ids], np.zeros(seg_ids.size, dtype=bool)))
       stats_all.append(stats)
   if private:
     d_cc3 = d_cc.view(sz, sy, sx)
@@ -628,7 +628,8 @@ def _skeletonize(
           t0 = time.perf_counter()
           ptm = {} if tm is not None else None
           (pvox, prad, plens), stats = _private_arena(d_cc3, d_dbf3, segid, bb, an, params, root, tb, ta, ptm)
-          raw.append((pvox, prad, plens, np.full(plens.size, h_orig[segid], dtype=h_orig.dtype)))
+          raw.append((pvox, prad, plens, np.full(plens.size, h_orig[segid], dtype=h_orig.dtype),
+                      np.ones(plens.size, dtype=bool)))
           stats_all.append(stats)
           if tm is not None:
             tm["soma"] = tm.get("soma", 0.0) + time.perf_counter() - t0
@@ -640,7 +641,7 @@ def _skeletonize(
       main_stream.wait_stream(side)
   if handle is not None:
     vox, rad, seg_off, seg_ids, stats = engine.trace_arena_finish(handle)
-    raw.insert(0, (vox, rad, np.diff(seg_off), h_orig[seg_ids]))
+    raw.insert(0, (vox, rad, np.diff(seg_off), h_orig[seg_ids], np.zeros(seg_ids.size, dtype=bool)))
     stats_all.insert(0, stats)
   if tm is not None:
     tm["n_cc"] = n_cc
@@ -657,25 +658,27 @@ def _skeletonize(
 
 def join_raw(raw, device, id_dtype):
   """Concatenate per-arena path buffers: (voxels i32 [N] device with -1 terminators, radii f32 [N] device, segment
-  lengths int64 [S], original label of every segment [S])."""
+  lengths int64 [S], original label of every segment [S], traced-in-a-private-arena flag of every segment [S])."""
   if not raw:
     return (torch.empty(0, dtype=torch.int32, device=device), torch.empty(0, dtype=torch.float32, device=device),
-            np.zeros(0, dtype=np.int64), np.zeros(0, dtype=id_dtype))
+            np.zeros(0, dtype=np.int64), np.zeros(0, dtype=id_dtype), np.zeros(0, dtype=bool))
   if len(raw) == 1:
-    return raw[0][0], raw[0][1], np.asarray(raw[0][2], dtype=np.int64), np.asarray(raw[0][3])
+    return raw[0][0], raw[0][1], np.asarray(raw[0][2], dtype=np.int64), np.asarray(raw[0][3]), np.asarray(raw[0][4], dtype=bool)
   return (torch.cat([r[0] for r in raw]), torch.cat([r[1] for r in raw]),
-          np.concatenate([np.asarray(r[2], dtype=np.int64) for r in raw]), np.concatenate([np.asarray(r[3]) for r in raw]))
+          np.concatenate([np.asarray(r[2], dtype=np.int64) for r in raw]), np.concatenate([np.asarray(r[3]) for r in raw]),
+          np.concatenate([np.asarray(r[4], dtype=bool) for r in raw]))
 
 
 def skeletons_from_raw(bundle, shape, anisotropy, tm=None):
   """Path buffers -> {original label: Skeleton}: one device-side assembly for every label of every arena (the connected
   components of one original label are consolidated together, which is what the reference's merge per id does,
   intake.py:509-517, 587-593), then one Skeleton object per label."""
-  vox, rad, lens, gids = bundle
+  vox, rad, lens, gids, priv = bundle
   an = tuple(float(a) for a in anisotropy)
   t0 = time.perf_counter()
   seg_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
-  results = engine.assemble(vox, rad, seg_off, np.arange(lens.size, dtype=np.int64), shape, an, group_ids=gids)
+  results = engine.assemble(vox, rad, seg_off, np.arange(lens.size, dtype=np.int64), shape, an, group_ids=gids,
+                            seg_private=priv)
   if tm is not None:
     if vox.device.type == "cuda":
       torch.cuda.synchronize()

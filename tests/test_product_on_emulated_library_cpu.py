@@ -235,3 +235,54 @@ def test_sharded_over_two_ranks_gloo():
   for k in ref:
     assert np.array_equal(out[k][0], ref[k]["vertices"]) and np.array_equal(out[k][1], ref[k]["edges"])
     np.testing.assert_allclose(out[k][2], ref[k]["radii"], rtol=1e-4)
+
+
+def test_assemble_kernel_equals_general_path(product):
+  """b2t_assemble (one CTA per label: dense-volume hash set + two shared-memory bitonic sorts) against the torch
+  sort / unique formulation of the same consolidate semantics, on random path buffers: several segments per group,
+  revisited voxels, repeated edges, a path of one voxel (dropped: no edge), segments of one group far apart in the
+  buffer, a private-arena group, and one group above the kernel's capacity (general path for that group only)."""
+  import torch
+  from kimimaro_b200 import engine
+  rng = np.random.default_rng(11)
+  shape = (40, 36, 30)
+  V = shape[0] * shape[1] * shape[2]
+  cap = int(engine.lib().b2t_assemble_group_cap())
+  vox, gids, priv, lens = [], [], [], []
+
+  def walk(n):
+    p = rng.integers(5, 25, size=3)
+    out = []
+    for _ in range(n):
+      p = np.clip(p + rng.integers(-1, 2, size=3), 0, np.array(shape) - 1)
+      out.append(int(p[0] + shape[0] * (p[1] + shape[1] * p[2])))
+    return out
+
+  for seg in range(60):
+    g = int(rng.integers(1, 12))
+    entries = []
+    for _ in range(int(rng.integers(1, 5))):
+      entries += walk(int(rng.integers(1, 40))) + [-1]
+    vox += entries
+    lens.append(len(entries))
+    gids.append(g)
+    priv.append(g == 7)
+  big = []                                                      # group 99: more entries than one CTA takes
+  while len(big) <= cap:
+    big += walk(200) + [-1]
+  vox += big
+  lens.append(len(big))
+  gids.append(99)
+  priv.append(False)
+  d_vox = torch.tensor(vox, dtype=torch.int32)
+  d_rad = torch.tensor(rng.random(len(vox)).astype(np.float32))
+  seg_off = np.concatenate(([0], np.cumsum(lens)))
+  seg_ids = np.arange(len(lens))
+  kw = dict(shape=shape, anisotropy=(16.0, 16.0, 40.0), offset=(3, 0, 1), group_ids=np.array(gids))
+  got = engine.assemble(d_vox, d_rad, seg_off, seg_ids, seg_private=np.array(priv), **kw)
+  ref = engine._assemble_general(d_vox, d_rad, seg_off, seg_ids, **kw)
+  assert sorted(got) == sorted(ref) and 99 in got
+  for k in ref:
+    assert np.array_equal(got[k][0], ref[k][0]) and np.array_equal(got[k][1], ref[k][1]), k
+    # radii: the general path takes the first occurrence too
+    assert np.array_equal(got[k][2], ref[k][2]), k
