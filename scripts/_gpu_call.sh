@@ -1,13 +1,16 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/gpu_tests.log 2>&1; tail -3 gpurun_out/gpu_tests.log
-timeout 600 python bench.py --gpus 1 --steps 8 --warmup 3 --no-cpu --no-strict > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 300 gpurun_out/bench_n1.err
-B2T_ASSEMBLE=0 timeout 600 python bench.py --gpus 1 --steps 8 --warmup 3 --no-cpu --no-strict > gpurun_out/bench_n1_torchasm.json 2> gpurun_out/bench_n1_torchasm.err
+: > gpurun_out/phase_ab.jsonl
+for rep in 1 2; do
+  for v in default edfm_old edfm_minb2; do
+    if [ $v = default ]; then L=$PWD/kimimaro_b200/libb2t.so; else L=$PWD/kimimaro_b200/_variants/$v.so; fi
+    B2T_LIB=$L B2T_X=$v timeout 300 python scripts/phase_times.py 512 3 >> gpurun_out/phase_ab.jsonl 2>> gpurun_out/phase_ab.err
+  done
+done
+tail -3 gpurun_out/phase_ab.err
 python - <<'PY'
 import json
-for f in ("gpurun_out/bench_n1.json","gpurun_out/bench_n1_torchasm.json"):
-  try:
-    r=json.loads(open(f).read().strip().splitlines()[-1])
-    print(f, r["n_gpus"], round(r["ms_per_step"],2), round(r["e2e"]["ms_per_step"],2), r["parity"]["tier_a_identical_to_oracle_in_same_mode"], r["gpu_launches"]); print(r["phases_ms"]); print(r["per_step_ms"])
-  except Exception as e: print(f, "ERR", e)
+for l in open("gpurun_out/phase_ab.jsonl"):
+  r = json.loads(l); ph = r["phases_ms"]
+  print(r["env"].get("B2T_X"), r["pass_ms"], {k: ph.get(k) for k in ("find_root","daf","paths","soma","soma_daf")}, r.get("identical_to_oracle_same_mode"))
 PY
