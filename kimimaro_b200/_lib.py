@@ -114,6 +114,20 @@ def invalidation_mode():
   return _invalidation
 
 
+_raw_stream = None
+
+
 def stream_ptr():
+  """cudaStream_t of torch's current stream on the current device (every C call takes it).  torch.cuda.current_stream()
+  resolves the device through several Python layers (~15 us, a hundred times per pass); the raw getter does not."""
+  global _raw_stream
   import torch
+  if _raw_stream is None:
+    getter = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    _raw_stream = getter if getter is not None else False
+  if _raw_stream:
+    try:
+      return c_vp(_raw_stream(torch.cuda.current_device()))
+    except Exception:             # no CUDA runtime behind torch (the CPU suite's emulated library stubs current_stream)
+      _raw_stream = False
   return c_vp(torch.cuda.current_stream().cuda_stream)

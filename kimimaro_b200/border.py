@@ -179,6 +179,20 @@ def centroid_from_sums(xsum, ysum, count, sx, sy, wx, wy):
   return (int(f32(px / wx)), int(f32(py / wy)))
 
 
+def centroids_from_sums(xsum, ysum, count, sx, sy, wx, wy):
+  """centroid_from_sums for arrays of labels at once -> int64 [n, 2].  Every step is one IEEE float32 operation per
+  element (multiply, divide, subtract, add, compare, truncate), which numpy evaluates identically for scalars and arrays."""
+  wx, wy = f32(wx), f32(wy)
+  ct = np.asarray(count).astype(np.float32)
+  cx = f32(f32(wx * f32(sx)) / f32(2))
+  cy = f32(f32(wy * f32(sy)) / f32(2))
+  px = (wx * np.asarray(xsum, dtype=np.float32)) / ct
+  py = (wy * np.asarray(ysum, dtype=np.float32)) / ct
+  px = np.where((px - cx) >= 0, px, px + wx)
+  py = np.where((py - cy) >= 0, py, py + wy)
+  return np.stack([(px / wx).astype(np.int64), (py / wy).astype(np.int64)], axis=1)
+
+
 def targets_from_candidates(cand_idx, cand_lab, labels, first_pos, xsum, ysum, count, sx, sy, wx, wy):
   """
   find_border_targets (pyx:591-648) when the per-label reductions were done on the device:
@@ -210,8 +224,9 @@ def targets_from_candidates(cand_idx, cand_lab, labels, first_pos, xsum, ysum, c
     px = (mi % sx).astype(np.float32)
     py = (mi // sx).astype(np.float32)
     labs_multi = cl[starts[~single]]
-    cxy = np.array([centroid_from_sums(xsum[slot[l]], ysum[slot[l]], count[slot[l]], sx, sy, wx, wy)
-                    for l in labs_multi.tolist()], dtype=np.float32).reshape(-1, 2)
+    sl = np.array([slot[l] for l in labs_multi.tolist()], dtype=np.int64)
+    cxy = centroids_from_sums(np.asarray(xsum)[sl], np.asarray(ysum)[sl], np.asarray(count)[sl], sx, sy, wx,
+                              wy).astype(np.float32).reshape(-1, 2)
     rep = (ends - starts)[~single]
     c1, c2, c3, c4 = _criteria(px, py, np.repeat(cxy[:, 0], rep), np.repeat(cxy[:, 1], rep), sx, sy, wx, wy)
     o2 = np.lexsort((np.arange(ml.size), c4, c3, c2, c1, ml))

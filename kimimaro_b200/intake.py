@@ -577,8 +577,26 @@ def _skeletonize(
   tb_map, ta_map = {}, {}
   has_targets = set(border_targets.keys()) | set(extra_before.keys()) | set(extra_after.keys())
   if has_targets:
+    # linear indices of all border targets in one go (the common case: a label with border targets and no extra ones)
+    bt_lin = {}
+    if border_targets:
+      keys = list(border_targets.keys())
+      arrs = [border_targets[k] for k in keys]
+      allp = np.concatenate(arrs).astype(np.int64).reshape(-1, 3)
+      alll = (allp[:, 0] + sx * (allp[:, 1] + sy * allp[:, 2])).tolist()
+      o = 0
+      for k, a in zip(keys, arrs):
+        bt_lin[k] = alll[o:o + len(a)]
+        o += len(a)
     for i, segid in enumerate(main.tolist()):
       if segid not in has_targets:
+        continue
+      if segid in bt_lin and segid not in extra_before and segid not in extra_after:
+        l = bt_lin[segid]
+        if l:
+          roots[i] = l[-1]                                       # the last border target is the root (intake.py:484-486)
+          if len(l) > 1:
+            tb_map[i] = l[:-1]
         continue
       tb, ta, root = manual_targets(segid)
       if root is not None:
