@@ -420,25 +420,29 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
     edf_multi(d_cc, shape, anisotropy, src, 1, ws, free_space=(float(jobs.free_space[0]), int(jobs.root[0])))
   else:
     edf_labels(d_cc, shape, anisotropy, jobs.root, jobs.segid, jobs.n_fg, ws)
-  maxdaf, target_idx = field_argmax(d_cc, ws.dist, shape, n_rows)
-  lap("daf")
-
-  # ---- PDRF + work fields + target buckets (trace.py:147-148, 315-356; pyx:995-1006) ----
+  daf_best = field_argmax_launch(d_cc, ws.dist, shape, n_rows)
+  # host work that needs nothing from the sweep runs while it is in flight: M per label (a loop over numpy scalars, see
+  # compute_M_array), the tables and the buffers of the next step
   M = np.zeros(n_rows + 1, dtype=np.float32)
   inv = np.zeros(n_rows + 1, dtype=np.float32)
   active = np.zeros(n_rows + 1, dtype=np.uint8)
   M[jobs.segid] = compute_M_array(jobs.dbf_max)
-  md = maxdaf[jobs.segid].astype(np.float32)
-  with np.errstate(all="ignore"):
-    inv[jobs.segid] = np.where(md != 0, np.float32(1) / md, np.float32(0)).astype(np.float32)   # trace.py:352-354
   active[jobs.segid] = 1
-  d_M, d_inv, d_active = _dev(M), _dev(inv), _dev(active)
+  d_M, d_active = _dev(M), _dev(active)
   ntab = (n_rows + 1) * NBUCKETS
   hist = torch.empty(ntab + 1, dtype=torch.int32, device=dev)
   cursor = torch.empty(ntab + 1, dtype=torch.int32, device=dev)
   keys = torch.empty(max(n_fg_total, 1), dtype=torch.int64, device=dev)
   pdrf = torch.empty(V, dtype=torch.float32, device=dev)
   claim = torch.empty(V, dtype=torch.int64, device=dev)
+  maxdaf, target_idx = field_argmax_read(daf_best)
+  lap("daf")
+
+  # ---- PDRF + work fields + target buckets (trace.py:147-148, 315-356; pyx:995-1006) ----
+  md = maxdaf[jobs.segid].astype(np.float32)
+  with np.errstate(all="ignore"):
+    inv[jobs.segid] = np.where(md != 0, np.float32(1) / md, np.float32(0)).astype(np.float32)   # trace.py:352-354
+  d_inv = _dev(inv)
   check(L.b2t_pdrf_and_buckets(_p(d_cc), _p(d_dbf), _p(ws.dist), _p(pdrf), _p(claim), c_i64(sx), c_i64(sy),
                                c_i64(sz), c_u32(n_rows), _p(d_M), _p(d_inv), _p(d_active),
                                c_f32(params["pdrf_scale"]), c_f32(params["pdrf_exponent"]), c_int(NBUCKETS),

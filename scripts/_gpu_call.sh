@@ -1,2 +1,10 @@
-python scripts/host_prof.py > gpurun_out/host_prof.txt 2>&1; head -64 gpurun_out/host_prof.txt | cut -c1-170
-python scripts/border_prof.py 2>&1 | head -1
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/gpu_tests.log 2>&1; tail -3 gpurun_out/gpu_tests.log
+timeout 600 python bench.py --gpus 1 --steps 8 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 300 gpurun_out/bench_n1.err
+python - <<'PY'
+import json
+for f in ("gpurun_out/bench_n1.json",):
+  r=json.loads(open(f).read().strip().splitlines()[-1])
+  print(f, r["n_gpus"], round(r["ms_per_step"],2), round(r["e2e"]["ms_per_step"],2), r["parity"], r["gpu_launches"], r["roofline"]["frac"], r["cpu_baseline"]["value"]); print(r["phases_ms"]); print(r["per_step_ms"])
+PY
