@@ -297,10 +297,11 @@ def run_b200(args):
 
   # per-phase breakdowns (extra steps with synchronising laps, not part of the metric)
   tme = {}
-  skeletonize(host_view, anisotropy=AN, progress=False, in_place=True, label_subset=subset, timings=tme)
+  bshard = (rank, world, None) if world > 1 else None          # the six faces of the border targets split over the ranks, as in the timed steps
+  skeletonize(host_view, anisotropy=AN, progress=False, in_place=True, label_subset=subset, timings=tme, border_shard=bshard)
   e2e_phases = {k: round(1e3 * v, 3) for k, v in tme.items() if isinstance(v, float)}
   tm = {}
-  skeletonize(shape, device_labels=d_labels, anisotropy=AN, progress=False, label_subset=subset, timings=tm)
+  skeletonize(shape, device_labels=d_labels, anisotropy=AN, progress=False, label_subset=subset, timings=tm, border_shard=bshard)
   phases = {k: round(1e3 * v, 3) for k, v in tm.items() if isinstance(v, float)}
   phases_per_rank = None
   if world > 1:              # what every rank spends where (its share of the labels): the limiter of the strong scaling
