@@ -414,7 +414,8 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
 
   # ---- DAF from the roots, all labels at once (trace.py:139-145) ----
   has_free = jobs.free_space > 0
-  assert not has_free.any() or n_jobs == 1, "free-space seeding is per arena"
+  if has_free.any() and n_jobs != 1:
+    raise B2TError("free-space seeding (soma mode) needs an arena of its own")
   src = _dev(jobs.root.astype(np.uint32).view(np.int32))
   if has_free.any():
     edf_multi(d_cc, shape, anisotropy, src, 1, ws, free_space=(float(jobs.free_space[0]), int(jobs.root[0])))

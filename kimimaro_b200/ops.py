@@ -34,11 +34,13 @@ def edt(d_labels, shape, anisotropy=(1.0, 1.0, 1.0), black_border=False, out=Non
   d_labels: flat device tensor of an unsigned integer dtype; shape: (sx,sy) or (sx,sy,sz).
   2-D shapes run the 2-D transform like the library (intake.py:565)."""
   ndim = len(shape)
-  assert ndim in (2, 3)
+  if ndim not in (2, 3):
+    raise ValueError(f"edt: shape must have 2 or 3 extents, got {tuple(shape)}")
   sx, sy = int(shape[0]), int(shape[1])
   sz = int(shape[2]) if ndim == 3 else 1
   an = [float(a) for a in anisotropy] + [1.0] * (3 - len(anisotropy))
-  assert d_labels.is_cuda and d_labels.is_contiguous() and d_labels.numel() == sx * sy * sz
+  if not (d_labels.is_cuda and d_labels.is_contiguous() and d_labels.numel() == sx * sy * sz):
+    raise ValueError("edt: d_labels must be a contiguous device tensor of sx * sy * sz elements")
   if out is None:
     out = torch.empty(sx * sy * sz, dtype=torch.float32, device=d_labels.device)
   # uint32 labels get a scratch volume so that the column passes can run as stencil + envelope (b2t_edt_ws);
