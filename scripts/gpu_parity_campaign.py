@@ -41,7 +41,15 @@ for c in range(n_cases):
   n_tubes = int(rng.integers(3, 14))
   an = ANISO[int(rng.integers(0, len(ANISO)))]
   dt = DTYPES[int(rng.integers(0, len(DTYPES)))]
-  lab = synthetic_tubes(shape, n_tubes, seed=int(rng.integers(1, 1 << 30)), anisotropy=an).astype(dt)
+  dense = c % 5 == 4          # every fifth case: a dense segmentation (Voronoi cells, no background), like real EM labels
+  if dense:
+    shape = tuple(int(v) for v in rng.integers(32, 72, size=3))
+    pts = rng.random((n_tubes + 4, 3)) * np.array(shape)
+    g = np.stack(np.meshgrid(*[np.arange(s_) for s_ in shape], indexing="ij"), axis=-1).astype(np.float32)
+    d2 = ((g[..., None, :] - pts[None, None, None, :, :].astype(np.float32)) ** 2 * np.array(an, np.float32) ** 2).sum(-1)
+    lab = np.asfortranarray((np.argmin(d2, axis=-1) + 1).astype(dt))
+  else:
+    lab = synthetic_tubes(shape, n_tubes, seed=int(rng.integers(1, 1 << 30)), anisotropy=an).astype(dt)
   kw = dict(anisotropy=an, dust_threshold=int(rng.choice([50, 200, 1000])), fix_borders=bool(rng.integers(0, 2)),
             fix_branching=bool(rng.integers(0, 4) > 0), fill_holes=bool(rng.integers(0, 5) == 0))
   if rng.integers(0, 3) == 0:
@@ -61,7 +69,7 @@ for c in range(n_cases):
   ok_default += d_ok
   ok_strict += s_ok
   n_skel += len(ref)
-  print(json.dumps({"case": c, "shape": shape, "tubes": n_tubes, "anisotropy": an, "dtype": np.dtype(dt).name,
+  print(json.dumps({"case": c, "shape": shape, "tubes": n_tubes, "dense": bool(dense), "anisotropy": an, "dtype": np.dtype(dt).name,
                     "options": {k: v for k, v in kw.items() if k != "anisotropy"}, "skeletons": len(ref),
                     "default_equals_oracle": bool(d_ok), "strict_equals_reference_heap_order": bool(s_ok)}), flush=True)
 print(json.dumps({"summary": True, "cases": n_cases, "seed": seed, "skeletons": n_skel, "default_equals_oracle": ok_default,
