@@ -151,13 +151,15 @@ int b2t_field_argmax(const uint32_t* d_cc, const float* d_dist, int64_t sx, int6
  *           CachedTargetFinder.__init__           ext/skeletontricks/skeletontricks.pyx:995-1006
  * d_dist holds DAF on entry and +inf on exit; d_pdrf / d_claim are initialised on every voxel of
  * an active label; d_keys receives (daf_bits << 32 | index) partitioned into nbuckets DAF buckets per
- * label: bucket b of label l is d_keys[d_cursor[l*nb+b] - d_hist[l*nb+b] .. d_cursor[l*nb+b]).
+ * label: bucket b of the label in table row r is d_keys[d_cursor[r*nb+b] - d_hist[r*nb+b] .. d_cursor[r*nb+b]).
+ * d_row[l] (l = 0 .. n_labels) is the table row of cc label l, 0xffffffff for a label that does not take part; the
+ * tables have n_rows rows (the traced labels, not the cc ids: dust components cost nothing).
  * d_M[l] = float32(1 / dbf_max**1.01), d_inv_maxdaf[l] = 1 / DAF[target] (0 if that is 0): computed by
  * the host with the reference's numpy expressions (trace.py:336, 353). */
 int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist, float* d_pdrf,
                          uint64_t* d_claim, int64_t sx, int64_t sy, int64_t sz,
                          uint32_t n_labels, const float* d_M, const float* d_inv_maxdaf,
-                         const uint8_t* d_active, float pdrf_scale, float pdrf_exponent, int nbuckets,
+                         const uint32_t* d_row, uint32_t n_rows, float pdrf_scale, float pdrf_exponent, int nbuckets,
                          uint32_t* d_hist, uint32_t* d_cursor, uint64_t* d_keys, void* stream);
 
 /* K4 + K5  the path loop ----------------------------------------------------------------------------------

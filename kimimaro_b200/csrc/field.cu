@@ -520,8 +520,8 @@ struct PdrfParams {
   unsigned long long* claim; // set to ~0 (valid) on participating voxels
   const float* M;            // per label: f32(1 / dbf_max^1.01)     (trace.py:336)
   const float* inv_maxdaf;   // per label: 1 / DAF[target], 0 when max_daf == 0 (trace.py:352-354)
-  const uint8_t* active;     // per label: 1 = take part
-  uint32_t* hist;            // [ (n_labels+1) * nbuckets ]
+  const uint32_t* row;       // per label: its row in the (label x bucket) tables, 0xffffffff = does not take part
+  uint32_t* hist;            // [ n_rows * nbuckets ]
   uint32_t n_labels;
   int nbuckets;
   float pdrf_scale;
@@ -559,7 +559,7 @@ __global__ void pdrf_kernel(PdrfParams p) {
     bool valid = false;
     if (i < p.V) {
       l = p.cc[i];
-      valid = l != 0 && l <= p.n_labels && p.active[l];
+      valid = l != 0 && l <= p.n_labels && p.row[l] != 0xffffffffu;
     }
     uint32_t key = 0;
     if (valid) {
@@ -578,7 +578,7 @@ __global__ void pdrf_kernel(PdrfParams p) {
       if (inv != 0.0f) P = __fadd_rn(P, __fmul_rn(daf, inv));
       p.pdrf[i] = P;
       p.claim[i] = ~0ull;
-      key = l * (uint32_t)p.nbuckets + (uint32_t)daf_bucket(daf, inv, p.nbuckets);
+      key = p.row[l] * (uint32_t)p.nbuckets + (uint32_t)daf_bucket(daf, inv, p.nbuckets);
     }
     bool leader; uint32_t rank, size; int ll;
     warp_group(valid, key, lane, leader, rank, size, ll);
@@ -590,7 +590,7 @@ struct ScatterParams {
   const uint32_t* cc;
   float* dist;               // holds DAF on entry; reset to +inf on exit for participating voxels
   const float* inv_maxdaf;
-  const uint8_t* active;
+  const uint32_t* row;
   uint32_t* cursor;          // exclusive-scanned histogram, advanced by the scatter
   unsigned long long* keys;  // (daf_bits << 32) | linear index, bucket-partitioned per label
   uint32_t n_labels;
@@ -608,14 +608,14 @@ __global__ void bucket_scatter_kernel(ScatterParams p) {
     bool valid = false;
     if (i < p.V) {
       l = p.cc[i];
-      valid = l != 0 && l <= p.n_labels && p.active[l];
+      valid = l != 0 && l <= p.n_labels && p.row[l] != 0xffffffffu;
     }
     float daf = 0.0f;
     uint32_t key = 0;
     if (valid) {
       daf = p.dist[i];
       if (__float_as_uint(daf) >= kInfBits) daf = 0.0f;
-      key = l * (uint32_t)p.nbuckets + (uint32_t)daf_bucket(daf, p.inv_maxdaf[l], p.nbuckets);
+      key = p.row[l] * (uint32_t)p.nbuckets + (uint32_t)daf_bucket(daf, p.inv_maxdaf[l], p.nbuckets);
     }
     bool leader; uint32_t rank, size; int ll;
     warp_group(valid, key, lane, leader, rank, size, ll);
@@ -868,18 +868,20 @@ B2T_EXPORT int b2t_field_argmax(const uint32_t* d_cc, const float* d_dist, int64
 B2T_EXPORT int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist, float* d_pdrf,
                                     uint64_t* d_claim, int64_t sx, int64_t sy, int64_t sz,
                                     uint32_t n_labels, const float* d_M, const float* d_inv_maxdaf,
-                                    const uint8_t* d_active, float pdrf_scale, float pdrf_exponent, int nbuckets,
+                                    const uint32_t* d_row, uint32_t n_rows, float pdrf_scale, float pdrf_exponent, int nbuckets,
                                     uint32_t* d_hist, uint32_t* d_cursor, uint64_t* d_keys, void* stream) {
   if (int rc = check_dims(sx, sy, sz)) return rc;
   B2T_REQUIRE(nbuckets >= 1 && nbuckets <= 4096, "nbuckets out of range");
   cudaStream_t st = (cudaStream_t)stream;
   const uint64_t V = (uint64_t)sx * sy * sz;
-  const uint64_t ntab = ((uint64_t)n_labels + 1) * nbuckets;
+  B2T_REQUIRE(d_row != nullptr, "b2t_pdrf_and_buckets: null row table");
+  const uint64_t ntab = (uint64_t)n_rows * nbuckets;   // rows = participating labels, not cc ids: a chunk with 10^6 dust
+                                                       // components keeps tables of its few thousand traced labels
   B2T_CUDA_TRY(cudaMemsetAsync(d_hist, 0, (ntab + 1) * sizeof(uint32_t), st));
   PdrfParams p;
   p.cc = d_cc; p.dbf = d_dbf; p.daf = d_dist; p.pdrf = d_pdrf;
   p.claim = reinterpret_cast<unsigned long long*>(d_claim);
-  p.M = d_M; p.inv_maxdaf = d_inv_maxdaf; p.active = d_active; p.hist = d_hist;
+  p.M = d_M; p.inv_maxdaf = d_inv_maxdaf; p.row = d_row; p.hist = d_hist;
   p.n_labels = n_labels; p.nbuckets = nbuckets; p.pdrf_scale = pdrf_scale; p.exponent = pdrf_exponent;
   p.n_squarings = -1;
   {
@@ -893,7 +895,7 @@ B2T_EXPORT int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, fl
   p.V = V;
   const uint64_t want = (V + 255) / 256;
   const unsigned blocks = (unsigned)(want < 148ull * 32 ? want : 148ull * 32);
-  B2T_REQUIRE(ntab < 0xffffffffull, "b2t_pdrf_and_buckets: (labels + 1) * nbuckets must stay below 2^32");
+  B2T_REQUIRE(ntab < 0xffffffffull, "b2t_pdrf_and_buckets: rows * nbuckets must stay below 2^32");
   B2T_LAUNCH_SYNC(pdrf_kernel, blocks, 256, st)(p);
   if (ntab <= (uint64_t)kScanTile) {
     B2T_LAUNCH_SYNC(exclusive_scan_kernel, 1, 1024, st)(d_hist, d_cursor, ntab);
@@ -922,7 +924,7 @@ B2T_EXPORT int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, fl
     b2t_count_launches(2);
   }
   ScatterParams s;
-  s.cc = d_cc; s.dist = d_dist; s.inv_maxdaf = d_inv_maxdaf; s.active = d_active; s.cursor = d_cursor;
+  s.cc = d_cc; s.dist = d_dist; s.inv_maxdaf = d_inv_maxdaf; s.row = d_row; s.cursor = d_cursor;
   s.keys = reinterpret_cast<unsigned long long*>(d_keys); s.n_labels = n_labels; s.nbuckets = nbuckets; s.V = V;
   B2T_LAUNCH_SYNC(bucket_scatter_kernel, blocks, 256, st)(s);
   B2T_CUDA_TRY(cudaGetLastError());

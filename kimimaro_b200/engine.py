@@ -33,7 +33,7 @@ _lib.declare("b2t_edf_labels", [c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, 
                                 c_vp, c_vp])
 _lib.declare("b2t_field_argmax", [c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp])
 _lib.declare("b2t_pdrf_and_buckets", [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_u32, c_vp, c_vp,
-                                      c_vp, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp])
+                                      c_vp, c_u32, c_f32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp])
 _lib.declare("b2t_trace_batch", [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32,
                                  c_vp, c_int, c_f32, c_f32, c_f32, c_f32, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_vp, c_u64, c_u64, c_int, c_vp, c_vp])
@@ -426,11 +426,11 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   # compute_M_array), the tables and the buffers of the next step
   M = np.zeros(n_rows + 1, dtype=np.float32)
   inv = np.zeros(n_rows + 1, dtype=np.float32)
-  active = np.zeros(n_rows + 1, dtype=np.uint8)
+  row = np.full(n_rows + 1, NONE, dtype=np.uint32)          # cc id -> row of the (label x bucket) tables: one row per job
   M[jobs.segid] = compute_M_array(jobs.dbf_max)
-  active[jobs.segid] = 1
-  d_M, d_active = _dev(M), _dev(active)
-  ntab = (n_rows + 1) * NBUCKETS
+  row[jobs.segid] = np.arange(n_jobs, dtype=np.uint32)
+  d_M, d_row = _dev(M), _dev(row.view(np.int32))
+  ntab = max(n_jobs, 1) * NBUCKETS
   hist = torch.empty(ntab + 1, dtype=torch.int32, device=dev)
   cursor = torch.empty(ntab + 1, dtype=torch.int32, device=dev)
   keys = torch.empty(max(n_fg_total, 1), dtype=torch.int64, device=dev)
@@ -445,7 +445,7 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
     inv[jobs.segid] = np.where(md != 0, np.float32(1) / md, np.float32(0)).astype(np.float32)   # trace.py:352-354
   d_inv = _dev(inv)
   check(L.b2t_pdrf_and_buckets(_p(d_cc), _p(d_dbf), _p(ws.dist), _p(pdrf), _p(claim), c_i64(sx), c_i64(sy),
-                               c_i64(sz), c_u32(n_rows), _p(d_M), _p(d_inv), _p(d_active),
+                               c_i64(sz), c_u32(n_rows), _p(d_M), _p(d_inv), _p(d_row), c_u32(max(n_jobs, 1)),
                                c_f32(params["pdrf_scale"]), c_f32(params["pdrf_exponent"]), c_int(NBUCKETS),
                                _p(hist), _p(cursor), _p(keys), stream_ptr()), "b2t_pdrf_and_buckets")
   lap("pdrf")
@@ -507,7 +507,7 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   desc["path_off"] = np.concatenate(([0], np.cumsum(caps)[:-1]))
   desc["path_cap"] = caps
   desc["max_paths"] = NONE if params["max_paths"] is None else int(params["max_paths"])
-  desc["bucket_row"] = desc["segid"]
+  desc["bucket_row"] = order                                  # row of the job in the bucket tables (row[segid] above)
   region = int(nfg.sum())
   path_off = int(caps.sum())
   if path_off >= 2 ** 32 or region >= 2 ** 32:

@@ -123,7 +123,7 @@ def test_distance_field_argmax_pdrf(emu, an, nb):
   inv = np.zeros(n + 1, np.float32)
   with np.errstate(all="ignore"):                          # trace.py:352-354: only when max DAF is not 0
     inv[1:] = np.where(vals[1:] != 0, np.float32(1) / vals[1:], np.float32(0)).astype(np.float32)
-  active = np.ones(n + 1, np.uint8)
+  row = np.concatenate(([0xFFFFFFFF], np.arange(n))).astype(np.uint32)      # table row of label l: l - 1
   V = ccf.size               # nb = 1024: the (label x bucket) table spans two tiles of the multi-block scan
   pdrf, claim = np.zeros(V, np.float32), np.zeros(V, np.uint64)
   hist, cursor = np.zeros((n + 1) * nb + 1, np.uint32), np.zeros((n + 1) * nb + 1, np.uint32)
@@ -131,7 +131,7 @@ def test_distance_field_argmax_pdrf(emu, an, nb):
   dbff = np.ascontiguousarray(all_dbf.reshape(-1, order="F"))
   params = teasar.DEFAULT_TEASAR_PARAMS
   assert emu.b2t_pdrf_and_buckets(p(ccf), p(dbff), p(dist), p(pdrf), p(claim), c_i64(sx), c_i64(sy), c_i64(sz), c_u32(n), p(M),
-                                  p(inv), p(active), c_f32(params["pdrf_scale"]), c_f32(params["pdrf_exponent"]), nb, p(hist),
+                                  p(inv), p(row), c_u32(n), c_f32(params["pdrf_scale"]), c_f32(params["pdrf_exponent"]), nb, p(hist),
                                   p(cursor), p(keys), None) == 0
   P = pdrf.reshape(cc.shape, order="F")
   for l in range(1, n + 1):
@@ -143,7 +143,7 @@ def test_distance_field_argmax_pdrf(emu, an, nb):
     ref = teasar.compute_pdrf(dbfmax[l], params["pdrf_scale"], params["pdrf_exponent"], DBF, daf, daf[tuple(ref_target[l])])
     assert np.array_equal(P[m], ref[m]), l
     # every voxel of the label sits in exactly one bucket, buckets ordered by DAF
-    rows = slice(l * nb, (l + 1) * nb)
+    rows = slice((l - 1) * nb, l * nb)
     assert hist[rows].sum() == m.sum()
     ends = cursor[rows]
     ks = [keys[e - h:e] for e, h in zip(ends, hist[rows])]
