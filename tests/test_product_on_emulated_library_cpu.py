@@ -286,3 +286,51 @@ def test_assemble_kernel_equals_general_path(product):
     assert np.array_equal(got[k][0], ref[k][0]) and np.array_equal(got[k][1], ref[k][1]), k
     # radii: the general path takes the first occurrence too
     assert np.array_equal(got[k][2], ref[k][2]), k
+
+
+def test_assemble_kernel_edge_cases(product):
+  """b2t_assemble at its edges: a group of exactly the kernel's capacity, a group whose only path has one voxel (no edge:
+  the label yields nothing), a path that returns to a voxel (cycle edge kept once), two segments of one group sharing
+  their junction voxel, and an empty buffer."""
+  import torch
+  from kimimaro_b200 import engine
+  shape = (64, 64, 64)
+  cap = int(engine.lib().b2t_assemble_group_cap())
+  kw = dict(shape=shape, anisotropy=(4.0, 4.0, 40.0))
+  assert engine.assemble(torch.zeros(0, dtype=torch.int32), torch.zeros(0), np.zeros(1, np.int64), np.zeros(0, np.int64), **kw) == {}
+  lin = lambda x, y, z: x + 64 * (y + 64 * z)
+  segs = {
+    1: [lin(5, 5, 5), -1],                                                  # single voxel: dropped
+    2: [lin(1, 1, 1), lin(2, 1, 1), lin(2, 2, 1), lin(1, 1, 1), -1],        # returns to its start
+    3: [lin(9, 9, 9), lin(10, 9, 9), -1],
+    4: [lin(10, 9, 9), lin(10, 10, 9), -1],                                 # same group as 3 below: shared junction
+  }
+  full = []                                                                 # exactly `cap` entries: a snake through the volume
+  x = y = z = 20
+  while len(full) < cap - 1:
+    full.append(lin(x, y, z))
+    x += 1
+    if x == 60:
+      x, y = 20, y + 1
+      if y == 60:
+        y, z = 20, z + 1
+  full.append(-1)
+  assert len(full) == cap
+  segs[5] = full
+  gid = {1: 11, 2: 12, 3: 13, 4: 13, 5: 15}
+  vox, lens, gids = [], [], []
+  for k in sorted(segs):
+    vox += segs[k]
+    lens.append(len(segs[k]))
+    gids.append(gid[k])
+  d_vox = torch.tensor(vox, dtype=torch.int32)
+  d_rad = torch.arange(len(vox), dtype=torch.float32)
+  seg_off = np.concatenate(([0], np.cumsum(lens)))
+  got = engine.assemble(d_vox, d_rad, seg_off, np.arange(len(lens)), group_ids=np.array(gids), **kw)
+  ref = engine._assemble_general(d_vox, d_rad, seg_off, np.arange(len(lens)), group_ids=np.array(gids), **kw)
+  assert sorted(got) == sorted(ref) == [12, 13, 15]
+  for k in ref:
+    assert all(np.array_equal(a, b) for a, b in zip(got[k], ref[k])), k
+  assert got[12][0].shape == (3, 3) and got[12][1].shape == (3, 2)          # triangle: three vertices, three edges
+  assert got[13][0].shape == (3, 3) and got[13][1].shape == (2, 2)
+  assert got[15][0].shape == (cap - 1, 3)
