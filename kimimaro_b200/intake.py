@@ -53,10 +53,14 @@ _NP_OF_TORCH = {torch.uint8: np.uint8, torch.int8: np.int8, torch.int16: np.int1
                 torch.int64: np.int64, torch.uint16: np.uint16, torch.uint32: np.uint32, torch.uint64: np.uint64}
 
 
-def format_labels(labels, in_place):
-  """kimimaro/intake.py:315-342."""
+def format_labels(labels, in_place, keep_c_order=False):
+  """kimimaro/intake.py:315-342.  keep_c_order: a C-contiguous array is returned as it is (the caller uploads it and
+  transposes on the device: a transposing host copy of a 512^3 volume takes several hundred ms)."""
   labels = np.asarray(labels)
-  if not (in_place and labels.flags["F_CONTIGUOUS"]):
+  # The reference copies unless in_place (it edits the array: fastremap.renumber, masking).  Here the host array is only
+  # ever READ -- it is uploaded, all edits happen on the device copy -- so a Fortran-contiguous array is used as it is
+  # whatever in_place says (the copy of a 512^3 uint32 volume costs 100 ms, more than the whole pass).
+  if not labels.flags["F_CONTIGUOUS"] and not (keep_c_order and labels.flags["C_CONTIGUOUS"]):
     labels = np.copy(labels, order="F")
   if labels.dtype == bool:
     labels = labels.view(np.uint8)
@@ -72,6 +76,40 @@ def format_labels(labels, in_place):
   if labels.dtype.kind not in "iu":
     raise TypeError("labels must be of integer or boolean type, got {}".format(labels.dtype))
   return labels
+
+
+_STAGE = {}          # one pinned staging buffer, kept between calls (pinning memory costs more than a pass)
+_STAGE_CHUNK = 32 << 20
+_STAGE_MIN = 64 << 20
+
+
+def _upload(flat):
+  """Host -> device copy of the label volume.  A pinned array goes down in one asynchronous copy (9.5 ms per 512 MiB).
+  An ordinary (pageable) numpy array would crawl through the driver's small bounce buffer (150 ms per 512 MiB measured):
+  it is copied chunk by chunk into a pinned staging buffer by a few threads (numpy releases the GIL for the copy) and
+  every chunk is sent on as soon as it has landed, so the host copy and the upload overlap."""
+  t = torch.from_numpy(flat)
+  nbytes = flat.nbytes
+  if nbytes < _STAGE_MIN or not torch.cuda.is_available() or t.is_pinned() or os.environ.get("B2T_STAGED_UPLOAD", "1") == "0":
+    return t.cuda(non_blocking=True)
+  from concurrent.futures import ThreadPoolExecutor
+  buf = _STAGE.get("buf")
+  if buf is None or buf.numel() < nbytes:
+    _STAGE.clear()
+    buf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    _STAGE["buf"] = buf
+    _STAGE["pool"] = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1))
+  pool = _STAGE["pool"]
+  src = flat.view(np.uint8)
+  stage = buf.numpy()
+  d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+  bounds = list(range(0, nbytes, _STAGE_CHUNK)) + [nbytes]
+  futs = [pool.submit(np.copyto, stage[a:b], src[a:b]) for a, b in zip(bounds[:-1], bounds[1:])]
+  for f, a, b in zip(futs, bounds[:-1], bounds[1:]):
+    f.result()
+    d[a:b].copy_(buf[a:b], non_blocking=True)
+  torch.cuda.current_stream().synchronize()                   # the staging buffer is reused by the next call
+  return d.view(t.dtype)
 
 
 def _merge_params(teasar_params):
@@ -446,14 +484,22 @@ def _skeletonize(
     # launcher uploaded it: torch has no kernels for the unsigned types, so the device tensor carries signed bit patterns)
     key_dtype = np.dtype(label_dtype) if label_dtype is not None else _NP_OF_TORCH.get(device_labels.dtype)
   else:
-    all_labels = format_labels(all_labels, in_place=in_place)
+    all_labels = format_labels(all_labels, in_place=in_place, keep_c_order=True)
     shape = all_labels.shape
     size = all_labels.size
     key_dtype = all_labels.dtype
     if size <= dust_threshold:
       return {}
-    flat = all_labels.reshape(-1, order="F")
-    d_labels = torch.from_numpy(flat.view(_VIEW[flat.dtype.itemsize])).cuda(non_blocking=True)
+    if all_labels.flags["F_CONTIGUOUS"]:
+      flat = all_labels.reshape(-1, order="F")
+      d_labels = _upload(flat.view(_VIEW[flat.dtype.itemsize]))
+    else:                                                      # C order: upload the bytes as they lie, transpose on the device
+      flat = all_labels.reshape(-1)
+      d_c = _upload(flat.view(_VIEW[flat.dtype.itemsize]))
+      if d_c.dtype in (torch.uint16, torch.uint32, torch.uint64):
+        d_c = d_c.view(_TVIEW[d_c.element_size()])
+      d_labels = d_c.view(shape[0], shape[1], shape[2]).permute(2, 1, 0).contiguous().view(-1)
+      del d_c
   if size <= dust_threshold:
     return {}
   if d_labels.dtype in (torch.uint16, torch.uint32, torch.uint64):

@@ -334,3 +334,22 @@ def test_assemble_kernel_edge_cases(product):
   assert got[12][0].shape == (3, 3) and got[12][1].shape == (3, 2)          # triangle: three vertices, three edges
   assert got[13][0].shape == (3, 3) and got[13][1].shape == (2, 2)
   assert got[15][0].shape == (cap - 1, 3)
+
+
+def test_c_order_input_equals_fortran_input(product):
+  """A C-contiguous volume is uploaded as it lies and transposed on the device; a Fortran-contiguous one is uploaded
+  without the reference's defensive host copy (the host array is never written).  Same skeletons either way, and the
+  caller's arrays are untouched."""
+  from tests.synth import synthetic_tubes
+  lab_f = np.asfortranarray(synthetic_tubes((44, 36, 28), 4, seed=21))
+  lab_c = np.ascontiguousarray(lab_f)
+  assert lab_c.flags["C_CONTIGUOUS"] and not lab_c.flags["F_CONTIGUOUS"]
+  keep_f, keep_c = lab_f.copy(), lab_c.copy()
+  kw = dict(anisotropy=(16, 16, 40), dust_threshold=50, progress=False)
+  a = product.skeletonize(lab_f, **kw)
+  b = product.skeletonize(lab_c, **kw)
+  assert sorted(a) == sorted(b) and len(a) > 0
+  for k in a:
+    assert np.array_equal(a[k].vertices, b[k].vertices) and np.array_equal(a[k].edges, b[k].edges)
+    assert np.array_equal(a[k].radii, b[k].radii)
+  assert np.array_equal(lab_f, keep_f) and np.array_equal(lab_c, keep_c)
