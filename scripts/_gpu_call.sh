@@ -1,25 +1,8 @@
 mkdir -p gpurun_out
-: > gpurun_out/phase_ab.jsonl
-for v in 1 0; do
-  B2T_STAGED_UPLOAD=$v B2T_X=staged$v timeout 300 python scripts/phase_times.py 512 3 >> gpurun_out/phase_ab.jsonl 2>> gpurun_out/phase_ab.err
-done
-tail -3 gpurun_out/phase_ab.err
+timeout 600 python -m pytest tests/test_multi_gpu.py -x -q -m gpu 2>&1 | tail -1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu --no-strict > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -c 300 gpurun_out/bench_n2.err
 python - <<'PY'
 import json
-for l in open("gpurun_out/phase_ab.jsonl"):
-  r = json.loads(l); ph = r["phases_ms"]
-  print(r["env"].get("B2T_X"), r["pass_ms"], ph.get("h2d"), ph.get("ccl"), r.get("identical_to_oracle_same_mode"))
+r=json.loads(open("gpurun_out/bench_n2.json").read().strip().splitlines()[-1])
+print(r["n_gpus"], round(r["ms_per_step"],2), round(r["e2e"]["ms_per_step"],2), r["parity"]["tier_a_identical_to_oracle_in_same_mode"], [round(p["total"],1) for p in r["phases_ms_per_rank"]], r["per_step_ms"])
 PY
-python - <<'PY'
-import time, numpy as np, torch, sys
-sys.path.insert(0, ".")
-import kimimaro_b200
-from bench import make_volume
-vol = make_volume(512)
-c = np.ascontiguousarray(vol)
-kimimaro_b200.skeletonize(c, anisotropy=(16,16,40), progress=False)
-t=time.perf_counter(); a = kimimaro_b200.skeletonize(c, anisotropy=(16,16,40), progress=False); torch.cuda.synchronize(); print("C-order pass ms", 1e3*(time.perf_counter()-t), len(a))
-t=time.perf_counter(); b = kimimaro_b200.skeletonize(vol, anisotropy=(16,16,40), progress=False); torch.cuda.synchronize(); print("F-order pass ms", 1e3*(time.perf_counter()-t), len(b))
-print("equal", sorted(a)==sorted(b) and all(np.array_equal(a[k].vertices,b[k].vertices) and np.array_equal(a[k].edges,b[k].edges) for k in a))
-PY
-timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -1

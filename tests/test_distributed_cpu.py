@@ -90,6 +90,9 @@ def _upload_worker(rank, world, port, q):
   whole, shape, dtype = kd.upload_sharded(vol, torch.device("cpu"))
   ok = shape == (7, 5, 3) and dtype == np.uint32 and np.array_equal(
     whole.numpy().view(np.uint32), vol.reshape(-1, order="F"))
+  # a C-ordered volume is split as it lies and transposed after the all-gather: same Fortran-ordered result
+  whole_c, shape_c, _ = kd.upload_sharded(np.ascontiguousarray(vol), torch.device("cpu"))
+  ok = ok and shape_c == (7, 5, 3) and np.array_equal(whole_c.numpy().view(np.uint32), vol.reshape(-1, order="F"))
   q.put((rank, bool(ok)))
   dist.barrier()
   dist.destroy_process_group()
