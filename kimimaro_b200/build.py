@@ -73,6 +73,7 @@ VARIANTS = {
   "t256_minb3_cap1k": ["-DB2T_TRACE_THREADS=256", "-DB2T_TRACE_MINB=3", "-DB2T_RR_SOLO_CAP=1024"],
   "batch2": ["-DB2T_RR_BATCH=2"],
   "edf_solo": ["-DB2T_EDF_SOLO=1"],   # per-label sweeps with the frontier in shared memory (slower: see field.cu)
+  "pdrf_cg": ["-DB2T_PDRF_CA=0"],     # railroad_solo gathers the PDRF from L2 only (the form before call 58)
   "minb1": ["-DB2T_TRACE_MINB=1"],    # 128 registers, one resident CTA per SM
   "t256_minb3": ["-DB2T_TRACE_THREADS=256", "-DB2T_TRACE_MINB=3"],   # 85 registers
   "t256_minb2": ["-DB2T_TRACE_THREADS=256", "-DB2T_TRACE_MINB=2"],   # 128 registers

@@ -675,6 +675,18 @@ __device__ uint32_t railroad(const Arena& A, const LabelDesc& L, uint32_t target
 #ifndef B2T_RR_SOLO
 #define B2T_RR_SOLO 1                  // solo CTAs use railroad_solo (0: the global-memory form everywhere)
 #endif
+// railroad_solo's neighbour gather of the PDRF reads through L1 (B2T_PDRF_CA=1, the default): a label's PDRF only changes
+// between two searches and only by stores of the CTA that owns the label (the rail zeroing), which write through and keep
+// that SM's L1 line current; a sector may also hold voxels of OTHER labels whose owners zero them on other SMs, but a
+// neighbour whose cc is not this label's is never used.  Measured: path loop 27.15 -> 26.19 ms, digests identical.
+#ifndef B2T_PDRF_CA
+#define B2T_PDRF_CA 1
+#endif
+#if B2T_PDRF_CA && !defined(B2T_HOST_EMU)
+#define B2T_PDRF_LD(p_) __ldca(p_)
+#else
+#define B2T_PDRF_LD(p_) __ldcg(p_)
+#endif
 constexpr uint32_t kSoloCap = B2T_RR_SOLO_CAP;
 struct RrLists {
   unsigned long long mid[2][kSoloCap];
@@ -838,7 +850,7 @@ __device__ uint32_t railroad_solo(const Arena& A, const LabelDesc& L, uint32_t t
         const bool ok = planeok && nx >= 0 && nx < A.d.sx && ny >= 0 && ny < A.d.sy && !(j == 4 && q == 1u);
         const uint32_t v = (uint32_t)(base + (int64_t)ddy * A.d.sx + ddx);
         lv[j] = ok ? __ldg(&A.cc[v]) : seg + 1u;                          // never equal to seg
-        c[j] = ok ? __ldcg(&A.pdrf[v]) : 0.0f;
+        c[j] = ok ? B2T_PDRF_LD(&A.pdrf[v]) : 0.0f;
       }
       if (__float_as_uint(du) != dq) continue;                            // a superseded pair: its voxel has (had) a closer one
       uint32_t nd[9], old[9];
