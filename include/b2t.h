@@ -173,7 +173,9 @@ int b2t_pdrf_and_buckets(const uint32_t* d_cc, const float* d_dbf, float* d_dist
  *   segid, root, n_fg, region_off, path_off, path_cap, tb_off, tb_n, ta_off, ta_n, max_paths (0xffffffff =
  *   None), soma_mode, soma_radius (float32), bucket_row, soma_done, pre_invalid, bbox_x0, bbox_x1 (x extent of the
  *   label's bounding box: the reference runs on that crop, intake.py:463-466, and STRICT reproduces the duplicate
- *   pushes of its neighbour table at the crop's x faces), two reserved words
+ *   pushes of its neighbour table at the crop's x faces), single_path (1: exactly one path, to the first manual target,
+ *   nothing invalidated -- dijkstra3d.dijkstra(PDRF, end, start) of trace.point_to_point, kimimaro/trace.py:358-390, with
+ *   fix_branching == 0, root = end and d_dist = the node-weighted field grown from end), one reserved word
  * d_scratch: b2t_trace_scratch_words(sum(n_fg)) u32; d_paths: pool of voxel indices, each path [rail ... target] terminated by
  * 0xffffffff; d_out_len / d_out_npaths / d_out_status: n_desc; d_out_stats: 4*n_desc; d_work_counter: 1 u32.
  * invalidation_mode: B2T_INVALIDATE_*; claim_window_voxels: width of a WINDOW round.  STRICT only: d_heap holds heap_words

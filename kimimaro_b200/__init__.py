@@ -15,7 +15,7 @@ __version__ = "0.1.0"
 
 def __getattr__(name):
   # lazy: `import kimimaro_b200` must work on a CPU-only box (build / CI), torch is imported on first use
-  if name in ("skeletonize", "DimensionError", "DEFAULT_TEASAR_PARAMS", "synapses_to_targets"):
+  if name in ("skeletonize", "DimensionError", "DEFAULT_TEASAR_PARAMS", "synapses_to_targets", "connect_points"):
     from . import intake
     return getattr(intake, name)
   if name in ("set_invalidation_mode", "invalidation_mode"):    # "window" (default) | "strict" (the reference's heap order)

@@ -118,7 +118,8 @@ struct LabelDesc {
   uint32_t bbox_x0, bbox_x1;  // x extent of the label's bounding box (inclusive): the reference runs on the bbox crop
                               // (intake.py:463-466), and the x faces of THAT array are where the corner entries of its
                               // neighbour table alias (strict mode reproduces the duplicate pushes)
-  uint32_t reserved0, reserved1;
+  uint32_t single_path; // 1: one path to the first manual target and nothing else (point_to_point, trace.py:358-390)
+  uint32_t reserved1;
 };
 
 struct Params {
@@ -1466,7 +1467,9 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
   uint32_t tb_n = L.tb_n, ta_n = L.ta_n;
   uint32_t max_paths = (L.max_paths == 0xffffffffu) ? valid : L.max_paths;
   uint32_t npaths = 0, used = 0;
-  if ((unsigned long long)tb_n + ta_n >= max_paths) max_paths = 0;  // trace.py:217-218: return []
+  const bool single = L.single_path == 1u;
+  if (single) max_paths = 1;
+  else if ((unsigned long long)tb_n + ta_n >= max_paths) max_paths = 0;  // trace.py:217-218: return []
   while ((valid > 0 || tb_n > 0 || ta_n > 0) && npaths < max_paths) {
     uint32_t target;
     if (tb_n > 0) target = P.targets[L.tb_off + (--tb_n)];
@@ -1513,7 +1516,7 @@ __device__ void trace_label(const Arena& A, const LabelDesc& L, const Pools& P, 
       len = k;
       team_sync<TEAM>();
     }
-    if (valid > 0) {
+    if (valid > 0 && !single) {
       uint32_t n;
       if (prm.inval_mode == B2T_INVALIDATE_STRICT) {
         n = invalidate_strict<TEAM>(A, L, P, job, pout, len, prm.scale, prm.konst, S, T);

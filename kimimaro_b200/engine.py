@@ -342,7 +342,7 @@ DESC_DTYPE = np.dtype([
   ("segid", "<u4"), ("root", "<u4"), ("n_fg", "<u4"), ("region_off", "<u4"), ("path_off", "<u4"),
   ("path_cap", "<u4"), ("tb_off", "<u4"), ("tb_n", "<u4"), ("ta_off", "<u4"), ("ta_n", "<u4"),
   ("max_paths", "<u4"), ("soma_mode", "<u4"), ("soma_radius", "<f4"), ("bucket_row", "<u4"),
-  ("soma_done", "<u4"), ("pre_invalid", "<u4"), ("bbox_x0", "<u4"), ("bbox_x1", "<u4"), ("reserved0", "<u4"),
+  ("soma_done", "<u4"), ("pre_invalid", "<u4"), ("bbox_x0", "<u4"), ("bbox_x1", "<u4"), ("single_path", "<u4"),
   ("reserved1", "<u4"),
 ])
 assert DESC_DTYPE.itemsize == 80
@@ -353,7 +353,7 @@ class Jobs:
   root == -1 means "find a root" (trace.py:128-129); tb / ta map a job index to its list of manual targets
   (linear voxel indices) and only hold the labels that have any."""
   def __init__(self, segid, n_fg, first, root, dbf_max, tb=None, ta=None, soma_mode=None, soma_radius=None,
-               free_space=None, bbox_x=None):
+               free_space=None, bbox_x=None, daf_source=None):
     self.segid = np.asarray(segid, dtype=np.int64)
     n = self.segid.size
     self.n_fg = np.asarray(n_fg, dtype=np.int64)
@@ -367,6 +367,9 @@ class Jobs:
     self.free_space = np.zeros(n, dtype=np.float32) if free_space is None else np.asarray(free_space, dtype=np.float32)
     # x extent (inclusive) of every label's bounding box: the array the reference's invalidation runs on
     self.bbox_x = None if bbox_x is None else np.asarray(bbox_x, dtype=np.int64).reshape(n, 2)
+    # source of the DAF when it is not the root (point_to_point, trace.py:358-390: DAF from `start`, path field from `end`)
+    self.daf_source = None if daf_source is None else np.asarray(daf_source, dtype=np.int64)
+    self.single_path = False    # True: every job yields exactly one path, to its first manual target, nothing is invalidated
 
   def __len__(self):
     return int(self.segid.size)
@@ -420,7 +423,7 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   if has_free.any():
     edf_multi(d_cc, shape, anisotropy, src, 1, ws, free_space=(float(jobs.free_space[0]), int(jobs.root[0])))
   else:
-    edf_labels(d_cc, shape, anisotropy, jobs.root, jobs.segid, jobs.n_fg, ws)
+    edf_labels(d_cc, shape, anisotropy, jobs.root if jobs.daf_source is None else jobs.daf_source, jobs.segid, jobs.n_fg, ws)
   daf_best = field_argmax_launch(d_cc, ws.dist, shape, n_rows)
   # host work that needs nothing from the sweep runs while it is in flight: M per label (a loop over numpy scalars, see
   # compute_M_array), the tables and the buffers of the next step
@@ -464,6 +467,7 @@ def trace_arena_start(d_cc, d_dbf, shape, anisotropy, jobs, params, n_rows, timi
   desc["n_fg"] = jobs.n_fg[order]
   desc["soma_mode"] = jobs.soma_mode[order]
   desc["soma_radius"] = jobs.soma_radius[order]
+  desc["single_path"] = 1 if getattr(jobs, "single_path", False) else 0
   if jobs.bbox_x is not None:
     desc["bbox_x0"], desc["bbox_x1"] = jobs.bbox_x[order, 0], jobs.bbox_x[order, 1]
   else:

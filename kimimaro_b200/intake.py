@@ -793,6 +793,48 @@ def skeletons_from_raw(bundle, shape, anisotropy, tm=None):
   return out
 
 
+def connect_points(labels, start, end, anisotropy=(1, 1, 1), fill_holes=False, in_place=False, pdrf_scale=100000,
+                   pdrf_exponent=4):
+  """kimimaro.connect_points (kimimaro/intake.py:268-313) -> trace.point_to_point (kimimaro/trace.py:358-390): the
+  centreline between two chosen voxels of a binary image.  EDT with a black border, DAF from `start`, PDRF, then
+  dijkstra3d.dijkstra(PDRF, end, start): here the node-weighted distance field from `end` (b2t_edf_labels with the PDRF
+  as node weights) and the walk from `start` along parents by rule T3 (the fix_branching=False machinery of the path
+  kernel, one path).  The Skeleton comes back like Skeleton.from_path: vertices in PATH order (end first), edges
+  (i, i+1), radii = DBF, physical units.  fill_holes is accepted and unused, like in the reference."""
+  an = tuple(float(a) for a in anisotropy)
+  start = tuple(int(v) for v in start)
+  end = tuple(int(v) for v in end)
+  lab = format_labels(np.asarray(labels).astype(bool), in_place=True)
+  shape = lab.shape
+  sx, sy, sz = shape
+  start, end = start + (0,) * (3 - len(start)), end + (0,) * (3 - len(end))
+  lin = lambda p: int(p[0]) + sx * (int(p[1]) + sy * int(p[2]))
+  d_labels = _upload(lab.reshape(-1, order="F"))
+  d_cc, n_cc = engine.connected_components(d_labels, shape)
+  c_start, c_end = int(d_cc[lin(start)].item()), int(d_cc[lin(end)].item())
+  if c_start == 0 or c_start != c_end:
+    raise ValueError("Cannot extract centerline from disconnected components.")
+  d_dbf = edt(d_labels, shape, an, black_border=True)
+  dbf_max = np.float32(d_dbf.max().item())                    # of the whole image, like np.max(DBF) in point_to_point
+  n_fg = int((d_cc == c_start).sum().item())
+  jobs = engine.Jobs([c_start], [n_fg], [lin(start)], [lin(end)], [dbf_max], tb={0: [lin(start)]}, daf_source=[lin(start)])
+  jobs.single_path = True
+  params = dict(engine.TRACE_DEFAULTS)
+  params.update(pdrf_scale=pdrf_scale, pdrf_exponent=pdrf_exponent, fix_branching=False)
+  vox, rad, seg_off, _, _ = engine.trace_arena(d_cc, d_dbf, shape, an, jobs, params, n_cc)
+  h_vox = vox.cpu().numpy().view(np.uint32).astype(np.int64)
+  keep = h_vox != 0xFFFFFFFF
+  path = h_vox[keep]
+  radii = rad.cpu().numpy()[keep]
+  z, r = np.divmod(path, sx * sy)
+  y, x = np.divmod(r, sx)
+  skel = Skeleton.from_path(np.stack([x, y, z], axis=1))      # trace.py:386: vertices in path order, edges (i, i+1)
+  skel.radii = radii.astype(np.float32)                       # trace.py:388-389: DBF at the vertices
+  skel.vertices *= np.array(an, dtype=np.float32)             # intake.py:310-311
+  skel.space = "physical"
+  return skel
+
+
 @functools.wraps(_skeletonize)
 def skeletonize(*args, **kwargs):
   # A full (generation 2) pass of CPython's cyclic collector walks every tracked object of the process

@@ -645,6 +645,40 @@ def fill_all_holes(cc_labels, n_cc, return_fill_count=False):
   return cc_labels
 
 
+def point_to_point(binary_img, start, end, anisotropy=(1, 1, 1), pdrf_scale=100000, pdrf_exponent=4):
+  """trace.py:358-390.  dijkstra3d.dijkstra(PDRF, end, start) = the parent walk from `start` through the node-weighted
+  field grown from `end` (parental_field + path_from_parents: the path reads source -> target, i.e. end first)."""
+  binary_img = np.asfortranarray(binary_img).view(np.uint8) if binary_img.dtype == bool else np.asfortranarray(binary_img, dtype=np.uint8)
+  DBF = orc.edt(binary_img, anisotropy=anisotropy, black_border=True)
+  dbf_max = np.max(DBF)
+  DBF[DBF == 0] = np.inf                                    # zero2inf
+  DAF, target = orc.euclidean_distance_field(binary_img, tuple(start), anisotropy=anisotropy, return_max_location=True)
+  DAF[DAF == np.inf] = 0                                    # inf2zero
+  PDRF = compute_pdrf(dbf_max, pdrf_scale, pdrf_exponent, DBF, DAF, DAF[tuple(target)])
+  parents = orc.parental_field(PDRF, tuple(end))
+  path = orc.path_from_parents(parents, tuple(start))
+  skel = skel_from_path(path)
+  verts = skel["vertices"].flatten().astype(np.uint32)
+  skel["radii"] = DBF[verts[::3], verts[1::3], verts[2::3]].astype(np.float32)
+  return skel
+
+
+def connect_points(labels, start, end, anisotropy=(1, 1, 1), fill_holes=False, in_place=False, pdrf_scale=100000,
+                   pdrf_exponent=4):
+  """intake.py:268-313."""
+  anisotropy = np.array(anisotropy, dtype=np.float32)
+  start, end = tuple(start), tuple(end)
+  labels = format_labels(np.asarray(labels).astype(bool))
+  start, end = start + (0,) * (3 - len(start)), end + (0,) * (3 - len(end))
+  cc_labels, _ = orc.connected_components(labels.view(np.uint8))
+  if cc_labels[start] == 0 or cc_labels[start] != cc_labels[end]:
+    raise ValueError("Cannot extract centerline from disconnected components.")
+  skel = point_to_point(labels, start, end, anisotropy=tuple(float(a) for a in anisotropy), pdrf_scale=pdrf_scale,
+                        pdrf_exponent=pdrf_exponent)
+  skel["vertices"] = skel["vertices"] * anisotropy
+  return skel
+
+
 def skeletonize(all_labels, teasar_params=DEFAULT_TEASAR_PARAMS, anisotropy=(1, 1, 1), object_ids=None,
                 dust_threshold=1000, fix_branching=True, fix_borders=True,
                 extra_targets_before=(), extra_targets_after=(), invalidation_mode=None,

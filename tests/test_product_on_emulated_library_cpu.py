@@ -353,3 +353,25 @@ def test_c_order_input_equals_fortran_input(product):
     assert np.array_equal(a[k].vertices, b[k].vertices) and np.array_equal(a[k].edges, b[k].edges)
     assert np.array_equal(a[k].radii, b[k].radii)
   assert np.array_equal(lab_f, keep_f) and np.array_equal(lab_c, keep_c)
+
+
+def test_connect_points(product):
+  """kimimaro.connect_points (intake.py:268-313 -> trace.point_to_point, trace.py:358-390): the product (DAF from start,
+  PDRF, node-weighted field from end, parent walk: one path through the fix_branching=False machinery) against the
+  oracle's restatement, vertices in path order; two voxels in different components raise like the reference."""
+  from oracle import teasar
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes((48, 40, 32), 3, seed=5)
+  for an in ((16, 16, 40), (1, 1, 1)):
+    ids = [int(v) for v in np.unique(lab) if v]
+    pts = np.argwhere(lab == ids[0])
+    start, end = tuple(int(v) for v in pts[0]), tuple(int(v) for v in pts[-1])
+    got = product.connect_points(lab, start, end, anisotropy=an)
+    ref = teasar.connect_points(lab, start, end, anisotropy=an)
+    assert np.array_equal(got.vertices, ref["vertices"]) and np.array_equal(got.edges, ref["edges"])
+    np.testing.assert_allclose(got.radii, ref["radii"], rtol=1e-4)
+    assert got.space == "physical" and got.vertices.shape[0] >= 2
+    assert np.array_equal(got.vertices[0], np.array(end, np.float32) * np.array(an, np.float32))    # the path starts at `end`
+    assert np.array_equal(got.vertices[-1], np.array(start, np.float32) * np.array(an, np.float32))
+  with pytest.raises(ValueError):
+    product.connect_points(lab, tuple(int(v) for v in np.argwhere(lab == 0)[0]), end)

@@ -123,3 +123,24 @@ def test_parallel_argument_is_accepted(gpu):
   skels = kimimaro.skeletonize(labels, teasar_params=tp, anisotropy=(1, 1, 1), dust_threshold=1000, progress=False,
                                parallel=2)
   assert len(skels) == 4
+
+
+def test_connect_points(gpu):
+  """kimimaro.connect_points (intake.py:268-313, trace.py:358-390) on the CUDA path against the oracle's restatement:
+  vertices in path order (end first), radii, both anisotropies; disconnected end points raise."""
+  import kimimaro_b200
+  from oracle import teasar
+  from tests.synth import synthetic_tubes
+  lab = synthetic_tubes((96, 80, 64), 4, seed=9)
+  ids = [int(v) for v in np.unique(lab) if v]
+  for an in ((16, 16, 40), (1, 1, 1), (4, 4, 40)):
+    for seg in ids[:2]:
+      pts = np.argwhere(lab == seg)
+      start, end = tuple(int(v) for v in pts[0]), tuple(int(v) for v in pts[-1])
+      got = kimimaro_b200.connect_points(lab == seg, start, end, anisotropy=an)
+      ref = teasar.connect_points(lab == seg, start, end, anisotropy=an)
+      assert np.array_equal(got.vertices, ref["vertices"]) and np.array_equal(got.edges, ref["edges"])
+      np.testing.assert_allclose(got.radii, ref["radii"], rtol=1e-4)
+  with pytest.raises(ValueError):                             # a background voxel belongs to no component
+    kimimaro_b200.connect_points(lab, tuple(int(v) for v in np.argwhere(lab == 0)[0]),
+                                 tuple(int(v) for v in np.argwhere(lab == ids[0])[0]))
