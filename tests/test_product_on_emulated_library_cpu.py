@@ -173,6 +173,14 @@ def test_more_of_the_api(product):
   tp = dict(product.DEFAULT_TEASAR_PARAMS, soma_detection_threshold=100, soma_acceptance_threshold=180)
   kw = dict(anisotropy=(16, 16, 40), dust_threshold=100, teasar_params=tp)
   _compare(product.skeletonize(ball, progress=False, **kw), teasar.skeletonize(ball, **kw))
+  # ... the default soma ball (2 * DBF + 300 nm) swallows this whole label; with a small one paths remain (root at the soma
+  # centre, cull of path points inside the soma radius), and with acceptance out of reach the private arena traces it as an
+  # ordinary label
+  for extra in (dict(soma_invalidation_scale=0.5, soma_invalidation_const=0), dict(soma_acceptance_threshold=1e9)):
+    kw2 = dict(kw, teasar_params=dict(tp, **extra))
+    ref = teasar.skeletonize(ball, **kw2)
+    assert 3 in ref and ref[3]["vertices"].shape[0] > 10
+    _compare(product.skeletonize(ball, progress=False, **kw2), ref)
   tubes = synthetic_tubes((56, 48, 32), 5, seed=4)
   ids = [int(v) for v in np.unique(tubes) if v][:3]
   pt = tuple(int(v) for v in np.argwhere(tubes == ids[0])[7])
@@ -189,7 +197,24 @@ def test_more_of_the_api(product):
 
 
 # ---- N > 1: labels sharded over two ranks (gloo), one gather of packed skeleton buffers to rank 0 ----
-def _sharded_worker(rank, world, port, lib_path, q):
+def _soma_and_tubes():
+  """a soma (detected and accepted with the thresholds below: private arena) next to two ordinary tubes"""
+  from tests.synth import synthetic_tubes
+  vol = np.zeros((76, 44, 30), np.uint32, order="F")
+  x, y, z = np.ogrid[:44, :44, :30]
+  ball = np.zeros((44, 44, 30), np.uint32)
+  ball[(x - 22) ** 2 + (y - 22) ** 2 + ((z - 15) * 2.5) ** 2 <= 15 ** 2] = 3
+  ball[20:24, 20:24, :] = 3
+  ball[21:23, 21:23, 14:16] = 0
+  vol[:44] = ball
+  tubes = synthetic_tubes((30, 44, 30), 2, seed=8)
+  vol[46:] = np.where(tubes != 0, tubes + 10, 0)
+  # accepted as a soma, with a small one-off ball so that paths remain (the default 2 * DBF + 300 nm swallows the whole label)
+  tp = dict(soma_detection_threshold=100, soma_acceptance_threshold=180, soma_invalidation_scale=0.5, soma_invalidation_const=0)
+  return vol, tp
+
+
+def _sharded_worker(rank, world, port, lib_path, q, with_soma=False):
   os.environ["MASTER_ADDR"] = "127.0.0.1"
   os.environ["MASTER_PORT"] = str(port)
   import torch
@@ -199,11 +224,15 @@ def _sharded_worker(rank, world, port, lib_path, q):
   from tests.synth import synthetic_tubes
   dist.init_process_group("gloo", rank=rank, world_size=world)
   labels = synthetic_tubes((56, 48, 32), 6, seed=12)
+  extra = {}
+  if with_soma:
+    labels, tp = _soma_and_tubes()
+    extra["teasar_params"] = dict(product.DEFAULT_TEASAR_PARAMS, **tp)
   # skeletonize_sharded (kimimaro_b200/distributed.py) as it runs on GPUs, on CPU tensors: every rank uploads its piece of
   # the volume, all-gather, LPT share of the components, ONE gather of the raw path buffers, one assembly on rank 0
   tm = {}
   out = kd.skeletonize_sharded(labels, device=torch.device("cpu"), anisotropy=(16, 16, 40), dust_threshold=100,
-                               progress=False, timings=tm)
+                               progress=False, timings=tm, **extra)
   if rank == 0:
     q.put(({k: (v.vertices.copy(), v.edges.copy(), v.radii.copy()) for k, v in out.items()}, tm["n_traced"]))
   else:
@@ -375,3 +404,29 @@ def test_connect_points(product):
     assert np.array_equal(got.vertices[-1], np.array(start, np.float32) * np.array(an, np.float32))
   with pytest.raises(ValueError):
     product.connect_points(lab, tuple(int(v) for v in np.argwhere(lab == 0)[0]), end)
+
+
+def test_sharded_with_a_private_arena_gloo():
+  """Two gloo ranks, one of which traces the soma label in its private arena: the raw path buffers of both (the private
+  flag travels with the segments) are assembled on rank 0 in one pass and equal the oracle's skeletons."""
+  import torch.multiprocessing as mp
+  from oracle import teasar
+  from tests.test_distributed_cpu import _free_port
+  lib_path = _build()
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, lib_path, q, True)) for r in range(2)]
+  for p in procs:
+    p.start()
+  out, _ = q.get(timeout=600)
+  for p in procs:
+    p.join(timeout=600)
+    assert p.exitcode == 0
+  vol, tp = _soma_and_tubes()
+  ref = teasar.skeletonize(vol, anisotropy=(16, 16, 40), dust_threshold=100,
+                           teasar_params=dict(teasar.DEFAULT_TEASAR_PARAMS, **tp))
+  assert sorted(out) == sorted(ref) and 3 in ref and len(ref) >= 2
+  for k in ref:
+    assert np.array_equal(out[k][0], ref[k]["vertices"]) and np.array_equal(out[k][1], ref[k]["edges"]), k
+    np.testing.assert_allclose(out[k][2], ref[k]["radii"], rtol=1e-4)
