@@ -1,15 +1,15 @@
 // Phase B of the TEASAR trace: the per-label path loop of kimimaro/trace.py:196-267 as ONE
 // device-resident kernel (sm_100a).  One CTA owns one label for the whole loop -- no host round
-// trip per path -- and CTAs pull labels (largest first) from a device work counter, so ~1000
-// labels are in flight on the 148 SMs at any time.
+// trip per path -- and CTAs pull labels (largest first) from a device work counter: two 512-thread
+// CTAs per SM, 296 labels in flight on the 148 SMs (the few labels above 100 k voxels get a cluster).
 //
 //   per path:  target   manual_targets_before (LIFO) | CachedTargetFinder | manual_targets_after
 //                       (trace.py:225-230; pyx:1008-1045).  The finder is a block arg-max over the
 //                       current DAF bucket (keys built by field.cu), ties by largest index (rule T5).
-//              road     dijkstra3d.railroad(PDRF, target) (trace.py:240-242): threshold-batched
-//                       label-correcting sweep from the target, warp per frontier voxel / lane per
-//                       neighbour, atomicMin on float bits, stops once every voxel at least as
-//                       close as the best rail-adjacent voxel is final; parents by rule T3.
+//              road     dijkstra3d.railroad(PDRF, target) (trace.py:240-242): delta-stepping over
+//                       (distance, voxel) pairs with lazy deletion from the target (near lists in shared
+//                       memory for a solo CTA), atomicMin on float bits, stops once every voxel at least
+//                       as close as the best rail-adjacent voxel is final; parents by rule T3.
 //              cull     soma only (trace.py:246-251), float64 with the reference's uint32 wrap.
 //              erase    roll_invalidation_ball_inside_component (pyx:373-418 ->
 //                       dijkstra_invalidation.hpp:239-332), three claim orders (b2t_set_invalidation_mode):
