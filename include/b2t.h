@@ -92,6 +92,9 @@ int b2t_edt_config_roles(int enable, int stencil_v2, float predict_scale);
  * registers (the stack of a blob lives in local memory; its walk was one L2 round trip per row), 1 = the original loop.
  * pop_ahead = 1 keeps the entry below the top of the stack in registers during the build (a pop then needs no load before
  * the next intersection).  Same result. */
+/* x pass of b2t_edt_ws: 1 = TMA-staged tiles (cp.async.bulk.tensor loads / stores of 256 x 8 boxes; rows of 256 or 512
+ * labels), 0 = the register-only kernel; same bits.  Returns the number of TMA x-pass launches so far (tma < 0: query). */
+long long b2t_edt_config_xpass(int tma);
 int b2t_edt_config_envelope(int query_prefetch, int pop_ahead);
 
 

@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "edt_fh3.cuh"
+#include "edt_xtma.cuh"
 
 namespace {
 
@@ -823,12 +824,12 @@ edt_pass_col_fh3_kernel(const T* __restrict__ labels, float* __restrict__ f, int
 // Kernel selection (experiments and A/B timing; results are identical whatever is chosen).  Initialised from the
 // environment -- B2T_EDT_ALGO: 3 = shared-memory-ring F-H (default), 2 = local-memory F-H, w = windowed search;
 // B2T_FH3 = "C,MINB,R,B": one of the compiled instantiations -- and changeable at run time with b2t_edt_config().
-struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hwr, hpf, hminb; int ec, eminb, er, eb; int roles, sopt; float pscale; int eqp, epp; };
+struct EdtCfg { int algo, c, minb, r, b; int hybrid, hwy, hwz, hwr, hpf, hminb; int ec, eminb, er, eb; int roles, sopt; float pscale; int eqp, epp; int xtma; };
 static EdtCfg& edt_cfg() {
   static EdtCfg cfg = []() {
     // hwy = 0: tap radii chosen from the anisotropy; stencil_column_v2 on; envelope write-out with four entries of lookahead
     // (round 2, call 49: bit-identical on all seven inputs of scripts/k1_shot.py, 2.388 -> 2.324 ms on synthetic-512)
-    EdtCfg c{3, 16, 6, 32, 4, 1, 0, 0, 4, 11, 8, 32, 4, 32, 8, 0, 1, 1.0f, 4, 0};
+    EdtCfg c{3, 16, 6, 32, 4, 1, 0, 0, 4, 11, 8, 32, 4, 32, 8, 0, 1, 1.0f, 4, 0, 0};
     const char* a = getenv("B2T_EDT_ALGO");
     if (a) c.algo = (a[0] == 'w') ? 1 : (a[0] == '2' ? 2 : 3);
     const char* e = getenv("B2T_FH3");
@@ -841,6 +842,8 @@ static EdtCfg& edt_cfg() {
     if (q) c.eqp = (atoi(q) == 4) ? 4 : 1;
     const char* pp = getenv("B2T_EDT_PP");      // "1": the envelope kernel's build keeps the entry below the top in registers
     if (pp) c.epp = atoi(pp) ? 1 : 0;
+    const char* xt = getenv("B2T_EDT_XTMA");    // "1": the x pass stages its tiles with TMA (edt_xtma.cuh)
+    if (xt) c.xtma = atoi(xt) ? 1 : 0;
     const char* o = getenv("B2T_EDT_STENCIL");  // "1": the first stencil body; "2": stencil_column_v2 (default)
     if (o) c.sopt = (atoi(o) == 1) ? 0 : 1;
     return c;
@@ -1192,7 +1195,9 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
   {
     const int64_t nrows = sy * sz;
     const unsigned blocks = (unsigned)((nrows + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    if (sx <= 128) edt_pass_x_v2_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
+    // x pass with TMA-staged tiles (edt_xtma.cuh) when asked for and the row length is one or two boxes; else the v2 kernel
+    if (c.xtma && xtma::launch(labels, a, sx, nrows, wx, black_border, st)) { /* launched */ }
+    else if (sx <= 128) edt_pass_x_v2_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
     else if (sx <= 256) edt_pass_x_v2_kernel<8><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
     else if (sx <= 512) edt_pass_x_v2_kernel<16><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
     else edt_pass_x_v2_kernel<32><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
@@ -1204,6 +1209,13 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
   B2T_CUDA_TRY(cudaGetLastError());
   b2t_count_launches(ndim == 3 ? 5 : 3);
   return B2T_OK;
+}
+
+// x pass of b2t_edt_ws: 1 = TMA-staged tiles (edt_xtma.cuh; rows of 256 or 512 labels), 0 = the register-only v2 kernel.
+// Returns the number of TMA x-pass launches so far (tma < 0: query only).
+B2T_EXPORT long long b2t_edt_config_xpass(int tma) {
+  if (tma >= 0) edt_cfg().xtma = tma ? 1 : 0;
+  return (long long)xtma::launches();
 }
 
 B2T_EXPORT int b2t_edt_config_envelope(int query_prefetch, int pop_ahead) {

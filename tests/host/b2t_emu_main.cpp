@@ -23,6 +23,7 @@ EMU_EXPORT int b2t_edt_config(int, int, int, int, int) { return 0; }
 EMU_EXPORT int b2t_edt_config_hybrid(int, int, int, int, int, int) { return 0; }
 EMU_EXPORT int b2t_edt_config_roles(int, int, float) { return 0; }
 EMU_EXPORT int b2t_edt_config_envelope(int, int) { return 0; }
+EMU_EXPORT long long b2t_edt_config_xpass(int) { return 0; }
 EMU_EXPORT size_t b2t_edt_workspace_bytes(int64_t sx, int64_t sy, int64_t sz) {
   return (sx <= 0 || sy <= 0 || sz <= 0) ? 0 : (size_t)sx * sy * sz * sizeof(float) + 64;
 }

@@ -170,3 +170,29 @@ def test_hybrid_fallbacks_keep_tolerance(gpu, orc, dtype):
   for shape, an in (((96, 80, 48), (3.3, 4.7, 10.1)), ((97, 64, 40), (16, 16, 40))):
     lab = np.asfortranarray((synthetic_tubes(shape, 12, seed=6) % 200).astype(dtype))
     _run(gpu, orc, lab, an, False)
+
+
+def test_x_pass_tma_form_is_bit_identical(gpu):
+  """b2t_edt_config_xpass(1): the x pass of b2t_edt_ws stages its tiles with TMA (edt_xtma.cuh: cp.async.bulk.tensor loads
+  and stores behind an mbarrier).  Same bits as the register-only kernel on rows of 512 and of 256 labels, with and
+  without a black border, and the launch counter proves that the TMA kernel is the one that ran."""
+  import ctypes
+  import torch
+  from kimimaro_b200 import ops, _lib
+  from tests.synth import synthetic_tubes
+  L = _lib.lib()
+  L.b2t_edt_config_xpass.restype = ctypes.c_longlong
+  L.b2t_edt_config_xpass.argtypes = [ctypes.c_int]
+  try:
+    for shape, an, bb in (((512, 96, 40), (16, 16, 40), False), ((256, 64, 48), (4, 4, 40), True), ((512, 33, 7), (1, 1, 1), False)):
+      lab = synthetic_tubes(shape, 12, seed=5).astype(np.uint32)
+      d = ops.to_device_f(lab)
+      L.b2t_edt_config_xpass(0)
+      a = ops.edt(d, shape, an, bb).clone()
+      before = L.b2t_edt_config_xpass(1)
+      b = ops.edt(d, shape, an, bb).clone()
+      torch.cuda.synchronize()
+      assert L.b2t_edt_config_xpass(-1) == before + 1, "the TMA x pass did not launch"
+      assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+  finally:
+    L.b2t_edt_config_xpass(0)
