@@ -843,7 +843,7 @@ static EdtCfg& edt_cfg() {
     const char* pp = getenv("B2T_EDT_PP");      // "1": the envelope kernel's build keeps the entry below the top in registers
     if (pp) c.epp = atoi(pp) ? 1 : 0;
     const char* xt = getenv("B2T_EDT_XTMA");    // "1": the x pass stages its tiles with TMA (edt_xtma.cuh)
-    if (xt) c.xtma = atoi(xt) ? 1 : 0;
+    if (xt) c.xtma = atoi(xt) == 2 ? 2 : (atoi(xt) ? 1 : 0);
     const char* o = getenv("B2T_EDT_STENCIL");  // "1": the first stencil body; "2": stencil_column_v2 (default)
     if (o) c.sopt = (atoi(o) == 1) ? 0 : 1;
     return c;
@@ -1196,7 +1196,7 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
     const int64_t nrows = sy * sz;
     const unsigned blocks = (unsigned)((nrows + kWarpsPerBlock - 1) / kWarpsPerBlock);
     // x pass with TMA-staged tiles (edt_xtma.cuh) when asked for and the row length is one or two boxes; else the v2 kernel
-    if (c.xtma && xtma::launch(labels, a, sx, nrows, wx, black_border, st)) { /* launched */ }
+    if (c.xtma && xtma::launch(labels, a, sx, nrows, wx, black_border, st, c.xtma)) { /* launched */ }
     else if (sx <= 128) edt_pass_x_v2_kernel<4><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
     else if (sx <= 256) edt_pass_x_v2_kernel<8><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
     else if (sx <= 512) edt_pass_x_v2_kernel<16><<<blocks, kWarpsPerBlock * 32, 0, st>>>(labels, a, (int)sx, nrows, wx, black_border);
@@ -1214,7 +1214,7 @@ B2T_EXPORT int b2t_edt_ws(const void* d_labels, int label_bytes, int64_t sx, int
 // x pass of b2t_edt_ws: 1 = TMA-staged tiles (edt_xtma.cuh; rows of 256 or 512 labels), 0 = the register-only v2 kernel.
 // Returns the number of TMA x-pass launches so far (tma < 0: query only).
 B2T_EXPORT long long b2t_edt_config_xpass(int tma) {
-  if (tma >= 0) edt_cfg().xtma = tma ? 1 : 0;
+  if (tma >= 0) edt_cfg().xtma = tma > 2 ? 1 : tma;      // 1: a tile per CTA; 2: persistent CTAs with a two-stage ring
   return (long long)xtma::launches();
 }
 

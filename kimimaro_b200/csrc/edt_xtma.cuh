@@ -48,28 +48,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                : "memory");
 }
 
-// NB = boxes per row (sx = NB * 256), SEG = labels per lane (sx = 32 * SEG)
+// one warp, one row: labels from the tile in shared memory (NB boxes of 256), results to the result tile
 template <int NB>
-__global__ void __launch_bounds__(kRows * 32) edt_pass_x_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
-                                                                     const __grid_constant__ CUtensorMap tm_out, int sx,
-                                                                     int64_t nrows, float w, int black_border) {
+__device__ __forceinline__ void row_from_tile(const uint32_t (*tin)[kRows][kBoxW], float (*tout)[kRows][kBoxW], int wrp, int lane,
+                                              int sx, float w, int black_border) {
   constexpr int SEG = NB * kBoxW / 32;
-  __shared__ __align__(128) uint32_t s_in[NB][kRows][kBoxW];
-  __shared__ __align__(128) float s_out[NB][kRows][kBoxW];
-  __shared__ __align__(8) unsigned long long bar;
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int64_t row0 = (int64_t)blockIdx.x * kRows;
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&bar, (uint32_t)(NB * kRows * kBoxW * sizeof(uint32_t)));
-#pragma unroll
-    for (int b = 0; b < NB; b++) tma_load_2d(&s_in[b][0][0], &tm_in, &bar, b * kBoxW, (int)row0);
-  }
-  mbar_wait(&bar, 0);
   const int p0 = lane * SEG;
   const int bx = p0 / kBoxW, px = p0 % kBoxW;           // a lane's 16 labels lie inside one box
-  const uint32_t* lrow = &s_in[bx][wrp][px];
+  const uint32_t* lrow = &tin[bx][wrp][px];
   uint32_t lab[SEG];
 #pragma unroll
   for (int q = 0; q < SEG / 4; q++) {
@@ -120,10 +106,31 @@ __global__ void __launch_bounds__(kRows * 32) edt_pass_x_tma_kernel(const __grid
     }
     val[j] = v;
   }
-  float* orow = &s_out[bx][wrp][px];
+  float* orow = &tout[bx][wrp][px];
 #pragma unroll
   for (int q = 0; q < SEG / 4; q++)
     *reinterpret_cast<float4*>(orow + 4 * q) = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
+}
+
+// NB = boxes per row (sx = NB * 256), SEG = labels per lane (sx = 32 * SEG)
+template <int NB>
+__global__ void __launch_bounds__(kRows * 32) edt_pass_x_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                                     const __grid_constant__ CUtensorMap tm_out, int sx,
+                                                                     int64_t nrows, float w, int black_border) {
+  __shared__ __align__(128) uint32_t s_in[NB][kRows][kBoxW];
+  __shared__ __align__(128) float s_out[NB][kRows][kBoxW];
+  __shared__ __align__(8) unsigned long long bar;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * kRows;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, (uint32_t)(NB * kRows * kBoxW * sizeof(uint32_t)));
+#pragma unroll
+    for (int b = 0; b < NB; b++) tma_load_2d(&s_in[b][0][0], &tm_in, &bar, b * kBoxW, (int)row0);
+  }
+  mbar_wait(&bar, 0);
+  row_from_tile<NB>(s_in, s_out, wrp, lane, sx, w, black_border);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the bulk store
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -132,6 +139,55 @@ __global__ void __launch_bounds__(kRows * 32) edt_pass_x_tma_kernel(const __grid
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // shared memory stays alive until it has been read
   }
+}
+
+// The same pass as a PERSISTENT kernel with a two-stage ring: while the warps work on tile i out of stage i & 1, the
+// loads of tile i + 1 are in flight into the other stage and the store of tile i - 1 drains; two block barriers per tile.
+template <int NB>
+__global__ void __launch_bounds__(kRows * 32) edt_pass_x_tma2_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                                      const __grid_constant__ CUtensorMap tm_out, int sx,
+                                                                      int64_t nrows, float w, int black_border) {
+  extern __shared__ __align__(128) unsigned char xtma_smem[];
+  typedef uint32_t TileIn[NB][kRows][kBoxW];
+  typedef float TileOut[NB][kRows][kBoxW];
+  TileIn* s_in = reinterpret_cast<TileIn*>(xtma_smem);                              // [2]
+  TileOut* s_out = reinterpret_cast<TileOut*>(xtma_smem + 2 * sizeof(TileIn));      // [2]
+  __shared__ __align__(8) unsigned long long full[2];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int64_t ntiles = (nrows + kRows - 1) / kRows;
+  constexpr uint32_t kBytes = (uint32_t)(NB * kRows * kBoxW * sizeof(uint32_t));
+  if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+  __syncthreads();
+  int64_t t = blockIdx.x;
+  if (t >= ntiles) return;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&full[0], kBytes);
+#pragma unroll
+    for (int b = 0; b < NB; b++) tma_load_2d(&s_in[0][b][0][0], &tm_in, &full[0], b * kBoxW, (int)(t * kRows));
+  }
+  for (uint32_t it = 0; t < ntiles; it++, t += gridDim.x) {
+    const uint32_t st = it & 1u;
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");    // the store that read s_out[st] two tiles ago is done with it
+      const int64_t tn = t + gridDim.x;
+      if (tn < ntiles) {                                                // s_in[st ^ 1] was read in the last iteration: free
+        mbar_expect_tx(&full[st ^ 1u], kBytes);
+#pragma unroll
+        for (int b = 0; b < NB; b++) tma_load_2d(&s_in[st ^ 1u][b][0][0], &tm_in, &full[st ^ 1u], b * kBoxW, (int)(tn * kRows));
+      }
+    }
+    __syncthreads();
+    mbar_wait(&full[st], (it >> 1) & 1u);
+    row_from_tile<NB>(s_in[st], s_out[st], wrp, lane, sx, w, black_border);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int b = 0; b < NB; b++) tma_store_2d(&tm_out, &s_out[st][b][0][0], b * kBoxW, (int)(t * kRows));
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -164,11 +220,32 @@ inline bool make_map(CUtensorMap* m, CUtensorMapDataType dt, const void* base, i
 inline unsigned long long& launches() { static unsigned long long n = 0; return n; }
 
 // returns false when this form does not apply (the caller launches the v2 kernel instead)
-inline bool launch(const uint32_t* labels, float* out, int64_t sx, int64_t nrows, float w, int black_border, cudaStream_t st) {
+inline bool launch(const uint32_t* labels, float* out, int64_t sx, int64_t nrows, float w, int black_border, cudaStream_t st,
+                   int form = 1) {
   if (sx != 256 && sx != 512) return false;
   CUtensorMap tin, tout;
   if (!make_map(&tin, CU_TENSOR_MAP_DATA_TYPE_UINT32, labels, sx, nrows)) return false;
   if (!make_map(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out, sx, nrows)) return false;
+  if (form == 2) {                                          // persistent, two-stage ring (dynamic shared memory)
+    const size_t smem1 = 4 * (size_t)1 * kRows * kBoxW * 4, smem2 = 4 * (size_t)2 * kRows * kBoxW * 4;
+    static bool attr = false;
+    if (!attr) {
+      if (cudaFuncSetAttribute(edt_pass_x_tma2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1) != cudaSuccess ||
+          cudaFuncSetAttribute(edt_pass_x_tma2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess)
+        return false;
+      attr = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t ntiles = (nrows + kRows - 1) / kRows;
+    const int per_sm = sx == 256 ? 6 : 3;
+    const unsigned grid = (unsigned)(ntiles < (int64_t)sms * per_sm ? ntiles : (int64_t)sms * per_sm);
+    if (sx == 256) edt_pass_x_tma2_kernel<1><<<grid, kRows * 32, smem1, st>>>(tin, tout, (int)sx, nrows, w, black_border);
+    else edt_pass_x_tma2_kernel<2><<<grid, kRows * 32, smem2, st>>>(tin, tout, (int)sx, nrows, w, black_border);
+    launches()++;
+    return true;
+  }
   const unsigned blocks = (unsigned)((nrows + kRows - 1) / kRows);
   if (sx == 256) edt_pass_x_tma_kernel<1><<<blocks, kRows * 32, 0, st>>>(tin, tout, (int)sx, nrows, w, black_border);
   else edt_pass_x_tma_kernel<2><<<blocks, kRows * 32, 0, st>>>(tin, tout, (int)sx, nrows, w, black_border);

@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-timeout 150 python -m pytest tests/test_edt_gpu.py -x -q -m gpu 2>&1 | tail -2
-timeout 120 python - <<'PY'
+timeout 100 python -m pytest tests/test_edt_gpu.py -x -q -m gpu 2>&1 | tail -2
+timeout 90 python - <<'PY'
 import ctypes, sys, json
 sys.path.insert(0, ".")
 import numpy as np, torch
@@ -12,7 +12,7 @@ d = ops.to_device_f(vol)
 out = torch.empty(vol.size, dtype=torch.float32, device="cuda")
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 res = {}
-for form in (0, 1, 0, 1):
+for form in (0, 1, 2, 0, 1, 2):
   L.b2t_edt_config_xpass(form)
   for _ in range(3): ops.edt(d, vol.shape, (16, 16, 40), False, out=out)
   ts = []

@@ -189,10 +189,11 @@ def test_x_pass_tma_form_is_bit_identical(gpu):
       d = ops.to_device_f(lab)
       L.b2t_edt_config_xpass(0)
       a = ops.edt(d, shape, an, bb).clone()
-      before = L.b2t_edt_config_xpass(1)
-      b = ops.edt(d, shape, an, bb).clone()
-      torch.cuda.synchronize()
-      assert L.b2t_edt_config_xpass(-1) == before + 1, "the TMA x pass did not launch"
-      assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+      for form in (1, 2):                                    # a tile per CTA; persistent CTAs with a two-stage ring
+        before = L.b2t_edt_config_xpass(form)
+        b = ops.edt(d, shape, an, bb).clone()
+        torch.cuda.synchronize()
+        assert L.b2t_edt_config_xpass(-1) == before + 1, "the TMA x pass did not launch"
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), form
   finally:
     L.b2t_edt_config_xpass(0)
