@@ -21,6 +21,12 @@ def __getattr__(name):
   if name in ("set_invalidation_mode", "invalidation_mode"):    # "window" (default) | "strict" (the reference's heap order)
     from . import _lib
     return getattr(_lib, name)
+  if name in ("postprocess", "join_close_components"):            # chunk-stitch post-processing (kimimaro/__init__.py:23)
+    from . import post
+    return getattr(post, name)
+  if name == "post":
+    import importlib
+    return importlib.import_module(".post", __name__)
   if name == "skeletonize_sharded":                             # one process per GPU, labels sharded over the ranks
     from . import distributed
     return distributed.skeletonize_sharded
