@@ -196,6 +196,38 @@ def test_more_of_the_api(product):
   _compare(product.skeletonize(plane, progress=False, **kw), teasar.skeletonize(plane, **kw))
 
 
+@pytest.mark.parametrize("axis", ["x", "y"])
+def test_joinability_and_postprocess(product, axis):
+  """automated_test.py:282-333 scaled down (64 x 64 x 20 instead of 256 x 256 x 20), then the chunk-stitch post-processing:
+  chunks overlapping in one z plane merge into ONE component when fix_borders=True put their end points on the same
+  face voxels; kimimaro_b200.postprocess leaves a single cycle-free tree.  Every chunk result equals the oracle's."""
+  from kimimaro_b200 import post
+  from kimimaro_b200.skeleton import Skeleton
+  from oracle import teasar
+  tp = {"const": 10, "scale": 10, "pdrf_exponent": 4, "pdrf_scale": 100000}
+  labels = np.zeros((64, 64, 20), dtype=np.uint8)
+  labels[(np.s_[8:40, :, :] if axis == "x" else np.s_[:, 8:40, :])] = 1
+
+  def halves(fix_borders):
+    kw = dict(teasar_params=tp, anisotropy=(1, 1, 1), dust_threshold=0, fix_borders=fix_borders)
+    parts = []
+    for chunk in (labels[:, :, :10], labels[:, :, 9:]):
+      res = product.skeletonize(chunk, progress=False, parallel=1, **kw)
+      _compare(res, teasar.skeletonize(chunk, **kw))
+      parts.append(res[1])
+    parts[1].vertices[:, 2] += 9
+    return parts[0].merge(parts[1])
+
+  merged_fb = halves(True)
+  assert len(merged_fb.components()) == 1
+  assert not Skeleton.equivalent(halves(False), merged_fb)
+  out = product.postprocess(merged_fb, dust_threshold=0, tick_threshold=5)
+  assert out.id == merged_fb.id
+  assert len(out.components()) == 1
+  assert len(post.find_cycle(out.edges.astype(np.int32))) == 0
+  assert out.edges.shape[0] == out.vertices.shape[0] - 1
+
+
 # ---- N > 1: labels sharded over two ranks (gloo), one gather of packed skeleton buffers to rank 0 ----
 def _soma_and_tubes():
   """a soma (detected and accepted with the thresholds below: private arena) next to two ordinary tubes"""

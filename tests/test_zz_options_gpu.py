@@ -144,3 +144,39 @@ def test_connect_points(gpu):
   with pytest.raises(ValueError):                             # a background voxel belongs to no component
     kimimaro_b200.connect_points(lab, tuple(int(v) for v in np.argwhere(lab == 0)[0]),
                                  tuple(int(v) for v in np.argwhere(lab == ids[0])[0]))
+
+
+@pytest.mark.parametrize("axis", ["x", "y"])
+def test_joinability_and_postprocess(gpu, axis):
+  """automated_test.py:282-333: two chunks that overlap in one z plane; with fix_borders=True their skeletons meet in that
+  plane and merge into one component, without it they do not give the same merged skeleton.  Then the chunk-stitch
+  post-processing (kimimaro_b200.postprocess, post.py:49-87) leaves one cycle-free component with the label's id."""
+  import kimimaro_b200 as kimimaro
+  from kimimaro_b200 import post
+  from kimimaro_b200.skeleton import Skeleton
+
+  def run(labels, fix_borders):
+    return kimimaro.skeletonize(
+      labels, teasar_params={"const": 10, "scale": 10, "pdrf_exponent": 4, "pdrf_scale": 100000}, anisotropy=(1, 1, 1),
+      object_ids=None, dust_threshold=0, progress=False, fix_branching=True, in_place=False, fix_borders=fix_borders,
+      parallel=1)
+
+  labels = np.zeros((256, 256, 20), dtype=np.uint8)
+  labels[(np.s_[32:160, :, :] if axis == "x" else np.s_[:, 32:160, :])] = 1
+
+  def halves(fix_borders):
+    a = run(labels[:, :, :10], fix_borders)[1]
+    b = run(labels[:, :, 9:], fix_borders)[1]
+    b.vertices[:, 2] += 9
+    return a.merge(b)
+
+  merged_fb = halves(True)
+  assert len(merged_fb.components()) == 1
+  merged = halves(False)
+  assert not Skeleton.equivalent(merged, merged_fb)
+
+  out = kimimaro.postprocess(merged_fb, dust_threshold=0, tick_threshold=5)
+  assert out.id == merged_fb.id
+  assert len(out.components()) == 1
+  assert len(post.find_cycle(out.edges.astype(np.int32))) == 0
+  assert out.edges.shape[0] == out.vertices.shape[0] - 1        # a tree
