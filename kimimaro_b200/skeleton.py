@@ -7,7 +7,7 @@ provides a compatible class with the fields and methods the reference's callers 
 (SURVEY 8a row T): id, vertices (float32 Nx3), edges (uint32 Mx2), radii (float32), vertex_types
 (uint8), space, transform (3x4 float32), extra_attributes; empty, from_path, simple_merge,
 consolidate, merge, clone, cable_length, components, terminals, branches, voxel_space,
-physical_space, to_swc / from_swc, equivalent.  The class is used unconditionally (HAVE_OSTEOID only records
+physical_space, to_swc / from_swc, to_precomputed / from_precomputed, equivalent.  The class is used unconditionally (HAVE_OSTEOID only records
 whether the original is importable; converting is `osteoid.Skeleton(s.vertices, s.edges, s.radii, ...)`).
 """
 import numpy as np
@@ -250,3 +250,56 @@ class Skeleton:
     edges = [[ids[p], i] for i, p in enumerate(parents) if p in ids]
     return cls(np.array(verts, np.float32).reshape(-1, 3), np.array(edges, np.uint32).reshape(-1, 2),
                np.array(radii, np.float32), np.array(types, np.uint8))
+
+  # -- Neuroglancer precomputed (what Igneous stores per label after kimimaro.skeletonize) --------
+  @property
+  def radius(self):
+    return self.radii
+
+  def to_precomputed(self):
+    """uint32 n_vertices, uint32 n_edges, float32 vertices [n][3], uint32 edges [m][2], then every entry of
+    extra_attributes in order ([n][num_components] of its data_type); little endian, C order."""
+    import struct
+    verts = np.ascontiguousarray(self.vertices, dtype="<f4")
+    edges = np.ascontiguousarray(self.edges, dtype="<u4")
+    out = [struct.pack("<II", verts.shape[0], edges.shape[0]), verts.tobytes("C"), edges.tobytes("C")]
+    for attr in self.extra_attributes:
+      arr = np.asarray(getattr(self, attr["id"]))
+      if arr.size != verts.shape[0] * int(attr["num_components"]):
+        raise ValueError("attribute {} has {} values for {} vertices".format(attr["id"], arr.size, verts.shape[0]))
+      out.append(np.ascontiguousarray(arr, dtype=np.dtype(attr["data_type"]).newbyteorder("<")).tobytes("C"))
+    return b"".join(out)
+
+  @classmethod
+  def from_precomputed(cls, data, segid=None, vertex_attributes=None):
+    """Inverse of to_precomputed; vertex_attributes defaults to radius (float32) + vertex_types (uint8) when the
+    buffer is long enough for them, and to none for a bare vertices + edges buffer."""
+    import struct
+    if len(data) < 8:
+      raise ValueError("precomputed skeleton buffer shorter than its 8-byte header")
+    n, m = struct.unpack_from("<II", data, 0)
+    off = 8
+    need = off + 12 * n + 8 * m
+    if len(data) < need:
+      raise ValueError("precomputed skeleton buffer truncated: {} bytes, {} needed".format(len(data), need))
+    verts = np.frombuffer(data, dtype="<f4", count=3 * n, offset=off).reshape(n, 3).copy()
+    off += 12 * n
+    edges = np.frombuffer(data, dtype="<u4", count=2 * m, offset=off).reshape(m, 2).copy()
+    off += 8 * m
+    if vertex_attributes is None:
+      vertex_attributes = [] if len(data) == off else [
+        {"id": "radius", "data_type": "float32", "num_components": 1},
+        {"id": "vertex_types", "data_type": "uint8", "num_components": 1},
+      ]
+    skel = cls(verts, edges, segid=segid, extra_attributes=[dict(a) for a in vertex_attributes])
+    for attr in vertex_attributes:
+      dt = np.dtype(attr["data_type"]).newbyteorder("<")
+      count = n * int(attr["num_components"])
+      if len(data) < off + count * dt.itemsize:
+        raise ValueError("precomputed skeleton buffer truncated in attribute " + attr["id"])
+      arr = np.frombuffer(data, dtype=dt, count=count, offset=off).copy()
+      off += count * dt.itemsize
+      if int(attr["num_components"]) > 1:
+        arr = arr.reshape(n, int(attr["num_components"]))
+      setattr(skel, "radii" if attr["id"] == "radius" else attr["id"], arr)
+    return skel
