@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2t.so")
 SOURCES = ["capi.cu", "edt.cu", "field.cu", "trace.cu", "preamble.cu"]
-HEADERS = ["common.cuh", "edt_fh3.cuh", os.path.join("..", "..", "include", "b2t.h")]
+HEADERS = ["common.cuh", "edt_fh3.cuh", "edt_xtma.cuh", os.path.join("..", "..", "include", "b2t.h")]
 
 NVCC_FLAGS = [
   "-gencode", "arch=compute_100a,code=sm_100a",
