@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """
-TEST INFRASTRUCTURE -- generates tests/golden/post_golden.npz by RUNNING the reference's own
+TEST INFRASTRUCTURE -- generates tests/golden/post_golden_v2.npz by RUNNING the reference's own
 /root/reference/kimimaro/post.py (unmodified, loaded from where it lies) on seeded random merged skeletons.
 
 The reference module imports four things this image does not have; they are supplied as follows and nothing else is
@@ -28,7 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 REF = os.environ.get("KIMIMARO_REFERENCE", "/root/reference")
-OUT = os.path.join(ROOT, "tests", "golden", "post_golden.npz")
+OUT = os.path.join(ROOT, "tests", "golden", "post_golden_v2.npz")
 
 
 def load_reference_post():
@@ -132,24 +132,25 @@ def random_case(rng, loops):
   return verts, edges, np.array(radii, dtype=np.float32)
 
 
-def pack(skel):
-  s = skel.consolidate()
-  return s.vertices.astype(np.float32), s.edges.astype(np.uint32), s.radii.astype(np.float32)
+NAMES = ("in", "loops", "dust", "join", "joinr", "ticks", "post")
 
 
 def main():
+  """One npz of five arrays: all vertices / radii / edges end to end, counts[case, NAMES index] = (vertices, edges) of
+  each block in that order, params[case] = (tick threshold, dust threshold, join radius, loops knob)."""
   ref, Skeleton = load_reference_post()
   rng = np.random.default_rng(0xB200_9057)
-  blob = {}
   n_cases = 60
+  V, R, E = [], [], []
+  counts = np.zeros((n_cases, len(NAMES), 2), dtype=np.int64)
+  params = np.zeros((n_cases, 4), dtype=np.float64)
   for c in range(n_cases):
     loops = 0 if c % 3 == 0 else 3
     v, e, r = random_case(rng, loops)
     tick = float(rng.choice([25.0, 60.0, 150.0, 400.0]))
     dust = float(rng.choice([0.0, 40.0, 200.0]))
     join_r = float(rng.choice([30.0, 150.0, np.inf]))
-    blob["in_v_%d" % c], blob["in_e_%d" % c], blob["in_r_%d" % c] = v, e, r
-    blob["params_%d" % c] = np.array([tick, dust, join_r, loops], dtype=np.float64)
+    params[c] = (tick, dust, join_r, loops)
 
     def fresh():
       return Skeleton(v.copy(), e.copy(), r.copy(), segid=c + 1).consolidate()
@@ -161,11 +162,16 @@ def main():
     out["joinr"] = ref.join_close_components(fresh(), restrict_by_radius=True)
     out["ticks"] = ref.remove_ticks(ref.remove_loops(fresh()), tick)      # ticks are defined on trees
     out["post"] = ref.postprocess(Skeleton(v.copy(), e.copy(), r.copy(), segid=c + 1), dust, tick)
-    for name, sk in out.items():
-      pv, pe, pr = pack(sk)
-      blob["%s_v_%d" % (name, c)], blob["%s_e_%d" % (name, c)], blob["%s_r_%d" % (name, c)] = pv, pe, pr
-  blob["n_cases"] = np.array(n_cases)
-  np.savez_compressed(OUT, **blob)
+    for k, name in enumerate(NAMES):
+      if name == "in":
+        pv, pe, pr = v, e, r
+      else:
+        s = out[name].consolidate()
+        pv, pe, pr = s.vertices.astype(np.float32), s.edges.astype(np.uint32), s.radii.astype(np.float32)
+      counts[c, k] = (pv.shape[0], pe.shape[0])
+      V.append(pv.reshape(-1, 3)), R.append(pr.reshape(-1)), E.append(pe.reshape(-1, 2))
+  np.savez_compressed(OUT, vertices=np.concatenate(V), radii=np.concatenate(R), edges=np.concatenate(E),
+                      counts=counts, params=params)
   print("wrote", OUT, os.path.getsize(OUT), "bytes,", n_cases, "cases")
 
 

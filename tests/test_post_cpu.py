@@ -309,14 +309,25 @@ def test_postprocess_stitches_two_chunks():
 
 def test_against_reference_run_goldens():
   import os
-  path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "post_golden.npz")
+  path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "post_golden_v2.npz")
   z = np.load(path)
-  n = int(z["n_cases"])
-  assert n >= 50
-  counts = {"loops": 0, "ticks": 0, "join": 0}
+  names = ("in", "loops", "dust", "join", "joinr", "ticks", "post")       # scripts/make_post_golden.py: NAMES
+  counts, params = z["counts"], z["params"]
+  n = counts.shape[0]
+  assert n >= 50 and counts.shape[1] == len(names)
+  v_end = np.cumsum(counts[:, :, 0].reshape(-1))
+  e_end = np.cumsum(counts[:, :, 1].reshape(-1))
+  assert v_end[-1] == z["vertices"].shape[0] == z["radii"].shape[0] and e_end[-1] == z["edges"].shape[0]
+
+  def block(c, name):
+    k = c * len(names) + names.index(name)
+    nv, ne = counts[c, names.index(name)]
+    return (z["vertices"][v_end[k] - nv:v_end[k]], z["edges"][e_end[k] - ne:e_end[k]], z["radii"][v_end[k] - nv:v_end[k]])
+
+  changed = {"loops": 0, "ticks": 0, "join": 0}
   for c in range(n):
-    v, e, r = z["in_v_%d" % c], z["in_e_%d" % c], z["in_r_%d" % c]
-    tick, dust, join_r, _ = z["params_%d" % c].tolist()
+    v, e, r = block(c, "in")
+    tick, dust, join_r, _ = params[c].tolist()
 
     def fresh():
       return Skeleton(v.copy(), e.copy(), r.copy(), segid=c + 1).consolidate()
@@ -331,15 +342,16 @@ def test_against_reference_run_goldens():
     }
     for name, sk in got.items():
       s = sk.consolidate()
-      assert np.array_equal(s.vertices, z["%s_v_%d" % (name, c)]), (c, name, "vertices")
-      assert np.array_equal(s.edges, z["%s_e_%d" % (name, c)]), (c, name, "edges")
-      assert np.array_equal(s.radii, z["%s_r_%d" % (name, c)]), (c, name, "radii")
+      wv, we, wr = block(c, name)
+      assert np.array_equal(s.vertices.reshape(-1, 3), wv), (c, name, "vertices")
+      assert np.array_equal(s.edges.reshape(-1, 2), we), (c, name, "edges")
+      assert np.array_equal(s.radii, wr), (c, name, "radii")
     base = fresh()
-    counts["loops"] += int(got["loops"].edges.shape[0] != base.edges.shape[0])
-    counts["ticks"] += int(got["ticks"].consolidate().edges.shape[0] != got["loops"].consolidate().edges.shape[0])
-    counts["join"] += int(got["join"].consolidate().edges.shape[0] != base.edges.shape[0])
+    changed["loops"] += int(got["loops"].edges.shape[0] != base.edges.shape[0])
+    changed["ticks"] += int(got["ticks"].consolidate().edges.shape[0] != got["loops"].consolidate().edges.shape[0])
+    changed["join"] += int(got["join"].consolidate().edges.shape[0] != base.edges.shape[0])
   # the cases must exercise the rules, not pass through them
-  assert counts["loops"] >= 15 and counts["ticks"] >= 15 and counts["join"] >= 15, counts
+  assert changed["loops"] >= 15 and changed["ticks"] >= 15 and changed["join"] >= 15, changed
 
 
 def test_precomputed_round_trip():
