@@ -367,7 +367,12 @@ def _trim_component(skeleton, threshold):
   one superedge is left: take the shortest terminal superedge; stop if it is not below the threshold; delete its vertex
   path; a branch point that falls to two superedges is dissolved and its two superedges become one, which from then on
   ranks as a terminal superedge whatever its end points are (post.py:335).
+
+  The reference scans every superedge per removal (min over a set, a list comprehension over the dict per dissolved
+  branch point); the same choices are made here from a heap with lazy deletion and a node -> superedges index.  A tie of
+  the minimum is the one case where the order of Python's set decides, and there the set is scanned like the reference.
   """
+  import heapq
   if skeleton.empty():
     return skeleton
   span = create_distance_graph(skeleton)
@@ -385,31 +390,68 @@ def _trim_component(skeleton, threshold):
     nbr[b].add(a)
 
   outer = set(e for e in span.keys() if (e[0] in tips or e[1] in tips))
+  born = {e: k for k, e in enumerate(span.keys())}          # the dict's insertion order, kept across deletions
+  clock = len(born)
+  at = defaultdict(set)                                       # node -> superedges that end there
+  for e in span:
+    at[e[0]].add(e)
+    at[e[1]].add(e)
+  heap = [(span[e], born[e], e) for e in outer]
+  heapq.heapify(heap)
+
+  def drop(e):
+    del span[e]
+    del born[e]
+    for x in e:
+      at[x].discard(e)
 
   def dissolve(v):
-    joined = [e for e in span.keys() if v in e]
+    nonlocal clock
+    joined = sorted(at[v], key=born.get)                      # = [e for e in span if v in e]
     total = 0.0
     for e in joined:
       outer.discard(e)
       total += span[e]
-      del span[e]
     ends = set(x for e in joined for x in e)
     ends.remove(v)
-    span[tuple(ends)] = total
-    outer.add(tuple(ends))
+    for e in joined:
+      drop(e)
+    fused = tuple(ends)
+    if fused not in span:
+      born[fused] = clock
+      clock += 1
+    span[fused] = total
+    for x in fused:
+      at[x].add(fused)
+    outer.add(fused)
+    heapq.heappush(heap, (total, born[fused], fused))
     arms[v] = 0
 
+  def live(item):
+    d, k, e = item
+    return e in outer and born.get(e) == k and span[e] == d
+
   while len(span) > 1 and outer:
-    tick = min(outer, key=span.get)
+    while heap and not live(heap[0]):
+      heapq.heappop(heap)
+    first = heapq.heappop(heap)
+    while heap and not live(heap[0]):
+      heapq.heappop(heap)
+    if heap and heap[0][0] == first[0]:
+      tick = min(outer, key=span.get)                         # a tie: the set's own order decides (post.py:338)
+      if tick != first[2]:
+        heapq.heappush(heap, first)
+    else:
+      tick = first[2]
     if span[tick] >= threshold:
       break
     a, b = tick
-    path = _hop_path(nbr, a, b)
+    path = _hop_path(nbr, a, b) if len(nbr[a]) <= len(nbr[b]) else _hop_path(nbr, b, a)
     for u, v in zip(path[:-1], path[1:]):
       nbr[u].discard(v)
       nbr[v].discard(u)
-    del span[tick]
     outer.remove(tick)
+    drop(tick)
     arms[a] -= 1
     arms[b] -= 1
     if arms[a] == 2:
