@@ -372,3 +372,77 @@ def test_precomputed_round_trip():
   with pytest.raises(ValueError):
     Skeleton.from_precomputed(buf[:20])
   assert Skeleton.from_precomputed(Skeleton().to_precomputed()).empty()
+
+
+def _trim_literal(skeleton, threshold):
+  """The scan form of post.py:262-362 (min over the set, a list comprehension per dissolved branch point): what
+  kimimaro_b200.post._trim_component must choose like, ties included."""
+  from collections import defaultdict
+  span = post.create_distance_graph(skeleton)
+  edges = np.asarray(skeleton.edges).reshape(-1, 2)
+  ids, deg = np.unique(edges, return_counts=True)
+  tips = set(ids[deg == 1].tolist())
+  arms = defaultdict(int)
+  for v, c in zip(ids.tolist(), deg.tolist()):
+    if c >= 3:
+      arms[v] = c
+  nbr = defaultdict(set)
+  for a, b in edges.tolist():
+    nbr[a].add(b)
+    nbr[b].add(a)
+  outer = set(e for e in span.keys() if (e[0] in tips or e[1] in tips))
+
+  def dissolve(v):
+    joined = [e for e in span.keys() if v in e]
+    total = 0.0
+    for e in joined:
+      outer.discard(e)
+      total += span[e]
+      del span[e]
+    ends = set(x for e in joined for x in e)
+    ends.remove(v)
+    span[tuple(ends)] = total
+    outer.add(tuple(ends))
+    arms[v] = 0
+
+  while len(span) > 1 and outer:
+    tick = min(outer, key=span.get)
+    if span[tick] >= threshold:
+      break
+    a, b = tick
+    path = post._hop_path(nbr, a, b)
+    for u, v in zip(path[:-1], path[1:]):
+      nbr[u].discard(v)
+      nbr[v].discard(u)
+    del span[tick]
+    outer.remove(tick)
+    arms[a] -= 1
+    arms[b] -= 1
+    if arms[a] == 2:
+      dissolve(a)
+    if arms[b] == 2:
+      dissolve(b)
+  return sorted((u, v) for u in nbr for v in nbr[u] if u < v)
+
+
+def test_trim_component_equals_the_scan_form():
+  rng = np.random.default_rng(0x71C5)
+  removed = 0
+  for case in range(40):
+    n = int(rng.integers(5, 400))
+    parent = [int(rng.integers(max(0, i - 6), i)) for i in range(1, n)]
+    pos = np.zeros((n, 3), np.float32)
+    for i in range(1, n):
+      if case % 2 == 0:                       # lattice steps: many ticks of exactly equal length
+        step = np.zeros(3)
+        step[int(rng.integers(0, 3))] = float(rng.choice([-10, 10]))
+      else:
+        step = rng.uniform(-1, 1, 3) * 10 + np.array([5.0, 0, 0])
+      pos[i] = pos[parent[i - 1]] + step
+    skel = Skeleton(pos, np.array([(p, i + 1) for i, p in enumerate(parent)], np.uint32))
+    for threshold in (15.0, 35.0, 80.0, 1e9):
+      want = _trim_literal(skel.clone(), threshold)
+      got = post._trim_component(skel.clone(), threshold)
+      assert [tuple(e) for e in got.edges.tolist()] == want, (case, threshold)
+      removed += int(len(want) < n - 1)
+  assert removed >= 80
