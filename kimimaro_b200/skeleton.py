@@ -176,10 +176,13 @@ class Skeleton:
     return np.flatnonzero(self._degrees() >= 3)
 
   def components(self):
-    """Connected components as a list of consolidated Skeletons."""
-    n = self.vertices.shape[0]
-    if n == 0:
+    """Connected components as a list of Skeletons.  Like osteoid, the skeleton is consolidated first (duplicate
+    vertices merged, isolated ones kept out of every component), so parts come in the order of their lowest
+    consolidated vertex and keep that vertex order."""
+    if self.vertices.shape[0] == 0:
       return []
+    self = self.consolidate(remove_disconnected_vertices=False)
+    n = self.vertices.shape[0]
     import scipy.sparse
     import scipy.sparse.csgraph
     e = self.edges.astype(np.int64)
